@@ -1,0 +1,146 @@
+"""In-tree native build: `python -m horovod_b200.build [--force] [--no-torch]`.
+
+Produces (next to this file, git-ignored but shipped by gpurun):
+  lib/libhvd_core.so   C++ runtime + sm_100a CUDA kernels (g++ / nvcc, no torch headers: compiles in seconds)
+  lib/_hvd_torch.so    pybind11/ATen binding linked against libhvd_core.so
+
+Role parity: the reference's CMakeLists.txt + setup.py CMake driver
+(horovod/CMakeLists.txt, cmake/build_utils.py:93-118 for the -gencode list).
+Here the only device target is sm_100a.
+"""
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+import sysconfig
+from concurrent.futures import ThreadPoolExecutor
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(ROOT, "csrc")
+OUT = os.path.join(ROOT, "lib")
+OBJ = os.path.join(ROOT, "build", "obj")
+CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+NVCC = os.path.join(CUDA_HOME, "bin", "nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+CORE_DIRS = ["common", "common/optim", "transport", "ops", "symm", "kernels"]
+
+
+def _sources():
+    cc, cu = [], []
+    for d in CORE_DIRS:
+        p = os.path.join(CSRC, d)
+        for f in sorted(os.listdir(p)):
+            if f.endswith(".cc"):
+                cc.append(os.path.join(p, f))
+            elif f.endswith(".cu"):
+                cu.append(os.path.join(p, f))
+    return cc, cu
+
+
+def _header_digest():
+    h = hashlib.sha1()
+    for base, _, files in sorted(os.walk(CSRC)):
+        for f in sorted(files):
+            if f.endswith((".h", ".cuh")):
+                with open(os.path.join(base, f), "rb") as fh:
+                    h.update(fh.read())
+    return h.hexdigest()[:12]
+
+
+def _needs(src, obj, stamp):
+    if not os.path.exists(obj) or os.path.getmtime(obj) < os.path.getmtime(src):
+        return True
+    return not os.path.exists(obj + "." + stamp)
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + "\n")
+        raise RuntimeError("build failed: " + os.path.basename(cmd[-1] if cmd else ""))
+    return r.stdout
+
+
+def _compile(src, stamp, force, verbose):
+    rel = os.path.relpath(src, CSRC).replace("/", "__")
+    obj = os.path.join(OBJ, rel + ".o")
+    if not force and not _needs(src, obj, stamp):
+        return obj
+    inc = ["-I" + os.path.join(CUDA_HOME, "include"), "-I/usr/include"]
+    if src.endswith(".cu"):
+        cmd = [NVCC] + ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + inc + ["-c", src, "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+    else:
+        cmd = ["g++", "-O2", "-g1", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-function", "-pthread"] + inc + ["-c", src, "-o", obj]
+    out = _run(cmd)
+    if verbose and out.strip():
+        print(out)
+    for f in os.listdir(OBJ):
+        if f.startswith(rel + ".o.") and f != rel + ".o." + stamp:
+            os.remove(os.path.join(OBJ, f))
+    open(obj + "." + stamp, "w").close()
+    return obj
+
+
+def build_core(force=False, verbose=False):
+    os.makedirs(OUT, exist_ok=True)
+    os.makedirs(OBJ, exist_ok=True)
+    stamp = _header_digest()
+    cc, cu = _sources()
+    with ThreadPoolExecutor(max_workers=max(2, os.cpu_count() or 4)) as ex:
+        objs = list(ex.map(lambda s: _compile(s, stamp, force, verbose), cu + cc))
+    lib = os.path.join(OUT, "libhvd_core.so")
+    newest = max(os.path.getmtime(o) for o in objs)
+    if force or not os.path.exists(lib) or os.path.getmtime(lib) < newest:
+        _run([NVCC] + ARCH + ["-shared", "-o", lib] + objs + ["-cudart", "static", "-lpthread", "-ldl", "-lrt"])
+    return lib
+
+
+def build_torch(force=False):
+    import torch
+    from torch.utils import cpp_extension
+
+    src = os.path.join(CSRC, "torch", "binding.cc")
+    lib = os.path.join(OUT, "_hvd_torch.so")
+    core = os.path.join(OUT, "libhvd_core.so")
+    stamp_file = os.path.join(OBJ, "torch_binding.stamp")
+    stamp = _header_digest() + "-" + torch.__version__
+    old = open(stamp_file).read() if os.path.exists(stamp_file) else ""
+    if (not force and os.path.exists(lib) and os.path.getmtime(lib) >= os.path.getmtime(src) and old == stamp):
+        return lib
+    inc = ["-I" + p for p in cpp_extension.include_paths()] + ["-I" + os.path.join(CUDA_HOME, "include"),
+                                                               "-I" + sysconfig.get_paths()["include"]]
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    abi = int(torch._C._GLIBCXX_USE_CXX11_ABI) if hasattr(torch._C, "_GLIBCXX_USE_CXX11_ABI") else 1
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-DTORCH_EXTENSION_NAME=_hvd_torch",
+           "-DTORCH_API_INCLUDE_EXTENSION_H", "-D_GLIBCXX_USE_CXX11_ABI=%d" % abi, "-Wno-deprecated-declarations"] + inc + [
+               src, "-o", lib, "-L" + OUT, "-lhvd_core", "-L" + tlib, "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch", "-ltorch_python",
+               "-L" + os.path.join(CUDA_HOME, "lib64"), "-lcudart",
+               "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + tlib]
+    _run(cmd)
+    with open(stamp_file, "w") as f:
+        f.write(stamp)
+    return lib
+
+
+def build_all(force=False, verbose=False, with_torch=True):
+    libs = [build_core(force, verbose)]
+    if with_torch:
+        libs.append(build_torch(force))
+    return libs
+
+
+def clean():
+    shutil.rmtree(os.path.join(ROOT, "build"), ignore_errors=True)
+    shutil.rmtree(OUT, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    if "--clean" in sys.argv:
+        clean()
+    libs = build_all(force="--force" in sys.argv, verbose="-v" in sys.argv, with_torch="--no-torch" not in sys.argv)
+    for l in libs:
+        print("built", l)

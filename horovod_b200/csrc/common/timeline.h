@@ -1,0 +1,87 @@
+// Chrome-tracing timeline (chrome://tracing / Perfetto JSON).  Each tensor is a
+// "process" row; its lifetime goes NEGOTIATING -> TOP_LEVEL -> ACTIVITY.
+// Records are pushed into a bounded ring and written by a dedicated thread so
+// the cycle thread never blocks on file IO.  Can be started/stopped at runtime
+// (hvd.start_timeline / stop_timeline).
+// Parity: horovod/common/timeline.{h,cc} (boost::lockfree spsc_queue there, an
+// own ring here); activity names follow common.h:80-114.
+#pragma once
+#include <atomic>
+#include <condition_variable>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+#include "common.h"
+#include "message.h"
+
+namespace hvd {
+
+// activity names
+#define HVD_ACT_WAIT_FOR_DATA "WAIT_FOR_DATA"
+#define HVD_ACT_QUEUE "QUEUE"
+#define HVD_ACT_MEMCPY_IN_FUSION_BUFFER "MEMCPY_IN_FUSION_BUFFER"
+#define HVD_ACT_MEMCPY_OUT_FUSION_BUFFER "MEMCPY_OUT_FUSION_BUFFER"
+#define HVD_ACT_P2P_ALLREDUCE_ONESHOT "P2P_ALLREDUCE_ONESHOT"
+#define HVD_ACT_P2P_ALLREDUCE_TWOSHOT "P2P_ALLREDUCE_TWOSHOT"
+#define HVD_ACT_P2P_ALLREDUCE_NVLS "P2P_ALLREDUCE_NVLS"
+#define HVD_ACT_P2P_ALLGATHER "P2P_ALLGATHER"
+#define HVD_ACT_P2P_BROADCAST "P2P_BROADCAST"
+#define HVD_ACT_P2P_ALLTOALL "P2P_ALLTOALL"
+#define HVD_ACT_P2P_REDUCESCATTER "P2P_REDUCESCATTER"
+#define HVD_ACT_P2P_ADASUM "P2P_ADASUM"
+#define HVD_ACT_NCCL_ALLREDUCE "NCCL_ALLREDUCE"
+#define HVD_ACT_CPU_ALLREDUCE "CPU_ALLREDUCE"
+#define HVD_ACT_CPU_ALLGATHER "CPU_ALLGATHER"
+#define HVD_ACT_CPU_BROADCAST "CPU_BROADCAST"
+#define HVD_ACT_CPU_ALLTOALL "CPU_ALLTOALL"
+#define HVD_ACT_CPU_REDUCESCATTER "CPU_REDUCESCATTER"
+#define HVD_ACT_CPU_ADASUM "CPU_ADASUM"
+
+class Timeline {
+ public:
+  ~Timeline() { Shutdown(); }
+  void Initialize(const std::string& file, int world_size);
+  void Shutdown();
+  bool Initialized() const { return initialized_.load(std::memory_order_acquire); }
+  void SetMarkCycles(bool v) { mark_cycles_ = v; }
+
+  void NegotiateStart(const std::string& name, RequestType type);
+  void NegotiateRankReady(const std::string& name, int rank);
+  void NegotiateEnd(const std::string& name);
+  void Start(const std::string& name, ResponseType type, size_t bytes = 0);
+  void ActivityStart(const std::string& name, const std::string& activity);
+  void ActivityEnd(const std::string& name);
+  void ActivityStartAll(const std::vector<std::shared_ptr<TensorTableEntry>>& es, const std::string& activity);
+  void ActivityEndAll(const std::vector<std::shared_ptr<TensorTableEntry>>& es);
+  void End(const std::string& name, const std::string& args = "");
+  void MarkCycleStart();
+
+ private:
+  enum class State { UNKNOWN, NEGOTIATING, TOP_LEVEL, ACTIVITY };
+  struct Record { char phase; int pid; std::string name; std::string args; int64_t ts_us; bool meta = false; };
+  void Push(Record r);
+  int Pid(const std::string& tensor_name);  // allocates + emits process_name metadata
+  void WriterLoop();
+  int64_t NowUs() const;
+
+  std::atomic<bool> initialized_{false};
+  bool mark_cycles_ = false;
+  std::mutex mu_;  // producers (cycle thread + finalizer threads)
+  std::unordered_map<std::string, int> pids_;
+  std::unordered_map<std::string, State> states_;
+  uint64_t start_ns_ = 0;
+  // bounded ring, single consumer
+  std::vector<Record> ring_;
+  size_t head_ = 0, tail_ = 0;  // guarded by ring_mu_
+  std::mutex ring_mu_;
+  std::condition_variable ring_cv_;
+  std::thread writer_;
+  bool stop_ = false;
+  FILE* file_ = nullptr;
+  bool first_record_ = true;
+};
+
+}  // namespace hvd

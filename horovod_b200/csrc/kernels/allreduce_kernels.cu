@@ -1,0 +1,407 @@
+// Fused allreduce / reducescatter over peer-mapped symmetric buffers (sm_100a).
+//
+// One launch per fused response:
+//   pack     every tensor -> my symmetric buffer   (prescale, cast T -> wire W)
+//   barrier  CTA b of all ranks (release/acquire flags written into peer memory)
+//   one-shot : each rank loads the same 16 B vector from all N peers over
+//              NVLink, reduces in fp32/int32/fp64 registers, applies
+//              postscale (Average), casts W -> T and stores straight into the
+//              output tensors.                                  [(N-1)·S in]
+//   two-shot : rank r reduces the chunks it owns and stores the result into
+//              every peer's buffer, barrier, every rank unpacks its own buffer
+//              into the output tensors.                         [2(N-1)/N·S]
+//   NVLS     : same as two-shot but the reduction is one
+//              multimem.ld_reduce (the NVSwitch adds) and the broadcast one
+//              multimem.st on the multicast mapping.            [~S/N in+out]
+// The chunk -> CTA mapping is the same in all phases (chunk c belongs to CTA
+// c % grid on every rank), so CTA b only ever needs to synchronise with CTA b
+// of its peers: no grid-wide barrier, no cooperative launch.
+//
+// Replaces: batched_scaled_memcpy_k + ncclAllReduce + batched_scaled_memcpy_k
+// (reference ops/cuda/cuda_kernels.cu:259-324, ops/nccl_operations.cc:231-283).
+#include "p2p_common.cuh"
+
+namespace hvd {
+namespace kern {
+
+namespace {
+
+constexpr int kRowBytes = kThreads * 16;  // one 16 B vector per thread
+
+template <typename W> struct Nvls { static constexpr bool ok = false; };
+template <> struct Nvls<float> {
+  static constexpr bool ok = true;
+  static __device__ __forceinline__ uint4 ld_reduce(const void* p) {
+    uint4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+  }
+};
+template <> struct Nvls<__nv_bfloat16> {
+  static constexpr bool ok = true;
+  static __device__ __forceinline__ uint4 ld_reduce(const void* p) {
+    uint4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+  }
+};
+template <> struct Nvls<__half> {
+  static constexpr bool ok = true;
+  static __device__ __forceinline__ uint4 ld_reduce(const void* p) {
+    uint4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.f16x2 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+  }
+};
+__device__ __forceinline__ void multimem_st(void* p, const uint4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ---- phase bodies ----------------------------------------------------------
+// Every loop handles U rows (U * 8 KiB) per trip: all loads of a trip are issued
+// before the first dependent store so each thread keeps U (x N peers) 16 B
+// requests in flight — NVLink round trips are ~2 us, HBM ~0.7 us.
+
+template <typename T, typename W, int U>
+__device__ __forceinline__ void pack_range(const TensorDesc* descs, int nd, int64_t total, char* buf, int64_t lo, int64_t hi,
+                                           typename ScaleOf<typename Traits<W>::Acc>::type scale) {
+  using A = typename Traits<W>::Acc;
+  constexpr int NW = 16 / (int)sizeof(W);
+  DescCursor cur;
+  cur.init(descs, nd, total);
+  for (int64_t o0 = lo + (int64_t)threadIdx.x * 16; o0 < hi; o0 += (int64_t)U * kRowBytes) {
+    A a[U][NW];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const int64_t o = o0 + (int64_t)j * kRowBytes;
+      if (o < hi) {
+        cur.seek(o);
+        const TensorDesc& d = cur.d[cur.i];
+        const int64_t e = (o - cur.lo) / (int64_t)sizeof(W);
+        load_elems<T, NW, A>(reinterpret_cast<const T*>(d.in) + e, d.count - e, a[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const int64_t o = o0 + (int64_t)j * kRowBytes;
+      if (o < hi) {
+#pragma unroll
+        for (int i = 0; i < NW; ++i) a[j][i] = apply_scale<A>(a[j][i], scale);
+        st_stream(buf + o, pack_vec<W, NW>(a[j]));
+      }
+    }
+  }
+}
+
+template <typename T, typename W, int U>
+__device__ __forceinline__ void unpack_range(const TensorDesc* descs, int nd, int64_t total, const char* buf, int64_t lo,
+                                             int64_t hi) {
+  using A = typename Traits<W>::Acc;
+  constexpr int NW = 16 / (int)sizeof(W);
+  DescCursor cur;
+  cur.init(descs, nd, total);
+  for (int64_t o0 = lo + (int64_t)threadIdx.x * 16; o0 < hi; o0 += (int64_t)U * kRowBytes) {
+    uint4 v[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const int64_t o = o0 + (int64_t)j * kRowBytes;
+      if (o < hi) v[j] = ld_stream(buf + o);
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const int64_t o = o0 + (int64_t)j * kRowBytes;
+      if (o < hi) {
+        cur.seek(o);
+        const TensorDesc& d = cur.d[cur.i];
+        const int64_t e = (o - cur.lo) / (int64_t)sizeof(W);
+        if (e < d.count) {
+          A a[NW];
+          unpack_vec<W, NW>(v[j], a);
+          store_elems<T, NW, A>(reinterpret_cast<T*>(d.out) + e, d.count - e, a);
+        }
+      }
+    }
+  }
+}
+
+// Issues the loads of the vector at byte offset `o` from all peers.
+template <int NR> __device__ __forceinline__ void peer_loads(const CommParams& cp, int64_t o, uint4* v) {
+#pragma unroll
+  for (int k = 0; k < NR; ++k) {
+    // start at my own buffer and rotate so that at any instant the N ranks pull from N different peers
+    int p = cp.rank + k; if (p >= cp.nranks) p -= cp.nranks;
+    if (k < cp.nranks) v[k] = ld_stream(reinterpret_cast<const char*>(cp.buf[p]) + o);
+  }
+}
+template <typename W, int NR>
+__device__ __forceinline__ void peer_combine(const CommParams& cp, const uint4* v, int op, typename Traits<W>::Acc* acc) {
+  using A = typename Traits<W>::Acc;
+  constexpr int NW = 16 / (int)sizeof(W);
+  unpack_vec<W, NW>(v[0], acc);
+#pragma unroll
+  for (int k = 1; k < NR; ++k) {
+    if (k < cp.nranks) {
+      A b[NW];
+      unpack_vec<W, NW>(v[k], b);
+#pragma unroll
+      for (int i = 0; i < NW; ++i) acc[i] = combine<A>(acc[i], b[i], op);
+    }
+  }
+}
+
+template <typename T, typename W, int NR>
+__global__ void __launch_bounds__(kThreads, 1)
+allreduce_kernel(const __grid_constant__ CommParams cp, const __grid_constant__ AllreduceArgs a, const int chunk_bytes) {
+  using A = typename Traits<W>::Acc;
+  using S = typename ScaleOf<A>::type;
+  constexpr int NW = 16 / (int)sizeof(W);
+  constexpr int U = 8 / NR;  // rows per trip in the peer phases
+  const int cta = blockIdx.x, grid = gridDim.x;
+  const TensorDesc* descs = a.descs ? a.descs : a.inline_descs;
+  const TensorDesc* odescs = a.out_descs ? a.out_descs : descs;
+  const int nout = a.out_descs ? a.nout : a.ndesc;
+  uint32_t epoch = cp.epochs[cta];
+  char* mybuf = reinterpret_cast<char*>(cp.buf[cp.rank]);
+  const int64_t total = a.total_bytes;
+  const int64_t nchunks = (total + chunk_bytes - 1) / chunk_bytes;
+  const S prescale = (S)a.prescale, postscale = (S)a.postscale;
+  bool alive = true;
+
+  // ---- pack ----
+  for (int64_t c = cta; c < nchunks; c += grid) {
+    const int64_t lo = c * chunk_bytes;
+    const int64_t hi = lo + chunk_bytes < total ? lo + chunk_bytes : total;
+    pack_range<T, W, 4>(descs, a.ndesc, total, mybuf, lo, hi, prescale);
+  }
+  if (cp.nranks > 1) alive = peer_barrier(cp, epoch, cta); else __syncthreads();
+
+  if (a.variant == kOneShot) {
+    // ---- reduce straight into the outputs ----
+    DescCursor cur;
+    cur.init(odescs, nout, total);
+    for (int64_t c = cta; c < nchunks && alive; c += grid) {
+      int64_t lo = c * chunk_bytes;
+      int64_t hi = lo + chunk_bytes < total ? lo + chunk_bytes : total;
+      if (lo < a.reduce_lo) lo = a.reduce_lo;
+      if (hi > a.reduce_hi) hi = a.reduce_hi;
+      for (int64_t o0 = lo + (int64_t)threadIdx.x * 16; o0 < hi; o0 += (int64_t)U * kRowBytes) {
+        uint4 v[U][NR];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const int64_t o = o0 + (int64_t)j * kRowBytes;
+          if (o < hi) peer_loads<NR>(cp, o, v[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const int64_t o = o0 + (int64_t)j * kRowBytes;
+          if (o < hi) {
+            A acc[NW];
+            peer_combine<W, NR>(cp, v[j], a.op, acc);
+            cur.seek(o);
+            const TensorDesc& d = cur.d[cur.i];
+            const int64_t e = (o - cur.lo) / (int64_t)sizeof(W);
+            if (e < d.count) {
+#pragma unroll
+              for (int i = 0; i < NW; ++i) acc[i] = apply_scale<A>(acc[i], postscale);
+              store_elems<T, NW, A>(reinterpret_cast<T*>(d.out) + e, d.count - e, acc);
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ---- reduce the chunks I own, publish to every peer ----
+    for (int64_t c = cta, k = 0; c < nchunks && alive; c += grid, ++k) {
+      int owner = (int)((k + cta) % cp.nranks);
+      if (owner != cp.rank) continue;
+      const int64_t lo = c * chunk_bytes;
+      const int64_t hi = lo + chunk_bytes < total ? lo + chunk_bytes : total;
+      if (a.variant == kNvls) {
+        if constexpr (Nvls<W>::ok) {
+          constexpr int UN = 4;
+          for (int64_t o0 = lo + (int64_t)threadIdx.x * 16; o0 < hi; o0 += (int64_t)UN * kRowBytes) {
+            uint4 v[UN];
+#pragma unroll
+            for (int j = 0; j < UN; ++j) {
+              const int64_t o = o0 + (int64_t)j * kRowBytes;
+              if (o < hi) v[j] = Nvls<W>::ld_reduce(reinterpret_cast<const char*>(cp.mc_buf) + o);
+            }
+#pragma unroll
+            for (int j = 0; j < UN; ++j) {
+              const int64_t o = o0 + (int64_t)j * kRowBytes;
+              if (o < hi) {
+                if (postscale != (S)1) {
+                  A acc[NW];
+                  unpack_vec<W, NW>(v[j], acc);
+#pragma unroll
+                  for (int i = 0; i < NW; ++i) acc[i] = apply_scale<A>(acc[i], postscale);
+                  v[j] = pack_vec<W, NW>(acc);
+                }
+                multimem_st(reinterpret_cast<char*>(cp.mc_buf) + o, v[j]);
+              }
+            }
+          }
+        }
+      } else {
+        for (int64_t o0 = lo + (int64_t)threadIdx.x * 16; o0 < hi; o0 += (int64_t)U * kRowBytes) {
+          uint4 v[U][NR];
+#pragma unroll
+          for (int j = 0; j < U; ++j) {
+            const int64_t o = o0 + (int64_t)j * kRowBytes;
+            if (o < hi) peer_loads<NR>(cp, o, v[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < U; ++j) {
+            const int64_t o = o0 + (int64_t)j * kRowBytes;
+            if (o < hi) {
+              A acc[NW];
+              peer_combine<W, NR>(cp, v[j], a.op, acc);
+#pragma unroll
+              for (int i = 0; i < NW; ++i) acc[i] = apply_scale<A>(acc[i], postscale);
+              const uint4 r = pack_vec<W, NW>(acc);
+#pragma unroll
+              for (int p = 0; p < NR; ++p) {
+                int q = cp.rank + p; if (q >= cp.nranks) q -= cp.nranks;
+                if (p < cp.nranks) st_stream(reinterpret_cast<char*>(cp.buf[q]) + o, r);
+              }
+            }
+          }
+        }
+      }
+    }
+    if (alive) alive = peer_barrier(cp, epoch, cta);
+    // ---- unpack my buffer ----
+    for (int64_t c = cta; c < nchunks && alive; c += grid) {
+      int64_t lo = c * chunk_bytes;
+      int64_t hi = lo + chunk_bytes < total ? lo + chunk_bytes : total;
+      if (lo < a.reduce_lo) lo = a.reduce_lo;
+      if (hi > a.reduce_hi) hi = a.reduce_hi;
+      if (lo < hi) unpack_range<T, W, 4>(odescs, nout, total, mybuf, lo, hi);
+    }
+  }
+  if (threadIdx.x == 0) cp.epochs[cta] = epoch;
+}
+
+// Stand-alone pack / unpack (NCCL baseline path): whole grid strides over rows.
+template <typename T, typename W>
+__global__ void __launch_bounds__(kThreads)
+pack_unpack_kernel(char* buffer, const TensorDesc* descs, int nd, int64_t total, double scale, int direction) {
+  using A = typename Traits<W>::Acc;
+  using S = typename ScaleOf<A>::type;
+  constexpr int NW = 16 / (int)sizeof(W);
+  DescCursor cur;
+  cur.init(descs, nd, total);
+  for (int64_t o = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 16; o < total; o += (int64_t)gridDim.x * kRowBytes) {
+    cur.seek(o);
+    const TensorDesc& d = cur.d[cur.i];
+    const int64_t e = (o - cur.lo) / (int64_t)sizeof(W);
+    A acc[NW];
+    if (direction == 0) {
+      load_elems<T, NW, A>(reinterpret_cast<const T*>(d.in) + e, d.count - e, acc);
+#pragma unroll
+      for (int i = 0; i < NW; ++i) acc[i] = apply_scale<A>(acc[i], (S)scale);
+      st_stream(buffer + o, pack_vec<W, NW>(acc));
+    } else {
+      if (e >= d.count) continue;
+      unpack_vec<W, NW>(ld_stream(buffer + o), acc);
+#pragma unroll
+      for (int i = 0; i < NW; ++i) acc[i] = apply_scale<A>(acc[i], (S)scale);
+      store_elems<T, NW, A>(reinterpret_cast<T*>(d.out) + e, d.count - e, acc);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) scale_kernel(const T* in, T* out, int64_t n, double scale) {
+  using A = typename Traits<T>::Acc;
+  using S = typename ScaleOf<A>::type;
+  constexpr int N = 16 / (int)sizeof(T);
+  for (int64_t e = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * N; e < n; e += (int64_t)gridDim.x * kThreads * N) {
+    A a[N];
+    load_elems<T, N, A>(in + e, n - e, a);
+#pragma unroll
+    for (int i = 0; i < N; ++i) a[i] = apply_scale<A>(a[i], (S)scale);
+    store_elems<T, N, A>(out + e, n - e, a);
+  }
+}
+
+template <typename T, typename W>
+cudaError_t launch_tw(const CommParams& cp, const AllreduceArgs& a, int chunk_bytes, cudaStream_t s) {
+  dim3 grid(a.ctas), block(kThreads);
+  if (cp.nranks <= 2) allreduce_kernel<T, W, 2><<<grid, block, 0, s>>>(cp, a, chunk_bytes);
+  else if (cp.nranks <= 4) allreduce_kernel<T, W, 4><<<grid, block, 0, s>>>(cp, a, chunk_bytes);
+  else allreduce_kernel<T, W, 8><<<grid, block, 0, s>>>(cp, a, chunk_bytes);
+  return cudaGetLastError();
+}
+
+template <typename T, typename W>
+cudaError_t launch_pu(char* buffer, const TensorDesc* descs, int nd, int64_t total, double scale, int dir, int ctas,
+                      cudaStream_t s) {
+  pack_unpack_kernel<T, W><<<ctas, kThreads, 0, s>>>(buffer, descs, nd, total, scale, dir);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+// dtype codes: hvd::DataType
+#define HVD_DISPATCH(dtype, wire, FN, ...)                                                         \
+  switch (dtype) {                                                                                 \
+    case 0: return FN<uint8_t, uint8_t>(__VA_ARGS__);                                               \
+    case 9: return FN<uint8_t, uint8_t>(__VA_ARGS__);                                               \
+    case 1: return FN<int8_t, int8_t>(__VA_ARGS__);                                                 \
+    case 2: case 3: return FN<int16_t, int16_t>(__VA_ARGS__);                                       \
+    case 4: return FN<int32_t, int32_t>(__VA_ARGS__);                                               \
+    case 5: return FN<int64_t, int64_t>(__VA_ARGS__);                                               \
+    case 6: return FN<__half, __half>(__VA_ARGS__);                                                 \
+    case 7:                                                                                        \
+      if (wire == 10) return FN<float, __nv_bfloat16>(__VA_ARGS__);                                 \
+      if (wire == 6) return FN<float, __half>(__VA_ARGS__);                                         \
+      return FN<float, float>(__VA_ARGS__);                                                         \
+    case 8: return FN<double, double>(__VA_ARGS__);                                                 \
+    case 10: return FN<__nv_bfloat16, __nv_bfloat16>(__VA_ARGS__);                                  \
+    default: return cudaErrorInvalidValue;                                                         \
+  }
+
+cudaError_t LaunchAllreduce(const CommParams& cp, const AllreduceArgs& args, cudaStream_t stream) {
+  if (args.ctas < 1 || args.ctas > kMaxCtas || cp.nranks < 1 || cp.nranks > kMaxPeers) return cudaErrorInvalidValue;
+  if (args.total_bytes <= 0) return cudaSuccess;
+  if (args.variant == kNvls) {
+    const int w = args.dtype == 7 ? (args.wire_dtype == 10 || args.wire_dtype == 6 ? args.wire_dtype : 7) : args.dtype;
+    if (!(w == 7 || w == 6 || w == 10) || args.op != 1 || cp.mc_buf == nullptr) return cudaErrorInvalidValue;
+  }
+  // chunk size: enough chunks that every (rank, CTA) pair owns work, bounded by [8 KiB, 32 KiB]
+  int64_t want = args.total_bytes / ((int64_t)args.ctas * cp.nranks);
+  int chunk = (int)((want / kRowBytes) * kRowBytes);
+  if (chunk < kRowBytes) chunk = kRowBytes;
+  if (chunk > kChunkBytes) chunk = kChunkBytes;
+  HVD_DISPATCH(args.dtype, args.wire_dtype, launch_tw, cp, args, chunk, stream)
+}
+
+cudaError_t LaunchPackUnpack(void* buffer, const TensorDesc* descs, int ndesc, int64_t total_bytes, int dtype,
+                             int wire_dtype, double scale, int direction, int ctas, cudaStream_t stream) {
+  if (total_bytes <= 0) return cudaSuccess;
+  HVD_DISPATCH(dtype, wire_dtype, launch_pu, (char*)buffer, descs, ndesc, total_bytes, scale, direction, ctas, stream)
+}
+
+namespace {
+template <typename T, typename W> cudaError_t launch_scale(const void* in, void* out, int64_t n, double scale, cudaStream_t s) {
+  int64_t per = (int64_t)kThreads * (16 / sizeof(T));
+  int64_t blocks = (n + per - 1) / per;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  scale_kernel<T><<<(int)blocks, kThreads, 0, s>>>((const T*)in, (T*)out, n, scale);
+  return cudaGetLastError();
+}
+}  // namespace
+
+cudaError_t LaunchScale(const void* in, void* out, int64_t count, int dtype, double scale, cudaStream_t stream) {
+  if (count <= 0) return cudaSuccess;
+  const int wire = dtype;
+  HVD_DISPATCH(dtype, wire, launch_scale, in, out, count, scale, stream)
+}
+
+}  // namespace kern
+}  // namespace hvd

@@ -1,0 +1,116 @@
+// Host-side interface of the sm_100a peer-to-peer collective kernels.
+//
+// These kernels replace the reference's three-launch GPU data path
+// (batched_scaled_memcpy_k -> ncclAllReduce -> batched_scaled_memcpy_k,
+// horovod/common/ops/cuda/cuda_kernels.cu:259-324 + ops/nccl_operations.cc:185-287)
+// with ONE launch that packs (prescale + cast) gradients into a symmetric
+// buffer, synchronises with peer GPUs through release/acquire flags in peer
+// memory, reduces by loading/storing peer buffers directly over NVLink (or
+// through the NVSwitch with multimem.ld_reduce / multimem.st), applies
+// postscale/average + cast and scatters the result to the output tensors.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace hvd {
+namespace kern {
+
+constexpr int kMaxPeers = 8;          // one NVSwitch domain of the HGX B200 box
+constexpr int kMaxCtas = 128;         // flag slots per team
+constexpr int kThreads = 512;
+constexpr int kChunkBytes = 32768;    // kThreads * 16 B * 4
+constexpr int kInlineDescs = 6;
+constexpr int kFlagWords = kMaxCtas * kMaxPeers;
+
+// Everything a kernel needs to talk to its peers. Passed by value
+// (__grid_constant__).
+struct CommParams {
+  int nranks;
+  int rank;
+  void* buf[kMaxPeers];         // op data buffer of every rank, mapped into this process
+  uint32_t* flags[kMaxPeers];   // flag words of every rank: [cta][src_rank]
+  void* mc_buf;                 // multicast (NVLS) mapping of the same buffer, or nullptr
+  uint32_t* epochs;             // local: per-CTA barrier epoch, persists across launches
+  const int* abort_flag;        // host-mapped; non-zero => stop spinning (peer failure / shutdown)
+};
+
+// One tensor of a fused response. `offset` is the tensor's byte offset inside
+// the fused buffer in WIRE dtype (128 B aligned); `count` in elements.
+struct TensorDesc {
+  const void* in;
+  void* out;
+  int64_t offset;
+  int64_t count;
+};
+
+enum Variant : int { kOneShot = 0, kTwoShot = 1, kNvls = 2 };
+// reduce op codes follow hvd::ReduceOp: 1 SUM (AVERAGE arrives as SUM + postscale), 3 MIN, 4 MAX, 5 PRODUCT
+// dtype codes follow hvd::DataType.
+
+struct AllreduceArgs {
+  const TensorDesc* descs;      // device table (nullptr => use inline_descs)
+  TensorDesc inline_descs[kInlineDescs];
+  int ndesc;
+  int64_t total_bytes;          // wire bytes of the fused buffer region, multiple of 128
+  int64_t reduce_lo, reduce_hi; // byte range this rank must produce output for (allreduce: [0,total))
+  double prescale, postscale;
+  int op;
+  int dtype, wire_dtype;
+  int variant;
+  int ctas;
+  // reducescatter: outputs use their own table (offsets relative to the fused buffer)
+  const TensorDesc* out_descs;  // nullptr => same as descs
+  int nout;
+};
+
+// Fused allreduce / reducescatter.  Returns cudaErrorInvalidValue for
+// unsupported dtype combinations.
+cudaError_t LaunchAllreduce(const CommParams& cp, const AllreduceArgs& args, cudaStream_t stream);
+
+// Generic "pack -> barrier -> pull" used by allgather / broadcast / alltoall.
+// send: local src -> local symmetric buffer offset; recv: peer buffer offset -> local dst.
+struct CopyDesc {
+  const void* src;   // send: local source; recv: unused
+  void* dst;         // recv: local destination; send: unused
+  int64_t offset;    // byte offset in the (sender's) symmetric buffer
+  int64_t bytes;
+  int peer;          // recv: which rank's buffer to pull from
+  int pad;
+};
+struct ExchangeArgs {
+  const CopyDesc* sends; int nsend;
+  const CopyDesc* recvs; int nrecv;
+  int ctas;
+};
+cudaError_t LaunchExchange(const CommParams& cp, const ExchangeArgs& args, cudaStream_t stream);
+
+// Stand-alone batched pack / unpack / scale (NCCL-baseline path and odd cases).
+// direction 0: tensors -> buffer (prescale), 1: buffer -> tensors (postscale)
+cudaError_t LaunchPackUnpack(void* buffer, const TensorDesc* descs, int ndesc, int64_t total_bytes, int dtype,
+                             int wire_dtype, double scale, int direction, int ctas, cudaStream_t stream);
+cudaError_t LaunchScale(const void* in, void* out, int64_t count, int dtype, double scale, cudaStream_t stream);
+
+// Adasum pairwise step between this rank and `partner` over the symmetric
+// buffer: computes dot(a,b), |a|^2, |b|^2 per tensor segment, then
+// a <- acoeff*a + bcoeff*b on the half this rank keeps.  See adasum_kernels.cu.
+struct AdasumArgs {
+  const TensorDesc* descs; int ndesc;   // tensors (fp32/fp16/bf16) inside the fused buffer
+  int64_t total_bytes;
+  int dtype;
+  int ctas;
+  double* scratch;                      // device: 3 doubles per tensor per level, symmetric region
+};
+cudaError_t LaunchAdasum(const CommParams& cp, const AdasumArgs& args, cudaStream_t stream);
+
+// Fused multi-tensor optimizer updates (see optim_kernels.cu)
+struct SgdTensor { void* param; const void* grad; void* momentum; int64_t count; };
+cudaError_t LaunchFusedSgd(const SgdTensor* table, int n, int64_t max_count, float lr, float momentum, float dampening,
+                           float weight_decay, int nesterov, float grad_scale, int first_step, int param_dtype,
+                           int grad_dtype, cudaStream_t stream);
+struct AdamTensor { void* param; const void* grad; void* exp_avg; void* exp_avg_sq; int64_t count; };
+cudaError_t LaunchFusedAdamW(const AdamTensor* table, int n, int64_t max_count, float lr, float beta1, float beta2,
+                             float eps, float weight_decay, float bias_c1, float bias_c2, float grad_scale,
+                             int adamw, int param_dtype, int grad_dtype, cudaStream_t stream);
+
+}  // namespace kern
+}  // namespace hvd

@@ -1,0 +1,258 @@
+#include "cpu_ops.h"
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include "../common/half.h"
+
+namespace hvd {
+namespace cpu {
+
+namespace {
+
+template <typename T> inline T Combine(T a, T b, ReduceOp op) {
+  switch (op) {
+    case ReduceOp::MIN: return b < a ? b : a;
+    case ReduceOp::MAX: return b > a ? b : a;
+    case ReduceOp::PRODUCT: return a * b;
+    default: return a + b;
+  }
+}
+template <typename T> void ReduceT(T* d, const T* s, int64_t n, ReduceOp op) {
+  if (op == ReduceOp::SUM || op == ReduceOp::AVERAGE || op == ReduceOp::ADASUM) { for (int64_t i = 0; i < n; ++i) d[i] = d[i] + s[i]; return; }
+  for (int64_t i = 0; i < n; ++i) d[i] = Combine<T>(d[i], s[i], op);
+}
+template <float (*ToF)(uint16_t), uint16_t (*FromF)(float)> void Reduce16(uint16_t* d, const uint16_t* s, int64_t n, ReduceOp op) {
+  for (int64_t i = 0; i < n; ++i) d[i] = FromF(Combine<float>(ToF(d[i]), ToF(s[i]), op));
+}
+template <typename T> void ScaleT(T* b, int64_t n, double s) { for (int64_t i = 0; i < n; ++i) b[i] = (T)(b[i] * s); }
+
+double LoadAsDouble(const void* p, int64_t i, DataType t) {
+  switch (t) {
+    case DataType::FLOAT16: return HalfBitsToFloat(((const uint16_t*)p)[i]);
+    case DataType::BFLOAT16: return BF16BitsToFloat(((const uint16_t*)p)[i]);
+    case DataType::FLOAT32: return ((const float*)p)[i];
+    default: return ((const double*)p)[i];
+  }
+}
+void StoreFromDouble(void* p, int64_t i, DataType t, double v) {
+  switch (t) {
+    case DataType::FLOAT16: ((uint16_t*)p)[i] = FloatToHalfBits((float)v); break;
+    case DataType::BFLOAT16: ((uint16_t*)p)[i] = FloatToBF16Bits((float)v); break;
+    case DataType::FLOAT32: ((float*)p)[i] = (float)v; break;
+    default: ((double*)p)[i] = v; break;
+  }
+}
+
+}  // namespace
+
+void ReduceInto(void* dst, const void* src, int64_t n, DataType dtype, ReduceOp op) {
+  switch (dtype) {
+    case DataType::UINT8: case DataType::BOOL: ReduceT((uint8_t*)dst, (const uint8_t*)src, n, op); break;
+    case DataType::INT8: ReduceT((int8_t*)dst, (const int8_t*)src, n, op); break;
+    case DataType::UINT16: ReduceT((uint16_t*)dst, (const uint16_t*)src, n, op); break;
+    case DataType::INT16: ReduceT((int16_t*)dst, (const int16_t*)src, n, op); break;
+    case DataType::INT32: ReduceT((int32_t*)dst, (const int32_t*)src, n, op); break;
+    case DataType::INT64: ReduceT((int64_t*)dst, (const int64_t*)src, n, op); break;
+    case DataType::FLOAT32: ReduceT((float*)dst, (const float*)src, n, op); break;
+    case DataType::FLOAT64: ReduceT((double*)dst, (const double*)src, n, op); break;
+    case DataType::FLOAT16: Reduce16<HalfBitsToFloat, FloatToHalfBits>((uint16_t*)dst, (const uint16_t*)src, n, op); break;
+    case DataType::BFLOAT16: Reduce16<BF16BitsToFloat, FloatToBF16Bits>((uint16_t*)dst, (const uint16_t*)src, n, op); break;
+  }
+}
+
+void ScaleBuffer(void* buf, int64_t n, DataType dtype, double s) {
+  if (s == 1.0) return;
+  switch (dtype) {
+    case DataType::UINT8: case DataType::BOOL: ScaleT((uint8_t*)buf, n, s); break;
+    case DataType::INT8: ScaleT((int8_t*)buf, n, s); break;
+    case DataType::UINT16: ScaleT((uint16_t*)buf, n, s); break;
+    case DataType::INT16: ScaleT((int16_t*)buf, n, s); break;
+    case DataType::INT32: ScaleT((int32_t*)buf, n, s); break;
+    case DataType::INT64: ScaleT((int64_t*)buf, n, s); break;
+    case DataType::FLOAT32: { float* b = (float*)buf; float f = (float)s; for (int64_t i = 0; i < n; ++i) b[i] *= f; break; }
+    case DataType::FLOAT64: ScaleT((double*)buf, n, s); break;
+    case DataType::FLOAT16: { uint16_t* b = (uint16_t*)buf; for (int64_t i = 0; i < n; ++i) b[i] = FloatToHalfBits(HalfBitsToFloat(b[i]) * (float)s); break; }
+    case DataType::BFLOAT16: { uint16_t* b = (uint16_t*)buf; for (int64_t i = 0; i < n; ++i) b[i] = FloatToBF16Bits(BF16BitsToFloat(b[i]) * (float)s); break; }
+  }
+}
+
+// ---------------------------------------------------------------------------
+
+void Allreduce(Transport* t, void* buf, int64_t count, DataType dtype, ReduceOp op) {
+  const int n = t->size(), r = t->rank();
+  if (n == 1 || count == 0) return;
+  const size_t es = DataTypeSize(dtype);
+  char* b = (char*)buf;
+  if ((size_t)count * es < 32768 || count < n) {
+    // latency regime: reduce at rank 0, broadcast
+    if (r == 0) {
+      std::vector<char> tmp((size_t)count * es);
+      for (int p = 1; p < n; ++p) { t->Recv(p, tmp.data(), tmp.size()); ReduceInto(b, tmp.data(), count, dtype, op); }
+      for (int p = 1; p < n; ++p) t->Send(p, b, (size_t)count * es);
+    } else {
+      t->Send(0, b, (size_t)count * es);
+      t->Recv(0, b, (size_t)count * es);
+    }
+    return;
+  }
+  // bandwidth regime: ring reduce-scatter + ring allgather
+  std::vector<int64_t> off(n + 1);
+  for (int i = 0; i <= n; ++i) off[i] = count * i / n;
+  int64_t maxseg = 0;
+  for (int i = 0; i < n; ++i) maxseg = std::max(maxseg, off[i + 1] - off[i]);
+  std::vector<char> tmp((size_t)maxseg * es);
+  const int next = (r + 1) % n, prev = (r - 1 + n) % n;
+  for (int s = 0; s < n - 1; ++s) {
+    int si = (r - s + n) % n, ri = (r - s - 1 + n) % n;
+    t->SendRecv(next, b + off[si] * es, (size_t)(off[si + 1] - off[si]) * es, prev, tmp.data(), (size_t)(off[ri + 1] - off[ri]) * es);
+    ReduceInto(b + off[ri] * es, tmp.data(), off[ri + 1] - off[ri], dtype, op);
+  }
+  for (int s = 0; s < n - 1; ++s) {
+    int si = (r + 1 - s + n) % n, ri = (r - s + n) % n;
+    t->SendRecv(next, b + off[si] * es, (size_t)(off[si + 1] - off[si]) * es, prev, b + off[ri] * es, (size_t)(off[ri + 1] - off[ri]) * es);
+  }
+}
+
+void Allgatherv(Transport* t, const void* in, void* out, const std::vector<int64_t>& bytes) {
+  const int n = t->size(), r = t->rank();
+  std::vector<int64_t> displ(n + 1, 0);
+  for (int i = 0; i < n; ++i) displ[i + 1] = displ[i] + bytes[i];
+  char* o = (char*)out;
+  if (in != o + displ[r] && bytes[r]) memcpy(o + displ[r], in, (size_t)bytes[r]);
+  if (n == 1) return;
+  const int next = (r + 1) % n, prev = (r - 1 + n) % n;
+  for (int s = 0; s < n - 1; ++s) {
+    int si = (r - s + n) % n, ri = (r - s - 1 + n) % n;
+    t->SendRecv(next, o + displ[si], (size_t)bytes[si], prev, o + displ[ri], (size_t)bytes[ri]);
+  }
+}
+
+void Broadcast(Transport* t, void* buf, int64_t bytes, int root) {
+  const int n = t->size(), r = t->rank();
+  if (n == 1 || bytes == 0) return;
+  // binomial tree rooted at `root`
+  int vr = (r - root + n) % n;
+  int mask = 1;
+  while (mask < n) {
+    if (vr & mask) { t->Recv(((vr - mask) + root) % n, buf, (size_t)bytes); break; }
+    mask <<= 1;
+  }
+  mask >>= 1;
+  while (mask > 0) {
+    if (vr + mask < n) t->Send(((vr + mask) + root) % n, buf, (size_t)bytes);
+    mask >>= 1;
+  }
+}
+
+void Alltoallv(Transport* t, const void* in, const std::vector<int64_t>& sb, void* out, const std::vector<int64_t>& rb) {
+  const int n = t->size(), r = t->rank();
+  std::vector<int64_t> sd(n + 1, 0), rd(n + 1, 0);
+  for (int i = 0; i < n; ++i) { sd[i + 1] = sd[i] + sb[i]; rd[i + 1] = rd[i] + rb[i]; }
+  const char* i8 = (const char*)in; char* o8 = (char*)out;
+  if (sb[r]) memcpy(o8 + rd[r], i8 + sd[r], (size_t)sb[r]);
+  for (int s = 1; s < n; ++s) {
+    int to = (r + s) % n, from = (r - s + n) % n;
+    t->SendRecv(to, i8 + sd[to], (size_t)sb[to], from, o8 + rd[from], (size_t)rb[from]);
+  }
+}
+
+void Reducescatter(Transport* t, void* buf, const std::vector<int64_t>& counts, void* out, DataType dtype, ReduceOp op) {
+  const int n = t->size(), r = t->rank();
+  const size_t es = DataTypeSize(dtype);
+  std::vector<int64_t> off(n + 1, 0);
+  for (int i = 0; i < n; ++i) off[i + 1] = off[i] + counts[i];
+  char* b = (char*)buf;
+  if (n > 1) {
+    int64_t maxseg = *std::max_element(counts.begin(), counts.end());
+    std::vector<char> tmp((size_t)maxseg * es);
+    const int next = (r + 1) % n, prev = (r - 1 + n) % n;
+    for (int s = 0; s < n - 1; ++s) {
+      int si = (r - s - 1 + 2 * n) % n, ri = (r - s - 2 + 2 * n) % n;
+      t->SendRecv(next, b + off[si] * es, (size_t)counts[si] * es, prev, tmp.data(), (size_t)counts[ri] * es);
+      ReduceInto(b + off[ri] * es, tmp.data(), counts[ri], dtype, op);
+    }
+  }
+  if (counts[r]) memcpy(out, b + off[r] * es, (size_t)counts[r] * es);
+}
+
+// ---------------------------------------------------------------------------
+// Adasum VHDD
+
+Status AdasumAllreduce(Transport* t, void* buf, const std::vector<int64_t>& tensor_counts, DataType dtype) {
+  const int n = t->size(), r = t->rank();
+  if (n == 1) return Status::OK();
+  if (n & (n - 1)) return Status::PreconditionError("Running Adasum with non-power-of-2 ranks is not supported yet.");
+  if (!(dtype == DataType::FLOAT16 || dtype == DataType::BFLOAT16 || dtype == DataType::FLOAT32 || dtype == DataType::FLOAT64))
+    return Status::PreconditionError("Adasum supports only floating point tensors.");
+  const size_t es = DataTypeSize(dtype);
+  const int nt = (int)tensor_counts.size();
+  std::vector<int64_t> toff(nt + 1, 0);
+  for (int i = 0; i < nt; ++i) toff[i + 1] = toff[i] + tensor_counts[i];
+  const int64_t total = toff[nt];
+  char* b = (char*)buf;
+
+  struct Lvl { int64_t start, len, kept_start, kept_len, sent_start, sent_len; };
+  std::vector<Lvl> levels;
+  int64_t start = 0, len = total;
+  std::vector<char> recvbuf;
+  std::vector<double> dots(3 * (size_t)nt), dots_tmp(3 * (size_t)nt);
+
+  for (int level = 1; level < n; level <<= 1) {
+    const int partner = r ^ level;
+    const bool lower = (r & level) == 0;
+    const int64_t h0 = len / 2, h1 = len - h0;
+    Lvl L;
+    L.start = start; L.len = len;
+    L.kept_start = lower ? start : start + h0; L.kept_len = lower ? h0 : h1;
+    L.sent_start = lower ? start + h0 : start; L.sent_len = lower ? h1 : h0;
+    levels.push_back(L);
+    recvbuf.resize((size_t)L.kept_len * es);
+    t->SendRecv(partner, b + L.sent_start * es, (size_t)L.sent_len * es, partner, recvbuf.data(), (size_t)L.kept_len * es);
+    // own kept piece belongs to A on the lower side, to B on the upper side
+    const char* mine = b + L.kept_start * es;
+    const char* theirs = recvbuf.data();
+    std::fill(dots.begin(), dots.end(), 0.0);
+    for (int ti = 0; ti < nt; ++ti) {
+      int64_t lo = std::max(toff[ti], L.kept_start), hi = std::min(toff[ti + 1], L.kept_start + L.kept_len);
+      double dab = 0, daa = 0, dbb = 0;
+      for (int64_t e = lo; e < hi; ++e) {
+        double m = LoadAsDouble(mine, e - L.kept_start, dtype), o = LoadAsDouble(theirs, e - L.kept_start, dtype);
+        double a = lower ? m : o, bb = lower ? o : m;
+        dab += a * bb; daa += a * a; dbb += bb * bb;
+      }
+      dots[3 * ti] = dab; dots[3 * ti + 1] = daa; dots[3 * ti + 2] = dbb;
+    }
+    // sum the partial dots over the 2*level ranks that jointly hold this vector pair
+    for (int d = 1; d < 2 * level; d <<= 1) {
+      int p = r ^ d;
+      t->SendRecv(p, dots.data(), dots.size() * 8, p, dots_tmp.data(), dots_tmp.size() * 8);
+      for (size_t i = 0; i < dots.size(); ++i) dots[i] += dots_tmp[i];
+    }
+    for (int ti = 0; ti < nt; ++ti) {
+      int64_t lo = std::max(toff[ti], L.kept_start), hi = std::min(toff[ti + 1], L.kept_start + L.kept_len);
+      if (lo >= hi) continue;
+      const double dab = dots[3 * ti], daa = dots[3 * ti + 1], dbb = dots[3 * ti + 2];
+      const double tiny = std::sqrt(DBL_MIN);
+      double ac = 1.0, bc = 1.0;
+      if (daa >= tiny) ac = 1.0 - dab / (2.0 * daa);
+      if (dbb >= tiny) bc = 1.0 - dab / (2.0 * dbb);
+      for (int64_t e = lo; e < hi; ++e) {
+        double m = LoadAsDouble(mine, e - L.kept_start, dtype), o = LoadAsDouble(theirs, e - L.kept_start, dtype);
+        double a = lower ? m : o, bb = lower ? o : m;
+        StoreFromDouble(b + L.kept_start * es, e - L.kept_start, dtype, ac * a + bc * bb);
+      }
+    }
+    start = L.kept_start; len = L.kept_len;
+  }
+  // distance-halving allgather: undo the splits in reverse order
+  for (int li = (int)levels.size() - 1, level = n >> 1; li >= 0; --li, level >>= 1) {
+    const Lvl& L = levels[li];
+    const int partner = r ^ level;
+    t->SendRecv(partner, b + L.kept_start * es, (size_t)L.kept_len * es, partner, b + L.sent_start * es, (size_t)L.sent_len * es);
+  }
+  return Status::OK();
+}
+
+}  // namespace cpu
+}  // namespace hvd

@@ -1,0 +1,624 @@
+#include "gpu_ops.h"
+#include <unistd.h>
+#include <algorithm>
+#include <cstring>
+#include "../common/env.h"
+#include "../common/logging.h"
+#include "../kernels/p2p_kernels.h"
+#include "../symm/symm_memory.h"
+#include "cpu_ops.h"
+#include "nccl_baseline.h"
+
+namespace hvd {
+
+#define HVD_CUDA(call)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (call);                                                                \
+    if (_e != cudaSuccess) return Status::UnknownError(std::string(#call) + " failed: " + cudaGetErrorString(_e)); \
+  } while (0)
+
+namespace {
+constexpr size_t kRingBytes = 8 << 20;
+int64_t Align128(int64_t b) { return (b + 127) / 128 * 128; }
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// GpuContext
+
+GpuContext& GpuContext::Get() { static GpuContext c; return c; }
+
+int GpuContext::DeviceCount() {
+  if (count_ == -2) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    count_ = n;
+  }
+  return count_;
+}
+bool GpuContext::Available() { return DeviceCount() > 0; }
+
+GpuContext::PerDevice& GpuContext::Dev(int device) {
+  auto it = devs_.find(device);
+  if (it != devs_.end()) return it->second;
+  PerDevice& d = devs_[device];
+  cudaSetDevice(device);
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  cudaStreamCreateWithPriority(&d.stream, cudaStreamNonBlocking, hi);  // highest priority, like the reference (cuda_operations.cc:202-209)
+  cudaHostAlloc((void**)&d.host_ring, kRingBytes, cudaHostAllocDefault);
+  cudaMalloc((void**)&d.dev_ring, kRingBytes);
+  return d;
+}
+
+cudaStream_t GpuContext::Stream(int device) { std::lock_guard<std::mutex> l(mu_); return Dev(device).stream; }
+
+SharedEvent* GpuContext::NewEvent(int device, int refs) {
+  std::lock_guard<std::mutex> l(mu_);
+  PerDevice& d = Dev(device);
+  auto* e = new SharedEvent();
+  e->device = device;
+  e->refs = refs;
+  if (!d.pool.empty()) { e->ev = d.pool.back(); d.pool.pop_back(); }
+  else { cudaSetDevice(device); cudaEventCreateWithFlags(&e->ev, cudaEventDisableTiming); }
+  return e;
+}
+
+void GpuContext::Release(SharedEvent* e) {
+  if (!e) return;
+  if (e->refs.fetch_sub(1) > 1) return;
+  {
+    std::lock_guard<std::mutex> l(mu_);
+    auto it = devs_.find(e->device);
+    if (it != devs_.end() && e->ev) it->second.pool.push_back(e->ev);
+  }
+  delete e;
+}
+
+const void* GpuContext::Stage(int device, const void* host, size_t bytes, cudaStream_t s) {
+  std::lock_guard<std::mutex> l(mu_);
+  PerDevice& d = Dev(device);
+  const size_t raw = bytes;
+  bytes = (bytes + 255) / 256 * 256;
+  if (bytes > kRingBytes) return nullptr;
+  if (d.ring_off + bytes > kRingBytes) { cudaStreamSynchronize(s); d.ring_off = 0; }  // wrap: everything older is consumed
+  char* h = d.host_ring + d.ring_off;
+  char* dv = d.dev_ring + d.ring_off;
+  d.ring_off += bytes;
+  memcpy(h, host, raw);
+  cudaMemcpyAsync(dv, h, raw, cudaMemcpyHostToDevice, s);
+  return dv;
+}
+
+void* GpuContext::TempAlloc(int device, size_t bytes, bool zero, cudaStream_t s) {
+  void* p = nullptr;
+  cudaSetDevice(device);
+  if (cudaMallocAsync(&p, bytes ? bytes : 16, s) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (zero) cudaMemsetAsync(p, 0, bytes ? bytes : 16, s);
+  std::lock_guard<std::mutex> l(mu_);
+  Dev(device).temps.push_back(p);
+  return p;
+}
+void GpuContext::TempFreeAll(int device, cudaStream_t s) {
+  std::vector<void*> t;
+  { std::lock_guard<std::mutex> l(mu_); t.swap(Dev(device).temps); }
+  for (void* p : t) cudaFreeAsync(p, s);
+}
+
+void GpuContext::Reset() {
+  std::lock_guard<std::mutex> l(mu_);
+  for (auto& kv : devs_) {
+    cudaSetDevice(kv.first);
+    if (kv.second.stream) { cudaStreamSynchronize(kv.second.stream); cudaStreamDestroy(kv.second.stream); }
+    for (auto e : kv.second.pool) cudaEventDestroy(e);
+    if (kv.second.host_ring) cudaFreeHost(kv.second.host_ring);
+    if (kv.second.dev_ring) cudaFree(kv.second.dev_ring);
+  }
+  devs_.clear();
+  cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// helpers
+
+namespace {
+
+struct Piece { const char* in; char* out; int64_t count; };
+
+void WaitReady(Entries& es, cudaStream_t s) {
+  void* last = nullptr;
+  for (auto& e : es) {
+    if (e && e->ready_event && e->ready_event != last) { cudaStreamWaitEvent(s, (cudaEvent_t)e->ready_event, 0); last = e->ready_event; }
+  }
+}
+
+Status FinishEvent(int device, cudaStream_t s, size_t nrefs, SharedEvent** done) {
+  SharedEvent* ev = GpuContext::Get().NewEvent(device, (int)std::max<size_t>(nrefs, 1));
+  cudaError_t e = cudaEventRecord(ev->ev, s);
+  if (e != cudaSuccess) { GpuContext::Get().Release(ev); return Status::UnknownError(std::string("cudaEventRecord: ") + cudaGetErrorString(e)); }
+  *done = ev;
+  return Status::OK();
+}
+
+// Allreduce pieces: real entries, or zero placeholders for tensors this (joined) rank never submitted.
+Status BuildPieces(Entries& es, const Response& r, int device, cudaStream_t s, std::vector<Piece>* pieces) {
+  const size_t esz = DataTypeSize(r.dtype);
+  for (size_t i = 0; i < es.size(); ++i) {
+    if (es[i]) {
+      pieces->push_back({(const char*)es[i]->input, (char*)es[i]->output, es[i]->shape.num_elements()});
+    } else {
+      int64_t cnt = i < r.tensor_sizes.size() ? r.tensor_sizes[i] : 0;
+      char* z = (char*)GpuContext::Get().TempAlloc(device, (size_t)cnt * esz, true, s);
+      if (!z) return Status::UnknownError("out of device memory for join placeholder");
+      pieces->push_back({z, z, cnt});
+    }
+  }
+  return Status::OK();
+}
+
+}  // namespace
+
+std::shared_ptr<SymmTeam> GpuOps::EnsureTeam(ProcessSet& ps, int device) {
+  if (ps.team_tried) return ps.team;
+  ps.team_tried = true;
+  Transport* t = ps.transport.get();
+  // unique tag for the fd-passing sockets: coordinator pid + counter, agreed through the transport
+  int64_t tag[2] = {(int64_t)getpid(), (int64_t)(++team_counter_)};
+  t->Bcast(tag, sizeof tag, 0);
+  std::string why;
+  bool single = t->single_host();
+  uint64_t ok = single ? 1 : 0;
+  t->AllreduceBits(&ok, 1, nullptr, 0);
+  if (!ok) { LOG(INFO) << "process set " << ps.id << " spans hosts: GPU collectives are staged through the CPU transport"; return nullptr; }
+  size_t bytes = ps.id == 0 ? env_.symm_buffer_bytes : std::min<size_t>(env_.symm_buffer_bytes, 32ull << 20);
+  ps.team = SymmTeam::Create(t, device, bytes, env_.want_multicast,
+                             std::to_string(tag[0]) + "-" + std::to_string(tag[1]) + "-" + std::to_string(ps.id), &why);
+  if (!ps.team) LOG(WARNING) << "peer-mapped symmetric memory unavailable for process set " << ps.id << " (" << why
+                             << "); GPU collectives fall back to host staging";
+  else LOG(INFO) << "process set " << ps.id << ": symmetric team of " << ps.team->nranks() << " GPUs, backend "
+                 << ps.team->backend() << ", 2 x " << (ps.team->buffer_bytes() >> 20) << " MiB";
+  return ps.team;
+}
+
+std::string GpuOps::Describe(ProcessSet& ps) {
+  if (!ps.team_tried) return "backend=" + env_.backend + " (no GPU collective issued yet)";
+  if (!ps.team) return "backend=host-staged";
+  return "backend=" + env_.backend + " symm=" + ps.team->backend() + " buffer=" + std::to_string(ps.team->buffer_bytes());
+}
+
+// ---------------------------------------------------------------------------
+// allreduce
+
+Status GpuOps::Allreduce(ProcessSet& ps, Entries& es, const Response& r, SharedEvent** done) {
+  const int me = ps.set_rank(), n = ps.set_size();
+  const int device = r.devices[me];
+  HVD_CUDA(cudaSetDevice(device));
+  GpuContext& ctx = GpuContext::Get();
+  cudaStream_t s = ctx.Stream(device);
+  WaitReady(es, s);
+  std::vector<Piece> pieces;
+  Status st = BuildPieces(es, r, device, s, &pieces);
+  if (!st.ok()) return st;
+  const size_t esz = DataTypeSize(r.dtype);
+
+  if (n == 1) {
+    const double sc = r.prescale * r.postscale;
+    for (auto& p : pieces) {
+      if (p.in != p.out || sc != 1.0) HVD_CUDA(kern::LaunchScale(p.in, p.out, p.count, (int)r.dtype, sc, s));
+    }
+  } else if (env_.backend == "nccl") {
+    st = NcclAllreduce(ps, es, r, device, s);
+    if (!st.ok()) return st;
+  } else {
+    std::shared_ptr<SymmTeam> team = env_.backend == "cpu" ? nullptr : EnsureTeam(ps, device);
+    if (!team) {
+      st = StagedOnHost(ps, es, r, device, s);
+      if (!st.ok()) return st;
+    } else {
+      // wire dtype: optional in-kernel compression of fp32 sums
+      DataType wire = r.dtype;
+      if (r.dtype == DataType::FLOAT32 && (env_.wire_dtype == DataType::BFLOAT16 || env_.wire_dtype == DataType::FLOAT16) &&
+          (r.reduce_op == ReduceOp::SUM || r.reduce_op == ReduceOp::AVERAGE))
+        wire = env_.wire_dtype;
+      const int64_t wsz = (int64_t)DataTypeSize(wire);
+      const int64_t cap = (int64_t)team->buffer_bytes() / 128 * 128;
+      const TunableParams& tp = *env_.params;
+      // split into segments that fit the symmetric buffer
+      std::vector<kern::TensorDesc> descs;
+      int64_t seg_bytes = 0;
+      auto flush = [&]() -> Status {
+        if (descs.empty()) return Status::OK();
+        kern::AllreduceArgs a {};
+        a.ndesc = (int)descs.size();
+        a.total_bytes = seg_bytes;
+        a.reduce_lo = 0; a.reduce_hi = seg_bytes;
+        a.prescale = r.prescale; a.postscale = r.postscale;
+        a.op = (int)r.reduce_op; a.dtype = (int)r.dtype; a.wire_dtype = (int)wire;
+        // variant by message size (thresholds are autotuned)
+        int variant = kern::kTwoShot;
+        const bool nvls_ok = team->has_multicast() && (r.reduce_op == ReduceOp::SUM || r.reduce_op == ReduceOp::AVERAGE) &&
+                             (wire == DataType::FLOAT32 || wire == DataType::FLOAT16 || wire == DataType::BFLOAT16);
+        if (env_.variant == "oneshot") variant = kern::kOneShot;
+        else if (env_.variant == "twoshot") variant = kern::kTwoShot;
+        else if (env_.variant == "nvls" && nvls_ok) variant = kern::kNvls;
+        else {
+          if (seg_bytes <= tp.oneshot_max_bytes) variant = kern::kOneShot;
+          else if (nvls_ok && seg_bytes >= tp.nvls_min_bytes) variant = kern::kNvls;
+        }
+        a.variant = variant;
+        int64_t per = variant == kern::kOneShot ? 16384 : (int64_t)8192 * n;
+        a.ctas = (int)std::max<int64_t>(1, std::min<int64_t>(tp.comm_ctas, (seg_bytes + per - 1) / per));
+        if (a.ndesc <= kern::kInlineDescs) {
+          memcpy(a.inline_descs, descs.data(), descs.size() * sizeof(kern::TensorDesc));
+          a.descs = nullptr;
+        } else {
+          a.descs = (const kern::TensorDesc*)ctx.Stage(device, descs.data(), descs.size() * sizeof(kern::TensorDesc), s);
+          if (!a.descs) return Status::UnknownError("descriptor table too large");
+        }
+        kern::CommParams cp = team->Params(team->NextSlot());
+        if (env_.timeline && env_.timeline->Initialized())
+          env_.timeline->ActivityStartAll(es, variant == kern::kOneShot ? HVD_ACT_P2P_ALLREDUCE_ONESHOT
+                                              : variant == kern::kNvls ? HVD_ACT_P2P_ALLREDUCE_NVLS : HVD_ACT_P2P_ALLREDUCE_TWOSHOT);
+        cudaError_t ce = kern::LaunchAllreduce(cp, a, s);
+        if (ce != cudaSuccess) return Status::UnknownError(std::string("allreduce kernel launch failed: ") + cudaGetErrorString(ce));
+        descs.clear();
+        seg_bytes = 0;
+        return Status::OK();
+      };
+      for (auto& p : pieces) {
+        int64_t done_el = 0;
+        while (done_el < p.count || (p.count == 0 && done_el == 0)) {
+          if (p.count == 0) break;
+          int64_t space = cap - seg_bytes;
+          if (space < 128) { st = flush(); if (!st.ok()) return st; space = cap; }
+          int64_t take = std::min<int64_t>(p.count - done_el, space / wsz);
+          kern::TensorDesc d;
+          d.in = p.in + done_el * esz; d.out = p.out + done_el * esz; d.offset = seg_bytes; d.count = take;
+          descs.push_back(d);
+          seg_bytes += Align128(take * wsz);
+          done_el += take;
+        }
+      }
+      st = flush();
+      if (!st.ok()) return st;
+    }
+  }
+  ctx.TempFreeAll(device, s);
+  return FinishEvent(device, s, es.size(), done);
+}
+
+Status GpuOps::NcclAllreduce(ProcessSet& ps, Entries& es, const Response& r, int device, cudaStream_t s) {
+  if (!ps.nccl_tried) {
+    ps.nccl_tried = true;
+    std::string why;
+    ps.nccl = NcclCreateComm(ps.transport.get(), device, &why);
+    if (!ps.nccl) LOG(WARNING) << "NCCL baseline unavailable: " << why;
+  }
+  if (!ps.nccl) return StagedOnHost(ps, es, r, device, s);
+  GpuContext& ctx = GpuContext::Get();
+  const size_t esz = DataTypeSize(r.dtype);
+  std::vector<Piece> pieces;
+  Status st = BuildPieces(es, r, device, s, &pieces);
+  if (!st.ok()) return st;
+  if (pieces.size() == 1) {
+    // unfused: optional prescale kernel, ncclAllReduce(input -> output), optional postscale kernel
+    // (reference nccl_operations.cc:238-283)
+    const Piece& p = pieces[0];
+    const void* in = p.in;
+    if (r.prescale != 1.0) { HVD_CUDA(kern::LaunchScale(p.in, p.out, p.count, (int)r.dtype, r.prescale, s)); in = p.out; }
+    st = NcclAllReduceCall(*ps.nccl, in, p.out, p.count, r.dtype, r.reduce_op, s);
+    if (!st.ok()) return st;
+    if (r.postscale != 1.0) HVD_CUDA(kern::LaunchScale(p.out, p.out, p.count, (int)r.dtype, r.postscale, s));
+    return Status::OK();
+  }
+  // fused: scaled pack -> ncclAllReduce in place on the fusion buffer -> scaled unpack
+  std::vector<kern::TensorDesc> descs;
+  int64_t total = 0;
+  for (auto& p : pieces) {
+    kern::TensorDesc d; d.in = p.in; d.out = p.out; d.offset = total; d.count = p.count;
+    descs.push_back(d);
+    total += Align128(p.count * (int64_t)esz);
+  }
+  char* fusion = (char*)ctx.TempAlloc(device, (size_t)total, false, s);
+  if (!fusion) return Status::UnknownError("out of device memory for the NCCL fusion buffer");
+  const auto* dtab = (const kern::TensorDesc*)ctx.Stage(device, descs.data(), descs.size() * sizeof(kern::TensorDesc), s);
+  if (!dtab) return Status::UnknownError("descriptor table too large");
+  HVD_CUDA(kern::LaunchPackUnpack(fusion, dtab, (int)descs.size(), total, (int)r.dtype, (int)r.dtype, r.prescale, 0, 148, s));
+  st = NcclAllReduceCall(*ps.nccl, fusion, fusion, total / (int64_t)esz, r.dtype, r.reduce_op, s);
+  if (!st.ok()) return st;
+  HVD_CUDA(kern::LaunchPackUnpack(fusion, dtab, (int)descs.size(), total, (int)r.dtype, (int)r.dtype, r.postscale, 1, 148, s));
+  return Status::OK();
+}
+
+// Host-staged fallback (multi-host sets, no peer access): D2H, CPU collective, H2D.
+Status GpuOps::StagedOnHost(ProcessSet& ps, Entries& es, const Response& r, int device, cudaStream_t s) {
+  const size_t esz = DataTypeSize(r.dtype);
+  std::vector<Piece> pieces;
+  Status st = BuildPieces(es, r, device, s, &pieces);
+  if (!st.ok()) return st;
+  int64_t total = 0;
+  for (auto& p : pieces) total += p.count;
+  std::vector<char> host((size_t)total * esz);
+  int64_t off = 0;
+  for (auto& p : pieces) { HVD_CUDA(cudaMemcpyAsync(host.data() + off * esz, p.in, (size_t)p.count * esz, cudaMemcpyDeviceToHost, s)); off += p.count; }
+  HVD_CUDA(cudaStreamSynchronize(s));
+  cpu::ScaleBuffer(host.data(), total, r.dtype, r.prescale);
+  cpu::Allreduce(ps.transport.get(), host.data(), total, r.dtype, r.reduce_op);
+  cpu::ScaleBuffer(host.data(), total, r.dtype, r.postscale);
+  off = 0;
+  for (auto& p : pieces) { HVD_CUDA(cudaMemcpyAsync(p.out, host.data() + off * esz, (size_t)p.count * esz, cudaMemcpyHostToDevice, s)); off += p.count; }
+  HVD_CUDA(cudaStreamSynchronize(s));  // `host` dies with this frame
+  return Status::OK();
+}
+
+// ---------------------------------------------------------------------------
+// reducescatter: pack per-destination block windows, every rank reduces only
+// its own block straight into its output (one-shot restricted to a range).
+
+Status GpuOps::Reducescatter(ProcessSet& ps, Entries& es, const Response& r, SharedEvent** done) {
+  const int me = ps.set_rank(), n = ps.set_size();
+  const int device = r.devices[me];
+  HVD_CUDA(cudaSetDevice(device));
+  GpuContext& ctx = GpuContext::Get();
+  cudaStream_t s = ctx.Stream(device);
+  WaitReady(es, s);
+  const int64_t esz = (int64_t)DataTypeSize(r.dtype);
+  for (auto& e : es) {
+    if (!e) return Status::PreconditionError("Reducescatter is not supported with Join at this time.");
+    const int64_t dim0 = e->shape.dim(0);
+    int64_t row = 1;
+    for (int d = 1; d < e->shape.ndim(); ++d) row *= e->shape.dim(d);
+    std::vector<int64_t> rows;
+    ReducescatterRows(dim0, n, &rows);
+    std::vector<int64_t> boff(n + 1, 0);
+    for (int i = 0; i < n; ++i) boff[i + 1] = boff[i] + rows[i] * row;  // in elements
+    if (!e->output) {
+      std::vector<int64_t> oshape = e->shape.dims();
+      oshape[0] = rows[me];
+      e->output = e->alloc_output ? e->alloc_output(oshape) : nullptr;
+      if (!e->output && rows[me] * row > 0) return Status::UnknownError("reducescatter: output allocation failed");
+    }
+    if (n == 1) {
+      const double sc = r.prescale * r.postscale;
+      if (e->input != e->output || sc != 1.0) HVD_CUDA(kern::LaunchScale(e->input, e->output, dim0 * row, (int)r.dtype, sc, s));
+      continue;
+    }
+    std::shared_ptr<SymmTeam> team = (env_.backend == "cpu") ? nullptr : EnsureTeam(ps, device);
+    if (!team) {
+      // host staged
+      std::vector<char> host((size_t)(dim0 * row * esz)), out((size_t)(rows[me] * row * esz));
+      HVD_CUDA(cudaMemcpyAsync(host.data(), e->input, host.size(), cudaMemcpyDeviceToHost, s));
+      HVD_CUDA(cudaStreamSynchronize(s));
+      cpu::ScaleBuffer(host.data(), dim0 * row, r.dtype, r.prescale);
+      std::vector<int64_t> counts(n);
+      for (int i = 0; i < n; ++i) counts[i] = rows[i] * row;
+      cpu::Reducescatter(ps.transport.get(), host.data(), counts, out.data(), r.dtype, r.reduce_op);
+      cpu::ScaleBuffer(out.data(), counts[me], r.dtype, r.postscale);
+      HVD_CUDA(cudaMemcpyAsync(e->output, out.data(), out.size(), cudaMemcpyHostToDevice, s));
+      HVD_CUDA(cudaStreamSynchronize(s));
+      continue;
+    }
+    int64_t maxblock = 0;
+    for (int i = 0; i < n; ++i) maxblock = std::max(maxblock, rows[i] * row * esz);
+    const int64_t cap = (int64_t)team->buffer_bytes();
+    int64_t win = std::min<int64_t>(Align128(maxblock), cap / n / 128 * 128);  // window bytes per destination block
+    if (win <= 0) continue;
+    for (int64_t w0 = 0; w0 < maxblock; w0 += win) {
+      std::vector<kern::TensorDesc> in_descs(n);
+      for (int q = 0; q < n; ++q) {
+        int64_t bbytes = rows[q] * row * esz;
+        int64_t cnt = std::max<int64_t>(0, std::min(win, bbytes - w0)) / esz;
+        in_descs[q].in = (const char*)e->input + boff[q] * esz + w0;
+        in_descs[q].out = nullptr;
+        in_descs[q].offset = q * win;
+        in_descs[q].count = cnt;
+      }
+      kern::TensorDesc od;
+      int64_t mybytes = rows[me] * row * esz;
+      od.in = nullptr; od.out = (char*)e->output + w0; od.offset = me * win;
+      od.count = std::max<int64_t>(0, std::min(win, mybytes - w0)) / esz;
+      kern::AllreduceArgs a {};
+      a.ndesc = n;
+      a.total_bytes = (int64_t)n * win;
+      a.reduce_lo = me * win; a.reduce_hi = me * win + Align128(od.count * esz);
+      a.prescale = r.prescale; a.postscale = r.postscale;
+      a.op = (int)r.reduce_op; a.dtype = (int)r.dtype; a.wire_dtype = (int)r.dtype;
+      a.variant = kern::kOneShot;
+      a.ctas = (int)std::max<int64_t>(1, std::min<int64_t>(env_.params->comm_ctas, (a.total_bytes + 16383) / 16384));
+      std::vector<kern::TensorDesc> table(in_descs);
+      table.push_back(od);
+      const auto* dt = (const kern::TensorDesc*)ctx.Stage(device, table.data(), table.size() * sizeof(kern::TensorDesc), s);
+      if (!dt) return Status::UnknownError("descriptor table too large");
+      a.descs = dt; a.out_descs = dt + n; a.nout = 1;
+      kern::CommParams cp = team->Params(team->NextSlot());
+      cudaError_t ce = kern::LaunchAllreduce(cp, a, s);
+      if (ce != cudaSuccess) return Status::UnknownError(std::string("reducescatter kernel launch failed: ") + cudaGetErrorString(ce));
+    }
+  }
+  ctx.TempFreeAll(device, s);
+  return FinishEvent(device, s, es.size(), done);
+}
+
+// ---------------------------------------------------------------------------
+// allgather / broadcast / alltoall through the exchange kernel
+
+namespace {
+Status RunExchange(SymmTeam& team, GpuContext& ctx, int device, cudaStream_t s, std::vector<kern::CopyDesc>& sends,
+                   std::vector<kern::CopyDesc>& recvs, int max_ctas) {
+  std::vector<kern::CopyDesc> table(sends);
+  table.insert(table.end(), recvs.begin(), recvs.end());
+  int64_t bytes = 0;
+  for (auto& d : table) bytes += d.bytes;
+  kern::ExchangeArgs a {};
+  const kern::CopyDesc* dt = table.empty() ? nullptr
+      : (const kern::CopyDesc*)ctx.Stage(device, table.data(), table.size() * sizeof(kern::CopyDesc), s);
+  if (!table.empty() && !dt) return Status::UnknownError("descriptor table too large");
+  a.sends = dt; a.nsend = (int)sends.size();
+  a.recvs = dt ? dt + sends.size() : nullptr; a.nrecv = (int)recvs.size();
+  a.ctas = max_ctas;
+  (void)bytes;
+  kern::CommParams cp = team.Params(team.NextSlot());
+  cudaError_t ce = kern::LaunchExchange(cp, a, s);
+  if (ce != cudaSuccess) return Status::UnknownError(std::string("exchange kernel launch failed: ") + cudaGetErrorString(ce));
+  return Status::OK();
+}
+}  // namespace
+
+Status GpuOps::Allgather(ProcessSet& ps, Entries& es, const Response& r, SharedEvent** done) {
+  const int me = ps.set_rank(), n = ps.set_size();
+  const int device = r.devices[me];
+  HVD_CUDA(cudaSetDevice(device));
+  GpuContext& ctx = GpuContext::Get();
+  cudaStream_t s = ctx.Stream(device);
+  WaitReady(es, s);
+  const int64_t esz = (int64_t)DataTypeSize(r.dtype);
+  for (size_t ti = 0; ti < es.size(); ++ti) {
+    auto& e = es[ti];
+    if (!e) return Status::PreconditionError("Allgather is not supported with Join at this time.");
+    int64_t row = 1;
+    for (int d = 1; d < e->shape.ndim(); ++d) row *= e->shape.dim(d);
+    std::vector<int64_t> bytes(n), displ(n + 1, 0);
+    int64_t total_rows = 0;
+    for (int p = 0; p < n; ++p) {
+      int64_t d0 = r.tensor_sizes[ti * n + p];
+      bytes[p] = d0 * row * esz;
+      displ[p + 1] = displ[p] + bytes[p];
+      total_rows += d0;
+    }
+    std::vector<int64_t> oshape = e->shape.dims();
+    oshape[0] = total_rows;
+    e->output = e->alloc_output ? e->alloc_output(oshape) : e->output;
+    if (!e->output && displ[n] > 0) return Status::UnknownError("allgather: output allocation failed");
+    if (n == 1) { if (bytes[0]) HVD_CUDA(cudaMemcpyAsync(e->output, e->input, (size_t)bytes[0], cudaMemcpyDeviceToDevice, s)); continue; }
+    std::shared_ptr<SymmTeam> team = (env_.backend == "cpu") ? nullptr : EnsureTeam(ps, device);
+    if (!team) {
+      std::vector<char> host((size_t)displ[n]);
+      if (bytes[me]) HVD_CUDA(cudaMemcpyAsync(host.data() + displ[me], e->input, (size_t)bytes[me], cudaMemcpyDeviceToHost, s));
+      HVD_CUDA(cudaStreamSynchronize(s));
+      cpu::Allgatherv(ps.transport.get(), host.data() + displ[me], host.data(), bytes);
+      if (displ[n]) HVD_CUDA(cudaMemcpyAsync(e->output, host.data(), (size_t)displ[n], cudaMemcpyHostToDevice, s));
+      HVD_CUDA(cudaStreamSynchronize(s));
+      continue;
+    }
+    const int64_t cap = (int64_t)team->buffer_bytes() / 16 * 16;
+    int64_t maxb = *std::max_element(bytes.begin(), bytes.end());
+    for (int64_t w0 = 0; w0 < maxb; w0 += cap) {
+      std::vector<kern::CopyDesc> sends, recvs;
+      int64_t mine = std::max<int64_t>(0, std::min(cap, bytes[me] - w0));
+      if (mine) sends.push_back({(const char*)e->input + w0, nullptr, 0, mine, me, 0});
+      for (int k = 0; k < n; ++k) {
+        int p = (me + k) % n;
+        int64_t b = std::max<int64_t>(0, std::min(cap, bytes[p] - w0));
+        if (b) recvs.push_back({nullptr, (char*)e->output + displ[p] + w0, 0, b, p, 0});
+      }
+      Status st = RunExchange(*team, ctx, device, s, sends, recvs, env_.params->comm_ctas);
+      if (!st.ok()) return st;
+    }
+  }
+  return FinishEvent(device, s, es.size(), done);
+}
+
+Status GpuOps::Broadcast(ProcessSet& ps, Entries& es, const Response& r, SharedEvent** done) {
+  const int me = ps.set_rank(), n = ps.set_size();
+  const int device = r.devices[me];
+  HVD_CUDA(cudaSetDevice(device));
+  GpuContext& ctx = GpuContext::Get();
+  cudaStream_t s = ctx.Stream(device);
+  WaitReady(es, s);
+  const int root = r.root_rank;
+  for (auto& e : es) {
+    if (!e) return Status::PreconditionError("Broadcast is not supported with Join at this time.");
+    const int64_t bytes = (int64_t)e->bytes();
+    if (n == 1 || bytes == 0) {
+      if (e->output && e->output != e->input && bytes) HVD_CUDA(cudaMemcpyAsync(e->output, e->input, (size_t)bytes, cudaMemcpyDeviceToDevice, s));
+      continue;
+    }
+    std::shared_ptr<SymmTeam> team = (env_.backend == "cpu") ? nullptr : EnsureTeam(ps, device);
+    if (!team) {
+      std::vector<char> host((size_t)bytes);
+      if (me == root) { HVD_CUDA(cudaMemcpyAsync(host.data(), e->input, (size_t)bytes, cudaMemcpyDeviceToHost, s)); }
+      HVD_CUDA(cudaStreamSynchronize(s));
+      cpu::Broadcast(ps.transport.get(), host.data(), bytes, root);
+      if (me != root || e->output != e->input) HVD_CUDA(cudaMemcpyAsync(e->output, host.data(), (size_t)bytes, cudaMemcpyHostToDevice, s));
+      HVD_CUDA(cudaStreamSynchronize(s));
+      continue;
+    }
+    const int64_t cap = (int64_t)team->buffer_bytes() / 16 * 16;
+    for (int64_t w0 = 0; w0 < bytes; w0 += cap) {
+      int64_t b = std::min(cap, bytes - w0);
+      std::vector<kern::CopyDesc> sends, recvs;
+      if (me == root) sends.push_back({(const char*)e->input + w0, nullptr, 0, b, me, 0});
+      if (me != root || (e->output && e->output != e->input)) recvs.push_back({nullptr, (char*)e->output + w0, 0, b, root, 0});
+      Status st = RunExchange(*team, ctx, device, s, sends, recvs, env_.params->comm_ctas);
+      if (!st.ok()) return st;
+    }
+  }
+  return FinishEvent(device, s, es.size(), done);
+}
+
+Status GpuOps::Alltoall(ProcessSet& ps, Entries& es, const Response& r, SharedEvent** done) {
+  const int me = ps.set_rank(), n = ps.set_size();
+  const int device = r.devices[me];
+  HVD_CUDA(cudaSetDevice(device));
+  GpuContext& ctx = GpuContext::Get();
+  cudaStream_t s = ctx.Stream(device);
+  WaitReady(es, s);
+  const int64_t esz = (int64_t)DataTypeSize(r.dtype);
+  for (auto& e : es) {
+    if (!e) return Status::PreconditionError("Alltoall is not supported with Join at this time.");
+    int64_t row = 1;
+    for (int d = 1; d < e->shape.ndim(); ++d) row *= e->shape.dim(d);
+    // exchange the split matrix through the control plane (reference: AlltoallGetRecvSplits)
+    std::vector<int64_t> mine(n), all((size_t)n * n);
+    for (int p = 0; p < n; ++p) mine[p] = e->splits[p];
+    ps.transport->AllgatherInts(mine.data(), n, all.data());
+    std::vector<int64_t> sbytes(n), rbytes(n), sdisp(n + 1, 0), rdisp(n + 1, 0);
+    e->received_splits.assign(n, 0);
+    int64_t out_rows = 0;
+    for (int p = 0; p < n; ++p) {
+      sbytes[p] = mine[p] * row * esz;
+      e->received_splits[p] = (int32_t)all[(size_t)p * n + me];
+      rbytes[p] = all[(size_t)p * n + me] * row * esz;
+      sdisp[p + 1] = sdisp[p] + sbytes[p];
+      rdisp[p + 1] = rdisp[p] + rbytes[p];
+      out_rows += all[(size_t)p * n + me];
+    }
+    std::vector<int64_t> oshape = e->shape.dims();
+    oshape[0] = out_rows;
+    e->output = e->alloc_output ? e->alloc_output(oshape) : e->output;
+    if (!e->output && rdisp[n] > 0) return Status::UnknownError("alltoall: output allocation failed");
+    if (n == 1) { if (sbytes[0]) HVD_CUDA(cudaMemcpyAsync(e->output, e->input, (size_t)sbytes[0], cudaMemcpyDeviceToDevice, s)); continue; }
+    std::shared_ptr<SymmTeam> team = (env_.backend == "cpu") ? nullptr : EnsureTeam(ps, device);
+    if (!team) {
+      std::vector<char> hin((size_t)sdisp[n]), hout((size_t)rdisp[n]);
+      if (sdisp[n]) HVD_CUDA(cudaMemcpyAsync(hin.data(), e->input, (size_t)sdisp[n], cudaMemcpyDeviceToHost, s));
+      HVD_CUDA(cudaStreamSynchronize(s));
+      cpu::Alltoallv(ps.transport.get(), hin.data(), sbytes, hout.data(), rbytes);
+      if (rdisp[n]) HVD_CUDA(cudaMemcpyAsync(e->output, hout.data(), (size_t)rdisp[n], cudaMemcpyHostToDevice, s));
+      HVD_CUDA(cudaStreamSynchronize(s));
+      continue;
+    }
+    // window scheme: destination q's block occupies [q*win, (q+1)*win) of the sender's buffer
+    int64_t maxblock = 0;
+    for (size_t i = 0; i < all.size(); ++i) maxblock = std::max(maxblock, all[i] * row * esz);
+    const int64_t cap = (int64_t)team->buffer_bytes();
+    const int64_t win = std::min<int64_t>((maxblock + 15) / 16 * 16, cap / n / 16 * 16);
+    if (win <= 0) continue;
+    for (int64_t w0 = 0; w0 < maxblock; w0 += win) {
+      std::vector<kern::CopyDesc> sends, recvs;
+      for (int q = 0; q < n; ++q) {
+        int64_t b = std::max<int64_t>(0, std::min(win, sbytes[q] - w0));
+        if (b) sends.push_back({(const char*)e->input + sdisp[q] + w0, nullptr, q * win, b, me, 0});
+      }
+      for (int k = 0; k < n; ++k) {
+        int p = (me + k) % n;
+        int64_t b = std::max<int64_t>(0, std::min(win, rbytes[p] - w0));
+        if (b) recvs.push_back({nullptr, (char*)e->output + rdisp[p] + w0, me * win, b, p, 0});
+      }
+      Status st = RunExchange(*team, ctx, device, s, sends, recvs, env_.params->comm_ctas);
+      if (!st.ok()) return st;
+    }
+  }
+  return FinishEvent(device, s, es.size(), done);
+}
+
+}  // namespace hvd

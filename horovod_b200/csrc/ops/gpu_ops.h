@@ -1,0 +1,104 @@
+// GPU collective ops: the NVLink peer-to-peer product path, the NCCL baseline
+// path (reference-equivalent: pack kernel -> ncclAllReduce -> unpack kernel)
+// and the host-staged fallback, plus the per-device CUDA plumbing (private
+// high-priority stream, pooled events, descriptor staging ring).
+//
+// Parity: horovod/common/ops/gpu_operations.{h,cc} (GPUContext / GPUOpContext /
+// GPUAllreduce...), ops/cuda_operations.cc (streams, event pool),
+// ops/nccl_operations.{h,cc} (NCCL ops).
+#pragma once
+#include <atomic>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../common/common.h"
+#include "../common/controller.h"
+#include "../common/process_set.h"
+#include "../common/timeline.h"
+
+namespace hvd {
+
+// Completion event shared by every entry of a fused response.
+struct SharedEvent {
+  cudaEvent_t ev = nullptr;
+  std::atomic<int> refs{0};
+  int device = 0;
+};
+
+class GpuContext {
+ public:
+  static GpuContext& Get();
+  bool Available();
+  int DeviceCount();
+  cudaStream_t Stream(int device);
+  SharedEvent* NewEvent(int device, int refs);
+  void Release(SharedEvent* e);
+  // Copies a small host table to device memory on `s` (pinned ring -> device ring).
+  const void* Stage(int device, const void* host, size_t bytes, cudaStream_t s);
+  // zero-filled / scratch device memory that lives until the stream reaches this point
+  void* TempAlloc(int device, size_t bytes, bool zero, cudaStream_t s);
+  void TempFreeAll(int device, cudaStream_t s);
+  void Reset();
+
+ private:
+  struct PerDevice {
+    cudaStream_t stream = nullptr;
+    std::vector<cudaEvent_t> pool;
+    char* host_ring = nullptr; char* dev_ring = nullptr; size_t ring_off = 0;
+    std::vector<void*> temps;
+  };
+  PerDevice& Dev(int device);
+  std::mutex mu_;
+  std::map<int, PerDevice> devs_;
+  int count_ = -2;
+};
+
+using Entries = std::vector<std::shared_ptr<TensorTableEntry>>;
+
+struct GpuOpEnv {
+  const TunableParams* params = nullptr;
+  Timeline* timeline = nullptr;
+  std::string backend = "p2p";        // p2p | nccl | cpu
+  std::string variant = "auto";       // auto | oneshot | twoshot | nvls
+  DataType wire_dtype = DataType::FLOAT32;  // FLOAT32 = no compression
+  size_t symm_buffer_bytes = 128ull << 20;
+  bool want_multicast = true;
+};
+
+class GpuOps {
+ public:
+  explicit GpuOps(GpuOpEnv env) : env_(std::move(env)) {}
+  GpuOpEnv& env() { return env_; }
+  // Each op enqueues its kernels on the hvd stream and returns a shared
+  // completion event in *done (refs preset to entries.size()).
+  Status Allreduce(ProcessSet& ps, Entries& es, const Response& r, SharedEvent** done);
+  Status Adasum(ProcessSet& ps, Entries& es, const Response& r, SharedEvent** done);
+  Status Allgather(ProcessSet& ps, Entries& es, const Response& r, SharedEvent** done);
+  Status Broadcast(ProcessSet& ps, Entries& es, const Response& r, SharedEvent** done);
+  Status Alltoall(ProcessSet& ps, Entries& es, const Response& r, SharedEvent** done);
+  Status Reducescatter(ProcessSet& ps, Entries& es, const Response& r, SharedEvent** done);
+  // Description of the data path chosen for a set (for hvd.gpu_backend_info()).
+  std::string Describe(ProcessSet& ps);
+
+ private:
+  std::shared_ptr<SymmTeam> EnsureTeam(ProcessSet& ps, int device);
+  Status NcclAllreduce(ProcessSet& ps, Entries& es, const Response& r, int device, cudaStream_t s);
+  Status StagedOnHost(ProcessSet& ps, Entries& es, const Response& r, int device, cudaStream_t s);
+  // returns InProgress() when the kernel path does not apply (caller falls back to host staging)
+  Status AdasumP2P(ProcessSet& ps, SymmTeam& team, Entries& es, const Response& r, const std::vector<int64_t>& counts,
+                   int device, cudaStream_t s);
+  GpuOpEnv env_;
+  uint64_t team_counter_ = 0;
+};
+
+// Row split of dim 0 for reducescatter: the first dim0 % size ranks get one extra row
+// (reference ops/collective_operations.cc:314-330).
+inline void ReducescatterRows(int64_t dim0, int size, std::vector<int64_t>* rows) {
+  rows->assign(size, dim0 / size);
+  for (int i = 0; i < dim0 % size; ++i) (*rows)[i]++;
+}
+
+}  // namespace hvd

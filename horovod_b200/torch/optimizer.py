@@ -1,0 +1,509 @@
+"""DistributedOptimizer: wraps any torch optimizer so that gradients are
+allreduced (averaged) across ranks while the backward pass is still running.
+
+API parity: horovod/torch/optimizer.py (DistributedOptimizer factory,
+_DistributedOptimizer, _DistributedAdasumOptimizer).  Mechanism differences:
+hooks use `register_post_accumulate_grad_hook` (fires right after AccumulateGrad
+with no autograd-graph surgery), completion is event-chained (no host sync per
+tensor), and `fused=True` replaces the wrapped SGD/Adam(W) math by one
+multi-tensor sm_100a kernel (csrc/kernels/optim_kernels.cu).
+"""
+import warnings
+from contextlib import contextmanager
+
+import torch
+
+from horovod_b200.common.process_sets import global_process_set
+from horovod_b200.common.util import split_list
+from horovod_b200.torch import mpi_ops
+from horovod_b200.torch.compression import Compression
+from horovod_b200.torch.functions import broadcast_object
+from horovod_b200.torch.mpi_ops import (Adasum, Average, Sum, allreduce_async_, grouped_allreduce_async_, rank, size,
+                                        synchronize)
+
+
+class _DistributedOptimizer(torch.optim.Optimizer):
+    def __init__(self, params, named_parameters, compression, backward_passes_per_step=1, op=Average,
+                 gradient_predivide_factor=1.0, groups=None, sparse_as_dense=False, process_set=global_process_set,
+                 fused=False):
+        super(self.__class__, self).__init__(params)
+        self._compression = compression
+
+        if named_parameters is not None:
+            named_parameters = list(named_parameters)
+        else:
+            named_parameters = [(f'allreduce.noname.{i}.{j}', v)
+                                for i, param_group in enumerate(self.param_groups)
+                                for j, v in enumerate(param_group['params'])]
+        # make sure that named_parameters are tuples
+        if any([not isinstance(p, tuple) for p in named_parameters]):
+            raise ValueError('named_parameters should be a sequence of tuples (name, parameter), usually produced by '
+                             'model.named_parameters().')
+        dups = _find_duplicates([k for k, _ in named_parameters])
+        if len(dups) > 0:
+            raise ValueError('Parameter names in named_parameters must be unique. Found duplicates: %s' % ', '.join(dups))
+        all_param_ids = {id(v) for param_group in self.param_groups for v in param_group['params']}
+        named_param_ids = {id(v) for k, v in named_parameters}
+        unnamed_param_ids = all_param_ids - named_param_ids
+        if len(unnamed_param_ids):
+            raise ValueError('named_parameters was specified, but one or more model parameters were not named. Python '
+                             'object ids: %s' % ', '.join(str(id) for id in unnamed_param_ids))
+
+        self._parameter_names = {v: k for k, v in sorted(named_parameters)}
+        self.backward_passes_per_step = backward_passes_per_step
+        self._allreduce_delay = {v: self.backward_passes_per_step for _, v in sorted(named_parameters)}
+        self.op = op
+        self.gradient_predivide_factor = gradient_predivide_factor
+        self.sparse_as_dense = sparse_as_dense
+        self.process_set = process_set
+        self._fused = fused
+        self._fused_steps = 0
+
+        self._handles = {}
+        self._grad_accs = []
+        self._requires_update = set()
+        self._synchronized = False
+        self._should_synchronize = True
+
+        self._num_groups = None
+        self._groups = None
+        if groups is not None:
+            if not (isinstance(groups, list) or groups > 0):
+                raise ValueError('groups should be a non-negative integer or a list of list of torch.Tensor.')
+            if isinstance(groups, list):
+                grouped_parameter_ids = set()
+                for l in groups:
+                    for p in l:
+                        if not isinstance(p, torch.Tensor):
+                            raise ValueError('groups must consist of torch.Tensor.')
+                        if id(p) in grouped_parameter_ids:
+                            raise ValueError('A parameter can only appear once in groups.')
+                        grouped_parameter_ids.add(id(p))
+                self._groups = groups
+            else:
+                self._num_groups = groups
+        self._p_to_group = {}
+        self._group_counts = {}
+        self._group_handles = {}
+
+        if self.process_set.included() and (size() > 1 or True):
+            self._register_hooks()
+
+    # -- reference API ----------------------------------------------------------
+    def load_state_dict(self, *args, **kwargs):
+        self._handles = {}
+        self._synchronized = False
+        self._should_synchronize = True
+        for p in self._allreduce_delay:
+            self._allreduce_delay[p] = self.backward_passes_per_step
+        super(self.__class__, self).load_state_dict(*args, **kwargs)
+
+    @staticmethod
+    def find_duplicates(lst):
+        return _find_duplicates(lst)
+
+    def set_backward_passes_per_step(self, passes):
+        self.backward_passes_per_step = passes
+        for p in self._allreduce_delay:
+            self._allreduce_delay[p] = self.backward_passes_per_step
+
+    def _register_hooks(self):
+        if self._groups is not None:
+            p_list = []
+            # identify how many gradients each group expects
+            for i, group in enumerate(self._groups):
+                for p in group:
+                    self._p_to_group[p] = group
+                    p_list.append(p)
+                self._group_counts[id(group)] = 0
+            for param_group in self.param_groups:
+                for p in param_group['params']:
+                    if p.requires_grad and p not in self._p_to_group:
+                        self._p_to_group[p] = [p]
+                        self._group_counts[id(self._p_to_group[p])] = 0
+        elif self._num_groups:
+            p_list = []
+            for param_group in self.param_groups:
+                for p in param_group['params']:
+                    if p.requires_grad:
+                        p_list.append(p)
+            # rank-consistent grouping: order by name everywhere
+            p_list = sorted(p_list, key=lambda p: self._parameter_names.get(p))
+            self._groups = [list(g) for g in split_list(p_list, self._num_groups)]
+            for group in self._groups:
+                for p in group:
+                    self._p_to_group[p] = group
+                self._group_counts[id(group)] = 0
+
+        for param_group in self.param_groups:
+            for p in param_group['params']:
+                if p.requires_grad:
+                    self._requires_update.add(p)
+                    self._grad_accs.append(p.register_post_accumulate_grad_hook(self._make_hook(p)))
+
+    def _allreduce_grad_async(self, p):
+        if p.grad is None:
+            # gradient was not computed on this rank but the peers will reduce it: contribute zeros
+            p.grad = p.data.new_zeros(p.shape)
+        name = self._parameter_names.get(p)
+        tensor = p.grad
+        if tensor.is_sparse:
+            if self.sparse_as_dense:
+                tensor = tensor.to_dense()
+                p.grad = tensor
+            else:
+                return mpi_ops.sparse_allreduce_async(tensor, name=name, op=self.op, process_set=self.process_set), None
+        tensor_compressed, ctx = self._compression.compress(tensor)
+        if self.op == Average:
+            # split the averaging into pre- and post-division around the sum (reference optimizer.py:197-204)
+            prescale_factor = 1.0 / self.gradient_predivide_factor
+            postscale_factor = self.gradient_predivide_factor
+        else:
+            prescale_factor = 1.0
+            postscale_factor = 1.0
+        handle = allreduce_async_(tensor_compressed, name=name, op=self.op, prescale_factor=prescale_factor,
+                                  postscale_factor=postscale_factor, process_set=self.process_set)
+        return handle, ctx
+
+    def _grouped_allreduce_grad_async(self, ps):
+        name = self._parameter_names.get(ps[0])
+        for p in ps:
+            if p.grad is None:
+                p.grad = p.data.new_zeros(p.shape)
+        tensors_compressed, ctxs = zip(*[self._compression.compress(p.grad) for p in ps])
+        if self.op == Average:
+            prescale_factor = 1.0 / self.gradient_predivide_factor
+            postscale_factor = self.gradient_predivide_factor
+        else:
+            prescale_factor = 1.0
+            postscale_factor = 1.0
+        handle = grouped_allreduce_async_(list(tensors_compressed), name=name, op=self.op, prescale_factor=prescale_factor,
+                                          postscale_factor=postscale_factor, process_set=self.process_set)
+        return handle, ctxs
+
+    def _launch_group(self, group):
+        handle, ctxs = self._grouped_allreduce_grad_async(group)
+        self._group_handles[handle] = (group, ctxs)
+        for gp in group:
+            self._handles[gp] = (handle, None)
+        self._group_counts[id(group)] = 0
+
+    def _make_hook(self, p):
+        def hook(*ignore):
+            if p in self._handles and self._handles[p][0] is not None:
+                if self._allreduce_delay[p] <= 0:
+                    raise AssertionError(
+                        "Gradients were computed more than backward_passes_per_step times before call to step(). "
+                        "Increase backward_passes_per_step to accumulate gradients locally.")
+            assert not p.grad.requires_grad
+            assert self._allreduce_delay[p] > 0
+            handle, ctx = None, None
+            self._allreduce_delay[p] -= 1
+            if self._allreduce_delay[p] == 0:
+                if self._groups is not None:
+                    group = self._p_to_group[p]
+                    self._group_counts[id(group)] += 1
+                    if self._group_counts[id(group)] == len(group):
+                        self._launch_group(group)
+                        return
+                else:
+                    handle, ctx = self._allreduce_grad_async(p)
+            self._handles[p] = (handle, ctx)
+        return hook
+
+    def synchronize(self):
+        """Waits for every outstanding gradient allreduce (enqueueing the ones whose hook never fired so that all
+        ranks stay in lock-step) and writes the reduced gradients back."""
+        if not self.process_set.included():
+            self._synchronized = True
+            return
+        pending = [p for p in self._requires_update if p not in self._handles]
+        pending += [p for p, (h, _) in self._handles.items() if h is None]
+        if self._groups is not None:
+            launched = set()
+            for p in pending:
+                group = self._p_to_group[p]
+                if id(group) not in launched:
+                    launched.add(id(group))
+                    self._launch_group(group)
+        else:
+            for p in pending:
+                self._handles[p] = self._allreduce_grad_async(p)
+
+        waited = set()
+        for p, (handle, ctx) in self._handles.items():
+            if handle in self._group_handles:
+                if handle in waited:
+                    continue
+                waited.add(handle)
+                group, ctxs = self._group_handles[handle]
+                outputs = synchronize(handle)
+                for gp, out, c in zip(group, outputs, ctxs):
+                    self._allreduce_delay[gp] = self.backward_passes_per_step
+                    if out is not gp.grad:
+                        gp.grad.set_(self._compression.decompress(out, c))
+                continue
+            output = synchronize(handle)
+            self._allreduce_delay[p] = self.backward_passes_per_step
+            if p.grad.is_sparse:
+                aggregated = self._compression.decompress(output, ctx)
+                if not aggregated.is_sparse:
+                    aggregated = aggregated.to_sparse()
+                p.grad = aggregated
+            elif output is not None and output is not p.grad:
+                p.grad.set_(self._compression.decompress(output, ctx))
+        self._handles.clear()
+        self._group_handles.clear()
+        self._synchronized = True
+
+    @contextmanager
+    def skip_synchronize(self):
+        """Use after an explicit optimizer.synchronize() (e.g. gradient clipping) so step() does not sync again."""
+        self._should_synchronize = False
+        try:
+            yield
+        finally:
+            self._should_synchronize = True
+
+    def _hvd_super_step(self, closure=None):
+        return super(self.__class__, self).step(closure)
+
+    def step(self, closure=None):
+        if self._should_synchronize:
+            if self._synchronized:
+                warnings.warn("optimizer.step() called without optimizer.skip_synchronize() context after "
+                              "optimizer.synchronize(). This can cause training slowdown. You may want to consider "
+                              "using optimizer.skip_synchronize() context if you use optimizer.synchronize() in your "
+                              "code.")
+            self.synchronize()
+        self._synchronized = False
+        if self._fused and closure is None and _fused_step(self):
+            return None
+        return super(self.__class__, self).step(closure)
+
+    def zero_grad(self, *args, **kwargs):
+        if self._handles:
+            raise AssertionError("optimizer.zero_grad() was called after loss.backward() but before optimizer.step() or "
+                                 "optimizer.synchronize(). This is prohibited as it can cause a race condition.")
+        return super(self.__class__, self).zero_grad(*args, **kwargs)
+
+
+def _find_duplicates(lst):
+    seen = set()
+    dups = set()
+    for el in lst:
+        if el in seen:
+            dups.add(el)
+        seen.add(el)
+    return dups
+
+
+def _fused_step(opt):
+    """One multi-tensor kernel for the whole model when the wrapped optimizer is SGD or Adam/AdamW on CUDA."""
+    native = mpi_ops._native()
+    base = opt.__class__.__mro__[1] if len(opt.__class__.__mro__) > 1 else None
+    is_sgd = isinstance(opt, torch.optim.SGD)
+    is_adam = isinstance(opt, (torch.optim.Adam, torch.optim.AdamW))
+    if not (is_sgd or is_adam):
+        return False
+    with torch.no_grad():
+        for group in opt.param_groups:
+            params = [p for p in group['params'] if p.grad is not None]
+            if not params:
+                continue
+            if not all(p.is_cuda and p.is_contiguous() and p.grad.is_contiguous() and not p.grad.is_sparse for p in params):
+                return False
+            by_dtype = {}
+            for p in params:
+                by_dtype.setdefault((p.dtype, p.grad.dtype), []).append(p)
+            for (_, _), ps in by_dtype.items():
+                grads = [p.grad for p in ps]
+                if is_sgd:
+                    mom = group.get('momentum', 0.0)
+                    bufs, first = [], False
+                    if mom != 0.0:
+                        for p in ps:
+                            st = opt.state[p]
+                            if st.get('momentum_buffer') is None:
+                                st['momentum_buffer'] = torch.zeros_like(p)
+                                first = True
+                            bufs.append(st['momentum_buffer'])
+                        if first and any(opt.state[p].get('_hvd_init') for p in ps):
+                            return False
+                        for p in ps:
+                            opt.state[p]['_hvd_init'] = True
+                    if group.get('maximize', False):
+                        return False
+                    native.fused_sgd_step(ps, grads, bufs, float(group['lr']), float(mom), float(group.get('dampening', 0.0)),
+                                          float(group.get('weight_decay', 0.0)), bool(group.get('nesterov', False)), 1.0, first)
+                else:
+                    if group.get('amsgrad', False) or group.get('maximize', False):
+                        return False
+                    exp_avg, exp_avg_sq = [], []
+                    step = None
+                    for p in ps:
+                        st = opt.state[p]
+                        if len(st) == 0 or 'exp_avg' not in st:
+                            st['step'] = torch.tensor(0.0)
+                            st['exp_avg'] = torch.zeros_like(p, dtype=torch.float32)
+                            st['exp_avg_sq'] = torch.zeros_like(p, dtype=torch.float32)
+                        st['step'] = st['step'] + 1
+                        step = int(st['step'].item()) if torch.is_tensor(st['step']) else int(st['step'])
+                        exp_avg.append(st['exp_avg'])
+                        exp_avg_sq.append(st['exp_avg_sq'])
+                    b1, b2 = group['betas']
+                    adamw = isinstance(opt, torch.optim.AdamW) or bool(group.get('decoupled_weight_decay', False))
+                    native.fused_adam_step(ps, grads, exp_avg, exp_avg_sq, float(group['lr']), float(b1), float(b2),
+                                           float(group['eps']), float(group.get('weight_decay', 0.0)), step, 1.0, adamw)
+    return True
+
+
+class _DistributedAdasumOptimizer(torch.optim.Optimizer):
+    """Adasum works on parameter *deltas*: each parameter's hook runs the wrapped optimizer on that parameter only,
+    allreduces delta = p_new - p_start with op=Adasum and step() applies start + adasum(delta).
+    (reference horovod/torch/optimizer.py:345-513)"""
+
+    def __init__(self, params, named_parameters, compression, backward_passes_per_step=1):
+        super(self.__class__, self).__init__(params)
+        self._compression = compression
+        if named_parameters is not None:
+            named_parameters = list(named_parameters)
+        else:
+            named_parameters = [(f'allreduce.noname.{i}.{j}', v)
+                                for i, param_group in enumerate(self.param_groups)
+                                for j, v in enumerate(param_group['params'])]
+        all_param_ids = {id(v) for param_group in self.param_groups for v in param_group['params']}
+        named_param_ids = {id(v) for k, v in named_parameters}
+        unnamed_param_ids = all_param_ids - named_param_ids
+        if len(unnamed_param_ids):
+            raise ValueError('named_parameters was specified, but one or more model parameters were not named. Python '
+                             'object ids: %s' % ', '.join(str(id) for id in unnamed_param_ids))
+        self._parameter_names = {v: k for k, v in sorted(named_parameters)}
+        self.backward_passes_per_step = backward_passes_per_step
+        self._allreduce_delay = {v: self.backward_passes_per_step for _, v in sorted(named_parameters)}
+        self._handles = {}
+        self._grad_accs = []
+        self._requires_update = set()
+        self._synchronized = False
+        self._should_synchronize = True
+        self._starting_models = {p: torch.zeros_like(p, requires_grad=False) for _, p in named_parameters}
+        self._register_hooks()
+
+    def set_backward_passes_per_step(self, passes):
+        self.backward_passes_per_step = passes
+        for p in self._allreduce_delay:
+            self._allreduce_delay[p] = self.backward_passes_per_step
+
+    def _register_hooks(self):
+        for param_group in self.param_groups:
+            for p in param_group['params']:
+                if p.requires_grad:
+                    self._requires_update.add(p)
+                    self._grad_accs.append(p.register_post_accumulate_grad_hook(self._make_hook(p)))
+
+    def _allreduce_grad_async(self, p):
+        # run the wrapped optimizer on this parameter alone
+        name = self._parameter_names.get(p)
+        if p.grad is None:
+            p.grad = p.data.new_zeros(p.shape)
+        stashed_params = []
+        for group in self.param_groups:
+            stashed_params.append(group['params'])
+            if any(p is v for v in group['params']):
+                group['params'] = [p]
+            else:
+                group['params'] = []
+        start = self._starting_models[p]
+        start.data.copy_(p)
+        super(self.__class__, self).step()
+        p.data.sub_(start)  # p now holds the local delta
+        tensor_compressed, ctx = self._compression.compress(p.data)
+        handle = allreduce_async_(tensor_compressed, name=name, op=Adasum)
+        for stashed, group in zip(stashed_params, self.param_groups):
+            group['params'] = stashed
+        return handle, ctx
+
+    def _make_hook(self, p):
+        def hook(*ignore):
+            if p in self._handles and self._handles[p][0] is not None:
+                if self._allreduce_delay[p] <= 0:
+                    raise AssertionError(
+                        "Gradients were computed more than backward_passes_per_step times before call to step(). "
+                        "Increase backward_passes_per_step to accumulate gradients locally.")
+            assert not p.grad.requires_grad
+            assert self._allreduce_delay[p] > 0
+            handle, ctx = None, None
+            self._allreduce_delay[p] -= 1
+            if self._allreduce_delay[p] == 0:
+                handle, ctx = self._allreduce_grad_async(p)
+            self._handles[p] = (handle, ctx)
+        return hook
+
+    def synchronize(self):
+        pass
+
+    @contextmanager
+    def skip_synchronize(self):
+        raise AssertionError("Skipping synchronization is not supported when using Adasum optimizer.")
+
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            loss = closure()
+        missing_p = self._requires_update - set(self._handles.keys())
+        for p in missing_p:
+            self._allreduce_delay[p] = 0
+            handle, ctx = self._allreduce_grad_async(p)
+            self._handles[p] = (handle, ctx)
+        for p, (handle, ctx) in self._handles.items():
+            if handle is None:
+                handle, ctx = self._allreduce_grad_async(p)
+                self._handles[p] = (handle, ctx)
+        for p, (handle, ctx) in self._handles.items():
+            delta = synchronize(handle)
+            delta = self._compression.decompress(delta, ctx)
+            start = self._starting_models[p]
+            start.data.add_(delta.data)
+            p.data.copy_(start)
+            self._allreduce_delay[p] = self.backward_passes_per_step
+        self._handles.clear()
+        return loss
+
+    def zero_grad(self, *args, **kwargs):
+        if self._handles:
+            raise AssertionError("optimizer.zero_grad() was called after loss.backward() but before optimizer.step() or "
+                                 "optimizer.synchronize(). This is prohibited as it can cause a race condition.")
+        return super(self.__class__, self).zero_grad(*args, **kwargs)
+
+
+def DistributedOptimizer(optimizer, named_parameters=None, compression=Compression.none, backward_passes_per_step=1,
+                         op=Average, gradient_predivide_factor=1.0, num_groups=0, groups=None, sparse_as_dense=False,
+                         process_set=global_process_set, fused=False):
+    """Wraps `optimizer` so gradients are combined across ranks before the parameter update.
+
+    Arguments follow the reference (horovod/torch/optimizer.py:516-608). `fused=True` (new) runs the SGD /
+    Adam(W) update as one multi-tensor CUDA kernel."""
+    if gradient_predivide_factor != 1.0:
+        if rocm_built_safe():
+            raise ValueError('gradient_predivide_factor not supported yet with ROCm')
+        if op != Average:
+            raise ValueError('gradient_predivide_factor not supported with op != Average')
+    if num_groups != 0:
+        warnings.warn('Parameter `num_groups` has been replaced by `groups` and will be removed', DeprecationWarning)
+        if groups is None:
+            groups = num_groups
+    if op != Adasum or size() == 1:
+        cls = type(optimizer.__class__.__name__, (optimizer.__class__,), dict(_DistributedOptimizer.__dict__))
+        return cls(optimizer.param_groups, named_parameters, compression, backward_passes_per_step, op,
+                   gradient_predivide_factor, groups, sparse_as_dense, process_set, fused)
+    if process_set != global_process_set:
+        raise NotImplementedError("Adasum does not support non-global process sets yet.")
+    cls = type(optimizer.__class__.__name__, (optimizer.__class__,), dict(_DistributedAdasumOptimizer.__dict__))
+    return cls(optimizer.param_groups, named_parameters, compression, backward_passes_per_step)
+
+
+def rocm_built_safe():
+    try:
+        return mpi_ops.rocm_built()
+    except Exception:
+        return False
