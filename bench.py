@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""Headline benchmark: synthetic ResNet-50 training throughput with hvd.DistributedOptimizer — the reference's own
+benchmark (examples/pytorch/pytorch_synthetic_benchmark.py: torchvision-shape resnet50, SGD, op=Average, fixed random
+batch) — device-timed, max over ranks.  Also drives BERT-large / GPT-2-medium and the allreduce bandwidth sweep
+(`--model bert-large|gpt2-medium`, `--bench allreduce`).
+
+    python bench.py                               # 1 GPU
+    torchrun --nproc-per-node 8 bench.py --gpus 8 # 8 GPUs, one process per GPU
+
+Prints ONE JSON line on rank 0 (see the contract in the task description).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument('--gpus', type=int, default=1)
+    p.add_argument('--steps', type=int, default=30)
+    p.add_argument('--warmup', type=int, default=5)
+    p.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    p.add_argument('--model', default='resnet50', choices=['resnet50', 'bert-large', 'gpt2-medium'])
+    p.add_argument('--bench', default='train', choices=['train', 'allreduce'])
+    p.add_argument('--batch-size', type=int, default=None, help='per-GPU batch (default: 64 resnet50, 8 bert-large seq 512, 4 gpt2-medium seq 1024)')
+    p.add_argument('--seq-len', type=int, default=None)
+    p.add_argument('--no-fused-optimizer', action='store_true')
+    p.add_argument('--op', default='average', choices=['average', 'adasum'])
+    p.add_argument('--fp32', action='store_true', help='disable bf16 autocast')
+    p.add_argument('--sizes', default=None, help='allreduce sweep: comma separated byte sizes')
+    p.add_argument('--dtype', default='fp32', help='allreduce sweep dtype: fp32|bf16|fp16')
+    return p.parse_args()
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+        self.thread = None
+
+    def start(self):
+        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits',
+                                          '-lms', '200'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for l in self.lines:
+            f = [x.strip() for x in l.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def reference_arm(args):
+    """The unmodified reference cannot be installed offline (see DESIGN.md 'Reference install attempt'):
+    third_party/{gloo,flatbuffers,boost,eigen,lbfgs,HTTPRequest} are empty and there is no MPI."""
+    ref = os.path.join(ROOT, 'baseline', '_ref')
+    sys.path.insert(0, ref)
+    try:
+        import horovod.torch as ref_hvd  # noqa: F401
+    except Exception as e:
+        print(json.dumps({'impl': 'reference', 'unavailable':
+                          'horovod 0.28.1 does not build offline: third_party/gloo (and flatbuffers/boost/eigen/lbfgs) '
+                          'submodules are empty in /root/reference and no MPI is installed (cmake: add_subdirectory '
+                          'third_party/gloo has no CMakeLists.txt); import error: %s' % type(e).__name__}))
+        return 0
+    print(json.dumps({'impl': 'reference', 'unavailable': 'reference import unexpectedly succeeded but no driver is wired'}))
+    return 0
+
+
+def build_model(args, torch):
+    from horovod_b200 import models
+    if args.model == 'resnet50':
+        bs = args.batch_size or 64
+        model = models.resnet50().cuda().to(memory_format=torch.channels_last)
+
+        def make_batch(device):
+            x = torch.randn(bs, 3, 224, 224, device=device)
+            y = torch.randint(0, 1000, (bs,), device=device)
+            return (x, y)
+
+        def step_fn(batch):
+            x, y = batch
+            x = x.contiguous(memory_format=torch.channels_last)
+            return torch.nn.functional.cross_entropy(model(x), y)
+
+        return model, make_batch, step_fn, bs, None, 'images/sec'
+    if args.model == 'bert-large':
+        bs = args.batch_size or 8
+        seq = args.seq_len or 512
+        model = models.bert_large().cuda()
+
+        def make_batch(device):
+            ids = torch.randint(0, 30522, (bs, seq), device=device)
+            labels = torch.where(torch.rand(bs, seq, device=device) < 0.15, ids, torch.full_like(ids, -100))
+            nsp = torch.randint(0, 2, (bs,), device=device)
+            return (ids, labels, nsp)
+
+        def step_fn(batch):
+            ids, labels, nsp = batch
+            return model(ids, labels=labels, next_sentence_label=nsp)
+
+        return model, make_batch, step_fn, bs, seq, 'samples/sec'
+    bs = args.batch_size or 4
+    seq = args.seq_len or 1024
+    model = models.gpt2_medium().cuda()
+
+    def make_batch(device):
+        ids = torch.randint(0, 50257, (bs, seq), device=device)
+        return (ids,)
+
+    def step_fn(batch):
+        return model(batch[0], labels=batch[0])
+
+    return model, make_batch, step_fn, bs, seq, 'samples/sec'
+
+
+def train_bench(args):
+    import torch
+    import horovod_b200.torch as hvd
+
+    hvd.init()
+    rank, size = hvd.rank(), hvd.size()
+    local_rank = hvd.local_rank()
+    torch.cuda.set_device(local_rank)
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    model, make_batch, step_fn, bs, seq, unit = build_model(args, torch)
+    use_bf16 = not args.fp32
+    lr_scaler = size if args.op == 'average' else 1
+    if args.model == 'resnet50':
+        base_opt = torch.optim.SGD(model.parameters(), lr=0.01 * lr_scaler, momentum=0.9)
+    else:
+        base_opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01)
+    op = hvd.Average if args.op == 'average' else hvd.Adasum
+    opt = hvd.DistributedOptimizer(base_opt, named_parameters=model.named_parameters(), op=op,
+                                   fused=not args.no_fused_optimizer)
+    hvd.broadcast_parameters(model.state_dict(), root_rank=0)
+    hvd.broadcast_optimizer_state(opt, root_rank=0)
+    model.train()
+
+    dev_batch = make_batch('cuda')  # fixed synthetic batch on the device (as the reference benchmark does)
+    host_batch = tuple(t.cpu().pin_memory() for t in dev_batch)  # the e2e arm copies this every step
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host_batch)
+
+    def one_step(batch):
+        opt.zero_grad(set_to_none=False)
+        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=use_bf16):
+            loss = step_fn(batch)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def timed(nsteps, e2e):
+        hvd.barrier()
+        torch.cuda.synchronize()
+        k0 = hvd.runtime_stats()['kernel_launches']
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for _ in range(nsteps):
+            if e2e:
+                batch = tuple(t.cuda(non_blocking=True) for t in host_batch)
+                last = one_step(batch).item()  # device -> host read of the step's result
+            else:
+                last = one_step(dev_batch)
+        e1.record()
+        torch.cuda.synchronize()
+        hvd.barrier()
+        ms = e0.elapsed_time(e1)
+        k1 = hvd.runtime_stats()['kernel_launches']
+        # max over ranks
+        t = torch.tensor([ms], dtype=torch.float64)
+        ms = hvd.allreduce(t, op=hvd.Max, name='bench.ms').item()
+        return ms, k1 - k0, last
+
+    for _ in range(max(3, args.warmup)):
+        one_step(dev_batch)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, launches, _ = timed(args.steps, e2e=False)
+    clocks = sampler.stop() if sampler else None
+    # end-to-end arm: H2D of the inputs from pinned memory + D2H read of the loss inside the timed region
+    for _ in range(2):
+        one_step(tuple(t.cuda(non_blocking=True) for t in host_batch)).item()
+    e2e_ms, _, last_loss = timed(args.steps, e2e=True)
+
+    global_batch = bs * size
+    value = global_batch * args.steps / (ms / 1e3)
+    e2e_value = global_batch * args.steps / (e2e_ms / 1e3)
+    if rank == 0:
+        out = {
+            'metric': f'{args.model} synthetic training throughput, hvd.DistributedOptimizer op={args.op} (whole job)',
+            'value': round(value, 2), 'unit': unit, 'n_gpus': size, 'steps': args.steps, 'warmup': max(3, args.warmup),
+            'ms_per_step': round(ms / args.steps, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16' if use_bf16 else 'fp32(tf32)', 'data': 'synthetic (random images/tokens, random-init weights)',
+            'impl': 'ours',
+            'config': {'model': args.model, 'global_batch': global_batch, 'per_gpu_batch': bs, 'seq_len': seq,
+                       'parallelism': f'dp{size}', 'optimizer': 'SGD(momentum=0.9)' if args.model == 'resnet50' else 'AdamW',
+                       'fused_optimizer': not args.no_fused_optimizer, 'grad_dtype': 'fp32',
+                       'l2': 'per-step working set (activations + 100+ MB of gradients) exceeds the 126 MB L2; no explicit flush',
+                       'gpu_backend': hvd.gpu_backend_info(), 'tunables': hvd.tunable_params()},
+            'clocks': clocks,
+            'e2e': {'value': round(e2e_value, 2), 'unit': unit, 'ms_per_step': round(e2e_ms / args.steps, 3),
+                    'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4, 'last_loss': last_loss},
+            'gpu_launches': int(launches),
+        }
+        print(json.dumps(out), flush=True)
+    hvd.shutdown()
+    return 0
+
+
+def allreduce_bench(args):
+    """Bus bandwidth sweep: busBW = algBW * 2(N-1)/N, device-timed, max over ranks."""
+    import torch
+    import horovod_b200.torch as hvd
+
+    hvd.init()
+    rank, size = hvd.rank(), hvd.size()
+    torch.cuda.set_device(hvd.local_rank())
+    dt = {'fp32': torch.float32, 'bf16': torch.bfloat16, 'fp16': torch.float16}[args.dtype]
+    sizes = [int(s) for s in args.sizes.split(',')] if args.sizes else [1 << p for p in range(10, 31, 2)]
+    rows = []
+    for nbytes in sizes:
+        n = max(1, nbytes // torch.tensor([], dtype=dt).element_size())
+        x = torch.randn(n, device='cuda').to(dt)
+        iters = max(5, min(200, int(2e9 // max(nbytes, 1 << 16))))
+        for _ in range(5):
+            hvd.allreduce_(x, op=hvd.Sum, name=f'sweep.{nbytes}')
+        hvd.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            hvd.allreduce_(x, op=hvd.Sum, name=f'sweep.{nbytes}')
+        e1.record()
+        torch.cuda.synchronize()
+        ms = hvd.allreduce(torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64), op=hvd.Max, name='sweep.ms').item()
+        alg = nbytes / (ms / 1e3) / 1e9
+        rows.append({'bytes': nbytes, 'us': round(ms * 1e3, 2), 'algbw_gbs': round(alg, 2),
+                     'busbw_gbs': round(alg * 2 * (size - 1) / max(size, 1), 2)})
+    if rank == 0:
+        best = max(r['busbw_gbs'] for r in rows) if rows else 0.0
+        print(json.dumps({'metric': 'allreduce bus bandwidth sweep', 'value': best, 'unit': 'GB/s (peak busBW)', 'n_gpus': size,
+                          'higher_is_better': True, 'dtype': args.dtype, 'impl': 'ours', 'rows': rows,
+                          'config': {'gpu_backend': hvd.gpu_backend_info(), 'tunables': hvd.tunable_params(),
+                                     'roofline_gbs_per_dir': 900, 'measured_peer_copy_gbs': 770}}), flush=True)
+    hvd.shutdown()
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        return reference_arm(args)
+    if args.bench == 'allreduce':
+        return allreduce_bench(args)
+    return train_bench(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

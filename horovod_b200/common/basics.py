@@ -303,7 +303,7 @@ class HorovodBasics(object):
 
     def runtime_stats(self):
         return {'cycles': int(self.lib.hvd_stat(0)), 'idle_cycles': int(self.lib.hvd_stat(1)),
-                'responses': int(self.lib.hvd_stat(2))}
+                'responses': int(self.lib.hvd_stat(2)), 'kernel_launches': int(self.lib.hvd_stat(3))}
 
     def tunable_params(self):
         names = ['fusion_threshold_bytes', 'cycle_time_us', 'cache_enabled', 'oneshot_max_bytes', 'nvls_min_bytes',

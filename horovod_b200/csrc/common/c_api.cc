@@ -5,6 +5,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include "../kernels/p2p_kernels.h"
 #include "../symm/symm_memory.h"
 #include "engine.h"
 #include "env.h"
@@ -132,6 +133,7 @@ unsigned long long hvd_stat(int which) {
     case 0: return e.cycles();
     case 1: return e.fast_path_cycles();
     case 2: return e.responses_executed();
+    case 3: return kern::KernelLaunchCount();
     default: return 0;
   }
 }

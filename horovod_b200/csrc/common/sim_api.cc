@@ -1,0 +1,115 @@
+// Single-GPU simulation harness for the P2P kernels: N "ranks" are N plain
+// allocations on one device and N concurrently launched kernels on N streams.
+// The cross-"GPU" flag protocol, chunk ownership and descriptor walking are
+// exactly what runs across NVLink; only the address mapping differs.  Lets the
+// kernels be validated (and run under compute-sanitizer) on one B200.
+#include <cuda_runtime.h>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <vector>
+#include "../kernels/p2p_kernels.h"
+#include "../ops/gpu_ops.h"
+#include "../symm/symm_memory.h"
+
+using namespace hvd;
+
+namespace {
+struct Sim {
+  std::vector<std::shared_ptr<SymmTeam>> teams;
+  std::vector<cudaStream_t> streams;
+  size_t bytes = 0;
+};
+std::map<int, Sim> g_sims;  // by nranks
+
+Sim* GetSim(int nranks, int device, size_t buffer_bytes) {
+  Sim& s = g_sims[nranks];
+  if (s.teams.empty() || s.bytes < buffer_bytes) {
+    s.teams = SymmTeam::CreateSimulated(nranks, device, buffer_bytes);
+    s.bytes = buffer_bytes;
+    if (s.teams.empty()) return nullptr;
+    for (auto st : s.streams) cudaStreamDestroy(st);
+    s.streams.assign(nranks, nullptr);
+    for (int r = 0; r < nranks; ++r) cudaStreamCreateWithFlags(&s.streams[r], cudaStreamNonBlocking);
+  }
+  return &s;
+}
+int64_t Align128(int64_t b) { return (b + 127) / 128 * 128; }
+}  // namespace
+
+extern "C" {
+
+// in_ptrs/out_ptrs: [nranks][ntensors] device pointers. Returns 0 on success, else a cudaError_t (or -1).
+int hvd_sim_allreduce(int nranks, int device, int ntensors, const int64_t* counts, const uint64_t* in_ptrs,
+                      const uint64_t* out_ptrs, int dtype, int wire_dtype, int op, int variant, int ctas, double prescale,
+                      double postscale, int repeats, float* ms_out) {
+  if (cudaSetDevice(device) != cudaSuccess) return -1;
+  const int64_t wsz = (int64_t)DataTypeSize((DataType)wire_dtype);
+  int64_t total = 0;
+  std::vector<int64_t> offs(ntensors);
+  for (int i = 0; i < ntensors; ++i) { offs[i] = total; total += Align128(counts[i] * wsz); }
+  Sim* sim = GetSim(nranks, device, (size_t)std::max<int64_t>(total, 1 << 20));
+  if (!sim) return -1;
+  std::vector<const kern::TensorDesc*> dtabs(nranks);
+  for (int r = 0; r < nranks; ++r) {
+    std::vector<kern::TensorDesc> d(ntensors);
+    for (int i = 0; i < ntensors; ++i) {
+      d[i].in = (const void*)in_ptrs[(size_t)r * ntensors + i];
+      d[i].out = (void*)out_ptrs[(size_t)r * ntensors + i];
+      d[i].offset = offs[i];
+      d[i].count = counts[i];
+    }
+    dtabs[r] = (const kern::TensorDesc*)GpuContext::Get().Stage(device, d.data(), d.size() * sizeof(kern::TensorDesc), sim->streams[r]);
+    if (!dtabs[r]) return -2;
+  }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaDeviceSynchronize();
+  cudaEventRecord(e0, sim->streams[0]);
+  for (int it = 0; it < repeats; ++it) {
+    for (int r = 0; r < nranks; ++r) {
+      kern::AllreduceArgs a {};
+      a.descs = dtabs[r]; a.ndesc = ntensors; a.total_bytes = total; a.reduce_lo = 0; a.reduce_hi = total;
+      a.prescale = prescale; a.postscale = postscale; a.op = op; a.dtype = dtype; a.wire_dtype = wire_dtype;
+      a.variant = variant; a.ctas = ctas;
+      kern::CommParams cp = sim->teams[r]->Params(sim->teams[r]->NextSlot());
+      cudaError_t e = kern::LaunchAllreduce(cp, a, sim->streams[r]);
+      if (e != cudaSuccess) return (int)e;
+    }
+  }
+  cudaEventRecord(e1, sim->streams[0]);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (ms_out) cudaEventElapsedTime(ms_out, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return (int)e;
+}
+
+// Allgather-style exchange: every rank contributes `bytes` from in_ptrs[r]; out_ptrs[r] receives nranks*bytes.
+int hvd_sim_allgather(int nranks, int device, int64_t bytes, const uint64_t* in_ptrs, const uint64_t* out_ptrs, int ctas) {
+  if (cudaSetDevice(device) != cudaSuccess) return -1;
+  Sim* sim = GetSim(nranks, device, (size_t)std::max<int64_t>(bytes, 1 << 20));
+  if (!sim) return -1;
+  for (int r = 0; r < nranks; ++r) {
+    std::vector<kern::CopyDesc> t;
+    t.push_back({(const void*)in_ptrs[r], nullptr, 0, bytes, r, 0});
+    for (int k = 0; k < nranks; ++k) {
+      int p = (r + k) % nranks;
+      t.push_back({nullptr, (char*)out_ptrs[r] + (int64_t)p * bytes, 0, bytes, p, 0});
+    }
+    const auto* dt = (const kern::CopyDesc*)GpuContext::Get().Stage(device, t.data(), t.size() * sizeof(kern::CopyDesc), sim->streams[r]);
+    if (!dt) return -2;
+    kern::ExchangeArgs a {};
+    a.sends = dt; a.nsend = 1; a.recvs = dt + 1; a.nrecv = nranks; a.ctas = ctas;
+    kern::CommParams cp = sim->teams[r]->Params(sim->teams[r]->NextSlot());
+    cudaError_t e = kern::LaunchExchange(cp, a, sim->streams[r]);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return (int)cudaDeviceSynchronize();
+}
+
+void hvd_sim_reset() {
+  for (auto& kv : g_sims) for (auto st : kv.second.streams) cudaStreamDestroy(st);
+  g_sims.clear();
+}
+
+}  // extern "C"

@@ -24,6 +24,10 @@
 namespace hvd {
 namespace kern {
 
+static unsigned long long g_launches = 0;
+unsigned long long KernelLaunchCount() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+void CountKernelLaunch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
 namespace {
 
 constexpr int kRowBytes = kThreads * 16;  // one 16 B vector per thread
@@ -334,6 +338,7 @@ cudaError_t launch_tw(const CommParams& cp, const AllreduceArgs& a, int chunk_by
   if (cp.nranks <= 2) allreduce_kernel<T, W, 2><<<grid, block, 0, s>>>(cp, a, chunk_bytes);
   else if (cp.nranks <= 4) allreduce_kernel<T, W, 4><<<grid, block, 0, s>>>(cp, a, chunk_bytes);
   else allreduce_kernel<T, W, 8><<<grid, block, 0, s>>>(cp, a, chunk_bytes);
+  CountKernelLaunch();
   return cudaGetLastError();
 }
 
@@ -341,6 +346,7 @@ template <typename T, typename W>
 cudaError_t launch_pu(char* buffer, const TensorDesc* descs, int nd, int64_t total, double scale, int dir, int ctas,
                       cudaStream_t s) {
   pack_unpack_kernel<T, W><<<ctas, kThreads, 0, s>>>(buffer, descs, nd, total, scale, dir);
+  CountKernelLaunch();
   return cudaGetLastError();
 }
 
@@ -393,6 +399,7 @@ template <typename T, typename W> cudaError_t launch_scale(const void* in, void*
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   scale_kernel<T><<<(int)blocks, kThreads, 0, s>>>((const T*)in, (T*)out, n, scale);
+  CountKernelLaunch();
   return cudaGetLastError();
 }
 }  // namespace

@@ -79,6 +79,7 @@ exchange_kernel(const __grid_constant__ CommParams cp, const __grid_constant__ E
 cudaError_t LaunchExchange(const CommParams& cp, const ExchangeArgs& args, cudaStream_t stream) {
   if (args.ctas < 1 || args.ctas > kMaxCtas) return cudaErrorInvalidValue;
   exchange_kernel<<<args.ctas, kThreads, 0, stream>>>(cp, args);
+  CountKernelLaunch();
   return cudaGetLastError();
 }
 

@@ -138,6 +138,7 @@ cudaError_t LaunchFusedSgd(const SgdTensor* table, int n, int64_t max_count, flo
   else if (param_dtype == 10 && grad_dtype == 10) fused_sgd_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, kOptThreads, 0, stream>>>(table, lr, momentum, dampening, weight_decay, nesterov, grad_scale, first_step);
   else if (param_dtype == 6 && grad_dtype == 6) fused_sgd_kernel<__half, __half><<<grid, kOptThreads, 0, stream>>>(table, lr, momentum, dampening, weight_decay, nesterov, grad_scale, first_step);
   else return cudaErrorInvalidValue;
+  CountKernelLaunch();
   return cudaGetLastError();
 }
 
@@ -150,6 +151,7 @@ cudaError_t LaunchFusedAdamW(const AdamTensor* table, int n, int64_t max_count, 
   else if (param_dtype == 7 && grad_dtype == 10) fused_adam_kernel<float, __nv_bfloat16><<<grid, kOptThreads, 0, stream>>>(table, lr, beta1, beta2, eps, weight_decay, bias_c1, bias_c2, grad_scale, adamw);
   else if (param_dtype == 10 && grad_dtype == 10) fused_adam_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, kOptThreads, 0, stream>>>(table, lr, beta1, beta2, eps, weight_decay, bias_c1, bias_c2, grad_scale, adamw);
   else return cudaErrorInvalidValue;
+  CountKernelLaunch();
   return cudaGetLastError();
 }
 

@@ -15,6 +15,10 @@
 namespace hvd {
 namespace kern {
 
+// number of kernels of this library launched by this process (bench.py reports it as gpu_launches)
+unsigned long long KernelLaunchCount();
+void CountKernelLaunch();
+
 constexpr int kMaxPeers = 8;          // one NVSwitch domain of the HGX B200 box
 constexpr int kMaxCtas = 128;         // flag slots per team
 constexpr int kThreads = 512;

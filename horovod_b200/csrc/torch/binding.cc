@@ -128,9 +128,15 @@ DataType MapDtype(at::ScalarType t) {
 
 int DeviceOf(const at::Tensor& t) { return t.is_cuda() ? (int)t.get_device() : CPU_DEVICE_ID; }
 
+// Unnamed ops are numbered per op type (not by handle: handle counters diverge between ranks as soon as one rank
+// issues an extra named op, e.g. around hvd.join(), and the names must match across ranks).
+std::mutex g_noname_mu;
+std::unordered_map<std::string, int> g_noname_counters;
 std::string OpName(const char* op, const std::string& name, int handle) {
+  (void)handle;
   if (!name.empty()) return std::string(op) + "." + name;
-  return std::string(op) + ".noname." + std::to_string(handle);
+  std::lock_guard<std::mutex> l(g_noname_mu);
+  return std::string(op) + ".noname." + std::to_string(g_noname_counters[op]++);
 }
 
 void ThrowIfError(const Status& st) {
@@ -386,7 +392,11 @@ int WaitAndClear(int h) {
   return joined;
 }
 
-void Reset() { g_handles.Reset(); }
+void Reset() {
+  g_handles.Reset();
+  std::lock_guard<std::mutex> l(g_noname_mu);
+  g_noname_counters.clear();
+}
 
 // ---- fused optimizer kernels (B200-native extra; see kernels/optim_kernels.cu) --------------
 void FusedSgdStep(std::vector<at::Tensor> params, std::vector<at::Tensor> grads, std::vector<at::Tensor> momenta, double lr,

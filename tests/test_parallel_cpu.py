@@ -1,0 +1,53 @@
+"""np=2 (and 3, 4) CPU runs of the distributed op matrix through our own launcher — the "plumbing" config of
+BASELINE.json (`synthetic allreduce correctness world_size=2 on CPU`)."""
+import pytest
+
+from conftest import run_parallel
+
+
+@pytest.mark.parametrize("np_", [2])
+def test_ops_matrix_np2(native_built, np_):
+    rc, out = run_parallel("ops_worker.py", np=np_, timeout=400)
+    assert "ALL OK" in out, out[-3000:]
+
+
+def test_ops_matrix_np3_non_power_of_two(native_built):
+    rc, out = run_parallel("ops_worker.py", np=3, timeout=400,
+                           args=["--only", "rank_size,allreduce_sum_avg,allreduce_async_fused,allgather,broadcast,alltoall,"
+                                 "reducescatter,process_sets,errors,barrier_join,optimizer"])
+    assert "ALL OK" in out, out[-3000:]
+
+
+def test_tcp_control_plane(native_built):
+    """Same matrix subset with the shared-memory control plane disabled (pure TCP negotiation)."""
+    rc, out = run_parallel("ops_worker.py", np=2, timeout=400, env={"HVD_CONTROL_PLANE": "tcp"},
+                           args=["--only", "allreduce_sum_avg,allreduce_async_fused,cache_invalidation,barrier_join"])
+    assert "ALL OK" in out, out[-3000:]
+
+
+def test_cache_disabled_and_no_fusion(native_built):
+    rc, out = run_parallel("ops_worker.py", np=2, timeout=400,
+                           env={"HOROVOD_CACHE_CAPACITY": "0", "HOROVOD_FUSION_THRESHOLD": "0"},
+                           args=["--only", "allreduce_sum_avg,allreduce_async_fused,grouped_allreduce,barrier_join"])
+    assert "ALL OK" in out, out[-3000:]
+
+
+def test_torchrun_env_bootstrap(native_built, tmp_path):
+    """hvd.init() under a torchrun-style environment (RANK/WORLD_SIZE/MASTER_ADDR/MASTER_PORT, no hvdrun)."""
+    import os, socket, subprocess, sys
+    from conftest import REPO
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "w.py"
+    script.write_text("import torch\nimport horovod_b200.torch as hvd\nhvd.init()\n"
+                      "out = hvd.allreduce(torch.ones(4) * (hvd.rank() + 1), op=hvd.Sum)\n"
+                      "assert out.tolist() == [3.0] * 4, out\nassert hvd.local_size() == 2\nprint('OK', hvd.rank())\nhvd.shutdown()\n")
+    procs = []
+    for r in range(2):
+        e = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), LOCAL_WORLD_SIZE="2", MASTER_ADDR="127.0.0.1",
+                 MASTER_PORT=str(port), PYTHONPATH=REPO)
+        for k in list(e):
+            if k.startswith("HOROVOD_"):
+                del e[k]
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    outs = [p.communicate(timeout=180)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
