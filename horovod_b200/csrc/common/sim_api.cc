@@ -107,6 +107,37 @@ int hvd_sim_allgather(int nranks, int device, int64_t bytes, const uint64_t* in_
   return (int)cudaDeviceSynchronize();
 }
 
+// Adasum over N simulated ranks: in_ptrs/out_ptrs [nranks][ntensors]; dtype fp32/fp16/bf16.
+int hvd_sim_adasum(int nranks, int device, int ntensors, const int64_t* counts, const uint64_t* in_ptrs, const uint64_t* out_ptrs,
+                   int dtype, int ctas, double prescale, double postscale) {
+  if (cudaSetDevice(device) != cudaSuccess) return -1;
+  int64_t total = 0;
+  std::vector<int64_t> offs(ntensors);
+  for (int i = 0; i < ntensors; ++i) { offs[i] = total; total += Align128(counts[i] * 4); }
+  Sim* sim = GetSim(nranks, device, (size_t)std::max<int64_t>(total, 1 << 20));
+  if (!sim) return -1;
+  // the launches of one rank are stream ordered; ranks interleave level by level so that all kernels of a level are
+  // co-resident (each kernel of rank r waits at its barrier for the same kernel of the other ranks)
+  for (int r = 0; r < nranks; ++r) {
+    std::vector<kern::TensorDesc> d(ntensors);
+    for (int i = 0; i < ntensors; ++i) {
+      d[i].in = (const void*)in_ptrs[(size_t)r * ntensors + i];
+      d[i].out = (void*)out_ptrs[(size_t)r * ntensors + i];
+      d[i].offset = offs[i];
+      d[i].count = counts[i];
+    }
+    const auto* dt = (const kern::TensorDesc*)GpuContext::Get().Stage(device, d.data(), d.size() * sizeof(kern::TensorDesc), sim->streams[r]);
+    if (!dt) return -2;
+    kern::AdasumArgs a {};
+    a.descs = dt; a.ndesc = ntensors; a.total_bytes = total; a.dtype = dtype; a.ctas = ctas;
+    a.scratch_stride_bytes = kern::kAdasumScratchStride;
+    kern::CommParams cp = sim->teams[r]->Params(sim->teams[r]->NextSlot());
+    cudaError_t e = kern::LaunchAdasum(cp, a, prescale, postscale, sim->streams[r]);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return (int)cudaDeviceSynchronize();
+}
+
 void hvd_sim_reset() {
   for (auto& kv : g_sims) for (auto st : kv.second.streams) cudaStreamDestroy(st);
   g_sims.clear();

@@ -94,17 +94,18 @@ cudaError_t LaunchPackUnpack(void* buffer, const TensorDesc* descs, int ndesc, i
                              int wire_dtype, double scale, int direction, int ctas, cudaStream_t stream);
 cudaError_t LaunchScale(const void* in, void* out, int64_t count, int dtype, double scale, cudaStream_t stream);
 
-// Adasum pairwise step between this rank and `partner` over the symmetric
-// buffer: computes dot(a,b), |a|^2, |b|^2 per tensor segment, then
-// a <- acoeff*a + bcoeff*b on the half this rank keeps.  See adasum_kernels.cu.
+// Adasum (vector-halving distance-doubling with per-tensor adaptive coefficients) entirely on the GPUs of a
+// peer-mapped team; see adasum_kernels.cu.  Tensors are fp32 / fp16 / bf16; the fused vector lives in fp32.
 struct AdasumArgs {
-  const TensorDesc* descs; int ndesc;   // tensors (fp32/fp16/bf16) inside the fused buffer
-  int64_t total_bytes;
+  const TensorDesc* descs; int ndesc;   // device table; offsets are byte offsets of the FP32 fused vector (128 B aligned)
+  int64_t total_bytes;                  // fp32 bytes, multiple of 128
   int dtype;
   int ctas;
-  double* scratch;                      // device: 3 doubles per tensor per level, symmetric region
+  int64_t scratch_stride_bytes;         // distance between the two per-level partial-dot tables in the flag region
 };
-cudaError_t LaunchAdasum(const CommParams& cp, const AdasumArgs& args, cudaStream_t stream);
+constexpr int64_t kAdasumScratchStride = 30000;
+constexpr int kAdasumMaxTensors = 1250;
+cudaError_t LaunchAdasum(const CommParams& cp, const AdasumArgs& args, double prescale, double postscale, cudaStream_t stream);
 
 // Fused multi-tensor optimizer updates (see optim_kernels.cu)
 struct SgdTensor { void* param; const void* grad; void* momentum; int64_t count; };

@@ -72,8 +72,37 @@ Status GpuOps::Adasum(ProcessSet& ps, Entries& es, const Response& r, SharedEven
 // Peer-to-peer kernel path: see kernels/adasum_kernels.cu. Returns InProgress when not applicable.
 Status GpuOps::AdasumP2P(ProcessSet& ps, SymmTeam& team, Entries& es, const Response& r, const std::vector<int64_t>& counts,
                          int device, cudaStream_t s) {
-  (void)ps; (void)team; (void)es; (void)r; (void)counts; (void)device; (void)s;
-  return Status::InProgress();
+  (void)ps;
+  if (!(r.dtype == DataType::FLOAT32 || r.dtype == DataType::FLOAT16 || r.dtype == DataType::BFLOAT16)) return Status::InProgress();
+  if ((int)es.size() > kern::kAdasumMaxTensors) return Status::InProgress();
+  GpuContext& ctx = GpuContext::Get();
+  const size_t esz = DataTypeSize(r.dtype);
+  std::vector<kern::TensorDesc> descs(es.size());
+  int64_t total = 0;
+  for (size_t i = 0; i < es.size(); ++i) {
+    if (es[i]) { descs[i].in = es[i]->input; descs[i].out = es[i]->output; }
+    else {
+      void* z = ctx.TempAlloc(device, (size_t)counts[i] * esz, true, s);
+      if (!z) return Status::UnknownError("out of device memory for join placeholder");
+      descs[i].in = z; descs[i].out = z;
+    }
+    descs[i].offset = total;
+    descs[i].count = counts[i];
+    total += (counts[i] * 4 + 127) / 128 * 128;
+  }
+  if (total > (int64_t)team.buffer_bytes()) return Status::InProgress();  // larger than the symmetric buffer: host path
+  const auto* dt = (const kern::TensorDesc*)ctx.Stage(device, descs.data(), descs.size() * sizeof(kern::TensorDesc), s);
+  if (!dt) return Status::InProgress();
+  kern::AdasumArgs a {};
+  a.descs = dt; a.ndesc = (int)descs.size(); a.total_bytes = total; a.dtype = (int)r.dtype;
+  a.ctas = (int)std::max<int64_t>(1, std::min<int64_t>(env_.params->comm_ctas, (total + 16383) / 16384));
+  a.scratch_stride_bytes = kern::kAdasumScratchStride;
+  kern::CommParams cp = team.Params(team.NextSlot());
+  if (env_.timeline && env_.timeline->Initialized()) env_.timeline->ActivityStartAll(es, HVD_ACT_P2P_ADASUM);
+  cudaError_t e = kern::LaunchAdasum(cp, a, r.prescale, r.postscale, s);
+  if (e != cudaSuccess) return Status::UnknownError(std::string("adasum kernel launch failed: ") + cudaGetErrorString(e));
+  ctx.TempFreeAll(device, s);
+  return Status::OK();
 }
 
 }  // namespace hvd

@@ -149,7 +149,7 @@ void ThrowIfError(const Status& st) {
 }
 
 std::shared_ptr<TensorTableEntry> MakeEntry(const at::Tensor& in, const std::string& name) {
-  TORCH_CHECK(in.is_contiguous(), "Horovod: tensor must be contiguous");
+  TORCH_CHECK(in.is_non_overlapping_and_dense(), "Horovod: tensor must be dense (contiguous in some memory format)");
   auto e = std::make_shared<TensorTableEntry>();
   e->name = name;
   e->input = in.data_ptr();
@@ -411,7 +411,7 @@ void FusedSgdStep(std::vector<at::Tensor> params, std::vector<at::Tensor> grads,
   std::vector<kern::SgdTensor> table(params.size());
   int64_t maxc = 0;
   for (size_t i = 0; i < params.size(); ++i) {
-    TORCH_CHECK(params[i].is_cuda() && params[i].is_contiguous() && grads[i].is_contiguous(), "fused_sgd: tensors must be contiguous CUDA tensors");
+    TORCH_CHECK(params[i].is_cuda() && params[i].is_non_overlapping_and_dense() && grads[i].strides() == params[i].strides(), "fused_sgd: params/grads must be dense CUDA tensors with identical layout");
     table[i].param = params[i].data_ptr(); table[i].grad = grads[i].data_ptr();
     table[i].momentum = has_mom ? momenta[i].data_ptr() : nullptr;
     table[i].count = params[i].numel();
@@ -436,7 +436,7 @@ void FusedAdamStep(std::vector<at::Tensor> params, std::vector<at::Tensor> grads
   std::vector<kern::AdamTensor> table(params.size());
   int64_t maxc = 0;
   for (size_t i = 0; i < params.size(); ++i) {
-    TORCH_CHECK(params[i].is_cuda() && params[i].is_contiguous() && grads[i].is_contiguous(), "fused_adam: tensors must be contiguous CUDA tensors");
+    TORCH_CHECK(params[i].is_cuda() && params[i].is_non_overlapping_and_dense() && grads[i].strides() == params[i].strides(), "fused_adam: params/grads must be dense CUDA tensors with identical layout");
     table[i].param = params[i].data_ptr(); table[i].grad = grads[i].data_ptr();
     table[i].exp_avg = exp_avg[i].data_ptr(); table[i].exp_avg_sq = exp_avg_sq[i].data_ptr();
     table[i].count = params[i].numel();

@@ -81,11 +81,13 @@ def broadcast_optimizer_state(optimizer, root_rank, model=None, process_set=glob
         raise ValueError('cannot broadcast torch.optim.LBFGS state')
     state_dict = optimizer.state_dict()
     # Newly created optimizers have no state: materialise it with a zero-gradient step so every rank has the same keys
+    created = []
     if len(state_dict['state']) == 0:
         for group in optimizer.param_groups:
             for p in group['params']:
                 if p.requires_grad and p.grad is None:
-                    p.grad = p.data.new_zeros(p.size())
+                    p.grad = torch.zeros_like(p.data)
+                    created.append(p)
         # a zero-grad step must not move the weights: snapshot and restore
         saved = [[p.data.clone() for p in g['params']] for g in optimizer.param_groups]
         if optimizer.__class__.__module__.startswith('horovod_b200') or hasattr(optimizer, '_hvd_super_step'):
@@ -95,6 +97,8 @@ def broadcast_optimizer_state(optimizer, root_rank, model=None, process_set=glob
         for g, ps in zip(optimizer.param_groups, saved):
             for p, s in zip(g['params'], ps):
                 p.data.copy_(s)
+        for p in created:
+            p.grad = None  # leave no artificial gradients behind
         state_dict = optimizer.state_dict()
     if len(state_dict['state']) == 0:
         # stateless optimizer (plain SGD): only hyper-parameters travel

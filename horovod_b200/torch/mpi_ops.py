@@ -95,7 +95,21 @@ runtime_stats = _basics.runtime_stats
 tunable_params = _basics.tunable_params
 
 
-def _check_contiguous(tensor, what='tensor'):
+def _is_dense(tensor):
+    """Contiguous in ANY memory format (row-major, channels_last, ...): the storage is one gap-free block, so an
+    elementwise collective can treat it as a flat buffer (every rank holds the same layout)."""
+    if tensor.is_contiguous():
+        return True
+    if tensor.dim() == 4 and tensor.is_contiguous(memory_format=torch.channels_last):
+        return True
+    if tensor.dim() == 5 and tensor.is_contiguous(memory_format=torch.channels_last_3d):
+        return True
+    return False
+
+
+def _check_contiguous(tensor, what='tensor', allow_any_dense_format=False):
+    if allow_any_dense_format and _is_dense(tensor):
+        return
     if not tensor.is_contiguous():
         raise ValueError(f'Horovod: {what} must be contiguous; call .contiguous() first.')
 
@@ -120,7 +134,9 @@ def _adasum_checks(tensor, process_set):
 
 
 def _allreduce_async(tensor, output, name, op, prescale_factor, postscale_factor, process_set):
-    _check_contiguous(tensor)
+    _check_contiguous(tensor, allow_any_dense_format=True)
+    if output is not tensor and output.stride() != tensor.stride():
+        raise ValueError('Horovod: allreduce output must have the same memory layout as the input')
     if op == Adasum:
         _adasum_checks(tensor, process_set)
     if op == Average and not tensor.is_floating_point():
@@ -139,7 +155,7 @@ def allreduce_async(tensor, average=None, name=None, op=None, prescale_factor=1.
                     process_set=global_process_set):
     """Asynchronous averaging/summing allreduce; returns a handle for poll()/synchronize(). The input is not modified."""
     op = resolve_op(op, average, Average, Sum)
-    output = tensor.new_empty(tensor.shape)
+    output = torch.empty_like(tensor)  # preserves channels_last etc.
     return _allreduce_async(tensor, output, name, op, prescale_factor, postscale_factor, process_set)
 
 
@@ -189,7 +205,7 @@ def allreduce_(tensor, average=None, name=None, op=None, prescale_factor=1.0, po
 
 def _grouped_allreduce_async(tensors, outputs, name, op, prescale_factor, postscale_factor, process_set):
     for t in tensors:
-        _check_contiguous(t)
+        _check_contiguous(t, allow_any_dense_format=True)
     if op == Adasum:
         for t in tensors:
             _adasum_checks(t, process_set)
@@ -208,7 +224,7 @@ def grouped_allreduce_async(tensors, average=None, name=None, op=None, prescale_
                             process_set=global_process_set):
     """Allreduce of a list of tensors negotiated and fused as one unit."""
     op = resolve_op(op, average, Average, Sum)
-    outputs = [t.new_empty(t.shape) for t in tensors]
+    outputs = [torch.empty_like(t) for t in tensors]
     return _grouped_allreduce_async(tensors, outputs, name, op, prescale_factor, postscale_factor, process_set)
 
 
@@ -345,7 +361,7 @@ def grouped_allgather(tensors, name=None, process_set=global_process_set):
 # broadcast
 
 def _broadcast_async(tensor, output, root_rank, name, process_set):
-    _check_contiguous(tensor)
+    _check_contiguous(tensor, allow_any_dense_format=True)
     handle = _wrap_native(_native().broadcast_async, tensor, output, root_rank, name or '', process_set.process_set_id)
     _handle_map[handle] = (tensor, output, None)
     return handle
@@ -353,7 +369,7 @@ def _broadcast_async(tensor, output, root_rank, name, process_set):
 
 def broadcast_async(tensor, root_rank, name=None, process_set=global_process_set):
     """`root_rank` is a GLOBAL rank, also inside a process set."""
-    output = tensor.new_empty(tensor.shape)
+    output = torch.empty_like(tensor)
     return _broadcast_async(tensor, output, root_rank, name, process_set)
 
 

@@ -144,7 +144,7 @@ class _DistributedOptimizer(torch.optim.Optimizer):
     def _allreduce_grad_async(self, p):
         if p.grad is None:
             # gradient was not computed on this rank but the peers will reduce it: contribute zeros
-            p.grad = p.data.new_zeros(p.shape)
+            p.grad = torch.zeros_like(p.data)
         name = self._parameter_names.get(p)
         tensor = p.grad
         if tensor.is_sparse:
@@ -169,7 +169,7 @@ class _DistributedOptimizer(torch.optim.Optimizer):
         name = self._parameter_names.get(ps[0])
         for p in ps:
             if p.grad is None:
-                p.grad = p.data.new_zeros(p.shape)
+                p.grad = torch.zeros_like(p.data)
         tensors_compressed, ctxs = zip(*[self._compression.compress(p.grad) for p in ps])
         if self.op == Average:
             prescale_factor = 1.0 / self.gradient_predivide_factor
@@ -311,7 +311,7 @@ def _fused_step(opt):
             params = [p for p in group['params'] if p.grad is not None]
             if not params:
                 continue
-            if not all(p.is_cuda and p.is_contiguous() and p.grad.is_contiguous() and not p.grad.is_sparse for p in params):
+            if not all(p.is_cuda and not p.grad.is_sparse and mpi_ops._is_dense(p) and p.grad.stride() == p.stride() for p in params):
                 return False
             by_dtype = {}
             for p in params:
@@ -325,7 +325,7 @@ def _fused_step(opt):
                         for p in ps:
                             st = opt.state[p]
                             if st.get('momentum_buffer') is None:
-                                st['momentum_buffer'] = torch.zeros_like(p)
+                                st['momentum_buffer'] = torch.zeros_like(p, memory_format=torch.preserve_format)
                                 first = True
                             bufs.append(st['momentum_buffer'])
                         if first and any(opt.state[p].get('_hvd_init') for p in ps):
@@ -345,8 +345,8 @@ def _fused_step(opt):
                         st = opt.state[p]
                         if len(st) == 0 or 'exp_avg' not in st:
                             st['step'] = torch.tensor(0.0)
-                            st['exp_avg'] = torch.zeros_like(p, dtype=torch.float32)
-                            st['exp_avg_sq'] = torch.zeros_like(p, dtype=torch.float32)
+                            st['exp_avg'] = torch.zeros_like(p, dtype=torch.float32, memory_format=torch.preserve_format)
+                            st['exp_avg_sq'] = torch.zeros_like(p, dtype=torch.float32, memory_format=torch.preserve_format)
                         st['step'] = st['step'] + 1
                         step = int(st['step'].item()) if torch.is_tensor(st['step']) else int(st['step'])
                         exp_avg.append(st['exp_avg'])
@@ -405,7 +405,7 @@ class _DistributedAdasumOptimizer(torch.optim.Optimizer):
         # run the wrapped optimizer on this parameter alone
         name = self._parameter_names.get(p)
         if p.grad is None:
-            p.grad = p.data.new_zeros(p.shape)
+            p.grad = torch.zeros_like(p.data)
         stashed_params = []
         for group in self.param_groups:
             stashed_params.append(group['params'])

@@ -159,3 +159,42 @@ def test_pack_reduce_bandwidth_smoke():
     sim_allreduce(ins, outs, torch.float32, torch.float32, SUM, TWOSHOT, ctas=32, repeats=2)
     ms = sim_allreduce(ins, outs, torch.float32, torch.float32, SUM, TWOSHOT, ctas=32, repeats=5) / 5
     assert ms < 50.0, ms
+
+
+def _adasum_ref(vecs):
+    """fp64 oracle: pairwise adaptive sum in the VHDD tree order (reference ops/adasum/adasum.h:344-435)."""
+    if len(vecs) == 1:
+        return vecs[0]
+    h = len(vecs) // 2
+    a, b = _adasum_ref(vecs[:h]), _adasum_ref(vecs[h:])
+    dot, na, nb = (a * b).sum(), (a * a).sum(), (b * b).sum()
+    ac = 1 - dot / (2 * na) if na > 0 else 1.0
+    bc = 1 - dot / (2 * nb) if nb > 0 else 1.0
+    return ac * a + bc * b
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_adasum_kernels_vs_fp64_oracle(n, dtype):
+    lib = _lib()
+    lib.hvd_sim_adasum.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int64),
+                                   ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64), ctypes.c_int, ctypes.c_int,
+                                   ctypes.c_double, ctypes.c_double]
+    sizes = [5, 1000, 33333, 64]
+    ins = _make(n, sizes, dtype, seed=3)
+    # tensor 3: identical on every rank (parallel vectors -> result equals the input)
+    for r in range(n):
+        ins[r][3].copy_(ins[0][3])
+    outs = [[torch.empty_like(x) for x in row] for row in ins]
+    t = len(sizes)
+    counts = (ctypes.c_int64 * t)(*sizes)
+    ip = (ctypes.c_uint64 * (n * t))(*[x.data_ptr() for r in ins for x in r])
+    op_ = (ctypes.c_uint64 * (n * t))(*[x.data_ptr() for r in outs for x in r])
+    rc = lib.hvd_sim_adasum(n, 0, t, counts, ip, op_, DT[dtype], 8, 1.0, 1.0)
+    assert rc == 0, rc
+    tol = 1e-4 if dtype == torch.float32 else 3e-2
+    for i in range(t):
+        ref = _adasum_ref([ins[r][i].double() for r in range(n)])
+        for r in range(n):
+            torch.testing.assert_close(outs[r][i].double(), ref, rtol=tol, atol=tol)
+    torch.testing.assert_close(outs[0][3].double(), ins[0][3].double(), rtol=tol, atol=tol)
