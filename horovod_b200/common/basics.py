@@ -151,8 +151,9 @@ class HorovodBasics(object):
             from horovod_b200.runner.http.http_client import read_data_from_kvstore
             host = os.environ.get('HOROVOD_HOSTNAME', socket.gethostname())
             lrank = os.environ.get('HOROVOD_LOCAL_RANK', '0')
-            reply = read_data_from_kvstore(addr, port, 'rank_and_size', f'{host}:{lrank}',
-                                           timeout=float(os.environ.get('HOROVOD_ELASTIC_TIMEOUT', '600'))).decode()
+            etimeout = float(os.environ.get('HOROVOD_ELASTIC_TIMEOUT', '600'))
+            reply = read_data_from_kvstore(addr, port, 'rank_and_size', f'{host}:{lrank}', timeout=etimeout,
+                                           request_timeout=etimeout).decode()
             vals = [int(v) for v in reply.split(',')]
             if vals[0] < 0:
                 raise RuntimeError("This worker was removed from the job by the elastic driver")

@@ -18,7 +18,7 @@ from horovod_b200.runner.common.util import hosts as hosts_util
 from horovod_b200.runner.common.util import timeout as timeout_util
 from horovod_b200.runner.elastic import constants
 from horovod_b200.runner.elastic.discovery import HostManager
-from horovod_b200.runner.elastic.registration import WorkerStateRegistry
+from horovod_b200.runner.elastic.registration import RoundCoordinator
 from horovod_b200.runner.elastic.worker import HostUpdateResult, WorkerNotificationClient
 
 
@@ -67,7 +67,8 @@ class ElasticDriver(object):
         self._slots_ready = threading.Event()
         self._notify_clients = {}            # (host, local_rank) -> WorkerNotificationClient
         self._spawn = None
-        self._registry = WorkerStateRegistry(self, self._hosts, reset_limit=reset_limit)
+        self._registry = RoundCoordinator(self, self._hosts, reset_limit=reset_limit)
+        self._clean_stop = False
         self._collector = _ResultCollector()
         self._stop = threading.Event()
         self._poller = threading.Thread(target=self._poll_hosts, daemon=True)
@@ -85,7 +86,6 @@ class ElasticDriver(object):
         if error_message:
             self._collector.fail(error_message)
         self._stop.set()
-        self._rendezvous.stop() if hasattr(self._rendezvous, 'stop_hooks') else None
 
     def finished(self):
         return self._stop.is_set()
@@ -112,7 +112,8 @@ class ElasticDriver(object):
         return self._by_rank.get(0)
 
     def record_ready(self, host, slot):
-        return self._registry.record_ready(host, slot)
+        """A worker is (re-)initialising; blocks until the round it must join is published and returns its id."""
+        return self._registry.worker_ready(host, slot)
 
     def register_worker_server(self, host, slot, addresses, secret_key):
         self._notify_clients[(host, slot)] = WorkerNotificationClient(addresses, secret_key, self._verbose)
@@ -153,8 +154,9 @@ class ElasticDriver(object):
             self._by_rank = {si.rank: si for si in layout}
             self._world_size = len(layout)
             self._rendezvous.init(layout)
-            self._registry.reset(self._world_size)
-            return [si for si in layout if (si.hostname, si.local_rank) not in previous]
+            fresh = [si for si in layout if (si.hostname, si.local_rank) not in previous]
+            self._registry.begin_round(list(self._slots.keys()), [(si.hostname, si.local_rank) for si in fresh])
+            return fresh
 
     def _launch(self, slot_info):
         def run():
@@ -166,15 +168,16 @@ class ElasticDriver(object):
         self._collector.track(t)
 
     def _on_exit(self, slot_info, exit_code, timestamp):
-        if not self.has_rank_assignment(slot_info.hostname, slot_info.local_rank):
-            logging.info('worker %s[%d] was removed from the job; ignoring its exit', slot_info.hostname, slot_info.local_rank)
-            return
         name = '{}[{}]'.format(slot_info.hostname, slot_info.local_rank)
+        if not self.has_rank_assignment(slot_info.hostname, slot_info.local_rank):
+            logging.info('worker %s was removed from the job; ignoring its exit', name)
+            return
+        if self._stop.is_set() and exit_code != 0 and self._clean_stop:
+            return  # torn down by us after another rank finished successfully
+        self._registry.worker_exited(slot_info.hostname, slot_info.local_rank, exit_code)
         if exit_code == 0:
-            rnd = self._registry.record_success(slot_info.hostname, slot_info.local_rank)
-        else:
-            rnd = self._registry.record_failure(slot_info.hostname, slot_info.local_rank)
-        if self.finished() and self._registry.last_rendezvous() == rnd:
+            self._clean_stop = True
+        if self.finished():
             self._collector.put(name, (exit_code, timestamp))
 
     def _poll_hosts(self):

@@ -1,143 +1,129 @@
-"""Tracks what every worker of the current rendezvous round reported (READY after re-init, SUCCESS, FAILURE) and, once
-all `world_size` workers have reported, decides what the job does next: stop, blacklist failing hosts and resume with
-a new assignment, or give up after `reset_limit` resets.
+"""Round coordination for elastic jobs.
 
-Role parity: horovod/runner/elastic/registration.py (WorkerStateRegistry).
+A *round* is one rank assignment.  While a round runs, workers report to the coordinator in three ways:
+  ready    a worker re-initialises (after a failed collective or a host-change interrupt) and asks for its new rank
+  success  a worker process exited with code 0
+  failure  a worker process died / exited non-zero
+Once every member of the round has reported, the coordinator decides: finish the job (someone succeeded or everybody
+failed), or blacklist the failed hosts and ask the driver for the next round.  Callers of `worker_ready()` block until
+that next round is published, so they come back with their new rank.  Workers that were spawned FOR the current round
+get their rank immediately (the transport's own mesh rendezvous is what synchronises them with the survivors).
+
+Capability parity: horovod/runner/elastic/registration.py (WorkerStateRegistry: READY/SUCCESS/FAILURE barrier and the
+stop / blacklist / reset-limit / resume decision) — re-designed around a condition variable and explicit rounds
+instead of a resettable threading.Barrier.
 """
 import logging
 import threading
-from collections import defaultdict
 
-READY = 'READY'
-SUCCESS = 'SUCCESS'
-FAILURE = 'FAILURE'
+READY, SUCCESS, FAILURE = 'ready', 'success', 'failure'
 
 
-class WorkerStateRegistry(object):
-    def __init__(self, driver, host_manager, reset_limit=None, verbose=False):
+class RoundCoordinator(object):
+    def __init__(self, driver, host_manager, reset_limit=None):
         self._driver = driver
-        self._host_manager = host_manager
+        self._hosts = host_manager
         self._reset_limit = reset_limit
-        self._reset_count = 0
-        self._lock = threading.Lock()
-        self._states = {}
-        self._workers = defaultdict(set)
-        self._barrier = None
-        self._rendezvous_id = 0
-        self._verbose = verbose
-        self._size = 0
+        self._resets = 0
+        self._cv = threading.Condition()
+        self._round = 0
+        self._members = set()     # slots that must report before the round can be decided
+        self._fresh = set()       # members spawned for this round that have not asked for their rank yet
+        self._reports = {}        # slot -> READY | SUCCESS | FAILURE
+        self._deciding = False
 
-    def get_recorded_slots(self):
-        return self._states.keys()
+    # ---- driver side -----------------------------------------------------------------------------------------
+    def begin_round(self, all_slots, new_slots):
+        """Publishes a new assignment: `all_slots` are its members, `new_slots` the ones that get a fresh process."""
+        with self._cv:
+            self._round += 1
+            self._members = set(all_slots)
+            self._fresh = set(new_slots)
+            self._reports = {}
+            self._cv.notify_all()
+            return self._round
 
-    def get(self, state):
-        return self._workers[state]
+    @property
+    def round(self):
+        return self._round
 
-    def count(self, state):
-        return len(self._workers[state])
+    def reported(self, kind):
+        with self._cv:
+            return {s for s, k in self._reports.items() if k == kind}
 
-    def reset(self, size):
-        with self._lock:
-            logging.info('reset workers: {}'.format(size))
-            self._states.clear()
-            self._workers.clear()
-            self._barrier = threading.Barrier(parties=size, action=self._action)
-            self._rendezvous_id += 1
-            self._size = size
-
-    def size(self):
-        return self._size
-
-    def last_rendezvous(self):
-        return self._rendezvous_id
-
-    def record_ready(self, host, slot):
-        return self._record_state(host, slot, READY)
-
-    def record_success(self, host, slot):
-        return self._record_state(host, slot, SUCCESS)
-
-    def record_failure(self, host, slot):
-        return self._record_state(host, slot, FAILURE)
-
-    def _record_state(self, host, slot, state):
-        if self._driver.finished():
-            logging.info('driver finished, ignoring registration: {}[{}] = {}'.format(host, slot, state))
-            return self._rendezvous_id
-        if self._host_manager.is_blacklisted(host):
-            logging.warning('host registers state %s but is already blacklisted, ignoring: %s', state, host)
-            return self._rendezvous_id
+    # ---- worker side -------------------------------------------------------------------------------------------
+    def worker_ready(self, host, slot, timeout=None):
+        """Called on behalf of a worker that is (re-)initialising. Returns the round whose assignment it must use."""
         key = (host, slot)
-        with self._lock:
-            if key in self._states:
-                if state == FAILURE:
-                    # Worker originally recorded itself as READY, but the worker failed while waiting at the barrier. As
-                    # such, we need to update the state to FAILURE, and we don't want to call the action callback twice.
-                    logging.info('key exists, reset barrier: {}[{}] = {} -> {}'.format(host, slot, self._states[key], state))
-                    self._barrier.reset()
-                else:
-                    logging.error('key exists and new state %s not FAILURE, ignoring (current state is %s)', state, self._states[key])
-            if key not in self._states or state == FAILURE:
-                logging.info('record state: {}[{}] = {}'.format(host, slot, state))
-                if key in self._states:
-                    self._workers[self._states[key]].discard(key)
-                self._states[key] = state
-                self._workers[state].add(key)
-            rendezvous_id = self._rendezvous_id
-        rendezvous_id = self._wait(key, state, rendezvous_id)
-        return rendezvous_id
+        with self._cv:
+            if self._driver.finished():
+                return self._round
+            if key in self._fresh:
+                self._fresh.discard(key)
+                return self._round
+            if key not in self._members or self._hosts.is_blacklisted(host):
+                return self._round  # not part of the job any more: the caller will be told rank -1
+            seen = self._round
+            self._reports[key] = READY
+            self._maybe_decide()
+            while self._round == seen and not self._driver.finished():
+                if not self._cv.wait(timeout=timeout if timeout else 1.0) and timeout:
+                    break
+            return self._round
 
-    def _wait(self, key, state, rendezvous_id):
-        while True:
-            try:
-                self._barrier.wait()
-                return rendezvous_id
-            except threading.BrokenBarrierError:
-                if self._barrier.broken:
-                    # Timeout or other non-recoverable error, so exit
-                    raise
-                # Barrier has been reset
-                with self._lock:
-                    # Check to make sure the reset was not caused by a change of state for this key
-                    rendezvous_id = self._rendezvous_id
-                    saved_state = self._states.get(key, state)
-                    if saved_state != state:
-                        # This worker changed its state, so do not attempt to wait again to avoid double-counting
-                        raise RuntimeError('State {} overridden by {}'.format(state, saved_state))
+    def worker_exited(self, host, slot, exit_code):
+        key = (host, slot)
+        with self._cv:
+            rnd = self._round
+            if self._driver.finished() or key not in self._members:
+                return rnd
+            self._fresh.discard(key)
+            self._reports[key] = SUCCESS if exit_code == 0 else FAILURE
+            self._maybe_decide()
+            return rnd
 
-    def _action(self):
-        self._on_workers_recorded()
-
-    def _on_workers_recorded(self):
-        logging.info('all {} workers recorded'.format(self.size()))
-        # Check for success state, if any process succeeded, shutdown all other processes
-        if self.count(SUCCESS) > 0:
-            logging.info('success count == {} -> stop running'.format(self.count(SUCCESS)))
-            self._driver.stop()
+    # ---- decision ------------------------------------------------------------------------------------------------
+    def _maybe_decide(self):
+        # called with the lock held
+        if self._deciding or not self._members or set(self._reports) != self._members:
             return
-        # Check that all processes failed, indicating that processing should stop
-        if self.count(FAILURE) == self._size:
-            logging.error('failure count == {} -> stop running'.format(self._size))
-            self._driver.stop()
-            return
-        # Check for failures, and add them to the blacklisted hosts list
-        failures = self.get(FAILURE)
-        for host, slot in failures:
-            self._host_manager.blacklist(host)
-        # If every active host is blacklisted, then treat this as job failure
-        if all([self._host_manager.is_blacklisted(host) for host, slot in self.get_recorded_slots()]):
-            logging.error('blacklisted slots count == {} -> stop running'.format(self._size))
-            self._driver.stop()
-            return
-        # Check that we have already reset the maximum number of allowed times
-        if self._reset_limit is not None and self._reset_count >= self._reset_limit:
-            logging.error('reset count {} has exceeded limit {} -> stop running'.format(self._reset_count, self._reset_limit))
-            self._driver.stop(error_message='Job has been reset {} times which exceeds the --reset-limit of {}'.format(
-                self._reset_count, self._reset_limit))
-            return
+        self._deciding = True
         try:
-            self._reset_count += 1
-            self._driver.resume()
-        except Exception:
-            logging.exception('failed to activate new hosts -> stop running')
+            self._decide()
+        finally:
+            self._deciding = False
+
+    def _decide(self):
+        kinds = list(self._reports.values())
+        logging.info('round %d complete: %d ready, %d succeeded, %d failed', self._round, kinds.count(READY),
+                     kinds.count(SUCCESS), kinds.count(FAILURE))
+        if SUCCESS in kinds:
+            # training finished on some rank: the job is done, stragglers are torn down
             self._driver.stop()
+            self._cv.notify_all()
+            return
+        if kinds.count(FAILURE) == len(kinds):
+            logging.error('every worker of round %d failed -> stop', self._round)
+            self._driver.stop()
+            self._cv.notify_all()
+            return
+        for (host, _), kind in self._reports.items():
+            if kind == FAILURE:
+                self._hosts.blacklist(host)
+        if all(self._hosts.is_blacklisted(h) for (h, _) in self._members):
+            logging.error('all hosts of round %d are blacklisted -> stop', self._round)
+            self._driver.stop()
+            self._cv.notify_all()
+            return
+        if self._reset_limit is not None and self._resets >= self._reset_limit:
+            self._driver.stop(error_message='Job has been reset {} times which exceeds the --reset-limit of {}'.format(
+                self._resets, self._reset_limit))
+            self._cv.notify_all()
+            return
+        self._resets += 1
+        try:
+            self._driver.resume()   # -> begin_round() -> wakes the waiting worker_ready() callers
+        except Exception as e:
+            logging.exception('could not start the next round')
+            self._driver.stop(error_message=str(e))
+            self._cv.notify_all()

@@ -189,6 +189,8 @@ def test_discovery_script_and_blacklist(tmp_path):
     fixed.set({'b': 2})
     assert hm.update_available_hosts() == HostUpdateResult.removed
     hm.blacklist('b')
+    with pytest.raises(ValueError):
+        discovery.HostManager(fixed, cooldown_range=(0, 10))
     assert hm.is_blacklisted('b') and hm.current_hosts.count_available_slots() == 0
 
 
@@ -299,3 +301,24 @@ def test_elastic_state_and_sampler():
     model2 = torch.nn.Linear(2, 2)
     model2.load_state_dict(st._handlers['model']._saved_model_state)
     assert torch.equal(model.weight, model2.weight)
+
+
+def test_nic_probe_ring_in_process():
+    """Three probe agents (threads) + coordinator on this host: the loopback interface must survive the intersection."""
+    from horovod_b200.runner.common.util.timeout import Timeout
+    from horovod_b200.runner.driver.driver_service import ProbeCoordinator
+    from horovod_b200.runner.task.task_service import probe
+    key = secret.make_secret_key()
+    coord = ProbeCoordinator(3, key)
+    try:
+        ts = [threading.Thread(target=probe, args=(i, 3, coord.addresses(), key, None, 0.5), daemon=True) for i in range(3)]
+        for t in ts:
+            t.start()
+        reports = coord.wait_for_reports(Timeout(60, 'timed out waiting for {activity}'))
+        for t in ts:
+            t.join(10)
+        common = set.intersection(*reports.values())
+        assert 'lo' in common, reports
+        assert len(set(coord.host_ids().values())) == 1
+    finally:
+        coord.shutdown()
