@@ -75,6 +75,13 @@ void Engine::Wake() {
   wake_cv_.notify_one();
 }
 
+void Engine::NotePending(int64_t bytes) {
+  if (pending_bytes_.fetch_add(bytes > 0 ? bytes : 1) == 0) first_pending_ns_ = NowNs();
+}
+void Engine::RequestFlush() { flush_ = true; Wake(); }
+void Engine::BeginWait() { waiters_.fetch_add(1); Wake(); }
+void Engine::EndWait() { waiters_.fetch_sub(1); }
+
 std::shared_ptr<ProcessSet> Engine::MakeProcessSet(const std::vector<int>& ranks) {
   auto ps = std::make_shared<ProcessSet>();
   ps->ranks = ranks;
@@ -148,7 +155,7 @@ void Engine::BackgroundThread() {
     if (EnvIsSet(HOROVOD_CACHE_CAPACITY)) params_.SetCacheEnabled(EnvInt(HOROVOD_CACHE_CAPACITY, 1024) > 0, true);
     if (EnvIsSet(HVD_ONESHOT_MAX_BYTES)) params_.SetOneshotMaxBytes(EnvInt(HVD_ONESHOT_MAX_BYTES, 512 << 10), true);
     if (EnvIsSet(HVD_NVLS_MIN_BYTES)) params_.SetNvlsMinBytes(EnvInt(HVD_NVLS_MIN_BYTES, 1 << 20), true);
-    if (EnvIsSet(HVD_COMM_CTAS)) params_.SetCommCtas((int32_t)EnvInt(HVD_COMM_CTAS, 32), true);
+    if (EnvIsSet(HVD_COMM_CTAS)) params_.SetCommCtas((int32_t)EnvInt(HVD_COMM_CTAS, 64), true);
     params_.Initialize(cfg_.rank, EnvStr(HOROVOD_AUTOTUNE_LOG));
     params_.SetAutoTuning(EnvBool(HOROVOD_AUTOTUNE, false));
 
@@ -229,14 +236,48 @@ void Engine::BackgroundThread() {
 // ---------------------------------------------------------------------------
 // the cycle
 
+// When does a negotiation cycle start?  (The reference sleeps a fixed HOROVOD_CYCLE_TIME between cycles.)
+//   * immediately when a framework thread is WAITING on a handle (synchronize / poll -> RequestFlush)
+//   * as soon as HVD_BATCH_BYTES of tensors are queued (enough to amortise one fused NVLink kernel)
+//   * when the oldest queued tensor is HVD_BATCH_DELAY_MS old
+//   * every cycle_time when idle, so this rank still takes part in rounds other ranks start.
+// Each fused response costs one kernel launch whose CTAs rendezvous with the peer GPUs; fewer, larger responses keep
+// SMs for the overlapping backward pass (49 launches per ResNet-50 step doubled the step time; see profiles/).
 bool Engine::RunLoopOnce() {
+  static const int64_t batch_bytes = EnvInt("HVD_BATCH_BYTES", 16ll << 20);
+  static const double batch_delay_ms = EnvDouble("HVD_BATCH_DELAY_MS", 2.0);
+  static const double spin_us = EnvDouble("HVD_SPIN_US", 50.0);
   {
+    const auto idle_deadline = std::chrono::steady_clock::now() + std::chrono::duration<double, std::milli>(params_.params().cycle_time_ms);
+    // short spin first: a blocking allreduce in a tight loop re-enqueues within microseconds
+    const auto spin_end = std::chrono::steady_clock::now() + std::chrono::duration<double, std::micro>(spin_us);
+    while (!flush_.load(std::memory_order_acquire) && waiters_.load(std::memory_order_acquire) == 0 && pending_bytes_.load(std::memory_order_acquire) < batch_bytes &&
+           std::chrono::steady_clock::now() < spin_end) {
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
     std::unique_lock<std::mutex> l(wake_mu_);
-    if (!wake_flag_) wake_cv_.wait_for(l, std::chrono::duration<double, std::milli>(params_.params().cycle_time_ms), [&] { return wake_flag_; });
+    while (true) {
+      const int64_t pb = pending_bytes_.load();
+      const bool flush = flush_.load() || waiters_.load() > 0 || shutdown_requested_.load();
+      auto now = std::chrono::steady_clock::now();
+      if (flush || pb >= batch_bytes) break;
+      if (pb > 0 && (double)(NowNs() - first_pending_ns_.load()) >= batch_delay_ms * 1e6) break;
+      if (now >= idle_deadline) break;
+      auto until = idle_deadline;
+      if (pb > 0) {
+        auto d = std::chrono::steady_clock::now() + std::chrono::duration_cast<std::chrono::steady_clock::duration>(
+                     std::chrono::duration<double, std::milli>(std::max(0.0, batch_delay_ms - (double)(NowNs() - first_pending_ns_.load()) / 1e6)));
+        if (d < until) until = d;
+      }
+      wake_flag_ = false;
+      wake_cv_.wait_until(l, until, [&] { return wake_flag_; });
+    }
     wake_flag_ = false;
+    pending_bytes_ = 0;
+    flush_ = false;
   }
-  static const double linger_ms = EnvDouble("HVD_CYCLE_LINGER_MS", 0.0);
-  if (linger_ms > 0) std::this_thread::sleep_for(std::chrono::duration<double, std::milli>(linger_ms));
   ++cycles_;
   timeline_.MarkCycleStart();
   {  // runtime timeline start / stop requests
@@ -303,7 +344,15 @@ void Engine::PerformOperation(ProcessSet& ps, Response& r) {
     default: break;
   }
 
-  const int device = r.devices.empty() ? CPU_DEVICE_ID : r.devices[ps.set_rank()];
+  // The device is a LOCAL property: take it from an entry this rank submitted; a joined rank (no entries) uses the
+  // device it passed to hvd.join() — the coordinator cannot know it (response.devices only tells CPU vs GPU).
+  int device = r.devices.empty() ? CPU_DEVICE_ID : r.devices[ps.set_rank()];
+  if (device != CPU_DEVICE_ID) {
+    int local = -2;
+    for (auto& e : es) if (e) { local = e->device; break; }
+    if (local == -2) local = join_device_.load();
+    if (local >= 0) device = local;
+  }
   int64_t bytes = 0;
   for (auto n : r.tensor_sizes) bytes += n * (int64_t)DataTypeSize(r.dtype);
   if (timeline_.Initialized()) for (auto& e : es) if (e) timeline_.Start(e->name, r.type, e->bytes());
@@ -315,12 +364,12 @@ void Engine::PerformOperation(ProcessSet& ps, Response& r) {
       st = ExecuteCpu(ps, es, r);
     } else {
       switch (r.type) {
-        case ResponseType::ALLREDUCE: st = gpu_ops_->Allreduce(ps, es, r, &done); break;
-        case ResponseType::ADASUM: st = gpu_ops_->Adasum(ps, es, r, &done); break;
-        case ResponseType::ALLGATHER: st = gpu_ops_->Allgather(ps, es, r, &done); break;
-        case ResponseType::BROADCAST: st = gpu_ops_->Broadcast(ps, es, r, &done); break;
-        case ResponseType::ALLTOALL: st = gpu_ops_->Alltoall(ps, es, r, &done); break;
-        case ResponseType::REDUCESCATTER: st = gpu_ops_->Reducescatter(ps, es, r, &done); break;
+        case ResponseType::ALLREDUCE: st = gpu_ops_->Allreduce(ps, es, r, device, &done); break;
+        case ResponseType::ADASUM: st = gpu_ops_->Adasum(ps, es, r, device, &done); break;
+        case ResponseType::ALLGATHER: st = gpu_ops_->Allgather(ps, es, r, device, &done); break;
+        case ResponseType::BROADCAST: st = gpu_ops_->Broadcast(ps, es, r, device, &done); break;
+        case ResponseType::ALLTOALL: st = gpu_ops_->Alltoall(ps, es, r, device, &done); break;
+        case ResponseType::REDUCESCATTER: st = gpu_ops_->Reducescatter(ps, es, r, device, &done); break;
         default: st = Status::InvalidArgument("unsupported GPU response type"); break;
       }
     }
@@ -541,6 +590,7 @@ Status Engine::EnqueueAllreduces(std::vector<std::shared_ptr<TensorTableEntry>>&
   }
   st = ps->queue.AddToTensorQueueMulti(es, msgs);
   if (!st.ok()) { if (gid >= 0) ps->groups.DeregisterGroup(gid); return st; }
+  { int64_t b = 0; for (auto& e : es) b += (int64_t)e->bytes(); NotePending(b); }
   Wake();
   return Status::OK();
 }
@@ -564,6 +614,7 @@ Status Engine::EnqueueAllgathers(std::vector<std::shared_ptr<TensorTableEntry>>&
   }
   st = ps->queue.AddToTensorQueueMulti(es, msgs);
   if (!st.ok()) { if (gid >= 0) ps->groups.DeregisterGroup(gid); return st; }
+  { int64_t b = 0; for (auto& e : es) b += (int64_t)e->bytes(); NotePending(b); }
   Wake();
   return Status::OK();
 }
@@ -580,6 +631,7 @@ Status Engine::EnqueueBroadcast(std::shared_ptr<TensorTableEntry> e, int32_t psi
   e->process_set_id = psid; e->type = RequestType::BROADCAST; e->enqueue_ns = NowNs();
   st = ps->queue.AddToTensorQueue(e, MakeRequest(*e, ps->set_rank(), RequestType::BROADCAST));
   if (!st.ok()) return st;
+  NotePending((int64_t)e->bytes());
   Wake();
   return Status::OK();
 }
@@ -603,6 +655,7 @@ Status Engine::EnqueueAlltoall(std::shared_ptr<TensorTableEntry> e, int32_t psid
   e->process_set_id = psid; e->type = RequestType::ALLTOALL; e->enqueue_ns = NowNs();
   st = ps->queue.AddToTensorQueue(e, MakeRequest(*e, ps->set_rank(), RequestType::ALLTOALL));
   if (!st.ok()) return st;
+  NotePending((int64_t)e->bytes());
   Wake();
   return Status::OK();
 }
@@ -627,6 +680,7 @@ Status Engine::EnqueueReducescatters(std::vector<std::shared_ptr<TensorTableEntr
   }
   st = ps->queue.AddToTensorQueueMulti(es, msgs);
   if (!st.ok()) { if (gid >= 0) ps->groups.DeregisterGroup(gid); return st; }
+  { int64_t b = 0; for (auto& e : es) b += (int64_t)e->bytes(); NotePending(b); }
   Wake();
   return Status::OK();
 }
@@ -636,9 +690,10 @@ Status Engine::EnqueueJoin(std::shared_ptr<TensorTableEntry> e, int32_t psid) {
   Status st = CheckSet(psid, &ps);
   if (!st.ok()) return st;
   e->name = JOIN_TENSOR_NAME; e->process_set_id = psid; e->type = RequestType::JOIN;
+  if (e->device >= 0) join_device_ = e->device;
   st = ps->queue.AddToTensorQueue(e, MakeRequest(*e, ps->set_rank(), RequestType::JOIN));
   if (!st.ok()) return st;
-  Wake();
+  RequestFlush();
   return Status::OK();
 }
 
@@ -649,7 +704,7 @@ Status Engine::EnqueueBarrier(std::shared_ptr<TensorTableEntry> e, int32_t psid)
   e->name = BARRIER_TENSOR_NAME; e->process_set_id = psid; e->type = RequestType::BARRIER;
   st = ps->queue.AddToTensorQueue(e, MakeRequest(*e, ps->set_rank(), RequestType::BARRIER));
   if (!st.ok()) return st;
-  Wake();
+  RequestFlush();
   return Status::OK();
 }
 
@@ -676,7 +731,7 @@ int32_t Engine::AddProcessSet(const std::vector<int>& ranks_in, std::string* err
   q.shape.assign(ranks.begin(), ranks.end());
   st = g->queue.AddToTensorQueue(e, q);
   if (!st.ok()) { if (err) *err = st.reason(); return -1; }
-  Wake();
+  RequestFlush();
   Completion c = fut.get();
   if (!c.status.ok()) { if (err) *err = c.status.reason(); return -1; }
   return c.last_joined_rank;
@@ -696,7 +751,7 @@ int32_t Engine::RemoveProcessSet(int32_t id, std::string* err) {
   q.shape = {id};
   st = g->queue.AddToTensorQueue(e, q);
   if (!st.ok()) { if (err) *err = st.reason(); return -1; }
-  Wake();
+  RequestFlush();
   Completion c = fut.get();
   if (!c.status.ok()) { if (err) *err = c.status.reason(); return -1; }
   return c.last_joined_rank;

@@ -65,6 +65,11 @@ class Engine {
   Status EnqueueJoin(std::shared_ptr<TensorTableEntry> e, int32_t process_set_id);
   Status EnqueueBarrier(std::shared_ptr<TensorTableEntry> e, int32_t process_set_id);
 
+  // ---- batching hints from the framework binding ----
+  void RequestFlush();  // start a cycle now (someone polls a handle)
+  void BeginWait();     // a framework thread blocks on a handle: cycle continuously until EndWait()
+  void EndWait();
+
   // ---- process sets ----
   // Collective over the global set; blocks until every rank asked for the same set. Returns id or <0.
   int32_t AddProcessSet(const std::vector<int>& ranks, std::string* err);
@@ -93,6 +98,7 @@ class Engine {
   std::shared_ptr<ProcessSet> MakeProcessSet(const std::vector<int>& ranks);
   Status CheckSet(int32_t id, std::shared_ptr<ProcessSet>* out);
   void Wake();
+  void NotePending(int64_t bytes);
   void FailAll(const Status& s);
   void SetError(const std::string& m) { std::lock_guard<std::mutex> l(err_mu_); last_error_ = m; }
 
@@ -114,6 +120,10 @@ class Engine {
   std::mutex wake_mu_;
   std::condition_variable wake_cv_;
   bool wake_flag_ = false;
+  std::atomic<int64_t> pending_bytes_{0};
+  std::atomic<uint64_t> first_pending_ns_{0};
+  std::atomic<bool> flush_{false};
+  std::atomic<int> waiters_{0};
 
   // pending timeline commands (applied by the cycle thread)
   std::mutex tl_mu_;
@@ -124,6 +134,7 @@ class Engine {
   std::string last_error_;
   std::atomic<uint64_t> cycles_{0}, fast_cycles_{0}, responses_{0};
   std::atomic<int> noname_counter_{0};
+  std::atomic<int> join_device_{-1};  // CUDA device a joined rank contributes zeros from
 };
 
 }  // namespace hvd

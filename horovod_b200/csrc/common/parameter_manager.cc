@@ -10,7 +10,7 @@ namespace hvd {
 namespace {
 const int64_t kOneshotChoices[] = {64 << 10, 256 << 10, 512 << 10, 1 << 20, 2 << 20};
 const int64_t kNvlsChoices[] = {256 << 10, 1 << 20, 4 << 20, 1ll << 40};
-const int32_t kCtaChoices[] = {16, 32, 64};
+const int32_t kCtaChoices[] = {32, 64, 128};
 constexpr int kNumCategorical = 4;  // cache, oneshot, nvls, ctas
 }  // namespace
 

@@ -49,7 +49,7 @@ __device__ __forceinline__ void st_f4(void* p, float4 f) {
 
 // ---- pack: T -> fp32 fused vector -------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 adasum_pack_kernel(const __grid_constant__ CommParams cp, const TensorDesc* __restrict__ descs, int nd, int64_t total, float prescale) {
   const int cta = blockIdx.x, grid = gridDim.x;
   char* buf = reinterpret_cast<char*>(cp.buf[cp.rank]);
@@ -68,7 +68,7 @@ adasum_pack_kernel(const __grid_constant__ CommParams cp, const TensorDesc* __re
 }
 
 // ---- level phase 1: partial dot products ---------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 adasum_dots_kernel(const __grid_constant__ CommParams cp, const TensorDesc* __restrict__ descs, int nd, int64_t total,
                    int64_t keep_lo, int64_t keep_hi, int partner, int lower, double* __restrict__ scratch) {
   extern __shared__ double s_acc[];  // [3 * nd]
@@ -108,7 +108,7 @@ adasum_dots_kernel(const __grid_constant__ CommParams cp, const TensorDesc* __re
 }
 
 // ---- level phase 2: coefficients + in-place combine of my half ----------------------------
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 adasum_combine_kernel(const __grid_constant__ CommParams cp, const TensorDesc* __restrict__ descs, int nd, int64_t total,
                       int64_t keep_lo, int64_t keep_hi, int partner, int lower, int group_base, int group_size,
                       int64_t scratch_byte_off) {
@@ -151,7 +151,7 @@ adasum_combine_kernel(const __grid_constant__ CommParams cp, const TensorDesc* _
 struct GatherRanges { int64_t lo[kMaxPeers]; int64_t hi[kMaxPeers]; };
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 adasum_gather_kernel(const __grid_constant__ CommParams cp, const TensorDesc* __restrict__ descs, int nd, int64_t total,
                      const __grid_constant__ GatherRanges rg, float postscale) {
   const int cta = blockIdx.x, grid = gridDim.x;

@@ -157,7 +157,7 @@ __device__ __forceinline__ void peer_combine(const CommParams& cp, const uint4* 
 }
 
 template <typename T, typename W, int NR>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 allreduce_kernel(const __grid_constant__ CommParams cp, const __grid_constant__ AllreduceArgs a, const int chunk_bytes) {
   using A = typename Traits<W>::Acc;
   using S = typename ScaleOf<A>::type;

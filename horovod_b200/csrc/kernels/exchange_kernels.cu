@@ -51,7 +51,7 @@ __device__ __forceinline__ void for_my_chunks(int64_t offset, int64_t bytes, int
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 exchange_kernel(const __grid_constant__ CommParams cp, const __grid_constant__ ExchangeArgs a) {
   const int cta = blockIdx.x, grid = gridDim.x;
   uint32_t epoch = cp.epochs[cta];

@@ -153,8 +153,17 @@ __device__ __forceinline__ bool peer_barrier(const CommParams& cp, uint32_t& epo
     st_release_sys(cp.flags[peer] + cta * kMaxPeers + cp.rank, epoch);
     const uint32_t* mine = cp.flags[cp.rank] + cta * kMaxPeers + peer;
     uint32_t spins = 0;
+    unsigned long long t0 = 0;
     while ((int32_t)(ld_relaxed_sys(mine) - epoch) < 0) {
-      if ((++spins & 0x3fff) == 0 && cp.abort_flag && *reinterpret_cast<const volatile int*>(cp.abort_flag)) { s_abort = 1; break; }
+      if ((++spins & 0x3fff) == 0 && cp.abort_flag) {
+        if (*reinterpret_cast<volatile int*>(cp.abort_flag)) { s_abort = 1; break; }
+        if (cp.timeout_ns) {
+          unsigned long long now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > cp.timeout_ns) { *reinterpret_cast<volatile int*>(cp.abort_flag) = 2; s_abort = 1; break; }
+        }
+      }
     }
     (void)ld_acquire_sys(mine);  // acquire + L1 invalidate once, after the relaxed spin
   }

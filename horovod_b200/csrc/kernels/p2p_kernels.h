@@ -20,9 +20,12 @@ unsigned long long KernelLaunchCount();
 void CountKernelLaunch();
 
 constexpr int kMaxPeers = 8;          // one NVSwitch domain of the HGX B200 box
-constexpr int kMaxCtas = 128;         // flag slots per team
-constexpr int kThreads = 512;
-constexpr int kChunkBytes = 32768;    // kThreads * 16 B * 4
+constexpr int kMaxCtas = 256;         // flag slots per team
+// 256-thread CTAs capped at 128 registers: two fit on an SM and one fits NEXT TO resident compute CTAs of an
+// overlapping backward pass, so a communication kernel does not have to wait for whole SMs to drain
+// (512-thread x 128-register CTAs needed an empty SM each; measured 2x step-time inflation at 2 GPUs).
+constexpr int kThreads = 256;
+constexpr int kChunkBytes = 32768;    // kThreads * 16 B * 8
 constexpr int kInlineDescs = 6;
 constexpr int kFlagWords = kMaxCtas * kMaxPeers;
 
@@ -35,7 +38,8 @@ struct CommParams {
   uint32_t* flags[kMaxPeers];   // flag words of every rank: [cta][src_rank]
   void* mc_buf;                 // multicast (NVLS) mapping of the same buffer, or nullptr
   uint32_t* epochs;             // local: per-CTA barrier epoch, persists across launches
-  const int* abort_flag;        // host-mapped; non-zero => stop spinning (peer failure / shutdown)
+  int* abort_flag;              // host-mapped; non-zero => stop spinning (peer failure / shutdown / timeout)
+  unsigned long long timeout_ns; // a barrier that waits longer sets *abort_flag = 2 and bails out (0 = wait forever)
 };
 
 // One tensor of a fused response. `offset` is the tensor's byte offset inside

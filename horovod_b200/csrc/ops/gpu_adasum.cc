@@ -19,9 +19,8 @@ namespace hvd {
     if (_e != cudaSuccess) return Status::UnknownError(std::string(#call) + " failed: " + cudaGetErrorString(_e)); \
   } while (0)
 
-Status GpuOps::Adasum(ProcessSet& ps, Entries& es, const Response& r, SharedEvent** done) {
-  const int me = ps.set_rank(), n = ps.set_size();
-  const int device = r.devices[me];
+Status GpuOps::Adasum(ProcessSet& ps, Entries& es, const Response& r, int device, SharedEvent** done) {
+  const int n = ps.set_size();
   HVD_CUDA(cudaSetDevice(device));
   GpuContext& ctx = GpuContext::Get();
   cudaStream_t s = ctx.Stream(device);

@@ -158,7 +158,11 @@ Status BuildPieces(Entries& es, const Response& r, int device, cudaStream_t s, s
 }  // namespace
 
 std::shared_ptr<SymmTeam> GpuOps::EnsureTeam(ProcessSet& ps, int device) {
-  if (ps.team_tried) return ps.team;
+  if (ps.team_tried) {
+    if (ps.team && ps.team->abort_state() == 2)
+      throw TransportError("a peer GPU did not reach the collective's flag barrier within HVD_KERNEL_TIMEOUT_SECONDS");
+    return ps.team;
+  }
   ps.team_tried = true;
   Transport* t = ps.transport.get();
   // unique tag for the fd-passing sockets: coordinator pid + counter, agreed through the transport
@@ -174,7 +178,8 @@ std::shared_ptr<SymmTeam> GpuOps::EnsureTeam(ProcessSet& ps, int device) {
                              std::to_string(tag[0]) + "-" + std::to_string(tag[1]) + "-" + std::to_string(ps.id), &why);
   if (!ps.team) LOG(WARNING) << "peer-mapped symmetric memory unavailable for process set " << ps.id << " (" << why
                              << "); GPU collectives fall back to host staging";
-  else LOG(INFO) << "process set " << ps.id << ": symmetric team of " << ps.team->nranks() << " GPUs, backend "
+  if (ps.team) ps.team->set_timeout_seconds(EnvDouble("HVD_KERNEL_TIMEOUT_SECONDS", 60.0));
+  if (ps.team) LOG(INFO) << "process set " << ps.id << ": symmetric team of " << ps.team->nranks() << " GPUs, backend "
                  << ps.team->backend() << ", 2 x " << (ps.team->buffer_bytes() >> 20) << " MiB";
   return ps.team;
 }
@@ -188,9 +193,8 @@ std::string GpuOps::Describe(ProcessSet& ps) {
 // ---------------------------------------------------------------------------
 // allreduce
 
-Status GpuOps::Allreduce(ProcessSet& ps, Entries& es, const Response& r, SharedEvent** done) {
+Status GpuOps::Allreduce(ProcessSet& ps, Entries& es, const Response& r, int device, SharedEvent** done) {
   const int me = ps.set_rank(), n = ps.set_size();
-  const int device = r.devices[me];
   HVD_CUDA(cudaSetDevice(device));
   GpuContext& ctx = GpuContext::Get();
   cudaStream_t s = ctx.Stream(device);
@@ -245,7 +249,7 @@ Status GpuOps::Allreduce(ProcessSet& ps, Entries& es, const Response& r, SharedE
           else if (nvls_ok && seg_bytes >= tp.nvls_min_bytes) variant = kern::kNvls;
         }
         a.variant = variant;
-        int64_t per = variant == kern::kOneShot ? 16384 : (int64_t)8192 * n;
+        int64_t per = variant == kern::kOneShot ? 8192 : (int64_t)4096 * n;  // >= 2 rows (one-shot) or one row per rank (two-shot) per CTA
         a.ctas = (int)std::max<int64_t>(1, std::min<int64_t>(tp.comm_ctas, (seg_bytes + per - 1) / per));
         if (a.ndesc <= kern::kInlineDescs) {
           memcpy(a.inline_descs, descs.data(), descs.size() * sizeof(kern::TensorDesc));
@@ -354,9 +358,8 @@ Status GpuOps::StagedOnHost(ProcessSet& ps, Entries& es, const Response& r, int 
 // reducescatter: pack per-destination block windows, every rank reduces only
 // its own block straight into its output (one-shot restricted to a range).
 
-Status GpuOps::Reducescatter(ProcessSet& ps, Entries& es, const Response& r, SharedEvent** done) {
+Status GpuOps::Reducescatter(ProcessSet& ps, Entries& es, const Response& r, int device, SharedEvent** done) {
   const int me = ps.set_rank(), n = ps.set_size();
-  const int device = r.devices[me];
   HVD_CUDA(cudaSetDevice(device));
   GpuContext& ctx = GpuContext::Get();
   cudaStream_t s = ctx.Stream(device);
@@ -463,9 +466,8 @@ Status RunExchange(SymmTeam& team, GpuContext& ctx, int device, cudaStream_t s, 
 }
 }  // namespace
 
-Status GpuOps::Allgather(ProcessSet& ps, Entries& es, const Response& r, SharedEvent** done) {
+Status GpuOps::Allgather(ProcessSet& ps, Entries& es, const Response& r, int device, SharedEvent** done) {
   const int me = ps.set_rank(), n = ps.set_size();
-  const int device = r.devices[me];
   HVD_CUDA(cudaSetDevice(device));
   GpuContext& ctx = GpuContext::Get();
   cudaStream_t s = ctx.Stream(device);
@@ -517,9 +519,8 @@ Status GpuOps::Allgather(ProcessSet& ps, Entries& es, const Response& r, SharedE
   return FinishEvent(device, s, es.size(), done);
 }
 
-Status GpuOps::Broadcast(ProcessSet& ps, Entries& es, const Response& r, SharedEvent** done) {
+Status GpuOps::Broadcast(ProcessSet& ps, Entries& es, const Response& r, int device, SharedEvent** done) {
   const int me = ps.set_rank(), n = ps.set_size();
-  const int device = r.devices[me];
   HVD_CUDA(cudaSetDevice(device));
   GpuContext& ctx = GpuContext::Get();
   cudaStream_t s = ctx.Stream(device);
@@ -555,9 +556,8 @@ Status GpuOps::Broadcast(ProcessSet& ps, Entries& es, const Response& r, SharedE
   return FinishEvent(device, s, es.size(), done);
 }
 
-Status GpuOps::Alltoall(ProcessSet& ps, Entries& es, const Response& r, SharedEvent** done) {
+Status GpuOps::Alltoall(ProcessSet& ps, Entries& es, const Response& r, int device, SharedEvent** done) {
   const int me = ps.set_rank(), n = ps.set_size();
-  const int device = r.devices[me];
   HVD_CUDA(cudaSetDevice(device));
   GpuContext& ctx = GpuContext::Get();
   cudaStream_t s = ctx.Stream(device);

@@ -74,12 +74,12 @@ class GpuOps {
   GpuOpEnv& env() { return env_; }
   // Each op enqueues its kernels on the hvd stream and returns a shared
   // completion event in *done (refs preset to entries.size()).
-  Status Allreduce(ProcessSet& ps, Entries& es, const Response& r, SharedEvent** done);
-  Status Adasum(ProcessSet& ps, Entries& es, const Response& r, SharedEvent** done);
-  Status Allgather(ProcessSet& ps, Entries& es, const Response& r, SharedEvent** done);
-  Status Broadcast(ProcessSet& ps, Entries& es, const Response& r, SharedEvent** done);
-  Status Alltoall(ProcessSet& ps, Entries& es, const Response& r, SharedEvent** done);
-  Status Reducescatter(ProcessSet& ps, Entries& es, const Response& r, SharedEvent** done);
+  Status Allreduce(ProcessSet& ps, Entries& es, const Response& r, int device, SharedEvent** done);
+  Status Adasum(ProcessSet& ps, Entries& es, const Response& r, int device, SharedEvent** done);
+  Status Allgather(ProcessSet& ps, Entries& es, const Response& r, int device, SharedEvent** done);
+  Status Broadcast(ProcessSet& ps, Entries& es, const Response& r, int device, SharedEvent** done);
+  Status Alltoall(ProcessSet& ps, Entries& es, const Response& r, int device, SharedEvent** done);
+  Status Reducescatter(ProcessSet& ps, Entries& es, const Response& r, int device, SharedEvent** done);
   // Description of the data path chosen for a set (for hvd.gpu_backend_info()).
   std::string Describe(ProcessSet& ps);
 

@@ -235,11 +235,14 @@ kern::CommParams SymmTeam::Params(int which) const {
   cp.mc_buf = mc_va_[which];
   cp.epochs = epochs_;
   cp.abort_flag = abort_dev_;
+  cp.timeout_ns = timeout_ns_;
   return cp;
 }
 
 namespace {
-constexpr size_t kFlagRegionBytes = 64 * 1024;  // kFlagWords * 4 = 4 KiB used; rest reserved (adasum scalars)
+// flag words (kFlagWords * 4 = 8 KiB) followed by the two Adasum partial-dot tables (2 x kAdasumScratchStride)
+constexpr size_t kFlagRegionBytes = 128 * 1024;
+static_assert(kern::kFlagWords * 4 + 2 * kern::kAdasumScratchStride <= (long long)kFlagRegionBytes, "flag region too small");
 }
 
 std::shared_ptr<SymmTeam> SymmTeam::Create(Transport* t, int device, size_t buffer_bytes, bool want_mc,

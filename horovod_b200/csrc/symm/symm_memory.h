@@ -62,6 +62,9 @@ class SymmTeam {
   int NextSlot() { int s = slot_; slot_ ^= 1; return s; }
   int* host_abort_flag() { return abort_host_; }
   void Abort() { if (abort_host_) *abort_host_ = 1; }
+  // 0 = healthy, 1 = aborted by the host, 2 = a kernel timed out waiting for a peer
+  int abort_state() const { return abort_host_ ? *(volatile int*)abort_host_ : 0; }
+  void set_timeout_seconds(double s) { timeout_ns_ = s > 0 ? (unsigned long long)(s * 1e9) : 0; }
   const std::string& backend() const { return backend_; }  // "vmm", "vmm+mc", "ipc", "sim"
 
  private:
@@ -76,6 +79,7 @@ class SymmTeam {
   int* abort_host_ = nullptr;   // pinned, mapped
   int* abort_dev_ = nullptr;    // device alias of abort_host_
   int slot_ = 0;
+  unsigned long long timeout_ns_ = 0;
   std::string backend_;
   std::shared_ptr<Impl> impl_;  // owns driver handles / mappings
 };

@@ -353,7 +353,7 @@ int DoBarrier(int process_set_id) {
 bool PollHandle(int h) {
   auto st = g_handles.Get(h);
   if (!st) throw std::invalid_argument("Handle " + std::to_string(h) + " was not created or has been cleared.");
-  if (!g_handles.Done(st)) return false;
+  if (!g_handles.Done(st)) { Engine::Get().RequestFlush(); return false; }
   if (st->status.ok()) {
     for (auto* ev : st->events) {
       cudaError_t q = cudaEventQuery(ev->ev);
@@ -367,9 +367,11 @@ bool PollHandle(int h) {
 int WaitAndClear(int h) {
   auto st = g_handles.Get(h);
   if (!st) throw std::invalid_argument("Handle " + std::to_string(h) + " was not created or has been cleared.");
-  {
+  if (!g_handles.Done(st)) {
     py::gil_scoped_release release;
+    Engine::Get().BeginWait();
     g_handles.Wait(st);
+    Engine::Get().EndWait();
   }
   Status status = st->status;
   for (auto* ev : st->events) {

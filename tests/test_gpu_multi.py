@@ -15,7 +15,7 @@ def _ngpu():
 @pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
 def test_ops_matrix_p2p(native_built):
     n = 2 if _ngpu() < 4 else (4 if _ngpu() < 8 else 8)
-    rc, out = run_parallel("ops_worker.py", np=n, timeout=900, args=["--device", "cuda"], env={"HOROVOD_LOG_LEVEL": "info"})
+    rc, out = run_parallel("ops_worker.py", np=n, timeout=420, args=["--device", "cuda"], env={"HOROVOD_LOG_LEVEL": "info"})
     assert "ALL OK" in out, out[-4000:]
     assert "symmetric team" in out, out[-4000:]
 
@@ -23,21 +23,21 @@ def test_ops_matrix_p2p(native_built):
 @pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
 def test_ops_matrix_variants(native_built):
     for variant in ("oneshot", "twoshot"):
-        rc, out = run_parallel("ops_worker.py", np=2, timeout=600, env={"HVD_ALLREDUCE_VARIANT": variant},
+        rc, out = run_parallel("ops_worker.py", np=2, timeout=300, env={"HVD_ALLREDUCE_VARIANT": variant},
                                args=["--device", "cuda", "--only", "allreduce_sum_avg,allreduce_async_fused,allreduce_mixed_dtype_fusion,optimizer"])
         assert "ALL OK" in out, (variant, out[-3000:])
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
 def test_nccl_baseline_backend(native_built):
-    rc, out = run_parallel("ops_worker.py", np=2, timeout=600, env={"HVD_GPU_BACKEND": "nccl"},
+    rc, out = run_parallel("ops_worker.py", np=2, timeout=300, env={"HVD_GPU_BACKEND": "nccl"},
                            args=["--device", "cuda", "--only", "allreduce_sum_avg,allreduce_async_fused,optimizer"])
     assert "ALL OK" in out, out[-3000:]
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
 def test_wire_compression_env(native_built):
-    rc, out = run_parallel("ops_worker.py", np=2, timeout=600, env={"HVD_WIRE_DTYPE": "bf16"},
+    rc, out = run_parallel("ops_worker.py", np=2, timeout=300, env={"HVD_WIRE_DTYPE": "bf16"},
                            args=["--device", "cuda", "--only", "optimizer,allreduce_async_fused"])
     # bf16 on the wire: the fused test tolerances (1e-5) are too tight by design, so only the optimizer check must pass
     assert "[ok] optimizer" in out or "ALL OK" in out, out[-3000:]
