@@ -57,6 +57,7 @@ const char* RequestTypeName(RequestType t) {
     case RequestType::REDUCESCATTER: return "REDUCESCATTER";
     case RequestType::PROCESS_SET_ADD: return "PROCESS_SET_ADD";
     case RequestType::PROCESS_SET_REMOVE: return "PROCESS_SET_REMOVE";
+    case RequestType::SYMM_ALLOC: return "SYMM_ALLOC";
   }
   return "<unknown>";
 }

@@ -49,6 +49,7 @@ constexpr const char* JOIN_TENSOR_NAME = "join.noname";
 constexpr const char* BARRIER_TENSOR_NAME = "barrier.noname";
 constexpr const char* PS_ADD_PREFIX = "__process_set_add__:";
 constexpr const char* PS_REMOVE_PREFIX = "__process_set_remove__:";
+constexpr const char* SYMM_ALLOC_PREFIX = "__symm_alloc__:";
 
 // Every fused tensor starts on a 128 B boundary so that 16 B vector accesses,
 // TMA bulk copies and multimem.* never straddle two tensors (the reference pads
@@ -102,6 +103,7 @@ class TensorShape {
 enum class RequestType : uint8_t {
   ALLREDUCE = 0, ALLGATHER = 1, BROADCAST = 2, JOIN = 3, ADASUM = 4,
   ALLTOALL = 5, BARRIER = 6, REDUCESCATTER = 7, PROCESS_SET_ADD = 8, PROCESS_SET_REMOVE = 9,
+  SYMM_ALLOC = 11,  // collective allocation of a registered (peer-mapped) region; 10 is ResponseType::ERROR
 };
 const char* RequestTypeName(RequestType t);
 
@@ -111,6 +113,7 @@ struct Completion {
   void* done_event = nullptr;            // cudaEvent_t recorded on the hvd stream (GPU ops), else null
   std::vector<int32_t> received_splits;  // alltoall
   int32_t last_joined_rank = -1;         // join
+  void* aux_ptr = nullptr;               // SYMM_ALLOC: local address of the new region
 };
 using CompletionCallback = std::function<void(const Completion&)>;
 // Allocates (or resizes) the framework-owned output for ops whose size is only

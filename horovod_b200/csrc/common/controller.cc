@@ -376,12 +376,15 @@ Response Controller::ConstructResponse(const std::string& name, const std::vecto
   resp.postscale = first.postscale;
   resp.reduce_op = first.reduce_op;
   resp.root_rank = first.root_rank;
+  resp.symm_key = first.symm_key;
+  for (auto& q : requests) if (q.symm_key != first.symm_key) resp.symm_key = -1;  // zero-copy only if EVERY rank registered it identically
+  if ((int)requests.size() < set_size) resp.symm_key = -1;                         // joined ranks have no registered tensor
   resp.devices.assign(set_size, first.device);
   for (auto& q : requests) if (q.request_rank >= 0 && q.request_rank < set_size) resp.devices[q.request_rank] = q.device;
   if (t == RequestType::ALLGATHER) {
     resp.tensor_sizes.assign(set_size, 0);
     for (auto& q : requests) resp.tensor_sizes[q.request_rank] = q.shape[0];
-  } else if (t == RequestType::PROCESS_SET_ADD || t == RequestType::PROCESS_SET_REMOVE) {
+  } else if (t == RequestType::PROCESS_SET_ADD || t == RequestType::PROCESS_SET_REMOVE || t == RequestType::SYMM_ALLOC) {
     resp.tensor_sizes = first.shape;
   } else if (t != RequestType::BARRIER && t != RequestType::JOIN) {
     resp.tensor_sizes.push_back(TensorShape(first.shape).num_elements());
@@ -402,7 +405,7 @@ std::deque<Response> Controller::FuseResponses(std::deque<Response> responses, i
         Response& n = responses.front();
         bool compatible = n.type == r.type && n.dtype == r.dtype && n.devices == r.devices &&
                           n.prescale == r.prescale && n.postscale == r.postscale && n.reduce_op == r.reduce_op &&
-                          (!disable_group_fusion || n.group_id == r.group_id);
+                          (!disable_group_fusion || n.group_id == r.group_id) && n.symm_key < 0 && r.symm_key < 0;
         int64_t nb = compatible ? AlignedBytes(n) : 0;
         if (compatible && total + nb <= threshold) {
           total += nb;

@@ -39,7 +39,7 @@ struct TunableParams {
   bool cache_enabled = true;
   int64_t oneshot_max_bytes = 512 << 10;
   int64_t nvls_min_bytes = 1 << 20;
-  int32_t comm_ctas = 64;
+  int32_t comm_ctas = 128;
   uint8_t active = 0;  // autotune still running
 };
 

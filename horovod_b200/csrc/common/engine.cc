@@ -155,7 +155,7 @@ void Engine::BackgroundThread() {
     if (EnvIsSet(HOROVOD_CACHE_CAPACITY)) params_.SetCacheEnabled(EnvInt(HOROVOD_CACHE_CAPACITY, 1024) > 0, true);
     if (EnvIsSet(HVD_ONESHOT_MAX_BYTES)) params_.SetOneshotMaxBytes(EnvInt(HVD_ONESHOT_MAX_BYTES, 512 << 10), true);
     if (EnvIsSet(HVD_NVLS_MIN_BYTES)) params_.SetNvlsMinBytes(EnvInt(HVD_NVLS_MIN_BYTES, 1 << 20), true);
-    if (EnvIsSet(HVD_COMM_CTAS)) params_.SetCommCtas((int32_t)EnvInt(HVD_COMM_CTAS, 64), true);
+    if (EnvIsSet(HVD_COMM_CTAS)) params_.SetCommCtas((int32_t)EnvInt(HVD_COMM_CTAS, 128), true);
     params_.Initialize(cfg_.rank, EnvStr(HOROVOD_AUTOTUNE_LOG));
     params_.SetAutoTuning(EnvBool(HOROVOD_AUTOTUNE, false));
 
@@ -329,6 +329,28 @@ void Engine::PerformOperation(ProcessSet& ps, Response& r) {
       Completion c;
       if (sets_.Find(ranks) >= 0) c.status = Status::InvalidArgument("A process set with these ranks has already been added.");
       else c.last_joined_rank = sets_.Insert(MakeProcessSet(ranks));
+      for (auto& e : es) if (e && e->callback) e->callback(c);
+      return;
+    }
+    case ResponseType::SYMM_ALLOC: {
+      // collective allocation of a registered region on this set's peer-mapped team
+      Completion c;
+      int dev = -1;
+      for (auto& e : es) if (e) dev = e->device;
+      const size_t bytes = r.tensor_sizes.empty() ? 0 : (size_t)r.tensor_sizes[0];
+      std::shared_ptr<SymmTeam> team = dev >= 0 && ps.set_size() > 1 ? gpu_ops_->EnsureTeam(ps, dev) : nullptr;
+      uint64_t have = team ? 1 : 0;
+      ps.transport->AllreduceBits(&have, 1, nullptr, 0);
+      if (!have) {
+        c.status = Status::PreconditionError("symmetric memory is not available for this process set (single rank, "
+                                             "several hosts, or no peer access)");
+      } else {
+        std::string why;
+        int idx = team->AllocRegion(ps.transport.get(), bytes, cfg_.scope + "-" + std::to_string(cfg_.rendezvous_port) +
+                                                                    "-ps" + std::to_string(ps.id) + "-" + r.tensor_names[0], &why);
+        if (idx < 0) c.status = Status::UnknownError("symmetric allocation failed: " + why);
+        else c.aux_ptr = team->RegionPtr(idx);
+      }
       for (auto& e : es) if (e && e->callback) e->callback(c);
       return;
     }
@@ -586,6 +608,15 @@ Status Engine::EnqueueAllreduces(std::vector<std::shared_ptr<TensorTableEntry>>&
     e->type = type;
     Request q = MakeRequest(*e, ps->set_rank(), type);
     q.group_size = gid >= 0 ? (int32_t)es.size() : 0;
+    if (type == RequestType::ALLREDUCE && e->device >= 0 && e->input == e->output && es.size() == 1) {
+      // in-place tensor inside a registered symmetric region -> candidate for the zero-copy kernel
+      std::shared_ptr<SymmTeam> team;
+      { std::lock_guard<std::mutex> l(ps->team_mu); team = ps->team; }
+      int64_t off = 0;
+      int idx = -1;
+      if (team && (e->bytes() % 16) == 0 && team->FindRegion(e->input, e->bytes(), nullptr, &off, &idx) && (off % 16) == 0)
+        q.symm_key = ((int64_t)idx << 44) | off;
+    }
     msgs.push_back(std::move(q));
   }
   st = ps->queue.AddToTensorQueueMulti(es, msgs);
@@ -755,6 +786,29 @@ int32_t Engine::RemoveProcessSet(int32_t id, std::string* err) {
   Completion c = fut.get();
   if (!c.status.ok()) { if (err) *err = c.status.reason(); return -1; }
   return c.last_joined_rank;
+}
+
+// Collective (every member of the set must call it with the same size): allocates `bytes` of peer-mapped memory on
+// `device` and returns its local address. Tensors placed there take the zero-copy allreduce path.
+void* Engine::AllocSymmetric(size_t bytes, int device, int32_t psid, std::string* err) {
+  std::shared_ptr<ProcessSet> ps;
+  Status st = CheckSet(psid, &ps);
+  if (!st.ok()) { if (err) *err = st.reason(); return nullptr; }
+  auto e = std::make_shared<TensorTableEntry>();
+  e->name = SYMM_ALLOC_PREFIX + std::to_string(symm_alloc_counter_++);
+  e->type = RequestType::SYMM_ALLOC;
+  e->device = device;
+  std::promise<Completion> prom;
+  auto fut = prom.get_future();
+  e->callback = [&prom](const Completion& c) { prom.set_value(c); };
+  Request q = MakeRequest(*e, ps->set_rank(), RequestType::SYMM_ALLOC);
+  q.shape = {(int64_t)bytes};
+  st = ps->queue.AddToTensorQueue(e, q);
+  if (!st.ok()) { if (err) *err = st.reason(); return nullptr; }
+  RequestFlush();
+  Completion c = fut.get();
+  if (!c.status.ok()) { if (err) *err = c.status.reason(); return nullptr; }
+  return c.aux_ptr;
 }
 
 Status Engine::StartTimeline(const std::string& file, bool mark_cycles) {

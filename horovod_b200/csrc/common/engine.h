@@ -75,6 +75,8 @@ class Engine {
   int32_t AddProcessSet(const std::vector<int>& ranks, std::string* err);
   int32_t RemoveProcessSet(int32_t id, std::string* err);
   ProcessSetTable& process_sets() { return sets_; }
+  // Collective allocation of registered (peer-mapped) memory; returns the local address or nullptr (+err).
+  void* AllocSymmetric(size_t bytes, int device, int32_t process_set_id, std::string* err);
 
   // ---- timeline ----
   Status StartTimeline(const std::string& file, bool mark_cycles);
@@ -134,6 +136,7 @@ class Engine {
   std::string last_error_;
   std::atomic<uint64_t> cycles_{0}, fast_cycles_{0}, responses_{0};
   std::atomic<int> noname_counter_{0};
+  std::atomic<int> symm_alloc_counter_{0};
   std::atomic<int> join_device_{-1};  // CUDA device a joined rank contributes zeros from
 };
 

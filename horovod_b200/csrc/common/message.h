@@ -56,6 +56,7 @@ struct Request {
   ReduceOp reduce_op = ReduceOp::SUM;
   int32_t group_id = -1;
   int32_t group_size = 0;
+  int64_t symm_key = -1;  // (region << 44 | offset) when the tensor lives in registered symmetric memory, else -1
   void Serialize(ByteWriter& w) const;
   static Request Parse(ByteReader& r);
 };
@@ -69,7 +70,7 @@ struct RequestList {
 
 enum class ResponseType : uint8_t {
   ALLREDUCE = 0, ALLGATHER = 1, BROADCAST = 2, JOIN = 3, ADASUM = 4, ALLTOALL = 5,
-  BARRIER = 6, REDUCESCATTER = 7, PROCESS_SET_ADD = 8, PROCESS_SET_REMOVE = 9, ERROR = 10,
+  BARRIER = 6, REDUCESCATTER = 7, PROCESS_SET_ADD = 8, PROCESS_SET_REMOVE = 9, ERROR = 10, SYMM_ALLOC = 11,
 };
 const char* ResponseTypeName(ResponseType t);
 
@@ -88,6 +89,7 @@ struct Response {
   int32_t last_joined_rank = -1;
   int32_t root_rank = 0;
   int32_t group_id = -1;              // not serialised beyond fusion decisions
+  int64_t symm_key = -1;              // >= 0: every rank holds this tensor at the same place of the same registered region
   void Serialize(ByteWriter& w) const;
   static Response Parse(ByteReader& r);
 };

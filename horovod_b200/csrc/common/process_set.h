@@ -28,6 +28,7 @@ struct ProcessSet {
   std::unique_ptr<Controller> controller;
   // GPU state, created lazily by the first GPU collective on this set
   std::shared_ptr<SymmTeam> team;
+  mutable std::mutex team_mu;  // `team` is published by the background thread, read by enqueueing threads
   bool team_tried = false;
   std::shared_ptr<NcclComm> nccl;
   bool nccl_tried = false;

@@ -18,7 +18,7 @@ ResponseCache::State ResponseCache::Cached(const Request& r) const {
   const Slot& s = slots_[it->second];
   bool same = s.params_valid && s.type == r.type && s.dtype == r.dtype && s.shape == r.shape &&
               s.device == r.device && s.root_rank == r.root_rank && s.prescale == r.prescale &&
-              s.postscale == r.postscale && s.op == r.reduce_op;
+              s.postscale == r.postscale && s.op == r.reduce_op && s.symm_key == r.symm_key;
   return same ? State::HIT : State::INVALID;
 }
 
@@ -53,7 +53,7 @@ uint32_t ResponseCache::Put(const Response& single, const Request* local) {
   if (local) {
     s.type = local->type; s.dtype = local->dtype; s.shape = local->shape; s.device = local->device;
     s.root_rank = local->root_rank; s.prescale = local->prescale; s.postscale = local->postscale;
-    s.op = local->reduce_op;
+    s.op = local->reduce_op; s.symm_key = local->symm_key;
   }
   lru_.push_back(bit);
   s.lru_it = std::prev(lru_.end());

@@ -43,7 +43,7 @@ class ResponseCache {
     Response response;
     // this rank's request parameters
     RequestType type; DataType dtype; std::vector<int64_t> shape; int32_t device; int32_t root_rank;
-    double prescale, postscale; ReduceOp op;
+    double prescale, postscale; ReduceOp op; int64_t symm_key;
     std::list<uint32_t>::iterator lru_it;
   };
   uint32_t capacity_ = 1024;

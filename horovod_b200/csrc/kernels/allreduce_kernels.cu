@@ -289,6 +289,102 @@ allreduce_kernel(const __grid_constant__ CommParams cp, const __grid_constant__ 
   if (threadIdx.x == 0) cp.epochs[cta] = epoch;
 }
 
+// ---------------------------------------------------------------------------
+// Zero-copy allreduce on REGISTERED tensors (memory allocated with hvd.symm_empty / the bucketed DistributedOptimizer):
+// the user tensor itself is peer-mapped, so there is no pack and no unpack — the kernel is only the NVLink phase.
+//   barrier A   every rank's data is final (the kernel was ordered after the producer's ready event)
+//   reduce      rank r sums the chunks it owns out of all N tensors and stores the result into all N tensors
+//               (multimem.ld_reduce + multimem.st when the region is multicast-bound: the NVSwitch does the add
+//               and the broadcast); a chunk has exactly one reader — its owner — so writing in place is safe
+//   barrier B   every result landed
+template <typename W, int NR>
+__global__ void __launch_bounds__(kThreads, 2)
+inplace_allreduce_kernel(const __grid_constant__ CommParams cp, const __grid_constant__ InplaceArgs a) {
+  using A = typename Traits<W>::Acc;
+  using S = typename ScaleOf<A>::type;
+  constexpr int NW = 16 / (int)sizeof(W);
+  constexpr int U = 8 / NR;
+  const int cta = blockIdx.x, grid = gridDim.x;
+  uint32_t epoch = cp.epochs[cta];
+  const int64_t total = a.bytes;  // multiple of 16
+  const int chunk_bytes = a.chunk_bytes;
+  const int64_t nchunks = (total + chunk_bytes - 1) / chunk_bytes;
+  const S scale = (S)a.scale;
+  bool alive = peer_barrier(cp, epoch, cta);
+  for (int64_t c = cta, k = 0; c < nchunks && alive; c += grid, ++k) {
+    if ((int)((k + cta) % cp.nranks) != cp.rank) continue;
+    const int64_t lo = c * chunk_bytes;
+    const int64_t hi = lo + chunk_bytes < total ? lo + chunk_bytes : total;
+    if (a.use_multicast) {
+      if constexpr (Nvls<W>::ok) {
+        constexpr int UN = 4;
+        char* mc = reinterpret_cast<char*>(a.mc);
+        for (int64_t o0 = lo + (int64_t)threadIdx.x * 16; o0 < hi; o0 += (int64_t)UN * kRowBytes) {
+          uint4 v[UN];
+#pragma unroll
+          for (int j = 0; j < UN; ++j) { const int64_t o = o0 + (int64_t)j * kRowBytes; if (o < hi) v[j] = Nvls<W>::ld_reduce(mc + o); }
+#pragma unroll
+          for (int j = 0; j < UN; ++j) {
+            const int64_t o = o0 + (int64_t)j * kRowBytes;
+            if (o < hi) {
+              if (scale != (S)1) {
+                A acc[NW];
+                unpack_vec<W, NW>(v[j], acc);
+#pragma unroll
+                for (int i = 0; i < NW; ++i) acc[i] = apply_scale<A>(acc[i], scale);
+                v[j] = pack_vec<W, NW>(acc);
+              }
+              multimem_st(mc + o, v[j]);
+            }
+          }
+        }
+      }
+    } else {
+      for (int64_t o0 = lo + (int64_t)threadIdx.x * 16; o0 < hi; o0 += (int64_t)U * kRowBytes) {
+        uint4 v[U][NR];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const int64_t o = o0 + (int64_t)j * kRowBytes;
+          if (o < hi) {
+#pragma unroll
+            for (int p = 0; p < NR; ++p) {
+              int q = cp.rank + p; if (q >= cp.nranks) q -= cp.nranks;
+              if (p < cp.nranks) v[j][p] = ld_stream(reinterpret_cast<const char*>(a.ptr[q]) + o);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const int64_t o = o0 + (int64_t)j * kRowBytes;
+          if (o < hi) {
+            A acc[NW];
+            peer_combine<W, NR>(cp, v[j], a.op, acc);
+#pragma unroll
+            for (int i = 0; i < NW; ++i) acc[i] = apply_scale<A>(acc[i], scale);
+            const uint4 r = pack_vec<W, NW>(acc);
+#pragma unroll
+            for (int p = 0; p < NR; ++p) {
+              int q = cp.rank + p; if (q >= cp.nranks) q -= cp.nranks;
+              if (p < cp.nranks) st_stream(reinterpret_cast<char*>(a.ptr[q]) + o, r);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (alive) peer_barrier(cp, epoch, cta);
+  if (threadIdx.x == 0) cp.epochs[cta] = epoch;
+}
+
+template <typename W>
+cudaError_t launch_inplace(const CommParams& cp, const InplaceArgs& a, cudaStream_t s) {
+  if (cp.nranks <= 2) inplace_allreduce_kernel<W, 2><<<a.ctas, kThreads, 0, s>>>(cp, a);
+  else if (cp.nranks <= 4) inplace_allreduce_kernel<W, 4><<<a.ctas, kThreads, 0, s>>>(cp, a);
+  else inplace_allreduce_kernel<W, 8><<<a.ctas, kThreads, 0, s>>>(cp, a);
+  CountKernelLaunch();
+  return cudaGetLastError();
+}
+
 // Stand-alone pack / unpack (NCCL baseline path): whole grid strides over rows.
 template <typename T, typename W>
 __global__ void __launch_bounds__(kThreads)
@@ -384,6 +480,25 @@ cudaError_t LaunchAllreduce(const CommParams& cp, const AllreduceArgs& args, cud
   if (chunk < kRowBytes) chunk = kRowBytes;
   if (chunk > kChunkBytes) chunk = kChunkBytes;
   HVD_DISPATCH(args.dtype, args.wire_dtype, launch_tw, cp, args, chunk, stream)
+}
+
+cudaError_t LaunchInplaceAllreduce(const CommParams& cp, const InplaceArgs& args, cudaStream_t stream) {
+  if (args.ctas < 1 || args.ctas > kMaxCtas || args.bytes <= 0 || (args.bytes & 15)) return cudaErrorInvalidValue;
+  InplaceArgs a = args;
+  int64_t want = a.bytes / ((int64_t)a.ctas * cp.nranks);
+  int chunk = (int)((want / kRowBytes) * kRowBytes);
+  if (chunk < kRowBytes) chunk = kRowBytes;
+  if (chunk > kChunkBytes) chunk = kChunkBytes;
+  a.chunk_bytes = chunk;
+  switch (a.dtype) {
+    case 7: return launch_inplace<float>(cp, a, stream);
+    case 6: return launch_inplace<__half>(cp, a, stream);
+    case 10: return launch_inplace<__nv_bfloat16>(cp, a, stream);
+    case 8: if (a.use_multicast) return cudaErrorInvalidValue; return launch_inplace<double>(cp, a, stream);
+    case 4: if (a.use_multicast) return cudaErrorInvalidValue; return launch_inplace<int32_t>(cp, a, stream);
+    case 5: if (a.use_multicast) return cudaErrorInvalidValue; return launch_inplace<int64_t>(cp, a, stream);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 cudaError_t LaunchPackUnpack(void* buffer, const TensorDesc* descs, int ndesc, int64_t total_bytes, int dtype,

@@ -75,6 +75,22 @@ struct AllreduceArgs {
 // unsupported dtype combinations.
 cudaError_t LaunchAllreduce(const CommParams& cp, const AllreduceArgs& args, cudaStream_t stream);
 
+// Zero-copy allreduce on a registered (peer-mapped) tensor: ptr[r] = the tensor's address in rank r's region as
+// mapped into THIS process, mc = its multicast alias (or nullptr). In place on every rank. SUM-like ops only for
+// multicast; bytes must be a multiple of 16.
+struct InplaceArgs {
+  void* ptr[kMaxPeers];
+  void* mc;
+  int64_t bytes;
+  double scale;       // prescale * postscale (valid for SUM / AVERAGE)
+  int op;
+  int dtype;
+  int use_multicast;
+  int ctas;
+  int chunk_bytes;    // filled in by the launcher
+};
+cudaError_t LaunchInplaceAllreduce(const CommParams& cp, const InplaceArgs& args, cudaStream_t stream);
+
 // Generic "pack -> barrier -> pull" used by allgather / broadcast / alltoall.
 // send: local src -> local symmetric buffer offset; recv: peer buffer offset -> local dst.
 struct CopyDesc {

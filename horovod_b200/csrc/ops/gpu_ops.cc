@@ -174,8 +174,9 @@ std::shared_ptr<SymmTeam> GpuOps::EnsureTeam(ProcessSet& ps, int device) {
   t->AllreduceBits(&ok, 1, nullptr, 0);
   if (!ok) { LOG(INFO) << "process set " << ps.id << " spans hosts: GPU collectives are staged through the CPU transport"; return nullptr; }
   size_t bytes = ps.id == 0 ? env_.symm_buffer_bytes : std::min<size_t>(env_.symm_buffer_bytes, 32ull << 20);
-  ps.team = SymmTeam::Create(t, device, bytes, env_.want_multicast,
+  std::shared_ptr<SymmTeam> created = SymmTeam::Create(t, device, bytes, env_.want_multicast,
                              std::to_string(tag[0]) + "-" + std::to_string(tag[1]) + "-" + std::to_string(ps.id), &why);
+  { std::lock_guard<std::mutex> l(ps.team_mu); ps.team = created; }
   if (!ps.team) LOG(WARNING) << "peer-mapped symmetric memory unavailable for process set " << ps.id << " (" << why
                              << "); GPU collectives fall back to host staging";
   if (ps.team) ps.team->set_timeout_seconds(EnvDouble("HVD_KERNEL_TIMEOUT_SECONDS", 60.0));
@@ -218,6 +219,34 @@ Status GpuOps::Allreduce(ProcessSet& ps, Entries& es, const Response& r, int dev
       st = StagedOnHost(ps, es, r, device, s);
       if (!st.ok()) return st;
     } else {
+      // ---- zero-copy path: the tensor lives in registered symmetric memory on EVERY rank (negotiated symm_key) ----
+      const int64_t zc_bytes = pieces.size() == 1 ? pieces[0].count * (int64_t)esz : 0;
+      if (r.symm_key >= 0 && pieces.size() == 1 && es[0] && zc_bytes > env_.params->oneshot_max_bytes && env_.variant != "oneshot") {
+        SymmTeam::RegionView view;
+        int64_t off = 0;
+        if (team->FindRegion(pieces[0].in, (size_t)zc_bytes, &view, &off) && (((int64_t)(r.symm_key & ((1ll << 44) - 1))) == off)) {
+          kern::InplaceArgs ia {};
+          for (int p = 0; p < n; ++p) ia.ptr[p] = (char*)view.ptr[p] + off;
+          ia.mc = view.mc ? (char*)view.mc + off : nullptr;
+          ia.bytes = zc_bytes;
+          ia.scale = r.prescale * r.postscale;
+          ia.op = (int)r.reduce_op;
+          ia.dtype = (int)r.dtype;
+          const bool sum_like = r.reduce_op == ReduceOp::SUM || r.reduce_op == ReduceOp::AVERAGE;
+          ia.use_multicast = (ia.mc && sum_like && env_.variant != "twoshot" && (n >= 4 || env_.variant == "nvls") && zc_bytes >= env_.params->nvls_min_bytes &&
+                              (r.dtype == DataType::FLOAT32 || r.dtype == DataType::FLOAT16 || r.dtype == DataType::BFLOAT16)) ? 1 : 0;
+          if (sum_like || (r.prescale == 1.0 && r.postscale == 1.0)) {
+            ia.ctas = (int)std::max<int64_t>(1, std::min<int64_t>(env_.params->comm_ctas, (zc_bytes + 4096ll * n - 1) / (4096ll * n)));
+            kern::CommParams cp = team->Params(team->NextSlot());
+            if (env_.timeline && env_.timeline->Initialized())
+              env_.timeline->ActivityStartAll(es, ia.use_multicast ? HVD_ACT_P2P_ALLREDUCE_NVLS : HVD_ACT_P2P_ALLREDUCE_TWOSHOT);
+            cudaError_t ce = kern::LaunchInplaceAllreduce(cp, ia, s);
+            if (ce != cudaSuccess) return Status::UnknownError(std::string("zero-copy allreduce launch failed: ") + cudaGetErrorString(ce));
+            ctx.TempFreeAll(device, s);
+            return FinishEvent(device, s, es.size(), done);
+          }
+        }
+      }
       // wire dtype: optional in-kernel compression of fp32 sums
       DataType wire = r.dtype;
       if (r.dtype == DataType::FLOAT32 && (env_.wire_dtype == DataType::BFLOAT16 || env_.wire_dtype == DataType::FLOAT16) &&
@@ -246,11 +275,14 @@ Status GpuOps::Allreduce(ProcessSet& ps, Entries& es, const Response& r, int dev
         else if (env_.variant == "nvls" && nvls_ok) variant = kern::kNvls;
         else {
           if (seg_bytes <= tp.oneshot_max_bytes) variant = kern::kOneShot;
-          else if (nvls_ok && seg_bytes >= tp.nvls_min_bytes) variant = kern::kNvls;
+          else if (nvls_ok && n >= 4 && seg_bytes >= tp.nvls_min_bytes) variant = kern::kNvls;  // in-switch reduction pays off from 4 GPUs (measured: slower than two-shot at N=2)
         }
         a.variant = variant;
         int64_t per = variant == kern::kOneShot ? 8192 : (int64_t)4096 * n;  // >= 2 rows (one-shot) or one row per rank (two-shot) per CTA
-        a.ctas = (int)std::max<int64_t>(1, std::min<int64_t>(tp.comm_ctas, (seg_bytes + per - 1) / per));
+        // small messages are latency bound (few CTAs = cheap barrier, SMs left to compute); large ones need many loads in flight
+        const int64_t cap_ctas = seg_bytes <= (1 << 20) ? std::min<int64_t>(tp.comm_ctas, 16)
+                               : seg_bytes <= (16 << 20) ? std::min<int64_t>(tp.comm_ctas, 64) : tp.comm_ctas;
+        a.ctas = (int)std::max<int64_t>(1, std::min<int64_t>(cap_ctas, (seg_bytes + per - 1) / per));
         if (a.ndesc <= kern::kInlineDescs) {
           memcpy(a.inline_descs, descs.data(), descs.size() * sizeof(kern::TensorDesc));
           a.descs = nullptr;
@@ -297,7 +329,7 @@ Status GpuOps::NcclAllreduce(ProcessSet& ps, Entries& es, const Response& r, int
     ps.nccl = NcclCreateComm(ps.transport.get(), device, &why);
     if (!ps.nccl) LOG(WARNING) << "NCCL baseline unavailable: " << why;
   }
-  if (!ps.nccl) return StagedOnHost(ps, es, r, device, s);
+  if (!ps.nccl || !NcclSupportsDtype(r.dtype)) return StagedOnHost(ps, es, r, device, s);  // e.g. int16: NCCL has no such type
   GpuContext& ctx = GpuContext::Get();
   const size_t esz = DataTypeSize(r.dtype);
   std::vector<Piece> pieces;

@@ -83,8 +83,10 @@ class GpuOps {
   // Description of the data path chosen for a set (for hvd.gpu_backend_info()).
   std::string Describe(ProcessSet& ps);
 
- private:
+  // Lazily creates (collectively) the peer-mapped team of a process set.
   std::shared_ptr<SymmTeam> EnsureTeam(ProcessSet& ps, int device);
+
+ private:
   Status NcclAllreduce(ProcessSet& ps, Entries& es, const Response& r, int device, cudaStream_t s);
   Status StagedOnHost(ProcessSet& ps, Entries& es, const Response& r, int device, cudaStream_t s);
   // returns InProgress() when the kernel path does not apply (caller falls back to host staging)

@@ -55,6 +55,8 @@ NcclComm::~NcclComm() {
   if (comm && N().ok) N().CommDestroy((ncclComm_t)comm);
 }
 
+bool NcclSupportsDtype(DataType t) { ncclDataType_t o; return MapType(t, &o); }
+
 bool NcclAvailable(std::string* why) {
   if (!N().ok && why) *why = N().err;
   return N().ok;

@@ -18,6 +18,7 @@ struct NcclComm {
 };
 
 bool NcclAvailable(std::string* why = nullptr);
+bool NcclSupportsDtype(DataType t);
 // Collective over `t`.
 std::shared_ptr<NcclComm> NcclCreateComm(Transport* t, int device, std::string* why);
 // dtype/op follow hvd enums; AVERAGE must already be folded into postscale by the caller.

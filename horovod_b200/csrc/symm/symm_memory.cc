@@ -8,6 +8,7 @@
 #include <poll.h>
 #include <cstring>
 #include <fstream>
+#include <mutex>
 #include <sstream>
 #include "../common/logging.h"
 
@@ -195,10 +196,41 @@ struct SymmTeam::Impl {
   std::vector<void*> sim_all;  // SIM: allocations owned by rank 0's impl
   void* epochs = nullptr;
   int* abort_host = nullptr;
+  // registered (zero-copy) regions: user tensors that live in peer-mapped memory
+  struct Region {
+    size_t bytes = 0;
+    std::vector<CUmemGenericAllocationHandle> handles;  // VMM
+    std::vector<CUdeviceptr> vas;
+    CUmemGenericAllocationHandle mc_handle = 0;
+    CUdeviceptr mc_va = 0;
+    bool mc_bound = false;
+    std::vector<void*> ptrs;                             // IPC: [rank] own cudaMalloc, others ipc-opened
+  };
+  std::vector<Region> regions;
+  std::mutex region_mu;
+  void FreeRegion(Region& r) {
+    Driver& d = Drv();
+    if (kind == Kind::VMM) {
+      if (r.mc_va) { d.p_cuMemUnmap(r.mc_va, r.bytes); d.p_cuMemAddressFree(r.mc_va, r.bytes); }
+      if (r.mc_bound && r.mc_handle) { CUdevice dev; d.p_cuDeviceGet(&dev, device); d.p_cuMulticastUnbind(r.mc_handle, dev, 0, r.bytes); }
+      if (r.mc_handle) d.p_cuMemRelease(r.mc_handle);
+      for (size_t i = 0; i < r.vas.size(); ++i) {
+        if (r.vas[i]) { d.p_cuMemUnmap(r.vas[i], r.bytes); d.p_cuMemAddressFree(r.vas[i], r.bytes); }
+        if (r.handles[i]) d.p_cuMemRelease(r.handles[i]);
+      }
+    } else {
+      for (int i = 0; i < (int)r.ptrs.size(); ++i) {
+        if (!r.ptrs[i]) continue;
+        if (kind == Kind::SIM || i == rank) cudaFree(r.ptrs[i]); else cudaIpcCloseMemHandle(r.ptrs[i]);
+      }
+    }
+    r = Region();
+  }
 
   ~Impl() {
     cudaSetDevice(device);
     cudaDeviceSynchronize();
+    for (auto& r : regions) FreeRegion(r);
     Driver& d = Drv();
     if (kind == Kind::VMM) {
       if (mc_va) { d.p_cuMemUnmap(mc_va, alloc_bytes); d.p_cuMemAddressFree(mc_va, alloc_bytes); }
@@ -418,6 +450,148 @@ std::shared_ptr<SymmTeam> SymmTeam::Create(Transport* t, int device, size_t buff
   team->abort_host_ = impl->abort_host;
   if (!AllAgree(t, good)) { cudaGetLastError(); return fail("flag / epoch initialisation failed"); }
   return team;
+}
+
+// ---------------------------------------------------------------------------
+// registered regions
+
+int SymmTeam::AllocRegion(Transport* t, size_t bytes, const std::string& tag, std::string* why) {
+  auto fail = [&](const std::string& m) { if (why) *why = m; return -1; };
+  Impl& im = *impl_;
+  if (im.kind == Impl::Kind::SIM) return fail("simulated teams use AllocRegionSim");
+  cudaSetDevice(device_);
+  const int n = nranks_, me = rank_;
+  Driver& d = Drv();
+  Impl::Region reg;
+  std::vector<void*> ptr(n, nullptr);
+  void* mc_ptr = nullptr;
+  if (im.kind == Impl::Kind::VMM) {
+    CUmemAllocationProp prop {};
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = device_;
+    prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    size_t gran = 2 << 20, g = 0;
+    if (d.p_cuMemGetAllocationGranularity(&g, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) == CUDA_SUCCESS && g) gran = g;
+    const bool use_mc = has_multicast();
+    CUmulticastObjectProp mcprop {};
+    if (use_mc) {
+      mcprop.numDevices = n; mcprop.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR; mcprop.size = RoundUp(bytes, gran);
+      if (d.p_cuMulticastGetGranularity(&g, &mcprop, CU_MULTICAST_GRANULARITY_RECOMMENDED) == CUDA_SUCCESS && g > gran) gran = g;
+    }
+    const size_t alloc = RoundUp(bytes, gran);
+    reg.bytes = alloc;
+    reg.handles.assign(n, 0);
+    reg.vas.assign(n, 0);
+    bool good = d.p_cuMemCreate(&reg.handles[me], alloc, &prop, 0) == CUDA_SUCCESS;
+    int myfd = -1;
+    if (good) good = d.p_cuMemExportToShareableHandle(&myfd, reg.handles[me], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) == CUDA_SUCCESS;
+    FdChannel ch;
+    if (good) good = ch.Open("hvd-symm-" + tag, me);
+    if (!AllAgree(t, good)) { if (myfd >= 0) close(myfd); im.FreeRegion(reg); return fail("region allocation / fd export failed (out of memory?)"); }
+    std::vector<int> fds(n, -1);
+    for (int p = 0; p < n && good; ++p) if (p != me) good = ch.SendFd(p, myfd, 0, me);
+    for (int k = 0; k < n - 1 && good; ++k) {
+      int fd = -1; int32_t kind = 0, from = -1;
+      good = ch.RecvFd(&fd, &kind, &from, 30000) && kind == 0 && from >= 0 && from < n && from != me;
+      if (good) fds[from] = fd;
+    }
+    close(myfd);
+    for (int p = 0; p < n && good; ++p) {
+      if (p == me) continue;
+      good = d.p_cuMemImportFromShareableHandle(&reg.handles[p], (void*)(uintptr_t)fds[p], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) == CUDA_SUCCESS;
+    }
+    for (int fd : fds) if (fd >= 0) close(fd);
+    CUmemAccessDesc acc {};
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE; acc.location.id = device_; acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    for (int p = 0; p < n && good; ++p) {
+      good = d.p_cuMemAddressReserve(&reg.vas[p], alloc, gran, 0, 0) == CUDA_SUCCESS &&
+             d.p_cuMemMap(reg.vas[p], alloc, 0, reg.handles[p], 0) == CUDA_SUCCESS &&
+             d.p_cuMemSetAccess(reg.vas[p], alloc, &acc, 1) == CUDA_SUCCESS;
+      ptr[p] = (void*)reg.vas[p];
+    }
+    if (!AllAgree(t, good)) { im.FreeRegion(reg); return fail("mapping the peers' region failed"); }
+    if (use_mc) {
+      bool mg = true;
+      int mcfd = -1;
+      CUdevice cudev;
+      d.p_cuDeviceGet(&cudev, device_);
+      mcprop.size = alloc;
+      if (me == 0) {
+        mg = d.p_cuMulticastCreate(&reg.mc_handle, &mcprop) == CUDA_SUCCESS &&
+             d.p_cuMemExportToShareableHandle(&mcfd, reg.mc_handle, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) == CUDA_SUCCESS;
+        for (int p = 1; p < n && mg; ++p) mg = ch.SendFd(p, mcfd, 1, 0);
+        if (mcfd >= 0) close(mcfd);
+      }
+      mg = AllAgree(t, mg);
+      if (mg && me != 0) {
+        int fd = -1; int32_t kind = 0, from = -1;
+        mg = ch.RecvFd(&fd, &kind, &from, 30000) && kind == 1;
+        if (mg) mg = d.p_cuMemImportFromShareableHandle(&reg.mc_handle, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) == CUDA_SUCCESS;
+        if (fd >= 0) close(fd);
+      }
+      if (mg) mg = d.p_cuMulticastAddDevice(reg.mc_handle, cudev) == CUDA_SUCCESS;
+      mg = AllAgree(t, mg);
+      if (mg) { mg = d.p_cuMulticastBindMem(reg.mc_handle, 0, reg.handles[me], 0, alloc, 0) == CUDA_SUCCESS; reg.mc_bound = mg; }
+      if (mg) mg = d.p_cuMemAddressReserve(&reg.mc_va, alloc, gran, 0, 0) == CUDA_SUCCESS &&
+                   d.p_cuMemMap(reg.mc_va, alloc, 0, reg.mc_handle, 0) == CUDA_SUCCESS &&
+                   d.p_cuMemSetAccess(reg.mc_va, alloc, &acc, 1) == CUDA_SUCCESS;
+      mg = AllAgree(t, mg);
+      if (mg) mc_ptr = (void*)reg.mc_va;
+      else if (reg.mc_va) { d.p_cuMemUnmap(reg.mc_va, alloc); d.p_cuMemAddressFree(reg.mc_va, alloc); reg.mc_va = 0; }
+    }
+  } else {  // IPC
+    reg.bytes = RoundUp(bytes, 2 << 20);
+    reg.ptrs.assign(n, nullptr);
+    bool good = cudaMalloc(&reg.ptrs[me], reg.bytes) == cudaSuccess;
+    cudaIpcMemHandle_t h {};
+    if (good) good = cudaIpcGetMemHandle(&h, reg.ptrs[me]) == cudaSuccess;
+    if (!AllAgree(t, good)) { cudaGetLastError(); im.FreeRegion(reg); return fail("cudaMalloc / cudaIpcGetMemHandle failed"); }
+    std::vector<uint8_t> mineb((uint8_t*)&h, (uint8_t*)&h + sizeof h);
+    std::vector<std::vector<uint8_t>> all;
+    t->GatherBytes(mineb, &all, 0);
+    std::vector<uint8_t> cat;
+    if (me == 0) for (auto& v : all) cat.insert(cat.end(), v.begin(), v.end());
+    t->BcastBytes(&cat, 0);
+    for (int p = 0; p < n && good; ++p) {
+      if (p == me) continue;
+      cudaIpcMemHandle_t ph;
+      memcpy(&ph, cat.data() + (size_t)p * sizeof ph, sizeof ph);
+      good = cudaIpcOpenMemHandle(&reg.ptrs[p], ph, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+    }
+    if (!AllAgree(t, good)) { cudaGetLastError(); im.FreeRegion(reg); return fail("cudaIpcOpenMemHandle failed"); }
+    for (int p = 0; p < n; ++p) ptr[p] = reg.ptrs[p];
+  }
+  cudaMemset(ptr[me], 0, reg.bytes);
+  cudaDeviceSynchronize();
+  AllAgree(t, true);  // nobody touches a peer's region before it is zero-filled
+  std::lock_guard<std::mutex> l(im.region_mu);
+  RegionView v;
+  v.bytes = reg.bytes; v.mc = mc_ptr;
+  for (int p = 0; p < n; ++p) v.ptr[p] = ptr[p];
+  regions_.push_back(v);
+  im.regions.push_back(std::move(reg));
+  return (int)regions_.size() - 1;
+}
+
+bool SymmTeam::FindRegion(const void* p, size_t len, RegionView* view, int64_t* offset, int* index) const {
+  std::lock_guard<std::mutex> l(impl_->region_mu);
+  const char* c = (const char*)p;
+  for (size_t i = 0; i < regions_.size(); ++i) {
+    const char* base = (const char*)regions_[i].ptr[rank_];
+    if (c >= base && c + len <= base + regions_[i].bytes) {
+      if (view) *view = regions_[i];
+      if (offset) *offset = c - base;
+      if (index) *index = (int)i;
+      return true;
+    }
+  }
+  return false;
+}
+
+void* SymmTeam::RegionPtr(int index) const {
+  std::lock_guard<std::mutex> l(impl_->region_mu);
+  return index >= 0 && index < (int)regions_.size() ? regions_[index].ptr[rank_] : nullptr;
 }
 
 std::vector<std::shared_ptr<SymmTeam>> SymmTeam::CreateSimulated(int n, int device, size_t buffer_bytes) {

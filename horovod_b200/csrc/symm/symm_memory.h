@@ -67,6 +67,14 @@ class SymmTeam {
   void set_timeout_seconds(double s) { timeout_ns_ = s > 0 ? (unsigned long long)(s * 1e9) : 0; }
   const std::string& backend() const { return backend_; }  // "vmm", "vmm+mc", "ipc", "sim"
 
+  // ---- registered regions: user tensors allocated in peer-mapped memory get a zero-copy collective path ----
+  struct RegionView { void* ptr[kern::kMaxPeers] = {}; void* mc = nullptr; size_t bytes = 0; };
+  // Collective over the team's transport (background thread). Returns the region index or -1.
+  int AllocRegion(Transport* t, size_t bytes, const std::string& unique_tag, std::string* why);
+  // Is [p, p+len) inside a registered region of THIS rank?
+  bool FindRegion(const void* p, size_t len, RegionView* view, int64_t* offset, int* index = nullptr) const;
+  void* RegionPtr(int index) const;
+
  private:
   SymmTeam() = default;
   struct Impl;
@@ -81,6 +89,7 @@ class SymmTeam {
   int slot_ = 0;
   unsigned long long timeout_ns_ = 0;
   std::string backend_;
+  std::vector<RegionView> regions_;
   std::shared_ptr<Impl> impl_;  // owns driver handles / mappings
 };
 

@@ -13,6 +13,8 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
 #include <cuda_runtime.h>
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <unordered_map>
@@ -26,7 +28,7 @@ namespace {
 
 // ---- handle manager --------------------------------------------------------
 struct HandleState {
-  bool done = false;
+  std::atomic<bool> done{false};
   Status status;
   std::vector<SharedEvent*> events;  // one per fused response that carried members of this handle
   int device = CPU_DEVICE_ID;
@@ -70,10 +72,18 @@ class HandleManager {
     if (--st.pending <= 0) { st.done = true; cv_.notify_all(); }
   }
   void Wait(const std::shared_ptr<HandleState>& st) {
+    // a fused NVLink allreduce completes in tens of microseconds: spin briefly before paying a futex sleep + wake-up
+    const auto spin_end = std::chrono::steady_clock::now() + std::chrono::microseconds(200);
+    while (!st->done.load(std::memory_order_acquire) && std::chrono::steady_clock::now() < spin_end) {
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    if (st->done.load(std::memory_order_acquire)) { std::lock_guard<std::mutex> l(mu_); return; }
     std::unique_lock<std::mutex> l(mu_);
-    cv_.wait(l, [&] { return st->done; });
+    cv_.wait(l, [&] { return st->done.load(); });
   }
-  bool Done(const std::shared_ptr<HandleState>& st) { std::lock_guard<std::mutex> l(mu_); return st->done; }
+  bool Done(const std::shared_ptr<HandleState>& st) { return st->done.load(std::memory_order_acquire); }
   void Release(int h) { std::lock_guard<std::mutex> l(mu_); map_.erase(h); }
   void Reset() {
     std::lock_guard<std::mutex> l(mu_);
@@ -400,6 +410,23 @@ void Reset() {
   g_noname_counters.clear();
 }
 
+// ---- registered symmetric memory -------------------------------------------------------------
+// Collective: returns a uint8 CUDA tensor of `nbytes` that lives in peer-mapped memory. In-place allreduces on (views
+// of) it skip the fusion-buffer pack/unpack and run the zero-copy NVLink kernel. The memory stays valid until
+// hvd.shutdown().
+at::Tensor SymmEmpty(int64_t nbytes, int device, int process_set_id) {
+  TORCH_CHECK(nbytes > 0, "symm_empty: size must be positive");
+  std::string err;
+  void* p = nullptr;
+  {
+    py::gil_scoped_release release;
+    p = Engine::Get().AllocSymmetric((size_t)nbytes, device, process_set_id, &err);
+  }
+  if (!p) throw std::runtime_error("symm_empty failed: " + err);
+  auto opts = at::TensorOptions().dtype(at::kByte).device(at::kCUDA, device);
+  return at::from_blob(p, {nbytes}, [](void*) {}, opts);
+}
+
 // ---- fused optimizer kernels (B200-native extra; see kernels/optim_kernels.cu) --------------
 void FusedSgdStep(std::vector<at::Tensor> params, std::vector<at::Tensor> grads, std::vector<at::Tensor> momenta, double lr,
                   double momentum, double dampening, double weight_decay, bool nesterov, double grad_scale, bool first_step) {
@@ -470,6 +497,7 @@ PYBIND11_MODULE(_hvd_torch, m) {
   m.def("poll", &PollHandle);
   m.def("wait_and_clear", &WaitAndClear);
   m.def("reset", &Reset);
+  m.def("symm_empty", &SymmEmpty);
   m.def("fused_sgd_step", &FusedSgdStep);
   m.def("fused_adam_step", &FusedAdamStep);
 }

@@ -587,3 +587,36 @@ def barrier(process_set=global_process_set):
         _native().wait_and_clear(handle)
     except RuntimeError as e:
         raise HorovodInternalError(e)
+
+
+# ---------------------------------------------------------------------------
+# registered symmetric memory (new: no equivalent in the reference)
+
+def symm_empty(shape, dtype=torch.float32, device=None, process_set=global_process_set):
+    """COLLECTIVE. Returns an uninitialised CUDA tensor that lives in peer-mapped ("symmetric") memory of the process
+    set. In-place allreduces on it (or on a view of it that every rank takes identically) skip the fusion-buffer
+    pack/unpack and run the zero-copy NVLink kernel (`multimem` in-switch reduction where available).
+
+    Every member of the process set must call this with the same size. The memory is released by hvd.shutdown();
+    do not use the tensor afterwards."""
+    if isinstance(shape, int):
+        shape = (shape,)
+    numel = 1
+    for s in shape:
+        numel *= int(s)
+    itemsize = torch.empty(0, dtype=dtype).element_size()
+    nbytes = max(16, (numel * itemsize + 15) // 16 * 16)
+    if device is None:
+        device = torch.cuda.current_device()
+    dev_index = device.index if isinstance(device, torch.device) else int(device)
+    try:
+        raw = _native().symm_empty(nbytes, dev_index, process_set.process_set_id)
+    except RuntimeError as e:
+        raise HorovodInternalError(e)
+    return raw[:numel * itemsize].view(dtype).view(*shape)
+
+
+def symm_available(process_set=global_process_set):
+    """True when the zero-copy path can be used: CUDA, more than one rank, everything on one NVLink domain."""
+    return torch.cuda.is_available() and is_initialized() and process_set.size() is not None and process_set.size() > 1 \
+        and os.environ.get('HVD_GPU_BACKEND', 'p2p') == 'p2p' and os.environ.get('HOROVOD_ELASTIC') != '1'

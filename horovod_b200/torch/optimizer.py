@@ -8,11 +8,13 @@ with no autograd-graph surgery), completion is event-chained (no host sync per
 tensor), and `fused=True` replaces the wrapped SGD/Adam(W) math by one
 multi-tensor sm_100a kernel (csrc/kernels/optim_kernels.cu).
 """
+import os
 import warnings
 from contextlib import contextmanager
 
 import torch
 
+from horovod_b200.common.exceptions import HorovodInternalError
 from horovod_b200.common.process_sets import global_process_set
 from horovod_b200.common.util import split_list
 from horovod_b200.torch import mpi_ops
@@ -25,7 +27,7 @@ from horovod_b200.torch.mpi_ops import (Adasum, Average, Sum, allreduce_async_, 
 class _DistributedOptimizer(torch.optim.Optimizer):
     def __init__(self, params, named_parameters, compression, backward_passes_per_step=1, op=Average,
                  gradient_predivide_factor=1.0, groups=None, sparse_as_dense=False, process_set=global_process_set,
-                 fused=False):
+                 fused=False, zero_copy=None, bucket_cap_mb=32):
         super(self.__class__, self).__init__(params)
         self._compression = compression
 
@@ -85,6 +87,14 @@ class _DistributedOptimizer(torch.optim.Optimizer):
         self._p_to_group = {}
         self._group_counts = {}
         self._group_handles = {}
+        self._buckets = []
+        self._p_to_bucket = {}
+        self._zero_copy = False
+        if zero_copy is None:
+            zero_copy = os.environ.get('HVD_ZERO_COPY', '1') != '0'
+        if (zero_copy and groups is None and compression is Compression.none and op in (Average, Sum) and not sparse_as_dense
+                and self.process_set.included() and mpi_ops.symm_available(self.process_set)):
+            self._setup_buckets(int(bucket_cap_mb * 1024 * 1024))
 
         if self.process_set.included() and (size() > 1 or True):
             self._register_hooks()
@@ -140,6 +150,60 @@ class _DistributedOptimizer(torch.optim.Optimizer):
                 if p.requires_grad:
                     self._requires_update.add(p)
                     self._grad_accs.append(p.register_post_accumulate_grad_hook(self._make_hook(p)))
+
+    # ---- zero-copy gradient buckets (B200-first: the reference allreduces per-parameter tensors through a fusion buffer) ----
+    def _setup_buckets(self, cap_bytes):
+        """Lays the gradients of all dense CUDA parameters out in a few flat buffers of registered symmetric memory
+        (p.grad becomes a view, like DDP's gradient_as_bucket_view). A bucket is allreduced IN PLACE as one tensor by the
+        zero-copy NVLink kernel as soon as its last gradient is accumulated: no per-tensor negotiation, no pack/unpack."""
+        params = [p for g in self.param_groups for p in g['params']
+                  if p.requires_grad and p.is_cuda and mpi_ops._is_dense(p) and p.dtype in (torch.float32, torch.bfloat16, torch.float16)]
+        params.reverse()  # gradients become ready roughly in reverse registration order
+        by_dtype = {}
+        for p in params:
+            by_dtype.setdefault(p.dtype, []).append(p)
+        try:
+            for dtype, ps in by_dtype.items():
+                itemsize = ps[0].element_size()
+                cur, cur_bytes = [], 0
+                layouts = []
+                for p in ps:
+                    nbytes = (p.numel() * itemsize + 127) // 128 * 128
+                    if cur and cur_bytes + nbytes > cap_bytes:
+                        layouts.append((cur, cur_bytes))
+                        cur, cur_bytes = [], 0
+                    cur.append((p, cur_bytes))
+                    cur_bytes += nbytes
+                if cur:
+                    layouts.append((cur, cur_bytes))
+                for members, total in layouts:
+                    flat = mpi_ops.symm_empty(total // itemsize, dtype=dtype, device=members[0][0].device, process_set=self.process_set)
+                    flat.zero_()
+                    bucket = {'flat': flat, 'params': [m[0] for m in members], 'pending': len(members),
+                              'name': 'bucket.%d' % len(self._buckets), 'handle': None}
+                    for p, off in members:
+                        view = flat[off // itemsize: off // itemsize + p.numel()].as_strided(p.size(), p.stride())
+                        if p.grad is not None:
+                            view.copy_(p.grad)
+                        p.grad = view
+                        self._p_to_bucket[p] = bucket
+                    self._buckets.append(bucket)
+            self._zero_copy = True
+        except HorovodInternalError as e:
+            warnings.warn('zero-copy gradient buckets unavailable (%s); using the fused pack/unpack path' % e)
+            for b in self._buckets:
+                for p in b['params']:
+                    p.grad = None
+            self._buckets, self._p_to_bucket, self._zero_copy = [], {}, False
+
+    def _launch_bucket(self, bucket):
+        if self.op == Average:
+            prescale_factor, postscale_factor = 1.0 / self.gradient_predivide_factor, self.gradient_predivide_factor
+        else:
+            prescale_factor = postscale_factor = 1.0
+        bucket['handle'] = allreduce_async_(bucket['flat'], name=bucket['name'], op=self.op, prescale_factor=prescale_factor,
+                                            postscale_factor=postscale_factor, process_set=self.process_set)
+        bucket['pending'] = len(bucket['params'])
 
     def _allreduce_grad_async(self, p):
         if p.grad is None:
@@ -199,6 +263,17 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             assert self._allreduce_delay[p] > 0
             handle, ctx = None, None
             self._allreduce_delay[p] -= 1
+            bucket = self._p_to_bucket.get(p)
+            if bucket is not None:
+                if p.grad.data_ptr() != bucket['flat'].data_ptr() + self._bucket_offset(bucket, p):
+                    raise AssertionError('the gradient of a bucketed parameter was replaced (use optimizer.zero_grad(), '
+                                         'not p.grad = None, or construct DistributedOptimizer(..., zero_copy=False))')
+                self._handles[p] = ('bucket', None)
+                if self._allreduce_delay[p] == 0:
+                    bucket['pending'] -= 1
+                    if bucket['pending'] == 0:
+                        self._launch_bucket(bucket)
+                return
             if self._allreduce_delay[p] == 0:
                 if self._groups is not None:
                     group = self._p_to_group[p]
@@ -211,13 +286,31 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             self._handles[p] = (handle, ctx)
         return hook
 
+    def _bucket_offset(self, bucket, p):
+        offs = bucket.get('offsets')
+        if offs is None:
+            offs = bucket['offsets'] = {q: q.grad.data_ptr() - bucket['flat'].data_ptr() for q in bucket['params']}
+        return offs[p]
+
     def synchronize(self):
         """Waits for every outstanding gradient allreduce (enqueueing the ones whose hook never fired so that all
         ranks stay in lock-step) and writes the reduced gradients back."""
         if not self.process_set.included():
             self._synchronized = True
             return
-        pending = [p for p in self._requires_update if p not in self._handles]
+        if self._zero_copy:
+            for bucket in self._buckets:
+                if bucket['handle'] is None:
+                    # some gradient of this bucket was not produced on this rank (or accumulation is incomplete): reduce what
+                    # is there so that all ranks stay in lock-step (missing gradients are zeros)
+                    self._launch_bucket(bucket)
+            for bucket in self._buckets:
+                synchronize(bucket['handle'])
+                bucket['handle'] = None
+                for p in bucket['params']:
+                    self._allreduce_delay[p] = self.backward_passes_per_step
+                    self._handles.pop(p, None)
+        pending = [p for p in self._requires_update if p not in self._handles and p not in self._p_to_bucket]
         pending += [p for p, (h, _) in self._handles.items() if h is None]
         if self._groups is not None:
             launched = set()
@@ -285,6 +378,15 @@ class _DistributedOptimizer(torch.optim.Optimizer):
         if self._handles:
             raise AssertionError("optimizer.zero_grad() was called after loss.backward() but before optimizer.step() or "
                                  "optimizer.synchronize(). This is prohibited as it can cause a race condition.")
+        if self._zero_copy:
+            # bucketed gradients must stay views of the registered buffers: zero them in place (one memset per bucket)
+            for bucket in self._buckets:
+                bucket['flat'].zero_()
+            for group in self.param_groups:
+                for p in group['params']:
+                    if p not in self._p_to_bucket and p.grad is not None:
+                        p.grad = None
+            return None
         return super(self.__class__, self).zero_grad(*args, **kwargs)
 
 
@@ -478,7 +580,7 @@ class _DistributedAdasumOptimizer(torch.optim.Optimizer):
 
 def DistributedOptimizer(optimizer, named_parameters=None, compression=Compression.none, backward_passes_per_step=1,
                          op=Average, gradient_predivide_factor=1.0, num_groups=0, groups=None, sparse_as_dense=False,
-                         process_set=global_process_set, fused=False):
+                         process_set=global_process_set, fused=False, zero_copy=None, bucket_cap_mb=32):
     """Wraps `optimizer` so gradients are combined across ranks before the parameter update.
 
     Arguments follow the reference (horovod/torch/optimizer.py:516-608). `fused=True` (new) runs the SGD /
@@ -495,7 +597,7 @@ def DistributedOptimizer(optimizer, named_parameters=None, compression=Compressi
     if op != Adasum or size() == 1:
         cls = type(optimizer.__class__.__name__, (optimizer.__class__,), dict(_DistributedOptimizer.__dict__))
         return cls(optimizer.param_groups, named_parameters, compression, backward_passes_per_step, op,
-                   gradient_predivide_factor, groups, sparse_as_dense, process_set, fused)
+                   gradient_predivide_factor, groups, sparse_as_dense, process_set, fused, zero_copy, bucket_cap_mb)
     if process_set != global_process_set:
         raise NotImplementedError("Adasum does not support non-global process sets yet.")
     cls = type(optimizer.__class__.__name__, (optimizer.__class__,), dict(_DistributedAdasumOptimizer.__dict__))

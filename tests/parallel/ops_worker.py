@@ -506,6 +506,55 @@ def _():
         torch.testing.assert_close(hvd.synchronize(h), torch.full((16,), float(i + 1), device=DEV), rtol=1e-4, atol=1e-4)
 
 
+@check('symm_zero_copy')
+def _():
+    """Registered symmetric tensors: in-place allreduce through the zero-copy kernel (and the packed path when small)."""
+    if DEV.type != 'cuda' or size < 2 or not hvd.symm_available():
+        return
+    total = float(sum(range(1, size + 1)))
+    for dtype in [torch.float32, torch.bfloat16]:
+        t = hvd.symm_empty((1 << 20) + 24, dtype=dtype)          # > one-shot threshold -> zero-copy kernel
+        for rep in range(3):
+            t.fill_(rank + 1)
+            hvd.allreduce_(t, op=hvd.Sum, name=f'zc.{dtype}')
+            assert torch.allclose(t.float(), torch.full_like(t, total).float()), (dtype, rep, t[:4], t[-4:])
+        t.fill_(rank + 1)
+        hvd.allreduce_(t, op=hvd.Average, name=f'zc.avg.{dtype}', prescale_factor=2.0, postscale_factor=0.5)
+        assert torch.allclose(t.float(), torch.full_like(t, total / size).float(), rtol=1e-2), t[:4]
+        v = t[4096:4096 + (1 << 19)]                                # a view at an offset inside the region
+        v.fill_(float(rank))
+        hvd.allreduce_(v, op=hvd.Sum, name=f'zc.view.{dtype}')
+        assert torch.allclose(v.float(), torch.full_like(v, float(sum(range(size)))).float())
+        small = hvd.symm_empty(1000, dtype=dtype)                   # small: goes through the packed one-shot kernel
+        small.fill_(1.0)
+        hvd.allreduce_(small, op=hvd.Sum, name=f'zc.small.{dtype}')
+        assert torch.allclose(small.float(), torch.full_like(small, float(size)).float())
+    # min / max in place (no multicast for those)
+    t = hvd.symm_empty(1 << 19, dtype=torch.float32)
+    t.fill_(float(rank))
+    hvd.allreduce_(t, op=hvd.Max, name='zc.max')
+    assert (t == size - 1).all()
+    # bucketed optimizer == plain optimizer
+    torch.manual_seed(3)
+    m1 = torch.nn.Sequential(torch.nn.Linear(256, 512), torch.nn.ReLU(), torch.nn.Linear(512, 512)).to(DEV)
+    m2 = torch.nn.Sequential(torch.nn.Linear(256, 512), torch.nn.ReLU(), torch.nn.Linear(512, 512)).to(DEV)
+    hvd.broadcast_parameters(m1.state_dict(), 0)
+    m2.load_state_dict(m1.state_dict())
+    o1 = hvd.DistributedOptimizer(torch.optim.SGD(m1.parameters(), lr=0.05, momentum=0.9), named_parameters=m1.named_parameters(),
+                                  zero_copy=True, fused=True, bucket_cap_mb=0.6)
+    o2 = hvd.DistributedOptimizer(torch.optim.SGD(m2.parameters(), lr=0.05, momentum=0.9),
+                                  named_parameters=[('b.' + k, v) for k, v in m2.named_parameters()], zero_copy=False)
+    assert o1._zero_copy and len(o1._buckets) >= 2 and not o2._zero_copy
+    for step in range(4):
+        x = torch.randn(16, 256, generator=torch.Generator().manual_seed(10 * step + rank)).to(DEV)
+        for m, o in ((m1, o1), (m2, o2)):
+            o.zero_grad()
+            m(x).square().mean().backward()
+            o.step()
+    for a, b in zip(m1.parameters(), m2.parameters()):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
+
+
 @check('timeline')
 def _():
     import json, os, tempfile
