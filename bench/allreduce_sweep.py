@@ -22,7 +22,8 @@ p.add_argument('--configs', default='p2p:auto:64,nccl')
 p.add_argument('--sizes', default=','.join(str(1 << s) for s in range(10, 31, 2)))
 p.add_argument('--dtype', default='fp32')
 p.add_argument('--out', default=None)
-p.add_argument('--blocking', action='store_true', help='synchronize after every op (latency mode) instead of pipelining')
+p.add_argument('--symm', action='store_true', help='allocate the tensors in registered symmetric memory (zero-copy path)')
+p.add_argument('--inflight', type=int, default=1, help='number of distinct tensors kept in flight (1 = blocking loop)')
 args = p.parse_args()
 dt = {'fp32': torch.float32, 'bf16': torch.bfloat16, 'fp16': torch.float16}[args.dtype]
 sizes = [int(s) for s in args.sizes.split(',')]
@@ -41,7 +42,10 @@ for cfg in args.configs.split(','):
     rows = []
     for nbytes in sizes:
         n = max(1, nbytes // torch.tensor([], dtype=dt).element_size())
-        x = torch.ones(n, device='cuda', dtype=dt)
+        k = max(1, args.inflight)
+        use_symm = args.symm and parts[0] == 'p2p' and hvd.size() > 1
+        xs = [(hvd.symm_empty(n, dtype=dt) if use_symm else torch.empty(n, device='cuda', dtype=dt)).fill_(1) for _ in range(k)]
+        x = xs[0]
         iters = max(5, min(100, int(1e9 // max(nbytes, 1 << 18))))
         name = f'sweep.{nbytes}'
         for _ in range(3):
@@ -50,23 +54,31 @@ for cfg in args.configs.split(','):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        if args.blocking:
+        if k == 1:
             for _ in range(iters):
                 hvd.allreduce_(x, op=hvd.Sum, name=name)
         else:
-            # pipelined: distinct names in flight so the host never blocks between ops
-            hs = [hvd.allreduce_async_(x, op=hvd.Sum, name=f'{name}.{i % 8}') if False else None for i in range(0)]
-            for _ in range(iters):
-                hvd.allreduce_(x, op=hvd.Sum, name=name)
+            # k tensors in flight: the host enqueues ahead, kernels run back to back on the hvd stream
+            for _ in range(max(1, iters // k)):
+                hs = [hvd.allreduce_async_(xs[i], op=hvd.Sum, name=f'{name}.{i}') for i in range(k)]
+                for h in hs:
+                    hvd.synchronize(h)
+            iters = max(1, iters // k) * k
         e1.record()
         torch.cuda.synchronize()
+        # value check (a wrong-but-fast kernel must not produce a number)
+        x.fill_(1)
+        hvd.allreduce_(x, op=hvd.Sum, name=name)
+        torch.cuda.synchronize()
+        probe = torch.cat([x[:64].float(), x[-64:].float(), x[n // 2: n // 2 + 64].float()])
+        assert torch.all(probe == size), f'{cfg}: wrong allreduce result at {nbytes} B: {probe[:4].tolist()}'
         ms = hvd.allreduce(torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64), op=hvd.Max, name='sweep.ms').item()
         alg = nbytes / (ms / 1e3) / 1e9
         rows.append({'bytes': nbytes, 'us': round(ms * 1e3, 2), 'algbw_gbs': round(alg, 2),
                      'busbw_gbs': round(alg * 2 * (size - 1) / size, 2)})
-    results[cfg] = {'rows': rows, 'backend': hvd.gpu_backend_info(), 'tunables': hvd.tunable_params()}
+    results[cfg + (':symm' if args.symm else '')] = {'rows': rows, 'backend': hvd.gpu_backend_info(), 'tunables': hvd.tunable_params()}
     if rank == 0:
-        print(f'== {cfg}  [{hvd.gpu_backend_info()}]', flush=True)
+        print(f'== {cfg}{" symm" if args.symm else ""} inflight={args.inflight}  [{hvd.gpu_backend_info()}]', flush=True)
         for r in rows:
             print(f"  {r['bytes']:>12d} B  {r['us']:>10.2f} us  alg {r['algbw_gbs']:>8.2f} GB/s  bus {r['busbw_gbs']:>8.2f} GB/s", flush=True)
     hvd.shutdown()

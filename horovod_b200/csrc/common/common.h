@@ -140,6 +140,7 @@ struct TensorTableEntry {
   CompletionCallback callback;
   // filled in during execution
   std::vector<int32_t> received_splits;
+  std::shared_ptr<void> nvtx_range;  // NvtxOpRange: ends when the entry is destroyed (after its callback ran)
   uint64_t enqueue_ns = 0;
   size_t bytes() const { return (size_t)shape.num_elements() * DataTypeSize(dtype); }
 };

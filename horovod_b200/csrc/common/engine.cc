@@ -12,10 +12,30 @@
 #include "../symm/symm_memory.h"
 #include "env.h"
 #include "logging.h"
+#include "nvtx_op_range.h"
 
 namespace hvd {
 
 namespace {
+// NVTX range from enqueue until the entry dies (after its completion callback)
+void AttachNvtx(const std::shared_ptr<TensorTableEntry>& e) {
+  if (!NvtxEnabled()) return;
+  NvtxOp op = NvtxOp::ALLREDUCE;
+  const bool grouped = e->group_id >= 0;
+  switch (e->type) {
+    case RequestType::ALLREDUCE: op = grouped ? NvtxOp::GROUPED_ALLREDUCE : NvtxOp::ALLREDUCE; break;
+    case RequestType::ADASUM: op = NvtxOp::ADASUM; break;
+    case RequestType::ALLGATHER: op = grouped ? NvtxOp::GROUPED_ALLGATHER : NvtxOp::ALLGATHER; break;
+    case RequestType::BROADCAST: op = NvtxOp::BROADCAST; break;
+    case RequestType::ALLTOALL: op = NvtxOp::ALLTOALL; break;
+    case RequestType::REDUCESCATTER: op = grouped ? NvtxOp::GROUPED_REDUCESCATTER : NvtxOp::REDUCESCATTER; break;
+    default: break;
+  }
+  auto r = std::make_shared<NvtxOpRange>();
+  r->Start(op, (int64_t)e->bytes());
+  e->nvtx_range = r;
+}
+
 std::string JoinInts(const std::vector<int>& v) {
   std::ostringstream os;
   for (size_t i = 0; i < v.size(); ++i) os << (i ? "," : "") << v[i];
@@ -594,7 +614,7 @@ Status Engine::EnqueueAllreduces(std::vector<std::shared_ptr<TensorTableEntry>>&
   }
   for (auto& e : es) {
     e->process_set_id = psid;
-    e->enqueue_ns = NowNs();
+    e->enqueue_ns = NowNs(); AttachNvtx(e);
     e->group_id = gid;
     RequestType type = RequestType::ALLREDUCE;
     if (e->reduce_op == ReduceOp::ADASUM) {
@@ -638,7 +658,7 @@ Status Engine::EnqueueAllgathers(std::vector<std::shared_ptr<TensorTableEntry>>&
     gid = ps->groups.RegisterGroup(names);
   }
   for (auto& e : es) {
-    e->process_set_id = psid; e->type = RequestType::ALLGATHER; e->group_id = gid; e->enqueue_ns = NowNs();
+    e->process_set_id = psid; e->type = RequestType::ALLGATHER; e->group_id = gid; e->enqueue_ns = NowNs(); AttachNvtx(e);
     Request q = MakeRequest(*e, ps->set_rank(), RequestType::ALLGATHER);
     q.group_size = gid >= 0 ? (int32_t)es.size() : 0;
     msgs.push_back(std::move(q));
@@ -659,7 +679,7 @@ Status Engine::EnqueueBroadcast(std::shared_ptr<TensorTableEntry> e, int32_t psi
   if (it == ps->ranks.end())
     return Status::InvalidArgument("broadcast received invalid root rank " + std::to_string(e->root_rank) + " for provided process set");
   e->root_rank = (int)(it - ps->ranks.begin());
-  e->process_set_id = psid; e->type = RequestType::BROADCAST; e->enqueue_ns = NowNs();
+  e->process_set_id = psid; e->type = RequestType::BROADCAST; e->enqueue_ns = NowNs(); AttachNvtx(e);
   st = ps->queue.AddToTensorQueue(e, MakeRequest(*e, ps->set_rank(), RequestType::BROADCAST));
   if (!st.ok()) return st;
   NotePending((int64_t)e->bytes());
@@ -683,7 +703,7 @@ Status Engine::EnqueueAlltoall(std::shared_ptr<TensorTableEntry> e, int32_t psid
     for (auto s : e->splits) { if (s < 0) return Status::InvalidArgument("splits must be non-negative"); sum += s; }
     if (sum > e->shape.dim(0)) return Status::InvalidArgument("Sum of splits entries is greater than the first dimension of tensor.");
   }
-  e->process_set_id = psid; e->type = RequestType::ALLTOALL; e->enqueue_ns = NowNs();
+  e->process_set_id = psid; e->type = RequestType::ALLTOALL; e->enqueue_ns = NowNs(); AttachNvtx(e);
   st = ps->queue.AddToTensorQueue(e, MakeRequest(*e, ps->set_rank(), RequestType::ALLTOALL));
   if (!st.ok()) return st;
   NotePending((int64_t)e->bytes());
@@ -704,7 +724,7 @@ Status Engine::EnqueueReducescatters(std::vector<std::shared_ptr<TensorTableEntr
   }
   for (auto& e : es) {
     if (e->reduce_op == ReduceOp::AVERAGE) { e->reduce_op = ReduceOp::SUM; e->postscale /= (double)ps->set_size(); }
-    e->process_set_id = psid; e->type = RequestType::REDUCESCATTER; e->group_id = gid; e->enqueue_ns = NowNs();
+    e->process_set_id = psid; e->type = RequestType::REDUCESCATTER; e->group_id = gid; e->enqueue_ns = NowNs(); AttachNvtx(e);
     Request q = MakeRequest(*e, ps->set_rank(), RequestType::REDUCESCATTER);
     q.group_size = gid >= 0 ? (int32_t)es.size() : 0;
     msgs.push_back(std::move(q));

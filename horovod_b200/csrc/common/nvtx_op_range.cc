@@ -1,0 +1,57 @@
+#include "nvtx_op_range.h"
+#include <nvtx3/nvToolsExt.h>
+#include "env.h"
+
+namespace hvd {
+namespace {
+struct Domain {
+  bool enabled = false;
+  nvtxDomainHandle_t dom = nullptr;
+  nvtxStringHandle_t names[(int)NvtxOp::COUNT] = {};
+  Domain() {
+    enabled = !EnvBool("HOROVOD_DISABLE_NVTX_RANGES", false);
+    if (!enabled) return;
+    dom = nvtxDomainCreateA("hvd");
+    static const char* kNames[] = {"HorovodAllreduce", "HorovodGroupedAllreduce", "HorovodAllgather", "HorovodGroupedAllgather",
+                                   "HorovodBroadcast", "HorovodAlltoall", "HorovodReducescatter", "HorovodGroupedReducescatter",
+                                   "HorovodJoin", "HorovodBarrier", "HorovodAdasum"};
+    for (int i = 0; i < (int)NvtxOp::COUNT; ++i) names[i] = nvtxDomainRegisterStringA(dom, kNames[i]);
+  }
+};
+Domain& D() { static Domain d; return d; }
+}  // namespace
+
+bool NvtxEnabled() { return D().enabled; }
+
+void NvtxOpRange::Start(NvtxOp op, int64_t payload_bytes) {
+  Domain& d = D();
+  if (!d.enabled || active_) return;
+  nvtxEventAttributes_t a = {};
+  a.version = NVTX_VERSION;
+  a.size = NVTX_EVENT_ATTRIB_STRUCT_SIZE;
+  a.messageType = NVTX_MESSAGE_TYPE_REGISTERED;
+  a.message.registered = d.names[(int)op];
+  a.payloadType = NVTX_PAYLOAD_TYPE_INT64;
+  a.payload.llValue = payload_bytes;
+  id_ = nvtxDomainRangeStartEx(d.dom, &a);
+  active_ = true;
+}
+
+void NvtxOpRange::End() {
+  if (!active_) return;
+  nvtxDomainRangeEnd(D().dom, id_);
+  active_ = false;
+}
+
+void NvtxMark(const char* message) {
+  Domain& d = D();
+  if (!d.enabled) return;
+  nvtxEventAttributes_t a = {};
+  a.version = NVTX_VERSION;
+  a.size = NVTX_EVENT_ATTRIB_STRUCT_SIZE;
+  a.messageType = NVTX_MESSAGE_TYPE_ASCII;
+  a.message.ascii = message;
+  nvtxDomainMarkEx(d.dom, &a);
+}
+
+}  // namespace hvd

@@ -138,6 +138,33 @@ int hvd_sim_adasum(int nranks, int device, int ntensors, const int64_t* counts, 
   return (int)cudaDeviceSynchronize();
 }
 
+// Zero-copy in-place allreduce over N simulated ranks: ptrs[r] = rank r's tensor (plain device memory here).
+int hvd_sim_inplace(int nranks, int device, int64_t bytes, const uint64_t* ptrs, int dtype, int op, int ctas, double scale,
+                    int repeats, float* ms_out) {
+  if (cudaSetDevice(device) != cudaSuccess) return -1;
+  Sim* sim = GetSim(nranks, device, 1 << 20);
+  if (!sim) return -1;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaDeviceSynchronize();
+  cudaEventRecord(e0, sim->streams[0]);
+  for (int it = 0; it < repeats; ++it) {
+    for (int r = 0; r < nranks; ++r) {
+      kern::InplaceArgs a {};
+      for (int p = 0; p < nranks; ++p) a.ptr[p] = (void*)ptrs[p];
+      a.mc = nullptr; a.bytes = bytes; a.scale = scale; a.op = op; a.dtype = dtype; a.use_multicast = 0; a.ctas = ctas;
+      kern::CommParams cp = sim->teams[r]->Params(sim->teams[r]->NextSlot());
+      cudaError_t e = kern::LaunchInplaceAllreduce(cp, a, sim->streams[r]);
+      if (e != cudaSuccess) return (int)e;
+    }
+  }
+  cudaEventRecord(e1, sim->streams[0]);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (ms_out) cudaEventElapsedTime(ms_out, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return (int)e;
+}
+
 void hvd_sim_reset() {
   for (auto& kv : g_sims) for (auto st : kv.second.streams) cudaStreamDestroy(st);
   g_sims.clear();

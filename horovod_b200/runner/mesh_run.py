@@ -63,6 +63,11 @@ def create_run_env_vars(server_ip, server_port, nics=None, elastic=False):
         run_envs['NCCL_SOCKET_IFNAME'] = ','.join(nics)
     if elastic:
         run_envs['HOROVOD_ELASTIC'] = '1'
+    # workers must be able to import this package even when it is used from a source tree (not pip-installed)
+    pkg_parent = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    existing = os.environ.get('PYTHONPATH', '')
+    if pkg_parent not in existing.split(os.pathsep):
+        run_envs['PYTHONPATH'] = pkg_parent + (os.pathsep + existing if existing else '')
     return run_envs
 
 
