@@ -1,0 +1,64 @@
+"""Unit tests of framework-neutral helpers: async data loader, ray strategy/discovery logic (without ray), stores."""
+import pytest
+
+from horovod_b200.data import AsyncDataLoaderMixin, BaseDataLoader
+from horovod_b200.ray import strategy
+from horovod_b200.ray.elastic import RayHostDiscovery
+from horovod_b200.spark.common.store import LocalStore, Store
+
+
+class _Loader(BaseDataLoader):
+    def __init__(self, n, fail_at=None):
+        self.n, self.fail_at = n, fail_at
+
+    def __len__(self):
+        return self.n
+
+    def _iterate(self):
+        for i in range(self.n):
+            if self.fail_at == i:
+                raise ValueError('boom')
+            yield i
+
+
+class _AsyncLoader(AsyncDataLoaderMixin, _Loader):
+    pass
+
+
+def test_async_loader_epochs_and_errors():
+    l = _AsyncLoader(async_loader_queue_size=4, n=10)
+    assert list(l) == list(range(10))
+    assert list(l) == list(range(10))  # second epoch
+    l.close_async_loader()
+    sync = _AsyncLoader(async_loader_queue_size=0, n=5)
+    assert list(sync) == list(range(5))
+    bad = _AsyncLoader(async_loader_queue_size=2, n=5, fail_at=3)
+    with pytest.raises(ValueError):
+        list(bad)
+    bad.close_async_loader()
+
+
+def test_ray_rank_assignment_and_discovery():
+    envs = strategy.assign_ranks(['a', 'b', 'a', 'b', 'b'])
+    assert [e['HOROVOD_RANK'] for e in envs] == ['0', '2', '1', '3', '4']
+    assert envs[4]['HOROVOD_LOCAL_RANK'] == '2' and envs[4]['HOROVOD_CROSS_SIZE'] == '1' and envs[4]['HOROVOD_CROSS_RANK'] == '0'
+    assert envs[1]['HOROVOD_CROSS_RANK'] == '1' and envs[0]['HOROVOD_LOCAL_SIZE'] == '2'
+    bundles, strat = strategy.colocated_bundles(2, 4, cpus_per_worker=2, gpus_per_worker=1)
+    assert bundles == [{'CPU': 8, 'GPU': 4}] * 2 and strat == 'STRICT_SPREAD'
+    nodes = [{'alive': True, 'NodeManagerAddress': 'n1', 'Resources': {'CPU': 16, 'GPU': 8}},
+             {'alive': True, 'NodeManagerAddress': 'n2', 'Resources': {'CPU': 4}},
+             {'alive': False, 'NodeManagerAddress': 'n3', 'Resources': {'CPU': 64, 'GPU': 8}}]
+    d = RayHostDiscovery(use_gpu=True, cpus_per_worker=2, gpus_per_worker=1, nodes_fn=lambda: nodes)
+    assert d.find_available_hosts_and_slots() == {'n1': 8}
+    assert RayHostDiscovery(nodes_fn=lambda: nodes).find_available_hosts_and_slots() == {'n1': 16, 'n2': 4}
+
+
+def test_local_store(tmp_path):
+    s = Store.create(str(tmp_path))
+    assert isinstance(s, LocalStore)
+    ck = s.get_checkpoint_path('run1')
+    s.write(ck, b'abc')
+    assert s.exists(ck) and s.read(ck) == b'abc'
+    assert s.get_logs_path('run1').endswith('runs/run1/logs') and s.get_train_data_path(3).endswith('intermediate_train_data.3')
+    with pytest.raises(ImportError):
+        Store.create('hdfs://x/y')
