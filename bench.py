@@ -95,6 +95,8 @@ class ClockSampler:
 def reference_arm(args):
     """The unmodified reference cannot be installed offline (see DESIGN.md 'Reference install attempt'):
     third_party/{gloo,flatbuffers,boost,eigen,lbfgs,HTTPRequest} are empty and there is no MPI."""
+    if int(os.environ.get('RANK', '0')) != 0:
+        return 0  # one JSON line for the whole job
     ref = os.path.join(ROOT, 'baseline', '_ref')
     sys.path.insert(0, ref)
     try:

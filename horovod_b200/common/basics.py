@@ -60,6 +60,7 @@ class _EmbeddedRendezvous:
     """Rank 0 hosts the HTTP KV store in-process when no launcher-provided one exists (torchrun / manual env)."""
     server = None
     port = None
+    stores = []
 
 
 def _resolve_topology():
@@ -102,6 +103,7 @@ def _resolve_rendezvous(rank, size):
     agent_store = os.environ.get('TORCHELASTIC_USE_AGENT_STORE', '') == 'True'
     store = TCPStore(master_addr, master_port, size, is_master=(rank == 0 and not agent_store),
                      timeout=timedelta(seconds=_env_int('HOROVOD_GLOO_TIMEOUT_SECONDS', default=120)), wait_for_workers=False)
+    _EmbeddedRendezvous.stores.append(store)  # rank 0 may host the store: it must outlive this function
     key = 'hvd_b200/rendezvous/%s' % os.environ.get('TORCHELASTIC_RUN_ID', 'default')
     if rank == 0:
         if _EmbeddedRendezvous.server is None:
