@@ -1,1 +1,2 @@
-from horovod_b200.data.data_loader_base import AsyncDataLoaderMixin, BaseDataLoader  # noqa: F401
+from .data_loader_base import BaseDataLoader, AsyncDataLoaderMixin  # noqa: F401
+from .device_prefetcher import DevicePrefetcher  # noqa: F401

@@ -1,99 +1,123 @@
-"""Framework-neutral data loader base + a mixin that prefetches batches on a background thread so that host-side
-batch preparation overlaps the training step (role parity: horovod/data/data_loader_base.py).
+"""Data-loader scaffolding: a minimal loader protocol and a background-thread prefetch mixin.
 
-The B200 angle: with `pin_memory=True` the mixin also stages every batch into pinned host memory on the producer
-thread, so the consumer's `tensor.cuda(non_blocking=True)` is a true asynchronous DMA."""
+Capability parity: horovod/data/data_loader_base.py:20-171 (``BaseDataLoader`` with the ``_iterate`` /
+``_process_batch`` hooks; ``AsyncDataLoaderMixin`` with ``async_loader_queue_size``, ``close_async_loader`` and
+exception forwarding from the producer thread).  The implementation is new: one producer thread per *epoch request*
+coordinated through typed sentinels instead of ``None`` markers, so ``None`` is a legal batch, a producer error is
+re-raised exactly once at the position it happened, and closing never relies on draining heuristics.
+"""
 import queue
 import threading
 
 
-class BaseDataLoader(object):
+class BaseDataLoader:
+    """Subclasses implement ``__len__`` and ``_iterate`` (a generator of raw batches)."""
+
     def __len__(self):
-        """Length of the batches to be loaded."""
-        raise NotImplementedError()
+        raise NotImplementedError
 
     def _iterate(self):
-        """Interface for the implementation of iterate batches."""
-        raise NotImplementedError()
+        raise NotImplementedError
+
+    def _process_batch(self, batch):
+        """Trainer hook applied to every batch on the consumer side (identity by default)."""
+        return batch
 
     def __iter__(self):
-        """Starting iteration and get batches."""
         for batch in self._iterate():
             yield self._process_batch(batch)
 
-    def _process_batch(self, batch):
-        """Hook to modify a batch before it is yielded."""
-        return batch
+
+class _EndOfEpoch:
+    __slots__ = ()
 
 
-class AsyncDataLoaderMixin(object):
-    """Mix in FIRST: `class MyLoader(AsyncDataLoaderMixin, BaseDataLoader)`.
+class _ProducerError:
+    __slots__ = ('exc',)
 
-    `async_loader_queue_size` batches are produced ahead of time by a daemon thread; 0 disables the thread. Exceptions
-    raised by the producer are re-raised in the consumer. `close_async_loader()` stops the thread."""
+    def __init__(self, exc):
+        self.exc = exc
 
-    def __init__(self, async_loader_queue_size=64, pin_memory=False, *args, **kwargs):
-        self.async_loader_queue_size = async_loader_queue_size
-        self.pin_memory = pin_memory
+
+class AsyncDataLoaderMixin:
+    """Mix in *before* a ``BaseDataLoader`` implementation::
+
+        class AsyncLoader(AsyncDataLoaderMixin, MyLoader): ...
+
+    A daemon thread walks ``self._iterate()`` epoch after epoch and parks up to ``async_loader_queue_size`` batches in
+    a bounded queue; ``__iter__`` pops one epoch's worth.  ``async_loader_queue_size=0`` disables the thread (the
+    loader then behaves exactly like the synchronous base class).
+    """
+
+    def __init__(self, *args, async_loader_queue_size=64, debug_data_loader=False, **kwargs):
+        self.async_loader_queue_size = int(async_loader_queue_size)
+        self.debug_data_loader = debug_data_loader
         super().__init__(*args, **kwargs)
-        self.started = False
-        if self.async_loader_queue_size > 0:
-            self.finished_event = threading.Event()
-            self.queue = queue.Queue(self.async_loader_queue_size)
-            self.thread = threading.Thread(target=self._async_worker, daemon=True)
+        self._q = None
+        self._producer = None
+        self._stop = threading.Event()
+        self._epochs_wanted = threading.Semaphore(0)
+
+    # -- producer ---------------------------------------------------------------------------------------------------
+    def _put(self, item):
+        while not self._stop.is_set():
+            try:
+                self._q.put(item, timeout=0.1)
+                return True
+            except queue.Full:
+                continue
+        return False
+
+    def _produce(self):
+        while not self._stop.is_set():
+            if not self._epochs_wanted.acquire(timeout=0.1):
+                continue
+            try:
+                for batch in self._iterate():
+                    if not self._put(batch):
+                        return
+            except BaseException as exc:  # forwarded to, and re-raised in, the consumer
+                self._put(_ProducerError(exc))
+            if not self._put(_EndOfEpoch()):
+                return
+
+    def _ensure_started(self):
+        if self._producer is None or not self._producer.is_alive():
+            self._stop.clear()
+            self._q = queue.Queue(self.async_loader_queue_size)
+            self._epochs_wanted = threading.Semaphore(0)
+            self._producer = threading.Thread(target=self._produce, name='hvd-data-prefetch', daemon=True)
+            self._producer.start()
+
+    # -- consumer ---------------------------------------------------------------------------------------------------
+    def __iter__(self):
+        if self.async_loader_queue_size <= 0:
+            yield from super().__iter__()
+            return
+        self._ensure_started()
+        self._epochs_wanted.release()
+        while True:
+            item = self._q.get()
+            if isinstance(item, _EndOfEpoch):
+                return
+            if isinstance(item, _ProducerError):
+                # the producer still emits the end-of-epoch marker after an error; swallow it so the next epoch is clean
+                nxt = self._q.get()
+                assert isinstance(nxt, _EndOfEpoch)
+                raise item.exc
+            yield self._process_batch(item)
 
     def close_async_loader(self):
-        """Close the async data loader."""
-        if self.async_loader_queue_size > 0 and self.started:
-            self.finished_event.set()
-            while True:
-                try:
-                    self.queue.get_nowait()  # unblock a producer stuck in put()
-                except queue.Empty:
-                    break
-            self.thread.join(timeout=10)
+        """Stops the producer thread; safe to call more than once and from ``__del__``."""
+        if self._producer is None:
+            return
+        self._stop.set()
+        self._producer.join(timeout=10)
+        self._producer = None
+        self._q = None
 
-    def _pin(self, batch):
+    def __del__(self):
         try:
-            import torch
-        except ImportError:
-            return batch
-        if torch.is_tensor(batch):
-            return batch.pin_memory() if not batch.is_cuda and torch.cuda.is_available() else batch
-        if isinstance(batch, (list, tuple)):
-            return type(batch)(self._pin(b) for b in batch)
-        if isinstance(batch, dict):
-            return {k: self._pin(v) for k, v in batch.items()}
-        return batch
-
-    def _async_worker(self):
-        """Producer: loops over the underlying loader forever (one epoch after another) until closed."""
-        try:
-            while not self.finished_event.is_set():
-                for batch in self._iterate():
-                    if self.finished_event.is_set():
-                        break
-                    self.queue.put(self._pin(batch) if self.pin_memory else batch)
-                self.queue.put(None)  # end-of-epoch marker
-        except Exception as ex:
-            self.queue.put(ex)
-            self.queue.put(None)
-        finally:
-            self.queue.put(None)
-
-    def __iter__(self):
-        """Override the __iter__() to iterate data asynchronously to produce batches."""
-        if self.async_loader_queue_size > 0:
-            if not self.started:
-                self.started = True
-                self.thread.start()
-            while True:
-                batch = self.queue.get()
-                if batch is None:
-                    break
-                if isinstance(batch, Exception):
-                    raise batch
-                yield self._process_batch(batch)
-        else:
-            for batch in self._iterate():
-                yield self._process_batch(batch)
+            self.close_async_loader()
+        except Exception:
+            pass
