@@ -119,6 +119,7 @@ void Engine::FailAll(const Status& s) {
     auto ps = sets_.Get(id);
     if (!ps) continue;
     if (ps->team) ps->team->Abort();
+    if (ps->local_team) ps->local_team->Abort();
     ps->queue.FinalizeTensorQueue(s);
   }
 }

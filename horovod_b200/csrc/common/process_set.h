@@ -32,6 +32,10 @@ struct ProcessSet {
   bool team_tried = false;
   std::shared_ptr<NcclComm> nccl;
   bool nccl_tried = false;
+  // multi-host sets: intra-host peer-mapped team + cross-host communicator of the hierarchical GPU allreduce
+  std::shared_ptr<Transport> local_transport, cross_transport;
+  std::shared_ptr<SymmTeam> local_team;
+  bool hier_tried = false;
   bool member() const { return transport != nullptr; }
   int set_rank() const { return transport ? transport->rank() : -1; }
   int set_size() const { return (int)ranks.size(); }

@@ -27,6 +27,7 @@ namespace hvd {
 #define HVD_ACT_P2P_ALLREDUCE_ONESHOT "P2P_ALLREDUCE_ONESHOT"
 #define HVD_ACT_P2P_ALLREDUCE_TWOSHOT "P2P_ALLREDUCE_TWOSHOT"
 #define HVD_ACT_P2P_ALLREDUCE_NVLS "P2P_ALLREDUCE_NVLS"
+#define HVD_ACT_HIER_ALLREDUCE "HIERARCHICAL_ALLREDUCE"
 #define HVD_ACT_P2P_ALLGATHER "P2P_ALLGATHER"
 #define HVD_ACT_P2P_BROADCAST "P2P_BROADCAST"
 #define HVD_ACT_P2P_ALLTOALL "P2P_ALLTOALL"

@@ -104,10 +104,24 @@ void GpuContext::TempFreeAll(int device, cudaStream_t s) {
   for (void* p : t) cudaFreeAsync(p, s);
 }
 
+void* GpuContext::PinnedHost(int device, size_t bytes) {
+  std::lock_guard<std::mutex> l(mu_);
+  PerDevice& d = Dev(device);
+  if (d.pinned_bytes < bytes) {
+    if (d.pinned) cudaFreeHost(d.pinned);
+    d.pinned = nullptr; d.pinned_bytes = 0;
+    size_t want = std::max<size_t>(bytes, 1 << 20);
+    if (cudaHostAlloc(&d.pinned, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); d.pinned = nullptr; return nullptr; }
+    d.pinned_bytes = want;
+  }
+  return d.pinned;
+}
+
 void GpuContext::Reset() {
   std::lock_guard<std::mutex> l(mu_);
   for (auto& kv : devs_) {
     cudaSetDevice(kv.first);
+    if (kv.second.pinned) cudaFreeHost(kv.second.pinned);
     if (kv.second.stream) { cudaStreamSynchronize(kv.second.stream); cudaStreamDestroy(kv.second.stream); }
     for (auto e : kv.second.pool) cudaEventDestroy(e);
     if (kv.second.host_ring) cudaFreeHost(kv.second.host_ring);
@@ -172,7 +186,7 @@ std::shared_ptr<SymmTeam> GpuOps::EnsureTeam(ProcessSet& ps, int device) {
   bool single = t->single_host();
   uint64_t ok = single ? 1 : 0;
   t->AllreduceBits(&ok, 1, nullptr, 0);
-  if (!ok) { LOG(INFO) << "process set " << ps.id << " spans hosts: GPU collectives are staged through the CPU transport"; return nullptr; }
+  if (!ok) { LOG(INFO) << "process set " << ps.id << " spans hosts: no set-wide peer mapping (allreduce goes hierarchical when hosts are uniform)"; return nullptr; }
   size_t bytes = ps.id == 0 ? env_.symm_buffer_bytes : std::min<size_t>(env_.symm_buffer_bytes, 32ull << 20);
   std::shared_ptr<SymmTeam> created = SymmTeam::Create(t, device, bytes, env_.want_multicast,
                              std::to_string(tag[0]) + "-" + std::to_string(tag[1]) + "-" + std::to_string(ps.id), &why);
@@ -185,8 +199,126 @@ std::shared_ptr<SymmTeam> GpuOps::EnsureTeam(ProcessSet& ps, int device) {
   return ps.team;
 }
 
+namespace {
+Status RunExchange(SymmTeam& team, GpuContext& ctx, int device, cudaStream_t s, std::vector<kern::CopyDesc>& sends,
+                   std::vector<kern::CopyDesc>& recvs, int max_ctas);
+}
+
+bool GpuOps::EnsureHierarchy(ProcessSet& ps, int device) {
+  if (ps.hier_tried) {
+    if (ps.local_team && ps.local_team->abort_state() == 2)
+      throw TransportError("a peer GPU did not reach the collective's flag barrier within HVD_KERNEL_TIMEOUT_SECONDS");
+    return ps.local_team != nullptr;
+  }
+  ps.hier_tried = true;
+  Transport* t = ps.transport.get();
+  const int n = t->size(), me = t->rank();
+  // group the members by host (host ids come from the bootstrap hostname exchange, identical on every rank)
+  std::map<int, std::vector<int>> by_host;
+  for (int i = 0; i < n; ++i) by_host[t->host_id(i)].push_back(i);
+  const std::vector<int>& mine = by_host[t->host_id(me)];
+  const int L = (int)mine.size();
+  bool uniform = L >= 2 && L <= kern::kMaxPeers && EnvBool("HVD_HIERARCHICAL_ALLREDUCE", true);
+  for (auto& kv : by_host) if ((int)kv.second.size() != L) uniform = false;
+  int64_t tag[2] = {(int64_t)getpid(), (int64_t)(++team_counter_)};
+  t->Bcast(tag, sizeof tag, 0);
+  if (!uniform) return false;  // same decision on every rank: it only depends on the shared host table
+  const int li = (int)(std::find(mine.begin(), mine.end(), me) - mine.begin());
+  std::vector<int> cross;
+  for (auto& kv : by_host) cross.push_back(kv.second[li]);
+  ps.local_transport = t->Split(mine);
+  ps.cross_transport = t->Split(cross);
+  std::string why;
+  size_t bytes = ps.id == 0 ? env_.symm_buffer_bytes : std::min<size_t>(env_.symm_buffer_bytes, 32ull << 20);
+  std::shared_ptr<SymmTeam> created = SymmTeam::Create(ps.local_transport.get(), device, bytes, env_.want_multicast,
+      std::to_string(tag[0]) + "-" + std::to_string(tag[1]) + "-" + std::to_string(ps.id) + "-h" + std::to_string(t->host_id(me)), &why);
+  uint64_t ok = created ? 1 : 0;
+  t->AllreduceBits(&ok, 1, nullptr, 0);  // all hosts or none
+  if (!ok) {
+    LOG(WARNING) << "hierarchical allreduce unavailable for process set " << ps.id << (why.empty() ? "" : " (" + why + ")") << "; staging through the host";
+    return false;
+  }
+  created->set_timeout_seconds(EnvDouble("HVD_KERNEL_TIMEOUT_SECONDS", 60.0));
+  { std::lock_guard<std::mutex> l(ps.team_mu); ps.local_team = created; }
+  LOG(INFO) << "process set " << ps.id << ": hierarchical allreduce over " << by_host.size() << " hosts x " << L << " GPUs (intra-host "
+            << created->backend() << ")";
+  return true;
+}
+
+// reduce-scatter (intra-host kernel) -> shard allreduce over the cross-host CPU transport -> allgather (intra-host kernel)
+Status GpuOps::HierarchicalAllreduce(ProcessSet& ps, Entries& es, const Response& r, int device, cudaStream_t s) {
+  GpuContext& ctx = GpuContext::Get();
+  SymmTeam& team = *ps.local_team;
+  const int L = team.nranks(), li = team.rank();
+  const int64_t esz = (int64_t)DataTypeSize(r.dtype);
+  std::vector<Piece> pieces;
+  Status st = BuildPieces(es, r, device, s, &pieces);
+  if (!st.ok()) return st;
+  std::vector<kern::TensorDesc> descs;
+  int64_t total = 0;
+  for (auto& p : pieces) {
+    kern::TensorDesc d; d.in = p.in; d.out = p.out; d.offset = total; d.count = p.count;
+    descs.push_back(d);
+    total += Align128(p.count * esz);
+  }
+  if (total == 0) return Status::OK();
+  const int64_t B = Align128((total + L - 1) / L);  // shard bytes per local GPU
+  char* F = (char*)ctx.TempAlloc(device, (size_t)(B * L), true, s);
+  char* S = (char*)ctx.TempAlloc(device, (size_t)B, false, s);
+  if (!F || !S) return Status::UnknownError("out of device memory for the hierarchical fusion buffer");
+  const auto* dtab = (const kern::TensorDesc*)ctx.Stage(device, descs.data(), descs.size() * sizeof(kern::TensorDesc), s);
+  if (!dtab) return Status::UnknownError("descriptor table too large");
+  if (env_.timeline && env_.timeline->Initialized()) env_.timeline->ActivityStartAll(es, HVD_ACT_HIER_ALLREDUCE);
+  HVD_CUDA(kern::LaunchPackUnpack(F, dtab, (int)descs.size(), total, (int)r.dtype, (int)r.dtype, r.prescale, 0, 148, s));
+  // ---- 1. intra-host reduce-scatter: local GPU q ends up with block q of the host-local reduction ----
+  const int64_t cap = (int64_t)team.buffer_bytes();
+  const int64_t win = std::min<int64_t>(B, cap / L / 128 * 128);
+  for (int64_t w0 = 0; w0 < B; w0 += win) {
+    const int64_t cnt = std::min(win, B - w0) / esz;
+    std::vector<kern::TensorDesc> table(L + 1);
+    for (int q = 0; q < L; ++q) { table[q].in = F + q * B + w0; table[q].out = nullptr; table[q].offset = q * win; table[q].count = cnt; }
+    table[L].in = nullptr; table[L].out = S + w0; table[L].offset = li * win; table[L].count = cnt;
+    const auto* dt = (const kern::TensorDesc*)ctx.Stage(device, table.data(), table.size() * sizeof(kern::TensorDesc), s);
+    if (!dt) return Status::UnknownError("descriptor table too large");
+    kern::AllreduceArgs a {};
+    a.ndesc = L; a.descs = dt; a.out_descs = dt + L; a.nout = 1;
+    a.total_bytes = (int64_t)L * win;
+    a.reduce_lo = li * win; a.reduce_hi = li * win + Align128(cnt * esz);
+    a.prescale = 1.0; a.postscale = 1.0;
+    a.op = (int)r.reduce_op; a.dtype = (int)r.dtype; a.wire_dtype = (int)r.dtype;
+    a.variant = kern::kOneShot;
+    a.ctas = (int)std::max<int64_t>(1, std::min<int64_t>(env_.params->comm_ctas, (a.total_bytes + 16383) / 16384));
+    cudaError_t ce = kern::LaunchAllreduce(team.Params(team.NextSlot()), a, s);
+    if (ce != cudaSuccess) return Status::UnknownError(std::string("hierarchical reduce-scatter launch failed: ") + cudaGetErrorString(ce));
+  }
+  // ---- 2. cross-host allreduce of the shard (pinned staging; the CPU transport is the inter-node fabric here) ----
+  char* host = (char*)ctx.PinnedHost(device, (size_t)B);
+  if (!host) return Status::UnknownError("out of pinned host memory for the hierarchical shard");
+  HVD_CUDA(cudaMemcpyAsync(host, S, (size_t)B, cudaMemcpyDeviceToHost, s));
+  HVD_CUDA(cudaStreamSynchronize(s));
+  if (team.abort_state() == 2) return Status::UnknownError("intra-host reduce-scatter timed out waiting for a peer GPU");
+  cpu::Allreduce(ps.cross_transport.get(), host, B / esz, r.dtype, r.reduce_op);
+  HVD_CUDA(cudaMemcpyAsync(S, host, (size_t)B, cudaMemcpyHostToDevice, s));
+  // ---- 3. intra-host allgather of the shards back into the fusion buffer ----
+  const int64_t gcap = cap / 16 * 16;
+  for (int64_t w0 = 0; w0 < B; w0 += gcap) {
+    const int64_t b = std::min(gcap, B - w0);
+    std::vector<kern::CopyDesc> sends, recvs;
+    sends.push_back({S + w0, nullptr, 0, b, li, 0});
+    for (int k = 0; k < L; ++k) {
+      int p = (li + k) % L;
+      recvs.push_back({nullptr, F + p * B + w0, 0, b, p, 0});
+    }
+    st = RunExchange(team, ctx, device, s, sends, recvs, env_.params->comm_ctas);
+    if (!st.ok()) return st;
+  }
+  HVD_CUDA(kern::LaunchPackUnpack(F, dtab, (int)descs.size(), total, (int)r.dtype, (int)r.dtype, r.postscale, 1, 148, s));
+  return Status::OK();
+}
+
 std::string GpuOps::Describe(ProcessSet& ps) {
   if (!ps.team_tried) return "backend=" + env_.backend + " (no GPU collective issued yet)";
+  if (!ps.team && ps.local_team) return "backend=hierarchical intra-host symm=" + ps.local_team->backend() + " cross-host=cpu-transport";
   if (!ps.team) return "backend=host-staged";
   return "backend=" + env_.backend + " symm=" + ps.team->backend() + " buffer=" + std::to_string(ps.team->buffer_bytes());
 }
@@ -216,7 +348,8 @@ Status GpuOps::Allreduce(ProcessSet& ps, Entries& es, const Response& r, int dev
   } else {
     std::shared_ptr<SymmTeam> team = env_.backend == "cpu" ? nullptr : EnsureTeam(ps, device);
     if (!team) {
-      st = StagedOnHost(ps, es, r, device, s);
+      st = (env_.backend != "cpu" && EnsureHierarchy(ps, device)) ? HierarchicalAllreduce(ps, es, r, device, s)
+                                                                   : StagedOnHost(ps, es, r, device, s);
       if (!st.ok()) return st;
     } else {
       // ---- zero-copy path: the tensor lives in registered symmetric memory on EVERY rank (negotiated symm_key) ----

@@ -40,6 +40,8 @@ class GpuContext {
   const void* Stage(int device, const void* host, size_t bytes, cudaStream_t s);
   // zero-filled / scratch device memory that lives until the stream reaches this point
   void* TempAlloc(int device, size_t bytes, bool zero, cudaStream_t s);
+  // Grow-only pinned host staging buffer (one per device; used by the background thread only).
+  void* PinnedHost(int device, size_t bytes);
   void TempFreeAll(int device, cudaStream_t s);
   void Reset();
 
@@ -49,6 +51,7 @@ class GpuContext {
     std::vector<cudaEvent_t> pool;
     char* host_ring = nullptr; char* dev_ring = nullptr; size_t ring_off = 0;
     std::vector<void*> temps;
+    void* pinned = nullptr; size_t pinned_bytes = 0;
   };
   PerDevice& Dev(int device);
   std::mutex mu_;
@@ -89,6 +92,10 @@ class GpuOps {
  private:
   Status NcclAllreduce(ProcessSet& ps, Entries& es, const Response& r, int device, cudaStream_t s);
   Status StagedOnHost(ProcessSet& ps, Entries& es, const Response& r, int device, cudaStream_t s);
+  // Multi-host sets with the same number of GPUs per host: intra-host reduce-scatter kernel, cross-host CPU-transport
+  // allreduce of the 1/L shard, intra-host allgather kernel (the role of NCCLHierarchicalAllreduce).
+  bool EnsureHierarchy(ProcessSet& ps, int device);
+  Status HierarchicalAllreduce(ProcessSet& ps, Entries& es, const Response& r, int device, cudaStream_t s);
   // returns InProgress() when the kernel path does not apply (caller falls back to host staging)
   Status AdasumP2P(ProcessSet& ps, SymmTeam& team, Entries& es, const Response& r, const std::vector<int64_t>& counts,
                    int device, cudaStream_t s);

@@ -18,6 +18,7 @@
 #include <thread>
 #include "../common/logging.h"
 #include "transport.h"
+#include <algorithm>
 
 namespace hvd {
 namespace {
@@ -88,6 +89,7 @@ class TcpTransport : public Transport {
   int rank() const override { return rank_; }
   int size() const override { return size_; }
   bool single_host() const override { return single_host_; }
+  int host_id(int i) const override { return i >= 0 && i < (int)host_ids_.size() ? host_ids_[i] : 0; }
   void Send(int peer, const void* b, size_t n) override { WriteAll(fd(peer), b, n); }
   void Recv(int peer, void* b, size_t n) override { ReadAll(fd(peer), b, n); }
   void SendRecv(int sp, const void* sbuf, size_t sn, int rp, void* rbuf, size_t rn) override {
@@ -117,6 +119,7 @@ class TcpTransport : public Transport {
   }
   std::vector<int> fds_;
   bool single_host_ = true;
+  std::vector<int> host_ids_;
 
  private:
   int fd(int peer) const {
@@ -191,6 +194,12 @@ std::shared_ptr<Transport> CreateTcpTransport(int rank, int size, KVStore* store
   }
   if (!hostnames.empty()) {
     for (auto& h : hostnames) if (h != hostnames[rank]) t->single_host_ = false;
+    std::vector<std::string> uniq;
+    for (auto& h : hostnames) {
+      auto it = std::find(uniq.begin(), uniq.end(), h);
+      t->host_ids_.push_back((int)(it - uniq.begin()));
+      if (it == uniq.end()) uniq.push_back(h);
+    }
   }
   return t;
 }

@@ -54,6 +54,9 @@ class Transport {
 
   // true when every rank of this communicator lives on the same host
   virtual bool single_host() const { return true; }
+  // Small integer naming the host of local index i (equal ids <=> same host); used to derive the intra-host and
+  // cross-host sub-communicators of the hierarchical GPU collectives.
+  virtual int host_id(int /*i*/) const { return 0; }
 };
 
 // View of a parent transport restricted to a rank subset.
@@ -69,7 +72,11 @@ class SubTransport : public Transport {
   void SendRecv(int sp, const void* sb, size_t sn, int rp, void* rb, size_t rn) override {
     parent_->SendRecv(ranks_[sp], sb, sn, ranks_[rp], rb, rn);
   }
-  bool single_host() const override { return parent_->single_host(); }
+  bool single_host() const override {
+    for (int r : ranks_) if (parent_->host_id(r) != parent_->host_id(ranks_[0])) return false;
+    return true;
+  }
+  int host_id(int i) const override { return parent_->host_id(ranks_[i]); }
 
  private:
   Transport* parent_;

@@ -21,11 +21,22 @@ p.add_argument('--device', default='cpu')
 p.add_argument('--only', default='')
 args = p.parse_args()
 
+import os
+FAKE_HOSTS = int(os.environ.get('HVD_TEST_FAKE_HOSTS', '0'))
+if FAKE_HOSTS > 1:
+    # pretend the ranks of this box live on FAKE_HOSTS machines: the control plane drops to TCP, set-wide peer mapping is
+    # refused and GPU allreduce takes the hierarchical path (intra-"host" kernels + cross-"host" CPU transport)
+    _r, _n = int(os.environ['HOROVOD_RANK']), int(os.environ['HOROVOD_SIZE'])
+    _L = _n // FAKE_HOSTS
+    os.environ.update(HOROVOD_HOSTNAME='fakehost%d' % (_r // _L), HOROVOD_LOCAL_RANK=str(_r % _L), HOROVOD_LOCAL_SIZE=str(_L),
+                      HOROVOD_CROSS_RANK=str(_r // _L), HOROVOD_CROSS_SIZE=str(FAKE_HOSTS))
+
 hvd.init()
 rank, size = hvd.rank(), hvd.size()
+DEV_INDEX = rank if FAKE_HOSTS > 1 else hvd.local_rank()
 if args.device == 'cuda':
-    torch.cuda.set_device(hvd.local_rank())
-DEV = torch.device('cuda', hvd.local_rank()) if args.device == 'cuda' else torch.device('cpu')
+    torch.cuda.set_device(DEV_INDEX)
+DEV = torch.device('cuda', DEV_INDEX) if args.device == 'cuda' else torch.device('cpu')
 
 FLOATS = [torch.float32, torch.float64, torch.float16, torch.bfloat16]
 INTS = [torch.int32, torch.int64, torch.uint8, torch.int8, torch.int16]
@@ -64,6 +75,38 @@ def _():
     assert hvd.local_size() >= 1 and hvd.cross_size() >= 1
     assert hvd.local_rank() < hvd.local_size()
     assert hvd.is_initialized()
+
+
+@check('fake_hosts_topology')
+def _():
+    if FAKE_HOSTS <= 1:
+        return
+    L = size // FAKE_HOSTS
+    assert hvd.local_size() == L and hvd.cross_size() == FAKE_HOSTS
+    assert hvd.local_rank() == rank % L and hvd.cross_rank() == rank // L
+    assert hvd.is_homogeneous()
+
+
+@check('hierarchical_allreduce')
+def _():
+    # big enough for several reduce-scatter / allgather windows when HVD_SYMM_BUFFER_BYTES is small; fused odd sizes
+    for dtype in (torch.float32, torch.bfloat16, torch.int32):
+        tensors = [rand([n], dtype, 77 + rank * 13 + i) for i, n in enumerate([1, 1000003, 17, 262144])]
+        hs = [hvd.allreduce_async(t, op=hvd.Sum, name=f'hier.{dtype}.{i}') for i, t in enumerate(tensors)]
+        outs = [hvd.synchronize(h) for h in hs]
+        for i, n in enumerate([1, 1000003, 17, 262144]):
+            ref = sum(rand([n], dtype, 77 + r * 13 + i).double() for r in range(size)).to(dtype)
+            if dtype.is_floating_point:
+                torch.testing.assert_close(outs[i], ref, **tol(dtype))
+            else:
+                assert torch.equal(outs[i], ref)
+    x = torch.full((5, 3), float(rank + 1), device=DEV)
+    avg = hvd.allreduce(x, op=hvd.Average, name='hier.avg', prescale_factor=2.0)
+    torch.testing.assert_close(avg, torch.full((5, 3), 2.0 * (size + 1) / 2, device=DEV))
+    mx = hvd.allreduce(x, op=hvd.Max, name='hier.max')
+    assert torch.equal(mx, torch.full((5, 3), float(size), device=DEV))
+    if args.device == 'cuda' and FAKE_HOSTS > 1 and size // FAKE_HOSTS >= 2:
+        assert 'hierarchical' in hvd.gpu_backend_info(), hvd.gpu_backend_info()
 
 
 @check('allreduce_sum_avg')

@@ -41,3 +41,15 @@ def test_wire_compression_env(native_built):
                            args=["--device", "cuda", "--only", "optimizer,allreduce_async_fused"])
     # bf16 on the wire: the fused test tolerances (1e-5) are too tight by design, so only the optimizer check must pass
     assert "[ok] optimizer" in out or "ALL OK" in out, out[-3000:]
+
+
+@pytest.mark.skipif(_ngpu() < 4, reason="needs >= 4 GPUs (2 fake hosts x 2)")
+def test_hierarchical_allreduce_fake_hosts(native_built):
+    """The box's GPUs presented as 2 hosts: intra-host reduce-scatter/allgather kernels + cross-host CPU transport."""
+    n = 4 if _ngpu() < 8 else 8
+    rc, out = run_parallel("ops_worker.py", np=n, timeout=300,
+                           env={"HVD_TEST_FAKE_HOSTS": "2", "HOROVOD_LOG_LEVEL": "info", "HVD_SYMM_BUFFER_BYTES": str(2 << 20)},
+                           args=["--device", "cuda", "--only", "fake_hosts_topology,hierarchical_allreduce,allreduce_sum_avg,"
+                                 "allreduce_async_fused,allgather,broadcast,optimizer,barrier_join"])
+    assert "ALL OK" in out, out[-4000:]
+    assert "hierarchical allreduce over 2 hosts" in out, out[-4000:]

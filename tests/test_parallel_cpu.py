@@ -51,3 +51,11 @@ def test_torchrun_env_bootstrap(native_built, tmp_path):
         procs.append(subprocess.Popen([sys.executable, str(script)], env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
     outs = [p.communicate(timeout=180)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_fake_two_hosts_np4(native_built):
+    """4 ranks presented as 2 hosts x 2: TCP control plane, local/cross topology, multi-host CPU data plane."""
+    rc, out = run_parallel("ops_worker.py", np=4, timeout=400, env={"HVD_TEST_FAKE_HOSTS": "2"},
+                           args=["--only", "rank_size,fake_hosts_topology,allreduce_sum_avg,allreduce_async_fused,allgather,"
+                                 "broadcast,process_sets,barrier_join"])
+    assert "ALL OK" in out, out[-3000:]
