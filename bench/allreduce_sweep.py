@@ -36,6 +36,12 @@ for cfg in args.configs.split(','):
         os.environ['HVD_COMM_CTAS'] = parts[2]
     else:
         os.environ.pop('HVD_COMM_CTAS', None)
+    # optional 4th / 5th fields: multimem.ld_reduce per thread in flight (4|8), max chunk bytes of the zero-copy kernel
+    os.environ['HVD_NVLS_UNROLL'] = parts[3] if len(parts) > 3 else '4'
+    if len(parts) > 4:
+        os.environ['HVD_INPLACE_CHUNK_BYTES'] = parts[4]
+    else:
+        os.environ.pop('HVD_INPLACE_CHUNK_BYTES', None)
     hvd.init()
     rank, size = hvd.rank(), hvd.size()
     torch.cuda.set_device(hvd.local_rank())

@@ -19,6 +19,7 @@
 //
 // Replaces: batched_scaled_memcpy_k + ncclAllReduce + batched_scaled_memcpy_k
 // (reference ops/cuda/cuda_kernels.cu:259-324, ops/nccl_operations.cc:231-283).
+#include <cstdlib>
 #include "p2p_common.cuh"
 
 namespace hvd {
@@ -289,6 +290,34 @@ allreduce_kernel(const __grid_constant__ CommParams cp, const __grid_constant__ 
   if (threadIdx.x == 0) cp.epochs[cta] = epoch;
 }
 
+// One chunk of the in-switch allreduce: UN independent multimem.ld_reduce per thread are issued before the first
+// multimem.st so UN x 16 B per thread are in flight through the NVSwitch.
+template <typename W, int UN>
+__device__ __forceinline__ void nvls_inplace_rows(char* mc, int64_t lo, int64_t hi, typename ScaleOf<typename Traits<W>::Acc>::type scale) {
+  using A = typename Traits<W>::Acc;
+  using S = typename ScaleOf<A>::type;
+  constexpr int NW = 16 / (int)sizeof(W);
+  for (int64_t o0 = lo + (int64_t)threadIdx.x * 16; o0 < hi; o0 += (int64_t)UN * kRowBytes) {
+    uint4 v[UN];
+#pragma unroll
+    for (int j = 0; j < UN; ++j) { const int64_t o = o0 + (int64_t)j * kRowBytes; if (o < hi) v[j] = Nvls<W>::ld_reduce(mc + o); }
+#pragma unroll
+    for (int j = 0; j < UN; ++j) {
+      const int64_t o = o0 + (int64_t)j * kRowBytes;
+      if (o < hi) {
+        if (scale != (S)1) {
+          A acc[NW];
+          unpack_vec<W, NW>(v[j], acc);
+#pragma unroll
+          for (int i = 0; i < NW; ++i) acc[i] = apply_scale<A>(acc[i], scale);
+          v[j] = pack_vec<W, NW>(acc);
+        }
+        multimem_st(mc + o, v[j]);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Zero-copy allreduce on REGISTERED tensors (memory allocated with hvd.symm_empty / the bucketed DistributedOptimizer):
 // the user tensor itself is peer-mapped, so there is no pack and no unpack — the kernel is only the NVLink phase.
@@ -317,27 +346,9 @@ inplace_allreduce_kernel(const __grid_constant__ CommParams cp, const __grid_con
     const int64_t hi = lo + chunk_bytes < total ? lo + chunk_bytes : total;
     if (a.use_multicast) {
       if constexpr (Nvls<W>::ok) {
-        constexpr int UN = 4;
         char* mc = reinterpret_cast<char*>(a.mc);
-        for (int64_t o0 = lo + (int64_t)threadIdx.x * 16; o0 < hi; o0 += (int64_t)UN * kRowBytes) {
-          uint4 v[UN];
-#pragma unroll
-          for (int j = 0; j < UN; ++j) { const int64_t o = o0 + (int64_t)j * kRowBytes; if (o < hi) v[j] = Nvls<W>::ld_reduce(mc + o); }
-#pragma unroll
-          for (int j = 0; j < UN; ++j) {
-            const int64_t o = o0 + (int64_t)j * kRowBytes;
-            if (o < hi) {
-              if (scale != (S)1) {
-                A acc[NW];
-                unpack_vec<W, NW>(v[j], acc);
-#pragma unroll
-                for (int i = 0; i < NW; ++i) acc[i] = apply_scale<A>(acc[i], scale);
-                v[j] = pack_vec<W, NW>(acc);
-              }
-              multimem_st(mc + o, v[j]);
-            }
-          }
-        }
+        if (a.nvls_unroll == 8) nvls_inplace_rows<W, 8>(mc, lo, hi, scale);
+        else nvls_inplace_rows<W, 4>(mc, lo, hi, scale);
       }
     } else {
       for (int64_t o0 = lo + (int64_t)threadIdx.x * 16; o0 < hi; o0 += (int64_t)U * kRowBytes) {
@@ -488,8 +499,12 @@ cudaError_t LaunchInplaceAllreduce(const CommParams& cp, const InplaceArgs& args
   int64_t want = a.bytes / ((int64_t)a.ctas * cp.nranks);
   int chunk = (int)((want / kRowBytes) * kRowBytes);
   if (chunk < kRowBytes) chunk = kRowBytes;
-  if (chunk > kChunkBytes) chunk = kChunkBytes;
+  const int max_chunk = [] { const char* e = getenv("HVD_INPLACE_CHUNK_BYTES"); int v = e ? atoi(e) : kChunkBytes;
+                                    return v < kRowBytes ? kRowBytes : (v / kRowBytes) * kRowBytes; }();
+  const int unroll = [] { const char* e = getenv("HVD_NVLS_UNROLL"); return e && atoi(e) == 8 ? 8 : 4; }();
+  if (chunk > max_chunk) chunk = max_chunk;
   a.chunk_bytes = chunk;
+  a.nvls_unroll = unroll;
   switch (a.dtype) {
     case 7: return launch_inplace<float>(cp, a, stream);
     case 6: return launch_inplace<__half>(cp, a, stream);

@@ -88,6 +88,7 @@ struct InplaceArgs {
   int use_multicast;
   int ctas;
   int chunk_bytes;    // filled in by the launcher
+  int nvls_unroll;    // filled in by the launcher (4 | 8 multimem.ld_reduce in flight per thread)
 };
 cudaError_t LaunchInplaceAllreduce(const CommParams& cp, const InplaceArgs& args, cudaStream_t stream);
 

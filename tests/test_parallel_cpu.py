@@ -59,3 +59,8 @@ def test_fake_two_hosts_np4(native_built):
                            args=["--only", "rank_size,fake_hosts_topology,allreduce_sum_avg,allreduce_async_fused,allgather,"
                                  "broadcast,process_sets,barrier_join"])
     assert "ALL OK" in out, out[-3000:]
+
+
+def test_numpy_frontend_np2(native_built):
+    rc, out = run_parallel("numpy_worker.py", np=2, timeout=200)
+    assert "NUMPY OK" in out, out[-3000:]
