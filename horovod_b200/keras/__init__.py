@@ -1,6 +1,4 @@
-"""horovod_b200.keras — not available.
-
-The reference ships a keras binding (horovod/keras); this build targets PyTorch on B200 only and keras is not installed in
-the build image, so there is nothing to bind against. The native runtime is framework-neutral (csrc/common/engine.h takes
-raw device pointers + CUDA events): a keras adapter would mirror csrc/torch/binding.cc."""
-raise ImportError('horovod_b200.keras is not built: only the PyTorch binding (horovod_b200.torch) exists in this build')
+"""`import horovod_b200.keras as hvd` — stand-alone Keras entry point (parity: horovod/keras/__init__.py); Keras ≥ 2.4 is
+tf.keras, so this is the same implementation as `horovod_b200.tensorflow.keras`."""
+from horovod_b200.tensorflow.keras import *  # noqa: F401,F403
+from horovod_b200.tensorflow.keras import callbacks, elastic, DistributedOptimizer, load_model  # noqa: F401

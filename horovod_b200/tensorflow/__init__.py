@@ -1,6 +1,471 @@
-"""horovod_b200.tensorflow — not available.
+"""`import horovod_b200.tensorflow as hvd` — TensorFlow 2 front end.
 
-The reference ships a tensorflow binding (horovod/tensorflow); this build targets PyTorch on B200 only and tensorflow is not installed in
-the build image, so there is nothing to bind against. The native runtime is framework-neutral (csrc/common/engine.h takes
-raw device pointers + CUDA events): a tensorflow adapter would mirror csrc/torch/binding.cc."""
-raise ImportError('horovod_b200.tensorflow is not built: only the PyTorch binding (horovod_b200.torch) exists in this build')
+API parity with horovod/tensorflow/__init__.py (allreduce with IndexedSlices→allgather :58-176, grouped_allreduce
+:232-380, reducescatter :178-230, broadcast_global_variables :481, DistributedOptimizer :896, DistributedGradientTape
+:1125, PartialDistributedGradientTape :1204), functions.py (broadcast_variables :66, broadcast_object :97,
+allgather_object :177), mpi_ops.py (rank_op/size_op/... :576-660, join :564), compression.py and elastic.py.
+
+Design: there is NO TensorFlow custom-op library here (the reference's tensorflow/mpi_ops.cc + xla_mpi_ops.cc are ~2500
+lines of AsyncOpKernels).  TF tensors are handed to the runtime through the framework bridge (`horovod_b200._bridge`):
+DLPack for GPU tensors (the P2P kernels read/write TF's own HBM allocation), the numpy view for host tensors.  Inside
+`tf.function` graphs the collectives run as `tf.py_function` nodes; gradients are registered with
+`tf.custom_gradient`, with the same backward collectives the reference registers (allreduce↔allreduce,
+allgather↔reducescatter-by-slice, broadcast↔reduce-to-root, alltoall↔alltoall with the received splits).
+
+TensorFlow is not part of this image: importing this module without TensorFlow raises ImportError.
+"""
+try:
+    import tensorflow as tf
+except ImportError as _e:  # pragma: no cover - exercised only where TF is absent
+    raise ImportError('horovod_b200.tensorflow needs TensorFlow >= 2.4 (not installed in this environment); the PyTorch '
+                      'front end is horovod_b200.torch') from _e
+
+import warnings
+
+import torch as _torch
+
+from horovod_b200._bridge import BridgedOps as _BridgedOps, TensorBridge as _TensorBridge
+from horovod_b200.common.exceptions import HorovodInternalError, HostsUpdatedInterrupt  # noqa: F401
+from horovod_b200.torch import mpi_ops as _ops
+from horovod_b200.tensorflow.compression import Compression  # noqa: F401
+
+_dlpack = getattr(getattr(tf, 'experimental', None), 'dlpack', None)
+
+
+class _TFBridge(_TensorBridge):
+    name = 'tensorflow'
+
+    def to_torch(self, x):
+        if isinstance(x, tf.Variable):
+            x = x.value() if hasattr(x, 'value') else x
+        x = tf.convert_to_tensor(x)
+        dev = (getattr(x, 'device', '') or '').upper()
+        if 'GPU' in dev and _dlpack is not None:
+            return _torch.utils.dlpack.from_dlpack(_dlpack.to_dlpack(x))
+        return _torch.from_numpy(x.numpy().copy())
+
+    def from_torch(self, t, like=None):
+        if t.is_cuda and _dlpack is not None:
+            return _dlpack.from_dlpack(_torch.utils.dlpack.to_dlpack(t.contiguous()))
+        return tf.convert_to_tensor(t.detach().cpu().numpy())
+
+
+_b = _BridgedOps(_TFBridge())
+_ns = {}
+_b.export(_ns)
+for _k in ('init', 'shutdown', 'is_initialized', 'start_timeline', 'stop_timeline', 'size', 'local_size', 'cross_size',
+           'rank', 'local_rank', 'cross_rank', 'is_homogeneous', 'mpi_threads_supported', 'mpi_enabled', 'mpi_built',
+           'gloo_enabled', 'gloo_built', 'nccl_built', 'ddl_built', 'ccl_built', 'cuda_built', 'rocm_built', 'p2p_built',
+           'gpu_topology', 'gpu_backend_info', 'Average', 'Sum', 'Adasum', 'Min', 'Max', 'Product', 'global_process_set',
+           'ProcessSet', 'add_process_set', 'remove_process_set', 'barrier', 'broadcast_object', 'allgather_object'):
+    globals()[_k] = _ns[_k]
+del _k
+
+
+def join():
+    """Blocks until every rank joined; returns the last rank that joined (reference tensorflow/mpi_ops.py:564)."""
+    return _ops.join()
+
+
+def _eager():
+    return tf.executing_eagerly()
+
+
+def _run(fn, inputs, out_dtypes, name):
+    """Runs `fn(*eager tensors)` now (eager) or as a py_function node (inside tf.function)."""
+    if _eager():
+        return fn(*inputs)
+    return tf.py_function(fn, inputs, out_dtypes, name=name)
+
+
+def _normalize_name(name):
+    import re
+    return re.sub('[^a-zA-Z0-9_]', '_', name) if name else name
+
+
+# ---- scalar "ops" (reference mpi_ops.py:576-660: graph nodes whose value is read at run time, for elastic jobs) ----
+def size_op(process_set_id=0, name=None):
+    return _run(lambda: tf.constant(_ops.size() if process_set_id == 0 else len(_process_set_ranks(process_set_id)), tf.int32), [], tf.int32, name)
+
+
+def _process_set_ranks(ps_id):
+    from horovod_b200.common.process_sets import _basics as psb
+    return psb.process_set_ranks(ps_id)
+
+
+def process_set_included_op(process_set_id=0, name=None):
+    return _run(lambda: tf.constant(int(_ops.rank() in _process_set_ranks(process_set_id)) if process_set_id else 1, tf.int32), [], tf.int32, name)
+
+
+def local_size_op(name=None):
+    return _run(lambda: tf.constant(_ops.local_size(), tf.int32), [], tf.int32, name)
+
+
+def rank_op(name=None):
+    return _run(lambda: tf.constant(_ops.rank(), tf.int32), [], tf.int32, name)
+
+
+def local_rank_op(name=None):
+    return _run(lambda: tf.constant(_ops.local_rank(), tf.int32), [], tf.int32, name)
+
+
+# ---- differentiable collectives ---------------------------------------------------------------------------------------
+def _allreduce(tensor, name=None, op=_ops.Sum, prescale_factor=1.0, postscale_factor=1.0, process_set=_ops.global_process_set):
+    name = _normalize_name(name)
+
+    @tf.custom_gradient
+    def f(x):
+        y = _run(lambda t: _b.allreduce(t, name=name, op=op, prescale_factor=prescale_factor, postscale_factor=postscale_factor,
+                                        process_set=process_set), [x], x.dtype, name)
+        if not _eager():
+            y.set_shape(x.shape)
+
+        def grad(dy):
+            return _allreduce(dy, name=(name + '_grad') if name else None, op=op, prescale_factor=prescale_factor,
+                              postscale_factor=postscale_factor, process_set=process_set)
+        return y, grad
+    return f(tf.convert_to_tensor(tensor))
+
+
+def allgather(tensor, name=None, ignore_name_scope=False, process_set=_ops.global_process_set):
+    name = _normalize_name(name)
+
+    @tf.custom_gradient
+    def f(x):
+        y = _run(lambda t: _b.allgather(t, name=name, process_set=process_set), [x], x.dtype, name)
+
+        def grad(dy):
+            # every rank's slice of the summed upstream gradient (reference _allgather_grad, mpi_ops.py:228-257)
+            d0 = tf.shape(x, out_type=tf.int64)[:1]
+            sizes = tf.reshape(allgather(d0, name=(name + '_sizes') if name else None, process_set=process_set), [-1])
+            summed = _allreduce(dy, name=(name + '_grad') if name else None, op=_ops.Sum, process_set=process_set)
+            r = process_set.rank()
+            start = tf.reduce_sum(sizes[:r])
+            return summed[start:start + sizes[r]]
+        return y, grad
+    return f(tf.convert_to_tensor(tensor))
+
+
+def grouped_allgather(tensors, name=None, ignore_name_scope=False, process_set=_ops.global_process_set):
+    return [allgather(t, name=f'{name}_{i}' if name else None, process_set=process_set) for i, t in enumerate(tensors)]
+
+
+def broadcast(tensor, root_rank, name=None, ignore_name_scope=False, process_set=_ops.global_process_set):
+    name = _normalize_name(name)
+
+    @tf.custom_gradient
+    def f(x):
+        y = _run(lambda t: _b.broadcast(t, root_rank, name=name, process_set=process_set), [x], x.dtype, name)
+        if not _eager():
+            y.set_shape(x.shape)
+
+        def grad(dy):
+            g = _allreduce(dy, name=(name + '_grad') if name else None, op=_ops.Sum, process_set=process_set)
+            return g if process_set.rank() == root_rank else tf.zeros_like(g)
+        return y, grad
+    return f(tf.convert_to_tensor(tensor))
+
+
+def broadcast_(variables, root_rank, name=None, process_set=_ops.global_process_set):
+    """In-place broadcast of tf.Variables (reference mpi_ops.py:359-394)."""
+    for i, v in enumerate(variables):
+        v.assign(broadcast(v, root_rank, name=f'{name or "bcast_"}_{i}', process_set=process_set))
+    return variables
+
+
+def alltoall(tensor, splits=None, name=None, ignore_name_scope=False, process_set=_ops.global_process_set):
+    name = _normalize_name(name)
+    x = tf.convert_to_tensor(tensor)
+    if splits is None:
+        n = process_set.size()
+        splits = tf.fill([n], tf.shape(x)[0] // n)
+    splits = tf.cast(tf.convert_to_tensor(splits), tf.int32)
+
+    @tf.custom_gradient
+    def f(x, s):
+        y, rs = _run(lambda t, sp: _b.alltoall(t, splits=sp, name=name, process_set=process_set), [x, s], [x.dtype, tf.int32], name)
+
+        def grad(dy, _drs):
+            g, _ = alltoall(dy, splits=rs, name=(name + '_grad') if name else None, process_set=process_set)
+            return g, None
+        return (y, rs), grad
+    return f(x, splits)
+
+
+def _reducescatter(tensor, name=None, op=_ops.Sum, ignore_name_scope=False, process_set=_ops.global_process_set,
+                   prescale_factor=1.0, postscale_factor=1.0):
+    name = _normalize_name(name)
+
+    @tf.custom_gradient
+    def f(x):
+        y = _run(lambda t: _b.reducescatter(t, name=name, op=op, process_set=process_set, prescale_factor=prescale_factor,
+                                            postscale_factor=postscale_factor), [x], x.dtype, name)
+
+        def grad(dy):
+            g = allgather(dy, name=(name + '_grad') if name else None, process_set=process_set)
+            scale = prescale_factor * postscale_factor / (process_set.size() if op == _ops.Average else 1)
+            return g * tf.cast(scale, g.dtype) if scale != 1 else g
+        return y, grad
+    return f(tf.convert_to_tensor(tensor))
+
+
+def allreduce(tensor, average=None, device_dense='', device_sparse='', compression=Compression.none, op=None,
+              prescale_factor=1.0, postscale_factor=1.0, name=None, process_set=_ops.global_process_set):
+    """Dense tensors: allreduce.  tf.IndexedSlices: allgather of values and indices (reference __init__.py:91-120)."""
+    if average is not None:
+        warnings.warn('`average` is deprecated, use `op`', DeprecationWarning)
+        op = _ops.Average if average else _ops.Sum
+    op = _ops.Average if op is None else op
+    if isinstance(tensor, tf.IndexedSlices):
+        if op == _ops.Adasum:
+            raise NotImplementedError('The Adasum reduction does not currently support sparse tensors; pass sparse_as_dense=True')
+        values = allgather(tensor.values, name=(name + '_values') if name else None, process_set=process_set)
+        indices = allgather(tensor.indices, name=(name + '_indices') if name else None, process_set=process_set)
+        if op == _ops.Average:
+            values = values / tf.cast(process_set.size(), values.dtype)
+        return tf.IndexedSlices(values, indices, dense_shape=tensor.dense_shape)
+    if op == _ops.Average:
+        true_op, post = _ops.Sum, postscale_factor / process_set.size()
+    else:
+        true_op, post = op, postscale_factor
+    comp, ctx = compression.compress(tf.convert_to_tensor(tensor))
+    out = _allreduce(comp, name=name, op=true_op, prescale_factor=prescale_factor, postscale_factor=post, process_set=process_set)
+    return compression.decompress(out, ctx)
+
+
+def grouped_allreduce(tensors, average=None, device_dense='', device_sparse='', compression=Compression.none, op=None,
+                      prescale_factor=1.0, postscale_factor=1.0, name=None, process_set=_ops.global_process_set):
+    """One negotiated group: the members are fused into a single kernel launch (reference __init__.py:232-380)."""
+    if not tensors:
+        return tensors
+    if average is not None:
+        op = _ops.Average if average else _ops.Sum
+    op = _ops.Average if op is None else op
+    if any(isinstance(t, tf.IndexedSlices) for t in tensors):
+        return [allreduce(t, compression=compression, op=op, prescale_factor=prescale_factor, postscale_factor=postscale_factor,
+                          name=f'{name}_{i}' if name else None, process_set=process_set) for i, t in enumerate(tensors)]
+    pairs = [compression.compress(tf.convert_to_tensor(t)) for t in tensors]
+    xs = [p[0] for p in pairs]
+    name = _normalize_name(name)
+
+    @tf.custom_gradient
+    def f(*xs):
+        ys = _run(lambda *ts: _b.grouped_allreduce(list(ts), name=name, op=op, prescale_factor=prescale_factor,
+                                                   postscale_factor=postscale_factor, process_set=process_set),
+                  list(xs), [x.dtype for x in xs], name)
+        if not _eager():
+            for y, x in zip(ys, xs):
+                y.set_shape(x.shape)
+
+        def grad(*dys):
+            return grouped_allreduce(list(dys), op=op, prescale_factor=prescale_factor, postscale_factor=postscale_factor,
+                                     name=(name + '_grad') if name else None, process_set=process_set)
+        return list(ys), grad
+    outs = f(*xs)
+    return [compression.decompress(o, p[1]) for o, p in zip(outs, pairs)]
+
+
+def reducescatter(tensor, device_dense='', compression=Compression.none, op=_ops.Average, name=None,
+                  process_set=_ops.global_process_set, prescale_factor=1.0, postscale_factor=1.0):
+    comp, ctx = compression.compress(tf.convert_to_tensor(tensor))
+    out = _reducescatter(comp, name=name, op=op, process_set=process_set, prescale_factor=prescale_factor, postscale_factor=postscale_factor)
+    return compression.decompress(out, ctx)
+
+
+def grouped_reducescatter(tensors, device_dense='', compression=Compression.none, op=_ops.Average, name=None,
+                          process_set=_ops.global_process_set, prescale_factor=1.0, postscale_factor=1.0):
+    return [reducescatter(t, compression=compression, op=op, name=f'{name}_{i}' if name else None, process_set=process_set,
+                          prescale_factor=prescale_factor, postscale_factor=postscale_factor) for i, t in enumerate(tensors)]
+
+
+# ---- variables -----------------------------------------------------------------------------------------------------------
+def broadcast_variables(variables, root_rank, process_set=_ops.global_process_set, inplace=False):
+    """Assigns root_rank's value to every variable on every rank (reference functions.py:66-95)."""
+    variables = list(variables)
+    for i, v in enumerate(variables):
+        v.assign(broadcast(v, root_rank, name=f'bcast_var_{i}_{_normalize_name(getattr(v, "name", "") or str(i))}', process_set=process_set))
+    return variables
+
+
+def broadcast_global_variables(root_rank):
+    """TF1-style helper; under TF2 eager there is no global collection, so the v1 collection is used if present."""
+    if _eager():
+        raise RuntimeError('hvd.broadcast_global_variables() does not support eager execution. Use hvd.broadcast_variables(<model/optimizer variables>) instead.')
+    return broadcast_variables(tf.compat.v1.global_variables(), root_rank)
+
+
+# ---- gradient reduction helpers ---------------------------------------------------------------------------------------------
+def _group_indices(variables, groups):
+    """Returns a list of index lists.  `groups`: None (one list per variable), int (that many round-robin-free
+    contiguous buckets), or list of lists of variables (reference __init__.py:566-629)."""
+    n = len(variables)
+    if groups is None:
+        return [[i] for i in range(n)]
+    if isinstance(groups, int):
+        if groups <= 0:
+            raise ValueError('groups should be a non-negative integer or a list of list of tf.Variable.')
+        k = min(groups, n) or 1
+        per = (n + k - 1) // k
+        return [list(range(s, min(s + per, n))) for s in range(0, n, per)]
+    ids = {id(v): i for i, v in enumerate(variables)} if not hasattr(variables[0], 'ref') else {v.ref(): i for i, v in enumerate(variables)}
+    key = (lambda v: v.ref()) if hasattr(variables[0], 'ref') else id
+    seen, out = set(), []
+    for g in groups:
+        idx = [ids[key(v)] for v in g if key(v) in ids]
+        seen.update(idx)
+        if idx:
+            out.append(idx)
+    out.extend([i] for i in range(n) if i not in seen)
+    return out
+
+
+def _make_allreduce_grads_fn(name, device_dense, device_sparse, compression, sparse_as_dense, op, gradient_predivide_factor,
+                             groups, process_set):
+    if op == _ops.Average:
+        pre, post = 1.0 / gradient_predivide_factor, gradient_predivide_factor
+    else:
+        pre, post = 1.0, 1.0
+
+    def allreduce_grads(grads, variables=None, use_generic_names=False):
+        grads = list(grads)
+        if sparse_as_dense:
+            grads = [tf.convert_to_tensor(g) if isinstance(g, tf.IndexedSlices) else g for g in grads]
+        live = [i for i, g in enumerate(grads) if g is not None]
+        if process_set.size() == 1 and process_set.included():
+            return grads
+        out = list(grads)
+        if groups is not None and variables is not None:
+            for gi, idx in enumerate(_group_indices([variables[i] for i in live], groups)):
+                members = [live[j] for j in idx]
+                red = grouped_allreduce([grads[i] for i in members], compression=compression, op=op, prescale_factor=pre,
+                                        postscale_factor=post, name=f'{name}_group_{gi}', process_set=process_set)
+                for i, r in zip(members, red):
+                    out[i] = r
+        else:
+            for i in live:
+                gname = f'{name}_grad_{i}' if use_generic_names or variables is None else f'{name}_{_normalize_name(getattr(variables[i], "name", str(i)))}'
+                out[i] = allreduce(grads[i], compression=compression, op=op, prescale_factor=pre, postscale_factor=post,
+                                   name=gname, process_set=process_set)
+        return out
+    return allreduce_grads
+
+
+class LocalGradientAggregationHelper:
+    """Accumulates gradients over `backward_passes_per_step` calls and only then reduces them (reference
+    gradient_aggregation_eager.py:12-170).  Eager-mode implementation on tf.Variables."""
+
+    def __init__(self, backward_passes_per_step, allreduce_func, average_aggregated_gradients=False):
+        self.n = int(backward_passes_per_step)
+        self.allreduce_func = allreduce_func
+        self.average = average_aggregated_gradients
+        self.counter = 0
+        self.acc = None
+
+    def compute_gradients(self, grads, variables):
+        grads = [tf.convert_to_tensor(g) if isinstance(g, tf.IndexedSlices) else g for g in grads]
+        if self.n <= 1:
+            return self.allreduce_func(grads, variables)
+        if self.acc is None:
+            self.acc = [None if g is None else tf.Variable(tf.zeros_like(g), trainable=False) for g in grads]
+        for a, g in zip(self.acc, grads):
+            if a is not None and g is not None:
+                a.assign_add(g)
+        self.counter += 1
+        if self.counter < self.n:
+            return None  # caller must skip apply_gradients
+        self.counter = 0
+        agg = [None if a is None else (a / self.n if self.average else a.read_value()) for a in self.acc]
+        for a in self.acc:
+            if a is not None:
+                a.assign(tf.zeros_like(a))
+        return self.allreduce_func(agg, variables)
+
+
+class _DistributedGradientTape:
+    """Delegating wrapper: `.gradient()` reduces what the wrapped tape computed."""
+
+    def __init__(self, tape, allreduce_grads, local_sources=(), scale_local_gradients=True, process_set=_ops.global_process_set):
+        self._tape = tape
+        self._allreduce_grads = allreduce_grads
+        self._local = {(_v.ref() if hasattr(_v, 'ref') else id(_v)) for _v in local_sources}
+        self._scale_local = scale_local_gradients
+        self._process_set = process_set
+
+    def __getattr__(self, item):
+        return getattr(self._tape, item)
+
+    def __enter__(self):
+        self._tape.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        return self._tape.__exit__(*exc)
+
+    def register_local_source(self, source):
+        """Marks a variable whose gradient stays local (reference PartialDistributedGradientTape)."""
+        self._local.add(source.ref() if hasattr(source, 'ref') else id(source))
+
+    def gradient(self, target, sources, output_gradients=None, use_generic_names=False):
+        single = not isinstance(sources, (list, tuple))
+        srcs = [sources] if single else list(sources)
+        grads = list(self._tape.gradient(target, srcs, output_gradients))
+        key = (lambda v: v.ref()) if srcs and hasattr(srcs[0], 'ref') else id
+        is_local = [key(s) in self._local for s in srcs]
+        shared = [i for i, l in enumerate(is_local) if not l]
+        reduced = self._allreduce_grads([grads[i] for i in shared], [srcs[i] for i in shared], use_generic_names)
+        for i, r in zip(shared, reduced):
+            grads[i] = r
+        if self._scale_local and any(is_local):
+            n = self._process_set.size()
+            grads = [g / n if (l and g is not None) else g for g, l in zip(grads, is_local)]
+        return grads[0] if single else grads
+
+
+def DistributedGradientTape(gradtape, device_dense='', device_sparse='', compression=Compression.none, sparse_as_dense=False,
+                            op=_ops.Average, gradient_predivide_factor=1.0, num_groups=0, groups=None,
+                            process_set=_ops.global_process_set, scale_local_gradients=True):
+    if gradient_predivide_factor != 1.0 and op != _ops.Average:
+        raise ValueError('gradient_predivide_factor not supported with op != Average')
+    if num_groups != 0:
+        warnings.warn('Parameter `num_groups` has been replaced by `groups`', DeprecationWarning)
+        groups = groups if groups is not None else num_groups
+    if groups is not None and not (isinstance(groups, list) or groups > 0):
+        raise ValueError('groups should be a non-negative integer or a list of list of tf.Variable.')
+    fn = _make_allreduce_grads_fn('DistributedGradientTape', device_dense, device_sparse, compression, sparse_as_dense, op,
+                                  gradient_predivide_factor, groups, process_set)
+    return _DistributedGradientTape(gradtape, fn, (), scale_local_gradients, process_set)
+
+
+def PartialDistributedGradientTape(gradtape, device_dense='', device_sparse='', compression=Compression.none,
+                                   sparse_as_dense=False, op=_ops.Average, gradient_predivide_factor=1.0, num_groups=0,
+                                   groups=None, process_set=_ops.global_process_set, local_layers=None, scale_local_gradients=True):
+    """Like DistributedGradientTape, but the variables of `local_layers` keep their local gradients."""
+    tape = DistributedGradientTape(gradtape, device_dense, device_sparse, compression, sparse_as_dense, op,
+                                   gradient_predivide_factor, num_groups, groups, process_set, scale_local_gradients)
+    layers = [] if local_layers is None else (local_layers if isinstance(local_layers, (list, tuple)) else [local_layers])
+    for layer in layers:
+        for v in layer.trainable_weights:
+            tape.register_local_source(v)
+    return tape
+
+
+def DistributedOptimizer(optimizer, name=None, use_locking=False, device_dense='', device_sparse='', compression=Compression.none,
+                         sparse_as_dense=False, backward_passes_per_step=1, op=_ops.Average, gradient_predivide_factor=1.0,
+                         average_aggregated_gradients=False, num_groups=0, groups=None, process_set=_ops.global_process_set,
+                         scale_local_gradients=True):
+    """Wraps a Keras (TF2) optimizer so gradients are reduced across ranks before they are applied."""
+    if gradient_predivide_factor != 1.0 and op != _ops.Average:
+        raise ValueError('gradient_predivide_factor not supported with op != Average')
+    if op == _ops.Adasum and average_aggregated_gradients:
+        raise ValueError('Adasum does not support average_aggregated_gradients == True')
+    if num_groups != 0:
+        warnings.warn('Parameter `num_groups` has been replaced by `groups`', DeprecationWarning)
+        groups = groups if groups is not None else num_groups
+    from horovod_b200._keras import create_distributed_optimizer
+    return create_distributed_optimizer(tf.keras, optimizer, name, device_dense, device_sparse, compression, sparse_as_dense,
+                                        gradient_predivide_factor, op, backward_passes_per_step, average_aggregated_gradients,
+                                        groups, process_set, scale_local_gradients)
+
+
+from horovod_b200.tensorflow.sync_batch_norm import SyncBatchNormalization  # noqa: E402,F401
+from horovod_b200.tensorflow import elastic  # noqa: E402,F401

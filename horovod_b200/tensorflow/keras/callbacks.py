@@ -1,0 +1,2 @@
+from horovod_b200._keras.callbacks import (  # noqa: F401
+    BroadcastGlobalVariablesCallback, MetricAverageCallback, LearningRateScheduleCallback, LearningRateWarmupCallback)

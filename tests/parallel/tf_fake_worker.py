@@ -1,0 +1,117 @@
+"""np=N run of the TensorFlow front end against tests/fakes/tensorflow (see that file's disclaimer)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'fakes'))
+import numpy as np
+import tensorflow as tf
+
+assert tf.__version__.endswith('fake')
+import horovod_b200.tensorflow as hvd
+import horovod_b200.tensorflow.keras as hvdk
+
+hvd.init()
+r, n = hvd.rank(), hvd.size()
+
+x = tf.constant(np.arange(6, dtype=np.float32).reshape(2, 3) * (r + 1))
+np.testing.assert_allclose(hvd.allreduce(x, op=hvd.Sum, name='tf.sum').numpy(), np.arange(6).reshape(2, 3) * n * (n + 1) / 2)
+np.testing.assert_allclose(hvd.allreduce(x, name='tf.avg').numpy(), np.arange(6).reshape(2, 3) * (n + 1) / 2, rtol=1e-6)
+np.testing.assert_allclose(hvd.allreduce(x, name='tf.avg16', compression=hvd.Compression.fp16).numpy(),
+                           np.arange(6).reshape(2, 3) * (n + 1) / 2, rtol=1e-2)
+assert hvd.allreduce(x, name='tf.avg16b', compression=hvd.Compression.fp16).dtype == tf.float32
+# IndexedSlices -> allgather of values / indices, averaged
+sl = tf.IndexedSlices(tf.constant(np.ones((2, 3), np.float32) * (r + 1)), tf.constant(np.array([r, r + 1], np.int64)),
+                      dense_shape=tf.constant(np.array([n + 1, 3], np.int64)))
+out = hvd.allreduce(sl, name='tf.sparse')
+assert isinstance(out, tf.IndexedSlices) and out.values.shape == (2 * n, 3) and out.indices.numpy().tolist() == [q + d for q in range(n) for d in (0, 1)]
+np.testing.assert_allclose(out.values.numpy()[:2], np.ones((2, 3)) / n)
+
+g = hvd.grouped_allreduce([tf.constant(np.ones(3, np.float32) * r), tf.constant(np.ones((2, 2), np.float64))], op=hvd.Sum, name='tf.grp')
+assert g[0].numpy().tolist() == [n * (n - 1) / 2] * 3 and g[1].numpy().tolist() == [[n, n], [n, n]]
+
+ag = hvd.allgather(tf.constant(np.full((r + 1, 2), r, np.int32)), name='tf.ag')
+assert ag.shape == (n * (n + 1) // 2, 2)
+b = hvd.broadcast(tf.constant(np.full(3, r, np.int64)), root_rank=n - 1, name='tf.bc')
+assert b.numpy().tolist() == [n - 1] * 3
+o, rs = hvd.alltoall(tf.constant(np.arange(n, dtype=np.float32) + 10 * r), name='tf.a2a')
+assert o.numpy().tolist() == [10.0 * q + r for q in range(n)] and rs.numpy().tolist() == [1] * n
+rsx = hvd.reducescatter(tf.constant(np.ones((2 * n, 2), np.float32) * (r + 1)), op=hvd.Sum, name='tf.rs')
+assert rsx.shape == (2, 2) and np.all(rsx.numpy() == n * (n + 1) / 2)
+
+vs = [tf.Variable(np.full(4, float(r)), name='a:0'), tf.Variable(np.full((2, 2), float(r * 2)), name='b:0')]
+hvd.broadcast_variables(vs, root_rank=0)
+assert vs[0].numpy().tolist() == [0.0] * 4 and vs[1].numpy().tolist() == [[0.0, 0.0], [0.0, 0.0]]
+assert hvd.rank_op().numpy() == r and hvd.size_op().numpy() == n and hvd.local_rank_op().numpy() == hvd.local_rank()
+
+# DistributedGradientTape: dense + None + sparse-as-dense + a local (unsynchronised) source, grouped
+tape = tf.GradientTape()
+w = [tf.Variable(np.zeros(3), name='w0:0'), tf.Variable(np.zeros(2), name='w1:0'), tf.Variable(np.zeros(2), name='w2:0'),
+     tf.Variable(np.zeros(2), name='local:0')]
+tape.canned = [tf.constant(np.ones(3) * (r + 1)), None, tf.constant(np.ones(2) * 2 * (r + 1)), tf.constant(np.ones(2) * n)]
+dt = hvd.DistributedGradientTape(tape, groups=2)
+dt.register_local_source(w[3])
+with dt:
+    pass
+gr = dt.gradient(None, w)
+np.testing.assert_allclose(gr[0].numpy(), np.ones(3) * (n + 1) / 2)
+assert gr[1] is None
+np.testing.assert_allclose(gr[2].numpy(), np.ones(2) * (n + 1))
+np.testing.assert_allclose(gr[3].numpy(), np.ones(2))  # local gradient scaled by 1/size, not reduced
+dt2 = hvd.DistributedGradientTape(tape, op=hvd.Sum, sparse_as_dense=True)
+tape.canned = [sl]
+dense = dt2.gradient(None, [w[0]])[0]
+assert dense.shape == (n + 1, 3)
+
+# backward_passes_per_step aggregation helper
+calls = []
+helper = hvd.LocalGradientAggregationHelper(2, lambda g, v: calls.append(1) or [hvd.allreduce(x, op=hvd.Sum, name='agg') for x in g], True)
+assert helper.compute_gradients([tf.constant(np.ones(2) * 2.0)], [w[1]]) is None
+res = helper.compute_gradients([tf.constant(np.ones(2) * 4.0)], [w[1]])
+np.testing.assert_allclose(res[0].numpy(), np.ones(2) * 3.0 * n)
+assert len(calls) == 1
+
+# callbacks
+from horovod_b200.tensorflow.keras.callbacks import MetricAverageCallback, BroadcastGlobalVariablesCallback, LearningRateWarmupCallback
+logs = {'loss': float(r), 'acc': float(2 * r), 'note': 'text'}
+MetricAverageCallback().on_epoch_end(0, logs)
+assert abs(logs['loss'] - (n - 1) / 2) < 1e-9 and abs(logs['acc'] - (n - 1)) < 1e-9 and logs['note'] == 'text'
+
+
+class _Opt:
+    def __init__(self):
+        self.learning_rate = tf.Variable(np.array(0.1))
+        self.momentum = tf.Variable(np.array(0.9))
+        self._v = [tf.Variable(np.full(2, float(r)))]
+
+    def variables(self):
+        return self._v
+
+
+class _Model:
+    def __init__(self):
+        self.variables = [tf.Variable(np.full(3, float(r + 5)))]
+        self.optimizer = _Opt()
+
+
+m = _Model()
+cb = BroadcastGlobalVariablesCallback(0)
+cb.set_model(m)
+cb.on_batch_end(0)
+assert m.variables[0].numpy().tolist() == [5.0] * 3 and m.optimizer._v[0].numpy().tolist() == [0.0] * 2
+wu = LearningRateWarmupCallback(initial_lr=0.8, warmup_epochs=2, steps_per_epoch=4)
+wu.set_model(m)
+wu.on_train_begin()
+wu.on_epoch_begin(0)
+wu.on_batch_begin(0)
+lr0 = float(m.optimizer.learning_rate.numpy())
+assert abs(lr0 - 0.8 / n * (0.25 * (n - 1) / 2 + 1)) < 1e-9, lr0
+wu.on_batch_end(0)
+assert abs(float(m.optimizer.momentum.numpy()) - 0.9) < 1e-9
+wu.on_epoch_begin(1)
+wu.on_batch_begin(3)
+assert abs(float(m.optimizer.learning_rate.numpy()) - 0.8) < 1e-9  # epoch 1 + 3/4 + 1/4 == warmup_epochs
+assert hvdk.allreduce(np.array([1.0, 2.0]) * (r + 1), name='k.ar', op=hvd.Sum).tolist() == [n * (n + 1) / 2, n * (n + 1.0)]
+hvd.barrier()
+if r == 0:
+    print('TF FAKE OK')
+hvd.shutdown()

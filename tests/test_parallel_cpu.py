@@ -64,3 +64,20 @@ def test_fake_two_hosts_np4(native_built):
 def test_numpy_frontend_np2(native_built):
     rc, out = run_parallel("numpy_worker.py", np=2, timeout=200)
     assert "NUMPY OK" in out, out[-3000:]
+
+
+def test_tensorflow_frontend_against_fake_tf_np2(native_built):
+    """Control flow of horovod_b200.tensorflow (+ keras callbacks) over a numpy-backed TensorFlow stand-in
+    (tests/fakes/tensorflow): TensorFlow itself is not installed in this image."""
+    rc, out = run_parallel("tf_fake_worker.py", np=2, timeout=200)
+    assert "TF FAKE OK" in out, out[-3000:]
+
+
+def test_tensorflow_frontend_import_error_without_tf():
+    import importlib, sys
+    if importlib.util.find_spec("tensorflow") is not None:
+        pytest.skip("TensorFlow is installed")
+    for m in [k for k in sys.modules if k.startswith("horovod_b200.tensorflow")]:
+        del sys.modules[m]
+    with pytest.raises(ImportError, match="TensorFlow"):
+        importlib.import_module("horovod_b200.tensorflow")
