@@ -49,10 +49,15 @@ def _header_digest():
     return h.hexdigest()[:12]
 
 
+def _src_stamp(src, header_stamp):
+    """Content hash of the translation unit + every header: staleness never depends on file mtimes (a snapshot copied to
+    another machine keeps the contents but not necessarily the timestamps)."""
+    with open(src, "rb") as fh:
+        return hashlib.sha1(fh.read() + header_stamp.encode()).hexdigest()[:16]
+
+
 def _needs(src, obj, stamp):
-    if not os.path.exists(obj) or os.path.getmtime(obj) < os.path.getmtime(src):
-        return True
-    return not os.path.exists(obj + "." + stamp)
+    return not (os.path.exists(obj) and os.path.exists(obj + "." + stamp))
 
 
 def _run(cmd):
@@ -66,6 +71,7 @@ def _run(cmd):
 def _compile(src, stamp, force, verbose):
     rel = os.path.relpath(src, CSRC).replace("/", "__")
     obj = os.path.join(OBJ, rel + ".o")
+    stamp = _src_stamp(src, stamp)
     if not force and not _needs(src, obj, stamp):
         return obj
     inc = ["-I" + os.path.join(CUDA_HOME, "include"), "-I/usr/include"]
@@ -93,9 +99,13 @@ def build_core(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=max(2, os.cpu_count() or 4)) as ex:
         objs = list(ex.map(lambda s: _compile(s, stamp, force, verbose), cu + cc))
     lib = os.path.join(OUT, "libhvd_core.so")
-    newest = max(os.path.getmtime(o) for o in objs)
-    if force or not os.path.exists(lib) or os.path.getmtime(lib) < newest:
+    link_stamp = hashlib.sha1("".join(sorted(f for f in os.listdir(OBJ) if ".o." in f)).encode()).hexdigest()[:16]
+    stamp_file = os.path.join(OBJ, "core_link.stamp")
+    old = open(stamp_file).read() if os.path.exists(stamp_file) else ""
+    if force or not os.path.exists(lib) or old != link_stamp:
         _run([NVCC] + ARCH + ["-shared", "-o", lib] + objs + ["-cudart", "static", "-lpthread", "-ldl", "-lrt"])
+        with open(stamp_file, "w") as f:
+            f.write(link_stamp)
     return lib
 
 
@@ -107,9 +117,10 @@ def build_torch(force=False):
     lib = os.path.join(OUT, "_hvd_torch.so")
     core = os.path.join(OUT, "libhvd_core.so")
     stamp_file = os.path.join(OBJ, "torch_binding.stamp")
-    stamp = _header_digest() + "-" + torch.__version__
+    core_stamp = os.path.join(OBJ, "core_link.stamp")
+    stamp = _src_stamp(src, _header_digest()) + "-" + torch.__version__ + "-" + (open(core_stamp).read() if os.path.exists(core_stamp) else "")
     old = open(stamp_file).read() if os.path.exists(stamp_file) else ""
-    if (not force and os.path.exists(lib) and os.path.getmtime(lib) >= os.path.getmtime(src) and old == stamp):
+    if not force and os.path.exists(lib) and old == stamp:
         return lib
     inc = ["-I" + p for p in cpp_extension.include_paths()] + ["-I" + os.path.join(CUDA_HOME, "include"),
                                                                "-I" + sysconfig.get_paths()["include"]]

@@ -164,6 +164,7 @@ allreduce_kernel(const __grid_constant__ CommParams cp, const __grid_constant__ 
   using S = typename ScaleOf<A>::type;
   constexpr int NW = 16 / (int)sizeof(W);
   constexpr int U = 8 / NR;  // rows per trip in the peer phases
+  constexpr int UP = NW >= 16 ? 4 : 8;  // rows per trip in the local pack / unpack phases (8 x 16 B loads in flight per thread)
   const int cta = blockIdx.x, grid = gridDim.x;
   const TensorDesc* descs = a.descs ? a.descs : a.inline_descs;
   const TensorDesc* odescs = a.out_descs ? a.out_descs : descs;
@@ -179,7 +180,7 @@ allreduce_kernel(const __grid_constant__ CommParams cp, const __grid_constant__ 
   for (int64_t c = cta; c < nchunks; c += grid) {
     const int64_t lo = c * chunk_bytes;
     const int64_t hi = lo + chunk_bytes < total ? lo + chunk_bytes : total;
-    pack_range<T, W, 4>(descs, a.ndesc, total, mybuf, lo, hi, prescale);
+    pack_range<T, W, UP>(descs, a.ndesc, total, mybuf, lo, hi, prescale);
   }
   if (cp.nranks > 1) alive = peer_barrier(cp, epoch, cta); else __syncthreads();
 
@@ -284,7 +285,7 @@ allreduce_kernel(const __grid_constant__ CommParams cp, const __grid_constant__ 
       int64_t hi = lo + chunk_bytes < total ? lo + chunk_bytes : total;
       if (lo < a.reduce_lo) lo = a.reduce_lo;
       if (hi > a.reduce_hi) hi = a.reduce_hi;
-      if (lo < hi) unpack_range<T, W, 4>(odescs, nout, total, mybuf, lo, hi);
+      if (lo < hi) unpack_range<T, W, UP>(odescs, nout, total, mybuf, lo, hi);
     }
   }
   if (threadIdx.x == 0) cp.epochs[cta] = epoch;

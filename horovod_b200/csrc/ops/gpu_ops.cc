@@ -413,8 +413,12 @@ Status GpuOps::Allreduce(ProcessSet& ps, Entries& es, const Response& r, int dev
         a.variant = variant;
         int64_t per = variant == kern::kOneShot ? 8192 : (int64_t)4096 * n;  // >= 2 rows (one-shot) or one row per rank (two-shot) per CTA
         // small messages are latency bound (few CTAs = cheap barrier, SMs left to compute); large ones need many loads in flight
+        // >= 64 MiB of plain (unregistered) tensors: the local pack / unpack phases are HBM-latency bound at one CTA per
+        // SM (ncu: 12.5 % warps active, 1.3 TB/s), so go to two CTAs per SM
+        static const int64_t big_ctas = std::min<int64_t>(kern::kMaxCtas, EnvInt("HVD_LARGE_MSG_CTAS", 256));
         const int64_t cap_ctas = seg_bytes <= (1 << 20) ? std::min<int64_t>(tp.comm_ctas, 16)
-                               : seg_bytes <= (16 << 20) ? std::min<int64_t>(tp.comm_ctas, 64) : tp.comm_ctas;
+                               : seg_bytes <= (16 << 20) ? std::min<int64_t>(tp.comm_ctas, 64)
+                               : seg_bytes < (64 << 20) ? tp.comm_ctas : std::max<int64_t>(tp.comm_ctas, big_ctas);
         a.ctas = (int)std::max<int64_t>(1, std::min<int64_t>(cap_ctas, (seg_bytes + per - 1) / per));
         if (a.ndesc <= kern::kInlineDescs) {
           memcpy(a.inline_descs, descs.data(), descs.size() * sizeof(kern::TensorDesc));
