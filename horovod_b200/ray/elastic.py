@@ -1,33 +1,145 @@
-"""Host discovery backed by the Ray cluster state (role parity: horovod/ray/elastic_v2.py RayHostDiscovery)."""
+"""Elastic training on Ray (parity: horovod/ray/elastic.py: `RayHostDiscovery` :39-71, `ElasticRayExecutor` :150-470).
+
+Discovery asks Ray's global state for alive nodes and converts their CPU/GPU resources into slots; the elastic driver
+(`horovod_b200.runner.elastic.driver.ElasticDriver`) then treats Ray exactly like an ssh cluster whose "spawn a worker"
+callback creates an actor on the requested node instead of running ssh.
+"""
+import os
+import queue
+import threading
+
+from horovod_b200.runner.common.util import timeout as _timeout_mod
 from horovod_b200.runner.elastic.discovery import HostDiscovery
+from horovod_b200.runner.elastic.driver import ElasticDriver
+from horovod_b200.runner.elastic.rendezvous import create_rendezvous_handler
+from horovod_b200.runner.http.http_server import RendezvousServer
+from horovod_b200.runner.mesh_run import create_run_env_vars, create_slot_env_vars
 
 
 class RayHostDiscovery(HostDiscovery):
-    """Uses Ray global state to obtain host mapping. Assumes that the whole global state is available for usage."""
+    """Hosts and slots from `ray.nodes()`."""
 
-    def __init__(self, use_gpu=False, cpus_per_worker=1, gpus_per_worker=1, nodes_fn=None):
-        self.use_gpu = use_gpu
-        self.cpus_per_worker = cpus_per_worker
-        self.gpus_per_worker = gpus_per_worker
-        self._nodes_fn = nodes_fn  # injectable for tests; defaults to ray.nodes
+    def __init__(self, use_gpu=False, cpus_per_slot=1, gpus_per_slot=1, nodes_fn=None):
+        self.use_gpu, self.cpus_per_slot, self.gpus_per_slot = use_gpu, cpus_per_slot, gpus_per_slot
+        self._nodes_fn = nodes_fn
+
+    def _nodes(self):
+        if self._nodes_fn is not None:
+            return self._nodes_fn()
+        import ray
+        return ray.nodes()
 
     def find_available_hosts_and_slots(self):
-        """Returns a dict mapping <hostname> -> <number of slots>."""
-        if self._nodes_fn is None:
-            import ray
-            nodes = ray.nodes()
-        else:
-            nodes = self._nodes_fn()
-        host_mapping = {}
-        for node in nodes:
+        mapping = {}
+        for node in self._nodes():
             if not node.get('alive', node.get('Alive', False)):
                 continue
-            hostname = node.get('NodeManagerAddress') or node.get('NodeManagerHostname')
-            resources = node.get('Resources', {})
-            slots = resources.get('CPU', 0) // self.cpus_per_worker
-            if self.use_gpu:
-                slots = min(slots, resources.get('GPU', 0) // self.gpus_per_worker)
-            slots = int(slots)
-            if slots:
-                host_mapping[hostname] = slots
-        return host_mapping
+            res = node.get('Resources', {})
+            host = node.get('NodeManagerAddress') or node.get('NodeManagerHostname')
+            slots = int(res.get('GPU', 0) // self.gpus_per_slot) if self.use_gpu else int(res.get('CPU', 0) // self.cpus_per_slot)
+            if host and slots > 0:
+                mapping[host] = slots
+        return mapping
+
+
+class ElasticRayExecutor:
+    """Runs an elastic job: workers are (re)created as Ray actors whenever discovery reports a change.
+
+    `run(worker_fn)` returns the list of values returned by the workers of the final, successful round.
+    """
+
+    @staticmethod
+    def create_settings(min_num_proc=1, max_num_proc=None, reset_limit=None, elastic_timeout=600, timeout_s=30,
+                        ssh_identity_file=None, nics=None, **kwargs):
+        from horovod_b200.runner.elastic.settings import ElasticSettings
+        start_timeout = _timeout_mod.Timeout(timeout_s, message='Timed out waiting for {activity}. Please check connectivity between servers.')
+        return ElasticSettings(discovery=None, min_num_proc=min_num_proc, max_num_proc=max_num_proc, elastic_timeout=elastic_timeout,
+                               reset_limit=reset_limit, num_proc=min_num_proc, ssh_identity_file=ssh_identity_file, nics=nics,
+                               start_timeout=start_timeout, **kwargs)
+
+    def __init__(self, settings, use_gpu=False, cpus_per_slot=1, gpus_per_slot=None, env_vars=None, override_discovery=True,
+                 actor_factory=None):
+        if gpus_per_slot and not use_gpu:
+            raise ValueError('gpus_per_slot is set, but use_gpu is False. use_gpu must be True if gpus_per_slot is set.')
+        gpus_per_slot = gpus_per_slot or 1
+        if override_discovery:
+            settings.discovery = RayHostDiscovery(use_gpu=use_gpu, cpus_per_slot=cpus_per_slot, gpus_per_slot=gpus_per_slot)
+        self.settings, self.use_gpu = settings, use_gpu
+        self.cpus_per_slot, self.gpus_per_slot = cpus_per_slot, gpus_per_slot
+        self.env_vars = dict(env_vars or {})
+        self.driver, self.rendezvous = None, None
+        self._actor_factory = actor_factory  # (hostname, env) -> object with .execute(fn) [tests]; default: Ray actor
+
+    def start(self):
+        self.rendezvous = RendezvousServer(self.settings.verbose)
+        self.driver = ElasticDriver(self.rendezvous, self.settings.discovery, self.settings.min_num_proc, self.settings.max_num_proc,
+                                    timeout=self.settings.elastic_timeout, reset_limit=self.settings.reset_limit,
+                                    verbose=self.settings.verbose)
+        port = self.rendezvous.start_server()
+        create_rendezvous_handler(self.driver).install(self.rendezvous)
+        self.driver.wait_for_available_slots(self.settings.min_num_proc)
+        self._run_env = create_run_env_vars(_driver_ip(), port, nics=self.settings.nics, elastic=True)
+
+    def _make_actor(self, hostname, env):
+        if self._actor_factory is not None:
+            return self._actor_factory(hostname, env)
+        import ray
+        from horovod_b200.runner.cluster_job import WorkerActor
+        res = {f'node:{hostname}': 0.01}
+        cls = ray.remote(num_cpus=self.cpus_per_slot, num_gpus=self.gpus_per_slot if self.use_gpu else 0, resources=res)(WorkerActor)
+        actor = cls.remote()
+        ray.get(actor.update_env.remote(env))
+
+        class _H:
+            def execute(self_inner, fn):
+                return ray.get(actor.execute.remote(fn))
+
+            def kill(self_inner):
+                ray.kill(actor)
+        return _H()
+
+    def run(self, worker_fn, callbacks=None):
+        results_q = queue.Queue()
+
+        def spawn(slot_info, events):
+            env = dict(self.env_vars)
+            env.update(self._run_env)
+            env.update(create_slot_env_vars(slot_info))
+            env['HOROVOD_ELASTIC'] = '1'
+            actor = self._make_actor(slot_info.hostname, env)
+            done = threading.Event()
+            box = {}
+
+            def body():
+                try:
+                    box['value'] = actor.execute(worker_fn)
+                    box['code'] = 0
+                except Exception as e:  # a dead actor is a failed worker: the driver blacklists / re-plans
+                    box['code'], box['error'] = 1, e
+                done.set()
+            threading.Thread(target=body, daemon=True).start()
+            while not done.wait(0.1):
+                if any(e.is_set() for e in events):
+                    if hasattr(actor, 'kill'):
+                        actor.kill()
+                    return 1, 0
+            if box['code'] == 0:
+                results_q.put((slot_info.rank, box['value']))
+            return box['code'], 0
+
+        self.driver.start(self.settings.num_proc or self.settings.min_num_proc, spawn)
+        res = self.driver.get_results()
+        self.driver.stop()
+        self.rendezvous.stop()
+        if res.error_message:
+            raise RuntimeError(res.error_message)
+        out = {}
+        while not results_q.empty():
+            r, v = results_q.get()
+            out[r] = v
+        return [out[r] for r in sorted(out)]
+
+
+def _driver_ip():
+    from horovod_b200.runner.cluster_job import _routable_ip
+    return os.environ.get('HVD_DRIVER_IP', _routable_ip())

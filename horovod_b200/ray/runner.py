@@ -1,84 +1,151 @@
-"""RayExecutor: start N Ray actors, give each its rank environment + the address of the rendezvous KV server hosted by
-the driver, and run functions on all of them (role parity: horovod/ray/runner.py RayExecutor / Coordinator)."""
-from horovod_b200.ray import strategy
-from horovod_b200.runner.http.http_server import RendezvousServer
-from horovod_b200.runner.util import network
+"""RayExecutor: run hvd jobs on a Ray cluster.
+
+Parity: horovod/ray/runner.py (`RayExecutor.create_settings/start/run/run_remote/execute/execute_single/shutdown`
+:168-420, `Coordinator` :45-130) and strategy.py (`ColocatedStrategy` :66-137: num_hosts x num_workers_per_host with a
+STRICT_SPREAD placement group; `PGStrategy` :139-225: num_workers packed by a PACK placement group).
+
+The scheduler-independent part (rank table, rendezvous, env hand-off, ordered results) is
+`horovod_b200.runner.cluster_job.ClusterJob`; this file only maps "create a worker" onto Ray actors and placement
+groups.  Pass `backend=` to run the same executor on another ActorBackend (the tests use LocalProcessBackend since Ray
+is not installed in this image).
+"""
+from horovod_b200.runner.cluster_job import ActorBackend, ClusterJob, WorkerActor
 
 
-class RayExecutor(object):
-    def __init__(self, settings=None, num_workers=None, num_hosts=None, num_workers_per_host=1, cpus_per_worker=1,
-                 use_gpu=False, gpus_per_worker=None):
-        if num_workers is None and num_hosts is None:
-            raise ValueError('Either `num_workers` or `num_hosts` must be specified.')
-        self.settings = settings
-        self.num_workers = num_workers
-        self.num_hosts = num_hosts
-        self.num_workers_per_host = num_workers_per_host
-        self.cpus_per_worker = cpus_per_worker
-        self.use_gpu = use_gpu
-        self.gpus_per_worker = gpus_per_worker if gpus_per_worker is not None else (1 if use_gpu else 0)
-        self.workers = []
-        self._server = None
-        self._pg = None
+class _Settings:
+    """What create_settings returns (reference MiniSettings)."""
 
-    def start(self, executable_cls=None, executable_args=None, executable_kwargs=None, extra_env_vars=None):
+    def __init__(self, timeout_s=30, ssh_identity_file=None, ssh_str=None, placement_group_timeout_s=100, nics=None, verbose=0):
+        self.timeout_s, self.ssh_identity_file, self.ssh_str = timeout_s, ssh_identity_file, ssh_str
+        self.placement_group_timeout_s, self.nics, self.verbose = placement_group_timeout_s, nics, verbose
+
+
+class RayBackend(ActorBackend):
+    """Ray actors inside one placement group.  `bundles` is one resource dict per worker."""
+
+    def __init__(self, bundles, strategy='PACK', pg_timeout_s=100, use_current_placement_group=True):
         import ray
-        from ray.util.placement_group import placement_group
+        from ray.util.placement_group import get_current_placement_group, placement_group
+        self.ray = ray
+        self.bundles = bundles
+        self.pg, self._own_pg = None, False
+        if use_current_placement_group:
+            self.pg = get_current_placement_group()
+        if self.pg is None:
+            self.pg = placement_group(bundles, strategy=strategy)
+            self._own_pg = True
+            ready, _ = ray.wait([self.pg.ready()], timeout=pg_timeout_s)
+            if not ready:
+                raise TimeoutError('Placement group creation timed out. Make sure your cluster either has enough resources or use an '
+                                   'autoscaling cluster. Current resources available: %s, resources requested by the placement group: %s'
+                                   % (ray.available_resources(), bundles))
+        self._remote_cls = ray.remote(WorkerActor)
 
-        if self.num_hosts:
-            bundles, strat = strategy.colocated_bundles(self.num_hosts, self.num_workers_per_host, self.cpus_per_worker, self.gpus_per_worker)
-            total = self.num_hosts * self.num_workers_per_host
-        else:
-            bundles, strat = strategy.pack_bundles(self.num_workers, self.cpus_per_worker, self.gpus_per_worker)
-            total = self.num_workers
-        self._pg = placement_group(bundles, strategy=strat)
-        ray.get(self._pg.ready())
+    def create(self, index, env=None):
+        from ray.util.scheduling_strategies import PlacementGroupSchedulingStrategy
+        b = self.bundles[index]
+        opts = dict(num_cpus=b.get('CPU', 1), num_gpus=b.get('GPU', 0),
+                    scheduling_strategy=PlacementGroupSchedulingStrategy(placement_group=self.pg, placement_group_bundle_index=index))
+        actor = self._remote_cls.options(**opts).remote(index)
+        if env:
+            self.ray.get(actor.update_env.remote(env))
+        return actor
 
-        @ray.remote(num_cpus=self.cpus_per_worker, num_gpus=self.gpus_per_worker)
-        class _Worker(object):
-            def __init__(self):
-                self.executable = None
+    def call(self, handle, method, *args, **kwargs):
+        return getattr(handle, method).remote(*args, **kwargs)
 
-            def hostname(self):
-                import socket
-                return socket.gethostname()
+    def get(self, futures, timeout=None):
+        return self.ray.get(futures, timeout=timeout)
 
-            def update_env_vars(self, env):
-                import os
-                os.environ.update({k: str(v) for k, v in env.items()})
-
-            def start_executable(self, cls, args, kwargs):
-                self.executable = cls(*(args or []), **(kwargs or {}))
-
-            def execute(self, fn):
-                return fn(self.executable) if self.executable is not None else fn()
-
-        self.workers = [_Worker.options(placement_group=self._pg).remote() for _ in range(total)]
-        hostnames = ray.get([w.hostname.remote() for w in self.workers])
-        envs = strategy.assign_ranks(hostnames)
-        self._server = RendezvousServer()
-        port = self._server.start_server()
-        addr = network.get_driver_ip(None)
-        for w, env in zip(self.workers, envs):
-            env = dict(env, HOROVOD_GLOO_RENDEZVOUS_ADDR=addr, HOROVOD_GLOO_RENDEZVOUS_PORT=str(port), **(extra_env_vars or {}))
-            ray.get(w.update_env_vars.remote(env))
-        if executable_cls is not None:
-            ray.get([w.start_executable.remote(executable_cls, executable_args, executable_kwargs) for w in self.workers])
-
-    def execute(self, fn):
-        import ray
-        return ray.get([w.execute.remote(fn) for w in self.workers])
-
-    def run(self, fn, args=None, kwargs=None):
-        import ray
-        args, kwargs = args or [], kwargs or {}
-        return ray.get([w.execute.remote(lambda _=None: fn(*args, **kwargs)) for w in self.workers])
+    def kill(self, handle):
+        self.ray.kill(handle)
 
     def shutdown(self):
-        import ray
-        for w in self.workers:
-            ray.kill(w)
-        self.workers = []
-        if self._server:
-            self._server.stop()
-            self._server = None
+        if self._own_pg and self.pg is not None:
+            from ray.util.placement_group import remove_placement_group
+            remove_placement_group(self.pg)
+            self.pg = None
+
+
+class RayExecutor:
+    """Job class for hvd + Ray.
+
+    Either `num_workers` (packed wherever resources are) or `num_hosts` x `num_workers_per_host` (one bundle group per
+    host, spread strictly).  `use_gpu` gives every worker `gpus_per_worker` GPUs; CUDA_VISIBLE_DEVICES inside an
+    actor is what Ray sets, and hvd's local_rank indexes into it.
+    """
+
+    @classmethod
+    def create_settings(cls, timeout_s=30, ssh_identity_file=None, ssh_str=None, placement_group_timeout_s=100, nics=None):
+        return _Settings(timeout_s, ssh_identity_file, ssh_str, placement_group_timeout_s, nics)
+
+    def __init__(self, settings=None, num_workers=None, num_hosts=None, num_workers_per_host=1, cpus_per_worker=1, use_gpu=False,
+                 gpus_per_worker=None, use_current_placement_group=True, backend=None, env_vars=None):
+        if num_workers is None and num_hosts is None:
+            raise ValueError('Either `num_workers` or `num_hosts` must be set.')
+        if num_workers is not None and num_hosts is not None:
+            raise ValueError('Only one of `num_workers` and `num_hosts` may be set.')
+        if gpus_per_worker and not use_gpu:
+            raise ValueError('gpus_per_worker is set, but use_gpu is False. use_gpu must be True if gpus_per_worker is set.')
+        if use_gpu and isinstance(gpus_per_worker, int) and gpus_per_worker < 1:
+            raise ValueError(f'gpus_per_worker must be >= 1: Got {gpus_per_worker}.')
+        self.settings = settings or _Settings()
+        self.colocated = num_hosts is not None
+        self.num_workers = num_workers if num_workers is not None else num_hosts * num_workers_per_host
+        self.num_hosts, self.num_workers_per_host = num_hosts, num_workers_per_host
+        self.cpus_per_worker, self.use_gpu = cpus_per_worker, use_gpu
+        self.gpus_per_worker = (gpus_per_worker or 1) if use_gpu else 0
+        self.use_current_placement_group = use_current_placement_group
+        self.env_vars = dict(env_vars or {})
+        self._backend, self.job = backend, None
+
+    def _bundles(self):
+        return [{'CPU': self.cpus_per_worker, **({'GPU': self.gpus_per_worker} if self.use_gpu else {})} for _ in range(self.num_workers)]
+
+    def start(self, executable_cls=None, executable_args=None, executable_kwargs=None, extra_env_vars=None):
+        """Creates the workers, assigns ranks and (optionally) instantiates `executable_cls` on each of them."""
+        backend = self._backend
+        if backend is None:
+            backend = RayBackend(self._bundles(), 'STRICT_SPREAD' if self.colocated and self.num_workers_per_host == 1 else 'PACK',
+                                 self.settings.placement_group_timeout_s, self.use_current_placement_group)
+            self._backend = backend
+        env = dict(self.env_vars)
+        env.update(extra_env_vars or {})
+        self.job = ClusterJob(backend, self.num_workers, env=env, nics=self.settings.nics, verbose=getattr(self.settings, 'verbose', 0),
+                              start_timeout=max(self.settings.timeout_s, 30)).start()
+        self._has_executable = executable_cls is not None
+        if executable_cls is not None:
+            a, k = tuple(executable_args or ()), dict(executable_kwargs or {})
+
+            def make():
+                import builtins
+                builtins._hvd_ray_executable = executable_cls(*a, **k)
+                return True
+            self.job.run(make)
+
+    def execute(self, fn):
+        """fn(executable) on every worker (the object created by start(executable_cls=...)); results in rank order."""
+        def call():
+            import builtins
+            return fn(getattr(builtins, '_hvd_ray_executable', None))
+        return self.job.run(call)
+
+    def run(self, fn, args=None, kwargs=None):
+        return self.job.run(fn, tuple(args or ()), dict(kwargs or {}))
+
+    def run_remote(self, fn, args=None, kwargs=None):
+        """Non-blocking: returns the backend's futures (Ray ObjectRefs) in rank order."""
+        return self.job.run_remote(fn, tuple(args or ()), dict(kwargs or {}))
+
+    def execute_single(self, fn):
+        def call():
+            import builtins
+            return fn(getattr(builtins, '_hvd_ray_executable', None))
+        return self.job.run_single(call, 0)
+
+    def shutdown(self):
+        if self.job:
+            self.job.shutdown()
+            self.job = None
+        if hasattr(self._backend, 'shutdown'):
+            self._backend.shutdown()

@@ -1,0 +1,112 @@
+"""Ray / Spark integrations exercised on the scheduler-independent core with the local subprocess backend (neither Ray
+nor PySpark is installed here).  Reference coverage model: test/single/test_ray.py (RayExecutor: rank table, env,
+run/execute/execute_single/run_remote, train end-to-end) and test/integration/test_spark.py (`horovod.spark.run`)."""
+import os
+
+import pytest
+
+from horovod_b200.runner.cluster_job import ClusterJob, LocalProcessBackend, assign_slots
+
+
+def test_assign_slots_contiguous_per_node_and_heterogeneous():
+    slots = assign_slots(['a', 'b', 'a', 'b', 'a'])
+    assert [s.rank for s in slots] == [0, 3, 1, 4, 2]
+    assert [s.local_rank for s in slots] == [0, 0, 1, 1, 2]
+    assert [s.local_size for s in slots] == [3, 2, 3, 2, 3]
+    assert [s.cross_rank for s in slots] == [0, 1, 0, 1, 0]
+    assert [s.cross_size for s in slots] == [2, 2, 2, 2, 1]
+    assert all(s.size == 5 for s in slots)
+
+
+def _train(scale):
+    import torch
+    import horovod_b200.torch as hvd
+    hvd.init()
+    out = hvd.allreduce(torch.ones(3) * (hvd.rank() + 1) * scale, op=hvd.Sum).tolist()
+    res = (hvd.rank(), hvd.size(), hvd.local_rank(), hvd.local_size(), hvd.cross_rank(), out)
+    hvd.shutdown()
+    return res
+
+
+def test_cluster_job_runs_hvd_on_fake_two_node_layout(native_built):
+    backend = LocalProcessBackend(node_ids={0: 'n0', 1: 'n1', 2: 'n0', 3: 'n1'})
+    job = ClusterJob(backend, 4, env={'HOROVOD_LOG_LEVEL': 'warning', 'OMP_NUM_THREADS': '1'}).start()
+    try:
+        res = job.run(_train, args=(2.0,), timeout=120)
+    finally:
+        job.shutdown()
+    assert [r[0] for r in res] == [0, 1, 2, 3] and all(r[1] == 4 for r in res)
+    assert [r[2] for r in res] == [0, 1, 0, 1] and [r[4] for r in res] == [0, 0, 1, 1]
+    assert all(r[3] == 2 for r in res)
+    assert all(r[5] == [20.0] * 3 for r in res)
+
+
+def test_ray_executor_api_over_local_backend(native_built):
+    from horovod_b200.ray import RayExecutor
+
+    class Trainer:
+        def __init__(self, base):
+            self.base = base
+
+        def rank_plus(self):
+            return self.base + int(os.environ['HOROVOD_RANK'])
+
+    settings = RayExecutor.create_settings(timeout_s=30)
+    with pytest.raises(ValueError):
+        RayExecutor(settings)
+    with pytest.raises(ValueError):
+        RayExecutor(settings, num_workers=2, num_hosts=1)
+    with pytest.raises(ValueError):
+        RayExecutor(settings, num_workers=2, gpus_per_worker=1)
+    ex = RayExecutor(settings, num_workers=2, backend=LocalProcessBackend(), env_vars={'HVD_TEST_FLAG': 'x', 'OMP_NUM_THREADS': '1'})
+    ex.start(executable_cls=Trainer, executable_args=[100])
+    try:
+        assert ex.execute(lambda t: t.rank_plus()) == [100, 101]
+        assert ex.execute_single(lambda t: t.base) == 100
+        assert ex.run(lambda: os.environ['HVD_TEST_FLAG']) == ['x', 'x']
+        res = ex.run(_train, args=[1.0])
+        assert [r[0] for r in res] == [0, 1] and all(r[5] == [3.0] * 3 for r in res)
+        futs = ex.run_remote(lambda a, b=0: a + b, args=[1], kwargs={'b': 2})
+        assert ex.job.backend.get(futs, 30) == [3, 3]
+        with pytest.raises(RuntimeError, match='ZeroDivisionError'):
+            ex.run(lambda: 1 / 0)
+        assert ex.run(lambda: 'still alive') == ['still alive'] * 2
+    finally:
+        ex.shutdown()
+
+
+def test_ray_host_discovery_from_node_table():
+    from horovod_b200.ray import RayHostDiscovery
+    nodes = [{'alive': True, 'NodeManagerAddress': '10.0.0.1', 'Resources': {'CPU': 8.0, 'GPU': 4.0}},
+             {'alive': False, 'NodeManagerAddress': '10.0.0.2', 'Resources': {'CPU': 8.0, 'GPU': 4.0}},
+             {'alive': True, 'NodeManagerAddress': '10.0.0.3', 'Resources': {'CPU': 3.0}}]
+    assert RayHostDiscovery(use_gpu=True, gpus_per_slot=2, nodes_fn=lambda: nodes).find_available_hosts_and_slots() == {'10.0.0.1': 2}
+    assert RayHostDiscovery(cpus_per_slot=2, nodes_fn=lambda: nodes).find_available_hosts_and_slots() == {'10.0.0.1': 4, '10.0.0.3': 1}
+
+
+def _mp_launch(n, task_main):
+    """Stands in for a Spark barrier stage: n subprocesses that each run the task body."""
+    import multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    procs = [ctx.Process(target=task_main, args=(i, {'OMP_NUM_THREADS': '1', 'HOROVOD_LOG_LEVEL': 'warning'}), daemon=True) for i in range(n)]
+    for p in procs:
+        p.start()
+    return procs
+
+
+def test_spark_run_over_connect_back_tasks(native_built):
+    import horovod_b200.spark as hvd_spark
+    res = hvd_spark.run(_train, args=(1.0,), num_proc=3, _launch=_mp_launch, start_timeout=120, verbose=0)
+    assert [r[0] for r in res] == [0, 1, 2] and all(r[1] == 3 for r in res)
+    assert all(r[5] == [6.0] * 3 for r in res)
+    with pytest.raises(ValueError):
+        hvd_spark.run(_train, use_mpi=True, num_proc=1, _launch=_mp_launch)
+
+
+def test_spark_run_without_pyspark_raises():
+    import importlib.util
+    if importlib.util.find_spec('pyspark') is not None:
+        pytest.skip('PySpark is installed')
+    import horovod_b200.spark as hvd_spark
+    with pytest.raises(ImportError, match='PySpark'):
+        hvd_spark.run(lambda: 0)
