@@ -1,147 +1,151 @@
-"""Where estimators keep intermediate data, checkpoints and logs (role parity: horovod/spark/common/store.py:38-165).
-LocalStore works on any mounted filesystem; HDFS/DBFS variants need their client libraries and are gated."""
+"""Run artefact store for the estimators (parity: horovod/spark/common/store.py: `Store` interface :38-165,
+`FilesystemStore`/`LocalStore` :301-395; HDFS/DBFS stores map onto `FilesystemStore` with an fsspec/pyarrow
+filesystem).  Layout under `prefix_path`:
+
+    intermediate_train_data[.idx]/   parquet written by the estimator
+    intermediate_val_data[.idx]/
+    runs/<run_id>/checkpoint.pt      rank-0 checkpoints
+    runs/<run_id>/logs/
+"""
 import os
 import shutil
 
 
-class Store(object):
-    """Abstracts reading and writing of intermediate data and run results."""
-
-    def is_parquet_dataset(self, path):
-        raise NotImplementedError()
+class Store:
+    """Interface; `Store.create(path)` picks an implementation from the path's scheme."""
 
     def get_train_data_path(self, idx=None):
-        raise NotImplementedError()
+        raise NotImplementedError
 
     def get_val_data_path(self, idx=None):
-        raise NotImplementedError()
+        raise NotImplementedError
 
     def get_test_data_path(self, idx=None):
-        raise NotImplementedError()
-
-    def saving_runs(self):
-        raise NotImplementedError()
-
-    def get_runs_path(self):
-        raise NotImplementedError()
+        raise NotImplementedError
 
     def get_run_path(self, run_id):
-        raise NotImplementedError()
+        raise NotImplementedError
 
     def get_checkpoint_path(self, run_id):
-        raise NotImplementedError()
+        raise NotImplementedError
 
     def get_logs_path(self, run_id):
-        raise NotImplementedError()
-
-    def get_checkpoint_filename(self):
-        raise NotImplementedError()
-
-    def get_logs_subdir(self):
-        raise NotImplementedError()
+        raise NotImplementedError
 
     def exists(self, path):
-        raise NotImplementedError()
+        raise NotImplementedError
 
     def read(self, path):
-        raise NotImplementedError()
+        raise NotImplementedError
 
     def write(self, path, data):
-        raise NotImplementedError()
+        raise NotImplementedError
+
+    def write_text(self, path, text):
+        self.write(path, text.encode('utf-8'))
 
     @staticmethod
     def create(prefix_path, *args, **kwargs):
-        if prefix_path.startswith('hdfs://'):
-            raise ImportError('HDFSStore needs pyarrow.hdfs / fsspec[hdfs], not available in this environment')
-        if prefix_path.startswith('dbfs:/'):
-            raise ImportError('DBFSLocalStore is only meaningful on Databricks')
-        return LocalStore(prefix_path, *args, **kwargs)
+        scheme = prefix_path.split('://', 1)[0] if '://' in prefix_path else 'file'
+        if scheme == 'file':
+            return LocalStore(prefix_path, *args, **kwargs)
+        return FilesystemStore(prefix_path, *args, **kwargs)
 
 
 class FilesystemStore(Store):
-    """Store on a POSIX-like filesystem layout: <prefix>/intermediate_{train,val,test}_data, <prefix>/runs/<id>/..."""
+    """Any pyarrow.fs filesystem (local, hdfs://, s3://, gs://); paths handed out are URIs usable by pyarrow.dataset."""
 
-    def __init__(self, prefix_path, train_path=None, val_path=None, test_path=None, runs_path=None, save_runs=True):
-        self.prefix_path = self.get_full_path(prefix_path)
-        self._train_path = self._get_full_path_or_default(train_path, 'intermediate_train_data')
-        self._val_path = self._get_full_path_or_default(val_path, 'intermediate_val_data')
-        self._test_path = self._get_full_path_or_default(test_path, 'intermediate_test_data')
-        self._runs_path = self._get_full_path_or_default(runs_path, 'runs')
+    def __init__(self, prefix_path, train_path=None, val_path=None, test_path=None, runs_path=None, save_runs=True, filesystem=None):
+        self.prefix_path = prefix_path.rstrip('/')
+        self._train = train_path or self._join('intermediate_train_data')
+        self._val = val_path or self._join('intermediate_val_data')
+        self._test = test_path or self._join('intermediate_test_data')
+        self._runs = runs_path or self._join('runs')
         self._save_runs = save_runs
+        self._fs = filesystem
 
-    def _get_full_path_or_default(self, path, default_key):
-        return self.get_full_path(path) if path is not None else self._get_path(default_key)
+    def _join(self, *parts):
+        return '/'.join([self.prefix_path] + list(parts))
 
-    def _get_path(self, key):
-        return os.path.join(self.prefix_path, key)
+    @property
+    def fs(self):
+        if self._fs is None:
+            import pyarrow.fs as pafs
+            self._fs, self._root = pafs.FileSystem.from_uri(self.prefix_path)
+        return self._fs
 
-    def get_full_path(self, path):
-        return os.path.abspath(path)
-
-    def _indexed(self, base, idx):
-        return '{}.{}'.format(base, idx) if idx is not None else base
+    def _local(self, path):
+        """Path as the filesystem object wants it (URI scheme stripped)."""
+        return path.split('://', 1)[1] if '://' in path else path
 
     def get_train_data_path(self, idx=None):
-        return self._indexed(self._train_path, idx)
+        return self._train if idx is None else f'{self._train}.{idx}'
 
     def get_val_data_path(self, idx=None):
-        return self._indexed(self._val_path, idx)
+        return self._val if idx is None else f'{self._val}.{idx}'
 
     def get_test_data_path(self, idx=None):
-        return self._indexed(self._test_path, idx)
-
-    def is_parquet_dataset(self, path):
-        return os.path.isdir(path) and any(f.endswith('.parquet') for f in os.listdir(path))
+        return self._test if idx is None else f'{self._test}.{idx}'
 
     def saving_runs(self):
         return self._save_runs
 
     def get_runs_path(self):
-        return self._runs_path
+        return self._runs
 
     def get_run_path(self, run_id):
-        return os.path.join(self.get_runs_path(), run_id)
-
-    def get_checkpoint_path(self, run_id):
-        return os.path.join(self.get_run_path(run_id), self.get_checkpoint_filename()) if self._save_runs else None
-
-    def get_logs_path(self, run_id):
-        return os.path.join(self.get_run_path(run_id), self.get_logs_subdir()) if self._save_runs else None
+        return f'{self._runs}/{run_id}'
 
     def get_checkpoint_filename(self):
         return 'checkpoint.pt'
 
+    def get_checkpoint_path(self, run_id):
+        return f'{self.get_run_path(run_id)}/{self.get_checkpoint_filename()}' if self._save_runs else None
+
     def get_logs_subdir(self):
         return 'logs'
 
+    def get_logs_path(self, run_id):
+        return f'{self.get_run_path(run_id)}/{self.get_logs_subdir()}' if self._save_runs else None
+
     def exists(self, path):
-        return os.path.exists(path)
+        import pyarrow.fs as pafs
+        return self.fs.get_file_info(self._local(path)).type != pafs.FileType.NotFound
 
     def read(self, path):
-        with open(path, 'rb') as f:
+        with self.fs.open_input_stream(self._local(path)) as f:
             return f.read()
 
     def write(self, path, data):
-        os.makedirs(os.path.dirname(path), exist_ok=True)
-        tmp = path + '.tmp'
-        with open(tmp, 'wb') as f:
+        p = self._local(path)
+        self.fs.create_dir(os.path.dirname(p), recursive=True)
+        with self.fs.open_output_stream(p) as f:
             f.write(data)
-        os.replace(tmp, path)  # atomic: a reader never sees a half-written checkpoint
 
-    def sync_fn(self, run_id):
-        run_path = self.get_run_path(run_id)
+    def is_parquet_dataset(self, path):
+        import pyarrow.fs as pafs
+        info = self.fs.get_file_info(pafs.FileSelector(self._local(path), allow_not_found=True))
+        return any(i.path.endswith('.parquet') for i in info)
 
-        def fn(local_run_path):
-            if os.path.abspath(local_run_path) != os.path.abspath(run_path):
-                shutil.copytree(local_run_path, run_path, dirs_exist_ok=True)
-        return fn
+    def delete(self, path):
+        if self.exists(path):
+            self.fs.delete_dir(self._local(path))
 
 
 class LocalStore(FilesystemStore):
-    """Uses the local filesystem as a store of intermediate data and training artifacts."""
-    FS_PREFIX = 'file://'
+    """Plain directories on a filesystem every worker can see (single box, NFS)."""
 
     def __init__(self, prefix_path, *args, **kwargs):
-        if prefix_path.startswith(self.FS_PREFIX):
-            prefix_path = prefix_path[len(self.FS_PREFIX):]
-        super().__init__(prefix_path, *args, **kwargs)
+        if prefix_path.startswith('file://'):
+            prefix_path = prefix_path[len('file://'):]
+        super().__init__(os.path.abspath(prefix_path), *args, **kwargs)
+
+    @property
+    def fs(self):
+        if self._fs is None:
+            import pyarrow.fs as pafs
+            self._fs = pafs.LocalFileSystem()
+        return self._fs
+
+    def delete(self, path):
+        shutil.rmtree(path, ignore_errors=True)
