@@ -4,6 +4,7 @@
 // exactly what runs across NVLink; only the address mapping differs.  Lets the
 // kernels be validated (and run under compute-sanitizer) on one B200.
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -31,10 +32,29 @@ Sim* GetSim(int nranks, int device, size_t buffer_bytes) {
     for (auto st : s.streams) cudaStreamDestroy(st);
     s.streams.assign(nranks, nullptr);
     for (int r = 0; r < nranks; ++r) cudaStreamCreateWithFlags(&s.streams[r], cudaStreamNonBlocking);
+    // a scheduling deadlock of the simulation must surface as an error, not as a hung test
+    const char* to = getenv("HVD_KERNEL_TIMEOUT_SECONDS");
+    for (auto& t : s.teams) t->set_timeout_seconds(to ? atof(to) : 20.0);
   }
   return &s;
 }
 int64_t Align128(int64_t b) { return (b + 127) / 128 * 128; }
+
+// After the device drained: a barrier that timed out (scheduling deadlock of the simulation) is an error, and the team is
+// thrown away so that the next call starts from clean flags / epochs.
+int Finish(int nranks, cudaError_t sync_result) {
+  if (sync_result != cudaSuccess) return (int)sync_result;
+  auto it = g_sims.find(nranks);
+  if (it == g_sims.end()) return 0;
+  for (auto& t : it->second.teams) {
+    if (t->abort_state() != 0) {
+      for (auto st : it->second.streams) cudaStreamDestroy(st);
+      g_sims.erase(it);
+      return -3;
+    }
+  }
+  return 0;
+}
 }  // namespace
 
 extern "C" {
@@ -81,7 +101,7 @@ int hvd_sim_allreduce(int nranks, int device, int ntensors, const int64_t* count
   cudaError_t e = cudaDeviceSynchronize();
   if (ms_out) cudaEventElapsedTime(ms_out, e0, e1);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  return (int)e;
+  return Finish(nranks, e);
 }
 
 // Allgather-style exchange: every rank contributes `bytes` from in_ptrs[r]; out_ptrs[r] receives nranks*bytes.
@@ -104,7 +124,7 @@ int hvd_sim_allgather(int nranks, int device, int64_t bytes, const uint64_t* in_
     cudaError_t e = kern::LaunchExchange(cp, a, sim->streams[r]);
     if (e != cudaSuccess) return (int)e;
   }
-  return (int)cudaDeviceSynchronize();
+  return Finish(nranks, cudaDeviceSynchronize());
 }
 
 // Adasum over N simulated ranks: in_ptrs/out_ptrs [nranks][ntensors]; dtype fp32/fp16/bf16.
@@ -116,8 +136,10 @@ int hvd_sim_adasum(int nranks, int device, int ntensors, const int64_t* counts, 
   for (int i = 0; i < ntensors; ++i) { offs[i] = total; total += Align128(counts[i] * 4); }
   Sim* sim = GetSim(nranks, device, (size_t)std::max<int64_t>(total, 1 << 20));
   if (!sim) return -1;
-  // the launches of one rank are stream ordered; ranks interleave level by level so that all kernels of a level are
-  // co-resident (each kernel of rank r waits at its barrier for the same kernel of the other ranks)
+  // Step-major launch order (step k of EVERY rank before step k+1 of any rank): the streams of the simulated ranks may
+  // share a hardware queue, and a rank-major order would park rank 1's kernels behind rank 0's spinning ones.
+  std::vector<const kern::TensorDesc*> dtabs(nranks);
+  std::vector<kern::CommParams> cps(nranks);
   for (int r = 0; r < nranks; ++r) {
     std::vector<kern::TensorDesc> d(ntensors);
     for (int i = 0; i < ntensors; ++i) {
@@ -126,16 +148,21 @@ int hvd_sim_adasum(int nranks, int device, int ntensors, const int64_t* counts, 
       d[i].offset = offs[i];
       d[i].count = counts[i];
     }
-    const auto* dt = (const kern::TensorDesc*)GpuContext::Get().Stage(device, d.data(), d.size() * sizeof(kern::TensorDesc), sim->streams[r]);
-    if (!dt) return -2;
-    kern::AdasumArgs a {};
-    a.descs = dt; a.ndesc = ntensors; a.total_bytes = total; a.dtype = dtype; a.ctas = ctas;
-    a.scratch_stride_bytes = kern::kAdasumScratchStride;
-    kern::CommParams cp = sim->teams[r]->Params(sim->teams[r]->NextSlot());
-    cudaError_t e = kern::LaunchAdasum(cp, a, prescale, postscale, sim->streams[r]);
-    if (e != cudaSuccess) return (int)e;
+    dtabs[r] = (const kern::TensorDesc*)GpuContext::Get().Stage(device, d.data(), d.size() * sizeof(kern::TensorDesc), sim->streams[r]);
+    if (!dtabs[r]) return -2;
+    cps[r] = sim->teams[r]->Params(sim->teams[r]->NextSlot());
   }
-  return (int)cudaDeviceSynchronize();
+  const int steps = kern::AdasumNumLaunches(nranks);
+  for (int k = 0; k < steps; ++k) {
+    for (int r = 0; r < nranks; ++r) {
+      kern::AdasumArgs a {};
+      a.descs = dtabs[r]; a.ndesc = ntensors; a.total_bytes = total; a.dtype = dtype; a.ctas = ctas;
+      a.scratch_stride_bytes = kern::kAdasumScratchStride;
+      cudaError_t e = kern::LaunchAdasumStep(cps[r], a, prescale, postscale, sim->streams[r], k);
+      if (e != cudaSuccess) return (int)e;
+    }
+  }
+  return Finish(nranks, cudaDeviceSynchronize());
 }
 
 // Zero-copy in-place allreduce over N simulated ranks: ptrs[r] = rank r's tensor (plain device memory here).
@@ -162,7 +189,7 @@ int hvd_sim_inplace(int nranks, int device, int64_t bytes, const uint64_t* ptrs,
   cudaError_t e = cudaDeviceSynchronize();
   if (ms_out) cudaEventElapsedTime(ms_out, e0, e1);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  return (int)e;
+  return Finish(nranks, e);
 }
 
 void hvd_sim_reset() {

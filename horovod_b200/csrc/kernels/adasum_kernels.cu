@@ -178,12 +178,20 @@ adasum_gather_kernel(const __grid_constant__ CommParams cp, const TensorDesc* __
   if (threadIdx.x == 0) cp.epochs[cta] = epoch;
 }
 
+// `only` < 0: the whole sequence (production: one GPU per process).  `only` = k: just the k-th launch of the sequence
+// (pack = 0, dots/combine of level l = 1 + 2l / 2 + 2l, gather last) — the single-GPU simulation issues launch k of
+// EVERY rank before launch k+1 of any rank, otherwise streams that share a hardware queue deadlock (a kernel spinning in
+// its barrier sits in front of the peer kernel it is waiting for).
 template <typename T>
-cudaError_t run_adasum(const CommParams& cp, const AdasumArgs& a, double prescale, double postscale, cudaStream_t s) {
+cudaError_t run_adasum(const CommParams& cp, const AdasumArgs& a, double prescale, double postscale, cudaStream_t s, int only) {
   const int n = cp.nranks, rank = cp.rank;
   const int64_t total = a.total_bytes;
-  adasum_pack_kernel<T><<<a.ctas, kThreads, 0, s>>>(cp, a.descs, a.ndesc, total, (float)prescale);
-  CountKernelLaunch();
+  int step = 0;
+  if (only < 0 || only == step) {
+    adasum_pack_kernel<T><<<a.ctas, kThreads, 0, s>>>(cp, a.descs, a.ndesc, total, (float)prescale);
+    CountKernelLaunch();
+  }
+  ++step;
   // replay the halving for every rank (element granularity: 4 floats = one 16 B vector)
   GatherRanges rg;
   for (int p = 0; p < n; ++p) {
@@ -203,29 +211,48 @@ cudaError_t run_adasum(const CommParams& cp, const AdasumArgs& a, double prescal
     const int64_t klo = lower ? lo : mid, khi = lower ? mid : hi;
     const int64_t off = kFlagWords * 4 + (int64_t)(level & 1) * a.scratch_stride_bytes;
     double* scratch = reinterpret_cast<double*>(reinterpret_cast<char*>(cp.flags[rank]) + off);
-    cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)3 * a.ndesc * sizeof(double), s);
-    if (e != cudaSuccess) return e;
-    adasum_dots_kernel<<<a.ctas, kThreads, dots_smem, s>>>(cp, a.descs, a.ndesc, total, klo, khi, partner, lower, scratch);
-    CountKernelLaunch();
-    adasum_combine_kernel<<<a.ctas, kThreads, coef_smem, s>>>(cp, a.descs, a.ndesc, total, klo, khi, partner, lower,
-                                                               rank & ~(2 * d - 1), 2 * d, off);
-    CountKernelLaunch();
+    if (only < 0 || only == step) {
+      cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)3 * a.ndesc * sizeof(double), s);
+      if (e != cudaSuccess) return e;
+      adasum_dots_kernel<<<a.ctas, kThreads, dots_smem, s>>>(cp, a.descs, a.ndesc, total, klo, khi, partner, lower, scratch);
+      CountKernelLaunch();
+    }
+    ++step;
+    if (only < 0 || only == step) {
+      adasum_combine_kernel<<<a.ctas, kThreads, coef_smem, s>>>(cp, a.descs, a.ndesc, total, klo, khi, partner, lower,
+                                                                 rank & ~(2 * d - 1), 2 * d, off);
+      CountKernelLaunch();
+    }
+    ++step;
     lo = klo; hi = khi;
   }
-  adasum_gather_kernel<T><<<a.ctas, kThreads, 0, s>>>(cp, a.descs, a.ndesc, total, rg, (float)postscale);
-  CountKernelLaunch();
+  if (only < 0 || only == step) {
+    adasum_gather_kernel<T><<<a.ctas, kThreads, 0, s>>>(cp, a.descs, a.ndesc, total, rg, (float)postscale);
+    CountKernelLaunch();
+  }
   return cudaGetLastError();
 }
 
 }  // namespace
 
+int AdasumNumLaunches(int nranks) {
+  int levels = 0;
+  for (int d = 1; d < nranks; d <<= 1) ++levels;
+  return 2 + 2 * levels;
+}
+
 cudaError_t LaunchAdasum(const CommParams& cp, const AdasumArgs& args, double prescale, double postscale, cudaStream_t stream) {
+  return LaunchAdasumStep(cp, args, prescale, postscale, stream, -1);
+}
+
+cudaError_t LaunchAdasumStep(const CommParams& cp, const AdasumArgs& args, double prescale, double postscale, cudaStream_t stream,
+                             int only) {
   if (args.ctas < 1 || args.ctas > kMaxCtas || (cp.nranks & (cp.nranks - 1))) return cudaErrorInvalidValue;
   if (args.ndesc > kAdasumMaxTensors) return cudaErrorInvalidValue;  // smem / scratch table bound
   switch (args.dtype) {
-    case 7: return run_adasum<float>(cp, args, prescale, postscale, stream);
-    case 6: return run_adasum<__half>(cp, args, prescale, postscale, stream);
-    case 10: return run_adasum<__nv_bfloat16>(cp, args, prescale, postscale, stream);
+    case 7: return run_adasum<float>(cp, args, prescale, postscale, stream, only);
+    case 6: return run_adasum<__half>(cp, args, prescale, postscale, stream, only);
+    case 10: return run_adasum<__nv_bfloat16>(cp, args, prescale, postscale, stream, only);
     default: return cudaErrorInvalidValue;
   }
 }

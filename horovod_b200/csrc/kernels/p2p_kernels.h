@@ -127,6 +127,10 @@ struct AdasumArgs {
 constexpr int64_t kAdasumScratchStride = 30000;
 constexpr int kAdasumMaxTensors = 1250;
 cudaError_t LaunchAdasum(const CommParams& cp, const AdasumArgs& args, double prescale, double postscale, cudaStream_t stream);
+// Single-GPU simulation support: launch only step `only` of the sequence (see adasum_kernels.cu); -1 = all.
+cudaError_t LaunchAdasumStep(const CommParams& cp, const AdasumArgs& args, double prescale, double postscale, cudaStream_t stream,
+                             int only);
+int AdasumNumLaunches(int nranks);
 
 // Fused multi-tensor optimizer updates (see optim_kernels.cu)
 struct SgdTensor { void* param; const void* grad; void* momentum; int64_t count; };

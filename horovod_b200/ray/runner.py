@@ -23,11 +23,15 @@ class _Settings:
 class RayBackend(ActorBackend):
     """Ray actors inside one placement group.  `bundles` is one resource dict per worker."""
 
-    def __init__(self, bundles, strategy='PACK', pg_timeout_s=100, use_current_placement_group=True):
+    def __init__(self, bundles, strategy='PACK', pg_timeout_s=100, use_current_placement_group=True, worker_bundle=None,
+                 worker_resources=None):
         import ray
         from ray.util.placement_group import get_current_placement_group, placement_group
         self.ray = ray
         self.bundles = bundles
+        # worker i runs inside bundle worker_bundle[i] with worker_resources[i] (default: one bundle per worker)
+        self.worker_bundle = worker_bundle or list(range(len(bundles)))
+        self.worker_resources = worker_resources or [bundles[b] for b in self.worker_bundle]
         self.pg, self._own_pg = None, False
         if use_current_placement_group:
             self.pg = get_current_placement_group()
@@ -43,9 +47,10 @@ class RayBackend(ActorBackend):
 
     def create(self, index, env=None):
         from ray.util.scheduling_strategies import PlacementGroupSchedulingStrategy
-        b = self.bundles[index]
+        b = self.worker_resources[index]
         opts = dict(num_cpus=b.get('CPU', 1), num_gpus=b.get('GPU', 0),
-                    scheduling_strategy=PlacementGroupSchedulingStrategy(placement_group=self.pg, placement_group_bundle_index=index))
+                    scheduling_strategy=PlacementGroupSchedulingStrategy(placement_group=self.pg,
+                                                                         placement_group_bundle_index=self.worker_bundle[index]))
         actor = self._remote_cls.options(**opts).remote(index)
         if env:
             self.ray.get(actor.update_env.remote(env))
@@ -99,15 +104,23 @@ class RayExecutor:
         self.env_vars = dict(env_vars or {})
         self._backend, self.job = backend, None
 
-    def _bundles(self):
-        return [{'CPU': self.cpus_per_worker, **({'GPU': self.gpus_per_worker} if self.use_gpu else {})} for _ in range(self.num_workers)]
+    def _placement(self):
+        """(bundles, strategy, worker -> bundle index, per-worker resources)"""
+        from horovod_b200.ray import strategy
+        per_worker = {'CPU': self.cpus_per_worker, **({'GPU': self.gpus_per_worker} if self.use_gpu else {})}
+        if self.colocated:
+            bundles, strat = strategy.colocated_bundles(self.num_hosts, self.num_workers_per_host, self.cpus_per_worker, self.gpus_per_worker)
+            return bundles, strat, [i // self.num_workers_per_host for i in range(self.num_workers)], [per_worker] * self.num_workers
+        bundles, strat = strategy.pack_bundles(self.num_workers, self.cpus_per_worker, self.gpus_per_worker)
+        return bundles, strat, list(range(self.num_workers)), [per_worker] * self.num_workers
 
     def start(self, executable_cls=None, executable_args=None, executable_kwargs=None, extra_env_vars=None):
         """Creates the workers, assigns ranks and (optionally) instantiates `executable_cls` on each of them."""
         backend = self._backend
         if backend is None:
-            backend = RayBackend(self._bundles(), 'STRICT_SPREAD' if self.colocated and self.num_workers_per_host == 1 else 'PACK',
-                                 self.settings.placement_group_timeout_s, self.use_current_placement_group)
+            bundles, strat, worker_bundle, worker_res = self._placement()
+            backend = RayBackend(bundles, strat, self.settings.placement_group_timeout_s, self.use_current_placement_group,
+                                 worker_bundle, worker_res)
             self._backend = backend
         env = dict(self.env_vars)
         env.update(extra_env_vars or {})

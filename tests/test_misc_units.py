@@ -39,16 +39,23 @@ def test_async_loader_epochs_and_errors():
 
 
 def test_ray_rank_assignment_and_discovery():
-    envs = strategy.assign_ranks(['a', 'b', 'a', 'b', 'b'])
+    from horovod_b200.runner.cluster_job import assign_slots
+    from horovod_b200.runner.mesh_run import create_slot_env_vars
+    envs = [create_slot_env_vars(s) for s in assign_slots(['a', 'b', 'a', 'b', 'b'])]
     assert [e['HOROVOD_RANK'] for e in envs] == ['0', '2', '1', '3', '4']
     assert envs[4]['HOROVOD_LOCAL_RANK'] == '2' and envs[4]['HOROVOD_CROSS_SIZE'] == '1' and envs[4]['HOROVOD_CROSS_RANK'] == '0'
     assert envs[1]['HOROVOD_CROSS_RANK'] == '1' and envs[0]['HOROVOD_LOCAL_SIZE'] == '2'
+    assert strategy.pack_bundles(3, 2) == ([{'CPU': 2}] * 3, 'PACK')
+    from horovod_b200.ray import RayExecutor
+    ex = RayExecutor(RayExecutor.create_settings(), num_hosts=2, num_workers_per_host=4, cpus_per_worker=2, use_gpu=True)
+    b, st, wb, wr = ex._placement()
+    assert b == [{'CPU': 8, 'GPU': 4}] * 2 and st == 'STRICT_SPREAD' and wb == [0, 0, 0, 0, 1, 1, 1, 1] and wr[0] == {'CPU': 2, 'GPU': 1}
     bundles, strat = strategy.colocated_bundles(2, 4, cpus_per_worker=2, gpus_per_worker=1)
     assert bundles == [{'CPU': 8, 'GPU': 4}] * 2 and strat == 'STRICT_SPREAD'
     nodes = [{'alive': True, 'NodeManagerAddress': 'n1', 'Resources': {'CPU': 16, 'GPU': 8}},
              {'alive': True, 'NodeManagerAddress': 'n2', 'Resources': {'CPU': 4}},
              {'alive': False, 'NodeManagerAddress': 'n3', 'Resources': {'CPU': 64, 'GPU': 8}}]
-    d = RayHostDiscovery(use_gpu=True, cpus_per_worker=2, gpus_per_worker=1, nodes_fn=lambda: nodes)
+    d = RayHostDiscovery(use_gpu=True, cpus_per_slot=2, gpus_per_slot=1, nodes_fn=lambda: nodes)
     assert d.find_available_hosts_and_slots() == {'n1': 8}
     assert RayHostDiscovery(nodes_fn=lambda: nodes).find_available_hosts_and_slots() == {'n1': 16, 'n2': 4}
 
@@ -60,5 +67,6 @@ def test_local_store(tmp_path):
     s.write(ck, b'abc')
     assert s.exists(ck) and s.read(ck) == b'abc'
     assert s.get_logs_path('run1').endswith('runs/run1/logs') and s.get_train_data_path(3).endswith('intermediate_train_data.3')
-    with pytest.raises(ImportError):
-        Store.create('hdfs://x/y')
+    from horovod_b200.spark.common.store import FilesystemStore
+    remote = Store.create('hdfs://namenode:8020/x/y')  # lazily bound pyarrow.fs filesystem
+    assert type(remote) is FilesystemStore and remote.get_run_path('r') == 'hdfs://namenode:8020/x/y/runs/r'
