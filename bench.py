@@ -35,6 +35,7 @@ def parse():
     p.add_argument('--no-fused-optimizer', action='store_true')
     p.add_argument('--op', default='average', choices=['average', 'adasum'])
     p.add_argument('--fp32', action='store_true', help='disable bf16 autocast')
+    p.add_argument('--no-cuda-graph', action='store_true', help='eager forward/backward with gradient hooks instead of hvd.GraphedStep')
     p.add_argument('--sizes', default=None, help='allreduce sweep: comma separated byte sizes')
     p.add_argument('--dtype', default='fp32', help='allreduce sweep dtype: fp32|bf16|fp16')
     return p.parse_args()
@@ -187,13 +188,16 @@ def train_bench(args):
     host_batch = tuple(t.cpu().pin_memory() for t in dev_batch)  # the e2e arm copies this every step
     h2d_bytes = sum(t.numel() * t.element_size() for t in host_batch)
 
-    def one_step(batch):
-        opt.zero_grad(set_to_none=False)
+    def fwd(*batch):
         with torch.autocast('cuda', dtype=torch.bfloat16, enabled=use_bf16):
-            loss = step_fn(batch)
-        loss.backward()
-        opt.step()
-        return loss
+            return step_fn(batch)
+
+    # forward + backward replayed as one CUDA graph; step() then reduces the gradient buckets and applies the fused update
+    # (hvd.GraphedStep falls back to the eager hook-driven step if capture is impossible, e.g. for the Adasum optimizer)
+    graphed = hvd.GraphedStep(fwd, opt, dev_batch, enabled=not args.no_cuda_graph)
+
+    def one_step(batch):
+        return graphed(*batch)
 
     def timed(nsteps, e2e):
         hvd.barrier()
@@ -204,8 +208,10 @@ def train_bench(args):
         last = None
         for _ in range(nsteps):
             if e2e:
-                batch = tuple(t.cuda(non_blocking=True) for t in host_batch)
-                last = one_step(batch).item()  # device -> host read of the step's result
+                # host -> device copy of this step's inputs from pinned memory (straight into the graph's static inputs when
+                # the step is graphed), then a device -> host read of the step's result
+                batch = host_batch if graphed.captured else tuple(t.cuda(non_blocking=True) for t in host_batch)
+                last = one_step(batch).item()
             else:
                 last = one_step(dev_batch)
         e1.record()
@@ -228,7 +234,7 @@ def train_bench(args):
     clocks = sampler.stop() if sampler else None
     # end-to-end arm: H2D of the inputs from pinned memory + D2H read of the loss inside the timed region
     for _ in range(2):
-        one_step(tuple(t.cuda(non_blocking=True) for t in host_batch)).item()
+        one_step(host_batch if graphed.captured else tuple(t.cuda(non_blocking=True) for t in host_batch)).item()
     e2e_ms, _, last_loss = timed(args.steps, e2e=True)
 
     global_batch = bs * size
@@ -244,6 +250,7 @@ def train_bench(args):
             'config': {'model': args.model, 'global_batch': global_batch, 'per_gpu_batch': bs, 'seq_len': seq,
                        'parallelism': f'dp{size}', 'optimizer': 'SGD(momentum=0.9)' if args.model == 'resnet50' else 'AdamW',
                        'fused_optimizer': not args.no_fused_optimizer, 'grad_dtype': 'fp32',
+                       'cuda_graph': bool(graphed.captured), 'cuda_graph_fallback': graphed.fallback_reason,
                        'l2': 'per-step working set (activations + 100+ MB of gradients) exceeds the 126 MB L2; no explicit flush',
                        'gpu_backend': hvd.gpu_backend_info(), 'tunables': hvd.tunable_params()},
             'clocks': clocks,

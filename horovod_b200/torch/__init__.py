@@ -21,4 +21,5 @@ from horovod_b200.torch.functions import (broadcast_parameters, broadcast_optimi
                                           allgather_object)
 from horovod_b200.torch.optimizer import DistributedOptimizer  # noqa: F401
 from horovod_b200.torch.sync_batch_norm import SyncBatchNorm  # noqa: F401
+from horovod_b200.torch.graph import GraphedStep  # noqa: F401
 from horovod_b200.torch import elastic  # noqa: F401

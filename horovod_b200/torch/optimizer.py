@@ -60,6 +60,7 @@ class _DistributedOptimizer(torch.optim.Optimizer):
         self.process_set = process_set
         self._fused = fused
         self._fused_steps = 0
+        self._graph_mode = False  # set by hvd.GraphedStep: backward runs as a CUDA graph replay, hooks do not fire
 
         self._handles = {}
         self._grad_accs = []
@@ -254,6 +255,8 @@ class _DistributedOptimizer(torch.optim.Optimizer):
 
     def _make_hook(self, p):
         def hook(*ignore):
+            if self._graph_mode:
+                return  # (only runs while the graph is being captured) step() reduces every gradient after the replay
             if p in self._handles and self._handles[p][0] is not None:
                 if self._allreduce_delay[p] <= 0:
                     raise AssertionError(
@@ -297,6 +300,9 @@ class _DistributedOptimizer(torch.optim.Optimizer):
         ranks stay in lock-step) and writes the reduced gradients back."""
         if not self.process_set.included():
             self._synchronized = True
+            return
+        if self._graph_mode and self.process_set.size() == 1 and self.op in (Average, Sum):
+            self._synchronized = True  # one rank: the reduction is the identity (prescale * postscale == 1)
             return
         if self._zero_copy:
             for bucket in self._buckets:
@@ -385,8 +391,14 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             for group in self.param_groups:
                 for p in group['params']:
                     if p not in self._p_to_bucket and p.grad is not None:
-                        p.grad = None
+                        if self._graph_mode:
+                            p.grad.zero_()  # addresses baked into the captured graph must stay valid
+                        else:
+                            p.grad = None
             return None
+        if self._graph_mode:
+            kwargs['set_to_none'] = False
+            args = ()
         return super(self.__class__, self).zero_grad(*args, **kwargs)
 
 

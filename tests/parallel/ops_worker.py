@@ -428,6 +428,35 @@ def _():
                     assert torch.allclose(v, ref)
 
 
+@check('graphed_step')
+def _():
+    # hvd.GraphedStep on every rank: replayed forward/backward, reduction of all gradients in step(); the trajectory must
+    # equal single-process training on the concatenated global batch
+    if args.device != 'cuda':
+        return
+    def make():
+        torch.manual_seed(11)
+        return torch.nn.Sequential(torch.nn.Linear(16, 64), torch.nn.GELU(), torch.nn.Linear(64, 8)).to(DEV)
+    model, ref_model = make(), make()
+    hvd.broadcast_parameters(model.state_dict(), root_rank=0)
+    ref_model.load_state_dict(model.state_dict())
+    for fused in (True,):
+        opt = hvd.DistributedOptimizer(torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9),
+                                       named_parameters=model.named_parameters(), fused=fused)
+        ref_opt = torch.optim.SGD(ref_model.parameters(), lr=0.05, momentum=0.9)
+        data = lambda step, r: (torch.randn(8, 16, generator=torch.Generator().manual_seed(50 * step + r)).to(DEV),
+                                torch.randn(8, 8, generator=torch.Generator().manual_seed(70 * step + r)).to(DEV))
+        gs = hvd.GraphedStep(lambda x, y: torch.nn.functional.mse_loss(model(x), y), opt, data(0, rank))
+        assert gs.captured, gs.fallback_reason
+        for step in range(5):
+            gs(*data(step, rank))
+            ref_opt.zero_grad()
+            (sum(torch.nn.functional.mse_loss(ref_model(*data(step, r)[:1]), data(step, r)[1]) for r in range(size)) / size).backward()
+            ref_opt.step()
+        for a, b in zip(model.parameters(), ref_model.parameters()):
+            torch.testing.assert_close(a, b, rtol=2e-4, atol=2e-5)
+
+
 @check('optimizer')
 def _():
     torch.manual_seed(0)

@@ -24,7 +24,7 @@ def test_ops_matrix_p2p(native_built):
 def test_ops_matrix_variants(native_built):
     for variant in ("oneshot", "twoshot"):
         rc, out = run_parallel("ops_worker.py", np=2, timeout=300, env={"HVD_ALLREDUCE_VARIANT": variant},
-                               args=["--device", "cuda", "--only", "allreduce_sum_avg,allreduce_async_fused,allreduce_mixed_dtype_fusion,optimizer"])
+                               args=["--device", "cuda", "--only", "allreduce_sum_avg,allreduce_async_fused,allreduce_mixed_dtype_fusion,optimizer,graphed_step"])
         assert "ALL OK" in out, (variant, out[-3000:])
 
 

@@ -64,6 +64,44 @@ def test_fused_optimizer_matches_torch(hvd, opt_name):
     assert hvd.runtime_stats()['kernel_launches'] > before
 
 
+def _small_cnn():
+    torch.manual_seed(3)
+    return torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.BatchNorm2d(8), torch.nn.ReLU(),
+                               torch.nn.AdaptiveAvgPool2d(1), torch.nn.Flatten(), torch.nn.Linear(8, 5)).cuda()
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_graphed_step_matches_eager(hvd, fused):
+    """hvd.GraphedStep (forward+backward as one CUDA graph replay, reduction + update after it) follows the same
+    trajectory as the eager hook-driven step."""
+    xs = [torch.randn(16, 3, 12, 12, device='cuda') for _ in range(6)]
+    ys = [torch.randint(0, 5, (16,), device='cuda') for _ in range(6)]
+    ref = _small_cnn()
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.9)
+    for x, y in zip(xs, ys):
+        ropt.zero_grad()
+        torch.nn.functional.cross_entropy(ref(x), y).backward()
+        ropt.step()
+    model = _small_cnn()
+    opt = hvd.DistributedOptimizer(torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9), named_parameters=model.named_parameters(),
+                                   fused=fused)
+    bn_before = model[1].running_mean.clone()
+    step = hvd.GraphedStep(lambda x, y: torch.nn.functional.cross_entropy(model(x), y), opt, (xs[0], ys[0]), warmup_iters=2)
+    assert step.captured, step.fallback_reason
+    # the capture warm-up ran forward passes (BatchNorm statistics moved) but applied no update; realign the BN buffers
+    model[1].running_mean.copy_(bn_before)
+    model[1].running_var.fill_(1.0)
+    model[1].num_batches_tracked.zero_()
+    losses = [step(x, y).item() for x, y in zip(xs, ys)]
+    assert step.replays == 6 and all(l == l for l in losses)
+    for (n, a), (_, b) in zip(model.named_parameters(), ref.named_parameters()):
+        torch.testing.assert_close(a, b, rtol=2e-4, atol=2e-5, msg=lambda m, n=n: f'{n}: {m}')
+    torch.testing.assert_close(model[1].running_mean, ref[1].running_mean, rtol=1e-4, atol=1e-5)
+    # eager fallback keeps working on the same object type
+    eager = hvd.GraphedStep(lambda x, y: torch.nn.functional.cross_entropy(model(x), y), opt, (xs[0], ys[0]), enabled=False)
+    assert not eager.captured and eager.fallback_reason == 'disabled'
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()
