@@ -80,13 +80,27 @@ template <typename W, int NW> __device__ __forceinline__ uint4 pack_vec(const ty
 // in range, guarded scalar path with zero fill otherwise) into accumulators.
 template <typename T, int N, typename A> __device__ __forceinline__ void load_elems(const T* p, int64_t remaining, A* a) {
   constexpr int kBytes = N * (int)sizeof(T);
-  if (remaining >= N && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+  static_assert(kBytes >= 16 ? kBytes % 16 == 0 : (kBytes == 8 || kBytes == 4), "unsupported vector width");
+  constexpr int kAlign = kBytes >= 16 ? 16 : kBytes;
+  if (remaining >= N && ((reinterpret_cast<uintptr_t>(p) & (kAlign - 1)) == 0)) {
+    if constexpr (kBytes >= 16) {
 #pragma unroll
-    for (int k = 0; k < kBytes / 16; ++k) {
-      uint4 v = ld_stream(reinterpret_cast<const char*>(p) + 16 * k);
+      for (int k = 0; k < kBytes / 16; ++k) {
+        uint4 v = ld_stream(reinterpret_cast<const char*>(p) + 16 * k);
+        const T* q = reinterpret_cast<const T*>(&v);
+#pragma unroll
+        for (int i = 0; i < 16 / (int)sizeof(T); ++i) a[k * (16 / (int)sizeof(T)) + i] = (A)Traits<T>::to_acc(q[i]);
+      }
+    } else if constexpr (kBytes == 8) {  // e.g. 4 x bf16 feeding an fp32 wire vector (Adasum pack)
+      const uint2 v = *reinterpret_cast<const uint2*>(p);
       const T* q = reinterpret_cast<const T*>(&v);
 #pragma unroll
-      for (int i = 0; i < 16 / (int)sizeof(T); ++i) a[k * (16 / (int)sizeof(T)) + i] = (A)Traits<T>::to_acc(q[i]);
+      for (int i = 0; i < N; ++i) a[i] = (A)Traits<T>::to_acc(q[i]);
+    } else {
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(p);
+      const T* q = reinterpret_cast<const T*>(&v);
+#pragma unroll
+      for (int i = 0; i < N; ++i) a[i] = (A)Traits<T>::to_acc(q[i]);
     }
   } else {
 #pragma unroll
@@ -95,14 +109,30 @@ template <typename T, int N, typename A> __device__ __forceinline__ void load_el
 }
 template <typename T, int N, typename A> __device__ __forceinline__ void store_elems(T* p, int64_t remaining, const A* a) {
   constexpr int kBytes = N * (int)sizeof(T);
-  if (remaining >= N && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+  static_assert(kBytes >= 16 ? kBytes % 16 == 0 : (kBytes == 8 || kBytes == 4), "unsupported vector width");
+  constexpr int kAlign = kBytes >= 16 ? 16 : kBytes;
+  if (remaining >= N && ((reinterpret_cast<uintptr_t>(p) & (kAlign - 1)) == 0)) {
+    if constexpr (kBytes >= 16) {
 #pragma unroll
-    for (int k = 0; k < kBytes / 16; ++k) {
-      uint4 v;
+      for (int k = 0; k < kBytes / 16; ++k) {
+        uint4 v;
+        T* q = reinterpret_cast<T*>(&v);
+#pragma unroll
+        for (int i = 0; i < 16 / (int)sizeof(T); ++i) q[i] = Traits<T>::from_acc((typename Traits<T>::Acc)a[k * (16 / (int)sizeof(T)) + i]);
+        st_stream(reinterpret_cast<char*>(p) + 16 * k, v);
+      }
+    } else if constexpr (kBytes == 8) {
+      uint2 v;
       T* q = reinterpret_cast<T*>(&v);
 #pragma unroll
-      for (int i = 0; i < 16 / (int)sizeof(T); ++i) q[i] = Traits<T>::from_acc((typename Traits<T>::Acc)a[k * (16 / (int)sizeof(T)) + i]);
-      st_stream(reinterpret_cast<char*>(p) + 16 * k, v);
+      for (int i = 0; i < N; ++i) q[i] = Traits<T>::from_acc((typename Traits<T>::Acc)a[i]);
+      *reinterpret_cast<uint2*>(p) = v;
+    } else {
+      uint32_t v;
+      T* q = reinterpret_cast<T*>(&v);
+#pragma unroll
+      for (int i = 0; i < N; ++i) q[i] = Traits<T>::from_acc((typename Traits<T>::Acc)a[i]);
+      *reinterpret_cast<uint32_t*>(p) = v;
     }
   } else {
 #pragma unroll
