@@ -162,6 +162,7 @@ def build_model(args, torch):
 def train_bench(args):
     import torch
     import horovod_b200.torch as hvd
+    from horovod_b200.data import DevicePrefetcher
 
     hvd.init()
     rank, size = hvd.rank(), hvd.size()
@@ -178,8 +179,10 @@ def train_bench(args):
     else:
         base_opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01)
     op = hvd.Average if args.op == 'average' else hvd.Adasum
+    # graphed step: no backward/allreduce overlap to preserve, so fewer, larger buckets (fewer launches and host round trips)
     opt = hvd.DistributedOptimizer(base_opt, named_parameters=model.named_parameters(), op=op,
-                                   fused=not args.no_fused_optimizer)
+                                   fused=not args.no_fused_optimizer, **({} if op != hvd.Average else
+                                                                         {'bucket_cap_mb': 32 if args.no_cuda_graph else 256}))
     hvd.broadcast_parameters(model.state_dict(), root_rank=0)
     hvd.broadcast_optimizer_state(opt, root_rank=0)
     model.train()
@@ -206,13 +209,22 @@ def train_bench(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         last = None
-        for _ in range(nsteps):
-            if e2e:
-                # host -> device copy of this step's inputs from pinned memory (straight into the graph's static inputs when
-                # the step is graphed), then a device -> host read of the step's result
-                batch = host_batch if graphed.captured else tuple(t.cuda(non_blocking=True) for t in host_batch)
+        if e2e:
+            # every step: host -> device copy of that step's inputs from pinned memory on the prefetcher's copy stream (the
+            # copy of step i+1 overlaps the compute of step i), then a device -> host read of the step's loss
+            class _Loader:
+                def __len__(self):
+                    return nsteps
+
+                def __iter__(self):
+                    for _ in range(nsteps):
+                        yield host_batch
+            pf = DevicePrefetcher(_Loader(), device=f'cuda:{local_rank}', depth=2)
+            for batch in pf:
                 last = one_step(batch).item()
-            else:
+            assert pf.h2d_bytes == h2d_bytes * nsteps
+        else:
+            for _ in range(nsteps):
                 last = one_step(dev_batch)
         e1.record()
         torch.cuda.synchronize()
@@ -234,7 +246,7 @@ def train_bench(args):
     clocks = sampler.stop() if sampler else None
     # end-to-end arm: H2D of the inputs from pinned memory + D2H read of the loss inside the timed region
     for _ in range(2):
-        one_step(host_batch if graphed.captured else tuple(t.cuda(non_blocking=True) for t in host_batch)).item()
+        one_step(tuple(t.cuda(non_blocking=True) for t in host_batch)).item()
     e2e_ms, _, last_loss = timed(args.steps, e2e=True)
 
     global_batch = bs * size
