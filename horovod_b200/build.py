@@ -149,9 +149,48 @@ def clean():
     shutil.rmtree(OUT, ignore_errors=True)
 
 
+def build_tsan_selftest(force=False):
+    """ThreadSanitizer build of the C++ runtime + its native self-test (N engines in one process over the loopback
+    transport: controller, response cache, fusion, CPU ops, process sets, join, error paths) as a stand-alone executable.
+    The sm_100a kernel objects are linked as they are (device code is not instrumented).  The reference has no sanitizer
+    build at all."""
+    build_core()
+    odir = os.path.join(os.path.dirname(OBJ), "obj_tsan")
+    os.makedirs(odir, exist_ok=True)
+    hstamp = _header_digest()
+    cc, _ = _sources()
+    main = os.path.join(odir, "selftest_main.cc")
+    with open(main, "w") as f:
+        f.write('#include <cstdio>\nextern "C" int hvd_selftest(int nranks, char* log, int log_len);\n'
+                'int main() { static char log[1 << 16]; int rc = hvd_selftest(4, log, sizeof log); std::fputs(log, stdout); return rc; }\n')
+    inc = ["-I" + os.path.join(CUDA_HOME, "include")]
+
+    def one(src):
+        rel = os.path.relpath(src, CSRC).replace("/", "__") if src.startswith(CSRC) else os.path.basename(src)
+        obj = os.path.join(odir, rel + ".o")
+        stamp = _src_stamp(src, hstamp + "tsan")
+        if force or _needs(src, obj, stamp):
+            _run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-fPIC", "-pthread"] + inc + ["-c", src, "-o", obj])
+            for f in os.listdir(odir):
+                if f.startswith(rel + ".o.") and f != rel + ".o." + stamp:
+                    os.remove(os.path.join(odir, f))
+            open(obj + "." + stamp, "w").close()
+        return obj
+    with ThreadPoolExecutor(max_workers=max(2, os.cpu_count() or 4)) as ex:
+        objs = list(ex.map(one, cc + [main]))
+    kernels = [os.path.join(OBJ, f) for f in sorted(os.listdir(OBJ)) if f.startswith("kernels__") and f.endswith(".o")]
+    exe = os.path.join(os.path.dirname(OBJ), "selftest_tsan")
+    _run(["g++", "-fsanitize=thread", "-pthread"] + objs + kernels + ["-o", exe, "-L" + os.path.join(CUDA_HOME, "lib64"),
+                                                                      "-lcudart_static", "-ldl", "-lrt", "-lpthread"])
+    return exe
+
+
 if __name__ == "__main__":
     if "--clean" in sys.argv:
         clean()
+    if "--tsan" in sys.argv:
+        print("built", build_tsan_selftest(force="--force" in sys.argv))
+        sys.exit(0)
     libs = build_all(force="--force" in sys.argv, verbose="-v" in sys.argv, with_torch="--no-torch" not in sys.argv)
     for l in libs:
         print("built", l)

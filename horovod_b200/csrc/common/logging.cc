@@ -10,7 +10,7 @@ namespace hvd {
 namespace {
 std::atomic<int> g_level{-1};
 std::atomic<int> g_rank{-1};
-bool g_hide_time = false;
+std::atomic<bool> g_hide_time{false};
 
 LogLevel ParseLevel(const char* s) {
   if (!s) return LogLevel::WARNING;

@@ -28,6 +28,7 @@ int64_t Align128(int64_t b) { return (b + 127) / 128 * 128; }
 GpuContext& GpuContext::Get() { static GpuContext c; return c; }
 
 int GpuContext::DeviceCount() {
+  std::lock_guard<std::mutex> l(mu_);  // several engines may live in one process (native self-test)
   if (count_ == -2) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }

@@ -1,0 +1,39 @@
+"""Sanitizer jobs (the reference has none).
+
+* ThreadSanitizer build of the C++ runtime running the native self-test (4 engines in one process) — CPU.
+* compute-sanitizer memcheck over the P2P kernels in the single-GPU simulation — GPU.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+from conftest import REPO
+
+
+def test_native_selftest_under_thread_sanitizer():
+    if shutil.which('g++') is None:
+        pytest.skip('no g++')
+    from horovod_b200 import build
+    exe = build.build_tsan_selftest()
+    env = dict(os.environ, TSAN_OPTIONS='halt_on_error=0 report_signal_unsafe=0 exitcode=66', HOROVOD_LOG_LEVEL='error')
+    p = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=600)
+    err = p.stderr.decode(errors='replace')
+    if 'FATAL: ThreadSanitizer' in err and 'unexpected memory mapping' in err:
+        pytest.skip('ThreadSanitizer cannot run in this container (ASLR / memory layout)')
+    assert 'WARNING: ThreadSanitizer' not in err, err[-6000:]
+    assert p.returncode == 0, (p.returncode, p.stdout.decode()[-2000:], err[-2000:])
+
+
+@pytest.mark.gpu
+def test_p2p_kernels_under_compute_sanitizer_memcheck():
+    cs = shutil.which('compute-sanitizer') or '/usr/local/cuda/bin/compute-sanitizer'
+    if not os.path.exists(cs):
+        pytest.skip('compute-sanitizer not installed')
+    script = os.path.join(REPO, 'tests', 'sanitizer_target.py')
+    p = subprocess.run([cs, '--tool', 'memcheck', '--error-exitcode', '77', '--launch-timeout', '0', sys.executable, script],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600, env=dict(os.environ, PYTHONPATH=REPO))
+    out = p.stdout.decode(errors='replace')
+    assert p.returncode == 0 and 'SANITIZER TARGET OK' in out and 'ERROR SUMMARY: 0 errors' in out, out[-5000:]
