@@ -33,7 +33,7 @@ class GraphedStep:
         elif not (torch.cuda.is_available() and all(t.is_cuda for t in example_inputs)):
             self.fallback_reason = 'inputs are not CUDA tensors'
         elif not hasattr(optimizer, '_graph_mode'):
-            self.fallback_reason = 'optimizer is not a (non-Adasum) hvd.DistributedOptimizer'
+            self.fallback_reason = 'optimizer is not an hvd.DistributedOptimizer'
         else:
             try:
                 self._capture(warmup_iters)

@@ -501,6 +501,7 @@ class _DistributedAdasumOptimizer(torch.optim.Optimizer):
         self._synchronized = False
         self._should_synchronize = True
         self._starting_models = {p: torch.zeros_like(p, requires_grad=False) for _, p in named_parameters}
+        self._graph_mode = False  # hvd.GraphedStep: hooks are silent, step() runs the whole-model variant below
         self._register_hooks()
 
     def set_backward_passes_per_step(self, passes):
@@ -539,6 +540,8 @@ class _DistributedAdasumOptimizer(torch.optim.Optimizer):
 
     def _make_hook(self, p):
         def hook(*ignore):
+            if self._graph_mode:
+                return
             if p in self._handles and self._handles[p][0] is not None:
                 if self._allreduce_delay[p] <= 0:
                     raise AssertionError(
@@ -553,6 +556,31 @@ class _DistributedAdasumOptimizer(torch.optim.Optimizer):
             self._handles[p] = (handle, ctx)
         return hook
 
+    def _whole_model_step(self):
+        """Same math as the per-parameter hooks, issued once for the whole model (graph mode: backward was a CUDA graph
+        replay, so there is nothing to overlap with): stash, ONE wrapped-optimizer step over all parameters, delta =
+        new - start, Adasum-allreduce every delta (the engine fuses them up to the fusion threshold), start + result."""
+        ps = sorted(self._requires_update, key=lambda p: self._parameter_names.get(p))
+        for p in ps:
+            if p.grad is None:
+                p.grad = torch.zeros_like(p.data)
+        starts = [self._starting_models[p] for p in ps]
+        datas = [p.data for p in ps]
+        with torch.no_grad():
+            torch._foreach_copy_(starts, datas)
+            super(self.__class__, self).step()
+            torch._foreach_sub_(datas, starts)
+            handles = []
+            for p in ps:
+                comp, ctx = self._compression.compress(p.data)
+                handles.append((allreduce_async_(comp, name=self._parameter_names.get(p), op=Adasum), ctx, p))
+            for h, ctx, p in handles:
+                delta = self._compression.decompress(synchronize(h), ctx)
+                if delta is not p.data:
+                    p.data.copy_(delta)
+            torch._foreach_add_(starts, datas)
+            torch._foreach_copy_(datas, starts)
+
     def synchronize(self):
         pass
 
@@ -564,6 +592,9 @@ class _DistributedAdasumOptimizer(torch.optim.Optimizer):
         loss = None
         if closure is not None:
             loss = closure()
+        if self._graph_mode:
+            self._whole_model_step()
+            return loss
         missing_p = self._requires_update - set(self._handles.keys())
         for p in missing_p:
             self._allreduce_delay[p] = 0

@@ -578,6 +578,29 @@ def _():
         torch.testing.assert_close(hvd.synchronize(h), torch.full((16,), float(i + 1), device=DEV), rtol=1e-4, atol=1e-4)
 
 
+@check('adasum_whole_model')
+def _():
+    # graph-mode Adasum optimizer (one wrapped-optimizer step for the whole model, then all deltas) == per-parameter hooks
+    if size & (size - 1):
+        return
+    def make():
+        torch.manual_seed(5)
+        return torch.nn.Sequential(torch.nn.Linear(6, 12), torch.nn.Tanh(), torch.nn.Linear(12, 3)).to(DEV)
+    ma, mb = make(), make()
+    oa = hvd.DistributedOptimizer(torch.optim.SGD(ma.parameters(), lr=0.1, momentum=0.9), named_parameters=ma.named_parameters(), op=hvd.Adasum)
+    ob = hvd.DistributedOptimizer(torch.optim.SGD(mb.parameters(), lr=0.1, momentum=0.9), named_parameters=mb.named_parameters(), op=hvd.Adasum)
+    ob._graph_mode = True
+    for step in range(3):
+        x = torch.randn(5, 6, generator=torch.Generator().manual_seed(10 * step + rank)).to(DEV)
+        y = torch.randn(5, 3, generator=torch.Generator().manual_seed(77 * step + rank)).to(DEV)
+        for m, o in ((ma, oa), (mb, ob)):
+            o.zero_grad()
+            torch.nn.functional.mse_loss(m(x), y).backward()
+            o.step()
+    for a, b in zip(ma.parameters(), mb.parameters()):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
+
+
 @check('symm_zero_copy')
 def _():
     """Registered symmetric tensors: in-place allreduce through the zero-copy kernel (and the packed path when small)."""
