@@ -164,6 +164,9 @@ def train_bench(args):
     import horovod_b200.torch as hvd
     from horovod_b200.data import DevicePrefetcher
 
+    if args.op == 'adasum':
+        # the GPU Adasum kernels work inside the symmetric buffer: make it hold the largest single delta (GPT-2's 206 MB wte)
+        os.environ.setdefault('HVD_SYMM_BUFFER_BYTES', str(256 << 20))
     hvd.init()
     rank, size = hvd.rank(), hvd.size()
     local_rank = hvd.local_rank()

@@ -556,6 +556,9 @@ class _DistributedAdasumOptimizer(torch.optim.Optimizer):
             self._handles[p] = (handle, ctx)
         return hook
 
+    def _hvd_super_step(self, closure=None):
+        return super(self.__class__, self).step(closure)
+
     def _whole_model_step(self):
         """Same math as the per-parameter hooks, issued once for the whole model (graph mode: backward was a CUDA graph
         replay, so there is nothing to overlap with): stash, ONE wrapped-optimizer step over all parameters, delta =
