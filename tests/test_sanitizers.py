@@ -28,6 +28,8 @@ def test_native_selftest_under_thread_sanitizer():
 
 
 @pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get('HVD_RUN_COMPUTE_SANITIZER', '0') != '1',
+                    reason='opt-in (HVD_RUN_COMPUTE_SANITIZER=1): memcheck instruments every kernel of the process, minutes per run')
 def test_p2p_kernels_under_compute_sanitizer_memcheck():
     cs = shutil.which('compute-sanitizer') or '/usr/local/cuda/bin/compute-sanitizer'
     if not os.path.exists(cs):
