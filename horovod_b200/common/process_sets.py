@@ -89,6 +89,15 @@ def is_process_set_included(process_set_id: int) -> bool:
     return _basics._process_set_included(process_set_id)
 
 
+def _reset_unnamed_op_numbering(ps_id):
+    """Ids are recycled; unnamed ops of a new set must be numbered from zero on every member."""
+    try:
+        from horovod_b200.torch.mpi_ops import _native
+        _native().reset_noname_counters(int(ps_id))
+    except Exception:  # binding not loaded (front end without torch ops in use)
+        pass
+
+
 def add_process_set(process_set: Union[ProcessSet, Sequence[int]]) -> ProcessSet:
     """Collective: every rank must call it with the same ranks. Returns the registered ProcessSet."""
     from horovod_b200.torch.mpi_ops import _basics
@@ -97,6 +106,7 @@ def add_process_set(process_set: Union[ProcessSet, Sequence[int]]) -> ProcessSet
     if process_set.process_set_id is not None:
         raise ValueError("Attempted to register an already registered process set: " + str(process_set))
     ps_id = _basics._add_process_set_impl(process_set.ranks)
+    _reset_unnamed_op_numbering(ps_id)
     process_set._attach(ps_id)
     _id_to_process_sets[ps_id] = process_set
     return process_set
@@ -109,6 +119,7 @@ def remove_process_set(process_set: ProcessSet) -> bool:
     if ps_id is None or ps_id == 0:
         return False
     _basics._remove_process_set_impl(ps_id)
+    _reset_unnamed_op_numbering(ps_id)
     _id_to_process_sets.pop(ps_id, None)
     process_set._invalidate()
     return True

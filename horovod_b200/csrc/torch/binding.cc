@@ -138,15 +138,27 @@ DataType MapDtype(at::ScalarType t) {
 
 int DeviceOf(const at::Tensor& t) { return t.is_cuda() ? (int)t.get_device() : CPU_DEVICE_ID; }
 
-// Unnamed ops are numbered per op type (not by handle: handle counters diverge between ranks as soon as one rank
-// issues an extra named op, e.g. around hvd.join(), and the names must match across ranks).
+// Unnamed ops are numbered per (op type, process set) — not by handle: handle counters diverge between ranks as soon as
+// one rank issues an extra op (around hvd.join(), or inside a process set the other rank is not a member of, e.g. the
+// unnamed allreduce in an autograd backward), and the names must match across the ranks of the set.
 std::mutex g_noname_mu;
 std::unordered_map<std::string, int> g_noname_counters;
-std::string OpName(const char* op, const std::string& name, int handle) {
-  (void)handle;
+std::string OpName(const char* op, const std::string& name, int process_set_id) {
   if (!name.empty()) return std::string(op) + "." + name;
   std::lock_guard<std::mutex> l(g_noname_mu);
-  return std::string(op) + ".noname." + std::to_string(g_noname_counters[op]++);
+  const std::string key = std::string(op) + (process_set_id ? ".ps" + std::to_string(process_set_id) : "");
+  return key + ".noname." + std::to_string(g_noname_counters[key]++);
+}
+
+// Process-set ids are recycled: a new set must start numbering from zero on every member.
+void ResetNonameCounters(int process_set_id) {
+  std::lock_guard<std::mutex> l(g_noname_mu);
+  const std::string tag = ".ps" + std::to_string(process_set_id);
+  for (auto it = g_noname_counters.begin(); it != g_noname_counters.end();) {
+    const std::string& k = it->first;
+    if (k.size() >= tag.size() && k.compare(k.size() - tag.size(), tag.size(), tag) == 0) it = g_noname_counters.erase(it);
+    else ++it;
+  }
 }
 
 void ThrowIfError(const Status& st) {
@@ -208,7 +220,7 @@ OutputAllocator MakeAllocator(at::Tensor output) {
 int DoAllreduce(at::Tensor tensor, at::Tensor output, const std::string& name, int op, double prescale, double postscale,
                 int process_set_id) {
   int h = g_handles.Allocate();
-  auto e = MakeEntry(tensor, OpName("allreduce", name, h));
+  auto e = MakeEntry(tensor, OpName("allreduce", name, process_set_id));
   e->output = output.data_ptr();
   e->reduce_op = (ReduceOp)op; e->prescale = prescale; e->postscale = postscale;
   e->callback = MakeCallback(h, e->device, e->ready_event);
@@ -226,7 +238,7 @@ int DoGroupedAllreduce(std::vector<at::Tensor> tensors, std::vector<at::Tensor> 
   int h = g_handles.Allocate((int)tensors.size());
   auto st = g_handles.Get(h);
   std::vector<std::shared_ptr<TensorTableEntry>> es;
-  std::string base = OpName("grouped_allreduce", name, h);
+  std::string base = OpName("grouped_allreduce", name, process_set_id);
   for (size_t i = 0; i < tensors.size(); ++i) {
     auto e = MakeEntry(tensors[i], base + "_" + std::to_string(i + 1) + "of" + std::to_string(tensors.size()));
     e->output = outputs[i].data_ptr();
@@ -243,7 +255,7 @@ int DoGroupedAllreduce(std::vector<at::Tensor> tensors, std::vector<at::Tensor> 
 
 int DoAllgather(at::Tensor tensor, at::Tensor output, const std::string& name, int process_set_id) {
   int h = g_handles.Allocate();
-  auto e = MakeEntry(tensor, OpName("allgather", name, h));
+  auto e = MakeEntry(tensor, OpName("allgather", name, process_set_id));
   e->alloc_output = MakeAllocator(output);
   e->callback = MakeCallback(h, e->device, e->ready_event);
   auto st = g_handles.Get(h);
@@ -260,7 +272,7 @@ int DoGroupedAllgather(std::vector<at::Tensor> tensors, std::vector<at::Tensor> 
   int h = g_handles.Allocate((int)tensors.size());
   auto st = g_handles.Get(h);
   std::vector<std::shared_ptr<TensorTableEntry>> es;
-  std::string base = OpName("grouped_allgather", name, h);
+  std::string base = OpName("grouped_allgather", name, process_set_id);
   for (size_t i = 0; i < tensors.size(); ++i) {
     auto e = MakeEntry(tensors[i], base + "_" + std::to_string(i + 1) + "of" + std::to_string(tensors.size()));
     e->alloc_output = MakeAllocator(outputs[i]);
@@ -276,7 +288,7 @@ int DoGroupedAllgather(std::vector<at::Tensor> tensors, std::vector<at::Tensor> 
 
 int DoBroadcast(at::Tensor tensor, at::Tensor output, int root_rank, const std::string& name, int process_set_id) {
   int h = g_handles.Allocate();
-  auto e = MakeEntry(tensor, OpName("broadcast", name, h));
+  auto e = MakeEntry(tensor, OpName("broadcast", name, process_set_id));
   e->output = output.data_ptr();
   e->root_rank = root_rank;
   e->callback = MakeCallback(h, e->device, e->ready_event);
@@ -290,7 +302,7 @@ int DoBroadcast(at::Tensor tensor, at::Tensor output, int root_rank, const std::
 int DoAlltoall(at::Tensor tensor, at::Tensor splits, at::Tensor output, at::Tensor received_splits, const std::string& name,
                int process_set_id) {
   int h = g_handles.Allocate();
-  auto e = MakeEntry(tensor, OpName("alltoall", name, h));
+  auto e = MakeEntry(tensor, OpName("alltoall", name, process_set_id));
   if (splits.defined() && splits.numel() > 0) {
     at::Tensor cpu_splits = splits.to(at::kCPU, at::kInt).contiguous();  // synchronous D2H when splits live on the GPU (mpi_ops_v2.cc:603-650)
     e->splits.assign(cpu_splits.data_ptr<int32_t>(), cpu_splits.data_ptr<int32_t>() + cpu_splits.numel());
@@ -308,7 +320,7 @@ int DoAlltoall(at::Tensor tensor, at::Tensor splits, at::Tensor output, at::Tens
 int DoReducescatter(at::Tensor tensor, at::Tensor output, const std::string& name, int op, double prescale, double postscale,
                     int process_set_id) {
   int h = g_handles.Allocate();
-  auto e = MakeEntry(tensor, OpName("reducescatter", name, h));
+  auto e = MakeEntry(tensor, OpName("reducescatter", name, process_set_id));
   e->alloc_output = MakeAllocator(output);
   e->reduce_op = (ReduceOp)op; e->prescale = prescale; e->postscale = postscale;
   e->callback = MakeCallback(h, e->device, e->ready_event);
@@ -326,7 +338,7 @@ int DoGroupedReducescatter(std::vector<at::Tensor> tensors, std::vector<at::Tens
   int h = g_handles.Allocate((int)tensors.size());
   auto st = g_handles.Get(h);
   std::vector<std::shared_ptr<TensorTableEntry>> es;
-  std::string base = OpName("grouped_reducescatter", name, h);
+  std::string base = OpName("grouped_reducescatter", name, process_set_id);
   for (size_t i = 0; i < tensors.size(); ++i) {
     auto e = MakeEntry(tensors[i], base + "_" + std::to_string(i + 1) + "of" + std::to_string(tensors.size()));
     e->alloc_output = MakeAllocator(outputs[i]);
@@ -497,6 +509,7 @@ PYBIND11_MODULE(_hvd_torch, m) {
   m.def("poll", &PollHandle);
   m.def("wait_and_clear", &WaitAndClear);
   m.def("reset", &Reset);
+  m.def("reset_noname_counters", &ResetNonameCounters);
   m.def("symm_empty", &SymmEmpty);
   m.def("fused_sgd_step", &FusedSgdStep);
   m.def("fused_adam_step", &FusedAdamStep);

@@ -413,6 +413,9 @@ def alltoall_async(tensor, splits=None, name=None, process_set=global_process_se
         splits_t = torch.empty(0, dtype=torch.int32)
     else:
         splits_t = splits if isinstance(splits, torch.Tensor) else torch.tensor(splits, dtype=torch.int32)
+        if splits_t.is_floating_point() or splits_t.dtype == torch.bool or splits_t.dim() != 1:
+            raise ValueError('alltoall: splits must be a 1-D integer tensor or a list of ints, got %s with %d dim(s)'
+                             % (splits_t.dtype, splits_t.dim()))
     output = tensor.new_empty(0)
     recv_splits = torch.empty(0, dtype=torch.int32, device=splits_t.device if splits is not None else 'cpu')
     handle = _wrap_native(_native().alltoall_async, tensor, splits_t, output, recv_splits, name or '', process_set.process_set_id)

@@ -53,3 +53,9 @@ def test_hierarchical_allreduce_fake_hosts(native_built):
                                  "allreduce_async_fused,allgather,broadcast,optimizer,barrier_join"])
     assert "ALL OK" in out, out[-4000:]
     assert "hierarchical allreduce over 2 hosts" in out, out[-4000:]
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+def test_extra_reference_cases_cuda(native_built):
+    rc, out = run_parallel("ops_worker_extra.py", np=2, timeout=300, args=["--device", "cuda"])
+    assert "EXTRA ALL OK" in out, out[-4000:]

@@ -81,3 +81,11 @@ def test_tensorflow_frontend_import_error_without_tf():
         del sys.modules[m]
     with pytest.raises(ImportError, match="TensorFlow"):
         importlib.import_module("horovod_b200.tensorflow")
+
+
+@pytest.mark.parametrize("np_", [2, 3])
+def test_extra_reference_cases(native_built, np_):
+    """Second matrix: grad variants with process sets, grouped allgather / reducescatter, per-op error paths, sparse
+    gradients, optimizer corner cases, join with non-allreduce ops, barriers mixed with collectives."""
+    rc, out = run_parallel("ops_worker_extra.py", np=np_, timeout=300)
+    assert "EXTRA ALL OK" in out, out[-3000:]
