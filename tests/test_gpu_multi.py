@@ -12,6 +12,12 @@ def _ngpu():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
+# Tests written after the round's GPU budget was spent: they pass on the CPU data plane but have not run on a multi-GPU
+# box yet, so they are opt-in until they have (HVD_RUN_NEW_GPU_TESTS=1).
+_NEW = pytest.mark.skipif(__import__('os').environ.get('HVD_RUN_NEW_GPU_TESTS', '0') != '1',
+                          reason='not yet validated on a multi-GPU box; set HVD_RUN_NEW_GPU_TESTS=1')
+
+
 @pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
 def test_ops_matrix_p2p(native_built):
     n = 2 if _ngpu() < 4 else (4 if _ngpu() < 8 else 8)
@@ -43,6 +49,7 @@ def test_wire_compression_env(native_built):
     assert "[ok] optimizer" in out or "ALL OK" in out, out[-3000:]
 
 
+@_NEW
 @pytest.mark.skipif(_ngpu() < 4, reason="needs >= 4 GPUs (2 fake hosts x 2)")
 def test_hierarchical_allreduce_fake_hosts(native_built):
     """The box's GPUs presented as 2 hosts: intra-host reduce-scatter/allgather kernels + cross-host CPU transport."""
@@ -55,6 +62,7 @@ def test_hierarchical_allreduce_fake_hosts(native_built):
     assert "hierarchical allreduce over 2 hosts" in out, out[-4000:]
 
 
+@_NEW
 @pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
 def test_extra_reference_cases_cuda(native_built):
     rc, out = run_parallel("ops_worker_extra.py", np=2, timeout=300, args=["--device", "cuda"])
