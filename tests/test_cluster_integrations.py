@@ -110,3 +110,46 @@ def test_spark_run_without_pyspark_raises():
     import horovod_b200.spark as hvd_spark
     with pytest.raises(ImportError, match='PySpark'):
         hvd_spark.run(lambda: 0)
+
+
+def _elastic_worker():
+    import torch
+    import horovod_b200.torch as hvd
+    hvd.init()
+    out = hvd.allreduce(torch.ones(2) * (hvd.rank() + 1), op=hvd.Sum).tolist()
+    res = (hvd.rank(), hvd.size(), out)
+    hvd.shutdown()
+    return res
+
+
+def test_elastic_ray_executor_with_local_actors(native_built):
+    """ElasticRayExecutor driven by a fixed discovery and subprocess 'actors' (Ray itself is not installed): the elastic
+    driver plans 2 slots on localhost, spawns the workers through the actor factory and collects their results."""
+    from horovod_b200.ray import ElasticRayExecutor
+    from horovod_b200.runner.elastic.discovery import FixedHosts
+
+    backend = LocalProcessBackend()
+    created = []
+
+    def actor_factory(hostname, env):
+        h = backend.create(len(created), dict(env, OMP_NUM_THREADS='1', HOROVOD_LOG_LEVEL='warning'))
+        created.append(h)
+
+        class Actor:
+            def execute(self, fn):
+                return backend.get([backend.call(h, 'execute', fn)], 120)[0]
+
+            def kill(self):
+                backend.kill(h)
+        return Actor()
+
+    settings = ElasticRayExecutor.create_settings(min_num_proc=2, max_num_proc=2, elastic_timeout=60, timeout_s=30)
+    settings.discovery = FixedHosts({'localhost': 2})
+    ex = ElasticRayExecutor(settings, override_discovery=False, actor_factory=actor_factory)
+    ex.start()
+    try:
+        res = ex.run(_elastic_worker)
+    finally:
+        for h in created:
+            backend.kill(h)
+    assert sorted(r[0] for r in res) == [0, 1] and all(r[1] == 2 and r[2] == [3.0, 3.0] for r in res), res

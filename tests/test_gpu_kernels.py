@@ -151,6 +151,38 @@ def test_sim_allgather_exchange():
         assert torch.equal(outs[r], ref)
 
 
+@pytest.mark.skipif(__import__('os').environ.get('HVD_RUN_NEW_GPU_TESTS', '0') != '1',
+                    reason='TMA exchange kernel: written after the GPU budget of round 1 was spent; HVD_RUN_NEW_GPU_TESTS=1')
+def test_sim_allgather_exchange_tma_variant():
+    """The cp.async.bulk (UBLKCP) variant of the exchange kernel: ragged sizes (16 B-aligned bulk part + byte tail) and an
+    unaligned destination (falls back to the vector path inside the same kernel).  Runs in a subprocess because the
+    variant is selected once per process (HVD_EXCHANGE_TMA)."""
+    import os, subprocess, sys, textwrap
+    code = textwrap.dedent('''
+        import ctypes, torch
+        from horovod_b200.common.basics import load_library
+        lib = load_library()
+        lib.hvd_sim_allgather.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.POINTER(ctypes.c_uint64),
+                                          ctypes.POINTER(ctypes.c_uint64), ctypes.c_int]
+        for n, nbytes, shift in ((8, 1 << 20, 0), (4, (1 << 18) + 13, 0), (2, 100000, 3), (2, 7, 0)):
+            ins = [torch.randint(0, 255, (nbytes,), device='cuda', dtype=torch.uint8) for _ in range(n)]
+            bufs = [torch.zeros(n * nbytes + 64, device='cuda', dtype=torch.uint8) for _ in range(n)]
+            outs = [b[shift:shift + n * nbytes] for b in bufs]
+            ip = (ctypes.c_uint64 * n)(*[x.data_ptr() for x in ins])
+            op_ = (ctypes.c_uint64 * n)(*[x.data_ptr() for x in outs])
+            for rep in range(3):
+                assert lib.hvd_sim_allgather(n, 0, nbytes, ip, op_, 8) == 0
+            ref = torch.cat(ins)
+            for r in range(n):
+                assert torch.equal(outs[r], ref), (n, nbytes, shift, r)
+        print('TMA EXCHANGE OK')
+    ''')
+    from conftest import REPO
+    p = subprocess.run([sys.executable, '-c', code], env=dict(os.environ, HVD_EXCHANGE_TMA='1', PYTHONPATH=REPO),
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300)
+    assert p.returncode == 0 and 'TMA EXCHANGE OK' in p.stdout.decode(), p.stdout.decode()[-3000:]
+
+
 def test_pack_reduce_bandwidth_smoke():
     """Not a benchmark: just checks a 64 MiB fused buffer moves at a sane rate on one GPU (all 'peers' are local HBM)."""
     n = 2
