@@ -126,6 +126,7 @@ template <typename SrcOf, typename DstOf>
 __device__ __forceinline__ void tma_copy_my_chunks(TmaRing& ring, int64_t offset, int64_t bytes, int cta, int grid, SrcOf src_of,
                                                    DstOf dst_of) {
   const int64_t end = offset + (bytes & ~(int64_t)15);
+  if (end <= offset) return;  // fewer than 16 bytes: the byte tail of the caller covers it
   // chunk walker shared by the load side (`lc`) and the store side (`sc`)
   auto next_mine = [&](int64_t c) { while (c * kXChunk < end && (int)(c % grid) != cta) ++c; return c; };
   auto bounds = [&](int64_t c, int64_t& lo, int64_t& hi) {
