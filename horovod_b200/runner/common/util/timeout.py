@@ -1,4 +1,6 @@
-"""Deadline helper (reference runner/common/util/timeout.py)."""
+"""Deadline object handed around by the launcher ("all of this has to happen within N seconds").
+API parity: horovod/runner/common/util/timeout.py (`Timeout(timeout, message).remaining() / timed_out() /
+check_time_out_for(activity)`, `TimeoutException`).  Monotonic clock: an NTP step cannot fire or stall a deadline."""
 import time
 
 
@@ -6,18 +8,20 @@ class TimeoutException(Exception):
     pass
 
 
-class Timeout(object):
+class Timeout:
     def __init__(self, timeout, message):
-        self._timeout = timeout
-        self._timeout_at = time.time() + timeout
+        self._seconds = timeout
+        self._deadline = time.monotonic() + timeout
         self._message = message
 
     def remaining(self):
-        return max(0, self._timeout_at - time.time())
+        left = self._deadline - time.monotonic()
+        return left if left > 0 else 0
 
     def timed_out(self):
-        return time.time() > self._timeout_at
+        return time.monotonic() > self._deadline
 
     def check_time_out_for(self, activity):
+        """Raises TimeoutException (message formatted with {activity} and {timeout}) once the deadline passed."""
         if self.timed_out():
-            raise TimeoutException(self._message.format(activity=activity, timeout=self._timeout))
+            raise TimeoutException(self._message.format(activity=activity, timeout=self._seconds))

