@@ -1,21 +1,27 @@
-"""Which environment variables travel from the launcher to the workers (reference runner/common/util/env.py)."""
+"""Environment plumbing between launcher and workers (role parity: horovod/runner/common/util/env.py)."""
 import os
 import re
 
 LOG_LEVEL_STR = ['FATAL', 'ERROR', 'WARNING', 'INFO', 'DEBUG', 'TRACE']
+
+# never forwarded to workers: shell function exports (break `env VAR=...` quoting), the previous directory, the ssh
+# session of the person who launched the job, and any secret key (the job's own key is passed explicitly)
+_NOT_FORWARDED = re.compile(r'^(BASH_FUNC_.*|OLDPWD|SSH_.*|.*_SECRET_KEY)$')
 IGNORE_REGEXES = {'BASH_FUNC_.*', 'OLDPWD', 'SSH_.*', '.*_SECRET_KEY'}
 
+# (rank variable, size variable) in lookup order: hvdrun, Open MPI, PMI (MPICH / Intel MPI / Slurm), torchrun
+_RANK_SIZE_VARS = (('HOROVOD_RANK', 'HOROVOD_SIZE'), ('OMPI_COMM_WORLD_RANK', 'OMPI_COMM_WORLD_SIZE'),
+                   ('PMI_RANK', 'PMI_SIZE'), ('RANK', 'WORLD_SIZE'))
 
-def is_exportable(v):
-    return not any(re.match(r, v) for r in IGNORE_REGEXES)
+
+def is_exportable(name):
+    return _NOT_FORWARDED.match(name) is None
 
 
-def get_env_rank_and_size():
-    rank_env = ['HOROVOD_RANK', 'OMPI_COMM_WORLD_RANK', 'PMI_RANK', 'RANK']
-    size_env = ['HOROVOD_SIZE', 'OMPI_COMM_WORLD_SIZE', 'PMI_SIZE', 'WORLD_SIZE']
-    for rank_var, size_var in zip(rank_env, size_env):
-        rank = os.environ.get(rank_var)
-        size = os.environ.get(size_var)
-        if rank is not None and size is not None:
-            return int(rank), int(size)
+def get_env_rank_and_size(environ=None):
+    """(rank, size) from whichever launcher started this process; (0, 1) when none did."""
+    environ = os.environ if environ is None else environ
+    for rank_var, size_var in _RANK_SIZE_VARS:
+        if rank_var in environ and size_var in environ:
+            return int(environ[rank_var]), int(environ[size_var])
     return 0, 1

@@ -1,113 +1,113 @@
-"""Host/slot bookkeeping: parse `-H host:slots,...` / hostfiles and lay ranks out over hosts.
+"""Hosts, slots and the rank layout of a job.
 
-Role parity: horovod/runner/common/util/hosts.py (HostInfo, SlotInfo, parse_hosts, get_host_assignments).
+Role parity: horovod/runner/common/util/hosts.py (`HostInfo`, `SlotInfo`, `INVALID_SLOT_INFO`, `parse_hosts`,
+`parse_hosts_and_slots`, `parse_host_files`, `get_host_assignments`).  Layout rule: ranks fill host after host in the
+order given; `local_rank` counts inside a host; `cross_rank` of a process is its host's position among the hosts that
+have a process with the same `local_rank` (hosts may have different slot counts).
 """
-import collections
 import re
+
+_HOST_SLOTS = re.compile(r'^(?P<host>[\w.\-\[\]:]+):(?P<slots>\d+)$')
 
 
 class HostInfo:
+    __slots__ = ('hostname', 'slots')
+
     def __init__(self, hostname, slots):
-        self.hostname = hostname
-        self.slots = slots
+        self.hostname, self.slots = hostname, slots
 
     @staticmethod
     def from_string(host_string):
-        hostname, slots = host_string.strip().split(':')
-        return HostInfo(hostname, int(slots))
+        host, slots = _split_host_slots(host_string)
+        return HostInfo(host, slots)
 
     def __repr__(self):
-        return f'HostInfo({self.hostname}:{self.slots})'
+        return 'HostInfo(%s:%d)' % (self.hostname, self.slots)
 
 
 class SlotInfo:
+    """One process of the job: where it runs and all six rank / size numbers."""
+    _FIELDS = ('hostname', 'rank', 'local_rank', 'cross_rank', 'size', 'local_size', 'cross_size')
+
     def __init__(self, hostname, rank, local_rank, cross_rank, size=None, local_size=None, cross_size=None):
-        self.hostname = hostname
-        self.rank = rank
-        self.size = size
-        self.local_rank = local_rank
-        self.local_size = local_size
-        self.cross_rank = cross_rank
-        self.cross_size = cross_size
+        self.hostname, self.rank, self.local_rank, self.cross_rank = hostname, rank, local_rank, cross_rank
+        self.size, self.local_size, self.cross_size = size, local_size, cross_size
 
     def to_response_string(self):
-        return ','.join(str(v) for v in [self.rank, self.size, self.local_rank, self.local_size, self.cross_rank,
-                                         self.cross_size])
+        """`rank,size,local_rank,local_size,cross_rank,cross_size` — the elastic rendezvous reply."""
+        return '%s,%s,%s,%s,%s,%s' % (self.rank, self.size, self.local_rank, self.local_size, self.cross_rank, self.cross_size)
+
+    def _key(self):
+        return tuple(getattr(self, f) for f in self._FIELDS)
 
     def __eq__(self, other):
-        return isinstance(other, SlotInfo) and self.__dict__ == other.__dict__
+        return isinstance(other, SlotInfo) and self._key() == other._key()
+
+    def __hash__(self):
+        return hash(self._key())
 
     def __repr__(self):
-        return 'SlotInfo(%s)' % ', '.join(f'{k}={v}' for k, v in self.__dict__.items())
+        return 'SlotInfo(%s)' % ', '.join('%s=%s' % (f, getattr(self, f)) for f in self._FIELDS)
 
 
 INVALID_SLOT_INFO = SlotInfo(hostname='', rank=-1, local_rank=-1, cross_rank=-1, size=-1, local_size=-1, cross_size=-1)
 
 
-def parse_host_files(filename):
-    """Hostfile lines: `hostname slots=N` (mpirun style) or `hostname:N`."""
-    hosts = []
-    with open(filename, 'r') as f:
-        for line in f.readlines():
-            line = line.strip()
-            if not line or line.startswith('#'):
-                continue
-            m = re.match(r'^(\S+)\s+slots\s*=\s*(\d+)', line)
-            if m:
-                hosts.append(f'{m.group(1)}:{m.group(2)}')
-            elif ':' in line:
-                hosts.append(line.split()[0])
-            else:
-                hosts.append(f'{line.split()[0]}:1')
-    return ','.join(hosts)
+def _split_host_slots(text):
+    m = _HOST_SLOTS.match(text.strip())
+    if not m:
+        raise ValueError('Invalid host input, please make sure it has format as : host1:2,host2:4,host3:1.')
+    return m.group('host'), int(m.group('slots'))
 
 
 def parse_hosts_and_slots(hosts):
-    host_names = []
-    host_to_slots = {}
-    host_list = hosts.split(',')
-    pattern = re.compile(r'^[\w.\-\[\]:]+:\d+$')
-    for host in host_list:
-        if not pattern.match(host.strip()):
-            raise ValueError('Invalid host input, please make sure it has format as : host1:2,host2:4,host3:1.')
-        hostname, slots = host.strip().rsplit(':', 1)
-        host_names.append(hostname)
-        host_to_slots[hostname] = int(slots)
-    return host_names, host_to_slots
+    """'h1:2,h2:4' -> (['h1', 'h2'], {'h1': 2, 'h2': 4})"""
+    pairs = [_split_host_slots(item) for item in hosts.split(',')]
+    return [h for h, _ in pairs], dict(pairs)
 
 
 def parse_hosts(hosts_string):
-    """'h1:2,h2:4' -> [HostInfo]"""
-    return [HostInfo.from_string(s.strip().rsplit(':', 1)[0] + ':' + s.strip().rsplit(':', 1)[1]) for s in hosts_string.split(',')]
+    """'h1:2,h2:4' -> [HostInfo, HostInfo]"""
+    return [HostInfo.from_string(item) for item in hosts_string.split(',')]
+
+
+def parse_host_files(filename):
+    """A hostfile has one host per line: `name slots=N` (mpirun style), `name:N`, or a bare name (one slot); `#` starts a
+    comment.  Returns the equivalent `-H` string."""
+    entries = []
+    with open(filename) as f:
+        for raw in f:
+            line = raw.split('#', 1)[0].strip()
+            if not line:
+                continue
+            name = line.split()[0]
+            m = re.search(r'\bslots\s*=\s*(\d+)', line)
+            if m:
+                entries.append('%s:%s' % (name, m.group(1)))
+            elif ':' in name:
+                entries.append(name)
+            else:
+                entries.append(name + ':1')
+    return ','.join(entries)
 
 
 def get_host_assignments(hosts, min_num_proc, max_num_proc=None):
-    """Assign ranks host by host (all slots of host 0 first). Returns a list of SlotInfo, rank-ordered.
-
-    Raises ValueError when fewer than `min_num_proc` slots exist."""
-    host_ranks = []
-    cross_ranks = collections.defaultdict(dict)
-    rank = 0
-    for host_info in hosts:
-        ranks = []
-        for local_rank in range(host_info.slots):
-            if rank == max_num_proc:
-                break
-            ranks.append(rank)
+    """[HostInfo] -> rank-ordered [SlotInfo] using at most `max_num_proc` slots; ValueError when fewer than
+    `min_num_proc` slots are available."""
+    budget = max_num_proc if max_num_proc is not None else sum(h.slots for h in hosts)
+    used = []                                   # (hostname, processes placed on it)
+    for h in hosts:
+        take = max(0, min(h.slots, budget))
+        budget -= take
+        used.append((h.hostname, take))
+    world = sum(n for _, n in used)
+    if world < min_num_proc:
+        raise ValueError('Requested more processes ({}) than there are available slots ({})'.format(min_num_proc, world))
+    layout, rank = [], 0
+    for host_pos, (name, count) in enumerate(used):
+        for local_rank in range(count):
+            peers = [i for i, (_, n) in enumerate(used) if n > local_rank]   # hosts that have this local rank
+            layout.append(SlotInfo(hostname=name, rank=rank, local_rank=local_rank, cross_rank=peers.index(host_pos),
+                                   size=world, local_size=count, cross_size=len(peers)))
             rank += 1
-            cross_ranks_at_local = cross_ranks[local_rank]
-            cross_ranks_at_local[host_info.hostname] = len(cross_ranks_at_local)
-        host_ranks.append((host_info, ranks))
-    world_size = rank
-    if world_size < min_num_proc:
-        raise ValueError('Requested more processes ({}) than there are available slots ({})'.format(min_num_proc, world_size))
-    alloc_list = []
-    for host_info, ranks in host_ranks:
-        local_size = len(ranks)
-        for local_rank, rank in enumerate(ranks):
-            cross_ranks_at_local = cross_ranks[local_rank]
-            cross_rank = cross_ranks_at_local[host_info.hostname]
-            cross_size = len(cross_ranks_at_local)
-            alloc_list.append(SlotInfo(hostname=host_info.hostname, rank=rank, local_rank=local_rank, cross_rank=cross_rank,
-                                       size=world_size, local_size=local_size, cross_size=cross_size))
-    return alloc_list
+    return layout
