@@ -219,7 +219,9 @@ bool GpuOps::EnsureHierarchy(ProcessSet& ps, int device) {
   for (int i = 0; i < n; ++i) by_host[t->host_id(i)].push_back(i);
   const std::vector<int>& mine = by_host[t->host_id(me)];
   const int L = (int)mine.size();
-  bool uniform = L >= 2 && L <= kern::kMaxPeers && EnvBool("HVD_HIERARCHICAL_ALLREDUCE", true);
+  // on by default for uniform multi-host sets; HOROVOD_HIERARCHICAL_ALLREDUCE=0 (hvdrun --no-hierarchical-allreduce) forces
+  // the flat host-staged path
+  bool uniform = L >= 2 && L <= kern::kMaxPeers && EnvBool("HVD_HIERARCHICAL_ALLREDUCE", EnvBool("HOROVOD_HIERARCHICAL_ALLREDUCE", true));
   for (auto& kv : by_host) if ((int)kv.second.size() != L) uniform = false;
   int64_t tag[2] = {(int64_t)getpid(), (int64_t)(++team_counter_)};
   t->Bcast(tag, sizeof tag, 0);
