@@ -316,10 +316,12 @@ bool Engine::RunLoopOnce() {
     if (!ps || !ps->member()) continue;
     ps->controller->set_fusion_threshold(tp.fusion_threshold_bytes);
     ps->controller->set_cache_enabled(tp.cache_enabled);
-    ResponseList rl = ps->controller->ComputeResponseList(shutdown_requested_.load());
+    // only the GLOBAL set decides when the engine stops: the members of a sub-set may all have asked for shutdown while
+    // another rank has not yet, and leaving early would cut that rank's connections in the middle of a negotiation
+    ResponseList rl = ps->controller->ComputeResponseList(id == 0 && shutdown_requested_.load());
     if (rl.responses.empty()) ++fast_cycles_;
     for (auto& r : rl.responses) PerformOperation(*ps, r);
-    if (rl.shutdown) keep_going = false;
+    if (id == 0 && rl.shutdown) keep_going = false;
   }
   if (params_.IsAutoTuning() || tp.active) {
     auto g = sets_.Get(0);

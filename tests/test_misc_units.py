@@ -70,3 +70,23 @@ def test_local_store(tmp_path):
     from horovod_b200.spark.common.store import FilesystemStore
     remote = Store.create('hdfs://namenode:8020/x/y')  # lazily bound pyarrow.fs filesystem
     assert type(remote) is FilesystemStore and remote.get_run_path('r') == 'hdfs://namenode:8020/x/y/runs/r'
+
+
+def test_utils_timing_helpers():
+    from horovod_b200.utils import ClockSampler, device_timer, measured_peaks
+    lines = ['1965, 1965, 612.3, Not Active, Not Active, Not Active, Not Active',
+             '1410, 1965, 998.1, Not Active, Not Active, Not Active, Active',
+             'garbage', '1965, 1965, 700.0, Not Active, Not Active, Not Active, Not Active']
+    s = ClockSampler.summarise(lines)
+    assert s == {'sm_mhz': 1965.0, 'sm_max_mhz': 1965.0, 'samples': 3, 'reasons': ['sw_power_cap']}
+    assert ClockSampler.summarise([])['sm_mhz'] is None
+    with device_timer() as t:
+        sum(range(1000))
+    assert t.ms is not None and t.ms >= 0
+    assert isinstance(measured_peaks(), dict)
+
+
+def test_ops_package_surface():
+    import horovod_b200.ops as ops
+    assert ops.sim.DTYPE_CODE[__import__('torch').bfloat16] == 10 and ops.sim.TWOSHOT == 1
+    assert callable(ops.fused_sgd_step) and callable(ops.fused_adam_step) and callable(ops.symm_empty)

@@ -89,3 +89,11 @@ def test_extra_reference_cases(native_built, np_):
     gradients, optimizer corner cases, join with non-allreduce ops, barriers mixed with collectives."""
     rc, out = run_parallel("ops_worker_extra.py", np=np_, timeout=300)
     assert "EXTRA ALL OK" in out, out[-3000:]
+
+
+def test_parallel_package_np4(native_built):
+    """horovod_b200.parallel: local / cross / 2-D mesh process sets (4 ranks shown as 2 hosts x 2), shard helpers,
+    ShardedSGD == DistributedOptimizer(SGD)."""
+    rc, out = run_parallel("parallel_pkg_worker.py", np=4, timeout=300)
+    assert "PARALLEL PKG OK" in out, out[-3000:]
+    assert "background loop failed" not in out, out[-3000:]   # shutdown with sub-sets registered must be clean
