@@ -81,12 +81,14 @@ def create_distributed_optimizer(keras, optimizer, name, device_dense, device_sp
             finally:
                 self._hvd_reduced = False
 
-    cls = type(base.__name__, (base,), dict(_Distributed.__dict__))
+    # the wrapper class carries the wrapped optimizer's name so that a saved model reloads without this package
+    _Distributed.__name__ = base.__name__
+    _Distributed.__qualname__ = base.__qualname__
     cfg = optimizer.get_config()
     try:
-        return cls.from_config(cfg)
-    except Exception:
-        return cls(**cfg)
+        return _Distributed.from_config(cfg)
+    except Exception:  # noqa: BLE001 - optimizers whose from_config needs more than the config
+        return _Distributed(**cfg)
 
 
 def _value(x):

@@ -110,6 +110,49 @@ assert abs(float(m.optimizer.momentum.numpy()) - 0.9) < 1e-9
 wu.on_epoch_begin(1)
 wu.on_batch_begin(3)
 assert abs(float(m.optimizer.learning_rate.numpy()) - 0.8) < 1e-9  # epoch 1 + 3/4 + 1/4 == warmup_epochs
+# Keras optimizer wrapper: same class name, gradients averaged before the wrapped apply_gradients, local accumulation
+class SGD:
+    def __init__(self, learning_rate=0.5):
+        self.learning_rate = learning_rate
+        self.applied = 0
+
+    def get_config(self):
+        return {'learning_rate': self.learning_rate}
+
+    @classmethod
+    def from_config(cls, cfg):
+        return cls(**cfg)
+
+    def apply_gradients(self, grads_and_vars):
+        self.applied += 1
+        for g, v in grads_and_vars:
+            if g is not None:
+                v.assign(v.numpy() - self.learning_rate * g.numpy())
+
+
+dopt = hvdk.DistributedOptimizer(SGD(0.5))
+assert type(dopt).__name__ == 'SGD' and isinstance(dopt, SGD) and dopt.learning_rate == 0.5
+v1, v2 = tf.Variable(np.zeros(2), name='v1:0'), tf.Variable(np.ones(1), name='v2:0')
+dopt.apply_gradients([(tf.constant(np.ones(2) * (r + 1)), v1), (None, v2)])
+np.testing.assert_allclose(v1.numpy(), -0.5 * np.ones(2) * (n + 1) / 2)
+assert v2.numpy().tolist() == [1.0] and dopt.applied == 1
+acc = hvdk.DistributedOptimizer(SGD(1.0), backward_passes_per_step=2, average_aggregated_gradients=True)
+v3 = tf.Variable(np.zeros(1), name='v3:0')
+assert acc.apply_gradients([(tf.constant(np.ones(1) * 2.0), v3)]) is None and acc.applied == 0 and v3.numpy().tolist() == [0.0]
+acc.apply_gradients([(tf.constant(np.ones(1) * 4.0), v3)])
+np.testing.assert_allclose(v3.numpy(), [-3.0])   # mean of (2, 4), identical on every rank, averaged over ranks
+assert acc.applied == 1
+local_opt = hvdk.DistributedOptimizer(SGD(1.0))
+v4, v5 = tf.Variable(np.zeros(1), name='v4:0'), tf.Variable(np.zeros(1), name='v5:0')
+local_opt.register_local_var(v5)
+local_opt.apply_gradients([(tf.constant(np.ones(1) * (r + 1)), v4), (tf.constant(np.ones(1) * n), v5)])
+np.testing.assert_allclose(v4.numpy(), [-(n + 1) / 2])
+np.testing.assert_allclose(v5.numpy(), [-1.0])   # local variable: not reduced, scaled by 1/size
+try:
+    hvdk.DistributedOptimizer(SGD(), op=hvd.Sum, gradient_predivide_factor=2.0)
+    raise AssertionError('predivide with op != Average must be rejected')
+except ValueError:
+    pass
 assert hvdk.allreduce(np.array([1.0, 2.0]) * (r + 1), name='k.ar', op=hvd.Sum).tolist() == [n * (n + 1) / 2, n * (n + 1.0)]
 hvd.barrier()
 if r == 0:
