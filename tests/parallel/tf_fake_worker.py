@@ -154,6 +154,45 @@ try:
 except ValueError:
     pass
 assert hvdk.allreduce(np.array([1.0, 2.0]) * (r + 1), name='k.ar', op=hvd.Sum).tolist() == [n * (n + 1) / 2, n * (n + 1.0)]
+# elastic state for Keras models: commit / restore / sync through hvd.elastic.TensorFlowKerasState
+from horovod_b200.tensorflow.elastic import TensorFlowKerasState, TensorFlowState
+
+
+class _KModel:
+    def __init__(self, value):
+        self.variables = [tf.Variable(np.full(3, float(value)), name='kw:0')]
+        self.optimizer = None
+
+    def get_weights(self):
+        return [v.numpy() for v in self.variables]
+
+    def set_weights(self, ws):
+        for v, w in zip(self.variables, ws):
+            v.assign(w)
+
+
+km = _KModel(r + 1)
+kst = TensorFlowKerasState(km, epoch=r, batch=5)
+kst.sync()                                   # rank 0's weights and values everywhere
+assert km.variables[0].numpy().tolist() == [1.0] * 3 and kst.epoch == 0 and kst.batch == 5
+kst.epoch = 4
+kst.commit() if False else kst.save()
+km.variables[0].assign(np.full(3, 9.0))
+kst.epoch = 8
+kst.restore()
+assert km.variables[0].numpy().tolist() == [1.0] * 3 and kst.epoch == 4
+vst = TensorFlowState(variables=[tf.Variable(np.full(2, float(r)))], step=r)
+vst.sync()
+assert vst.variables[0].numpy().tolist() == [0.0, 0.0] and vst.step == 0
+
+# SyncBatchNormalization moments: mean / variance over the GLOBAL batch
+from horovod_b200.tensorflow.sync_batch_norm import SyncBatchNormalization
+bn = SyncBatchNormalization(name='sbn')
+xb = tf.constant(np.full((4, 2), float(r)))          # rank r contributes 4 rows of value r
+mean, var = bn._moments(xb, [0])
+allv = np.concatenate([np.full((4, 2), float(q)) for q in range(n)])
+np.testing.assert_allclose(mean.numpy(), allv.mean(0))
+np.testing.assert_allclose(var.numpy(), allv.var(0), atol=1e-12)
 hvd.barrier()
 if r == 0:
     print('TF FAKE OK')
