@@ -97,3 +97,10 @@ def test_parallel_package_np4(native_built):
     rc, out = run_parallel("parallel_pkg_worker.py", np=4, timeout=300)
     assert "PARALLEL PKG OK" in out, out[-3000:]
     assert "background loop failed" not in out, out[-3000:]   # shutdown with sub-sets registered must be clean
+
+
+def test_mxnet_frontend_against_fake_mxnet_np2(native_built):
+    """Control flow of horovod_b200.mxnet (ops, DistributedOptimizer, DistributedTrainer, broadcast_parameters incl.
+    deferred initialisation) over a numpy-backed MXNet stand-in (tests/fakes/mxnet)."""
+    rc, out = run_parallel("mx_fake_worker.py", np=2, timeout=200)
+    assert "MX FAKE OK" in out, out[-3000:]
