@@ -51,7 +51,19 @@ struct TensorDesc {
   int64_t count;
 };
 
-enum Variant : int { kOneShot = 0, kTwoShot = 1, kNvls = 2 };
+enum Variant : int { kOneShot = 0, kTwoShot = 1, kNvls = 2, kPipelined = 3 };
+
+// Software-pipelined variant (kPipelined): per-rank words inside the flag region, past the per-CTA barrier flags and the
+// Adasum scratch.  `packed` / `reduced` are written by the peers, the rest is local bookkeeping.
+constexpr int kPipeAreaOffset = 96 * 1024;   // bytes from the start of the flag region
+constexpr int kPipeMaxSlots = 32;
+constexpr int kPipePacked = 0;                       // [kMaxPeers] chunk counter published by every rank after its pack
+constexpr int kPipeReduced = 16;                     // [kMaxPeers] ... after its reduce + broadcast
+constexpr int kPipePackCnt = 64;                     // [kPipeMaxSlots] CTAs that finished packing the chunk in this slot
+constexpr int kPipeRedCnt = 64 + kPipeMaxSlots;      // [kPipeMaxSlots]
+constexpr int kPipeUnpackCnt = 64 + 2 * kPipeMaxSlots;
+constexpr int kPipeUnpackDone = 64 + 3 * kPipeMaxSlots;  // 1 word: chunks completely unpacked on this rank
+constexpr int kPipeAreaWords = 64 + 3 * kPipeMaxSlots + 16;
 // reduce op codes follow hvd::ReduceOp: 1 SUM (AVERAGE arrives as SUM + postscale), 3 MIN, 4 MAX, 5 PRODUCT
 // dtype codes follow hvd::DataType.
 
@@ -69,6 +81,13 @@ struct AllreduceArgs {
   // reducescatter: outputs use their own table (offsets relative to the fused buffer)
   const TensorDesc* out_descs;  // nullptr => same as descs
   int nout;
+  // kPipelined only: the symmetric buffer is a ring of `pipe_slots` chunks of `pipe_chunk_bytes`; `pipe_base` is the
+  // team-wide running chunk counter at the start of this launch (identical on all ranks), `pipe_use_nvls` selects the
+  // in-switch reduction
+  int64_t pipe_chunk_bytes;
+  int pipe_slots;
+  uint32_t pipe_base;
+  int pipe_use_nvls;
 };
 
 // Fused allreduce / reducescatter.  Returns cudaErrorInvalidValue for

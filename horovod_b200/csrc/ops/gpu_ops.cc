@@ -413,6 +413,18 @@ Status GpuOps::Allreduce(ProcessSet& ps, Entries& es, const Response& r, int dev
           if (seg_bytes <= tp.oneshot_max_bytes) variant = kern::kOneShot;
           else if (nvls_ok && n >= 4 && seg_bytes >= tp.nvls_min_bytes) variant = kern::kNvls;  // in-switch reduction pays off from 4 GPUs (measured: slower than two-shot at N=2)
         }
+        // opt-in: software-pipelined pack / NVLS / unpack for large segments of plain tensors (docs/roadmap.md B1)
+        static const bool pipelined_on = EnvBool("HVD_PIPELINED_ALLREDUCE", false);
+        static const int64_t pipe_chunk = std::max<int64_t>(1 << 20, EnvInt("HVD_PIPE_CHUNK_BYTES", 8 << 20) / 4096 * 4096);
+        static const int64_t pipe_min = EnvInt("HVD_PIPE_MIN_BYTES", 32 << 20);
+        if (pipelined_on && env_.variant == "auto" && seg_bytes >= pipe_min && (r.reduce_op == ReduceOp::SUM || r.reduce_op == ReduceOp::AVERAGE) &&
+            cap / pipe_chunk >= 2) {
+          variant = kern::kPipelined;
+          a.pipe_chunk_bytes = pipe_chunk;
+          a.pipe_slots = (int)std::min<int64_t>(kern::kPipeMaxSlots, cap / pipe_chunk);
+          a.pipe_base = team->NextPipeBase((uint32_t)((seg_bytes + pipe_chunk - 1) / pipe_chunk));
+          a.pipe_use_nvls = (nvls_ok && n >= 4) ? 1 : 0;
+        }
         a.variant = variant;
         int64_t per = variant == kern::kOneShot ? 8192 : (int64_t)4096 * n;  // >= 2 rows (one-shot) or one row per rank (two-shot) per CTA
         // small messages are latency bound (few CTAs = cheap barrier, SMs left to compute); large ones need many loads in flight
@@ -423,6 +435,7 @@ Status GpuOps::Allreduce(ProcessSet& ps, Entries& es, const Response& r, int dev
                                : seg_bytes <= (16 << 20) ? std::min<int64_t>(tp.comm_ctas, 64)
                                : seg_bytes < (64 << 20) ? tp.comm_ctas : std::max<int64_t>(tp.comm_ctas, big_ctas);
         a.ctas = (int)std::max<int64_t>(1, std::min<int64_t>(cap_ctas, (seg_bytes + per - 1) / per));
+        if (variant == kern::kPipelined) a.ctas = (int)std::min<int64_t>(kern::kMaxCtas, std::max<int64_t>(tp.comm_ctas, big_ctas)) / 4 * 4;
         if (a.ndesc <= kern::kInlineDescs) {
           memcpy(a.inline_descs, descs.data(), descs.size() * sizeof(kern::TensorDesc));
           a.descs = nullptr;

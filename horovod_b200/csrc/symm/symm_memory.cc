@@ -274,7 +274,8 @@ kern::CommParams SymmTeam::Params(int which) const {
 namespace {
 // flag words (kFlagWords * 4 = 8 KiB) followed by the two Adasum partial-dot tables (2 x kAdasumScratchStride)
 constexpr size_t kFlagRegionBytes = 128 * 1024;
-static_assert(kern::kFlagWords * 4 + 2 * kern::kAdasumScratchStride <= (long long)kFlagRegionBytes, "flag region too small");
+static_assert(kern::kFlagWords * 4 + 2 * kern::kAdasumScratchStride <= (long long)kern::kPipeAreaOffset, "Adasum scratch overlaps the pipeline words");
+static_assert(kern::kPipeAreaOffset + kern::kPipeAreaWords * 4 <= (long long)kFlagRegionBytes, "flag region too small");
 }
 
 std::shared_ptr<SymmTeam> SymmTeam::Create(Transport* t, int device, size_t buffer_bytes, bool want_mc,
