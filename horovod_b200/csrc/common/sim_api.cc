@@ -101,6 +101,7 @@ int hvd_sim_allreduce(int nranks, int device, int ntensors, const int64_t* count
         if (sl && atoi(sl) >= 2) a.pipe_slots = std::min(a.pipe_slots, atoi(sl));
         a.pipe_base = sim->teams[r]->NextPipeBase((uint32_t)((total + a.pipe_chunk_bytes - 1) / a.pipe_chunk_bytes));
         a.pipe_use_nvls = 0;
+        a.pipe_rblock_bytes = 8192;
       }
       kern::CommParams cp = sim->teams[r]->Params(sim->teams[r]->NextSlot());
       cudaError_t e = kern::LaunchAllreduce(cp, a, sim->streams[r]);

@@ -440,7 +440,9 @@ __device__ __forceinline__ bool pipe_wait(const CommParams& cp, const uint32_t* 
     (void)ld_acquire_sys(w);
   }
   __syncthreads();
-  return s_abort == 0;
+  const int aborted = s_abort;
+  __syncthreads();  // everyone has read the verdict before the next call may reset it
+  return aborted == 0;
 }
 
 // All threads of the CTA call it after their last store of a chunk.  Returns true in exactly one CTA per chunk (the
@@ -537,7 +539,7 @@ pipelined_allreduce_kernel(const __grid_constant__ CommParams cp, const __grid_c
     // ---------------- reduce + broadcast of my slice ----------------
     const S postscale = (S)a.postscale;
     const int ri = quad * 2 + (role - 1), nred = nquad * 2;
-    constexpr int64_t kRBlock = 4 * (int64_t)kRowBytes;  // 16 KiB
+    const int64_t kRBlock = a.pipe_rblock_bytes;  // work item of one reduce CTA (multiple of the 4 KiB row)
     for (int64_t c = 0; c < nchunks; ++c) {
       if (!pipe_wait(cp, mine + kPipePacked, cp.nranks, base + (uint32_t)c + 1u)) return;
       const int64_t clo = c * C, chi = clo + C < total ? clo + C : total;
@@ -671,6 +673,7 @@ cudaError_t LaunchAllreduce(const CommParams& cp, const AllreduceArgs& args, cud
   if (args.variant == kPipelined) {
     const int w = args.dtype == 7 ? (args.wire_dtype == 10 || args.wire_dtype == 6 ? args.wire_dtype : 7) : args.dtype;
     if (args.pipe_chunk_bytes <= 0 || (args.pipe_chunk_bytes % 4096) || args.pipe_slots < 2 || args.pipe_slots > kPipeMaxSlots ||
+        args.pipe_rblock_bytes < kRowBytes || (args.pipe_rblock_bytes % kRowBytes) ||
         args.out_descs != nullptr || args.reduce_lo != 0 || args.reduce_hi != args.total_bytes)
       return cudaErrorInvalidValue;
     if (args.pipe_use_nvls && (!(w == 7 || w == 6 || w == 10) || args.op != 1 || cp.mc_buf == nullptr)) return cudaErrorInvalidValue;

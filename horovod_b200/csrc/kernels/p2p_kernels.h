@@ -85,6 +85,7 @@ struct AllreduceArgs {
   // team-wide running chunk counter at the start of this launch (identical on all ranks), `pipe_use_nvls` selects the
   // in-switch reduction
   int64_t pipe_chunk_bytes;
+  int64_t pipe_rblock_bytes;    // bytes one reduce CTA handles per trip (multiple of 4096)
   int pipe_slots;
   uint32_t pipe_base;
   int pipe_use_nvls;

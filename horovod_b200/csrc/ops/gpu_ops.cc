@@ -421,6 +421,7 @@ Status GpuOps::Allreduce(ProcessSet& ps, Entries& es, const Response& r, int dev
             cap / pipe_chunk >= 2) {
           variant = kern::kPipelined;
           a.pipe_chunk_bytes = pipe_chunk;
+          a.pipe_rblock_bytes = std::max<int64_t>(4096, EnvInt("HVD_PIPE_RBLOCK_BYTES", 16384) / 4096 * 4096);
           a.pipe_slots = (int)std::min<int64_t>(kern::kPipeMaxSlots, cap / pipe_chunk);
           a.pipe_base = team->NextPipeBase((uint32_t)((seg_bytes + pipe_chunk - 1) / pipe_chunk));
           a.pipe_use_nvls = (nvls_ok && n >= 4) ? 1 : 0;
