@@ -1,7 +1,6 @@
 """Keras callbacks (parity: horovod/_keras/callbacks.py:23-215 and _keras/elastic.py:17-85): broadcast of the initial
 state, metric averaging, LR schedule / warm-up with momentum correction, elastic commit / batch / epoch bookkeeping.
 Written against the public Keras callback protocol only (`self.model`, `self.params`, `logs`)."""
-import warnings
 
 import tensorflow as tf
 

@@ -1,7 +1,6 @@
 """BERT for pre-training (masked LM + next-sentence heads), BERT-large by default: 24 layers, hidden 1024, 16 heads,
 FFN 4096, vocab 30522, max 512 positions, ~336 M parameters — the `BERT-large pretraining bf16` config of
 BASELINE.json.  Attention goes through torch's fused scaled_dot_product_attention."""
-import math
 from dataclasses import dataclass
 
 import torch

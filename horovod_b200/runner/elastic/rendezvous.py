@@ -8,7 +8,6 @@ runner/http/http_server.py instead of a handler subclass.
 import logging
 
 from horovod_b200.runner.common.util import network
-from horovod_b200.runner.common.util.hosts import INVALID_SLOT_INFO
 
 # GET methods
 GET_RANK_AND_SIZE = 'rank_and_size'

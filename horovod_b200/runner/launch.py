@@ -346,7 +346,6 @@ def _run_static(args):
 def _run_func_static(args, settings, nics):
     """Run-func mode: the pickled function travels through a KV store, results come back per rank."""
     from horovod_b200.runner.http.http_server import KVStoreServer
-    from horovod_b200.runner.common.util import codec
     import cloudpickle
     kvstore = KVStoreServer(verbose=settings.verbose)
     port = kvstore.start_server()

@@ -6,7 +6,6 @@ launch_gloo :242, gloo_run :295; the elastic variant lives in elastic_run below)
 native TCP/shm mesh (csrc/transport), hence the file name; the environment contract (HOROVOD_RANK, HOROVOD_SIZE,
 HOROVOD_LOCAL_RANK, ..., HOROVOD_GLOO_RENDEZVOUS_ADDR/PORT, HOROVOD_CONTROLLER) is the reference's.
 """
-import errno
 import os
 import shlex
 import sys

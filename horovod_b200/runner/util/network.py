@@ -1,5 +1,4 @@
 """Local network helpers (reference runner/util/network.py)."""
-import random
 import socket
 
 import psutil

@@ -10,7 +10,6 @@ events chained into the caller's stream, so `synchronize()` does not block the
 host on the GPU.
 """
 import os
-import warnings
 
 import torch
 

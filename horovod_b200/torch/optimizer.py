@@ -19,7 +19,6 @@ from horovod_b200.common.process_sets import global_process_set
 from horovod_b200.common.util import split_list
 from horovod_b200.torch import mpi_ops
 from horovod_b200.torch.compression import Compression
-from horovod_b200.torch.functions import broadcast_object
 from horovod_b200.torch.mpi_ops import (Adasum, Average, Sum, allreduce_async_, grouped_allreduce_async_, rank, size,
                                         synchronize)
 
