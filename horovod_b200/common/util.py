@@ -57,3 +57,98 @@ def resolve_op(op, average, Average, Sum):
 def is_version_greater_equal_than(ver, target):
     from packaging import version
     return version.parse(ver) >= version.parse(target)
+
+
+# ---- build / availability queries (role parity: horovod/common/util.py extension_available, gpu_available, *_built,
+# check_installed_version).  There is one native library for all front ends, so "is the <framework> extension
+# available" reduces to "is the native runtime built and is that framework importable".
+_FRAMEWORK_MODULE = {'torch': 'torch', 'tensorflow': 'tensorflow', 'mxnet': 'mxnet', 'keras': 'tensorflow', 'numpy': 'numpy'}
+
+
+def _native_lib():
+    from horovod_b200.common.basics import load_library
+    return load_library()
+
+
+def extension_available(ext_base_name, verbose=False):
+    """True when `horovod_b200.<ext_base_name>` can be used in this environment."""
+    import importlib.util
+    mod = _FRAMEWORK_MODULE.get(ext_base_name, ext_base_name)
+    if importlib.util.find_spec(mod) is None:
+        if verbose:
+            print('%s is not installed' % mod)
+        return False
+    try:
+        _native_lib()
+        return True
+    except Exception as e:  # noqa: BLE001
+        if verbose:
+            print('native runtime unavailable: %s' % e)
+        return False
+
+
+def gpu_available(ext_base_name='torch', verbose=False):
+    """True when the native runtime sees at least one CUDA device (the P2P kernels are sm_100a only)."""
+    if not extension_available(ext_base_name, verbose):
+        return False
+    try:
+        import torch
+        return bool(torch.cuda.is_available())
+    except ImportError:
+        return False
+
+
+def _built(query, verbose=False):
+    try:
+        return bool(getattr(_native_lib(), query)())
+    except Exception as e:  # noqa: BLE001
+        if verbose:
+            print('%s: %s' % (query, e))
+        return False
+
+
+def mpi_built(verbose=False):
+    return False  # there is no MPI data or control plane in this runtime
+
+
+def gloo_built(verbose=False):
+    return _built('hvd_gloo_built', verbose)  # the native TCP/shm mesh fills Gloo's role
+
+
+def nccl_built(verbose=False):
+    return _built('hvd_nccl_built', verbose)
+
+
+def ddl_built(verbose=False):
+    return False
+
+
+def ccl_built(verbose=False):
+    return False
+
+
+def check_installed_version(name, version, exception=None):
+    """Warns when the running `name` differs from the version the package was built against (the native binding is
+    compiled against torch headers; other front ends go through DLPack and have no build-time version)."""
+    import warnings
+    try:
+        from horovod_b200.build import ROOT
+        import os
+        stamp = os.path.join(ROOT, 'build', 'obj', 'torch_binding.stamp')
+        built = open(stamp).read().split('-')[1] if name == 'torch' and os.path.exists(stamp) else None
+    except Exception:  # noqa: BLE001
+        built = None
+    if built and built != version:
+        msg = ('horovod_b200 was built against %s %s but %s is running; rebuild with `python -m horovod_b200.build`' % (name, built, version))
+        if exception is not None:
+            raise type(exception)(msg)
+        warnings.warn(msg)
+        return False
+    return True
+
+
+def get_average_backwards_compatibility_fun(reduce_ops):
+    """Returns f(op, average) implementing the deprecated `average=` argument for a front end's ReduceOps namespace."""
+    def impl(op, average):
+        return resolve_op(op, average, reduce_ops.Average, reduce_ops.Sum)
+    return impl

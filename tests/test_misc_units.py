@@ -90,3 +90,28 @@ def test_ops_package_surface():
     import horovod_b200.ops as ops
     assert ops.sim.DTYPE_CODE[__import__('torch').bfloat16] == 10 and ops.sim.TWOSHOT == 1
     assert callable(ops.fused_sgd_step) and callable(ops.fused_adam_step) and callable(ops.symm_empty)
+
+
+def test_common_util_availability_helpers():
+    import torch
+    from horovod_b200.common import util
+    assert util.extension_available('torch') and not util.extension_available('definitely_not_a_framework')
+    assert util.gloo_built() and util.nccl_built() and not util.mpi_built() and not util.ddl_built() and not util.ccl_built()
+    assert util.gpu_available() == torch.cuda.is_available()
+    assert util.check_installed_version('torch', torch.__version__)
+    with pytest.warns(UserWarning, match='built against'):
+        assert not util.check_installed_version('torch', '0.0.0')
+    with pytest.raises(RuntimeError):
+        util.check_installed_version('torch', '0.0.0', exception=RuntimeError('x'))
+
+    class Ops:
+        Average, Sum = 0, 1
+    f = util.get_average_backwards_compatibility_fun(Ops)
+    assert f(None, None) == Ops.Average and f(None, False) == Ops.Sum and f(Ops.Sum, None) == Ops.Sum
+    with pytest.raises(ValueError):
+        f(Ops.Sum, True)
+    with util.env(HVD_T_X='1'):
+        import os
+        assert os.environ['HVD_T_X'] == '1'
+    assert 'HVD_T_X' not in __import__('os').environ
+    assert util.split_list([1, 2, 3, 4, 5], 2) == [[1, 2, 3], [4, 5]] and util.num_rank_is_power_2(8) and not util.num_rank_is_power_2(6)
