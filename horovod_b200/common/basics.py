@@ -142,11 +142,25 @@ class HorovodBasics(object):
             return
         if comm is not None and not isinstance(comm, (list, tuple)):
             raise ValueError("hvd.init(comm=...) only accepts a list of ranks in this build (no MPI).")
-        if comm:
-            raise ValueError("hvd.init(comm=[ranks]) subsets are not supported; use process sets instead.")
         rank, size, local_rank, local_size, cross_rank, cross_size = _resolve_topology()
         scope = 'mesh.%s.%d' % (os.environ.get('HOROVOD_RENDEZVOUS_EPOCH', '0'), self._init_count)
         addr, port = _resolve_rendezvous(rank, size)
+        if comm:
+            # a job over a subset of the launched ranks (reference basics.py:51-148 with a rank list): the members
+            # rendezvous under a scope derived from the list, are renumbered 0..len-1 in list order, and the native
+            # runtime derives local / cross ranks from the hostnames it exchanges
+            members = [int(r) for r in comm]
+            if len(set(members)) != len(members) or any(r < 0 or r >= size for r in members):
+                raise ValueError('hvd.init(comm=%r): ranks must be distinct and within [0, %d)' % (list(comm), size))
+            if rank not in members:
+                raise ValueError('hvd.init(comm=%r) called on rank %d, which is not part of that communicator' % (list(comm), rank))
+            import hashlib
+            scope += '.c' + hashlib.sha1(','.join(map(str, members)).encode()).hexdigest()[:10]
+            rank, size = members.index(rank), len(members)
+            if size == 1:
+                local_rank, local_size, cross_rank, cross_size = 0, 1, 0, 1
+            else:
+                local_rank = local_size = cross_rank = cross_size = -1
 
         if os.environ.get('HOROVOD_ELASTIC') == '1' and addr:
             # elastic: the driver assigns rank/size for this rendezvous round (reference gloo_context.cc:168-214)

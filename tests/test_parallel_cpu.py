@@ -104,3 +104,10 @@ def test_mxnet_frontend_against_fake_mxnet_np2(native_built):
     deferred initialisation) over a numpy-backed MXNet stand-in (tests/fakes/mxnet)."""
     rc, out = run_parallel("mx_fake_worker.py", np=2, timeout=200)
     assert "MX FAKE OK" in out, out[-3000:]
+
+
+def test_init_with_rank_subset_np3(native_built):
+    """hvd.init(comm=[2, 0]) on two of three launched ranks (renumbered in list order), hvd.init(comm=[1]) on the third;
+    a non-member is rejected (reference: common/basics.py init(comm=<rank list>))."""
+    rc, out = run_parallel("comm_subset_worker.py", np=3, timeout=200)
+    assert out.count("COMM SUBSET OK") == 3, out[-3000:]
