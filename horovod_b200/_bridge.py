@@ -46,6 +46,7 @@ class BridgedOps:
         return handle
 
     def synchronize(self, handle):
+        """Waits for an asynchronous op and returns its result as a framework tensor (list for grouped ops)."""
         like = self._likes.pop(handle, None)
         out = _ops.synchronize(handle)
         if isinstance(out, (list, tuple)):
@@ -57,66 +58,81 @@ class BridgedOps:
         return self.bridge.from_torch(out, like)
 
     def poll(self, handle):
+        """True once the asynchronous op behind `handle` has finished."""
         return _ops.poll(handle)
 
     # ---- allreduce -----------------------------------------------------------------------------------------------
     def allreduce_async(self, tensor, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0,
                         process_set=_ops.global_process_set):
+        """Asynchronous allreduce (default op: Average); returns a handle."""
         return self._track(_ops.allreduce_async(self._in(tensor), average, name, op, prescale_factor, postscale_factor,
                                                 process_set), tensor)
 
     def allreduce(self, tensor, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0,
                   process_set=_ops.global_process_set):
+        """Allreduce (default op: Average) of a framework tensor; the input is not modified."""
         return self.synchronize(self.allreduce_async(tensor, average, name, op, prescale_factor, postscale_factor,
                                                      process_set))
 
     def grouped_allreduce_async(self, tensors, average=None, name=None, op=None, prescale_factor=1.0,
                                 postscale_factor=1.0, process_set=_ops.global_process_set):
+        """Asynchronous allreduce of a list of tensors as one fused group; returns a handle."""
         return self._track(_ops.grouped_allreduce_async([self._in(t) for t in tensors], average, name, op, prescale_factor,
                                                         postscale_factor, process_set), list(tensors))
 
     def grouped_allreduce(self, tensors, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0,
                           process_set=_ops.global_process_set):
+        """Allreduce of a list of tensors as one fused group."""
         return self.synchronize(self.grouped_allreduce_async(tensors, average, name, op, prescale_factor,
                                                              postscale_factor, process_set))
 
     # ---- allgather / broadcast / alltoall / reducescatter --------------------------------------------------------
     def allgather_async(self, tensor, name=None, process_set=_ops.global_process_set):
+        """Asynchronous allgather along dim 0; returns a handle."""
         return self._track(_ops.allgather_async(self._in(tensor), name, process_set), tensor)
 
     def allgather(self, tensor, name=None, process_set=_ops.global_process_set):
+        """Concatenates the tensors of all ranks along dim 0 (dim 0 may differ between ranks)."""
         return self.synchronize(self.allgather_async(tensor, name, process_set))
 
     def grouped_allgather(self, tensors, name=None, process_set=_ops.global_process_set):
+        """Allgather of a list of tensors negotiated as one group."""
         h = self._track(_ops.grouped_allgather_async([self._in(t) for t in tensors], name, process_set), list(tensors))
         return self.synchronize(h)
 
     def broadcast_async(self, tensor, root_rank, name=None, process_set=_ops.global_process_set):
+        """Asynchronous broadcast of root_rank's tensor; returns a handle."""
         return self._track(_ops.broadcast_async(self._in(tensor), root_rank, name, process_set), tensor)
 
     def broadcast(self, tensor, root_rank, name=None, process_set=_ops.global_process_set):
+        """Returns root_rank's tensor on every rank."""
         return self.synchronize(self.broadcast_async(tensor, root_rank, name, process_set))
 
     def alltoall_async(self, tensor, splits=None, name=None, process_set=_ops.global_process_set):
+        """Asynchronous alltoall; returns a handle."""
         if splits is not None and not isinstance(splits, (list, tuple, torch.Tensor)):
             splits = self.bridge.to_torch(splits).to(torch.int32).cpu()
         return self._track(_ops.alltoall_async(self._in(tensor), splits, name, process_set),
                            ('alltoall', tensor) if splits is not None else tensor)
 
     def alltoall(self, tensor, splits=None, name=None, process_set=_ops.global_process_set):
+        """Scatters dim-0 slices to all ranks and gathers theirs; with `splits` returns (output, received_splits)."""
         return self.synchronize(self.alltoall_async(tensor, splits, name, process_set))
 
     def reducescatter_async(self, tensor, name=None, op=_ops.Average, process_set=_ops.global_process_set,
                             prescale_factor=1.0, postscale_factor=1.0):
+        """Asynchronous reducescatter; returns a handle."""
         return self._track(_ops.reducescatter_async(self._in(tensor), name, op, process_set, prescale_factor,
                                                     postscale_factor), tensor)
 
     def reducescatter(self, tensor, name=None, op=_ops.Average, process_set=_ops.global_process_set, prescale_factor=1.0,
                       postscale_factor=1.0):
+        """Reduces over ranks; rank r keeps the r-th slice of dim 0."""
         return self.synchronize(self.reducescatter_async(tensor, name, op, process_set, prescale_factor, postscale_factor))
 
     def grouped_reducescatter(self, tensors, name=None, op=_ops.Average, process_set=_ops.global_process_set,
                               prescale_factor=1.0, postscale_factor=1.0):
+        """Reducescatter of a list of tensors as one group."""
         h = self._track(_ops.grouped_reducescatter_async([self._in(t) for t in tensors], name, op, process_set,
                                                          prescale_factor, postscale_factor), list(tensors))
         return self.synchronize(h)
@@ -124,11 +140,13 @@ class BridgedOps:
     # ---- python objects ------------------------------------------------------------------------------------------
     @staticmethod
     def broadcast_object(obj, root_rank=0, name=None, process_set=_ops.global_process_set):
+        """Broadcasts an arbitrary picklable object from root_rank."""
         from horovod_b200.torch.functions import broadcast_object
         return broadcast_object(obj, root_rank, name, process_set)
 
     @staticmethod
     def allgather_object(obj, name=None, process_set=_ops.global_process_set):
+        """Returns [object of rank 0, object of rank 1, ...] on every rank."""
         from horovod_b200.torch.functions import allgather_object
         return allgather_object(obj, name, process_set)
 

@@ -204,10 +204,12 @@ class HorovodBasics(object):
                     ps._attach(i + 1)
 
     def shutdown(self):
+        """Stops the background thread; pending collectives fail with HorovodInternalError. Safe to call twice."""
         if self._lib is not None:
             self.lib.hvd_shutdown()
 
     def is_initialized(self):
+        """True between a successful init() and shutdown()."""
         return self._lib is not None and bool(self.lib.hvd_is_initialized())
 
     def _need_init(self, v):
@@ -216,55 +218,72 @@ class HorovodBasics(object):
         return v
 
     def size(self):
+        """Number of ranks in the job."""
         return self._need_init(self.lib.hvd_size())
 
     def local_size(self):
+        """Number of ranks on this host."""
         return self._need_init(self.lib.hvd_local_size())
 
     def cross_size(self):
+        """Number of hosts that have a rank with my local_rank."""
         return self._need_init(self.lib.hvd_cross_size())
 
     def rank(self):
+        """This process's rank in [0, size)."""
         return self._need_init(self.lib.hvd_rank())
 
     def local_rank(self):
+        """Rank among the processes of this host; the usual CUDA device index."""
         return self._need_init(self.lib.hvd_local_rank())
 
     def cross_rank(self):
+        """Index of my host among the hosts that have a rank with my local_rank."""
         return self._need_init(self.lib.hvd_cross_rank())
 
     def is_homogeneous(self):
+        """True when every host runs the same number of ranks."""
         return bool(self.lib.hvd_is_homogeneous())
 
     # ---- capability queries -------------------------------------------------
     def mpi_threads_supported(self):
+        """Always False: there is no MPI in this runtime."""
         return False
 
     def mpi_enabled(self):
+        """Always False: the control plane is the native TCP/shm mesh."""
         return bool(self.lib.hvd_mpi_enabled())
 
     def mpi_built(self):
+        """Always False (kept for API compatibility)."""
         return bool(self.lib.hvd_mpi_built())
 
     def gloo_enabled(self):
+        """True: the native TCP/shm mesh plays the role Gloo plays in the reference."""
         return bool(self.lib.hvd_gloo_enabled())
 
     def gloo_built(self):
+        """True (see gloo_enabled)."""
         return bool(self.lib.hvd_gloo_built())
 
     def nccl_built(self):
+        """True: the NCCL baseline data path is compiled in (libnccl is dlopen'ed on first use)."""
         return int(self.lib.hvd_nccl_built())
 
     def ddl_built(self):
+        """Always False."""
         return bool(self.lib.hvd_ddl_built())
 
     def ccl_built(self):
+        """Always False."""
         return bool(self.lib.hvd_ccl_built())
 
     def cuda_built(self):
+        """True when the native library was built with the sm_100a kernels."""
         return bool(self.lib.hvd_cuda_built())
 
     def rocm_built(self):
+        """Always False."""
         return bool(self.lib.hvd_rocm_built())
 
     def p2p_built(self):
@@ -273,9 +292,11 @@ class HorovodBasics(object):
 
     # ---- timeline -------------------------------------------------------------
     def start_timeline(self, file_path, mark_cycles=False):
+        """Starts writing a Chrome-tracing timeline to `file_path` (rank 0 writes); `mark_cycles` adds cycle markers."""
         self._check(self.lib.hvd_start_timeline(str(file_path).encode(), 1 if mark_cycles else 0))
 
     def stop_timeline(self):
+        """Stops the timeline started with start_timeline() / HOROVOD_TIMELINE."""
         self._check(self.lib.hvd_stop_timeline())
 
     # ---- process sets -----------------------------------------------------------
@@ -309,20 +330,24 @@ class HorovodBasics(object):
 
     # ---- introspection (new) ------------------------------------------------------
     def gpu_topology(self):
+        """Human-readable result of the GPU / NVLink topology discovery done in init()."""
         buf = ctypes.create_string_buffer(2048)
         self.lib.hvd_topology_string(buf, 2048)
         return buf.value.decode()
 
     def gpu_backend_info(self, process_set_id=0):
+        """Which GPU data path a process set uses (p2p / nccl / host-staged / hierarchical, symmetric-memory kind, buffer size)."""
         buf = ctypes.create_string_buffer(1024)
         self.lib.hvd_gpu_backend_string(process_set_id, buf, 1024)
         return buf.value.decode()
 
     def runtime_stats(self):
+        """Counters of the background thread: cycles, idle cycles, responses executed, kernels launched."""
         return {'cycles': int(self.lib.hvd_stat(0)), 'idle_cycles': int(self.lib.hvd_stat(1)),
                 'responses': int(self.lib.hvd_stat(2)), 'kernel_launches': int(self.lib.hvd_stat(3))}
 
     def tunable_params(self):
+        """Current values of the autotuned parameters (fusion threshold, cycle time, kernel crossovers, CTA count)."""
         names = ['fusion_threshold_bytes', 'cycle_time_us', 'cache_enabled', 'oneshot_max_bytes', 'nvls_min_bytes',
                  'comm_ctas', 'autotune_active']
         return {n: int(self.lib.hvd_param(i)) for i, n in enumerate(names)}

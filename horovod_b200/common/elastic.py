@@ -170,6 +170,7 @@ class _ElasticLoop:
 
 
 def run_fn(func, reset):
+    """Wraps `func(state, ...)` in the elastic retry loop; `reset` re-initialises the runtime after a failure."""
     loop = _ElasticLoop(func, reset)
 
     @functools.wraps(func)

@@ -23,20 +23,24 @@ def fused_sgd_step(params, grads, momentum_buffers, lr, momentum=0.0, dampening=
 
 def fused_adam_step(params, grads, exp_avgs, exp_avg_sqs, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, step=1,
                     grad_scale=1.0, adamw=True):
+    """One launch of Adam / AdamW for the whole parameter list (fp32 state; `step` is the 1-based step count)."""
     return _native().fused_adam_step(list(params), list(grads), list(exp_avgs), list(exp_avg_sqs), float(lr), float(beta1), float(beta2),
                                      float(eps), float(weight_decay), int(step), float(grad_scale), bool(adamw))
 
 
 def symm_empty(*args, **kwargs):
+    """Collective: a tensor in registered symmetric memory (see horovod_b200.torch.symm_empty)."""
     from horovod_b200.torch.mpi_ops import symm_empty as f
     return f(*args, **kwargs)
 
 
 def symm_available(*args, **kwargs):
+    """True when registered symmetric memory can be allocated for the process set."""
     from horovod_b200.torch.mpi_ops import symm_available as f
     return f(*args, **kwargs)
 
 
 def kernel_launches():
+    """Number of kernels of this library launched by this process so far."""
     from horovod_b200.torch.mpi_ops import runtime_stats
     return int(runtime_stats()['kernel_launches'])

@@ -84,6 +84,7 @@ class Mesh2D:
 
 
 def mesh_2d(rows, cols):
+    """Collective: registers the row and column process sets of a rows x cols grid over all ranks; returns a Mesh2D."""
     hvd = _hvd()
     if rows * cols != hvd.size():
         raise ValueError('mesh %dx%d does not cover %d ranks' % (rows, cols, hvd.size()))

@@ -22,6 +22,9 @@ import torch
 
 
 class GraphedStep:
+    """Training step whose forward + backward are one CUDA graph replay; `step(*inputs)` returns the (static) loss tensor.
+    `.captured` tells whether the graph is in use, `.fallback_reason` why not."""
+
     def __init__(self, step_fn, optimizer, example_inputs, warmup_iters=3, enabled=True):
         self.step_fn, self.optimizer = step_fn, optimizer
         self.captured, self.fallback_reason = False, None

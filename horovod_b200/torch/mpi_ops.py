@@ -61,6 +61,7 @@ def init(*args, **kwargs):
 
 
 def shutdown():
+    """Shuts the runtime down and forgets outstanding handles."""
     _basics.shutdown()
     if _lib is not None:
         _lib.reset()
@@ -196,6 +197,7 @@ def allreduce_async_(tensor, average=None, name=None, op=None, prescale_factor=1
 
 def allreduce_(tensor, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0,
                process_set=global_process_set):
+    """In-place synchronous allreduce; returns `tensor`."""
     handle = allreduce_async_(tensor, average, name, op, prescale_factor, postscale_factor, process_set)
     return synchronize(handle)
 
@@ -248,6 +250,7 @@ class HorovodGroupedAllreduce(torch.autograd.Function):
 
 def grouped_allreduce(tensors, average=None, name=None, compression=None, op=None, prescale_factor=1.0,
                       postscale_factor=1.0, process_set=global_process_set):
+    """Synchronous, differentiable allreduce of a list of tensors as ONE fused group (one kernel launch)."""
     from horovod_b200.torch.compression import Compression
     compression = compression or Compression.none
     compressed, ctxs = zip(*[compression.compress(t) for t in tensors])
@@ -257,12 +260,14 @@ def grouped_allreduce(tensors, average=None, name=None, compression=None, op=Non
 
 def grouped_allreduce_async_(tensors, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0,
                              process_set=global_process_set):
+    """In-place asynchronous grouped allreduce; returns one handle for the group."""
     op = resolve_op(op, average, Average, Sum)
     return _grouped_allreduce_async(tensors, tensors, name, op, prescale_factor, postscale_factor, process_set)
 
 
 def grouped_allreduce_(tensors, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0,
                        process_set=global_process_set):
+    """In-place synchronous grouped allreduce; returns the list of tensors."""
     handle = grouped_allreduce_async_(tensors, average, name, op, prescale_factor, postscale_factor, process_set)
     return synchronize(handle)
 
@@ -318,10 +323,12 @@ class HorovodAllgather(torch.autograd.Function):
 
 
 def allgather(tensor, name=None, process_set=global_process_set):
+    """Synchronous, differentiable allgather along dim 0 (dim 0 may differ between ranks)."""
     return HorovodAllgather.apply(tensor, name, process_set)
 
 
 def grouped_allgather_async(tensors, name=None, process_set=global_process_set):
+    """Asynchronous grouped allgather; synchronize() returns the list of outputs."""
     tensors = [t.reshape(1) if t.dim() == 0 else t for t in tensors]
     for t in tensors:
         _check_contiguous(t)
@@ -353,6 +360,7 @@ class HorovodGroupedAllgather(torch.autograd.Function):
 
 
 def grouped_allgather(tensors, name=None, process_set=global_process_set):
+    """Synchronous, differentiable allgather of a list of tensors negotiated as one group."""
     return list(HorovodGroupedAllgather.apply(name, process_set, *tensors))
 
 
@@ -389,14 +397,17 @@ class HorovodBroadcast(torch.autograd.Function):
 
 
 def broadcast(tensor, root_rank, name=None, process_set=global_process_set):
+    """Synchronous, differentiable broadcast of root_rank's tensor; the input is not modified."""
     return HorovodBroadcast.apply(tensor, root_rank, name, process_set)
 
 
 def broadcast_async_(tensor, root_rank, name=None, process_set=global_process_set):
+    """In-place asynchronous broadcast; returns a handle."""
     return _broadcast_async(tensor, tensor, root_rank, name, process_set)
 
 
 def broadcast_(tensor, root_rank, name=None, process_set=global_process_set):
+    """In-place synchronous broadcast; returns `tensor`."""
     handle = broadcast_async_(tensor, root_rank, name, process_set)
     return synchronize(handle)
 
@@ -445,6 +456,7 @@ class HorovodAlltoall(torch.autograd.Function):
 
 
 def alltoall(tensor, splits=None, name=None, process_set=global_process_set):
+    """Synchronous, differentiable alltoall; with `splits` returns (output, received_splits)."""
     return HorovodAlltoall.apply(tensor, splits, name, process_set)
 
 
@@ -487,6 +499,7 @@ class HorovodReducescatter(torch.autograd.Function):
 
 def reducescatter(tensor, name=None, compression=None, op=Average, process_set=global_process_set, prescale_factor=1.0,
                   postscale_factor=1.0):
+    """Synchronous, differentiable reducescatter: reduces over ranks, rank r keeps the r-th slice of dim 0."""
     from horovod_b200.torch.compression import Compression
     compression = compression or Compression.none
     tensor_compressed, ctx = compression.compress(tensor)
@@ -496,6 +509,7 @@ def reducescatter(tensor, name=None, compression=None, op=Average, process_set=g
 
 def grouped_reducescatter_async(tensors, name=None, op=Average, process_set=global_process_set, prescale_factor=1.0,
                                 postscale_factor=1.0):
+    """Asynchronous grouped reducescatter; synchronize() returns the list of shards."""
     for t in tensors:
         _check_contiguous(t)
     outputs = [t.new_empty(0) for t in tensors]
@@ -525,6 +539,7 @@ class HorovodGroupedReducescatter(torch.autograd.Function):
 
 def grouped_reducescatter(tensors, name=None, compression=None, op=Average, process_set=global_process_set,
                           prescale_factor=1.0, postscale_factor=1.0):
+    """Synchronous, differentiable reducescatter of a list of tensors as one group."""
     from horovod_b200.torch.compression import Compression
     compression = compression or Compression.none
     compressed, ctxs = zip(*[compression.compress(t) for t in tensors])
