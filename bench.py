@@ -35,6 +35,8 @@ def parse():
     p.add_argument('--no-fused-optimizer', action='store_true')
     p.add_argument('--op', default='average', choices=['average', 'adasum'])
     p.add_argument('--fp32', action='store_true', help='disable bf16 autocast')
+    p.add_argument('--bucket-wire-dtype', default=None, choices=['bf16', 'fp16'],
+                   help='experimental: reduce the fp32 gradient buckets as bf16/fp16 (registered shadow buckets)')
     p.add_argument('--no-cuda-graph', action='store_true', help='eager forward/backward with gradient hooks instead of hvd.GraphedStep')
     p.add_argument('--sizes', default=None, help='allreduce sweep: comma separated byte sizes')
     p.add_argument('--dtype', default='fp32', help='allreduce sweep dtype: fp32|bf16|fp16')
@@ -185,7 +187,8 @@ def train_bench(args):
     # graphed step: no backward/allreduce overlap to preserve, so fewer, larger buckets (fewer launches and host round trips)
     opt = hvd.DistributedOptimizer(base_opt, named_parameters=model.named_parameters(), op=op,
                                    fused=not args.no_fused_optimizer, **({} if op != hvd.Average else
-                                                                         {'bucket_cap_mb': 32 if args.no_cuda_graph else 256}))
+                                                                         {'bucket_cap_mb': 32 if args.no_cuda_graph else 256,
+                                                                          'bucket_wire_dtype': {'bf16': torch.bfloat16, 'fp16': torch.float16, None: None}[args.bucket_wire_dtype]}))
     hvd.broadcast_parameters(model.state_dict(), root_rank=0)
     hvd.broadcast_optimizer_state(opt, root_rank=0)
     model.train()
@@ -264,7 +267,7 @@ def train_bench(args):
             'impl': 'ours',
             'config': {'model': args.model, 'global_batch': global_batch, 'per_gpu_batch': bs, 'seq_len': seq,
                        'parallelism': f'dp{size}', 'optimizer': 'SGD(momentum=0.9)' if args.model == 'resnet50' else 'AdamW',
-                       'fused_optimizer': not args.no_fused_optimizer, 'grad_dtype': 'fp32',
+                       'fused_optimizer': not args.no_fused_optimizer, 'grad_dtype': 'fp32', 'bucket_wire_dtype': args.bucket_wire_dtype or 'fp32',
                        'cuda_graph': bool(graphed.captured), 'cuda_graph_fallback': graphed.fallback_reason,
                        'l2': 'per-step working set (activations + 100+ MB of gradients) exceeds the 126 MB L2; no explicit flush',
                        'gpu_backend': hvd.gpu_backend_info(), 'tunables': hvd.tunable_params()},

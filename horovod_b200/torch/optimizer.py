@@ -26,9 +26,14 @@ from horovod_b200.torch.mpi_ops import (Adasum, Average, Sum, allreduce_async_, 
 class _DistributedOptimizer(torch.optim.Optimizer):
     def __init__(self, params, named_parameters, compression, backward_passes_per_step=1, op=Average,
                  gradient_predivide_factor=1.0, groups=None, sparse_as_dense=False, process_set=global_process_set,
-                 fused=False, zero_copy=None, bucket_cap_mb=32):
+                 fused=False, zero_copy=None, bucket_cap_mb=32, bucket_wire_dtype=None):
         super(self.__class__, self).__init__(params)
         self._compression = compression
+        # opt-in: fp32 gradient buckets travel as bf16 / fp16 (a registered shadow bucket of half the bytes is what the
+        # zero-copy kernel reduces; the switch accumulates in fp32).  Not validated on hardware yet (docs/roadmap.md B3).
+        if bucket_wire_dtype is None:
+            bucket_wire_dtype = {'bf16': torch.bfloat16, 'fp16': torch.float16}.get(os.environ.get('HVD_BUCKET_WIRE_DTYPE', ''))
+        self._bucket_wire_dtype = bucket_wire_dtype
 
         if named_parameters is not None:
             named_parameters = list(named_parameters)
@@ -180,7 +185,14 @@ class _DistributedOptimizer(torch.optim.Optimizer):
                     flat = mpi_ops.symm_empty(total // itemsize, dtype=dtype, device=members[0][0].device, process_set=self.process_set)
                     flat.zero_()
                     bucket = {'flat': flat, 'params': [m[0] for m in members], 'pending': len(members),
-                              'name': 'bucket.%d' % len(self._buckets), 'handle': None}
+                              'name': 'bucket.%d' % len(self._buckets), 'handle': None, 'shadow': None, 'shadow_views': None}
+                    if self._bucket_wire_dtype is not None and dtype == torch.float32:
+                        shadow = mpi_ops.symm_empty(total // itemsize, dtype=self._bucket_wire_dtype, device=members[0][0].device,
+                                                    process_set=self.process_set)
+                        shadow.zero_()
+                        bucket['shadow'] = shadow
+                        bucket['shadow_views'] = {p: shadow[off // itemsize: off // itemsize + p.numel()].as_strided(p.size(), p.stride())
+                                                  for p, off in members}
                     for p, off in members:
                         view = flat[off // itemsize: off // itemsize + p.numel()].as_strided(p.size(), p.stride())
                         if p.grad is not None:
@@ -201,7 +213,11 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             prescale_factor, postscale_factor = 1.0 / self.gradient_predivide_factor, self.gradient_predivide_factor
         else:
             prescale_factor = postscale_factor = 1.0
-        bucket['handle'] = allreduce_async_(bucket['flat'], name=bucket['name'], op=self.op, prescale_factor=prescale_factor,
+        wire = bucket['flat']
+        if bucket.get('shadow') is not None:
+            wire = bucket['shadow']
+            wire.copy_(bucket['flat'])  # one cast kernel fp32 -> wire dtype on the caller's stream
+        bucket['handle'] = allreduce_async_(wire, name=bucket['name'], op=self.op, prescale_factor=prescale_factor,
                                             postscale_factor=postscale_factor, process_set=self.process_set)
         bucket['pending'] = len(bucket['params'])
 
@@ -294,7 +310,21 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             offs = bucket['offsets'] = {q: q.grad.data_ptr() - bucket['flat'].data_ptr() for q in bucket['params']}
         return offs[p]
 
-    def synchronize(self):
+    def _restore_shadows(self):
+        """Reduced values of wire-dtype shadow buckets -> the fp32 gradients that p.grad points at."""
+        for bucket in self._buckets:
+            if bucket.get('shadow') is not None and bucket.get('shadow_fresh'):
+                bucket['flat'].copy_(bucket['shadow'])
+                bucket['shadow_fresh'] = False
+
+    def _grad_for_update(self, p):
+        """The tensor the fused optimizer kernel should read as p's gradient (the wire-dtype shadow when it is fresh)."""
+        bucket = self._p_to_bucket.get(p)
+        if bucket is not None and bucket.get('shadow') is not None and bucket.get('shadow_fresh'):
+            return bucket['shadow_views'][p]
+        return p.grad
+
+    def synchronize(self, _defer_shadow_copy=False):
         """Waits for every outstanding gradient allreduce (enqueueing the ones whose hook never fired so that all
         ranks stay in lock-step) and writes the reduced gradients back."""
         if not self.process_set.included():
@@ -312,9 +342,13 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             for bucket in self._buckets:
                 synchronize(bucket['handle'])
                 bucket['handle'] = None
+                if bucket.get('shadow') is not None:
+                    bucket['shadow_fresh'] = True
                 for p in bucket['params']:
                     self._allreduce_delay[p] = self.backward_passes_per_step
                     self._handles.pop(p, None)
+        if self._zero_copy and not _defer_shadow_copy:
+            self._restore_shadows()  # callers of synchronize() (gradient clipping, ...) read p.grad
         pending = [p for p in self._requires_update if p not in self._handles and p not in self._p_to_bucket]
         pending += [p for p, (h, _) in self._handles.items() if h is None]
         if self._groups is not None:
@@ -373,10 +407,13 @@ class _DistributedOptimizer(torch.optim.Optimizer):
                               "optimizer.synchronize(). This can cause training slowdown. You may want to consider "
                               "using optimizer.skip_synchronize() context if you use optimizer.synchronize() in your "
                               "code.")
-            self.synchronize()
+            self.synchronize(_defer_shadow_copy=self._fused and closure is None)
         self._synchronized = False
         if self._fused and closure is None and _fused_step(self):
+            for bucket in self._buckets:
+                bucket['shadow_fresh'] = False
             return None
+        self._restore_shadows()
         return super(self.__class__, self).step(closure)
 
     def zero_grad(self, *args, **kwargs):
@@ -426,11 +463,14 @@ def _fused_step(opt):
                 continue
             if not all(p.is_cuda and not p.grad.is_sparse and mpi_ops._is_dense(p) and p.grad.stride() == p.stride() for p in params):
                 return False
+            grad_of = getattr(opt, '_grad_for_update', lambda q: q.grad)
             by_dtype = {}
             for p in params:
-                by_dtype.setdefault((p.dtype, p.grad.dtype), []).append(p)
+                by_dtype.setdefault((p.dtype, grad_of(p).dtype), []).append(p)
+            if any(pd == torch.float32 and gd == torch.float16 for pd, gd in by_dtype):
+                return False  # no fp32-parameter / fp16-gradient kernel
             for (_, _), ps in by_dtype.items():
-                grads = [p.grad for p in ps]
+                grads = [grad_of(p) for p in ps]
                 if is_sgd:
                     mom = group.get('momentum', 0.0)
                     bufs, first = [], False
@@ -625,7 +665,7 @@ class _DistributedAdasumOptimizer(torch.optim.Optimizer):
 
 def DistributedOptimizer(optimizer, named_parameters=None, compression=Compression.none, backward_passes_per_step=1,
                          op=Average, gradient_predivide_factor=1.0, num_groups=0, groups=None, sparse_as_dense=False,
-                         process_set=global_process_set, fused=False, zero_copy=None, bucket_cap_mb=32):
+                         process_set=global_process_set, fused=False, zero_copy=None, bucket_cap_mb=32, bucket_wire_dtype=None):
     """Wraps `optimizer` so gradients are combined across ranks before the parameter update.
 
     Arguments follow the reference (horovod/torch/optimizer.py:516-608). `fused=True` (new) runs the SGD /
@@ -642,7 +682,7 @@ def DistributedOptimizer(optimizer, named_parameters=None, compression=Compressi
     if op != Adasum or size() == 1:
         cls = type(optimizer.__class__.__name__, (optimizer.__class__,), dict(_DistributedOptimizer.__dict__))
         return cls(optimizer.param_groups, named_parameters, compression, backward_passes_per_step, op,
-                   gradient_predivide_factor, groups, sparse_as_dense, process_set, fused, zero_copy, bucket_cap_mb)
+                   gradient_predivide_factor, groups, sparse_as_dense, process_set, fused, zero_copy, bucket_cap_mb, bucket_wire_dtype)
     if process_set != global_process_set:
         raise NotImplementedError("Adasum does not support non-global process sets yet.")
     cls = type(optimizer.__class__.__name__, (optimizer.__class__,), dict(_DistributedAdasumOptimizer.__dict__))
