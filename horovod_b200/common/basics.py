@@ -139,7 +139,9 @@ class HorovodBasics(object):
         there is no MPI in this build). `process_sets`: list of ProcessSet objects / rank lists registered statically,
         or the string "dynamic" to enable add_process_set()/remove_process_set() at runtime (always enabled here)."""
         if self.is_initialized():
-            return
+            if self.lib.hvd_is_running():
+                return
+            self.lib.hvd_shutdown()  # the loop ended on its own (peer shutdown / failure): start from scratch
         if comm is not None and not isinstance(comm, (list, tuple)):
             raise ValueError("hvd.init(comm=...) only accepts a list of ranks in this build (no MPI).")
         rank, size, local_rank, local_size, cross_rank, cross_size = _resolve_topology()

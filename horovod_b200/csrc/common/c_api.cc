@@ -44,6 +44,7 @@ int hvd_init(int rank, int size, int local_rank, int local_size, int cross_rank,
 
 void hvd_shutdown() { Engine::Get().Shutdown(); }
 int hvd_is_initialized() { return Engine::Get().initialized() ? 1 : 0; }
+int hvd_is_running() { return Engine::Get().running() ? 1 : 0; }  // false once the loop ended (peer shutdown / failure)
 int hvd_rank() { return Engine::Get().initialized() ? Engine::Get().rank() : -1; }
 int hvd_size() { return Engine::Get().initialized() ? Engine::Get().size() : -1; }
 int hvd_local_rank() { return Engine::Get().initialized() ? Engine::Get().local_rank() : -1; }

@@ -65,7 +65,9 @@ Engine& Engine::Get() { static Engine* e = new Engine(); return *e; }  // leaked
 // init / shutdown
 
 Status Engine::Init(const InitConfig& cfg) {
-  if (initialized_.load()) return Status::OK();
+  // already running -> no-op.  A loop that ended on its own (a peer shut the job down, or it failed) leaves the rank /
+  // size queries valid until the local shutdown, like the reference; a new init() then starts a fresh runtime.
+  if (initialized_.load() && !loop_exited_.load()) return Status::OK();
   if (thread_.joinable()) thread_.join();
   cfg_ = cfg;
   init_done_ = false; init_failed_ = false; shutdown_requested_ = false; loop_exited_ = false;
@@ -251,7 +253,6 @@ void Engine::BackgroundThread() {
   sets_.Clear();
   transport_.reset();
   loop_exited_ = true;
-  initialized_ = false;
 }
 
 // ---------------------------------------------------------------------------

@@ -46,6 +46,7 @@ class Engine {
   Status Init(const InitConfig& cfg);
   void Shutdown();
   bool initialized() const { return initialized_.load(); }
+  bool running() const { return initialized_.load() && !loop_exited_.load(); }  // the background loop is alive
 
   int rank() const { return cfg_.rank; }
   int size() const { return cfg_.size; }

@@ -148,6 +148,7 @@ def _train_fn(model_bytes, opt_cls, opt_defaults, loss_fn, feature_cols, label_c
         if ckpt_path and hvd.rank() == 0:
             store.write(ckpt_path, _serialize({'model': model.state_dict(), 'optimizer': opt.state_dict(), 'epoch': epoch}))
     state = {k: v.cpu() for k, v in model.state_dict().items()} if hvd.rank() == 0 else None
+    hvd.barrier()  # shutdown is job-wide: nobody leaves while a peer still talks to the runtime
     hvd.shutdown()
     return {'history': history, 'state_dict': state}
 

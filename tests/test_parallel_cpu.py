@@ -111,3 +111,10 @@ def test_init_with_rank_subset_np3(native_built):
     a non-member is rejected (reference: common/basics.py init(comm=<rank list>))."""
     rc, out = run_parallel("comm_subset_worker.py", np=3, timeout=200)
     assert out.count("COMM SUBSET OK") == 3, out[-3000:]
+
+
+def test_peer_shutdown_semantics_np2(native_built):
+    """One rank shuts the job down: the other rank's rank()/size() stay valid until ITS shutdown, collectives fail with the
+    shut-down error (reference operations.cc: initialization_done survives the loop exit)."""
+    rc, out = run_parallel("peer_shutdown_worker.py", np=2, timeout=120)
+    assert "rank0 done" in out and "rank1 done" in out, out[-3000:]
