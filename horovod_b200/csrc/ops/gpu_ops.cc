@@ -330,7 +330,7 @@ std::string GpuOps::Describe(ProcessSet& ps) {
 // allreduce
 
 Status GpuOps::Allreduce(ProcessSet& ps, Entries& es, const Response& r, int device, SharedEvent** done) {
-  const int me = ps.set_rank(), n = ps.set_size();
+  const int n = ps.set_size();
   HVD_CUDA(cudaSetDevice(device));
   GpuContext& ctx = GpuContext::Get();
   cudaStream_t s = ctx.Stream(device);

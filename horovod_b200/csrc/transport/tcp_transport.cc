@@ -82,7 +82,7 @@ void ReadAll(int fd, void* buf, size_t n) {
 
 class TcpTransport : public Transport {
  public:
-  TcpTransport(int rank, int size) : rank_(rank), size_(size), fds_(size, -1) {}
+  TcpTransport(int rank, int size) : fds_(size, -1), rank_(rank), size_(size) {}
   ~TcpTransport() override {
     for (int fd : fds_) if (fd >= 0) { shutdown(fd, SHUT_RDWR); close(fd); }
   }
