@@ -91,7 +91,7 @@ ResponseList Controller::ComputeResponseList(bool shutdown_requested) {
   for (auto& kv : pending_hits_) { SetBit(and_words, 0, kv.first); SetBit(or_words, 1 + nw, kv.first); }
   if (local_joined_) std::fill(and_words.begin(), and_words.end(), ~0ull);
   for (uint32_t b : invalid_bits) SetBit(or_words, 1, b);
-  if (shutdown_requested) or_words[0] |= kStatusShutdown;
+  if (shutdown_requested || stall_shutdown_) or_words[0] |= kStatusShutdown;
   if (!uncached.empty()) or_words[0] |= kStatusUncached;
   if (!invalid_bits.empty()) or_words[0] |= kStatusInvalid;
   transport_->AllreduceBits(and_words.data(), (int)nw, or_words.data(), (int)or_words.size());
@@ -178,6 +178,9 @@ ResponseList Controller::ComputeResponseList(bool shutdown_requested) {
       responses.push_back(std::move(resp));
     }
   } else if (stall_.enabled() && stall_.ShouldPerformCheck()) {
+    // quiet cycle (nobody has new uncached requests): this is exactly when a stalled tensor sits at the coordinator, so
+    // the check must run here as well; a shutdown decision reaches the other ranks through next cycle's status bits
+    if (is_coordinator() && stall_.CheckForStalledTensors(size(), joined_ranks_)) stall_shutdown_ = true;
     stall_.UpdateCheckTime();
   }
 

@@ -84,6 +84,7 @@ class Controller {
   ResponseCache* cache_;
   Timeline* timeline_;
   StallInspector stall_;
+  bool stall_shutdown_ = false;  // coordinator: the stall inspector asked for a job-wide shutdown
 
   int64_t fusion_threshold_ = 128ll << 20;
   bool cache_enabled_ = true;

@@ -323,6 +323,7 @@ bool Engine::RunLoopOnce() {
     if (rl.responses.empty()) ++fast_cycles_;
     for (auto& r : rl.responses) PerformOperation(*ps, r);
     if (id == 0 && rl.shutdown) keep_going = false;
+    else if (rl.shutdown) shutdown_requested_ = true;  // a sub-set's stall inspector gave up: take the job down through the global set
   }
   if (params_.IsAutoTuning() || tp.active) {
     auto g = sets_.Get(0);

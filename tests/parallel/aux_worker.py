@@ -1,0 +1,53 @@
+"""Auxiliary subsystems end to end: stall inspector (warning + shutdown), autotuner log, timeline file."""
+import json
+import os
+import sys
+import time
+
+import torch
+
+import horovod_b200.torch as hvd
+from horovod_b200.common.exceptions import HorovodInternalError
+
+mode = sys.argv[1]
+hvd.init()
+r, n = hvd.rank(), hvd.size()
+if mode == 'stall_warning':
+    # rank 1 submits late: rank 0 (coordinator) must warn and name the missing rank, then the op completes
+    if r != 0:
+        time.sleep(3.5)
+    out = hvd.allreduce(torch.ones(2), op=hvd.Sum, name='late.tensor')
+    assert out.tolist() == [float(n)] * 2
+    print('STALL WARNING DONE', r, flush=True)
+elif mode == 'stall_shutdown':
+    if r == 0:
+        try:
+            hvd.allreduce(torch.ones(2), op=hvd.Sum, name='never.matched')
+            raise AssertionError('must fail')
+        except HorovodInternalError as e:
+            print('STALL SHUTDOWN RAISED', str(e)[:80].replace('\n', ' '), flush=True)
+    else:
+        time.sleep(6)
+        try:
+            hvd.allreduce(torch.ones(2), op=hvd.Sum, name='other.name')
+        except HorovodInternalError:
+            pass
+        print('PEER SAW SHUTDOWN', flush=True)
+elif mode == 'autotune':
+    x = torch.ones(1 << 14)
+    for step in range(400):
+        hs = [hvd.allreduce_async(x, op=hvd.Sum, name=f'at.{i}') for i in range(4)]
+        for h in hs:
+            hvd.synchronize(h)
+    print('AUTOTUNE PARAMS', json.dumps(hvd.tunable_params()), flush=True)
+elif mode == 'timeline':
+    path = sys.argv[2]
+    hvd.start_timeline(path, mark_cycles=True)
+    for i in range(5):
+        hvd.allreduce(torch.ones(64), name='tl.ar')
+        hvd.allgather(torch.ones(2, 2), name='tl.ag')
+    hvd.barrier()
+    hvd.stop_timeline()
+    hvd.barrier()
+    print('TIMELINE DONE', flush=True)
+hvd.shutdown()
