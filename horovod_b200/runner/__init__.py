@@ -76,6 +76,25 @@ class _HorovodArgs(object):
         self.np = v
 
 
+def _pickle_by_value_if_not_importable(func):
+    """Workers unpickle the function in a fresh interpreter.  A function defined in a script or a test module that is not
+    on the workers' import path would be pickled by reference and fail there with ModuleNotFoundError; such modules are
+    shipped by value instead (what cloudpickle already does for `__main__`)."""
+    import sys
+    import cloudpickle
+    name = getattr(func, '__module__', None)
+    mod = sys.modules.get(name)
+    if not name or name == '__main__' or mod is None or name.split('.')[0] == 'horovod_b200':
+        return
+    path = getattr(mod, '__file__', '') or ''
+    in_site = any(part in path for part in ('site-packages', 'dist-packages'))
+    if not in_site and hasattr(cloudpickle, 'register_pickle_by_value'):
+        try:
+            cloudpickle.register_pickle_by_value(mod)
+        except Exception:  # noqa: BLE001 - best effort; the by-reference pickle still works when the module is importable
+            pass
+
+
 def run(func, args=(), kwargs=None, np=1, min_np=None, max_np=None, slots=None, reset_limit=None, cooldown_range=None,
         hosts=None, hostfile=None, start_timeout=None, ssh_port=None, ssh_identity_file=None, disable_cache=None,
         output_filename=None, verbose=None, use_gloo=None, use_mpi=None, mpi_args=None, network_interfaces=None,
@@ -87,6 +106,8 @@ def run(func, args=(), kwargs=None, np=1, min_np=None, max_np=None, slots=None, 
 
     def wrapped_func():
         return func(*args, **kwargs)
+
+    _pickle_by_value_if_not_importable(func)
 
     hargs = _HorovodArgs()
     hargs.np = np

@@ -1,0 +1,82 @@
+"""`hvdrun` end to end on localhost (reference coverage model: test/integration/test_static_run.py): output capture
+files, rank prefixes, timestamps, exit-code propagation, slot validation, env forwarding, run-func API."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import REPO
+
+
+def hvdrun(*args, timeout=120, env=None):
+    e = dict(os.environ, PYTHONPATH=REPO + os.pathsep + os.environ.get('PYTHONPATH', ''), HOROVOD_LOG_LEVEL='warning')
+    e.update(env or {})
+    p = subprocess.run([sys.executable, '-m', 'horovod_b200.runner.launch', *args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       env=e, timeout=timeout, cwd=REPO)
+    return p.returncode, p.stdout.decode(errors='replace')
+
+
+PRINT_RANK = "import os; print('hello from', os.environ['HOROVOD_RANK'], 'of', os.environ['HOROVOD_SIZE'], os.environ.get('HVD_T_FORWARD', '-'))"
+
+
+def test_rank_prefixes_and_env_forwarding(native_built):
+    rc, out = hvdrun('-np', '2', sys.executable, '-c', PRINT_RANK, env={'HVD_T_FORWARD': 'forwarded'})
+    assert rc == 0, out
+    assert '[0]<stdout>:hello from 0 of 2 forwarded' in out and '[1]<stdout>:hello from 1 of 2 forwarded' in out, out
+
+
+def test_output_filename_writes_per_rank_files(native_built, tmp_path):
+    d = tmp_path / 'logs'
+    code = "import os, sys; print('to stdout', os.environ['HOROVOD_RANK']); print('to stderr', file=sys.stderr)"
+    rc, out = hvdrun('-np', '2', '--output-filename', str(d), sys.executable, '-c', code)
+    assert rc == 0, out
+    for r in (0, 1):
+        so = (d / f'rank.{r}' / 'stdout').read_text()
+        se = (d / f'rank.{r}' / 'stderr').read_text()
+        assert f'to stdout {r}' in so and 'to stderr' in se, (so, se)
+
+
+def test_timestamp_prefix(native_built):
+    import time
+    rc, out = hvdrun('-np', '1', '--prefix-output-with-timestamp', sys.executable, '-c', "print('stamped')")
+    assert rc == 0 and 'stamped' in out
+    line = [l for l in out.splitlines() if 'stamped' in l][0]
+    assert time.strftime('%Y') in line and '[0]<stdout>:stamped' in line, line
+
+
+def test_nonzero_exit_code_is_reported(native_built):
+    code = "import os, sys, time; r = int(os.environ['HOROVOD_RANK']); time.sleep(0.5 if r else 30) if r == 0 else None; sys.exit(3 if r == 1 else 0)"
+    rc, out = hvdrun('-np', '2', sys.executable, '-c', code, timeout=60)
+    assert rc != 0
+    assert 'exited with non-zero status' in out and 'Exit code: 3' in out and 'Process name: 1' in out, out
+
+
+def test_more_processes_than_slots_is_rejected(native_built):
+    rc, out = hvdrun('-np', '3', '-H', 'localhost:2', sys.executable, '-c', 'print(1)')
+    assert rc != 0 and 'Requested more processes (3) than there are available slots (2)' in out, out
+    rc, out = hvdrun('-np', '2', '-H', 'localhost', sys.executable, '-c', 'print(1)')
+    assert rc != 0 and 'Invalid host input' in out, out
+
+
+def test_version_and_missing_command(native_built):
+    rc, out = hvdrun('--version')
+    assert rc == 0 and out.strip()
+    rc, out = hvdrun('-np', '1')
+    assert rc != 0 and 'command' in out.lower(), out
+
+
+def _fn(a, b=0):
+    import horovod_b200.torch as hvd
+    hvd.init()
+    r = hvd.rank()
+    hvd.shutdown()
+    return (r, a + b)
+
+
+def test_run_func_api_returns_rank_ordered_results(native_built):
+    import horovod_b200
+    res = horovod_b200.run(_fn, args=(10,), kwargs={'b': 5}, np=2)
+    assert res == [(0, 15), (1, 15)]
+    with pytest.raises(Exception):
+        horovod_b200.run(lambda: 1 / 0, np=2)
