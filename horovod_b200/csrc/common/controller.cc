@@ -69,10 +69,14 @@ ResponseList Controller::ComputeResponseList(bool shutdown_requested) {
   }
   // Cached tensors that never became globally ready: push them to the
   // coordinator so the stall inspector can name the missing ranks.
-  if (stall_.enabled() && !pending_hits_.empty() && stall_.ShouldPerformCheck()) {
+  // Decided ONCE per cycle: the cycle blocks in the bit exchange below, so a second look at the clock further down would
+  // usually be the one that sees the interval expire and this block would never run.
+  const bool stall_check_now = stall_.enabled() && stall_.ShouldPerformCheck();
+  if (stall_check_now && !pending_hits_.empty()) {
     std::vector<std::string> stalled;
     stall_.CollectStalledCachedTensors(&stalled);
     for (auto& n : stalled) {
+      LOG(DEBUG) << "cached tensor " << n << " is not ready everywhere after the stall-warning time: renegotiating it through the coordinator";
       uint32_t bit = cache_->PeekBit(n);
       auto it = bit == UINT32_MAX ? pending_hits_.end() : pending_hits_.find(bit);
       if (it != pending_hits_.end()) {
@@ -146,7 +150,7 @@ ResponseList Controller::ComputeResponseList(bool shutdown_requested) {
         for (auto& q : rl.requests) CoordinatorHandleRequest(q, r);
       }
       CoordinatorCollectReady(&fresh.responses);
-      if (stall_.enabled() && stall_.ShouldPerformCheck()) {
+      if (stall_check_now) {
         if (stall_.CheckForStalledTensors(size(), joined_ranks_)) fresh.shutdown = true;
         stall_.UpdateCheckTime();
       }
@@ -177,7 +181,7 @@ ResponseList Controller::ComputeResponseList(bool shutdown_requested) {
       }
       responses.push_back(std::move(resp));
     }
-  } else if (stall_.enabled() && stall_.ShouldPerformCheck()) {
+  } else if (stall_check_now) {
     // quiet cycle (nobody has new uncached requests): this is exactly when a stalled tensor sits at the coordinator, so
     // the check must run here as well; a shutdown decision reaches the other ranks through next cycle's status bits
     if (is_coordinator() && stall_.CheckForStalledTensors(size(), joined_ranks_)) stall_shutdown_ = true;

@@ -19,6 +19,15 @@ if mode == 'stall_warning':
     out = hvd.allreduce(torch.ones(2), op=hvd.Sum, name='late.tensor')
     assert out.tolist() == [float(n)] * 2
     print('STALL WARNING DONE', r, flush=True)
+elif mode == 'stall_cached':
+    # the tensor is in the response cache (fast path, no coordinator involved); a late rank must still be reported
+    for _ in range(4):
+        hvd.allreduce(torch.ones(2), op=hvd.Sum, name='cached.tensor')
+    if r != 0:
+        time.sleep(3.5)
+    out = hvd.allreduce(torch.ones(2), op=hvd.Sum, name='cached.tensor')
+    assert out.tolist() == [float(n)] * 2
+    print('STALL CACHED DONE', r, flush=True)
 elif mode == 'stall_shutdown':
     if r == 0:
         try:

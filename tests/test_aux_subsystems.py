@@ -13,6 +13,23 @@ def test_stall_inspector_warns_and_names_missing_rank(native_built):
     assert "waiting for remainder of ranks" in out and "late.tensor: [1]" in out, out[-3000:]
 
 
+def test_stall_inspector_reports_cached_tensors(native_built):
+    rc, out = run_parallel("aux_worker.py", np=2, timeout=120, args=["stall_cached"],
+                           env={"HOROVOD_STALL_CHECK_TIME_SECONDS": "1", "HOROVOD_LOG_LEVEL": "warning"})
+    assert out.count("STALL CACHED DONE") == 2, out[-3000:]
+    assert "waiting for remainder of ranks" in out and "cached.tensor: [1]" in out, out[-3000:]
+
+
+def test_static_timeline_env(native_built, tmp_path):
+    path = tmp_path / "static_timeline.json"
+    rc, out = run_parallel("aux_worker.py", np=2, timeout=120, args=["stall_warning"],
+                           env={"HOROVOD_TIMELINE": str(path), "HOROVOD_STALL_CHECK_DISABLE": "1"})
+    assert out.count("STALL WARNING DONE") == 2
+    raw = path.read_text().strip()
+    events = json.loads(raw if raw.endswith("]") else raw.rstrip(",") + "]")
+    assert any(isinstance(e, dict) and "ALLREDUCE" in str(e.get("name")) for e in events)
+
+
 def test_stall_inspector_shutdown(native_built):
     rc, out = run_parallel("aux_worker.py", np=2, timeout=120, args=["stall_shutdown"], expect_fail=True,
                            env={"HOROVOD_STALL_CHECK_TIME_SECONDS": "1", "HOROVOD_STALL_SHUTDOWN_TIME_SECONDS": "3",
