@@ -67,3 +67,10 @@ def test_hierarchical_allreduce_fake_hosts(native_built):
 def test_extra_reference_cases_cuda(native_built):
     rc, out = run_parallel("ops_worker_extra.py", np=2, timeout=300, args=["--device", "cuda"])
     assert "EXTRA ALL OK" in out, out[-4000:]
+
+
+@_NEW
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+def test_op_api_edge_cases_cuda(native_built):
+    rc, out = run_parallel("edge_worker.py", np=2, timeout=300, args=["cuda"], env={"HOROVOD_FUSION_THRESHOLD": "65536"})
+    assert "EDGE OK" in out, out[-4000:]

@@ -118,3 +118,11 @@ def test_peer_shutdown_semantics_np2(native_built):
     shut-down error (reference operations.cc: initialization_done survives the loop exit)."""
     rc, out = run_parallel("peer_shutdown_worker.py", np=2, timeout=120)
     assert "rank0 done" in out and "rank1 done" in out, out[-3000:]
+
+
+@pytest.mark.parametrize("np_", [2, 3])
+def test_op_api_edge_cases(native_built, np_):
+    """Empty / 0-dim / bool tensors, 300 ops in flight, tensors above a 64 KiB fusion threshold, name reuse across op
+    types, non-contiguous inputs, exact int64 sums."""
+    rc, out = run_parallel("edge_worker.py", np=np_, timeout=200, env={"HOROVOD_FUSION_THRESHOLD": "65536"})
+    assert "EDGE OK" in out, out[-3000:]
