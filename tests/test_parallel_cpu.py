@@ -126,3 +126,10 @@ def test_op_api_edge_cases(native_built, np_):
     types, non-contiguous inputs, exact int64 sums."""
     rc, out = run_parallel("edge_worker.py", np=np_, timeout=200, env={"HOROVOD_FUSION_THRESHOLD": "65536"})
     assert "EDGE OK" in out, out[-3000:]
+
+
+def test_join_with_cached_responses_np3(native_built):
+    """Ranks that joined keep serving responses that live in the cache (bit-vector fast path): the active rank's sums contain
+    only its own contribution, Average still divides by the full size, and the cache entry survives the join."""
+    rc, out = run_parallel("join_cached_worker.py", np=3, timeout=120)
+    assert "JOIN CACHED OK" in out, out[-3000:]
