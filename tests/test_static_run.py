@@ -80,3 +80,20 @@ def test_run_func_api_returns_rank_ordered_results(native_built):
     assert res == [(0, 15), (1, 15)]
     with pytest.raises(Exception):
         horovod_b200.run(lambda: 1 / 0, np=2)
+
+
+def test_hard_crash_of_one_worker_terminates_the_job(native_built):
+    """kill -9 of one rank while the other sits in a collective: the launcher tears the job down and reports the signal."""
+    import time
+    code = ("import os, signal, time, torch\n"
+            "import horovod_b200.torch as hvd\n"
+            "hvd.init()\n"
+            "hvd.allreduce(torch.ones(2))\n"
+            "if hvd.rank() == 1:\n"
+            "    os.kill(os.getpid(), signal.SIGKILL)\n"
+            "hvd.allreduce(torch.ones(2), name='never')\n"
+            "time.sleep(60)\n")
+    t0 = time.time()
+    rc, out = hvdrun('-np', '2', sys.executable, '-c', code, timeout=90)
+    assert rc != 0 and time.time() - t0 < 60, out
+    assert 'Process name: 1' in out and ('Exit code: 137' in out or 'Exit code: -9' in out), out
