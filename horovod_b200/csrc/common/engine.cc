@@ -815,7 +815,7 @@ int32_t Engine::RemoveProcessSet(int32_t id, std::string* err) {
 
 // Collective (every member of the set must call it with the same size): allocates `bytes` of peer-mapped memory on
 // `device` and returns its local address. Tensors placed there take the zero-copy allreduce path.
-void* Engine::AllocSymmetric(size_t bytes, int device, int32_t psid, std::string* err) {
+void* Engine::AllocSymmetric(size_t bytes, int device, int32_t psid, std::string* err, std::shared_ptr<void>* keep_alive) {
   std::shared_ptr<ProcessSet> ps;
   Status st = CheckSet(psid, &ps);
   if (!st.ok()) { if (err) *err = st.reason(); return nullptr; }
@@ -833,6 +833,10 @@ void* Engine::AllocSymmetric(size_t bytes, int device, int32_t psid, std::string
   RequestFlush();
   Completion c = fut.get();
   if (!c.status.ok()) { if (err) *err = c.status.reason(); return nullptr; }
+  if (keep_alive) {
+    std::lock_guard<std::mutex> l(ps->team_mu);
+    if (ps->team) *keep_alive = ps->team->KeepAlive();
+  }
   return c.aux_ptr;
 }
 

@@ -77,7 +77,8 @@ class Engine {
   int32_t RemoveProcessSet(int32_t id, std::string* err);
   ProcessSetTable& process_sets() { return sets_; }
   // Collective allocation of registered (peer-mapped) memory; returns the local address or nullptr (+err).
-  void* AllocSymmetric(size_t bytes, int device, int32_t process_set_id, std::string* err);
+  // `keep_alive` (optional) receives a token that keeps the region mapped for as long as the caller holds it
+  void* AllocSymmetric(size_t bytes, int device, int32_t process_set_id, std::string* err, std::shared_ptr<void>* keep_alive = nullptr);
 
   // ---- timeline ----
   Status StartTimeline(const std::string& file, bool mark_cycles);

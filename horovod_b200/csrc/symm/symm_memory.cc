@@ -259,6 +259,8 @@ struct SymmTeam::Impl {
 
 SymmTeam::~SymmTeam() = default;
 
+std::shared_ptr<void> SymmTeam::KeepAlive() const { return std::static_pointer_cast<void>(impl_); }
+
 kern::CommParams SymmTeam::Params(int which) const {
   kern::CommParams cp {};
   cp.nranks = nranks_;

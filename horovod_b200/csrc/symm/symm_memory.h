@@ -95,6 +95,11 @@ class SymmTeam {
   std::string backend_;
   std::vector<RegionView> regions_;
   std::shared_ptr<Impl> impl_;  // owns driver handles / mappings
+
+ public:
+  // Token that keeps every mapping of this team alive (framework tensors placed in registered regions hold one, so a
+  // tensor that outlives hvd.shutdown() / an elastic reset never points at unmapped memory).
+  std::shared_ptr<void> KeepAlive() const;
 };
 
 }  // namespace hvd

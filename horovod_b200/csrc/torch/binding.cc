@@ -430,13 +430,16 @@ at::Tensor SymmEmpty(int64_t nbytes, int device, int process_set_id) {
   TORCH_CHECK(nbytes > 0, "symm_empty: size must be positive");
   std::string err;
   void* p = nullptr;
+  std::shared_ptr<void> keep;
   {
     py::gil_scoped_release release;
-    p = Engine::Get().AllocSymmetric((size_t)nbytes, device, process_set_id, &err);
+    p = Engine::Get().AllocSymmetric((size_t)nbytes, device, process_set_id, &err, &keep);
   }
   if (!p) throw std::runtime_error("symm_empty failed: " + err);
   auto opts = at::TensorOptions().dtype(at::kByte).device(at::kCUDA, device);
-  return at::from_blob(p, {nbytes}, [](void*) {}, opts);
+  // the tensor co-owns the team's mappings: it stays valid memory after hvd.shutdown() / an elastic reset (it then simply
+  // is no longer registered with the new team and takes the packed path)
+  return at::from_blob(p, {nbytes}, [keep](void*) mutable { keep.reset(); }, opts);
 }
 
 // ---- fused optimizer kernels (B200-native extra; see kernels/optim_kernels.cu) --------------
