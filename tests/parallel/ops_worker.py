@@ -19,6 +19,7 @@ from horovod_b200.common.exceptions import HorovodInternalError
 p = argparse.ArgumentParser()
 p.add_argument('--device', default='cpu')
 p.add_argument('--only', default='')
+p.add_argument('--skip', default='')
 args = p.parse_args()
 
 import os
@@ -578,6 +579,39 @@ def _():
         torch.testing.assert_close(hvd.synchronize(h), torch.full((16,), float(i + 1), device=DEV), rtol=1e-4, atol=1e-4)
 
 
+@check('adasum_stability')
+def _():
+    # every rank holds a multiple of the same direction, with magnitudes (a) near the smallest normal number of the dtype and
+    # (b) spread geometrically from tiny to sqrt(max): the dot products / norms must not underflow or overflow, and Adasum of
+    # parallel vectors is their average (reference test_adasum_pytorch.py::test_stability, ::test_stability_2)
+    if size & (size - 1):
+        return
+    import math
+    import numpy as np
+    dtypes = [(torch.float32, np.float32)]  # like the reference: fp32 (+ fp16 on GPUs); the accumulators are fp64
+    if DEV.type == 'cuda':
+        dtypes.append((torch.float16, np.float16))
+    for tdt, ndt in dtypes:
+        rng = np.random.RandomState(2)
+        N = 1024
+        tiny, big = float(np.finfo(ndt).tiny), math.sqrt(float(np.finfo(ndt).max))
+        a1 = rng.normal(0, tiny, (N, 1))
+        r1 = rng.normal(0, 1, (size, 1))
+        a2 = rng.normal(0, 1, (N, 1))
+        r2 = np.array([big ** ((i + 1) / size) * tiny ** ((size - i - 1) / size) for i in range(size)]).reshape(size, 1)
+        rng.shuffle(r2)
+        for tag, a, rr in (('tiny', a1, r1), ('spread', a2, r2)):
+            q = np.dot(a, rr.T).astype(ndt).astype(np.float64)
+            t = torch.from_numpy(q[:, rank].astype(ndt)).to(DEV)
+            hvd.allreduce_(t, op=hvd.Adasum, name=f'adasum.stab.{tag}.{tdt}')
+            expected = q.sum(axis=1) / size
+            got = t.double().cpu().numpy()
+            denom = np.linalg.norm(expected)
+            ratio = np.linalg.norm(expected - got) / denom if denom > 0 else np.linalg.norm(got)
+            limit = {np.float16: 1e-2, np.float32: 1e-4, np.float64: 1e-8}[ndt]
+            assert ratio < limit, (tag, tdt, ratio)
+
+
 @check('adasum_whole_model')
 def _():
     # graph-mode Adasum optimizer (one wrapped-optimizer step for the whole model, then all deltas) == per-parameter hooks
@@ -681,8 +715,9 @@ def _():
 
 failed = []
 only = set(args.only.split(',')) if args.only else None
+skip = set(args.skip.split(',')) if args.skip else set()
 for fn in CHECKS:
-    if only and fn._check_name not in only:
+    if (only and fn._check_name not in only) or fn._check_name in skip:
         continue
     t0 = time.time()
     try:
