@@ -133,3 +133,10 @@ def test_join_with_cached_responses_np3(native_built):
     only its own contribution, Average still divides by the full size, and the cache entry survives the join."""
     rc, out = run_parallel("join_cached_worker.py", np=3, timeout=120)
     assert "JOIN CACHED OK" in out, out[-3000:]
+
+
+def test_static_process_sets_np4(native_built):
+    """hvd.init(process_sets=[even, odd]): ids, membership, collectives inside a set, non-member rejection, duplicate
+    rejection, re-init with the same static sets."""
+    rc, out = run_parallel("static_sets_worker.py", np=4, timeout=200)
+    assert "STATIC SETS OK" in out, out[-3000:]
