@@ -1,0 +1,282 @@
+"""DataFrame -> Parquet shards in the Store, with metadata and a cache of already materialised DataFrames.
+
+Role parity: horovod/spark/common/util.py (`prepare_data` :686-741, `_get_or_create_dataset` :560-660, `check_validation`
+:525-541, `get_simple_meta_from_parquet` :400-470, `to_list` / vector handling :150-260) and common/cache.py
+(`TrainingDataCache`).  The reference writes Parquet for Petastorm and keeps Petastorm metadata; here the shards are read
+back by `horovod_b200.spark.data_loaders` (pyarrow.dataset), the metadata is computed from the Parquet schema and the
+first row group, and the input can be a Spark or a pandas DataFrame.
+"""
+import contextlib
+import os
+import threading
+import uuid
+import weakref
+
+import numpy as np
+
+
+def is_spark_df(df):
+    return type(df).__module__.startswith('pyspark.')
+
+
+def check_columns(df, columns, what):
+    have = set(df.columns)
+    missing = [c for c in columns if c not in have]
+    if missing:
+        raise ValueError('%s column(s) %s not found in the DataFrame (columns: %s)' % (what, missing, sorted(have)))
+
+
+def check_validation(validation, df=None):
+    """`validation` is None, a fraction in [0, 1) or the name of a boolean-ish column."""
+    if validation is None:
+        return
+    if isinstance(validation, str):
+        if df is not None and validation not in df.columns:
+            raise ValueError('Validation column "%s" does not exist in the DataFrame' % validation)
+        return
+    if isinstance(validation, bool) or not isinstance(validation, (int, float)):
+        raise ValueError('Param validation must be of type "float" or "str", found: %s' % type(validation))
+    if not 0 <= validation < 1:
+        raise ValueError('Validation split %s must be in the range: [0, 1)' % validation)
+
+
+def split_validation(df, validation, seed):
+    """-> (train_df, val_df or None)."""
+    if validation is None or validation == 0:
+        return df, None
+    if isinstance(validation, str):
+        if is_spark_df(df):
+            flag = df[validation].cast('boolean')
+            return df.filter(~flag).drop(validation), df.filter(flag).drop(validation)
+        mask = df[validation].astype(bool)
+        return df[~mask].drop(columns=[validation]), df[mask].drop(columns=[validation])
+    frac = float(validation)
+    if is_spark_df(df):
+        train, val = df.randomSplit([1 - frac, frac], seed=seed)
+        return train, val
+    val = df.sample(frac=frac, random_state=seed)
+    return df.drop(val.index), val
+
+
+def _densify(value):
+    """Spark ML vectors (DenseVector / SparseVector), numpy arrays and nested lists -> plain nested lists."""
+    if hasattr(value, 'toArray'):
+        return value.toArray().tolist()
+    if isinstance(value, np.ndarray):
+        return value.tolist()
+    return value
+
+
+def _pandas_to_table(pdf, columns):
+    import pyarrow as pa
+    data = {}
+    for c in columns:
+        col = pdf[c]
+        first = col.iloc[0] if len(col) else None
+        if hasattr(first, 'toArray') or isinstance(first, (np.ndarray, list, tuple)):
+            data[c] = pa.array([_densify(v) for v in col])
+        else:
+            data[c] = pa.array(col.to_numpy())
+    return pa.table(data)
+
+
+def write_parquet(df, path, store, num_files, columns=None):
+    """Writes `df[columns]` as `num_files` Parquet files under `path`; returns the row count."""
+    store.delete(path)
+    if is_spark_df(df):
+        out = df.select(*columns) if columns else df
+        vector_cols = [f.name for f in out.schema.fields if type(f.dataType).__name__ == 'VectorUDT']
+        if vector_cols:
+            from pyspark.ml.functions import vector_to_array
+            for c in vector_cols:
+                out = out.withColumn(c, vector_to_array(out[c]))
+        out.repartition(num_files).write.mode('overwrite').parquet(path)
+        return out.count()
+    import pyarrow.parquet as pq
+    cols = list(columns) if columns else list(df.columns)
+    table = _pandas_to_table(df, cols)
+    local = store._local(path)
+    store.fs.create_dir(local, recursive=True)
+    rows = table.num_rows
+    per_file = -(-rows // num_files) if rows else 0
+    for i in range(num_files):
+        if i * per_file < rows:
+            pq.write_table(table.slice(i * per_file, per_file), os.path.join(local, 'part-%05d.parquet' % i), filesystem=store.fs)
+    return rows
+
+
+def parquet_metadata(store, path):
+    """{'rows': N, 'avg_row_size': bytes, 'columns': {name: {'dtype': numpy dtype name, 'shape': per-row shape or None}}}.
+    The per-row shape of a list column comes from the first row (ragged columns report None)."""
+    import pyarrow.dataset as ds
+    dataset = ds.dataset(store._local(path), format='parquet', filesystem=store.fs)
+    rows = dataset.count_rows()
+    head = dataset.head(1)
+    total_bytes = 0
+    for frag in dataset.get_fragments():
+        md = frag.metadata
+        total_bytes += sum(md.row_group(i).total_byte_size for i in range(md.num_row_groups))
+    cols = {}
+    for name in head.schema.names:
+        values = head.column(name).to_pylist()
+        first = values[0] if values else None
+        if isinstance(first, (list, tuple)):
+            arr = np.asarray(first)
+            cols[name] = {'dtype': arr.dtype.name if arr.dtype != object else 'object',
+                          'shape': list(arr.shape) if arr.dtype != object else None}
+        else:
+            np_dtype = head.schema.field(name).type.to_pandas_dtype()
+            cols[name] = {'dtype': np.dtype(np_dtype).name if np_dtype is not object else 'object', 'shape': []}
+    return {'rows': rows, 'avg_row_size': (total_bytes / rows) if rows else 0, 'columns': cols}
+
+
+def check_shape_compatibility(metadata, feature_columns, label_columns, input_shapes=None, output_shapes=None, label_shapes=None):
+    """Every declared shape must hold exactly the number of elements a row of its column has (-1 = the batch dimension)."""
+    def count(shape):
+        n = 1
+        for d in shape:
+            n *= d if d != -1 else 1
+        return n
+
+    def check(kind, cols, shapes):
+        if shapes is None:
+            return
+        if len(shapes) != len(cols):
+            raise ValueError('%s column count %d must equal the number of %s shapes %d' % (kind, len(cols), kind, len(shapes)))
+        for col, shape in zip(cols, shapes):
+            row_shape = metadata['columns'][col]['shape']
+            if row_shape is None:
+                continue
+            if count(row_shape) != count(shape):
+                raise ValueError('%s column "%s" with %d elements per row does not match the declared shape %s'
+                                 % (kind, col, count(row_shape), list(shape)))
+    check('feature', feature_columns, input_shapes)
+    check('label', label_columns, label_shapes if label_shapes is not None else output_shapes)
+
+
+class PreparedDataset:
+    """What the estimators train on: Parquet paths in the store plus row counts and column metadata."""
+
+    def __init__(self, idx, train_path, val_path, train_rows, val_rows, metadata):
+        self.idx, self.train_path, self.val_path = idx, train_path, val_path
+        self.train_rows, self.val_rows, self.metadata = train_rows, val_rows, metadata
+
+    def __repr__(self):
+        return 'PreparedDataset(idx=%s, train_rows=%d, val_rows=%d)' % (self.idx, self.train_rows, self.val_rows)
+
+
+class _DatasetCache:
+    """Remembers which DataFrame objects are already materialised in which store so that fitting several models (a
+    hyper-parameter search) on the same DataFrame writes the Parquet once.  Entries die with their DataFrame."""
+
+    def __init__(self):
+        self._lock = threading.Lock()
+        self._entries = {}       # key -> (weakref to df or None, PreparedDataset, users)
+
+    @staticmethod
+    def _key(df, store, validation, columns, num_files):
+        return (id(df), getattr(store, 'prefix_path', id(store)), repr(validation), tuple(columns), num_files)
+
+    def lookup(self, df, store, validation, columns, num_files):
+        key = self._key(df, store, validation, columns, num_files)
+        with self._lock:
+            hit = self._entries.get(key)
+            if hit is None:
+                return key, None
+            ref, dataset, users = hit
+            if ref is not None and ref() is not df:          # the id was recycled by another object
+                del self._entries[key]
+                return key, None
+            if not store.exists(dataset.train_path):
+                del self._entries[key]
+                return key, None
+            self._entries[key] = (ref, dataset, users + 1)
+            return key, dataset
+
+    def insert(self, key, df, dataset):
+        try:
+            ref = weakref.ref(df)
+        except TypeError:
+            ref = None
+        with self._lock:
+            self._entries[key] = (ref, dataset, 1)
+
+    def release(self, key):
+        with self._lock:
+            hit = self._entries.get(key)
+            if hit:
+                self._entries[key] = (hit[0], hit[1], max(0, hit[2] - 1))
+
+    def clear(self, store=None):
+        """Forgets (and deletes from `store`) every materialised dataset nobody is training on."""
+        with self._lock:
+            for key, (ref, dataset, users) in list(self._entries.items()):
+                if users == 0:
+                    if store is not None:
+                        store.delete(dataset.train_path)
+                        if dataset.val_path:
+                            store.delete(dataset.val_path)
+                    del self._entries[key]
+
+
+_dataset_cache = _DatasetCache()
+
+
+def clear_training_cache(store=None):
+    _dataset_cache.clear(store)
+
+
+@contextlib.contextmanager
+def prepare_data(num_processes, store, df, label_columns, feature_columns, validation=None, sample_weight_col=None,
+                 partitions_per_process=1, random_seed=0, verbose=0, keep=True):
+    """Materialises `df` (split into train / validation) as Parquet in `store`; yields a PreparedDataset.
+
+    keep=True leaves the files in the store and remembers them for the next fit on the same DataFrame object;
+    keep=False deletes them when the block ends."""
+    check_validation(validation, df)
+    columns = list(feature_columns) + list(label_columns) + ([sample_weight_col] if sample_weight_col else [])
+    check_columns(df, columns, 'Training')
+    num_files = max(1, num_processes * partitions_per_process)
+    key, dataset = _dataset_cache.lookup(df, store, validation, columns, num_files)
+    if dataset is None:
+        idx = uuid.uuid4().hex[:8]
+        select = columns + ([validation] if isinstance(validation, str) else [])
+        train_df, val_df = split_validation(df[select] if not is_spark_df(df) else df.select(*select), validation, random_seed)
+        train_path, val_path = store.get_train_data_path(idx), store.get_val_data_path(idx)
+        train_rows = write_parquet(train_df, train_path, store, num_files, columns)
+        if train_rows < num_processes:
+            store.delete(train_path)
+            raise ValueError('%d training rows cannot be spread over %d processes' % (train_rows, num_processes))
+        val_rows = 0
+        if val_df is not None:
+            val_rows = write_parquet(val_df, val_path, store, num_files, columns)
+            if val_rows == 0:
+                store.delete(val_path)
+        dataset = PreparedDataset(idx, train_path, val_path if val_rows else None, train_rows, val_rows,
+                                  parquet_metadata(store, train_path))
+        if verbose:
+            print('prepared %s: %d train rows, %d validation rows, %.0f bytes/row' %
+                  (dataset.idx, train_rows, val_rows, dataset.metadata['avg_row_size']), flush=True)
+        if keep:
+            _dataset_cache.insert(key, df, dataset)
+    try:
+        yield dataset
+    finally:
+        if keep:
+            _dataset_cache.release(key)
+        else:
+            store.delete(dataset.train_path)
+            if dataset.val_path:
+                store.delete(dataset.val_path)
+
+
+def existing_dataset(store, dataset_idx=None):
+    """PreparedDataset for Parquet that is already in the store (`fit_on_parquet`)."""
+    train_path = store.get_train_data_path(dataset_idx)
+    if not store.exists(train_path) or not store.is_parquet_dataset(train_path):
+        raise ValueError('No Parquet training data at %s' % train_path)
+    val_path = store.get_val_data_path(dataset_idx)
+    has_val = store.exists(val_path) and store.is_parquet_dataset(val_path)
+    meta = parquet_metadata(store, train_path)
+    val_rows = parquet_metadata(store, val_path)['rows'] if has_val else 0
+    return PreparedDataset(dataset_idx, train_path, val_path if has_val else None, meta['rows'], val_rows, meta)
