@@ -7,7 +7,7 @@ from horovod_b200.tensorflow import (  # noqa: F401
     cross_rank, is_homogeneous, mpi_threads_supported, mpi_enabled, mpi_built, gloo_enabled, gloo_built, nccl_built,
     ddl_built, ccl_built, cuda_built, rocm_built, Average, Sum, Adasum, Min, Max, Product, global_process_set, ProcessSet,
     add_process_set, remove_process_set, Compression, broadcast_variables, broadcast_object, allgather_object,
-    SyncBatchNormalization, PartialDistributedGradientTape)
+    SyncBatchNormalization, PartialDistributedGradientTape, barrier)
 from horovod_b200.tensorflow.keras import callbacks, elastic  # noqa: F401
 
 
