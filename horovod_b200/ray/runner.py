@@ -85,7 +85,21 @@ class RayExecutor:
         return _Settings(timeout_s, ssh_identity_file, ssh_str, placement_group_timeout_s, nics)
 
     def __init__(self, settings=None, num_workers=None, num_hosts=None, num_workers_per_host=1, cpus_per_worker=1, use_gpu=False,
-                 gpus_per_worker=None, use_current_placement_group=True, backend=None, env_vars=None):
+                 gpus_per_worker=None, use_current_placement_group=True, backend=None, env_vars=None, min_workers=None,
+                 max_workers=None, reset_limit=None, cooldown_range=None, elastic_timeout=600, override_discovery=True,
+                 elastic_actor_factory=None):
+        self.elastic = min_workers is not None or max_workers is not None
+        if self.elastic:
+            if num_workers is not None or num_hosts is not None:
+                raise ValueError('`num_workers` / `num_hosts` describe a static job; use `min_workers` / `max_workers` alone for an elastic one.')
+            if min_workers is None or min_workers < 1:
+                raise ValueError('`min_workers` must be provided (>= 1) for an elastic job.')
+            if max_workers is not None and max_workers < min_workers:
+                raise ValueError('`max_workers` (%s) must not be smaller than `min_workers` (%s).' % (max_workers, min_workers))
+            self._elastic_args = dict(min_workers=min_workers, max_workers=max_workers, reset_limit=reset_limit,
+                                      cooldown_range=cooldown_range, elastic_timeout=elastic_timeout,
+                                      override_discovery=override_discovery, actor_factory=elastic_actor_factory)
+            num_workers = min_workers
         if num_workers is None and num_hosts is None:
             raise ValueError('Either `num_workers` or `num_hosts` must be set.')
         if num_workers is not None and num_hosts is not None:
@@ -107,15 +121,35 @@ class RayExecutor:
     def _placement(self):
         """(bundles, strategy, worker -> bundle index, per-worker resources)"""
         from horovod_b200.ray import strategy
-        per_worker = {'CPU': self.cpus_per_worker, **({'GPU': self.gpus_per_worker} if self.use_gpu else {})}
         if self.colocated:
-            bundles, strat = strategy.colocated_bundles(self.num_hosts, self.num_workers_per_host, self.cpus_per_worker, self.gpus_per_worker)
-            return bundles, strat, [i // self.num_workers_per_host for i in range(self.num_workers)], [per_worker] * self.num_workers
-        bundles, strat = strategy.pack_bundles(self.num_workers, self.cpus_per_worker, self.gpus_per_worker)
-        return bundles, strat, list(range(self.num_workers)), [per_worker] * self.num_workers
+            plan = strategy.ColocatedStrategy(self.num_hosts, self.num_workers_per_host, self.cpus_per_worker, self.gpus_per_worker)
+        else:
+            plan = strategy.PackStrategy(self.num_workers, self.cpus_per_worker, self.gpus_per_worker)
+        return plan.describe()
+
+    def _start_elastic(self, extra_env_vars):
+        from horovod_b200.ray.elastic import ElasticRayExecutor
+        a = self._elastic_args
+        settings = ElasticRayExecutor.create_settings(min_num_proc=a['min_workers'], max_num_proc=a['max_workers'],
+                                                      reset_limit=a['reset_limit'], elastic_timeout=a['elastic_timeout'],
+                                                      timeout_s=self.settings.timeout_s, nics=self.settings.nics,
+                                                      **({'cooldown_range': a['cooldown_range']} if a['cooldown_range'] else {}))
+        if not a['override_discovery']:
+            settings.discovery = getattr(self.settings, 'discovery', None)
+        env = dict(self.env_vars)
+        env.update(extra_env_vars or {})
+        self._elastic_executor = ElasticRayExecutor(settings, use_gpu=self.use_gpu, cpus_per_slot=self.cpus_per_worker,
+                                                    gpus_per_slot=self.gpus_per_worker or None, env_vars=env,
+                                                    override_discovery=a['override_discovery'], actor_factory=a['actor_factory'])
+        self._elastic_executor.start()
 
     def start(self, executable_cls=None, executable_args=None, executable_kwargs=None, extra_env_vars=None):
-        """Creates the workers, assigns ranks and (optionally) instantiates `executable_cls` on each of them."""
+        """Creates the workers, assigns ranks and (optionally) instantiates `executable_cls` on each of them.  An elastic
+        executor (`min_workers` / `max_workers`) starts discovery + rendezvous instead; its workers are created by `run`."""
+        if self.elastic:
+            if executable_cls is not None:
+                raise ValueError('executable_cls is not supported by the elastic executor: workers come and go between resets.')
+            return self._start_elastic(extra_env_vars)
         backend = self._backend
         if backend is None:
             bundles, strat, worker_bundle, worker_res = self._placement()
@@ -143,7 +177,10 @@ class RayExecutor:
             return fn(getattr(builtins, '_hvd_ray_executable', None))
         return self.job.run(call)
 
-    def run(self, fn, args=None, kwargs=None):
+    def run(self, fn, args=None, kwargs=None, callbacks=None):
+        if self.elastic:
+            import functools
+            return self._elastic_executor.run(functools.partial(fn, *tuple(args or ()), **dict(kwargs or {})), callbacks=callbacks)
         return self.job.run(fn, tuple(args or ()), dict(kwargs or {}))
 
     def run_remote(self, fn, args=None, kwargs=None):

@@ -153,3 +153,36 @@ def test_elastic_ray_executor_with_local_actors(native_built):
         for h in created:
             backend.kill(h)
     assert sorted(r[0] for r in res) == [0, 1] and all(r[1] == 2 and r[2] == [3.0, 3.0] for r in res), res
+
+
+def test_unified_ray_executor_elastic_mode(native_built):
+    """RayExecutor(min_workers=..., max_workers=...) (the reference's v2 API) delegates to the elastic executor."""
+    from horovod_b200.ray import RayExecutor
+    from horovod_b200.runner.elastic.discovery import FixedHosts
+
+    backend = LocalProcessBackend()
+    created = []
+
+    def actor_factory(hostname, env):
+        h = backend.create(len(created), dict(env, OMP_NUM_THREADS='1', HOROVOD_LOG_LEVEL='warning'))
+        created.append(h)
+
+        class Actor:
+            def execute(self, fn):
+                return backend.get([backend.call(h, 'execute', fn)], 120)[0]
+
+            def kill(self):
+                backend.kill(h)
+        return Actor()
+
+    settings = RayExecutor.create_settings(timeout_s=30)
+    settings.discovery = FixedHosts({'localhost': 2})
+    ex = RayExecutor(settings, min_workers=2, max_workers=2, elastic_timeout=60, override_discovery=False,
+                     elastic_actor_factory=actor_factory, cpus_per_worker=1)
+    ex.start()
+    try:
+        res = ex.run(_elastic_worker)
+    finally:
+        for h in created:
+            backend.kill(h)
+    assert sorted(r[0] for r in res) == [0, 1] and all(r[1] == 2 and r[2] == [3.0, 3.0] for r in res), res
