@@ -70,12 +70,7 @@ def create_run_env_vars(server_ip, server_port, nics=None, elastic=False):
     return run_envs
 
 
-def get_ssh_command(local_command, host, port=None, identity_file=None, timeout_s=None):
-    port_arg = f'-p {port}' if port is not None else ''
-    identity_file_arg = f'-i {identity_file}' if identity_file is not None else ''
-    timeout_arg = f'-o ConnectTimeout={timeout_s}' if timeout_s is not None else ''
-    return (f'ssh -o PasswordAuthentication=no -o StrictHostKeyChecking=no {timeout_arg} {host} {port_arg} '
-            f'{identity_file_arg} {shlex.quote(local_command)}')
+from horovod_b200.runner.util.remote import get_ssh_command  # noqa: E402,F401  (kept importable from here)
 
 
 def _slot_info_to_command_fn(run_command, env, settings=None):

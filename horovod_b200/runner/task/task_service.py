@@ -40,6 +40,10 @@ def probe(index, num_hosts, coordinator_addresses, key, nics=None, linger_s=2.0)
         agent.shutdown()
 
 
-if __name__ == '__main__':
-    idx, n, addrs, key, nics = (codec.loads_base64(a) for a in sys.argv[1:6])
+def main(argv=None):
+    idx, n, addrs, key, nics = (codec.loads_base64(a) for a in (sys.argv if argv is None else argv)[1:6])
     probe(idx, n, addrs, key, nics)
+
+
+if __name__ == '__main__':
+    main()

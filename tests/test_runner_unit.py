@@ -338,3 +338,30 @@ def test_nic_probe_ring_in_process():
         assert len(set(coord.host_ids().values())) == 1
     finally:
         coord.shutdown()
+
+
+def test_remote_command_and_pipe():
+    import threading
+    from horovod_b200.runner.util import remote, streams
+    cmd = remote.get_ssh_command("echo 'a b'", 'node7', port=2222, identity_file='/k/id', timeout_s=5)
+    assert cmd.startswith('ssh -o PasswordAuthentication=no -o StrictHostKeyChecking=no -o ConnectTimeout=5 -p 2222 -i /k/id node7 ')
+    assert cmd.endswith("""'echo '"'"'a b'"'"''""")
+    assert remote.get_remote_command('ls', 'localhost') == 'ls' and remote.get_remote_command('ls', '10.255.255.1').startswith('ssh ')
+    assert remote.ssh_argv('h')[-1] == 'h' and '-p' not in remote.ssh_argv('h')
+
+    pipe = streams.Pipe(max_chunks=2)
+    got = []
+    reader = threading.Thread(target=lambda: got.extend(iter(pipe)))
+    reader.start()
+    for chunk in ('hello ', 'world', '', b'\x00\x01'.decode('latin1')):
+        pipe.write(chunk)
+    pipe.close()
+    reader.join(5)
+    assert ''.join(got) == 'hello world\x00\x01'
+    p2 = streams.Pipe()
+    p2.write(b'abcdef')
+    assert p2.read(2) == b'ab' and p2.read(100) == b'cdef'
+    p2.close()
+    assert p2.read() is None
+    with pytest.raises(RuntimeError):
+        p2.write(b'x')
