@@ -228,7 +228,9 @@ struct SymmTeam::Impl {
   }
 
   ~Impl() {
-    cudaSetDevice(device);
+    // may run very late (a symm_empty tensor that outlived hvd.shutdown() dies at interpreter exit): when the runtime is
+    // already unloading there is nothing left to unmap, the process's address space goes away with it
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return; }
     cudaDeviceSynchronize();
     for (auto& r : regions) FreeRegion(r);
     Driver& d = Drv();
