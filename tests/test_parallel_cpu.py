@@ -140,3 +140,10 @@ def test_static_process_sets_np4(native_built):
     rejection, re-init with the same static sets."""
     rc, out = run_parallel("static_sets_worker.py", np=4, timeout=200)
     assert "STATIC SETS OK" in out, out[-3000:]
+
+
+def test_broadcast_optimizer_state_every_torch_optimizer(native_built):
+    """All 13 optimizer classes torch ships (LBFGS / SparseAdam excluded): different hyper-parameters and state per rank,
+    equal to the root's afterwards; state on the root only; wrapped optimizer."""
+    rc, out = run_parallel("optim_state_worker.py", np=2, timeout=300)
+    assert "OPTIM STATE OK" in out, out[-3000:]
