@@ -80,7 +80,9 @@ def _compile(src, stamp, force, verbose):
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
     else:
-        cmd = ["g++", "-O2", "-g1", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-function", "-pthread"] + inc + ["-c", src, "-o", obj]
+        # the host reduction / scaling loops of ops/ want the vectoriser (-O3); the rest of the runtime is control flow
+        opt = "-O3" if os.sep + "ops" + os.sep in src else "-O2"
+        cmd = ["g++", opt, "-g1", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-function", "-pthread"] + inc + ["-c", src, "-o", obj]
     out = _run(cmd)
     if verbose and out.strip():
         print(out)

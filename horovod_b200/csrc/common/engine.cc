@@ -107,7 +107,11 @@ void Engine::EndWait() { waiters_.fetch_sub(1); }
 std::shared_ptr<ProcessSet> Engine::MakeProcessSet(const std::vector<int>& ranks) {
   auto ps = std::make_shared<ProcessSet>();
   ps->ranks = ranks;
-  ps->transport = transport_->Split(ranks);
+  // the set of ALL ranks talks through the root transport itself, so that it keeps the shared-memory control and data
+  // planes of a single-host job (a Split view only forwards point-to-point traffic)
+  bool everyone = (int)ranks.size() == transport_->size();
+  for (size_t i = 0; everyone && i < ranks.size(); ++i) everyone = ranks[i] == (int)i;
+  ps->transport = everyone ? transport_ : transport_->Split(ranks);
   if (ps->transport) {
     ps->cache.set_capacity((uint32_t)EnvInt(HOROVOD_CACHE_CAPACITY, 1024));
     ps->controller.reset(new Controller(ps->transport, &ps->queue, &ps->cache, cfg_.rank == ranks[0] ? &timeline_ : nullptr));

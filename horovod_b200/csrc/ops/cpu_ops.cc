@@ -1,7 +1,10 @@
 #include "cpu_ops.h"
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "../common/half.h"
 
@@ -18,9 +21,15 @@ template <typename T> inline T Combine(T a, T b, ReduceOp op) {
     default: return a + b;
   }
 }
-template <typename T> void ReduceT(T* d, const T* s, int64_t n, ReduceOp op) {
-  if (op == ReduceOp::SUM || op == ReduceOp::AVERAGE || op == ReduceOp::ADASUM) { for (int64_t i = 0; i < n; ++i) d[i] = d[i] + s[i]; return; }
-  for (int64_t i = 0; i < n; ++i) d[i] = Combine<T>(d[i], s[i], op);
+// dst and src never overlap (a slot / receive buffer vs the caller's buffer): __restrict__ lets the loops vectorise
+// without runtime alias checks; the operator is selected once, outside the loop.
+template <typename T> void ReduceT(T* __restrict__ d, const T* __restrict__ s, int64_t n, ReduceOp op) {
+  switch (op) {
+    case ReduceOp::MIN: for (int64_t i = 0; i < n; ++i) d[i] = s[i] < d[i] ? s[i] : d[i]; return;
+    case ReduceOp::MAX: for (int64_t i = 0; i < n; ++i) d[i] = s[i] > d[i] ? s[i] : d[i]; return;
+    case ReduceOp::PRODUCT: for (int64_t i = 0; i < n; ++i) d[i] = d[i] * s[i]; return;
+    default: for (int64_t i = 0; i < n; ++i) d[i] = d[i] + s[i]; return;
+  }
 }
 template <float (*ToF)(uint16_t), uint16_t (*FromF)(float)> void Reduce16(uint16_t* d, const uint16_t* s, int64_t n, ReduceOp op) {
   for (int64_t i = 0; i < n; ++i) d[i] = FromF(Combine<float>(ToF(d[i]), ToF(s[i]), op));
@@ -78,12 +87,113 @@ void ScaleBuffer(void* buf, int64_t n, DataType dtype, double s) {
 }
 
 // ---------------------------------------------------------------------------
+// Shared-memory data plane (single-host communicators; see transport.h:ShmData).  The host analogue of the two-shot GPU
+// kernel: every rank publishes a piece of its buffer in its slot, reduces the 1/N of the piece it owns straight out of
+// the peers' slots, and everybody copies the reduced chunks back.  No socket, no intermediate copies besides the slot.
+
+namespace {
+
+bool ShmAllreduce(Transport* t, char* b, int64_t count, DataType dtype, ReduceOp op) {
+  ShmData d;
+  if (!t->ShmDataPlane(&d)) return false;
+  const int n = t->size(), r = t->rank();
+  const size_t es = DataTypeSize(dtype);
+  const int64_t per_piece = (int64_t)(d.slot_bytes / es);
+  static const bool prof = getenv("HVD_SHM_PROFILE") != nullptr;
+  double tt[5] = {0, 0, 0, 0, 0};
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  for (int64_t done = 0; done < count; done += per_piece) {
+    const int64_t m = std::min(per_piece, count - done);
+    const int half = (int)(t->ShmNextPiece() & 1);
+    char* mine = d.slot(r, half);
+    double t0 = prof ? now() : 0;
+    memcpy(mine, b + done * es, (size_t)m * es);
+    double t1 = prof ? now() : 0;
+    t->Barrier();
+    double t2 = prof ? now() : 0;
+    const int64_t lo = m * r / n, hi = m * (r + 1) / n;
+    for (int p = 1; p < n && hi > lo; ++p) ReduceInto(mine + lo * es, d.slot((r + p) % n, half) + lo * es, hi - lo, dtype, op);
+    double t3 = prof ? now() : 0;
+    t->Barrier();
+    double t4 = prof ? now() : 0;
+    for (int q = 0; q < n; ++q) {
+      const int64_t ql = m * q / n, qh = m * (q + 1) / n;
+      if (qh > ql) memcpy(b + (done + ql) * es, d.slot(q, half) + ql * es, (size_t)(qh - ql) * es);
+    }
+    if (prof) { double t5 = now(); tt[0] += t1 - t0; tt[1] += t2 - t1; tt[2] += t3 - t2; tt[3] += t4 - t3; tt[4] += t5 - t4; }
+  }
+  if (prof && count * (int64_t)es >= (1 << 20))
+    fprintf(stderr, "[shm allreduce %lld B rank %d] in %.2f ms, barrier %.2f, reduce %.2f, barrier %.2f, out %.2f\n", (long long)(count * es), r,
+            tt[0] * 1e3, tt[1] * 1e3, tt[2] * 1e3, tt[3] * 1e3, tt[4] * 1e3);
+  return true;
+}
+
+bool ShmReducescatter(Transport* t, const char* b, const std::vector<int64_t>& off, char* out, DataType dtype, ReduceOp op) {
+  ShmData d;
+  if (!t->ShmDataPlane(&d)) return false;
+  const int n = t->size(), r = t->rank();
+  const size_t es = DataTypeSize(dtype);
+  const int64_t count = off[n], per_piece = (int64_t)(d.slot_bytes / es);
+  for (int64_t done = 0; done < count; done += per_piece) {
+    const int64_t m = std::min(per_piece, count - done);
+    const int half = (int)(t->ShmNextPiece() & 1);
+    memcpy(d.slot(r, half), b + done * es, (size_t)m * es);
+    t->Barrier();
+    // the part of my output segment that lies inside this piece
+    const int64_t lo = std::max(off[r], done), hi = std::min(off[r + 1], done + m);
+    if (hi > lo) {
+      char* dst = out + (lo - off[r]) * es;
+      memcpy(dst, d.slot(r, half) + (lo - done) * es, (size_t)(hi - lo) * es);
+      for (int p = 1; p < n; ++p) ReduceInto(dst, d.slot((r + p) % n, half) + (lo - done) * es, hi - lo, dtype, op);
+    }
+  }
+  return true;
+}
+
+bool ShmAllgatherv(Transport* t, const char* in, char* o, const std::vector<int64_t>& bytes, const std::vector<int64_t>& displ) {
+  ShmData d;
+  if (!t->ShmDataPlane(&d)) return false;
+  const int n = t->size(), r = t->rank();
+  const int64_t longest = *std::max_element(bytes.begin(), bytes.end());
+  const int64_t S = (int64_t)d.slot_bytes;
+  for (int64_t done = 0; done < longest; done += S) {
+    const int half = (int)(t->ShmNextPiece() & 1);
+    const int64_t mine = std::min(S, bytes[r] - done);
+    if (mine > 0) memcpy(d.slot(r, half), in + done, (size_t)mine);
+    t->Barrier();
+    for (int q = 0; q < n; ++q) {
+      const int64_t theirs = std::min(S, bytes[q] - done);
+      if (q != r && theirs > 0) memcpy(o + displ[q] + done, d.slot(q, half), (size_t)theirs);
+    }
+  }
+  return true;
+}
+
+bool ShmBroadcast(Transport* t, char* buf, int64_t bytes, int root) {
+  ShmData d;
+  if (!t->ShmDataPlane(&d)) return false;
+  const int r = t->rank();
+  const int64_t S = (int64_t)d.slot_bytes;
+  for (int64_t done = 0; done < bytes; done += S) {
+    const int half = (int)(t->ShmNextPiece() & 1);
+    const int64_t m = std::min(S, bytes - done);
+    if (r == root) memcpy(d.slot(root, half), buf + done, (size_t)m);
+    t->Barrier();
+    if (r != root) memcpy(buf + done, d.slot(root, half), (size_t)m);
+  }
+  return true;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
 
 void Allreduce(Transport* t, void* buf, int64_t count, DataType dtype, ReduceOp op) {
   const int n = t->size(), r = t->rank();
   if (n == 1 || count == 0) return;
   const size_t es = DataTypeSize(dtype);
   char* b = (char*)buf;
+  if (ShmAllreduce(t, b, count, dtype, op)) return;
   if ((size_t)count * es < 32768 || count < n) {
     // latency regime: reduce at rank 0, broadcast
     if (r == 0) {
@@ -121,6 +231,7 @@ void Allgatherv(Transport* t, const void* in, void* out, const std::vector<int64
   char* o = (char*)out;
   if (in != o + displ[r] && bytes[r]) memcpy(o + displ[r], in, (size_t)bytes[r]);
   if (n == 1) return;
+  if (ShmAllgatherv(t, o + displ[r], o, bytes, displ)) return;
   const int next = (r + 1) % n, prev = (r - 1 + n) % n;
   for (int s = 0; s < n - 1; ++s) {
     int si = (r - s + n) % n, ri = (r - s - 1 + n) % n;
@@ -131,6 +242,7 @@ void Allgatherv(Transport* t, const void* in, void* out, const std::vector<int64
 void Broadcast(Transport* t, void* buf, int64_t bytes, int root) {
   const int n = t->size(), r = t->rank();
   if (n == 1 || bytes == 0) return;
+  if (ShmBroadcast(t, (char*)buf, bytes, root)) return;
   // binomial tree rooted at `root`
   int vr = (r - root + n) % n;
   int mask = 1;
@@ -163,6 +275,7 @@ void Reducescatter(Transport* t, void* buf, const std::vector<int64_t>& counts, 
   std::vector<int64_t> off(n + 1, 0);
   for (int i = 0; i < n; ++i) off[i + 1] = off[i] + counts[i];
   char* b = (char*)buf;
+  if (n > 1 && ShmReducescatter(t, b, off, (char*)out, dtype, op)) return;
   if (n > 1) {
     int64_t maxseg = *std::max_element(counts.begin(), counts.end());
     std::vector<char> tmp((size_t)maxseg * es);

@@ -11,8 +11,11 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include "../common/logging.h"
@@ -37,12 +40,38 @@ struct Segment {
   Slot slots[kMaxRanks];
 };
 
+// A process that exited but has not been reaped yet (a zombie) still answers kill(pid, 0): look at its state as well.
+bool ProcessAlive(int pid) {
+  if (kill(pid, 0) != 0 && errno == ESRCH) return false;
+  char path[64];
+  snprintf(path, sizeof path, "/proc/%d/stat", pid);
+  FILE* f = fopen(path, "r");
+  if (!f) return errno != ENOENT;          // no procfs: trust kill()
+  char buf[512];
+  size_t n = fread(buf, 1, sizeof buf - 1, f);
+  fclose(f);
+  buf[n] = 0;
+  const char* close_paren = strrchr(buf, ')');   // "pid (comm) S ...": comm may contain spaces and parentheses
+  return !(close_paren && close_paren[1] == ' ' && (close_paren[2] == 'Z' || close_paren[2] == 'X'));
+}
+
 class ShmControlTransport : public Transport {
  public:
   ShmControlTransport(std::shared_ptr<Transport> base, Segment* seg) : base_(std::move(base)), seg_(seg) {
     seg_->slots[base_->rank()].pid = (int32_t)getpid();
   }
-  ~ShmControlTransport() override { munmap(seg_, sizeof(Segment)); }
+  ~ShmControlTransport() override {
+    munmap(seg_, sizeof(Segment));
+    if (data_) munmap(data_, data_bytes_);
+  }
+  void AttachData(char* data, size_t total_bytes, size_t slot_bytes) { data_ = data; data_bytes_ = total_bytes; slot_bytes_ = slot_bytes; }
+  bool ShmDataPlane(ShmData* out) override {
+    if (!data_) return false;
+    out->base = data_; out->slot_bytes = slot_bytes_;
+    return true;
+  }
+  uint64_t ShmNextPiece() override { return piece_++; }
+  int host_id(int i) const override { return base_->host_id(i); }
   int rank() const override { return base_->rank(); }
   int size() const override { return base_->size(); }
   int global_rank(int i) const override { return base_->global_rank(i); }
@@ -91,7 +120,7 @@ class ShmControlTransport : public Transport {
         if (now - last_check > std::chrono::seconds(1)) {
           last_check = now;
           int pid = s.pid;
-          if (pid > 0 && kill(pid, 0) != 0 && errno == ESRCH)
+          if (pid > 0 && !ProcessAlive(pid))
             throw TransportError("rank " + std::to_string(r) + " (pid " + std::to_string(pid) + ") died");
         }
       }
@@ -100,7 +129,25 @@ class ShmControlTransport : public Transport {
   std::shared_ptr<Transport> base_;
   Segment* seg_;
   uint64_t round_ = 0;
+  char* data_ = nullptr;
+  size_t data_bytes_ = 0, slot_bytes_ = 0;
+  uint64_t piece_ = 0;
 };
+
+// Maps `bytes` of a named segment; the creator reserves the pages up front (posix_fallocate) so that a too-small /dev/shm
+// shows up here as an error instead of a SIGBUS in the middle of a collective.
+char* MapNamed(const std::string& name, size_t bytes, bool create) {
+  int fd = create ? shm_open(name.c_str(), O_CREAT | O_EXCL | O_RDWR, 0600) : shm_open(name.c_str(), O_RDWR, 0600);
+  if (fd < 0) return nullptr;
+  if (create && (ftruncate(fd, (off_t)bytes) != 0 || posix_fallocate(fd, 0, (off_t)bytes) != 0)) {
+    close(fd);
+    shm_unlink(name.c_str());
+    return nullptr;
+  }
+  void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  return p == MAP_FAILED ? nullptr : (char*)p;
+}
 
 }  // namespace
 
@@ -139,7 +186,31 @@ std::shared_ptr<Transport> WrapWithShmControl(std::shared_ptr<Transport> base, c
     LOG(DEBUG) << "shared-memory control plane unavailable; using the base transport";
     return base;
   }
-  return std::make_shared<ShmControlTransport>(std::move(base), seg);
+  auto shm = std::make_shared<ShmControlTransport>(base, seg);
+
+  // ---- data plane (host tensors of a single-host job never touch a socket) ----
+  const char* dp = getenv("HVD_SHM_DATA_PLANE");
+  if (dp && atoi(dp) == 0) return shm;
+  size_t slot = 1u << 20;
+  if (const char* sb = getenv("HVD_SHM_SLOT_BYTES")) slot = (size_t)std::max(4096LL, atoll(sb));
+  slot = (slot + 4095) & ~(size_t)4095;
+  const size_t total = slot * 2 * (size_t)base->size();
+  const std::string dname = name + "-d";
+  char* data = nullptr;
+  if (base->rank() == 0) { shm_unlink(dname.c_str()); data = MapNamed(dname, total, true); }
+  uint64_t okd = base->rank() == 0 ? (data != nullptr) : 1;
+  shm->AllreduceBits(&okd, 1, nullptr, 0);
+  if (okd && base->rank() != 0) data = MapNamed(dname, total, false);
+  uint64_t okd2 = okd ? (uint64_t)(data != nullptr) : 0;
+  shm->AllreduceBits(&okd2, 1, nullptr, 0);
+  if (base->rank() == 0) shm_unlink(dname.c_str());
+  if (!okd2) {
+    if (data) munmap(data, total);
+    LOG(DEBUG) << "shared-memory data plane unavailable (" << total << " bytes of /dev/shm); host tensors use the base transport";
+    return shm;
+  }
+  shm->AttachData(data, total, slot);
+  return shm;
 }
 
 }  // namespace hvd

@@ -25,6 +25,15 @@ class TransportError : public std::runtime_error {
   explicit TransportError(const std::string& m) : std::runtime_error(m) {}
 };
 
+// Shared-memory data plane of a single-host communicator: every rank owns two slots ("halves") of `slot_bytes` in one
+// POSIX shm segment that all ranks map.  Collectives move a message through it in pieces; piece k uses half k & 1, and
+// because every piece contains a barrier after its writes, a half is never overwritten while a peer still reads it.
+struct ShmData {
+  char* base = nullptr;
+  size_t slot_bytes = 0;
+  char* slot(int rank, int half) const { return base + ((size_t)rank * 2 + (size_t)half) * slot_bytes; }
+};
+
 class Transport {
  public:
   virtual ~Transport() = default;
@@ -57,6 +66,11 @@ class Transport {
   // Small integer naming the host of local index i (equal ids <=> same host); used to derive the intra-host and
   // cross-host sub-communicators of the hierarchical GPU collectives.
   virtual int host_id(int /*i*/) const { return 0; }
+
+  // Shared-memory data plane (see ShmData); false when this communicator has none.  ShmNextPiece() returns the running
+  // piece number (identical on every rank because collectives are issued in the same order everywhere).
+  virtual bool ShmDataPlane(ShmData* /*out*/) { return false; }
+  virtual uint64_t ShmNextPiece() { return 0; }
 };
 
 // View of a parent transport restricted to a rank subset.

@@ -1,0 +1,91 @@
+"""Host-tensor collectives through the shared-memory data plane: many pieces (HVD_SHM_SLOT_BYTES is set tiny by the test),
+odd sizes, every dtype / reduce op, uneven allgather, broadcast from every root, reducescatter with uneven splits, and a
+long mixed sequence (the piece counter / double buffering must stay consistent across different collectives)."""
+import os
+
+import torch
+
+import horovod_b200.torch as hvd
+
+hvd.init()
+rank, size = hvd.rank(), hvd.size()
+gen = torch.Generator().manual_seed(7)
+
+
+def data(n, dtype, r):
+    g = torch.Generator().manual_seed(1000 * r + n % 97)
+    if dtype.is_floating_point:
+        return (torch.rand(n, generator=g, dtype=torch.float32) * 2 - 1).to(dtype)
+    if dtype == torch.bool:
+        return torch.rand(n, generator=g) > 0.5
+    return torch.randint(-3 if dtype != torch.uint8 else 0, 4, (n,), generator=g).to(dtype)
+
+
+checked = 0
+for n in (1, 5, 1023, 1024, 1025, 4099, 70001):
+    for dtype in (torch.float32, torch.float64, torch.float16, torch.bfloat16, torch.int32, torch.int64, torch.uint8, torch.int8, torch.int16):
+        xs = [data(n, dtype, r) for r in range(size)]
+        for op, fn in ((hvd.Sum, lambda a, b: a + b), (hvd.Min, torch.minimum), (hvd.Max, torch.maximum), (hvd.Product, lambda a, b: a * b)):
+            if op == hvd.Product and not dtype.is_floating_point:
+                continue
+            out = hvd.allreduce(xs[rank], op=op, name='a.%d.%s.%d' % (n, dtype, op))
+            # reference in the order the data plane reduces a chunk: owner first, then (owner+1), ...; for 16-bit floats every
+            # step rounds, so compare against a float32 accumulation with a tolerance instead
+            if dtype in (torch.float16, torch.bfloat16):
+                ref = xs[0].float()
+                for r in range(1, size):
+                    ref = fn(ref, xs[r].float())
+                assert torch.allclose(out.float(), ref, rtol=2e-2, atol=2e-2), (n, dtype, op)
+            else:
+                ref = xs[0].clone()
+                for r in range(1, size):
+                    ref = fn(ref, xs[r])
+                if dtype.is_floating_point:
+                    assert torch.allclose(out, ref, rtol=1e-5, atol=1e-6), (n, dtype, op)
+                else:
+                    assert torch.equal(out, ref), (n, dtype, op)
+            checked += 1
+        avg = hvd.allreduce(xs[rank].float(), op=hvd.Average, name='avg.%d.%s' % (n, dtype))
+        assert torch.allclose(avg, sum(x.float() for x in xs) / size, rtol=1e-5, atol=1e-5)
+
+# uneven allgather (rank r contributes (r+1)*k rows), including an empty contribution
+for k in (0, 1, 333, 5000):
+    mine = torch.arange((rank + 1) * k * 3, dtype=torch.float32).reshape(-1, 3) + 1000 * rank
+    out = hvd.allgather(mine, name='ag.%d' % k)
+    ref = torch.cat([torch.arange((r + 1) * k * 3, dtype=torch.float32).reshape(-1, 3) + 1000 * r for r in range(size)])
+    assert torch.equal(out, ref), k
+
+# broadcast from every root, sizes around the slot size
+for root in range(size):
+    for n in (1, 1024, 1025, 50000):
+        t = torch.full((n,), float(rank + 1), dtype=torch.float64)
+        hvd.broadcast_(t, root_rank=root, name='bc.%d.%d' % (root, n))
+        assert torch.all(t == root + 1)
+
+# reducescatter, even and uneven first dimension
+for rows in (size, size * 7 + 1, 4000 + size - 1):
+    x = torch.arange(rows * 5, dtype=torch.float32).reshape(rows, 5) * (rank + 1)
+    out = hvd.reducescatter(x, op=hvd.Sum, name='rs.%d' % rows)
+    full = torch.arange(rows * 5, dtype=torch.float32).reshape(rows, 5) * (size * (size + 1) // 2)
+    base, extra = divmod(rows, size)
+    starts = [r * base + min(r, extra) for r in range(size + 1)]
+    assert torch.equal(out, full[starts[rank]:starts[rank + 1]]), rows
+
+# long mixed async sequence with fusion
+handles = []
+for i in range(40):
+    t = torch.full((257 * (i % 5 + 1),), float(rank + i))
+    handles.append((i, t.numel(), hvd.allreduce_async(t, op=hvd.Sum, name='mix.%d' % i)))
+    if i % 3 == 0:
+        b = torch.full((100 + i,), float(rank))
+        hvd.broadcast_(b, root_rank=i % size, name='mixb.%d' % i)
+        assert torch.all(b == i % size)
+for i, n, h in handles:
+    out = hvd.synchronize(h)
+    assert torch.all(out == sum(r + i for r in range(size))) and out.numel() == n
+
+info = os.environ.get('HVD_SHM_DATA_PLANE', '1')
+hvd.barrier()
+if rank == 0:
+    print('SHM PLANE OK', checked, 'plane=' + info)
+hvd.shutdown()
