@@ -147,3 +147,12 @@ def test_broadcast_optimizer_state_every_torch_optimizer(native_built):
     equal to the root's afterwards; state on the root only; wrapped optimizer."""
     rc, out = run_parallel("optim_state_worker.py", np=2, timeout=300)
     assert "OPTIM STATE OK" in out, out[-3000:]
+
+
+@pytest.mark.parametrize("np_,env", [(2, {"HVD_SHM_SLOT_BYTES": "4096"}), (3, {"HVD_SHM_SLOT_BYTES": "4096"}),
+                                     (3, {"HVD_SHM_DATA_PLANE": "0"}), (2, {"HVD_CONTROL_PLANE": "tcp"})])
+def test_shared_memory_data_plane(native_built, np_, env):
+    """Host-tensor collectives through the shm slots with a tiny slot size (many pieces, double buffering across different
+    collectives), and the same program with the data plane / the whole shm overlay switched off."""
+    rc, out = run_parallel("shm_plane_worker.py", np=np_, timeout=400, env=env)
+    assert "SHM PLANE OK" in out, out[-3000:]
