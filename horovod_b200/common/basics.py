@@ -348,6 +348,24 @@ class HorovodBasics(object):
         return {'cycles': int(self.lib.hvd_stat(0)), 'idle_cycles': int(self.lib.hvd_stat(1)),
                 'responses': int(self.lib.hvd_stat(2)), 'kernel_launches': int(self.lib.hvd_stat(3))}
 
+    def metrics(self):
+        """Monotonic counters of this rank since init(): {'allreduce': {'responses', 'tensors', 'bytes', 'on_gpu', 'errors'}, ...}
+        per collective type (a fused response counts once in 'responses' and once per tensor in 'tensors'), plus the
+        'runtime' block of `runtime_stats()`.  Cheap (a few atomic loads); see horovod_b200.utils.metrics for exporters."""
+        lib = self.lib
+        lib.hvd_metric.restype = ctypes.c_ulonglong
+        fields = ('responses', 'tensors', 'bytes', 'on_gpu', 'errors')
+        out = {}
+        buf = ctypes.create_string_buffer(64)
+        for ty in range(12):
+            if lib.hvd_metric_type_name(ty, buf, 64) != 0:
+                continue
+            vals = {f: int(lib.hvd_metric(ty, i)) for i, f in enumerate(fields)}
+            if any(vals.values()):
+                out[buf.value.decode().lower()] = vals
+        out['runtime'] = self.runtime_stats()
+        return out
+
     def tunable_params(self):
         """Current values of the autotuned parameters (fusion threshold, cycle time, kernel crossovers, CTA count)."""
         names = ['fusion_threshold_bytes', 'cycle_time_us', 'cache_enabled', 'oneshot_max_bytes', 'nvls_min_bytes',

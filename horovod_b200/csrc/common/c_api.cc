@@ -138,6 +138,17 @@ unsigned long long hvd_stat(int which) {
     default: return 0;
   }
 }
+// named counters: hvd_metric(type, field) with type = ResponseType value, field = Engine::MetricField
+unsigned long long hvd_metric(int type, int field) {
+  if (type < 0 || type >= Engine::kMetricTypes || field < 0 || field >= Engine::kPerType) return 0;
+  return Engine::Get().metric(type, field);
+}
+int hvd_metric_type_name(int type, char* out, int cap) {
+  if (type < 0 || type >= Engine::kMetricTypes || cap <= 0) return -1;
+  const char* n = ResponseTypeName((ResponseType)type);
+  snprintf(out, (size_t)cap, "%s", n ? n : "");
+  return 0;
+}
 // tunables (read back what the autotuner / env decided)
 long long hvd_param(int which) {
   const TunableParams& p = Engine::Get().parameter_manager().params();

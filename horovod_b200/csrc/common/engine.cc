@@ -72,6 +72,7 @@ Status Engine::Init(const InitConfig& cfg) {
   cfg_ = cfg;
   init_done_ = false; init_failed_ = false; shutdown_requested_ = false; loop_exited_ = false;
   cycles_ = 0; fast_cycles_ = 0; responses_ = 0;
+  for (auto& m : op_metrics_) m = 0;
   ResetLogLevelFromEnv();
   SetLogRank(cfg.rank);
   thread_ = std::thread(&Engine::BackgroundThread, this);
@@ -348,7 +349,11 @@ void Engine::PerformOperation(ProcessSet& ps, Response& r) {
   for (auto& e : es) if (e && e->group_id >= 0) ps.groups.DeregisterGroup(e->group_id);
 
   switch (r.type) {
-    case ResponseType::ERROR: finish_all(Status::PreconditionError(r.error_message)); return;
+    case ResponseType::ERROR:
+      op_metrics_[(int)ResponseType::ERROR * kPerType + kResponses].fetch_add(1, std::memory_order_relaxed);
+      op_metrics_[(int)ResponseType::ERROR * kPerType + kTensors].fetch_add(r.tensor_names.size(), std::memory_order_relaxed);
+      finish_all(Status::PreconditionError(r.error_message));
+      return;
     case ResponseType::JOIN:
       for (auto& e : es) if (e && e->callback) { Completion c; c.last_joined_rank = ps.ranks[std::max(0, r.last_joined_rank)]; e->callback(c); }
       return;
@@ -431,6 +436,19 @@ void Engine::PerformOperation(ProcessSet& ps, Response& r) {
   }
 
   if (ps.set_rank() == 0 && ps.id == 0 && params_.IsAutoTuning()) params_.Update(r.tensor_names, bytes);
+  {
+    const int ty = (int)r.type;
+    if (ty >= 0 && ty < kMetricTypes) {
+      auto* m = &op_metrics_[ty * kPerType];
+      m[kResponses].fetch_add(1, std::memory_order_relaxed);
+      m[kTensors].fetch_add(r.tensor_names.size(), std::memory_order_relaxed);
+      int64_t payload = 0;   // bytes this rank contributed (allgather / alltoall sizes are per rank, the entries know them)
+      for (auto& e : es) if (e) payload += (int64_t)e->bytes();
+      m[kBytes].fetch_add((uint64_t)(payload > 0 ? payload : bytes), std::memory_order_relaxed);
+      if (device != CPU_DEVICE_ID) m[kOnGpu].fetch_add(1, std::memory_order_relaxed);
+      if (!st.ok()) m[kErrors].fetch_add(1, std::memory_order_relaxed);
+    }
+  }
 
   if (done) {
     if (timeline_.Initialized()) {

@@ -93,6 +93,11 @@ class Engine {
   uint64_t cycles() const { return cycles_.load(); }
   uint64_t fast_path_cycles() const { return fast_cycles_.load(); }
   uint64_t responses_executed() const { return responses_.load(); }
+  // Named monotonic counters (hvd.metrics()): per collective type the number of executed (fused) responses, tensors and
+  // payload bytes, split by where they ran (gpu / host), plus errors.  Index = type * kPerType + field.
+  static constexpr int kMetricTypes = 12, kPerType = 5;
+  enum MetricField { kResponses = 0, kTensors = 1, kBytes = 2, kOnGpu = 3, kErrors = 4 };
+  uint64_t metric(int type, int field) const { return op_metrics_[type * kPerType + field].load(std::memory_order_relaxed); }
 
  private:
   void BackgroundThread();
@@ -137,6 +142,7 @@ class Engine {
   mutable std::mutex err_mu_;
   std::string last_error_;
   std::atomic<uint64_t> cycles_{0}, fast_cycles_{0}, responses_{0};
+  std::atomic<uint64_t> op_metrics_[kMetricTypes * kPerType] = {};
   std::atomic<int> noname_counter_{0};
   std::atomic<int> symm_alloc_counter_{0};
   std::atomic<int> join_device_{-1};  // CUDA device a joined rank contributes zeros from

@@ -92,6 +92,7 @@ p2p_built = _basics.p2p_built
 gpu_topology = _basics.gpu_topology
 gpu_backend_info = _basics.gpu_backend_info
 runtime_stats = _basics.runtime_stats
+metrics = _basics.metrics
 tunable_params = _basics.tunable_params
 
 

@@ -66,3 +66,10 @@ def test_runtime_timeline_is_valid_chrome_trace(native_built, tmp_path):
     assert any(n and "CYCLE_START" in n for n in names)
     tids = {e.get("args", {}).get("name") for e in events if isinstance(e, dict) and e.get("ph") == "M"}
     assert any(t and "tl.ar" in t for t in tids), tids
+
+
+def test_metrics_counters_and_exporters(native_built):
+    """hvd.metrics(): per-collective counters (fusion visible as responses < tensors, error responses counted), Interval deltas,
+    Prometheus text endpoint with rank labels, periodic log line."""
+    rc, out = run_parallel("metrics_worker.py", np=2, timeout=200)
+    assert "METRICS OK" in out, out[-3000:]
