@@ -160,7 +160,7 @@ class BridgedOps:
         for k in ('init', 'shutdown', 'is_initialized', 'start_timeline', 'stop_timeline', 'size', 'local_size',
                   'cross_size', 'rank', 'local_rank', 'cross_rank', 'is_homogeneous', 'mpi_threads_supported',
                   'mpi_enabled', 'mpi_built', 'gloo_enabled', 'gloo_built', 'nccl_built', 'ddl_built', 'ccl_built',
-                  'cuda_built', 'rocm_built', 'p2p_built', 'gpu_topology', 'gpu_backend_info', 'runtime_stats', 'metrics',
+                  'cuda_built', 'rocm_built', 'p2p_built', 'gpu_topology', 'gpu_backend_info', 'runtime_stats', 'metrics', 'control_plane_info',
                   'tunable_params', 'join', 'barrier', 'Average', 'Sum', 'Adasum', 'Min', 'Max', 'Product',
                   'global_process_set'):
             namespace[k] = getattr(_ops, k)

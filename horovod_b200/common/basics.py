@@ -343,6 +343,12 @@ class HorovodBasics(object):
         self.lib.hvd_gpu_backend_string(process_set_id, buf, 1024)
         return buf.value.decode()
 
+    def control_plane_info(self):
+        """What negotiation and host-tensor collectives of the global process set run on (shared memory / two-level / TCP)."""
+        buf = ctypes.create_string_buffer(512)
+        self.lib.hvd_control_plane_string(buf, 512)
+        return buf.value.decode()
+
     def runtime_stats(self):
         """Counters of the background thread: cycles, idle cycles, responses executed, kernels launched."""
         return {'cycles': int(self.lib.hvd_stat(0)), 'idle_cycles': int(self.lib.hvd_stat(1)),

@@ -138,6 +138,11 @@ unsigned long long hvd_stat(int which) {
     default: return 0;
   }
 }
+int hvd_control_plane_string(char* out, int cap) {
+  if (cap <= 0) return -1;
+  snprintf(out, (size_t)cap, "%s", Engine::Get().ControlPlaneString().c_str());
+  return 0;
+}
 // named counters: hvd_metric(type, field) with type = ResponseType value, field = Engine::MetricField
 unsigned long long hvd_metric(int type, int field) {
   if (type < 0 || type >= Engine::kMetricTypes || field < 0 || field >= Engine::kPerType) return 0;

@@ -154,10 +154,10 @@ void Engine::BackgroundThread() {
       for (int r = 0; r < cfg_.size; ++r) hosts[r] = r == cfg_.rank ? host : store.Get(cfg_.scope, "host." + std::to_string(r), timeout);
       transport_ = CreateTcpTransport(cfg_.rank, cfg_.size, &store, cfg_.scope, adv, timeout, hosts);
       std::string cp = EnvStr(HVD_CONTROL_PLANE, "auto");
-      if (cp != "tcp" && transport_->single_host()) {
+      if (cp != "tcp") {
         std::string seg = "hvd-" + std::to_string(cfg_.rendezvous_port) + "-";
         for (char c : cfg_.scope) seg.push_back(isalnum((unsigned char)c) ? c : '_');
-        transport_ = WrapWithShmControl(transport_, seg);
+        transport_ = transport_->single_host() ? WrapWithShmControl(transport_, seg) : WrapWithHierarchicalControl(transport_, seg);
       }
       // local / cross topology when the launcher did not provide it
       if (cfg_.local_size <= 0) {

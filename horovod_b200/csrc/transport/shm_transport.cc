@@ -55,6 +55,31 @@ bool ProcessAlive(int pid) {
   return !(close_paren && close_paren[1] == ' ' && (close_paren[2] == 'Z' || close_paren[2] == 'X'));
 }
 
+// Spin (pause -> yield -> 50 us naps) until the slot's sequence reaches `k`; once a second make sure its owner still lives.
+void WaitSlot(Slot& s, uint64_t k, int r) {
+  uint64_t spins = 0;
+  auto last_check = std::chrono::steady_clock::now();
+  while (s.seq.load(std::memory_order_acquire) < k) {
+    ++spins;
+    if (spins < 2000) {
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    } else if (spins < 20000) {
+      std::this_thread::yield();
+    } else {
+      std::this_thread::sleep_for(std::chrono::microseconds(50));
+      auto now = std::chrono::steady_clock::now();
+      if (now - last_check > std::chrono::seconds(1)) {
+        last_check = now;
+        int pid = s.pid;
+        if (pid > 0 && !ProcessAlive(pid))
+          throw TransportError("rank " + std::to_string(r) + " (pid " + std::to_string(pid) + ") died");
+      }
+    }
+  }
+}
+
 class ShmControlTransport : public Transport {
  public:
   ShmControlTransport(std::shared_ptr<Transport> base, Segment* seg) : base_(std::move(base)), seg_(seg) {
@@ -71,6 +96,10 @@ class ShmControlTransport : public Transport {
     return true;
   }
   uint64_t ShmNextPiece() override { return piece_++; }
+  std::string Describe() const override {
+    return std::string("control: shared memory (") + std::to_string(size()) + " ranks, one host); host data: " +
+           (data_ ? "shared-memory slots of " + std::to_string(slot_bytes_) + " bytes" : std::string("ring over the base transport"));
+  }
   int host_id(int i) const override { return base_->host_id(i); }
   int rank() const override { return base_->rank(); }
   int size() const override { return base_->size(); }
@@ -103,29 +132,7 @@ class ShmControlTransport : public Transport {
   void Barrier() override { AllreduceBits(nullptr, 0, nullptr, 0); }
 
  private:
-  void WaitSeq(Slot& s, uint64_t k, int r) {
-    uint64_t spins = 0;
-    auto last_check = std::chrono::steady_clock::now();
-    while (s.seq.load(std::memory_order_acquire) < k) {
-      ++spins;
-      if (spins < 2000) {
-#if defined(__x86_64__)
-        __builtin_ia32_pause();
-#endif
-      } else if (spins < 20000) {
-        std::this_thread::yield();
-      } else {
-        std::this_thread::sleep_for(std::chrono::microseconds(50));
-        auto now = std::chrono::steady_clock::now();
-        if (now - last_check > std::chrono::seconds(1)) {
-          last_check = now;
-          int pid = s.pid;
-          if (pid > 0 && !ProcessAlive(pid))
-            throw TransportError("rank " + std::to_string(r) + " (pid " + std::to_string(pid) + ") died");
-        }
-      }
-    }
-  }
+  static void WaitSeq(Slot& s, uint64_t k, int r) { WaitSlot(s, k, r); }
   std::shared_ptr<Transport> base_;
   Segment* seg_;
   uint64_t round_ = 0;
@@ -133,7 +140,6 @@ class ShmControlTransport : public Transport {
   size_t data_bytes_ = 0, slot_bytes_ = 0;
   uint64_t piece_ = 0;
 };
-
 // Maps `bytes` of a named segment; the creator reserves the pages up front (posix_fallocate) so that a too-small /dev/shm
 // shows up here as an error instead of a SIGBUS in the middle of a collective.
 char* MapNamed(const std::string& name, size_t bytes, bool create) {
@@ -149,6 +155,131 @@ char* MapNamed(const std::string& name, size_t bytes, bool create) {
   return p == MAP_FAILED ? nullptr : (char*)p;
 }
 
+
+// Two-level control plane of a MULTI-host job: the ranks of one host fold their bit vectors in a per-host shm segment, the
+// host leaders exchange the folded vectors over the base (TCP) transport, and the leaders publish the result back through
+// shm.  Per negotiation cycle the job sends 2 (H - 1) small TCP messages instead of 2 (N - 1) — with 8 GPUs per host an
+// 8x lighter load on rank 0, and no socket at all between the ranks of a host.
+class HierShmControlTransport : public Transport {
+ public:
+  HierShmControlTransport(std::shared_ptr<Transport> base, Segment* seg, std::vector<int> local, int local_index,
+                          std::vector<int> leaders)
+      : base_(std::move(base)), seg_(seg), local_(std::move(local)), li_(local_index), leaders_(std::move(leaders)) {
+    seg_->slots[li_].pid = (int32_t)getpid();
+  }
+  ~HierShmControlTransport() override { munmap(seg_, sizeof(Segment)); }
+  int rank() const override { return base_->rank(); }
+  int size() const override { return base_->size(); }
+  int global_rank(int i) const override { return base_->global_rank(i); }
+  bool single_host() const override { return false; }
+  int host_id(int i) const override { return base_->host_id(i); }
+  void Send(int p, const void* b, size_t n) override { base_->Send(p, b, n); }
+  void Recv(int p, void* b, size_t n) override { base_->Recv(p, b, n); }
+  void SendRecv(int sp, const void* sb, size_t sn, int rp, void* rb, size_t rn) override {
+    base_->SendRecv(sp, sb, sn, rp, rb, rn);
+  }
+
+  void AllreduceBits(uint64_t* and_words, int n_and, uint64_t* or_words, int n_or) override {
+    const int n = n_and + n_or;
+    if (n > kMaxWords) { Transport::AllreduceBits(and_words, n_and, or_words, n_or); return; }
+    const uint64_t k = ++round_;
+    const int buf = (int)(k & 1);
+    const int nlocal = (int)local_.size();
+    Slot& result = seg_->slots[nlocal];          // one slot past the members: the leader's answer
+    if (li_ != 0) {
+      Slot& me = seg_->slots[li_];
+      if (n_and) memcpy(me.data[buf], and_words, (size_t)n_and * 8);
+      if (n_or) memcpy(me.data[buf] + n_and, or_words, (size_t)n_or * 8);
+      me.seq.store(k, std::memory_order_release);
+      WaitSlot(result, k, local_[0]);
+      if (n_and) memcpy(and_words, result.data[buf], (size_t)n_and * 8);
+      if (n_or) memcpy(or_words, result.data[buf] + n_and, (size_t)n_or * 8);
+      return;
+    }
+    // ---- host leader ----
+    for (int j = 1; j < nlocal; ++j) {
+      Slot& s = seg_->slots[j];
+      WaitSlot(s, k, local_[j]);
+      for (int i = 0; i < n_and; ++i) and_words[i] &= s.data[buf][i];
+      for (int i = 0; i < n_or; ++i) or_words[i] |= s.data[buf][n_and + i];
+    }
+    if (leaders_.size() > 1) {
+      std::vector<uint64_t> mine((size_t)std::max(n, 1)), tmp((size_t)std::max(n, 1));
+      if (n_and) memcpy(mine.data(), and_words, (size_t)n_and * 8);
+      if (n_or) memcpy(mine.data() + n_and, or_words, (size_t)n_or * 8);
+      const size_t wire = (size_t)std::max(n, 1) * 8;      // an empty vector (barrier) still travels as one word
+      if (rank() == leaders_[0]) {
+        for (size_t h = 1; h < leaders_.size(); ++h) {
+          base_->Recv(leaders_[h], tmp.data(), wire);
+          for (int i = 0; i < n_and; ++i) mine[i] &= tmp[i];
+          for (int i = n_and; i < n; ++i) mine[i] |= tmp[i];
+        }
+        for (size_t h = 1; h < leaders_.size(); ++h) base_->Send(leaders_[h], mine.data(), wire);
+      } else {
+        base_->Send(leaders_[0], mine.data(), wire);
+        base_->Recv(leaders_[0], mine.data(), wire);
+      }
+      if (n_and) memcpy(and_words, mine.data(), (size_t)n_and * 8);
+      if (n_or) memcpy(or_words, mine.data() + n_and, (size_t)n_or * 8);
+    }
+    if (n_and) memcpy(result.data[buf], and_words, (size_t)n_and * 8);
+    if (n_or) memcpy(result.data[buf] + n_and, or_words, (size_t)n_or * 8);
+    result.seq.store(k, std::memory_order_release);
+  }
+  void Barrier() override { AllreduceBits(nullptr, 0, nullptr, 0); }
+  std::string Describe() const override {
+    return "control: two-level (shared memory among the " + std::to_string(local_.size()) + " ranks of this host, " +
+           std::to_string(leaders_.size()) + " host leaders over the base transport); host data: ring over the base transport";
+  }
+
+ private:
+  std::shared_ptr<Transport> base_;
+  Segment* seg_;
+  std::vector<int> local_;     // ranks of my host, ascending; local_[0] is the host leader
+  int li_;                     // my index in local_
+  std::vector<int> leaders_;   // leader of every host, ascending
+  uint64_t round_ = 0;
+};
+
+}  // namespace
+
+std::shared_ptr<Transport> WrapWithHierarchicalControl(std::shared_ptr<Transport> base, const std::string& segment_name) {
+  const int n = base->size(), me = base->rank();
+  if (n == 1 || base->single_host()) return base;
+  std::vector<int> local, leaders;
+  std::vector<int> seen_hosts;
+  for (int r = 0; r < n; ++r) {
+    const int h = base->host_id(r);
+    if (h == base->host_id(me)) local.push_back(r);
+    if (std::find(seen_hosts.begin(), seen_hosts.end(), h) == seen_hosts.end()) { seen_hosts.push_back(h); leaders.push_back(r); }
+  }
+  // worth it only if some host has several ranks; every rank evaluates the same table, so the decision is collective
+  bool any_shared = (int)leaders.size() < n;
+  if (!any_shared || (int)local.size() + 1 > kMaxRanks) return base;
+  const int li = (int)(std::find(local.begin(), local.end(), me) - local.begin());
+  const std::string name = "/" + segment_name + "-h" + std::to_string(base->host_id(me));
+  Segment* seg = nullptr;
+  int ok = 1;
+  if (li == 0) {
+    shm_unlink(name.c_str());
+    seg = (Segment*)MapNamed(name, sizeof(Segment), true);
+    if (!seg) ok = 0; else { memset((void*)seg, 0, sizeof(Segment)); seg->nranks = (uint32_t)local.size(); seg->magic.store(0x48564448); }
+  }
+  uint64_t okw = (uint64_t)ok;
+  base->AllreduceBits(&okw, 1, nullptr, 0);            // every leader created its segment
+  if (okw && li != 0) { seg = (Segment*)MapNamed(name, sizeof(Segment), false); if (!seg) ok = 0; }
+  uint64_t ok2 = okw ? (uint64_t)ok : 0;
+  base->AllreduceBits(&ok2, 1, nullptr, 0);            // everybody mapped it
+  if (li == 0) shm_unlink(name.c_str());
+  if (!ok2) {
+    if (seg) munmap(seg, sizeof(Segment));
+    LOG(DEBUG) << "two-level control plane unavailable; negotiation stays on the base transport";
+    return base;
+  }
+  return std::make_shared<HierShmControlTransport>(std::move(base), seg, std::move(local), li, std::move(leaders));
+}
+
+namespace {
 }  // namespace
 
 std::shared_ptr<Transport> WrapWithShmControl(std::shared_ptr<Transport> base, const std::string& segment_name) {

@@ -69,6 +69,8 @@ class Transport {
 
   // Shared-memory data plane (see ShmData); false when this communicator has none.  ShmNextPiece() returns the running
   // piece number (identical on every rank because collectives are issued in the same order everywhere).
+  // one line for logs / hvd.control_plane_info(): what the negotiation and the host data path run on
+  virtual std::string Describe() const { return "control: point-to-point star over the base transport; host data: ring over the base transport"; }
   virtual bool ShmDataPlane(ShmData* /*out*/) { return false; }
   virtual uint64_t ShmNextPiece() { return 0; }
 };
@@ -145,5 +147,9 @@ std::shared_ptr<Transport> LoopbackEndpoint(std::shared_ptr<LoopbackHub> hub, in
 // all on one host and replaces AllreduceBits/Barrier with atomics on a POSIX
 // shm segment (microseconds instead of a TCP round trip).
 std::shared_ptr<Transport> WrapWithShmControl(std::shared_ptr<Transport> base, const std::string& segment_name);
+// Multi-host variant: bit vectors are folded per host in shared memory and only the host leaders talk over the base
+// transport (2 (H-1) messages per negotiation cycle instead of 2 (N-1)).  Returns `base` for single-host jobs, jobs with
+// one rank per host, or when shared memory is unavailable.
+std::shared_ptr<Transport> WrapWithHierarchicalControl(std::shared_ptr<Transport> base, const std::string& segment_name);
 
 }  // namespace hvd

@@ -7,7 +7,7 @@ from horovod_b200.torch.mpi_ops import (  # noqa: F401
     init, shutdown, is_initialized, start_timeline, stop_timeline,
     size, local_size, cross_size, rank, local_rank, cross_rank, is_homogeneous,
     mpi_threads_supported, mpi_enabled, mpi_built, gloo_enabled, gloo_built, nccl_built, ddl_built, ccl_built,
-    cuda_built, rocm_built, p2p_built, gpu_topology, gpu_backend_info, runtime_stats, metrics, tunable_params,
+    cuda_built, rocm_built, p2p_built, gpu_topology, gpu_backend_info, runtime_stats, metrics, control_plane_info, tunable_params,
     allreduce, allreduce_async, allreduce_, allreduce_async_,
     grouped_allreduce, grouped_allreduce_async, grouped_allreduce_, grouped_allreduce_async_,
     sparse_allreduce_async,

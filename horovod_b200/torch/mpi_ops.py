@@ -93,6 +93,7 @@ gpu_topology = _basics.gpu_topology
 gpu_backend_info = _basics.gpu_backend_info
 runtime_stats = _basics.runtime_stats
 metrics = _basics.metrics
+control_plane_info = _basics.control_plane_info
 tunable_params = _basics.tunable_params
 
 

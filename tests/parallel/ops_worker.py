@@ -86,6 +86,10 @@ def _():
     assert hvd.local_size() == L and hvd.cross_size() == FAKE_HOSTS
     assert hvd.local_rank() == rank % L and hvd.cross_rank() == rank // L
     assert hvd.is_homogeneous()
+    # negotiation: shm among the ranks of a "host", host leaders over TCP (unless the test forces the TCP control plane)
+    info = hvd.control_plane_info()
+    if os.environ.get('HVD_CONTROL_PLANE') != 'tcp' and L > 1:
+        assert 'two-level' in info and '%d ranks of this host' % L in info and '%d host leaders' % FAKE_HOSTS in info, info
 
 
 @check('hierarchical_allreduce')

@@ -7,9 +7,18 @@ import torch
 
 import horovod_b200.torch as hvd
 
+FAKE_HOSTS = int(os.environ.get('HVD_TEST_FAKE_HOSTS', '0'))
+if FAKE_HOSTS > 1:          # present the ranks as FAKE_HOSTS machines: two-level control plane, TCP data plane
+    _r, _n = int(os.environ['HOROVOD_RANK']), int(os.environ['HOROVOD_SIZE'])
+    _L = _n // FAKE_HOSTS
+    os.environ.update(HOROVOD_HOSTNAME='fakehost%d' % (_r // _L), HOROVOD_LOCAL_RANK=str(_r % _L), HOROVOD_LOCAL_SIZE=str(_L),
+                      HOROVOD_CROSS_RANK=str(_r // _L), HOROVOD_CROSS_SIZE=str(FAKE_HOSTS))
+
 hvd.init()
 rank, size = hvd.rank(), hvd.size()
 gen = torch.Generator().manual_seed(7)
+if FAKE_HOSTS > 1:
+    assert 'two-level' in hvd.control_plane_info(), hvd.control_plane_info()
 
 
 def data(n, dtype, r):
@@ -87,5 +96,5 @@ for i, n, h in handles:
 info = os.environ.get('HVD_SHM_DATA_PLANE', '1')
 hvd.barrier()
 if rank == 0:
-    print('SHM PLANE OK', checked, 'plane=' + info)
+    print('SHM PLANE OK', checked, 'plane=' + info, '|', hvd.control_plane_info())
 hvd.shutdown()
