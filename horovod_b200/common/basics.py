@@ -343,10 +343,10 @@ class HorovodBasics(object):
         self.lib.hvd_gpu_backend_string(process_set_id, buf, 1024)
         return buf.value.decode()
 
-    def control_plane_info(self):
-        """What negotiation and host-tensor collectives of the global process set run on (shared memory / two-level / TCP)."""
+    def control_plane_info(self, process_set_id=0):
+        """What negotiation and host-tensor collectives of a process set run on (shared memory / two-level / TCP)."""
         buf = ctypes.create_string_buffer(512)
-        self.lib.hvd_control_plane_string(buf, 512)
+        self.lib.hvd_control_plane_string(int(getattr(process_set_id, 'process_set_id', process_set_id)), buf, 512)
         return buf.value.decode()
 
     def runtime_stats(self):

@@ -138,9 +138,9 @@ unsigned long long hvd_stat(int which) {
     default: return 0;
   }
 }
-int hvd_control_plane_string(char* out, int cap) {
+int hvd_control_plane_string(int process_set_id, char* out, int cap) {
   if (cap <= 0) return -1;
-  snprintf(out, (size_t)cap, "%s", Engine::Get().ControlPlaneString().c_str());
+  snprintf(out, (size_t)cap, "%s", Engine::Get().ControlPlaneString(process_set_id).c_str());
   return 0;
 }
 // named counters: hvd_metric(type, field) with type = ResponseType value, field = Engine::MetricField

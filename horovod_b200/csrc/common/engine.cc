@@ -105,6 +105,14 @@ void Engine::RequestFlush() { flush_ = true; Wake(); }
 void Engine::BeginWait() { waiters_.fetch_add(1); Wake(); }
 void Engine::EndWait() { waiters_.fetch_sub(1); }
 
+std::string Engine::ControlPlaneString(int process_set_id) {
+  if (!transport_) return "not initialised";
+  if (process_set_id == 0) return transport_->Describe();
+  auto ps = sets_.Get(process_set_id);
+  if (!ps) return "no such process set";
+  return ps->transport ? ps->transport->Describe() : std::string("not a member of this process set");
+}
+
 std::shared_ptr<ProcessSet> Engine::MakeProcessSet(const std::vector<int>& ranks) {
   auto ps = std::make_shared<ProcessSet>();
   ps->ranks = ranks;

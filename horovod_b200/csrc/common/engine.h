@@ -88,7 +88,7 @@ class Engine {
   ParameterManager& parameter_manager() { return params_; }
   Timeline& timeline() { return timeline_; }
   std::string TopologyString() const { return topology_str_; }
-  std::string ControlPlaneString() const { return transport_ ? transport_->Describe() : std::string("not initialised"); }
+  std::string ControlPlaneString(int process_set_id = 0);
   std::string last_error() const { std::lock_guard<std::mutex> l(err_mu_); return last_error_; }
   // statistics for tests / bench
   uint64_t cycles() const { return cycles_.load(); }

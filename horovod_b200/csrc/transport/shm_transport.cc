@@ -34,10 +34,22 @@ struct alignas(64) Slot {
   uint64_t data[2][kMaxWords];
 };
 
+// Process sets (sub-communicators) of a single-host job negotiate through their own, smaller slots: one "channel" per
+// Split() call.  Channels are handed out by a counter that advances on EVERY rank for EVERY Split (members or not), so the
+// members of a set agree on theirs without talking; they are not recycled — when they run out, a set uses the base transport.
+constexpr int kSubChannels = 8;
+constexpr int kSubWords = 64;   // 4096 cache bits per process set
+
+struct alignas(64) SubSlot {
+  std::atomic<uint64_t> seq;
+  uint64_t data[2][kSubWords];
+};
+
 struct Segment {
   std::atomic<uint32_t> magic;
   uint32_t nranks;
   Slot slots[kMaxRanks];
+  SubSlot sub[kSubChannels][kMaxRanks];
 };
 
 // A process that exited but has not been reaped yet (a zombie) still answers kill(pid, 0): look at its state as well.
@@ -56,10 +68,12 @@ bool ProcessAlive(int pid) {
 }
 
 // Spin (pause -> yield -> 50 us naps) until the slot's sequence reaches `k`; once a second make sure its owner still lives.
-void WaitSlot(Slot& s, uint64_t k, int r) {
+void WaitSeqReaches(std::atomic<uint64_t>& seq, const int32_t& owner_pid, uint64_t k, int r);
+void WaitSlot(Slot& s, uint64_t k, int r) { WaitSeqReaches(s.seq, s.pid, k, r); }
+void WaitSeqReaches(std::atomic<uint64_t>& seq, const int32_t& owner_pid, uint64_t k, int r) {
   uint64_t spins = 0;
   auto last_check = std::chrono::steady_clock::now();
-  while (s.seq.load(std::memory_order_acquire) < k) {
+  while (seq.load(std::memory_order_acquire) < k) {
     ++spins;
     if (spins < 2000) {
 #if defined(__x86_64__)
@@ -72,13 +86,49 @@ void WaitSlot(Slot& s, uint64_t k, int r) {
       auto now = std::chrono::steady_clock::now();
       if (now - last_check > std::chrono::seconds(1)) {
         last_check = now;
-        int pid = s.pid;
+        int pid = owner_pid;
         if (pid > 0 && !ProcessAlive(pid))
           throw TransportError("rank " + std::to_string(r) + " (pid " + std::to_string(pid) + ") died");
       }
     }
   }
 }
+
+// A process set of a single-host job: point-to-point traffic goes through the parent, the per-cycle bit exchange and the
+// barrier run on the set's own channel of the parent's segment.
+class ShmSubTransport : public SubTransport {
+ public:
+  ShmSubTransport(Transport* parent, std::vector<int> ranks, int my_index, Segment* seg, int channel)
+      : SubTransport(parent, std::move(ranks), my_index), seg_(seg), channel_(channel) {}
+  void AllreduceBits(uint64_t* and_words, int n_and, uint64_t* or_words, int n_or) override {
+    const int n = n_and + n_or;
+    if (size() == 1) return;
+    if (n > kSubWords) { Transport::AllreduceBits(and_words, n_and, or_words, n_or); return; }
+    const uint64_t k = ++round_;
+    const int buf = (int)(k & 1);
+    SubSlot* row = seg_->sub[channel_];
+    SubSlot& me = row[ranks_[my_]];
+    if (n_and) memcpy(me.data[buf], and_words, (size_t)n_and * 8);
+    if (n_or) memcpy(me.data[buf] + n_and, or_words, (size_t)n_or * 8);
+    me.seq.store(k, std::memory_order_release);
+    for (int i = 0; i < size(); ++i) {
+      if (i == my_) continue;
+      SubSlot& s = row[ranks_[i]];
+      WaitSeqReaches(s.seq, seg_->slots[ranks_[i]].pid, k, ranks_[i]);
+      for (int w = 0; w < n_and; ++w) and_words[w] &= s.data[buf][w];
+      for (int w = 0; w < n_or; ++w) or_words[w] |= s.data[buf][n_and + w];
+    }
+  }
+  void Barrier() override { AllreduceBits(nullptr, 0, nullptr, 0); }
+  std::string Describe() const override {
+    return "control: shared memory channel " + std::to_string(channel_) + " (" + std::to_string(size()) + " of the host's ranks); host data: ring over the base transport";
+  }
+
+ private:
+  Segment* seg_;
+  int channel_;
+  uint64_t round_ = 0;
+};
 
 class ShmControlTransport : public Transport {
  public:
@@ -96,6 +146,14 @@ class ShmControlTransport : public Transport {
     return true;
   }
   uint64_t ShmNextPiece() override { return piece_++; }
+  std::shared_ptr<Transport> Split(const std::vector<int>& ranks) override {
+    const int channel = next_channel_++;                         // advances on members and non-members alike
+    auto it = std::find(ranks.begin(), ranks.end(), rank());
+    if (it == ranks.end()) return nullptr;
+    const int idx = (int)(it - ranks.begin());
+    if (channel >= kSubChannels) return std::make_shared<SubTransport>(this, ranks, idx);
+    return std::make_shared<ShmSubTransport>(this, ranks, idx, seg_, channel);
+  }
   std::string Describe() const override {
     return std::string("control: shared memory (") + std::to_string(size()) + " ranks, one host); host data: " +
            (data_ ? "shared-memory slots of " + std::to_string(slot_bytes_) + " bytes" : std::string("ring over the base transport"));
@@ -139,6 +197,7 @@ class ShmControlTransport : public Transport {
   char* data_ = nullptr;
   size_t data_bytes_ = 0, slot_bytes_ = 0;
   uint64_t piece_ = 0;
+  int next_channel_ = 0;
 };
 // Maps `bytes` of a named segment; the creator reserves the pages up front (posix_fallocate) so that a too-small /dev/shm
 // shows up here as an error instead of a SIGBUS in the middle of a collective.

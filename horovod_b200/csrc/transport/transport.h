@@ -94,7 +94,7 @@ class SubTransport : public Transport {
   }
   int host_id(int i) const override { return parent_->host_id(ranks_[i]); }
 
- private:
+ protected:
   Transport* parent_;
   std::vector<int> ranks_;
   int my_;

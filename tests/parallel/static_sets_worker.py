@@ -21,6 +21,10 @@ g = hvd.allgather(torch.tensor([float(r)]), process_set=mine, name='static.ag')
 assert g.tolist() == [float(q) for q in mine.ranks]
 b = hvd.broadcast(torch.tensor([float(r)]), root_rank=mine.ranks[-1], process_set=mine, name='static.bc')
 assert b.item() == float(mine.ranks[-1])
+# on one host the sets negotiate through their own shared-memory channel (unless the test forces TCP)
+if os.environ.get('HVD_CONTROL_PLANE') != 'tcp' and n > 2:
+    assert 'shared memory channel' in hvd.control_plane_info(mine), hvd.control_plane_info(mine)
+    assert 'not a member' in hvd.control_plane_info(other)
 try:
     hvd.allreduce(torch.ones(1), process_set=other, name='static.notmember')
     raise AssertionError('a non-member must not be able to use the set')
