@@ -70,16 +70,28 @@ bool ProcessAlive(int pid) {
 // Spin (pause -> yield -> 50 us naps) until the slot's sequence reaches `k`; once a second make sure its owner still lives.
 void WaitSeqReaches(std::atomic<uint64_t>& seq, const int32_t& owner_pid, uint64_t k, int r);
 void WaitSlot(Slot& s, uint64_t k, int r) { WaitSeqReaches(s.seq, s.pid, k, r); }
+// Waiting policy: `pauses` busy polls (lowest latency, burns a core), then `yields` sched_yield polls (lets a runnable peer
+// on the same core in), then 50 us naps (a job whose ranks have nothing to agree on must not spin).  Containers with a CPU
+// quota may prefer fewer yields: HVD_SHM_SPIN_PAUSES / HVD_SHM_SPIN_YIELDS.
+struct SpinPolicy {
+  uint64_t pauses = 2000, yields = 18000;
+  SpinPolicy() {
+    if (const char* e = getenv("HVD_SHM_SPIN_PAUSES")) pauses = (uint64_t)std::max(0LL, atoll(e));
+    if (const char* e = getenv("HVD_SHM_SPIN_YIELDS")) yields = (uint64_t)std::max(0LL, atoll(e));
+  }
+};
+
 void WaitSeqReaches(std::atomic<uint64_t>& seq, const int32_t& owner_pid, uint64_t k, int r) {
+  static const SpinPolicy policy;
   uint64_t spins = 0;
   auto last_check = std::chrono::steady_clock::now();
   while (seq.load(std::memory_order_acquire) < k) {
     ++spins;
-    if (spins < 2000) {
+    if (spins < policy.pauses) {
 #if defined(__x86_64__)
       __builtin_ia32_pause();
 #endif
-    } else if (spins < 20000) {
+    } else if (spins < policy.pauses + policy.yields) {
       std::this_thread::yield();
     } else {
       std::this_thread::sleep_for(std::chrono::microseconds(50));
