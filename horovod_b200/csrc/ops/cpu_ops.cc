@@ -184,6 +184,45 @@ bool ShmBroadcast(Transport* t, char* buf, int64_t bytes, int root) {
   return true;
 }
 
+// Every rank publishes, in front of each piece of its send buffer, where the block for each destination starts (a
+// receiver knows how much it gets from a peer, not where that block sits in the peer's buffer) and how long the buffer is
+// (so that all ranks agree on the number of pieces after the first barrier).
+bool ShmAlltoallv(Transport* t, const char* in, const std::vector<int64_t>& sd, char* out, const std::vector<int64_t>& rd,
+                  const std::vector<int64_t>& rb) {
+  ShmData d;
+  if (!t->ShmDataPlane(&d)) return false;
+  const int n = t->size(), r = t->rank();
+  const int64_t hdr = (int64_t)(n + 1) * 8;
+  const int64_t S = (int64_t)d.slot_bytes - hdr;
+  if (S < 4096) return false;
+  const int64_t my_total = sd[n];
+  int64_t pieces = 1;
+  for (int64_t p = 0; p < pieces; ++p) {
+    const int half = (int)(t->ShmNextPiece() & 1);
+    char* mine = d.slot(r, half);
+    int64_t* h = (int64_t*)mine;
+    for (int i = 0; i < n; ++i) h[i] = sd[i];
+    h[n] = my_total;
+    const int64_t len = std::min(S, my_total - p * S);
+    if (len > 0) memcpy(mine + hdr, in + p * S, (size_t)len);
+    t->Barrier();
+    if (p == 0) {
+      int64_t longest = 0;
+      for (int q = 0; q < n; ++q) longest = std::max(longest, ((const int64_t*)d.slot(q, half))[n]);
+      pieces = std::max<int64_t>(1, (longest + S - 1) / S);
+    }
+    const int64_t piece_lo = p * S, piece_hi = piece_lo + S;
+    for (int q = 0; q < n; ++q) {
+      if (q == r || rb[q] == 0) continue;
+      const char* theirs = d.slot(q, half);
+      const int64_t want_lo = ((const int64_t*)theirs)[r], want_hi = want_lo + rb[q];
+      const int64_t lo = std::max(want_lo, piece_lo), hi = std::min(want_hi, piece_hi);
+      if (hi > lo) memcpy(out + rd[q] + (lo - want_lo), theirs + hdr + (lo - piece_lo), (size_t)(hi - lo));
+    }
+  }
+  return true;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------
@@ -263,6 +302,7 @@ void Alltoallv(Transport* t, const void* in, const std::vector<int64_t>& sb, voi
   for (int i = 0; i < n; ++i) { sd[i + 1] = sd[i] + sb[i]; rd[i + 1] = rd[i] + rb[i]; }
   const char* i8 = (const char*)in; char* o8 = (char*)out;
   if (sb[r]) memcpy(o8 + rd[r], i8 + sd[r], (size_t)sb[r]);
+  if (n > 1 && ShmAlltoallv(t, i8, sd, o8, rd, rb)) return;
   for (int s = 1; s < n; ++s) {
     int to = (r + s) % n, from = (r - s + n) % n;
     t->SendRecv(to, i8 + sd[to], (size_t)sb[to], from, o8 + rd[from], (size_t)rb[from]);

@@ -81,6 +81,22 @@ struct SpinPolicy {
   }
 };
 
+// Peers' pids are only meaningful inside one pid namespace.  Ranks that share /dev/shm but not the pid namespace (one
+// container per rank with host IPC) would look dead to each other: the wrappers verify once, right after start-up, that
+// every peer's pid is visible and otherwise switch the liveness check off (failures then surface through the base transport).
+std::atomic<bool> g_trust_pids{true};
+
+void VerifyPeerPids(Segment* seg, int nslots, int my_slot) {
+  for (int i = 0; i < nslots; ++i) {
+    const int pid = seg->slots[i].pid;
+    if (i != my_slot && pid > 0 && !ProcessAlive(pid)) {
+      if (g_trust_pids.exchange(false))
+        LOG(WARNING) << "peer pids are not visible from this process (separate pid namespaces?); shared-memory waits will not detect dead peers";
+      return;
+    }
+  }
+}
+
 void WaitSeqReaches(std::atomic<uint64_t>& seq, const int32_t& owner_pid, uint64_t k, int r) {
   static const SpinPolicy policy;
   uint64_t spins = 0;
@@ -98,7 +114,7 @@ void WaitSeqReaches(std::atomic<uint64_t>& seq, const int32_t& owner_pid, uint64
       auto now = std::chrono::steady_clock::now();
       if (now - last_check > std::chrono::seconds(1)) {
         last_check = now;
-        int pid = owner_pid;
+        int pid = g_trust_pids.load(std::memory_order_relaxed) ? (int)owner_pid : 0;
         if (pid > 0 && !ProcessAlive(pid))
           throw TransportError("rank " + std::to_string(r) + " (pid " + std::to_string(pid) + ") died");
       }
@@ -347,7 +363,11 @@ std::shared_ptr<Transport> WrapWithHierarchicalControl(std::shared_ptr<Transport
     LOG(DEBUG) << "two-level control plane unavailable; negotiation stays on the base transport";
     return base;
   }
-  return std::make_shared<HierShmControlTransport>(std::move(base), seg, std::move(local), li, std::move(leaders));
+  const int nlocal = (int)local.size();
+  auto hier = std::make_shared<HierShmControlTransport>(std::move(base), seg, std::move(local), li, std::move(leaders));
+  hier->Barrier();                       // every rank of this host has published its pid
+  VerifyPeerPids(seg, nlocal, li);
+  return hier;
 }
 
 namespace {
@@ -389,6 +409,8 @@ std::shared_ptr<Transport> WrapWithShmControl(std::shared_ptr<Transport> base, c
     return base;
   }
   auto shm = std::make_shared<ShmControlTransport>(base, seg);
+  shm->Barrier();                        // every rank has published its pid
+  VerifyPeerPids(seg, base->size(), base->rank());
 
   // ---- data plane (host tensors of a single-host job never touch a socket) ----
   const char* dp = getenv("HVD_SHM_DATA_PLANE");

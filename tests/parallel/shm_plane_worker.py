@@ -80,6 +80,24 @@ for rows in (size, size * 7 + 1, 4000 + size - 1):
     starts = [r * base + min(r, extra) for r in range(size + 1)]
     assert torch.equal(out, full[starts[rank]:starts[rank + 1]]), rows
 
+# alltoall: even splits, uneven splits (rank r sends (r + q + 1) * k rows to rank q), empty blocks, more than one piece
+for k in (1, 7, 400):
+    splits = [(rank + q + 1) * k if (rank + q) % 3 else 0 for q in range(size)]
+    rows = sum(splits)
+    x = torch.arange(rows * 2, dtype=torch.float32).reshape(rows, 2) + 10000 * rank
+    out, rsplits = hvd.alltoall(x, splits=torch.tensor(splits), name='a2a.%d' % k)
+    expect, exp_splits = [], []
+    for q in range(size):                       # what rank q sends to me
+        qs = [(q + d + 1) * k if (q + d) % 3 else 0 for d in range(size)]
+        start = sum(qs[:rank])
+        full = torch.arange(sum(qs) * 2, dtype=torch.float32).reshape(sum(qs), 2) + 10000 * q
+        expect.append(full[start:start + qs[rank]])
+        exp_splits.append(qs[rank])
+    assert rsplits.tolist() == exp_splits, (rsplits, exp_splits)
+    assert torch.equal(out, torch.cat(expect)), k
+even = hvd.alltoall(torch.arange(size * 3, dtype=torch.int64) + 100 * rank, name='a2a.even')
+assert even.tolist() == [100 * q + 3 * rank + j for q in range(size) for j in range(3)]
+
 # long mixed async sequence with fusion
 handles = []
 for i in range(40):
