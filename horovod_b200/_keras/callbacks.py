@@ -211,3 +211,45 @@ class UpdateEpochStateCallback(tf.keras.callbacks.Callback):
 
     def on_epoch_end(self, epoch, logs=None):
         self.state.epoch = self._initial + epoch + 1 if epoch < self._initial else epoch + 1
+
+
+class BestModelCheckpoint(tf.keras.callbacks.Callback):
+    """Keeps the best model seen so far (by `monitor`) at `filepath`; the estimators set `filepath` to the run's checkpoint
+    in the Store (reference _keras/callbacks.py `BestModelCheckpoint`: a ModelCheckpoint with save_best_only=True whose
+    path is filled in later).  Written on the Callback protocol only, so it does not depend on the ModelCheckpoint class of
+    a particular Keras version; `save_fn(model, filepath)` overrides how the model is written."""
+
+    def __init__(self, monitor='val_loss', verbose=0, mode='auto', save_freq='epoch', filepath=None, save_weights_only=False,
+                 save_fn=None):
+        super().__init__()
+        if mode not in ('auto', 'min', 'max'):
+            raise ValueError("mode must be 'auto', 'min' or 'max'")
+        if mode == 'auto':
+            mode = 'max' if any(key in monitor for key in ('acc', 'auc', 'fmeasure', 'f1')) else 'min'
+        self.monitor, self.verbose, self.mode, self.save_freq = monitor, verbose, mode, save_freq
+        self.filepath, self.save_weights_only, self.save_fn = filepath, save_weights_only, save_fn
+        self.best = float('inf') if mode == 'min' else float('-inf')
+        self.best_epoch = None
+
+    def _improved(self, value):
+        return value < self.best if self.mode == 'min' else value > self.best
+
+    def on_epoch_end(self, epoch, logs=None):
+        value = (logs or {}).get(self.monitor)
+        if value is None:
+            return
+        value = float(value)
+        if not self._improved(value):
+            return
+        self.best, self.best_epoch = value, epoch
+        if self.filepath is None:
+            return
+        path = self.filepath.format(epoch=epoch + 1, **(logs or {})) if '{' in self.filepath else self.filepath
+        if self.save_fn is not None:
+            self.save_fn(self.model, path)
+        elif self.save_weights_only:
+            self.model.save_weights(path)
+        else:
+            self.model.save(path)
+        if self.verbose:
+            print('Epoch %d: %s improved to %.5f, saving model to %s' % (epoch + 1, self.monitor, value, path))

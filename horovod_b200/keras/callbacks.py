@@ -1,4 +1,4 @@
-"""Keras callbacks (parity: horovod/tensorflow/keras/callbacks.py)."""
+"""Keras callbacks (parity: horovod/keras/callbacks.py)."""
 from horovod_b200._keras.callbacks import (  # noqa: F401
     BroadcastGlobalVariablesCallback, MetricAverageCallback, LearningRateScheduleCallback, LearningRateWarmupCallback,
     BestModelCheckpoint)

@@ -294,6 +294,46 @@ def broadcast_global_variables(root_rank):
     return broadcast_variables(tf.compat.v1.global_variables(), root_rank)
 
 
+def broadcast_object_fn(root_rank=0, session=None, name=None, process_set=_ops.global_process_set):
+    """Returns fn(obj) -> root_rank's obj (the reference builds a reusable graph for TF1 sessions; here the object path is
+    eager in both modes, so this is a closure over `broadcast_object`)."""
+    def _bcast(obj):
+        return _ns['broadcast_object'](obj, root_rank=root_rank, name=name, process_set=process_set)
+    return _bcast
+
+
+class BroadcastGlobalVariablesHook(getattr(getattr(tf.compat.v1, 'train', None), 'SessionRunHook', object)):
+    """TF1 `SessionRunHook` that broadcasts all global variables from `root_rank` once the session exists (reference
+    tensorflow/__init__.py:269-303).  With TF2 eager execution use `broadcast_variables` / the Keras callback instead."""
+
+    def __init__(self, root_rank, device=''):
+        super().__init__()
+        self.root_rank, self.device = root_rank, device
+        self.bcast_op = None
+
+    def begin(self):
+        graph = tf.compat.v1.get_default_graph() if hasattr(tf.compat.v1, 'get_default_graph') else None
+        if self.bcast_op is None or getattr(self.bcast_op, 'graph', None) is not graph:
+            variables = tf.compat.v1.global_variables()
+            self.bcast_op = tf.group(*[v.assign(broadcast(v, self.root_rank, name='bcast_hook_%d' % i)) for i, v in enumerate(variables)]) \
+                if hasattr(tf, 'group') else [v.assign(broadcast(v, self.root_rank, name='bcast_hook_%d' % i)) for i, v in enumerate(variables)]
+
+    def after_create_session(self, session, coord):
+        if session is not None and hasattr(session, 'run') and not isinstance(self.bcast_op, list):
+            session.run(self.bcast_op)
+
+
+def check_num_rank_power_of_2(num_rank):
+    """Adasum's vector-halving needs a power-of-two number of ranks."""
+    from horovod_b200.common.util import num_rank_is_power_2
+    return num_rank_is_power_2(num_rank)
+
+
+def gpu_available():
+    from horovod_b200.common.util import gpu_available as _gpu
+    return _gpu('torch')
+
+
 # ---- gradient reduction helpers ---------------------------------------------------------------------------------------------
 def _group_indices(variables, groups):
     """Returns a list of index lists.  `groups`: None (one list per variable), int (that many round-robin-free

@@ -28,6 +28,30 @@ def DistributedOptimizer(optimizer, name=None, device_dense='', device_sparse=''
                                               average_aggregated_gradients, groups, process_set, scale_local_gradients)
 
 
+def PartialDistributedOptimizer(optimizer, name=None, device_dense='', device_sparse='', compression=Compression.none,
+                                sparse_as_dense=False, gradient_predivide_factor=1.0, op=Average, backward_passes_per_step=1,
+                                average_aggregated_gradients=False, groups=None, process_set=global_process_set,
+                                local_layers=None, scale_local_gradients=True):
+    """DistributedOptimizer whose gradients for the variables of `local_layers` stay local (they are only scaled by
+    1/size when `scale_local_gradients`): for model-parallel layers such as per-rank embedding shards (reference
+    tensorflow/keras/__init__.py:173-230)."""
+    if local_layers is None:
+        local_layers = []
+    elif not isinstance(local_layers, (list, tuple)):
+        local_layers = [local_layers]
+    if not all(hasattr(layer, 'trainable_weights') for layer in local_layers):
+        raise ValueError('All local layers must be of tf.keras.layers.Layer type.')
+    opt = DistributedOptimizer(optimizer, name=name, device_dense=device_dense, device_sparse=device_sparse, compression=compression,
+                               sparse_as_dense=sparse_as_dense, gradient_predivide_factor=gradient_predivide_factor, op=op,
+                               backward_passes_per_step=backward_passes_per_step,
+                               average_aggregated_gradients=average_aggregated_gradients, groups=groups, process_set=process_set,
+                               scale_local_gradients=scale_local_gradients)
+    for layer in local_layers:
+        for var in layer.trainable_weights:
+            opt.register_local_var(var)
+    return opt
+
+
 def broadcast_global_variables(root_rank):
     return _impl.broadcast_global_variables(tf.keras.backend, root_rank)
 

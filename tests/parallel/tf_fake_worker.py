@@ -148,6 +148,39 @@ local_opt.register_local_var(v5)
 local_opt.apply_gradients([(tf.constant(np.ones(1) * (r + 1)), v4), (tf.constant(np.ones(1) * n), v5)])
 np.testing.assert_allclose(v4.numpy(), [-(n + 1) / 2])
 np.testing.assert_allclose(v5.numpy(), [-1.0])   # local variable: not reduced, scaled by 1/size
+# PartialDistributedOptimizer: the variables of `local_layers` are registered as local
+class _Layer:
+    def __init__(self, *variables):
+        self.trainable_weights = list(variables)
+
+
+v6, v7 = tf.Variable(np.zeros(1), name='v6:0'), tf.Variable(np.zeros(1), name='v7:0')
+popt = hvdk.PartialDistributedOptimizer(SGD(1.0), local_layers=[_Layer(v7)])
+popt.apply_gradients([(tf.constant(np.ones(1) * (r + 1)), v6), (tf.constant(np.ones(1) * n), v7)])
+np.testing.assert_allclose(v6.numpy(), [-(n + 1) / 2])
+np.testing.assert_allclose(v7.numpy(), [-1.0])
+try:
+    hvdk.PartialDistributedOptimizer(SGD(1.0), local_layers=[object()])
+    raise AssertionError('local_layers must be layers')
+except ValueError:
+    pass
+import horovod_b200.keras as hk
+assert hk.PartialDistributedOptimizer is hvdk.PartialDistributedOptimizer and hk.callbacks.BestModelCheckpoint is hvdk.callbacks.BestModelCheckpoint
+assert hk.elastic.KerasState is hvdk.elastic.KerasState
+# BestModelCheckpoint: saves only on improvement, mode inferred from the metric name
+saved = []
+best = hvdk.callbacks.BestModelCheckpoint(monitor='val_loss', filepath='/tmp/ckpt-{epoch}', save_fn=lambda model, path: saved.append(path))
+best.set_model(object())
+for epoch, value in enumerate([1.0, 0.5, 0.7, 0.4]):
+    best.on_epoch_end(epoch, {'val_loss': value})
+assert saved == ['/tmp/ckpt-1', '/tmp/ckpt-2', '/tmp/ckpt-4'] and best.best == 0.4 and best.best_epoch == 3
+assert hvdk.callbacks.BestModelCheckpoint(monitor='val_acc').mode == 'max'
+# TF extras
+assert hvd.broadcast_object_fn(root_rank=n - 1, name='bofn')({'from': r}) == {'from': n - 1}
+assert hvd.check_num_rank_power_of_2(4) and not hvd.check_num_rank_power_of_2(6) and hvd.gpu_available() in (True, False)
+hook = hvd.BroadcastGlobalVariablesHook(0)
+hook.begin()
+hook.after_create_session(None, None)
 try:
     hvdk.DistributedOptimizer(SGD(), op=hvd.Sum, gradient_predivide_factor=2.0)
     raise AssertionError('predivide with op != Average must be rejected')
