@@ -97,3 +97,43 @@ def test_hard_crash_of_one_worker_terminates_the_job(native_built):
     rc, out = hvdrun('-np', '2', sys.executable, '-c', code, timeout=90)
     assert rc != 0 and time.time() - t0 < 60, out
     assert 'Process name: 1' in out and ('Exit code: 137' in out or 'Exit code: -9' in out), out
+
+
+def test_workers_do_not_outlive_a_killed_launcher(native_built, tmp_path):
+    """SIGKILL the launcher (it cannot run any cleanup): the per-worker supervisor processes notice the parent is gone and
+    take the workers down — nothing keeps spinning in a collective forever."""
+    import signal
+    import time
+    script = tmp_path / 'sleeper.py'
+    script.write_text(
+        "import horovod_b200.torch as hvd, torch, time, os\n"
+        "hvd.init()\n"
+        "open(%r + '/pid.%%d' %% hvd.rank(), 'w').write(str(os.getpid()))\n"
+        "for i in range(3000):\n"
+        "    hvd.allreduce(torch.ones(4), name='s')\n"
+        "    time.sleep(0.05)\n" % str(tmp_path))
+    env = dict(os.environ, PYTHONPATH=REPO + os.pathsep + os.environ.get('PYTHONPATH', ''), HOROVOD_LOG_LEVEL='warning')
+    launcher = subprocess.Popen([sys.executable, '-m', 'horovod_b200.runner.launch', '-np', '2', sys.executable, str(script)],
+                                env=env, cwd=REPO, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    try:
+        deadline = time.time() + 60
+        while time.time() < deadline and not all((tmp_path / ('pid.%d' % r)).exists() for r in range(2)):
+            time.sleep(0.2)
+        pids = [int((tmp_path / ('pid.%d' % r)).read_text()) for r in range(2)]
+        launcher.send_signal(signal.SIGKILL)
+        launcher.wait(10)
+
+        def alive(pid):
+            try:
+                os.kill(pid, 0)
+            except ProcessLookupError:
+                return False
+            with open('/proc/%d/stat' % pid) as f:            # a zombie waiting to be reaped by init is dead for our purposes
+                return f.read().rsplit(')', 1)[1].split()[0] not in ('Z', 'X')
+        deadline = time.time() + 30
+        while time.time() < deadline and any(alive(p) for p in pids):
+            time.sleep(0.5)
+        assert not any(alive(p) for p in pids), 'workers %s survived their launcher' % [p for p in pids if alive(p)]
+    finally:
+        if launcher.poll() is None:
+            launcher.kill()
