@@ -122,6 +122,9 @@ void WaitSeqReaches(std::atomic<uint64_t>& seq, const int32_t& owner_pid, uint64
   }
 }
 
+char* MapNamed(const std::string& name, size_t bytes, bool create);
+size_t DataSlotBytes();
+
 // A process set of a single-host job: point-to-point traffic goes through the parent, the per-cycle bit exchange and the
 // barrier run on the set's own channel of the parent's segment.
 class ShmSubTransport : public SubTransport {
@@ -149,13 +152,43 @@ class ShmSubTransport : public SubTransport {
   }
   void Barrier() override { AllreduceBits(nullptr, 0, nullptr, 0); }
   std::string Describe() const override {
-    return "control: shared memory channel " + std::to_string(channel_) + " (" + std::to_string(size()) + " of the host's ranks); host data: ring over the base transport";
+    return "control: shared memory channel " + std::to_string(channel_) + " (" + std::to_string(size()) + " of the host's ranks); host data: " +
+           (data_ ? "shared-memory slots of " + std::to_string(slot_bytes_) + " bytes" : std::string("ring over the base transport"));
+  }
+  ~ShmSubTransport() override { if (data_) munmap(data_, data_bytes_); }
+  bool ShmDataPlane(ShmData* out) override {
+    if (!data_) return false;
+    out->base = data_; out->slot_bytes = slot_bytes_;
+    return true;
+  }
+  uint64_t ShmNextPiece() override { return piece_++; }
+
+  // Collective among the members (they are all inside Split() at the same time): the first member creates the set's own
+  // data segment, the others map it; the set's fresh control channel carries the two agreement rounds.
+  void CreateDataPlane(const std::string& name) {
+    if (size() < 2) return;
+    const char* dp = getenv("HVD_SHM_DATA_PLANE");
+    if (dp && atoi(dp) == 0) return;
+    const size_t slot = DataSlotBytes(), total = slot * 2 * (size_t)size();
+    char* data = nullptr;
+    if (my_ == 0) { shm_unlink(name.c_str()); data = MapNamed(name, total, true); }
+    uint64_t ok = my_ == 0 ? (uint64_t)(data != nullptr) : 1;
+    AllreduceBits(&ok, 1, nullptr, 0);
+    if (ok && my_ != 0) data = MapNamed(name, total, false);
+    uint64_t ok2 = ok ? (uint64_t)(data != nullptr) : 0;
+    AllreduceBits(&ok2, 1, nullptr, 0);
+    if (my_ == 0) shm_unlink(name.c_str());
+    if (!ok2) { if (data) munmap(data, total); return; }
+    data_ = data; data_bytes_ = total; slot_bytes_ = slot;
   }
 
  private:
   Segment* seg_;
   int channel_;
   uint64_t round_ = 0;
+  char* data_ = nullptr;
+  size_t data_bytes_ = 0, slot_bytes_ = 0;
+  uint64_t piece_ = 0;
 };
 
 class ShmControlTransport : public Transport {
@@ -180,8 +213,11 @@ class ShmControlTransport : public Transport {
     if (it == ranks.end()) return nullptr;
     const int idx = (int)(it - ranks.begin());
     if (channel >= kSubChannels) return std::make_shared<SubTransport>(this, ranks, idx);
-    return std::make_shared<ShmSubTransport>(this, ranks, idx, seg_, channel);
+    auto sub = std::make_shared<ShmSubTransport>(this, ranks, idx, seg_, channel);
+    if (data_) sub->CreateDataPlane(name_ + "-c" + std::to_string(channel) + "-d");
+    return sub;
   }
+  void set_name(const std::string& n) { name_ = n; }
   std::string Describe() const override {
     return std::string("control: shared memory (") + std::to_string(size()) + " ranks, one host); host data: " +
            (data_ ? "shared-memory slots of " + std::to_string(slot_bytes_) + " bytes" : std::string("ring over the base transport"));
@@ -226,7 +262,14 @@ class ShmControlTransport : public Transport {
   size_t data_bytes_ = 0, slot_bytes_ = 0;
   uint64_t piece_ = 0;
   int next_channel_ = 0;
+  std::string name_;
 };
+size_t DataSlotBytes() {
+  size_t slot = 1u << 20;
+  if (const char* sb = getenv("HVD_SHM_SLOT_BYTES")) slot = (size_t)std::max(4096LL, atoll(sb));
+  return (slot + 4095) & ~(size_t)4095;
+}
+
 // Maps `bytes` of a named segment; the creator reserves the pages up front (posix_fallocate) so that a too-small /dev/shm
 // shows up here as an error instead of a SIGBUS in the middle of a collective.
 char* MapNamed(const std::string& name, size_t bytes, bool create) {
@@ -409,15 +452,14 @@ std::shared_ptr<Transport> WrapWithShmControl(std::shared_ptr<Transport> base, c
     return base;
   }
   auto shm = std::make_shared<ShmControlTransport>(base, seg);
+  shm->set_name(name);
   shm->Barrier();                        // every rank has published its pid
   VerifyPeerPids(seg, base->size(), base->rank());
 
   // ---- data plane (host tensors of a single-host job never touch a socket) ----
   const char* dp = getenv("HVD_SHM_DATA_PLANE");
   if (dp && atoi(dp) == 0) return shm;
-  size_t slot = 1u << 20;
-  if (const char* sb = getenv("HVD_SHM_SLOT_BYTES")) slot = (size_t)std::max(4096LL, atoll(sb));
-  slot = (slot + 4095) & ~(size_t)4095;
+  const size_t slot = DataSlotBytes();
   const size_t total = slot * 2 * (size_t)base->size();
   const std::string dname = name + "-d";
   char* data = nullptr;

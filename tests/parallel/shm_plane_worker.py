@@ -111,6 +111,32 @@ for i, n, h in handles:
     out = hvd.synchronize(h)
     assert torch.all(out == sum(r + i for r in range(size))) and out.numel() == n
 
+# process sets have their own control channel and their own data slots
+if size >= 3 and FAKE_HOSTS <= 1:
+    evens = hvd.add_process_set([q for q in range(size) if q % 2 == 0])
+    odds = hvd.add_process_set([q for q in range(size) if q % 2 == 1])
+    mine = evens if rank % 2 == 0 else odds
+    members = mine.ranks
+    desc = hvd.control_plane_info(mine)
+    if os.environ.get('HVD_CONTROL_PLANE') != 'tcp':
+        assert 'shared memory channel' in desc, desc
+        if os.environ.get('HVD_SHM_DATA_PLANE', '1') != '0' and len(members) > 1:
+            assert 'shared-memory slots' in desc, desc
+    for n in (3, 5000, 70001):
+        x = torch.full((n,), float(rank + 1), dtype=torch.float64)
+        out = hvd.allreduce(x, op=hvd.Sum, process_set=mine, name='ps.ar.%d' % n)
+        assert torch.all(out == sum(q + 1 for q in members)), (n, out[:3])
+        g = hvd.allgather(torch.full((rank + 1, 2), float(rank)), process_set=mine, name='ps.ag.%d' % n)
+        assert g.shape[0] == sum(q + 1 for q in members) and g[0, 0] == members[0] and g[-1, 0] == members[-1]
+        b = torch.full((n,), float(rank))
+        hvd.broadcast_(b, root_rank=members[-1], process_set=mine, name='ps.bc.%d' % n)
+        assert torch.all(b == members[-1])
+        # interleave with the global set: the two planes keep separate piece counters and slots
+        tot = hvd.allreduce(torch.full((n,), 1.0), op=hvd.Sum, name='ps.global.%d' % n)
+        assert torch.all(tot == size)
+    hvd.remove_process_set(odds)
+    hvd.remove_process_set(evens)
+
 info = os.environ.get('HVD_SHM_DATA_PLANE', '1')
 hvd.barrier()
 if rank == 0:

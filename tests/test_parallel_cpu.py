@@ -150,7 +150,7 @@ def test_broadcast_optimizer_state_every_torch_optimizer(native_built):
 
 
 @pytest.mark.parametrize("np_,env", [(2, {"HVD_SHM_SLOT_BYTES": "4096"}), (3, {"HVD_SHM_SLOT_BYTES": "8192"}),
-                                     (3, {"HVD_SHM_DATA_PLANE": "0"}), (2, {"HVD_CONTROL_PLANE": "tcp"}),
+                                     (3, {"HVD_SHM_DATA_PLANE": "0"}), (2, {"HVD_CONTROL_PLANE": "tcp"}), (4, {"HVD_SHM_SLOT_BYTES": "16384"}),
                                      (4, {"HVD_TEST_FAKE_HOSTS": "2"})])
 def test_shared_memory_data_plane(native_built, np_, env):
     """Host-tensor collectives through the shm slots with a tiny slot size (many pieces, double buffering across different
