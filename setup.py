@@ -54,9 +54,9 @@ setup(
     name='horovod_b200',
     version='0.1.0',
     description='Blackwell-native data-parallel collective library with the capabilities of Horovod',
-    packages=find_packages(include=['horovod_b200', 'horovod_b200.*']),
+    packages=find_packages(include=['horovod_b200', 'horovod_b200.*', 'horovod']),
     package_data={'horovod_b200': ['lib/*.so', 'csrc/**/*']},
-    scripts=['bin/hvdrun'],
+    scripts=['bin/hvdrun', 'bin/horovodrun'],
     python_requires='>=3.9',
     install_requires=['torch', 'numpy', 'psutil', 'pyyaml', 'cloudpickle'],
     extras_require={'spark': ['pyspark', 'pyarrow', 'pandas'], 'ray': ['ray'], 'tensorflow': ['tensorflow'], 'mxnet': ['mxnet']},

@@ -137,3 +137,12 @@ def test_workers_do_not_outlive_a_killed_launcher(native_built, tmp_path):
     finally:
         if launcher.poll() is None:
             launcher.kill()
+
+
+def test_reference_program_runs_under_the_horovod_namespace(native_built):
+    """`import horovod.torch as hvd` + `horovodrun -np 2`: the drop-in namespace resolves to this framework's modules."""
+    env = dict(os.environ, PYTHONPATH=REPO + os.pathsep + os.environ.get('PYTHONPATH', ''), HOROVOD_LOG_LEVEL='warning')
+    r = subprocess.run([sys.executable, os.path.join(REPO, 'bin', 'horovodrun'), '-np', '2', sys.executable,
+                        os.path.join(REPO, 'tests', 'parallel', 'compat_namespace_worker.py')], env=env, cwd=REPO,
+                       capture_output=True, text=True, timeout=200)
+    assert r.returncode == 0 and 'COMPAT OK' in r.stdout, (r.stdout[-2000:], r.stderr[-3000:])
