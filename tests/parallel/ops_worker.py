@@ -363,15 +363,20 @@ def _():
         raise AssertionError('allgather dim mismatch must raise')
     except HorovodInternalError:
         pass
-    # duplicate in-flight name
+    # duplicate in-flight name.  A name is in flight until its response starts executing, which cannot happen before EVERY rank
+    # submitted it: rank 0 submits late, so on the other ranks the second submission deterministically meets the first.
     t = torch.ones(1 << 18, device=DEV)
-    h = hvd.allreduce_async(t, name='dup')
-    try:
-        hvd.allreduce_async(t, name='dup')
-        dup_raised = False
-    except (ValueError, HorovodInternalError):
-        dup_raised = True
-    hvd.synchronize(h)
+    if rank == 0:
+        time.sleep(1.0)
+        hvd.synchronize(hvd.allreduce_async(t, name='dup'))
+    else:
+        h = hvd.allreduce_async(t, name='dup')
+        try:
+            hvd.allreduce_async(t, name='dup')
+            raise AssertionError('a second in-flight submission of the same name must be rejected')
+        except (ValueError, HorovodInternalError) as e:
+            assert 'dup' in str(e), e
+        hvd.synchronize(h)
     # the library stays usable after errors
     assert torch.allclose(hvd.allreduce(torch.ones(2, device=DEV), op=hvd.Sum), torch.full((2,), float(size), device=DEV))
 

@@ -202,20 +202,22 @@ def _():
 
 @check('duplicate_names_per_op')
 def _():
-    big = torch.ones(1 << 16, device=DEV)
+    # rank 0 submits late: until then the first submission of the other ranks cannot start executing, so their second one
+    # deterministically finds the name in flight (see ops_worker.py 'errors')
     for fn, kw in ((hvd.allgather_async, {}), (hvd.broadcast_async, {'root_rank': 0}), (hvd.reducescatter_async, {})):
         t = torch.ones(size * 64, 16, device=DEV)
-        h = fn(t, name='dupname', **kw)
-        try:
-            h2 = fn(t, name='dupname', **kw)
-            hvd.synchronize(h2)
-            second_ok = True
-        except (ValueError, HorovodInternalError) as e:
-            second_ok = False
-            assert 'dupname' in str(e) or 'duplicate' in str(e).lower() or 'same name' in str(e).lower(), e
-        hvd.synchronize(h)
+        if rank == 0:
+            time.sleep(0.5)
+            hvd.synchronize(fn(t, name='dupname', **kw))
+        else:
+            h = fn(t, name='dupname', **kw)
+            try:
+                fn(t, name='dupname', **kw)
+                raise AssertionError('duplicate in-flight name must be rejected')
+            except (ValueError, HorovodInternalError) as e:
+                assert 'dupname' in str(e) or 'duplicate' in str(e).lower() or 'same name' in str(e).lower(), e
+            hvd.synchronize(h)
         hvd.barrier()
-    del big
 
 
 @check('sparse_gradients')

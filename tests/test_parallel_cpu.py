@@ -158,3 +158,8 @@ def test_shared_memory_data_plane(native_built, np_, env):
     presented as 2 hosts (two-level control plane: shm inside a host, leaders over TCP; data over the TCP ring)."""
     rc, out = run_parallel("shm_plane_worker.py", np=np_, timeout=400, env=env)
     assert "SHM PLANE OK" in out, out[-3000:]
+
+
+def test_reference_behavioural_details(native_built):
+    rc, out = run_parallel("appendix_a_worker.py", np=3, timeout=200)
+    assert "APPENDIX A OK dup_err=True" in out, out[-3000:]
