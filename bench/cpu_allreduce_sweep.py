@@ -25,8 +25,16 @@ p.add_argument('--out', default=None)
 p.add_argument('--no-gloo', action='store_true')
 args = p.parse_args()
 
+_fake = int(os.environ.get('HVD_TEST_FAKE_HOSTS', '0'))
+if _fake > 1:   # present the ranks of this box as several hosts (multi-host code paths: two-level control / data planes)
+    _r, _n = int(os.environ['HOROVOD_RANK']), int(os.environ['HOROVOD_SIZE'])
+    _L = _n // _fake
+    os.environ.update(HOROVOD_HOSTNAME='fakehost%d' % (_r // _L), HOROVOD_LOCAL_RANK=str(_r % _L), HOROVOD_LOCAL_SIZE=str(_L),
+                      HOROVOD_CROSS_RANK=str(_r // _L), HOROVOD_CROSS_SIZE=str(_fake))
 hvd.init()
 rank, size = hvd.rank(), hvd.size()
+if rank == 0:
+    print(hvd.control_plane_info(), flush=True)
 torch.set_num_threads(max(1, (os.cpu_count() or 4) // size))
 if not args.no_gloo:
     dist.init_process_group('gloo', rank=rank, world_size=size,

@@ -86,6 +86,9 @@ void ScaleBuffer(void* buf, int64_t n, DataType dtype, double s) {
   }
 }
 
+void RingAllreduce(Transport* t, char* b, int64_t count, DataType dtype, ReduceOp op);
+void RingAllgatherv(Transport* t, char* o, const std::vector<int64_t>& bytes, const std::vector<int64_t>& displ);
+
 // ---------------------------------------------------------------------------
 // Shared-memory data plane (single-host communicators; see transport.h:ShmData).  The host analogue of the two-shot GPU
 // kernel: every rank publishes a piece of its buffer in its slot, reduces the 1/N of the piece it owns straight out of
@@ -223,6 +226,79 @@ bool ShmAlltoallv(Transport* t, const char* in, const std::vector<int64_t>& sd, 
   return true;
 }
 
+// Multi-host, same number of ranks on every host.  Per piece: publish in the host's shm slots -> every local rank reduces the
+// 1/L chunk it owns over the ranks of its host -> the L chunk owners run L cross-host ring allreduces in parallel, each with
+// the owners of the same chunk on the other hosts (1/L of the bytes per TCP stream) -> everybody copies the chunks back.
+bool HierAllreduce(Transport* t, char* b, int64_t count, DataType dtype, ReduceOp op) {
+  HierData h;
+  if (!t->HierDataPlane(&h)) return false;
+  const int L = h.local_size, l = h.local_rank;
+  const size_t es = DataTypeSize(dtype);
+  const int64_t per_piece = (int64_t)(h.local.slot_bytes / es);
+  for (int64_t done = 0; done < count; done += per_piece) {
+    const int64_t m = std::min(per_piece, count - done);
+    const int half = (int)(t->ShmNextPiece() & 1);
+    char* mine = h.local.slot(l, half);
+    memcpy(mine, b + done * es, (size_t)m * es);
+    t->LocalBarrier();
+    const int64_t lo = m * l / L, hi = m * (l + 1) / L;
+    if (hi > lo) {
+      for (int p = 1; p < L; ++p) ReduceInto(mine + lo * es, h.local.slot((l + p) % L, half) + lo * es, hi - lo, dtype, op);
+      RingAllreduce(h.cross, mine + lo * es, hi - lo, dtype, op);
+    }
+    t->LocalBarrier();
+    for (int q = 0; q < L; ++q) {
+      const int64_t ql = m * q / L, qh = m * (q + 1) / L;
+      if (qh > ql) memcpy(b + (done + ql) * es, h.local.slot(q, half) + ql * es, (size_t)(qh - ql) * es);
+    }
+  }
+  return true;
+}
+
+// Two-level allgather: the ranks with my local index exchange their blocks across hosts (L parallel rings), then the ranks
+// of a host hand each other the columns they collected through shm.
+bool HierAllgatherv(Transport* t, char* o, const std::vector<int64_t>& bytes, const std::vector<int64_t>& displ) {
+  HierData h;
+  if (!t->HierDataPlane(&h)) return false;
+  const int L = h.local_size, l = h.local_rank;
+  const auto& column = *h.column;
+  const int H = (int)column[0].size();
+  // (1) cross-host ring over my column: afterwards `o` holds the blocks of every rank with my local index
+  {
+    std::vector<int64_t> cb((size_t)H), cd((size_t)H);
+    for (int x = 0; x < H; ++x) { cb[(size_t)x] = bytes[(size_t)column[(size_t)l][(size_t)x]]; cd[(size_t)x] = displ[(size_t)column[(size_t)l][(size_t)x]]; }
+    // the cross ring addresses blocks by their position in `o`: pass absolute displacements
+    std::vector<int64_t> d2(cd.begin(), cd.end());
+    d2.push_back(0);
+    RingAllgatherv(h.cross, o, cb, d2);
+  }
+  // (2) inside the host: column c travels through the slot of the local rank c, one piece (of the concatenated column) at a time
+  int64_t longest = 0;
+  std::vector<int64_t> col_bytes((size_t)L, 0);
+  for (int c = 0; c < L; ++c) { for (int r : column[(size_t)c]) col_bytes[(size_t)c] += bytes[(size_t)r]; longest = std::max(longest, col_bytes[(size_t)c]); }
+  const int64_t S = (int64_t)h.local.slot_bytes;
+  auto walk = [&](int c, int64_t piece_lo, int64_t piece_hi, char* slot, bool into_slot) {
+    int64_t pos = 0;                                  // running offset inside the concatenated column c
+    for (int r : column[(size_t)c]) {
+      const int64_t blo = pos, bhi = pos + bytes[(size_t)r];
+      const int64_t lo = std::max(blo, piece_lo), hi = std::min(bhi, piece_hi);
+      if (hi > lo) {
+        char* user = o + displ[(size_t)r] + (lo - blo);
+        char* shm = slot + (lo - piece_lo);
+        if (into_slot) memcpy(shm, user, (size_t)(hi - lo)); else memcpy(user, shm, (size_t)(hi - lo));
+      }
+      pos = bhi;
+    }
+  };
+  for (int64_t done = 0; done < longest; done += S) {
+    const int half = (int)(t->ShmNextPiece() & 1);
+    walk(l, done, done + S, h.local.slot(l, half), true);
+    t->LocalBarrier();
+    for (int c = 0; c < L; ++c) if (c != l) walk(c, done, done + S, h.local.slot(c, half), false);
+  }
+  return true;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------
@@ -233,6 +309,14 @@ void Allreduce(Transport* t, void* buf, int64_t count, DataType dtype, ReduceOp 
   const size_t es = DataTypeSize(dtype);
   char* b = (char*)buf;
   if (ShmAllreduce(t, b, count, dtype, op)) return;
+  if (HierAllreduce(t, b, count, dtype, op)) return;
+  RingAllreduce(t, b, count, dtype, op);
+}
+
+void RingAllreduce(Transport* t, char* b, int64_t count, DataType dtype, ReduceOp op) {
+  const int n = t->size(), r = t->rank();
+  if (n == 1 || count == 0) return;
+  const size_t es = DataTypeSize(dtype);
   if ((size_t)count * es < 32768 || count < n) {
     // latency regime: reduce at rank 0, broadcast
     if (r == 0) {
@@ -271,6 +355,13 @@ void Allgatherv(Transport* t, const void* in, void* out, const std::vector<int64
   if (in != o + displ[r] && bytes[r]) memcpy(o + displ[r], in, (size_t)bytes[r]);
   if (n == 1) return;
   if (ShmAllgatherv(t, o + displ[r], o, bytes, displ)) return;
+  if (HierAllgatherv(t, o, bytes, displ)) return;
+  RingAllgatherv(t, o, bytes, displ);
+}
+
+void RingAllgatherv(Transport* t, char* o, const std::vector<int64_t>& bytes, const std::vector<int64_t>& displ) {
+  const int n = t->size(), r = t->rank();
+  if (n == 1) return;
   const int next = (r + 1) % n, prev = (r - 1 + n) % n;
   for (int s = 0; s < n - 1; ++s) {
     int si = (r - s + n) % n, ri = (r - s - 1 + n) % n;

@@ -297,7 +297,30 @@ class HierShmControlTransport : public Transport {
       : base_(std::move(base)), seg_(seg), local_(std::move(local)), li_(local_index), leaders_(std::move(leaders)) {
     seg_->slots[li_].pid = (int32_t)getpid();
   }
-  ~HierShmControlTransport() override { munmap(seg_, sizeof(Segment)); }
+  ~HierShmControlTransport() override {
+    munmap(seg_, sizeof(Segment));
+    if (data_) munmap(data_, data_bytes_);
+  }
+  // ---- two-level data plane for host tensors ----
+  void AttachData(char* data, size_t total, size_t slot, std::vector<std::vector<int>> column) {
+    data_ = data; data_bytes_ = total; slot_bytes_ = slot; column_ = std::move(column);
+    cross_ = base_->Split(column_[li_]);
+  }
+  bool HierDataPlane(HierData* out) override {
+    if (!data_ || !cross_) return false;
+    out->local.base = data_; out->local.slot_bytes = slot_bytes_;
+    out->local_rank = li_; out->local_size = (int)local_.size();
+    out->cross = cross_.get(); out->column = &column_;
+    return true;
+  }
+  uint64_t ShmNextPiece() override { return piece_++; }
+  void LocalBarrier() override {
+    const uint64_t k = ++local_round_;
+    SubSlot* row = seg_->sub[0];
+    row[li_].seq.store(k, std::memory_order_release);
+    for (int j = 0; j < (int)local_.size(); ++j)
+      if (j != li_) WaitSeqReaches(row[j].seq, seg_->slots[j].pid, k, local_[j]);
+  }
   int rank() const override { return base_->rank(); }
   int size() const override { return base_->size(); }
   int global_rank(int i) const override { return base_->global_rank(i); }
@@ -359,7 +382,10 @@ class HierShmControlTransport : public Transport {
   void Barrier() override { AllreduceBits(nullptr, 0, nullptr, 0); }
   std::string Describe() const override {
     return "control: two-level (shared memory among the " + std::to_string(local_.size()) + " ranks of this host, " +
-           std::to_string(leaders_.size()) + " host leaders over the base transport); host data: ring over the base transport";
+           std::to_string(leaders_.size()) + " host leaders over the base transport); host data: " +
+           (data_ && cross_ ? "two-level (shared-memory slots of " + std::to_string(slot_bytes_) + " bytes inside a host, " +
+                                  std::to_string(local_.size()) + " parallel cross-host rings)"
+                            : std::string("ring over the base transport"));
   }
 
  private:
@@ -369,6 +395,11 @@ class HierShmControlTransport : public Transport {
   int li_;                     // my index in local_
   std::vector<int> leaders_;   // leader of every host, ascending
   uint64_t round_ = 0;
+  char* data_ = nullptr;
+  size_t data_bytes_ = 0, slot_bytes_ = 0;
+  uint64_t piece_ = 0, local_round_ = 0;
+  std::vector<std::vector<int>> column_;
+  std::shared_ptr<Transport> cross_;
 };
 
 }  // namespace
@@ -407,9 +438,40 @@ std::shared_ptr<Transport> WrapWithHierarchicalControl(std::shared_ptr<Transport
     return base;
   }
   const int nlocal = (int)local.size();
+  // column[l] = ranks with local index l, host by host; only defined when every host runs the same number of ranks
+  std::vector<std::vector<int>> column;
+  bool homogeneous = n % (int)leaders.size() == 0 && nlocal == n / (int)leaders.size();
+  if (homogeneous) {
+    column.assign((size_t)nlocal, {});
+    for (int h : seen_hosts) {
+      int l = 0;
+      for (int r = 0; r < n; ++r) if (base->host_id(r) == h) { if (l < nlocal) column[(size_t)l].push_back(r); ++l; }
+      if (l != nlocal) homogeneous = false;
+    }
+  }
+  auto raw = base;
   auto hier = std::make_shared<HierShmControlTransport>(std::move(base), seg, std::move(local), li, std::move(leaders));
   hier->Barrier();                       // every rank of this host has published its pid
   VerifyPeerPids(seg, nlocal, li);
+
+  // ---- data plane: per-host slots; collective over ALL ranks (every host takes the same decision) ----
+  const char* dp = getenv("HVD_SHM_DATA_PLANE");
+  uint64_t want = homogeneous && nlocal > 1 && !(dp && atoi(dp) == 0);
+  hier->AllreduceBits(&want, 1, nullptr, 0);
+  if (!want) return hier;
+  const size_t slot = DataSlotBytes(), total = slot * 2 * (size_t)nlocal;
+  const std::string dname = name + "-d";
+  char* data = nullptr;
+  if (li == 0) { shm_unlink(dname.c_str()); data = MapNamed(dname, total, true); }
+  uint64_t okd = li == 0 ? (uint64_t)(data != nullptr) : 1;
+  hier->AllreduceBits(&okd, 1, nullptr, 0);
+  if (okd && li != 0) data = MapNamed(dname, total, false);
+  uint64_t okd2 = okd ? (uint64_t)(data != nullptr) : 0;
+  hier->AllreduceBits(&okd2, 1, nullptr, 0);
+  if (li == 0) shm_unlink(dname.c_str());
+  if (!okd2) { if (data) munmap(data, total); return hier; }
+  hier->AttachData(data, total, slot, std::move(column));
+  (void)raw;
   return hier;
 }
 

@@ -34,6 +34,17 @@ struct ShmData {
   char* slot(int rank, int half) const { return base + ((size_t)rank * 2 + (size_t)half) * slot_bytes; }
 };
 
+class Transport;
+// Two-level data plane of a multi-host communicator whose hosts all run the same number of ranks: `local` are the shm slots
+// of the ranks of THIS host (indexed by local rank), `cross` connects the ranks with my local index on every host, and
+// `column[l]` lists, host by host, the communicator ranks with local index l.
+struct HierData {
+  ShmData local;
+  int local_rank = 0, local_size = 1;
+  Transport* cross = nullptr;
+  const std::vector<std::vector<int>>* column = nullptr;
+};
+
 class Transport {
  public:
   virtual ~Transport() = default;
@@ -71,6 +82,8 @@ class Transport {
   // piece number (identical on every rank because collectives are issued in the same order everywhere).
   // one line for logs / hvd.control_plane_info(): what the negotiation and the host data path run on
   virtual std::string Describe() const { return "control: point-to-point star over the base transport; host data: ring over the base transport"; }
+  virtual bool HierDataPlane(HierData* /*out*/) { return false; }
+  virtual void LocalBarrier() {}     // among the ranks of this host only (HierDataPlane users)
   virtual bool ShmDataPlane(ShmData* /*out*/) { return false; }
   virtual uint64_t ShmNextPiece() { return 0; }
 };

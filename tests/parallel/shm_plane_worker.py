@@ -14,6 +14,16 @@ if FAKE_HOSTS > 1:          # present the ranks as FAKE_HOSTS machines: two-leve
     os.environ.update(HOROVOD_HOSTNAME='fakehost%d' % (_r // _L), HOROVOD_LOCAL_RANK=str(_r % _L), HOROVOD_LOCAL_SIZE=str(_L),
                       HOROVOD_CROSS_RANK=str(_r // _L), HOROVOD_CROSS_SIZE=str(FAKE_HOSTS))
 
+HOST_MAP = os.environ.get('HVD_TEST_FAKE_HOST_MAP')          # e.g. "0,0,1": uneven hosts
+if HOST_MAP:
+    _hosts = [int(x) for x in HOST_MAP.split(',')]
+    _r = int(os.environ['HOROVOD_RANK'])
+    _mine = [i for i, h in enumerate(_hosts) if h == _hosts[_r]]
+    _uniq = sorted(set(_hosts))
+    os.environ.update(HOROVOD_HOSTNAME='fakehost%d' % _hosts[_r], HOROVOD_LOCAL_RANK=str(_mine.index(_r)), HOROVOD_LOCAL_SIZE=str(len(_mine)),
+                      HOROVOD_CROSS_RANK=str(_uniq.index(_hosts[_r])), HOROVOD_CROSS_SIZE=str(len(_uniq)))
+    FAKE_HOSTS = len(_uniq)
+
 hvd.init()
 rank, size = hvd.rank(), hvd.size()
 gen = torch.Generator().manual_seed(7)
