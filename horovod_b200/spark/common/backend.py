@@ -10,6 +10,15 @@ class Backend:
         raise NotImplementedError
 
 
+def default_num_proc():
+    """The active Spark context's default parallelism (what SparkBackend uses when num_proc is not given)."""
+    import pyspark
+    ctx = pyspark.SparkContext._active_spark_context
+    if ctx is None:
+        raise RuntimeError('Could not find an active SparkContext, are you running in a PySpark session?')
+    return ctx.defaultParallelism
+
+
 class SparkBackend(Backend):
     """Spark barrier tasks through `horovod_b200.spark.run`."""
 

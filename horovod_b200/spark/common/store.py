@@ -46,9 +46,14 @@ class Store:
 
     @staticmethod
     def create(prefix_path, *args, **kwargs):
+        """hdfs://... -> HDFSStore; dbfs:/... or /dbfs/... -> DBFSLocalStore; other URIs -> FilesystemStore; plain paths -> LocalStore."""
+        if DBFSLocalStore.matches(prefix_path):
+            return DBFSLocalStore(prefix_path, *args, **kwargs)
         scheme = prefix_path.split('://', 1)[0] if '://' in prefix_path else 'file'
         if scheme == 'file':
             return LocalStore(prefix_path, *args, **kwargs)
+        if scheme in ('hdfs', 'viewfs'):
+            return HDFSStore(prefix_path, *args, **kwargs)
         return FilesystemStore(prefix_path, *args, **kwargs)
 
 
@@ -149,3 +154,65 @@ class LocalStore(FilesystemStore):
 
     def delete(self, path):
         shutil.rmtree(path, ignore_errors=True)
+
+
+class HDFSStore(FilesystemStore):
+    """hdfs://[host[:port]]/path (reference store.py `HDFSStore`): a FilesystemStore on pyarrow's HadoopFileSystem.  Host / port /
+    user / kerberos ticket can be given explicitly; otherwise they come from the URI (or from the Hadoop configuration when the
+    URI has no authority: `hdfs:///path`)."""
+
+    def __init__(self, prefix_path, host=None, port=None, user=None, kerb_ticket=None, extra_conf=None, *args, **kwargs):
+        self._hdfs_kwargs = dict(host=host, port=port, user=user, kerb_ticket=kerb_ticket, extra_conf=extra_conf)
+        super().__init__(prefix_path, *args, **kwargs)
+
+    @staticmethod
+    def parse_url(url):
+        """-> (host or 'default', port or 0, path)"""
+        rest = url.split('://', 1)[1] if '://' in url else url
+        authority, _, path = rest.partition('/')
+        host, _, port = authority.partition(':')
+        return host or 'default', int(port) if port else 0, '/' + path
+
+    @property
+    def fs(self):
+        if self._fs is None:
+            import pyarrow.fs as pafs
+            host, port, _ = self.parse_url(self.prefix_path)
+            kw = {k: v for k, v in self._hdfs_kwargs.items() if v is not None}
+            kw.setdefault('host', host)
+            kw.setdefault('port', port)
+            self._fs = pafs.HadoopFileSystem(**kw)
+        return self._fs
+
+    def _local(self, path):
+        return self.parse_url(path)[2] if '://' in path else path
+
+
+def is_databricks():
+    return 'DATABRICKS_RUNTIME_VERSION' in os.environ
+
+
+class DBFSLocalStore(LocalStore):
+    """Databricks file system through its FUSE mount: `dbfs:/x` and `/dbfs/x` both mean the local path `/dbfs/x` (reference
+    store.py `DBFSLocalStore`).  Checkpoints are written with the `.tf` suffix the reference uses there."""
+
+    def __init__(self, prefix_path, *args, **kwargs):
+        super().__init__(self.normalize_path(prefix_path), *args, **kwargs)
+
+    @staticmethod
+    def matches(path):
+        return path.startswith('dbfs:/') or path == '/dbfs' or path.startswith('/dbfs/')
+
+    @staticmethod
+    def normalize_path(path):
+        if path.startswith('dbfs:///'):
+            return '/dbfs/' + path[len('dbfs:///'):]
+        if path.startswith('dbfs:/'):
+            return '/dbfs/' + path[len('dbfs:/'):].lstrip('/')
+        return path
+
+    def get_checkpoint_filename(self):
+        return 'checkpoint.tf'
+
+
+AbstractFilesystemStore = FilesystemStore

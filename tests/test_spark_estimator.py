@@ -59,3 +59,18 @@ def test_fit_linear_regression_two_procs(native_built, tmp_path):
     assert st.exists(st.get_checkpoint_path('t1'))
     ck = torch.load(__import__('io').BytesIO(st.read(st.get_checkpoint_path('t1'))), weights_only=False)
     assert ck['epoch'] == 5 and 'model' in ck
+
+
+def test_store_selection_and_path_rules(tmp_path):
+    from horovod_b200.spark.common import DBFSLocalStore, FilesystemStore, HDFSStore
+    assert isinstance(Store.create('hdfs://namenode:8020/user/x'), HDFSStore)
+    assert isinstance(Store.create('dbfs:/ml/run'), DBFSLocalStore) and isinstance(Store.create('/dbfs/ml/run'), DBFSLocalStore)
+    assert type(Store.create('s3://bucket/prefix')) is FilesystemStore and isinstance(Store.create(str(tmp_path)), LocalStore)
+    assert HDFSStore.parse_url('hdfs://nn:8020/a/b') == ('nn', 8020, '/a/b')
+    assert HDFSStore.parse_url('hdfs:///a/b') == ('default', 0, '/a/b') and HDFSStore.parse_url('hdfs://nn/a') == ('nn', 0, '/a')
+    h = HDFSStore('hdfs://nn:8020/base', user='me')
+    assert h.get_train_data_path(2) == 'hdfs://nn:8020/base/intermediate_train_data.2' and h._local(h.get_run_path('r')) == '/base/runs/r'
+    for given, want in (('dbfs:/a/b', '/dbfs/a/b'), ('dbfs:///a/b', '/dbfs/a/b'), ('/dbfs/a/b', '/dbfs/a/b'), ('/other', '/other')):
+        assert DBFSLocalStore.normalize_path(given) == want
+    d = DBFSLocalStore('dbfs:/ml')
+    assert d.prefix_path == '/dbfs/ml' and d.get_checkpoint_path('r').endswith('runs/r/checkpoint.tf')
