@@ -152,3 +152,29 @@ def get_average_backwards_compatibility_fun(reduce_ops):
     def impl(op, average):
         return resolve_op(op, average, reduce_ops.Average, reduce_ops.Sum)
     return impl
+
+
+EXTENSIONS = ['torch', 'tensorflow', 'mxnet', 'numpy']
+
+
+class HorovodVersionMismatchError(ImportError):
+    """The native binding was built against another version of the framework than the one that is running."""
+
+    def __init__(self, name, version, installed_version):
+        super().__init__(get_version_mismatch_message(name, version, installed_version))
+        self.name, self.version, self.installed_version = name, version, installed_version
+
+
+def get_version_mismatch_message(name, version, installed_version):
+    return ('Framework %s installed with version %s but found version %s.\n'
+            '             This can result in unexpected behavior including runtime errors.\n'
+            '             Rebuild the native libraries with `python -m horovod_b200.build --force` to build against the running version.'
+            % (name, installed_version, version))
+
+
+def get_extension_full_path(pkg_path=None, *args):
+    """Path of the shared object that serves a front end.  All front ends share ONE binding (`lib/_hvd_torch.so`) on top of
+    `lib/libhvd_core.so`; the arguments of the reference's per-framework lookup are accepted and ignored."""
+    import os
+    from horovod_b200.common.basics import lib_dir
+    return os.path.join(lib_dir(), '_hvd_torch.so')

@@ -16,7 +16,10 @@ import torch
 from horovod_b200.common.basics import HorovodBasics, lib_dir
 from horovod_b200.common.exceptions import HorovodInternalError
 from horovod_b200.common.process_sets import ProcessSet, global_process_set, _setup as _setup_process_sets
-from horovod_b200.common.util import resolve_op, num_rank_is_power_2
+from horovod_b200.common.process_sets import add_process_set, remove_process_set  # noqa: F401  (reference: importable from here)
+from horovod_b200.common.util import (resolve_op, num_rank_is_power_2, gpu_available,  # noqa: F401
+                                      get_average_backwards_compatibility_fun)
+from horovod_b200.torch.compression import Compression  # noqa: F401
 
 _basics = HorovodBasics()
 _lib = None
@@ -92,6 +95,12 @@ p2p_built = _basics.p2p_built
 gpu_topology = _basics.gpu_topology
 gpu_backend_info = _basics.gpu_backend_info
 runtime_stats = _basics.runtime_stats
+
+
+def handle_average_backwards_compatibility(op, average):
+    """op / deprecated `average=` -> the effective reduce op (reference torch/mpi_ops.py:80-84)."""
+    return resolve_op(op, average, Average, Sum)
+
 metrics = _basics.metrics
 control_plane_info = _basics.control_plane_info
 tunable_params = _basics.tunable_params
