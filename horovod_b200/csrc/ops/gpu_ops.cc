@@ -221,7 +221,10 @@ bool GpuOps::EnsureHierarchy(ProcessSet& ps, int device) {
   const int L = (int)mine.size();
   // on by default for uniform multi-host sets; HOROVOD_HIERARCHICAL_ALLREDUCE=0 (hvdrun --no-hierarchical-allreduce) forces
   // the flat host-staged path
-  bool uniform = L >= 2 && L <= kern::kMaxPeers && EnvBool("HVD_HIERARCHICAL_ALLREDUCE", EnvBool("HOROVOD_HIERARCHICAL_ALLREDUCE", true));
+  // HOROVOD_TORUS_ALLREDUCE (the reference's 2-D variant whose cross step stays on the GPU fabric) selects the same two-level
+  // schedule here: intra-host kernels + cross-host shard exchange
+  bool uniform = L >= 2 && L <= kern::kMaxPeers &&
+                 EnvBool("HVD_HIERARCHICAL_ALLREDUCE", EnvBool("HOROVOD_HIERARCHICAL_ALLREDUCE", true) || EnvBool("HOROVOD_TORUS_ALLREDUCE", false));
   for (auto& kv : by_host) if ((int)kv.second.size() != L) uniform = false;
   int64_t tag[2] = {(int64_t)getpid(), (int64_t)(++team_counter_)};
   t->Bcast(tag, sizeof tag, 0);

@@ -33,6 +33,7 @@ OPTIONS = [
     _opt('cache_capacity', 'params', 'cache_capacity', 'HOROVOD_CACHE_CAPACITY', nonneg=True),
     _opt('hierarchical_allreduce', 'params', 'hierarchical_allreduce', 'HOROVOD_HIERARCHICAL_ALLREDUCE', _flag),
     _opt('hierarchical_allgather', 'params', 'hierarchical_allgather', 'HOROVOD_HIERARCHICAL_ALLGATHER', _flag),
+    _opt('torus_allreduce', 'params', 'torus_allreduce', 'HOROVOD_TORUS_ALLREDUCE', _flag),
     _opt('thread_affinity', 'params', 'thread_affinity', 'HOROVOD_THREAD_AFFINITY'),
     _opt('num_nccl_streams', 'params', 'num_nccl_streams', 'HOROVOD_NUM_NCCL_STREAMS', nonneg=True),
     _opt('autotune', 'autotune', 'enabled', 'HOROVOD_AUTOTUNE', _flag, needs='autotune'),
@@ -49,6 +50,7 @@ OPTIONS = [
     _opt('stall_check_warning_time_seconds', 'stall_check', 'warning_time_seconds', 'HOROVOD_STALL_CHECK_TIME_SECONDS', nonneg=True),
     _opt('stall_check_shutdown_time_seconds', 'stall_check', 'shutdown_time_seconds', 'HOROVOD_STALL_SHUTDOWN_TIME_SECONDS', nonneg=True),
     _opt('mpi_threads_disable', 'library_options', 'mpi_threads_disable', 'HOROVOD_MPI_THREADS_DISABLE', _flag),
+    _opt('gloo_timeout_seconds', 'library_options', 'gloo_timeout_seconds', 'HOROVOD_GLOO_TIMEOUT_SECONDS', nonneg=True),
     _opt('gpu_backend', 'library_options', 'gpu_backend', 'HVD_GPU_BACKEND'),
     _opt('allreduce_variant', 'library_options', 'allreduce_variant', 'HVD_ALLREDUCE_VARIANT'),
     _opt('wire_dtype', 'library_options', 'wire_dtype', 'HVD_WIRE_DTYPE'),

@@ -186,6 +186,10 @@ def parse_args():
     group_hier.add_argument('--hierarchical-allreduce', action=make_override_true_action(override_args),
                             help='Two-level (intra-node NVLink, inter-node TCP) allreduce for multi-node jobs.')
     group_hier.add_argument('--no-hierarchical-allreduce', dest='hierarchical_allreduce', action=make_override_false_action(override_args))
+    group_torus = group_params.add_mutually_exclusive_group()
+    group_torus.add_argument('--torus-allreduce', action=make_override_true_action(override_args),
+                             help='2-D allreduce for multi-node jobs (here: the same two-level schedule as --hierarchical-allreduce).')
+    group_torus.add_argument('--no-torus-allreduce', dest='torus_allreduce', action=make_override_false_action(override_args))
     group_hiera = group_params.add_mutually_exclusive_group()
     group_hiera.add_argument('--hierarchical-allgather', action=make_override_true_action(override_args))
     group_hiera.add_argument('--no-hierarchical-allgather', dest='hierarchical_allgather', action=make_override_false_action(override_args))
@@ -235,6 +239,8 @@ def parse_args():
     gl = group_lib.add_mutually_exclusive_group()
     gl.add_argument('--mpi-threads-disable', action=make_override_true_action(override_args))
     gl.add_argument('--no-mpi-threads-disable', dest='mpi_threads_disable', action=make_override_false_action(override_args))
+    group_lib.add_argument('--gloo-timeout-seconds', action=make_override_action(override_args), type=int,
+                           help='Seconds a rank waits for its peers during bootstrap / rendezvous before giving up (default 60).')
     group_lib.add_argument('--mpi-args', action='store', dest='mpi_args', help='Extra MPI arguments to pass to mpirun.')
     group_lib.add_argument('--tcp', action='store_true', dest='tcp_flag', help='If this flag is set, only TCP is used for communication.')
     group_lib.add_argument('--binding-args', action='store', dest='binding_args', help='Process binding arguments.')
