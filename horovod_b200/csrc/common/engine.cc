@@ -1,4 +1,7 @@
 #include "engine.h"
+#include <arpa/inet.h>
+#include <ifaddrs.h>
+#include <netinet/in.h>
 #include <pthread.h>
 #include <sched.h>
 #include <unistd.h>
@@ -15,6 +18,29 @@
 #include "nvtx_op_range.h"
 
 namespace hvd {
+
+// IPv4 address of the first interface named in `ifaces` (comma separated) that has one; "" when none matches.
+static std::string InterfaceAddress(const std::string& ifaces) {
+  if (ifaces.empty()) return "";
+  struct ifaddrs* list = nullptr;
+  if (getifaddrs(&list) != 0) return "";
+  std::string found;
+  size_t start = 0;
+  while (found.empty() && start <= ifaces.size()) {
+    size_t end = ifaces.find(',', start);
+    if (end == std::string::npos) end = ifaces.size();
+    const std::string want = ifaces.substr(start, end - start);
+    for (struct ifaddrs* it = list; it && found.empty(); it = it->ifa_next) {
+      if (!it->ifa_addr || it->ifa_addr->sa_family != AF_INET || want != it->ifa_name) continue;
+      char buf[INET_ADDRSTRLEN];
+      if (inet_ntop(AF_INET, &((struct sockaddr_in*)it->ifa_addr)->sin_addr, buf, sizeof buf)) found = buf;
+    }
+    start = end + 1;
+  }
+  freeifaddrs(list);
+  if (found.empty()) LOG(WARNING) << "HOROVOD_GLOO_IFACE=" << ifaces << ": no such interface with an IPv4 address; using the default route";
+  return found;
+}
 
 namespace {
 // NVTX range from enqueue until the entry dies (after its completion callback)
@@ -153,7 +179,11 @@ void Engine::BackgroundThread() {
         throw TransportError("no rendezvous server configured (HOROVOD_GLOO_RENDEZVOUS_ADDR/PORT); launch with hvdrun or torchrun");
       HttpKVStore store(cfg_.rendezvous_addr, cfg_.rendezvous_port);
       double timeout = EnvDouble(HOROVOD_TIMEOUT_SECONDS, 60.0);
-      std::string adv = EnvStr("HVD_HOST_ADDR", store.LocalAddress());
+      // address peers connect to: HVD_HOST_ADDR, else the IPv4 address of the interface the launcher selected
+      // (--network-interfaces -> HOROVOD_GLOO_IFACE), else the local address of the route to the rendezvous server
+      std::string adv = EnvStr("HVD_HOST_ADDR", "");
+      if (adv.empty()) adv = InterfaceAddress(EnvStr("HOROVOD_GLOO_IFACE", ""));
+      if (adv.empty()) adv = store.LocalAddress();
       char hn[256] = "localhost";
       gethostname(hn, sizeof hn);
       std::string host = cfg_.hostname.empty() ? std::string(hn) : cfg_.hostname;
