@@ -17,6 +17,11 @@ if [ "$N" -ge 2 ]; then
   TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
   echo "== [$N GPUs] gated multi-GPU tests (extra op matrix on CUDA, hierarchical allreduce with 2 fake hosts)"
   timeout 600 python -m pytest tests/test_gpu_multi.py -q -x 2>&1 | tail -8
+  echo "== [$N GPUs] small-message latency: shared-memory control plane (now really in the negotiation path) vs TCP"
+  for cp in auto tcp; do
+    HVD_CONTROL_PLANE=$cp timeout 150 $TR --master-port 29520 bench/allreduce_sweep.py --sizes 4096,65536,1048576 --configs p2p:auto:128 \
+      --out $OUT/sweep${N}_latency_cp_${cp}.json 2>&1 | grep -v Warn | tail -6
+  done
   echo "== [$N GPUs] allgather / broadcast / alltoall / reducescatter vs torch.distributed NCCL"
   timeout 200 $TR --master-port 29521 bench/collective_sweep.py --nccl --out $OUT/collectives${N}.json 2>&1 | grep -v Warn | tail -30
   echo "== [$N GPUs] same, TMA bulk-copy exchange kernel"

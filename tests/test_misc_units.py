@@ -69,7 +69,7 @@ def test_local_store(tmp_path):
     assert s.get_logs_path('run1').endswith('runs/run1/logs') and s.get_train_data_path(3).endswith('intermediate_train_data.3')
     from horovod_b200.spark.common.store import FilesystemStore
     remote = Store.create('hdfs://namenode:8020/x/y')  # lazily bound pyarrow.fs filesystem
-    assert type(remote) is FilesystemStore and remote.get_run_path('r') == 'hdfs://namenode:8020/x/y/runs/r'
+    assert isinstance(remote, FilesystemStore) and remote.get_run_path('r') == 'hdfs://namenode:8020/x/y/runs/r'
 
 
 def test_utils_timing_helpers():
