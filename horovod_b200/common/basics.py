@@ -370,6 +370,8 @@ class HorovodBasics(object):
             if any(vals.values()):
                 out[buf.value.decode().lower()] = vals
         out['runtime'] = self.runtime_stats()
+        lib.hvd_host_path_count.restype = ctypes.c_ulonglong
+        out['host_paths'] = {name: int(lib.hvd_host_path_count(i)) for i, name in enumerate(('shared_memory', 'two_level', 'base_transport'))}
         return out
 
     def tunable_params(self):

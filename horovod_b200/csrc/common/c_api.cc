@@ -7,6 +7,7 @@
 #include <vector>
 #include "../kernels/p2p_kernels.h"
 #include "../symm/symm_memory.h"
+#include "../ops/cpu_ops.h"
 #include "engine.h"
 #include "env.h"
 #include "logging.h"
@@ -143,6 +144,7 @@ int hvd_control_plane_string(int process_set_id, char* out, int cap) {
   snprintf(out, (size_t)cap, "%s", Engine::Get().ControlPlaneString(process_set_id).c_str());
   return 0;
 }
+unsigned long long hvd_host_path_count(int which) { return cpu::HostPathCount(which); }
 // named counters: hvd_metric(type, field) with type = ResponseType value, field = Engine::MetricField
 unsigned long long hvd_metric(int type, int field) {
   if (type < 0 || type >= Engine::kMetricTypes || field < 0 || field >= Engine::kPerType) return 0;

@@ -1,5 +1,6 @@
 #include "cpu_ops.h"
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <chrono>
 #include <cmath>
@@ -85,6 +86,10 @@ void ScaleBuffer(void* buf, int64_t n, DataType dtype, double s) {
     case DataType::BFLOAT16: { uint16_t* b = (uint16_t*)buf; for (int64_t i = 0; i < n; ++i) b[i] = FloatToBF16Bits(BF16BitsToFloat(b[i]) * (float)s); break; }
   }
 }
+
+static std::atomic<unsigned long long> g_path_count[3];
+unsigned long long HostPathCount(int which) { return which >= 0 && which < 3 ? g_path_count[which].load(std::memory_order_relaxed) : 0; }
+static inline bool Took(int path, bool taken) { if (taken) g_path_count[path].fetch_add(1, std::memory_order_relaxed); return taken; }
 
 void RingAllreduce(Transport* t, char* b, int64_t count, DataType dtype, ReduceOp op);
 void RingAllgatherv(Transport* t, char* o, const std::vector<int64_t>& bytes, const std::vector<int64_t>& displ);
@@ -308,8 +313,9 @@ void Allreduce(Transport* t, void* buf, int64_t count, DataType dtype, ReduceOp 
   if (n == 1 || count == 0) return;
   const size_t es = DataTypeSize(dtype);
   char* b = (char*)buf;
-  if (ShmAllreduce(t, b, count, dtype, op)) return;
-  if (HierAllreduce(t, b, count, dtype, op)) return;
+  if (Took(0, ShmAllreduce(t, b, count, dtype, op))) return;
+  if (Took(1, HierAllreduce(t, b, count, dtype, op))) return;
+  Took(2, true);
   RingAllreduce(t, b, count, dtype, op);
 }
 
@@ -354,8 +360,9 @@ void Allgatherv(Transport* t, const void* in, void* out, const std::vector<int64
   char* o = (char*)out;
   if (in != o + displ[r] && bytes[r]) memcpy(o + displ[r], in, (size_t)bytes[r]);
   if (n == 1) return;
-  if (ShmAllgatherv(t, o + displ[r], o, bytes, displ)) return;
-  if (HierAllgatherv(t, o, bytes, displ)) return;
+  if (Took(0, ShmAllgatherv(t, o + displ[r], o, bytes, displ))) return;
+  if (Took(1, HierAllgatherv(t, o, bytes, displ))) return;
+  Took(2, true);
   RingAllgatherv(t, o, bytes, displ);
 }
 
@@ -372,7 +379,8 @@ void RingAllgatherv(Transport* t, char* o, const std::vector<int64_t>& bytes, co
 void Broadcast(Transport* t, void* buf, int64_t bytes, int root) {
   const int n = t->size(), r = t->rank();
   if (n == 1 || bytes == 0) return;
-  if (ShmBroadcast(t, (char*)buf, bytes, root)) return;
+  if (Took(0, ShmBroadcast(t, (char*)buf, bytes, root))) return;
+  Took(2, true);
   // binomial tree rooted at `root`
   int vr = (r - root + n) % n;
   int mask = 1;
@@ -393,7 +401,8 @@ void Alltoallv(Transport* t, const void* in, const std::vector<int64_t>& sb, voi
   for (int i = 0; i < n; ++i) { sd[i + 1] = sd[i] + sb[i]; rd[i + 1] = rd[i] + rb[i]; }
   const char* i8 = (const char*)in; char* o8 = (char*)out;
   if (sb[r]) memcpy(o8 + rd[r], i8 + sd[r], (size_t)sb[r]);
-  if (n > 1 && ShmAlltoallv(t, i8, sd, o8, rd, rb)) return;
+  if (n > 1 && Took(0, ShmAlltoallv(t, i8, sd, o8, rd, rb))) return;
+  if (n > 1) Took(2, true);
   for (int s = 1; s < n; ++s) {
     int to = (r + s) % n, from = (r - s + n) % n;
     t->SendRecv(to, i8 + sd[to], (size_t)sb[to], from, o8 + rd[from], (size_t)rb[from]);
@@ -406,7 +415,8 @@ void Reducescatter(Transport* t, void* buf, const std::vector<int64_t>& counts, 
   std::vector<int64_t> off(n + 1, 0);
   for (int i = 0; i < n; ++i) off[i + 1] = off[i] + counts[i];
   char* b = (char*)buf;
-  if (n > 1 && ShmReducescatter(t, b, off, (char*)out, dtype, op)) return;
+  if (n > 1 && Took(0, ShmReducescatter(t, b, off, (char*)out, dtype, op))) return;
+  if (n > 1) Took(2, true);
   if (n > 1) {
     int64_t maxseg = *std::max_element(counts.begin(), counts.end());
     std::vector<char> tmp((size_t)maxseg * es);

@@ -38,5 +38,9 @@ void Reducescatter(Transport* t, void* buf, const std::vector<int64_t>& counts, 
 // Requires power-of-two size. dtype: FLOAT16/BFLOAT16/FLOAT32/FLOAT64.
 Status AdasumAllreduce(Transport* t, void* buf, const std::vector<int64_t>& tensor_counts, DataType dtype);
 
+// How many host collectives took which data path since start-up: 0 = shared-memory slots, 1 = two-level (shm + cross-host
+// rings), 2 = ring / tree / star over the base transport.
+unsigned long long HostPathCount(int which);
+
 }  // namespace cpu
 }  // namespace hvd

@@ -33,6 +33,7 @@ assert d['error']['responses'] == 1, d
 assert m.seconds > 0 and m.rate('allreduce', 'bytes') > 0
 assert d['runtime']['responses'] >= 8 and d['runtime']['cycles'] > 0
 
+assert hvd.metrics()['host_paths']['shared_memory'] > 0 and hvd.metrics()['host_paths']['two_level'] == 0
 flat = metrics.flatten(hvd.metrics())
 assert flat['hvd_allreduce_tensors'] >= 13 and 'hvd_runtime_cycles' in flat
 
