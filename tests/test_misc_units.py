@@ -115,3 +115,21 @@ def test_common_util_availability_helpers():
         assert os.environ['HVD_T_X'] == '1'
     assert 'HVD_T_X' not in __import__('os').environ
     assert util.split_list([1, 2, 3, 4, 5], 2) == [[1, 2, 3], [4, 5]] and util.num_rank_is_power_2(8) and not util.num_rank_is_power_2(6)
+
+
+def test_bench_reference_arm_reports_unavailable():
+    """`bench.py --impl reference` must print ONE JSON line with impl=reference and exit 0 — and must not be fooled by the
+    drop-in `horovod` namespace of this repository."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--gpus', '1', '--steps', '2', '--warmup', '3'],
+                       cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith('{')][-1]
+    rec = json.loads(line)
+    assert rec['impl'] == 'reference' and ('unavailable' in rec or 'value' in rec)
+    if 'unavailable' in rec:
+        assert 'mpi_lib_v2' in rec['unavailable'] or 'does not build offline' in rec['unavailable']
