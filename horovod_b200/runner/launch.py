@@ -84,7 +84,7 @@ def check_build(verbose):
         [{ddl_ops}] DDL
         [{ccl_ops}] CCL
         [{mpi_ops}] MPI
-        [{gloo_ops}] Native CPU ops (TCP ring / tree)\
+        [{gloo_ops}] Native CPU ops (shared-memory slots on one host, shm + rings across hosts, TCP ring / tree otherwise)\
     '''.format(verbose_newline='\n' if verbose else '', version=horovod_b200.__version__, tensorflow=get_check(False),
                torch=get_check(True), mxnet=get_check(False), mpi=get_check(b.mpi_built()), gloo=get_check(b.gloo_built()),
                p2p=get_check(b.p2p_built()), nccl_ops=get_check(b.nccl_built()), ddl_ops=get_check(b.ddl_built()),
