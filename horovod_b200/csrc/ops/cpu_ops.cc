@@ -7,6 +7,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include "../common/half.h"
 
 namespace hvd {
@@ -35,6 +38,59 @@ template <typename T> void ReduceT(T* __restrict__ d, const T* __restrict__ s, i
 template <float (*ToF)(uint16_t), uint16_t (*FromF)(float)> void Reduce16(uint16_t* d, const uint16_t* s, int64_t n, ReduceOp op) {
   for (int64_t i = 0; i < n; ++i) d[i] = FromF(Combine<float>(ToF(d[i]), ToF(s[i]), op));
 }
+#if defined(__x86_64__)
+// fp16 through the F16C unit (8 conversions per instruction) when the CPU has it; the function carries its own target
+// attribute, so the rest of the library still runs on CPUs without AVX.  Operand order of min / max keeps the scalar
+// path's NaN behaviour (an unordered compare keeps the destination value).
+__attribute__((target("avx,f16c"))) void ReduceHalfF16C(uint16_t* __restrict__ d, const uint16_t* __restrict__ s, int64_t n, ReduceOp op) {
+  int64_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    const __m256 a = _mm256_cvtph_ps(_mm_loadu_si128((const __m128i*)(d + i)));
+    const __m256 b = _mm256_cvtph_ps(_mm_loadu_si128((const __m128i*)(s + i)));
+    __m256 r;
+    switch (op) {
+      case ReduceOp::MIN: r = _mm256_min_ps(b, a); break;
+      case ReduceOp::MAX: r = _mm256_max_ps(b, a); break;
+      case ReduceOp::PRODUCT: r = _mm256_mul_ps(a, b); break;
+      default: r = _mm256_add_ps(a, b); break;
+    }
+    _mm_storeu_si128((__m128i*)(d + i), _mm256_cvtps_ph(r, _MM_FROUND_TO_NEAREST_INT | _MM_FROUND_NO_EXC));
+  }
+  for (; i < n; ++i) d[i] = FloatToHalfBits(Combine<float>(HalfBitsToFloat(d[i]), HalfBitsToFloat(s[i]), op));
+}
+__attribute__((target("avx,f16c"))) void ScaleHalfF16C(uint16_t* b, int64_t n, float f) {
+  const __m256 scale = _mm256_set1_ps(f);
+  int64_t i = 0;
+  for (; i + 8 <= n; i += 8)
+    _mm_storeu_si128((__m128i*)(b + i), _mm256_cvtps_ph(_mm256_mul_ps(_mm256_cvtph_ps(_mm_loadu_si128((const __m128i*)(b + i))), scale),
+                                                        _MM_FROUND_TO_NEAREST_INT | _MM_FROUND_NO_EXC));
+  for (; i < n; ++i) b[i] = FloatToHalfBits(HalfBitsToFloat(b[i]) * f);
+}
+bool HaveF16C() { static const bool have = __builtin_cpu_supports("f16c") && __builtin_cpu_supports("avx"); return have; }
+#else
+bool HaveF16C() { return false; }
+#endif
+
+// bf16: widening is a shift, narrowing is round-to-nearest-even with the NaN case as a select (no branch), and the operator is
+// chosen outside the loop — the whole body vectorises.
+inline uint16_t NarrowBF16(float v) {
+  uint32_t x; memcpy(&x, &v, 4);
+  const uint32_t rounded = (x + 0x7fffu + ((x >> 16) & 1u)) >> 16;
+  const uint32_t quiet_nan = (x >> 16) | 0x40u;
+  return (uint16_t)(((x & 0x7fffffffu) > 0x7f800000u) ? quiet_nan : rounded);
+}
+template <typename F> void ReduceBF16With(uint16_t* __restrict__ d, const uint16_t* __restrict__ s, int64_t n, F f) {
+  for (int64_t i = 0; i < n; ++i) d[i] = NarrowBF16(f(BF16BitsToFloat(d[i]), BF16BitsToFloat(s[i])));
+}
+void ReduceBF16(uint16_t* d, const uint16_t* s, int64_t n, ReduceOp op) {
+  switch (op) {
+    case ReduceOp::MIN: ReduceBF16With(d, s, n, [](float a, float b) { return b < a ? b : a; }); return;
+    case ReduceOp::MAX: ReduceBF16With(d, s, n, [](float a, float b) { return b > a ? b : a; }); return;
+    case ReduceOp::PRODUCT: ReduceBF16With(d, s, n, [](float a, float b) { return a * b; }); return;
+    default: ReduceBF16With(d, s, n, [](float a, float b) { return a + b; }); return;
+  }
+}
+
 template <typename T> void ScaleT(T* b, int64_t n, double s) { for (int64_t i = 0; i < n; ++i) b[i] = (T)(b[i] * s); }
 
 double LoadAsDouble(const void* p, int64_t i, DataType t) {
@@ -66,8 +122,13 @@ void ReduceInto(void* dst, const void* src, int64_t n, DataType dtype, ReduceOp 
     case DataType::INT64: ReduceT((int64_t*)dst, (const int64_t*)src, n, op); break;
     case DataType::FLOAT32: ReduceT((float*)dst, (const float*)src, n, op); break;
     case DataType::FLOAT64: ReduceT((double*)dst, (const double*)src, n, op); break;
-    case DataType::FLOAT16: Reduce16<HalfBitsToFloat, FloatToHalfBits>((uint16_t*)dst, (const uint16_t*)src, n, op); break;
-    case DataType::BFLOAT16: Reduce16<BF16BitsToFloat, FloatToBF16Bits>((uint16_t*)dst, (const uint16_t*)src, n, op); break;
+    case DataType::FLOAT16:
+#if defined(__x86_64__)
+      if (HaveF16C()) { ReduceHalfF16C((uint16_t*)dst, (const uint16_t*)src, n, op); break; }
+#endif
+      Reduce16<HalfBitsToFloat, FloatToHalfBits>((uint16_t*)dst, (const uint16_t*)src, n, op);
+      break;
+    case DataType::BFLOAT16: ReduceBF16((uint16_t*)dst, (const uint16_t*)src, n, op); break;
   }
 }
 
@@ -82,8 +143,15 @@ void ScaleBuffer(void* buf, int64_t n, DataType dtype, double s) {
     case DataType::INT64: ScaleT((int64_t*)buf, n, s); break;
     case DataType::FLOAT32: { float* b = (float*)buf; float f = (float)s; for (int64_t i = 0; i < n; ++i) b[i] *= f; break; }
     case DataType::FLOAT64: ScaleT((double*)buf, n, s); break;
-    case DataType::FLOAT16: { uint16_t* b = (uint16_t*)buf; for (int64_t i = 0; i < n; ++i) b[i] = FloatToHalfBits(HalfBitsToFloat(b[i]) * (float)s); break; }
-    case DataType::BFLOAT16: { uint16_t* b = (uint16_t*)buf; for (int64_t i = 0; i < n; ++i) b[i] = FloatToBF16Bits(BF16BitsToFloat(b[i]) * (float)s); break; }
+    case DataType::FLOAT16: {
+      uint16_t* b = (uint16_t*)buf;
+#if defined(__x86_64__)
+      if (HaveF16C()) { ScaleHalfF16C(b, n, (float)s); break; }
+#endif
+      for (int64_t i = 0; i < n; ++i) b[i] = FloatToHalfBits(HalfBitsToFloat(b[i]) * (float)s);
+      break;
+    }
+    case DataType::BFLOAT16: { uint16_t* b = (uint16_t*)buf; const float f = (float)s; for (int64_t i = 0; i < n; ++i) b[i] = NarrowBF16(BF16BitsToFloat(b[i]) * f); break; }
   }
 }
 

@@ -166,3 +166,10 @@ def test_shared_memory_data_plane(native_built, np_, env):
 def test_reference_behavioural_details(native_built):
     rc, out = run_parallel("appendix_a_worker.py", np=3, timeout=200)
     assert "APPENDIX A OK dup_err=True" in out, out[-3000:]
+
+
+def test_half_precision_host_reductions_are_bit_exact(native_built):
+    """fp16 (F16C) and bf16 (auto-vectorised) host reductions against torch's fp32-op-then-round result, bit for bit, including
+    inf / NaN / subnormals / signed zeros and odd lengths (scalar tails)."""
+    rc, out = run_parallel("half_exact_worker.py", np=2, timeout=300)
+    assert "HALF EXACT OK" in out, out[-3000:]
