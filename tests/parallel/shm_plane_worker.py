@@ -67,6 +67,23 @@ for n in (1, 5, 1023, 1024, 1025, 4099, 70001):
         avg = hvd.allreduce(xs[rank].float(), op=hvd.Average, name='avg.%d.%s' % (n, dtype))
         assert torch.allclose(avg, sum(x.float() for x in xs) / size, rtol=1e-5, atol=1e-5)
 
+# big messages (several MiB): the helper-thread team splits the copy / reduce phases when HVD_CPU_THREADS > 1
+if int(os.environ.get('HVD_CPU_THREADS', '1')) != 1:
+    for n, dtype in ((3000001, torch.float32), (2500003, torch.bfloat16), (1500001, torch.int64)):
+        xs = [data(n, dtype, r) for r in range(size)]
+        for op, fn in ((hvd.Sum, lambda a, b: a + b), (hvd.Max, torch.maximum)):
+            out = hvd.allreduce(xs[rank], op=op, name='big.%s.%d' % (dtype, op))
+            ref = xs[0].float() if dtype == torch.bfloat16 else xs[0].clone()
+            for r in range(1, size):
+                ref = fn(ref, xs[r].float() if dtype == torch.bfloat16 else xs[r])
+            if dtype == torch.bfloat16:
+                assert torch.allclose(out.float(), ref, rtol=2e-2, atol=2e-2), (n, dtype, op)
+            elif dtype.is_floating_point:
+                assert torch.allclose(out, ref, rtol=1e-5, atol=1e-6), (n, dtype, op)
+            else:
+                assert torch.equal(out, ref), (n, dtype, op)
+            checked += 1
+
 # uneven allgather (rank r contributes (r+1)*k rows), including an empty contribution
 for k in (0, 1, 333, 5000):
     mine = torch.arange((rank + 1) * k * 3, dtype=torch.float32).reshape(-1, 3) + 1000 * rank

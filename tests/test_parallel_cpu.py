@@ -151,6 +151,7 @@ def test_broadcast_optimizer_state_every_torch_optimizer(native_built):
 
 @pytest.mark.parametrize("np_,env", [(2, {"HVD_SHM_SLOT_BYTES": "4096"}), (3, {"HVD_SHM_SLOT_BYTES": "8192"}),
                                      (3, {"HVD_SHM_DATA_PLANE": "0"}), (4, {"HVD_SHM_SLOT_BYTES": "16384"}),
+                                     (2, {"HVD_SHM_SLOT_BYTES": "4194304", "HVD_CPU_THREADS": "3"}),
                                      (4, {"HVD_TEST_FAKE_HOSTS": "2", "HVD_SHM_SLOT_BYTES": "8192"}),
                                      (3, {"HVD_TEST_FAKE_HOST_MAP": "0,0,1"})])
 def test_shared_memory_data_plane(native_built, np_, env):
