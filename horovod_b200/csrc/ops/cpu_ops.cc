@@ -425,6 +425,31 @@ bool HierAllgatherv(Transport* t, char* o, const std::vector<int64_t>& bytes, co
   return true;
 }
 
+void TreeBroadcast(Transport* t, void* buf, int64_t bytes, int root);
+
+// Two-level broadcast: across hosts only the ranks with the root's local index talk (binomial tree over H ranks instead of
+// N), then every host hands the data to its other ranks through the shm slot of that local index.
+bool HierBroadcast(Transport* t, char* buf, int64_t bytes, int root) {
+  HierData h;
+  if (!t->HierDataPlane(&h)) return false;
+  const auto& column = *h.column;
+  int root_l = -1, root_h = -1;
+  for (int l = 0; l < h.local_size && root_l < 0; ++l)
+    for (int x = 0; x < (int)column[(size_t)l].size(); ++x)
+      if (column[(size_t)l][(size_t)x] == root) { root_l = l; root_h = x; break; }
+  if (root_l < 0) return false;
+  if (h.local_rank == root_l) TreeBroadcast(h.cross, buf, bytes, root_h);
+  const int64_t S = (int64_t)h.local.slot_bytes;
+  for (int64_t done = 0; done < bytes; done += S) {
+    const int half = (int)(t->ShmNextPiece() & 1);
+    const int64_t m = std::min(S, bytes - done);
+    if (h.local_rank == root_l) memcpy(h.local.slot(root_l, half), buf + done, (size_t)m);
+    t->LocalBarrier();
+    if (h.local_rank != root_l) memcpy(buf + done, h.local.slot(root_l, half), (size_t)m);
+  }
+  return true;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------
@@ -501,7 +526,15 @@ void Broadcast(Transport* t, void* buf, int64_t bytes, int root) {
   const int n = t->size(), r = t->rank();
   if (n == 1 || bytes == 0) return;
   if (Took(0, ShmBroadcast(t, (char*)buf, bytes, root))) return;
+  if (Took(1, HierBroadcast(t, (char*)buf, bytes, root))) return;
   Took(2, true);
+  TreeBroadcast(t, buf, bytes, root);
+}
+
+namespace {
+void TreeBroadcast(Transport* t, void* buf, int64_t bytes, int root) {
+  const int n = t->size(), r = t->rank();
+  if (n == 1 || bytes == 0) return;
   // binomial tree rooted at `root`
   int vr = (r - root + n) % n;
   int mask = 1;
@@ -515,6 +548,7 @@ void Broadcast(Transport* t, void* buf, int64_t bytes, int root) {
     mask >>= 1;
   }
 }
+}  // namespace
 
 void Alltoallv(Transport* t, const void* in, const std::vector<int64_t>& sb, void* out, const std::vector<int64_t>& rb) {
   const int n = t->size(), r = t->rank();

@@ -164,6 +164,11 @@ if size >= 3 and FAKE_HOSTS <= 1:
     hvd.remove_process_set(odds)
     hvd.remove_process_set(evens)
 
+paths = hvd.metrics()['host_paths']
+if 'two-level (shared-memory slots' in hvd.control_plane_info():
+    assert paths['two_level'] > 0 and paths['shared_memory'] == 0, paths        # allreduce / allgather / broadcast took the two-level path
+elif 'host data: shared-memory slots' in hvd.control_plane_info():
+    assert paths['shared_memory'] > 0 and paths['two_level'] == 0, paths
 info = os.environ.get('HVD_SHM_DATA_PLANE', '1')
 hvd.barrier()
 if rank == 0:
