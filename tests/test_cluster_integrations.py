@@ -186,3 +186,31 @@ def test_unified_ray_executor_elastic_mode(native_built):
         for h in created:
             backend.kill(h)
     assert sorted(r[0] for r in res) == [0, 1] and all(r[1] == 2 and r[2] == [3.0, 3.0] for r in res), res
+
+
+def _fails_until_two(marker_dir):
+    """Raises on every rank while the job is wider than 2 ranks (a stand-in for 'one executor keeps dying')."""
+    import os
+    import torch
+    import horovod_b200.torch as hvd
+    hvd.init()
+    try:
+        if hvd.size() > 2:
+            open(os.path.join(marker_dir, 'attempt.%d.%d' % (hvd.size(), hvd.rank())), 'w').close()
+            raise RuntimeError('too wide: %d' % hvd.size())
+        out = hvd.allreduce(torch.ones(2), op=hvd.Sum, name='narrow').tolist()
+        return hvd.rank(), hvd.size(), out
+    finally:
+        hvd.shutdown()
+
+
+def test_spark_run_elastic_retries_with_fewer_tasks(native_built, tmp_path):
+    """run_elastic: a failed attempt is retried one task narrower until it fits (num_proc 3 -> 2 here), never below min_num_proc."""
+    import horovod_b200.spark as hvd_spark
+    res = hvd_spark.run_elastic(_fails_until_two, args=(str(tmp_path),), num_proc=3, min_num_proc=2, reset_limit=2, _launch=_mp_launch,
+                                start_timeout=120, verbose=0)
+    assert sorted(r[0] for r in res) == [0, 1] and all(r[1] == 2 and r[2] == [2.0, 2.0] for r in res), res
+    assert sorted(os.listdir(tmp_path)) == ['attempt.3.0', 'attempt.3.1', 'attempt.3.2']       # exactly one wide attempt
+    with pytest.raises(RuntimeError, match='too wide'):                                          # may not shrink below min_num_proc
+        hvd_spark.run_elastic(_fails_until_two, args=(str(tmp_path),), num_proc=3, min_num_proc=3, reset_limit=1, _launch=_mp_launch,
+                              start_timeout=120, verbose=0)
