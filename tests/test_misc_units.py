@@ -133,3 +133,21 @@ def test_bench_reference_arm_reports_unavailable():
     assert rec['impl'] == 'reference' and ('unavailable' in rec or 'value' in rec)
     if 'unavailable' in rec:
         assert 'mpi_lib_v2' in rec['unavailable'] or 'does not build offline' in rec['unavailable']
+
+
+def test_every_hvd_knob_is_documented():
+    """docs/knobs.md lists every HVD_* environment variable the sources read."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = set()
+    for base, _, files in os.walk(os.path.join(root, 'horovod_b200')):
+        if '__pycache__' in base or os.sep + 'build' in base:
+            continue
+        for f in files:
+            if f.endswith(('.cc', '.h', '.cu', '.cuh', '.py')):
+                with open(os.path.join(base, f), errors='ignore') as fh:
+                    names |= set(re.findall(r'["\'](HVD_[A-Z0-9_]+)["\']', fh.read()))
+    doc = open(os.path.join(root, 'docs', 'knobs.md')).read()
+    missing = sorted(n for n in names if n not in doc and not n.startswith('HVD_TEST_'))
+    assert not missing, 'undocumented knobs: %s' % missing
