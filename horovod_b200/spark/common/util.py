@@ -90,7 +90,9 @@ def write_parquet(df, path, store, num_files, columns=None):
             from pyspark.ml.functions import vector_to_array
             for c in vector_cols:
                 out = out.withColumn(c, vector_to_array(out[c]))
-        out.repartition(num_files).write.mode('overwrite').parquet(path)
+        # a scheme-less path would be resolved against the cluster's default filesystem (often HDFS): LocalStore means file://
+        spark_path = path if '://' in path else 'file://' + path
+        out.repartition(num_files).write.mode('overwrite').parquet(spark_path)
         return out.count()
     import pyarrow.parquet as pq
     cols = list(columns) if columns else list(df.columns)
