@@ -75,9 +75,11 @@ void WaitSlot(Slot& s, uint64_t k, int r) { WaitSeqReaches(s.seq, s.pid, k, r); 
 // quota may prefer fewer yields: HVD_SHM_SPIN_PAUSES / HVD_SHM_SPIN_YIELDS.
 struct SpinPolicy {
   uint64_t pauses = 2000, yields = 18000;
+  double timeout_s = 0;     // HVD_SHM_TIMEOUT_SECONDS: give up on a peer that is alive but does not arrive (0 = wait forever)
   SpinPolicy() {
     if (const char* e = getenv("HVD_SHM_SPIN_PAUSES")) pauses = (uint64_t)std::max(0LL, atoll(e));
     if (const char* e = getenv("HVD_SHM_SPIN_YIELDS")) yields = (uint64_t)std::max(0LL, atoll(e));
+    if (const char* e = getenv("HVD_SHM_TIMEOUT_SECONDS")) timeout_s = std::max(0.0, atof(e));
   }
 };
 
@@ -101,6 +103,7 @@ void WaitSeqReaches(std::atomic<uint64_t>& seq, const int32_t& owner_pid, uint64
   static const SpinPolicy policy;
   uint64_t spins = 0;
   auto last_check = std::chrono::steady_clock::now();
+  const auto started = last_check;
   while (seq.load(std::memory_order_acquire) < k) {
     ++spins;
     if (spins < policy.pauses) {
@@ -117,6 +120,9 @@ void WaitSeqReaches(std::atomic<uint64_t>& seq, const int32_t& owner_pid, uint64
         int pid = g_trust_pids.load(std::memory_order_relaxed) ? (int)owner_pid : 0;
         if (pid > 0 && !ProcessAlive(pid))
           throw TransportError("rank " + std::to_string(r) + " (pid " + std::to_string(pid) + ") died");
+        if (policy.timeout_s > 0 && std::chrono::duration<double>(now - started).count() > policy.timeout_s)
+          throw TransportError("rank " + std::to_string(r) + " did not reach the shared-memory exchange within " +
+                               std::to_string((int)policy.timeout_s) + " s (HVD_SHM_TIMEOUT_SECONDS)");
       }
     }
   }

@@ -174,3 +174,10 @@ def test_half_precision_host_reductions_are_bit_exact(native_built):
     inf / NaN / subnormals / signed zeros and odd lengths (scalar tails)."""
     rc, out = run_parallel("half_exact_worker.py", np=2, timeout=300)
     assert "HALF EXACT OK" in out, out[-3000:]
+
+
+def test_shm_wait_timeout_on_a_stopped_peer(native_built):
+    """HVD_SHM_TIMEOUT_SECONDS: rank 1 SIGSTOPs itself (alive, but its cycle thread is frozen); rank 0 gets a HorovodInternalError
+    after the timeout instead of spinning forever."""
+    rc, out = run_parallel("shm_timeout_worker.py", np=2, timeout=120, env={"HVD_SHM_TIMEOUT_SECONDS": "3"}, expect_fail=True)
+    assert "TIMEOUT RAISED" in out and "NO ERROR" not in out, out[-3000:]
