@@ -6,12 +6,13 @@
 namespace hvd {
 
 namespace {
-constexpr uint64_t kStatusShutdown = 1, kStatusUncached = 2, kStatusInvalid = 4;
+constexpr uint64_t kStatusShutdown = 1, kStatusUncached = 2, kStatusInvalid = 4, kStatusJoined = 8;
 
 inline void SetBit(std::vector<uint64_t>& w, size_t base, uint32_t bit) { w[base + bit / 64] |= (1ull << (bit % 64)); }
 inline bool GetBit(const std::vector<uint64_t>& w, size_t base, uint32_t bit) { return (w[base + bit / 64] >> (bit % 64)) & 1; }
 
 int64_t AlignedBytes(const Response& r) {
+  if (r.type == ResponseType::ALLGATHER) return r.payload_bytes;  // per-rank first dims x row bytes (ConstructResponse)
   int64_t total = 0;
   for (auto n : r.tensor_sizes) {
     int64_t b = n * (int64_t)DataTypeSize(r.dtype);
@@ -20,7 +21,12 @@ int64_t AlignedBytes(const Response& r) {
   return total;
 }
 
-bool Fusable(ResponseType t) { return t == ResponseType::ALLREDUCE || t == ResponseType::ADASUM; }
+// ALLGATHER and REDUCESCATTER fuse like the reference (controller.cc:915-918, :1003-1086); BROADCAST responses of one root
+// fuse as well (the reference never fuses them: hvd.broadcast_parameters is one launch per dtype here, not one per tensor).
+bool Fusable(ResponseType t) {
+  return t == ResponseType::ALLREDUCE || t == ResponseType::ADASUM || t == ResponseType::ALLGATHER ||
+         t == ResponseType::REDUCESCATTER || t == ResponseType::BROADCAST;
+}
 
 std::string ShapeStr(const std::vector<int64_t>& s) { return TensorShape(s).DebugString(); }
 }  // namespace
@@ -98,6 +104,7 @@ ResponseList Controller::ComputeResponseList(bool shutdown_requested) {
   if (shutdown_requested || stall_shutdown_) or_words[0] |= kStatusShutdown;
   if (!uncached.empty()) or_words[0] |= kStatusUncached;
   if (!invalid_bits.empty()) or_words[0] |= kStatusInvalid;
+  if (local_joined_) or_words[0] |= kStatusJoined;
   transport_->AllreduceBits(and_words.data(), (int)nw, or_words.data(), (int)or_words.size());
   const uint64_t status = or_words[0];
 
@@ -124,6 +131,10 @@ ResponseList Controller::ComputeResponseList(bool shutdown_requested) {
   for (uint32_t b = 0; b < nbits; ++b) {
     if (!GetBit(and_words, 0, b) || !GetBit(or_words, 1 + nw, b) || !cache_->HasBit(b)) continue;
     Response resp = cache_->GetResponse(b);
+    // A joined rank has no tensor in the registered region the cached response points at: while any rank is joined every
+    // rank (the OR bit is global) runs the cached response through the fusion-buffer kernel, where the joined rank
+    // contributes zeros (the slow path does the same in ConstructResponse).
+    if (status & kStatusJoined) resp.symm_key = -1;
     auto it = pending_hits_.find(b);
     if (it != pending_hits_.end()) {
       resp.group_id = it->second.group_id;
@@ -391,6 +402,9 @@ Response Controller::ConstructResponse(const std::string& name, const std::vecto
   if (t == RequestType::ALLGATHER) {
     resp.tensor_sizes.assign(set_size, 0);
     for (auto& q : requests) resp.tensor_sizes[q.request_rank] = q.shape[0];
+    int64_t row = (int64_t)DataTypeSize(first.dtype);
+    for (size_t d = 1; d < first.shape.size(); ++d) row *= first.shape[d];
+    for (auto d0 : resp.tensor_sizes) resp.payload_bytes += (d0 * row + FUSION_ALIGN_BYTES - 1) / FUSION_ALIGN_BYTES * FUSION_ALIGN_BYTES;
   } else if (t == RequestType::PROCESS_SET_ADD || t == RequestType::PROCESS_SET_REMOVE || t == RequestType::SYMM_ALLOC) {
     resp.tensor_sizes = first.shape;
   } else if (t != RequestType::BARRIER && t != RequestType::JOIN) {
@@ -412,12 +426,14 @@ std::deque<Response> Controller::FuseResponses(std::deque<Response> responses, i
         Response& n = responses.front();
         bool compatible = n.type == r.type && n.dtype == r.dtype && n.devices == r.devices &&
                           n.prescale == r.prescale && n.postscale == r.postscale && n.reduce_op == r.reduce_op &&
+                          n.root_rank == r.root_rank &&
                           (!disable_group_fusion || n.group_id == r.group_id) && n.symm_key < 0 && r.symm_key < 0;
         int64_t nb = compatible ? AlignedBytes(n) : 0;
         if (compatible && total + nb <= threshold) {
           total += nb;
           for (auto& s : n.tensor_names) r.tensor_names.push_back(std::move(s));
           for (auto s : n.tensor_sizes) r.tensor_sizes.push_back(s);
+          r.payload_bytes += n.payload_bytes;
         } else {
           skipped.push_back(std::move(n));  // look-ahead: keep scanning, preserve order of what we skip
         }

@@ -41,7 +41,7 @@ void Response::Serialize(ByteWriter& w) const {
   for (auto& s : tensor_names) w.str(s);
   w.str(error_message); w.vec_i32(devices); w.vec_i64(tensor_sizes); w.u8((uint8_t)dtype);
   w.f64(prescale); w.f64(postscale); w.u8((uint8_t)reduce_op); w.i32(last_joined_rank); w.i32(root_rank);
-  w.i32(group_id); w.i64(symm_key);
+  w.i32(group_id); w.i64(symm_key); w.i64(payload_bytes);
 }
 Response Response::Parse(ByteReader& r) {
   Response s; s.type = (ResponseType)r.u8(); int32_t n = r.i32();
@@ -49,7 +49,7 @@ Response Response::Parse(ByteReader& r) {
   for (int i = 0; i < n; ++i) s.tensor_names.push_back(r.str());
   s.error_message = r.str(); s.devices = r.vec_i32(); s.tensor_sizes = r.vec_i64(); s.dtype = (DataType)r.u8();
   s.prescale = r.f64(); s.postscale = r.f64(); s.reduce_op = (ReduceOp)r.u8(); s.last_joined_rank = r.i32();
-  s.root_rank = r.i32(); s.group_id = r.i32(); s.symm_key = r.i64();
+  s.root_rank = r.i32(); s.group_id = r.i32(); s.symm_key = r.i64(); s.payload_bytes = r.i64();
   return s;
 }
 std::vector<uint8_t> ResponseList::Serialize() const {

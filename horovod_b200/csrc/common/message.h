@@ -90,6 +90,7 @@ struct Response {
   int32_t root_rank = 0;
   int32_t group_id = -1;              // not serialised beyond fusion decisions
   int64_t symm_key = -1;              // >= 0: every rank holds this tensor at the same place of the same registered region
+  int64_t payload_bytes = 0;          // fusion accounting: bytes this response moves through the fusion / symmetric buffer
   void Serialize(ByteWriter& w) const;
   static Response Parse(ByteReader& r);
 };

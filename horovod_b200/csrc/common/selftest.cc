@@ -97,11 +97,24 @@ void TestFusion() {
   CHECK_T(out.size() == 2 && out[0].tensor_names.size() == 2);
   out = Controller::FuseResponses(grouped, 1 << 20, false);
   CHECK_T(out.size() == 1);
-  // allgather is never fused
+  // allgather fuses (per-rank first dims are concatenated tensor by tensor) up to the threshold on its output bytes
   std::deque<Response> ag;
-  Response g = MkResp("ag0", 4); g.type = ResponseType::ALLGATHER; ag.push_back(g);
-  g.tensor_names = {"ag1"}; ag.push_back(g);
-  CHECK_T(Controller::FuseResponses(ag, 1 << 20, false).size() == 2);
+  Response g = MkResp("ag0", 4); g.type = ResponseType::ALLGATHER; g.tensor_sizes = {2, 5}; g.payload_bytes = 256; ag.push_back(g);
+  g.tensor_names = {"ag1"}; g.tensor_sizes = {3, 1}; ag.push_back(g);
+  out = Controller::FuseResponses(ag, 1 << 20, false);
+  CHECK_T(out.size() == 1 && out[0].tensor_sizes == std::vector<int64_t>({2, 5, 3, 1}) && out[0].payload_bytes == 512);
+  CHECK_T(Controller::FuseResponses(ag, 300, false).size() == 2);
+  // reducescatter fuses with the allreduce rule; broadcasts fuse only when they share the root
+  std::deque<Response> rs;
+  Response q = MkResp("rs0", 100); q.type = ResponseType::REDUCESCATTER; rs.push_back(q);
+  q.tensor_names = {"rs1"}; rs.push_back(q);
+  CHECK_T(Controller::FuseResponses(rs, 1 << 20, false).size() == 1);
+  std::deque<Response> bc;
+  Response b0 = MkResp("b0", 100); b0.type = ResponseType::BROADCAST; b0.root_rank = 0; bc.push_back(b0);
+  Response b1 = MkResp("b1", 100); b1.type = ResponseType::BROADCAST; b1.root_rank = 1; bc.push_back(b1);
+  Response b2 = MkResp("b2", 100); b2.type = ResponseType::BROADCAST; b2.root_rank = 0; bc.push_back(b2);
+  out = Controller::FuseResponses(bc, 1 << 20, false);
+  CHECK_T(out.size() == 2 && out[0].tensor_names == std::vector<std::string>({"b0", "b2"}));
 }
 
 void TestValidation() {

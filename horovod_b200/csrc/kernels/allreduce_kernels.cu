@@ -75,18 +75,35 @@ __device__ __forceinline__ void pack_range(const TensorDesc* descs, int nd, int6
                                            typename ScaleOf<typename Traits<W>::Acc>::type scale) {
   using A = typename Traits<W>::Acc;
   constexpr int NW = 16 / (int)sizeof(W);
+  constexpr int64_t kSrcRow = (int64_t)kRowBytes / (int)sizeof(W) * (int)sizeof(T);  // source bytes per wire row
   DescCursor cur;
   cur.init(descs, nd, total);
   for (int64_t o0 = lo + (int64_t)threadIdx.x * 16; o0 < hi; o0 += (int64_t)U * kRowBytes) {
     A a[U][NW];
+    cur.seek(o0);
+    const int64_t olast = o0 + (int64_t)(U - 1) * kRowBytes;
+    const int64_t e0 = (o0 - cur.lo) / (int64_t)sizeof(W);
+    const char* src = cur.in + e0 * (int64_t)sizeof(T);
+    // fast path: all U vectors of this trip are full vectors of ONE tensor and the source is 16 B aligned (the row
+    // stride is a multiple of 16 B, so one check covers the trip): no cursor work, no bounds checks
+    if (olast < hi && olast + 16 <= cur.lo + cur.count * (int64_t)sizeof(W) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < U; ++j) load_elems_fast<T, NW, A>(reinterpret_cast<const T*>(src + j * kSrcRow), a[j]);
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+#pragma unroll
+        for (int i = 0; i < NW; ++i) a[j][i] = apply_scale<A>(a[j][i], scale);
+        st_stream(buf + o0 + (int64_t)j * kRowBytes, pack_vec<W, NW>(a[j]));
+      }
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < U; ++j) {
       const int64_t o = o0 + (int64_t)j * kRowBytes;
       if (o < hi) {
         cur.seek(o);
-        const TensorDesc& d = cur.d[cur.i];
         const int64_t e = (o - cur.lo) / (int64_t)sizeof(W);
-        load_elems<T, NW, A>(reinterpret_cast<const T*>(d.in) + e, d.count - e, a[j]);
+        load_elems<T, NW, A>(reinterpret_cast<const T*>(cur.in) + e, cur.count - e, a[j]);
       }
     }
 #pragma unroll
@@ -106,6 +123,7 @@ __device__ __forceinline__ void unpack_range(const TensorDesc* descs, int nd, in
                                              int64_t hi) {
   using A = typename Traits<W>::Acc;
   constexpr int NW = 16 / (int)sizeof(W);
+  constexpr int64_t kDstRow = (int64_t)kRowBytes / (int)sizeof(W) * (int)sizeof(T);
   DescCursor cur;
   cur.init(descs, nd, total);
   for (int64_t o0 = lo + (int64_t)threadIdx.x * 16; o0 < hi; o0 += (int64_t)U * kRowBytes) {
@@ -115,17 +133,29 @@ __device__ __forceinline__ void unpack_range(const TensorDesc* descs, int nd, in
       const int64_t o = o0 + (int64_t)j * kRowBytes;
       if (o < hi) v[j] = ld_stream(buf + o);
     }
+    cur.seek(o0);
+    const int64_t olast = o0 + (int64_t)(U - 1) * kRowBytes;
+    const int64_t e0 = (o0 - cur.lo) / (int64_t)sizeof(W);
+    char* dst = cur.out + e0 * (int64_t)sizeof(T);
+    if (olast < hi && olast + 16 <= cur.lo + cur.count * (int64_t)sizeof(W) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        A a[NW];
+        unpack_vec<W, NW>(v[j], a);
+        store_elems_fast<T, NW, A>(reinterpret_cast<T*>(dst + j * kDstRow), a);
+      }
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < U; ++j) {
       const int64_t o = o0 + (int64_t)j * kRowBytes;
       if (o < hi) {
         cur.seek(o);
-        const TensorDesc& d = cur.d[cur.i];
         const int64_t e = (o - cur.lo) / (int64_t)sizeof(W);
-        if (e < d.count) {
+        if (e < cur.count) {
           A a[NW];
           unpack_vec<W, NW>(v[j], a);
-          store_elems<T, NW, A>(reinterpret_cast<T*>(d.out) + e, d.count - e, a);
+          store_elems<T, NW, A>(reinterpret_cast<T*>(cur.out) + e, cur.count - e, a);
         }
       }
     }
@@ -193,6 +223,36 @@ allreduce_kernel(const __grid_constant__ CommParams cp, const __grid_constant__ 
       int64_t hi = lo + chunk_bytes < total ? lo + chunk_bytes : total;
       if (lo < a.reduce_lo) lo = a.reduce_lo;
       if (hi > a.reduce_hi) hi = a.reduce_hi;
+      if (a.oneshot_nvls) {
+        // reduce-scatter through the switch: one multimem.ld_reduce per vector instead of N peer loads
+        if constexpr (Nvls<W>::ok) {
+          constexpr int UN = 4;
+          for (int64_t o0 = lo + (int64_t)threadIdx.x * 16; o0 < hi; o0 += (int64_t)UN * kRowBytes) {
+            uint4 v[UN];
+#pragma unroll
+            for (int j = 0; j < UN; ++j) {
+              const int64_t o = o0 + (int64_t)j * kRowBytes;
+              if (o < hi) v[j] = Nvls<W>::ld_reduce(reinterpret_cast<const char*>(cp.mc_buf) + o);
+            }
+#pragma unroll
+            for (int j = 0; j < UN; ++j) {
+              const int64_t o = o0 + (int64_t)j * kRowBytes;
+              if (o < hi) {
+                A acc[NW];
+                unpack_vec<W, NW>(v[j], acc);
+                cur.seek(o);
+                const int64_t e = (o - cur.lo) / (int64_t)sizeof(W);
+                if (e < cur.count) {
+#pragma unroll
+                  for (int i = 0; i < NW; ++i) acc[i] = apply_scale<A>(acc[i], postscale);
+                  store_elems<T, NW, A>(reinterpret_cast<T*>(cur.out) + e, cur.count - e, acc);
+                }
+              }
+            }
+          }
+        }
+        continue;
+      }
       for (int64_t o0 = lo + (int64_t)threadIdx.x * 16; o0 < hi; o0 += (int64_t)U * kRowBytes) {
         uint4 v[U][NR];
 #pragma unroll
@@ -207,12 +267,11 @@ allreduce_kernel(const __grid_constant__ CommParams cp, const __grid_constant__ 
             A acc[NW];
             peer_combine<W, NR>(cp, v[j], a.op, acc);
             cur.seek(o);
-            const TensorDesc& d = cur.d[cur.i];
             const int64_t e = (o - cur.lo) / (int64_t)sizeof(W);
-            if (e < d.count) {
+            if (e < cur.count) {
 #pragma unroll
               for (int i = 0; i < NW; ++i) acc[i] = apply_scale<A>(acc[i], postscale);
-              store_elems<T, NW, A>(reinterpret_cast<T*>(d.out) + e, d.count - e, acc);
+              store_elems<T, NW, A>(reinterpret_cast<T*>(cur.out) + e, cur.count - e, acc);
             }
           }
         }
@@ -592,20 +651,19 @@ pack_unpack_kernel(char* buffer, const TensorDesc* descs, int nd, int64_t total,
   cur.init(descs, nd, total);
   for (int64_t o = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 16; o < total; o += (int64_t)gridDim.x * kRowBytes) {
     cur.seek(o);
-    const TensorDesc& d = cur.d[cur.i];
     const int64_t e = (o - cur.lo) / (int64_t)sizeof(W);
     A acc[NW];
     if (direction == 0) {
-      load_elems<T, NW, A>(reinterpret_cast<const T*>(d.in) + e, d.count - e, acc);
+      load_elems<T, NW, A>(reinterpret_cast<const T*>(cur.in) + e, cur.count - e, acc);
 #pragma unroll
       for (int i = 0; i < NW; ++i) acc[i] = apply_scale<A>(acc[i], (S)scale);
       st_stream(buffer + o, pack_vec<W, NW>(acc));
     } else {
-      if (e >= d.count) continue;
+      if (e >= cur.count) continue;
       unpack_vec<W, NW>(ld_stream(buffer + o), acc);
 #pragma unroll
       for (int i = 0; i < NW; ++i) acc[i] = apply_scale<A>(acc[i], (S)scale);
-      store_elems<T, NW, A>(reinterpret_cast<T*>(d.out) + e, d.count - e, acc);
+      store_elems<T, NW, A>(reinterpret_cast<T*>(cur.out) + e, cur.count - e, acc);
     }
   }
 }
@@ -669,6 +727,10 @@ cudaError_t LaunchAllreduce(const CommParams& cp, const AllreduceArgs& args, cud
   if (args.variant == kNvls) {
     const int w = args.dtype == 7 ? (args.wire_dtype == 10 || args.wire_dtype == 6 ? args.wire_dtype : 7) : args.dtype;
     if (!(w == 7 || w == 6 || w == 10) || args.op != 1 || cp.mc_buf == nullptr) return cudaErrorInvalidValue;
+  }
+  if (args.oneshot_nvls) {
+    const int w = args.dtype == 7 ? (args.wire_dtype == 10 || args.wire_dtype == 6 ? args.wire_dtype : 7) : args.dtype;
+    if (args.variant != kOneShot || !(w == 7 || w == 6 || w == 10) || args.op != 1 || cp.mc_buf == nullptr) return cudaErrorInvalidValue;
   }
   if (args.variant == kPipelined) {
     const int w = args.dtype == 7 ? (args.wire_dtype == 10 || args.wire_dtype == 6 ? args.wire_dtype : 7) : args.dtype;

@@ -37,6 +37,39 @@ __device__ __forceinline__ void copy_bytes_vec(const char* src, char* dst, int64
   }
 }
 
+// Root side of a multicast broadcast: local source -> multimem.st on the team's multicast mapping, i.e. ONE read of the
+// source and one NVLink egress stream that the switch replicates into every rank's symmetric buffer (a pull-style
+// broadcast makes the root serve N-1 readers).  `src` and `mc` are 16 B aligned; a tail shorter than 16 B is zero-padded
+// (the host pads the buffer window to 16 B).
+__device__ __forceinline__ void mc_copy_vec(const char* src, char* mc, int64_t n) {
+  const int64_t nv = n / 16;
+  if ((uintptr_t)src & 15) {  // unaligned source (a view into a larger tensor): assemble each vector from bytes
+    for (int64_t i = threadIdx.x; i < nv; i += kThreads) {
+      uint4 v;
+      char* b = reinterpret_cast<char*>(&v);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) b[k] = src[i * 16 + k];
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc + i * 16), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
+  } else
+  for (int64_t i0 = threadIdx.x; i0 < nv; i0 += 4 * kThreads) {
+    uint4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { int64_t i = i0 + (int64_t)j * kThreads; if (i < nv) v[j] = ld_stream(src + i * 16); }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int64_t i = i0 + (int64_t)j * kThreads;
+      if (i < nv) asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc + i * 16), "r"(v[j].x), "r"(v[j].y), "r"(v[j].z), "r"(v[j].w) : "memory");
+    }
+  }
+  if ((n & 15) && threadIdx.x == 0) {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    char* b = reinterpret_cast<char*>(&v);
+    for (int64_t i = nv * 16; i < n; ++i) b[i - nv * 16] = src[i];
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc + nv * 16), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  }
+}
+
 // Processes the part of [offset, offset+bytes) of a symmetric buffer that
 // falls into chunks owned by this CTA (chunk c -> CTA c % grid).
 template <typename F>
@@ -59,6 +92,13 @@ exchange_kernel(const __grid_constant__ CommParams cp, const __grid_constant__ E
   char* mybuf = reinterpret_cast<char*>(cp.buf[cp.rank]);
   for (int s = 0; s < a.nsend; ++s) {
     const CopyDesc d = a.sends[s];
+    if (d.pad == kSendMulticast && cp.mc_buf) {
+      char* mc = reinterpret_cast<char*>(cp.mc_buf);
+      for_my_chunks(d.offset, d.bytes, cta, grid, [&](int64_t lo, int64_t hi) {
+        mc_copy_vec(reinterpret_cast<const char*>(d.src) + (lo - d.offset), mc + lo, hi - lo);
+      });
+      continue;
+    }
     for_my_chunks(d.offset, d.bytes, cta, grid, [&](int64_t lo, int64_t hi) {
       copy_bytes_vec(reinterpret_cast<const char*>(d.src) + (lo - d.offset), mybuf + lo, hi - lo);
     });
@@ -181,7 +221,10 @@ exchange_tma_kernel(const __grid_constant__ CommParams cp, const __grid_constant
   for (int s = 0; s < a.nsend; ++s) {
     const CopyDesc d = a.sends[s];
     const char* src = reinterpret_cast<const char*>(d.src);
-    if (((((uintptr_t)src) | (uintptr_t)d.offset) & 15) == 0) {
+    if (d.pad == kSendMulticast && cp.mc_buf) {
+      char* mc = reinterpret_cast<char*>(cp.mc_buf);
+      for_my_chunks(d.offset, d.bytes, cta, grid, [&](int64_t lo, int64_t hi) { mc_copy_vec(src + (lo - d.offset), mc + lo, hi - lo); });
+    } else if (((((uintptr_t)src) | (uintptr_t)d.offset) & 15) == 0) {
       if (threadIdx.x == 0)
         tma_copy_my_chunks(ring, d.offset, d.bytes, cta, grid, [&](int64_t lo) { return src + (lo - d.offset); },
                            [&](int64_t lo) { return mybuf + lo; });

@@ -150,11 +150,18 @@ struct DescCursor {
   int n;
   int i;
   int64_t lo, hi, total;
+  // the current descriptor, held in registers: the table is read again only when the cursor crosses a tensor boundary
+  // (ncu of the round-1 kernel: the per-vector descriptor reload + 64-bit compares were ~40 % of the stall samples)
+  const char* in;
+  char* out;
+  int64_t count;
   __device__ __forceinline__ void init(const TensorDesc* descs, int ndesc, int64_t total_bytes) {
-    d = descs; n = ndesc; i = -1; lo = 0; hi = 0; total = total_bytes;
+    d = descs; n = ndesc; i = -1; lo = 0; hi = 0; total = total_bytes; in = nullptr; out = nullptr; count = 0;
   }
   __device__ __forceinline__ int64_t end_of(int k) const { return k + 1 < n ? d[k + 1].offset : total; }
+  __device__ __forceinline__ void load() { in = reinterpret_cast<const char*>(d[i].in); out = reinterpret_cast<char*>(d[i].out); count = d[i].count; }
   __device__ __forceinline__ void seek(int64_t o) {
+    if (i >= 0 && o >= lo && o < hi) return;
     if (i < 0 || o < lo) {
       int a = 0, b = n - 1;
       while (a < b) {
@@ -165,8 +172,40 @@ struct DescCursor {
     } else {
       while (o >= hi && i + 1 < n) { ++i; lo = hi; hi = end_of(i); }
     }
+    load();
   }
 };
+
+// N consecutive elements, caller guarantees a 16 B aligned address and N elements in range.
+template <typename T, int N, typename A> __device__ __forceinline__ void load_elems_fast(const T* p, A* a) {
+  constexpr int kBytes = N * (int)sizeof(T);
+  if constexpr (kBytes >= 16) {
+#pragma unroll
+    for (int k = 0; k < kBytes / 16; ++k) {
+      uint4 v = ld_stream(reinterpret_cast<const char*>(p) + 16 * k);
+      const T* q = reinterpret_cast<const T*>(&v);
+#pragma unroll
+      for (int i = 0; i < 16 / (int)sizeof(T); ++i) a[k * (16 / (int)sizeof(T)) + i] = (A)Traits<T>::to_acc(q[i]);
+    }
+  } else {
+    load_elems<T, N, A>(p, N, a);
+  }
+}
+template <typename T, int N, typename A> __device__ __forceinline__ void store_elems_fast(T* p, const A* a) {
+  constexpr int kBytes = N * (int)sizeof(T);
+  if constexpr (kBytes >= 16) {
+#pragma unroll
+    for (int k = 0; k < kBytes / 16; ++k) {
+      uint4 v;
+      T* q = reinterpret_cast<T*>(&v);
+#pragma unroll
+      for (int i = 0; i < 16 / (int)sizeof(T); ++i) q[i] = Traits<T>::from_acc((typename Traits<T>::Acc)a[k * (16 / (int)sizeof(T)) + i]);
+      st_stream(reinterpret_cast<char*>(p) + 16 * k, v);
+    }
+  } else {
+    store_elems<T, N, A>(p, N, a);
+  }
+}
 
 // ---------------------------------------------------------------------------
 // Cross-GPU barrier between CTA `cta` of every rank.  Flags hold monotonically
@@ -198,7 +237,9 @@ __device__ __forceinline__ bool peer_barrier(const CommParams& cp, uint32_t& epo
     (void)ld_acquire_sys(mine);  // acquire + L1 invalidate once, after the relaxed spin
   }
   __syncthreads();
-  return s_abort == 0;
+  const int aborted = s_abort;
+  __syncthreads();  // every thread has read the verdict before thread 0 of the next barrier may reset it
+  return aborted == 0;
 }
 
 }  // namespace kern

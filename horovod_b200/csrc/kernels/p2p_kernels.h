@@ -81,6 +81,7 @@ struct AllreduceArgs {
   // reducescatter: outputs use their own table (offsets relative to the fused buffer)
   const TensorDesc* out_descs;  // nullptr => same as descs
   int nout;
+  int oneshot_nvls;             // kOneShot only: reduce with multimem.ld_reduce on the multicast mapping instead of N peer loads
   // kPipelined only: the symmetric buffer is a ring of `pipe_slots` chunks of `pipe_chunk_bytes`; `pipe_base` is the
   // team-wide running chunk counter at the start of this launch (identical on all ranks), `pipe_use_nvls` selects the
   // in-switch reduction
@@ -120,8 +121,9 @@ struct CopyDesc {
   int64_t offset;    // byte offset in the (sender's) symmetric buffer
   int64_t bytes;
   int peer;          // recv: which rank's buffer to pull from
-  int pad;
+  int pad;           // send: kSendMulticast = store through the multicast mapping (lands in EVERY rank's buffer at `offset`)
 };
+constexpr int kSendMulticast = 1;  // requires a 16 B aligned offset and a 16 B-padded window
 struct ExchangeArgs {
   const CopyDesc* sends; int nsend;
   const CopyDesc* recvs; int nrecv;

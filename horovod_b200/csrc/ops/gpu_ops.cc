@@ -202,7 +202,7 @@ std::shared_ptr<SymmTeam> GpuOps::EnsureTeam(ProcessSet& ps, int device) {
 
 namespace {
 Status RunExchange(SymmTeam& team, GpuContext& ctx, int device, cudaStream_t s, std::vector<kern::CopyDesc>& sends,
-                   std::vector<kern::CopyDesc>& recvs, int max_ctas);
+                   std::vector<kern::CopyDesc>& recvs, int max_ctas, int64_t grid_bytes);
 }
 
 bool GpuOps::EnsureHierarchy(ProcessSet& ps, int device) {
@@ -315,7 +315,7 @@ Status GpuOps::HierarchicalAllreduce(ProcessSet& ps, Entries& es, const Response
       int p = (li + k) % L;
       recvs.push_back({nullptr, F + p * B + w0, 0, b, p, 0});
     }
-    st = RunExchange(team, ctx, device, s, sends, recvs, env_.params->comm_ctas);
+    st = RunExchange(team, ctx, device, s, sends, recvs, env_.params->comm_ctas, b);
     if (!st.ok()) return st;
   }
   HVD_CUDA(kern::LaunchPackUnpack(F, dtab, (int)descs.size(), total, (int)r.dtype, (int)r.dtype, r.postscale, 1, 148, s));
@@ -544,8 +544,10 @@ Status GpuOps::StagedOnHost(ProcessSet& ps, Entries& es, const Response& r, int 
 }
 
 // ---------------------------------------------------------------------------
-// reducescatter: pack per-destination block windows, every rank reduces only
-// its own block straight into its output (one-shot restricted to a range).
+// reducescatter: the fused buffer is laid out destination-rank major — region q holds block q of EVERY tensor of the
+// (fused) response — so each rank reduces one contiguous range straight into its output tensors: one launch per fused
+// response (one-shot P2P loads, or multimem.ld_reduce in the switch).  The reference packs a rank-interleaved fusion
+// buffer, calls ncclReduceScatter and unpacks (gpu_operations.cc:655-928, nccl_operations.cc:1221-1346).
 
 Status GpuOps::Reducescatter(ProcessSet& ps, Entries& es, const Response& r, int device, SharedEvent** done) {
   const int me = ps.set_rank(), n = ps.set_size();
@@ -554,78 +556,111 @@ Status GpuOps::Reducescatter(ProcessSet& ps, Entries& es, const Response& r, int
   cudaStream_t s = ctx.Stream(device);
   WaitReady(es, s);
   const int64_t esz = (int64_t)DataTypeSize(r.dtype);
-  for (auto& e : es) {
+  struct Item { TensorTableEntry* e; std::vector<int64_t> cnt, boff; };  // per-destination block: elements, element offset
+  std::vector<Item> items(es.size());
+  for (size_t ti = 0; ti < es.size(); ++ti) {
+    auto& e = es[ti];
     if (!e) return Status::PreconditionError("Reducescatter is not supported with Join at this time.");
     const int64_t dim0 = e->shape.dim(0);
     int64_t row = 1;
     for (int d = 1; d < e->shape.ndim(); ++d) row *= e->shape.dim(d);
     std::vector<int64_t> rows;
     ReducescatterRows(dim0, n, &rows);
-    std::vector<int64_t> boff(n + 1, 0);
-    for (int i = 0; i < n; ++i) boff[i + 1] = boff[i] + rows[i] * row;  // in elements
+    Item& it = items[ti];
+    it.e = e.get(); it.cnt.assign(n, 0); it.boff.assign(n + 1, 0);
+    for (int i = 0; i < n; ++i) { it.cnt[i] = rows[i] * row; it.boff[i + 1] = it.boff[i] + it.cnt[i]; }
     if (!e->output) {
       std::vector<int64_t> oshape = e->shape.dims();
       oshape[0] = rows[me];
       e->output = e->alloc_output ? e->alloc_output(oshape) : nullptr;
-      if (!e->output && rows[me] * row > 0) return Status::UnknownError("reducescatter: output allocation failed");
-    }
-    if (n == 1) {
-      const double sc = r.prescale * r.postscale;
-      if (e->input != e->output || sc != 1.0) HVD_CUDA(kern::LaunchScale(e->input, e->output, dim0 * row, (int)r.dtype, sc, s));
-      continue;
-    }
-    std::shared_ptr<SymmTeam> team = (env_.backend == "cpu") ? nullptr : EnsureTeam(ps, device);
-    if (!team) {
-      // host staged
-      std::vector<char> host((size_t)(dim0 * row * esz)), out((size_t)(rows[me] * row * esz));
-      HVD_CUDA(cudaMemcpyAsync(host.data(), e->input, host.size(), cudaMemcpyDeviceToHost, s));
-      HVD_CUDA(cudaStreamSynchronize(s));
-      cpu::ScaleBuffer(host.data(), dim0 * row, r.dtype, r.prescale);
-      std::vector<int64_t> counts(n);
-      for (int i = 0; i < n; ++i) counts[i] = rows[i] * row;
-      cpu::Reducescatter(ps.transport.get(), host.data(), counts, out.data(), r.dtype, r.reduce_op);
-      cpu::ScaleBuffer(out.data(), counts[me], r.dtype, r.postscale);
-      HVD_CUDA(cudaMemcpyAsync(e->output, out.data(), out.size(), cudaMemcpyHostToDevice, s));
-      HVD_CUDA(cudaStreamSynchronize(s));
-      continue;
-    }
-    int64_t maxblock = 0;
-    for (int i = 0; i < n; ++i) maxblock = std::max(maxblock, rows[i] * row * esz);
-    const int64_t cap = (int64_t)team->buffer_bytes();
-    int64_t win = std::min<int64_t>(Align128(maxblock), cap / n / 128 * 128);  // window bytes per destination block
-    if (win <= 0) continue;
-    for (int64_t w0 = 0; w0 < maxblock; w0 += win) {
-      std::vector<kern::TensorDesc> in_descs(n);
-      for (int q = 0; q < n; ++q) {
-        int64_t bbytes = rows[q] * row * esz;
-        int64_t cnt = std::max<int64_t>(0, std::min(win, bbytes - w0)) / esz;
-        in_descs[q].in = (const char*)e->input + boff[q] * esz + w0;
-        in_descs[q].out = nullptr;
-        in_descs[q].offset = q * win;
-        in_descs[q].count = cnt;
-      }
-      kern::TensorDesc od;
-      int64_t mybytes = rows[me] * row * esz;
-      od.in = nullptr; od.out = (char*)e->output + w0; od.offset = me * win;
-      od.count = std::max<int64_t>(0, std::min(win, mybytes - w0)) / esz;
-      kern::AllreduceArgs a {};
-      a.ndesc = n;
-      a.total_bytes = (int64_t)n * win;
-      a.reduce_lo = me * win; a.reduce_hi = me * win + Align128(od.count * esz);
-      a.prescale = r.prescale; a.postscale = r.postscale;
-      a.op = (int)r.reduce_op; a.dtype = (int)r.dtype; a.wire_dtype = (int)r.dtype;
-      a.variant = kern::kOneShot;
-      a.ctas = (int)std::max<int64_t>(1, std::min<int64_t>(env_.params->comm_ctas, (a.total_bytes + 16383) / 16384));
-      std::vector<kern::TensorDesc> table(in_descs);
-      table.push_back(od);
-      const auto* dt = (const kern::TensorDesc*)ctx.Stage(device, table.data(), table.size() * sizeof(kern::TensorDesc), s);
-      if (!dt) return Status::UnknownError("descriptor table too large");
-      a.descs = dt; a.out_descs = dt + n; a.nout = 1;
-      kern::CommParams cp = team->Params(team->NextSlot());
-      cudaError_t ce = kern::LaunchAllreduce(cp, a, s);
-      if (ce != cudaSuccess) return Status::UnknownError(std::string("reducescatter kernel launch failed: ") + cudaGetErrorString(ce));
+      if (!e->output && it.cnt[me] > 0) return Status::UnknownError("reducescatter: output allocation failed");
     }
   }
+  if (n == 1) {
+    const double sc = r.prescale * r.postscale;
+    for (auto& it : items)
+      if (it.e->input != it.e->output || sc != 1.0) HVD_CUDA(kern::LaunchScale(it.e->input, it.e->output, it.boff[n], (int)r.dtype, sc, s));
+    return FinishEvent(device, s, es.size(), done);
+  }
+  std::shared_ptr<SymmTeam> team = (env_.backend == "cpu") ? nullptr : EnsureTeam(ps, device);
+  if (!team) {
+    for (auto& it : items) {
+      std::vector<char> host((size_t)(it.boff[n] * esz)), out((size_t)(it.cnt[me] * esz));
+      HVD_CUDA(cudaMemcpyAsync(host.data(), it.e->input, host.size(), cudaMemcpyDeviceToHost, s));
+      HVD_CUDA(cudaStreamSynchronize(s));
+      cpu::ScaleBuffer(host.data(), it.boff[n], r.dtype, r.prescale);
+      cpu::Reducescatter(ps.transport.get(), host.data(), it.cnt, out.data(), r.dtype, r.reduce_op);
+      cpu::ScaleBuffer(out.data(), it.cnt[me], r.dtype, r.postscale);
+      HVD_CUDA(cudaMemcpyAsync(it.e->output, out.data(), out.size(), cudaMemcpyHostToDevice, s));
+      HVD_CUDA(cudaStreamSynchronize(s));
+    }
+    return FinishEvent(device, s, es.size(), done);
+  }
+  const int64_t cap = (int64_t)team->buffer_bytes();
+  const int64_t region_cap = cap / n / 128 * 128;  // bytes available to one destination region
+  const bool sum_like = r.reduce_op == ReduceOp::SUM || r.reduce_op == ReduceOp::AVERAGE;
+  const bool float_wire = r.dtype == DataType::FLOAT32 || r.dtype == DataType::FLOAT16 || r.dtype == DataType::BFLOAT16;
+  // one launch over pieces {tensor, element window [w0, w0 + len) inside every destination block}
+  struct Piece { Item* it; int64_t w0, len; };
+  std::vector<Piece> seg;
+  std::vector<int64_t> used(n, 0);  // bytes used in region q by the current segment
+  auto flush = [&]() -> Status {
+    if (seg.empty()) return Status::OK();
+    const int64_t W = Align128(*std::max_element(used.begin(), used.end()));
+    std::vector<kern::TensorDesc> table;
+    table.reserve(seg.size() * (n + 1));
+    for (int q = 0; q < n; ++q) {
+      int64_t off = (int64_t)q * W;
+      for (auto& pc : seg) {
+        const int64_t c = std::max<int64_t>(0, std::min(pc.len, pc.it->cnt[q] - pc.w0));
+        kern::TensorDesc d;
+        d.in = (const char*)pc.it->e->input + (pc.it->boff[q] + pc.w0) * esz; d.out = nullptr; d.offset = off; d.count = c;
+        table.push_back(d);
+        off += Align128(std::max<int64_t>(0, std::min(pc.len, pc.it->cnt[q] - pc.w0)) * esz);
+      }
+    }
+    const int nin = (int)table.size();
+    int64_t off = (int64_t)me * W;
+    for (auto& pc : seg) {
+      const int64_t c = std::max<int64_t>(0, std::min(pc.len, pc.it->cnt[me] - pc.w0));
+      kern::TensorDesc d;
+      d.in = nullptr; d.out = (char*)pc.it->e->output + pc.w0 * esz; d.offset = off; d.count = c;
+      table.push_back(d);
+      off += Align128(c * esz);
+    }
+    kern::AllreduceArgs a {};
+    a.ndesc = nin;
+    a.total_bytes = (int64_t)n * W;
+    a.reduce_lo = (int64_t)me * W; a.reduce_hi = off;
+    a.prescale = r.prescale; a.postscale = r.postscale;
+    a.op = (int)r.reduce_op; a.dtype = (int)r.dtype; a.wire_dtype = (int)r.dtype;
+    a.variant = kern::kOneShot;
+    a.oneshot_nvls = (team->has_multicast() && sum_like && float_wire && n >= 4 && env_.variant != "oneshot" && env_.variant != "twoshot" &&
+                      a.total_bytes >= env_.params->nvls_min_bytes) ? 1 : 0;
+    a.ctas = (int)std::max<int64_t>(1, std::min<int64_t>(env_.params->comm_ctas, (a.total_bytes + 16383) / 16384));
+    const auto* dt = (const kern::TensorDesc*)ctx.Stage(device, table.data(), table.size() * sizeof(kern::TensorDesc), s);
+    if (!dt) return Status::UnknownError("descriptor table too large");
+    a.descs = dt; a.out_descs = dt + nin; a.nout = (int)seg.size();
+    kern::CommParams cp = team->Params(team->NextSlot());
+    cudaError_t ce = kern::LaunchAllreduce(cp, a, s);
+    if (ce != cudaSuccess) return Status::UnknownError(std::string("reducescatter kernel launch failed: ") + cudaGetErrorString(ce));
+    seg.clear(); used.assign(n, 0);
+    return Status::OK();
+  };
+  for (auto& it : items) {
+    const int64_t maxcnt = *std::max_element(it.cnt.begin(), it.cnt.end());
+    int64_t w0 = 0;
+    while (w0 < maxcnt) {
+      int64_t room = region_cap - *std::max_element(used.begin(), used.end());
+      if (room < 128) { Status st = flush(); if (!st.ok()) return st; room = region_cap; }
+      const int64_t len = std::min(maxcnt - w0, room / esz);
+      seg.push_back({&it, w0, len});
+      for (int q = 0; q < n; ++q) used[q] += Align128(std::max<int64_t>(0, std::min(len, it.cnt[q] - w0)) * esz);
+      w0 += len;
+    }
+  }
+  Status st = flush();
+  if (!st.ok()) return st;
   ctx.TempFreeAll(device, s);
   return FinishEvent(device, s, es.size(), done);
 }
@@ -634,27 +669,31 @@ Status GpuOps::Reducescatter(ProcessSet& ps, Entries& es, const Response& r, int
 // allgather / broadcast / alltoall through the exchange kernel
 
 namespace {
+// `grid_bytes` sizes the grid and MUST be the same number on every rank (CTA b rendezvouses with CTA b of its peers): a
+// 4-byte broadcast is one CTA and one flag per peer, not comm_ctas of them.
 Status RunExchange(SymmTeam& team, GpuContext& ctx, int device, cudaStream_t s, std::vector<kern::CopyDesc>& sends,
-                   std::vector<kern::CopyDesc>& recvs, int max_ctas) {
+                   std::vector<kern::CopyDesc>& recvs, int max_ctas, int64_t grid_bytes) {
   std::vector<kern::CopyDesc> table(sends);
   table.insert(table.end(), recvs.begin(), recvs.end());
-  int64_t bytes = 0;
-  for (auto& d : table) bytes += d.bytes;
   kern::ExchangeArgs a {};
   const kern::CopyDesc* dt = table.empty() ? nullptr
       : (const kern::CopyDesc*)ctx.Stage(device, table.data(), table.size() * sizeof(kern::CopyDesc), s);
   if (!table.empty() && !dt) return Status::UnknownError("descriptor table too large");
   a.sends = dt; a.nsend = (int)sends.size();
   a.recvs = dt ? dt + sends.size() : nullptr; a.nrecv = (int)recvs.size();
-  a.ctas = max_ctas;
-  (void)bytes;
+  a.ctas = (int)std::max<int64_t>(1, std::min<int64_t>(max_ctas, (grid_bytes + 32767) / 32768));
   kern::CommParams cp = team.Params(team.NextSlot());
   cudaError_t ce = kern::LaunchExchange(cp, a, s);
   if (ce != cudaSuccess) return Status::UnknownError(std::string("exchange kernel launch failed: ") + cudaGetErrorString(ce));
   return Status::OK();
 }
+int64_t Align16(int64_t b) { return (b + 15) / 16 * 16; }
 }  // namespace
 
+// A fused allgather response (several tensors, per-rank first dims in r.tensor_sizes) is ONE exchange launch: every rank
+// packs its blocks of all tensors back to back into its symmetric buffer and pulls every peer's blocks straight into the
+// output tensors.  The reference packs into a fusion buffer, calls ncclAllGather and unpacks (gpu_operations.cc:441-632,
+// nccl_operations.cc:906-1133).
 Status GpuOps::Allgather(ProcessSet& ps, Entries& es, const Response& r, int device, SharedEvent** done) {
   const int me = ps.set_rank(), n = ps.set_size();
   HVD_CUDA(cudaSetDevice(device));
@@ -662,52 +701,91 @@ Status GpuOps::Allgather(ProcessSet& ps, Entries& es, const Response& r, int dev
   cudaStream_t s = ctx.Stream(device);
   WaitReady(es, s);
   const int64_t esz = (int64_t)DataTypeSize(r.dtype);
+  struct Item { TensorTableEntry* e; std::vector<int64_t> bytes, displ; };
+  std::vector<Item> items(es.size());
   for (size_t ti = 0; ti < es.size(); ++ti) {
     auto& e = es[ti];
     if (!e) return Status::PreconditionError("Allgather is not supported with Join at this time.");
     int64_t row = 1;
     for (int d = 1; d < e->shape.ndim(); ++d) row *= e->shape.dim(d);
-    std::vector<int64_t> bytes(n), displ(n + 1, 0);
+    Item& it = items[ti];
+    it.e = e.get(); it.bytes.assign(n, 0); it.displ.assign(n + 1, 0);
     int64_t total_rows = 0;
     for (int p = 0; p < n; ++p) {
       int64_t d0 = r.tensor_sizes[ti * n + p];
-      bytes[p] = d0 * row * esz;
-      displ[p + 1] = displ[p] + bytes[p];
+      it.bytes[p] = d0 * row * esz;
+      it.displ[p + 1] = it.displ[p] + it.bytes[p];
       total_rows += d0;
     }
     std::vector<int64_t> oshape = e->shape.dims();
     oshape[0] = total_rows;
     e->output = e->alloc_output ? e->alloc_output(oshape) : e->output;
-    if (!e->output && displ[n] > 0) return Status::UnknownError("allgather: output allocation failed");
-    if (n == 1) { if (bytes[0]) HVD_CUDA(cudaMemcpyAsync(e->output, e->input, (size_t)bytes[0], cudaMemcpyDeviceToDevice, s)); continue; }
-    std::shared_ptr<SymmTeam> team = (env_.backend == "cpu") ? nullptr : EnsureTeam(ps, device);
-    if (!team) {
-      std::vector<char> host((size_t)displ[n]);
-      if (bytes[me]) HVD_CUDA(cudaMemcpyAsync(host.data() + displ[me], e->input, (size_t)bytes[me], cudaMemcpyDeviceToHost, s));
+    if (!e->output && it.displ[n] > 0) return Status::UnknownError("allgather: output allocation failed");
+  }
+  if (n == 1) {
+    for (auto& it : items) if (it.bytes[0]) HVD_CUDA(cudaMemcpyAsync(it.e->output, it.e->input, (size_t)it.bytes[0], cudaMemcpyDeviceToDevice, s));
+    return FinishEvent(device, s, es.size(), done);
+  }
+  std::shared_ptr<SymmTeam> team = (env_.backend == "cpu") ? nullptr : EnsureTeam(ps, device);
+  if (!team) {
+    for (auto& it : items) {
+      std::vector<char> host((size_t)it.displ[n]);
+      if (it.bytes[me]) HVD_CUDA(cudaMemcpyAsync(host.data() + it.displ[me], it.e->input, (size_t)it.bytes[me], cudaMemcpyDeviceToHost, s));
       HVD_CUDA(cudaStreamSynchronize(s));
-      cpu::Allgatherv(ps.transport.get(), host.data() + displ[me], host.data(), bytes);
-      if (displ[n]) HVD_CUDA(cudaMemcpyAsync(e->output, host.data(), (size_t)displ[n], cudaMemcpyHostToDevice, s));
+      cpu::Allgatherv(ps.transport.get(), host.data() + it.displ[me], host.data(), it.bytes);
+      if (it.displ[n]) HVD_CUDA(cudaMemcpyAsync(it.e->output, host.data(), (size_t)it.displ[n], cudaMemcpyHostToDevice, s));
       HVD_CUDA(cudaStreamSynchronize(s));
+    }
+    return FinishEvent(device, s, es.size(), done);
+  }
+  const int64_t cap = (int64_t)team->buffer_bytes() / 16 * 16;
+  // segment = tensors whose blocks fit together in every rank's symmetric buffer
+  std::vector<kern::CopyDesc> sends, recvs;
+  std::vector<int64_t> used(n, 0);
+  auto flush = [&]() -> Status {
+    if (sends.empty() && recvs.empty()) return Status::OK();
+    Status st = RunExchange(*team, ctx, device, s, sends, recvs, env_.params->comm_ctas, *std::max_element(used.begin(), used.end()));
+    sends.clear(); recvs.clear(); used.assign(n, 0);
+    return st;
+  };
+  for (auto& it : items) {
+    const int64_t maxb = *std::max_element(it.bytes.begin(), it.bytes.end());
+    if (maxb > cap) {
+      // one tensor larger than the buffer: windows of `cap` bytes, each its own launch
+      Status st = flush();
+      if (!st.ok()) return st;
+      for (int64_t w0 = 0; w0 < maxb; w0 += cap) {
+        int64_t mine = std::max<int64_t>(0, std::min(cap, it.bytes[me] - w0));
+        if (mine) sends.push_back({(const char*)it.e->input + w0, nullptr, 0, mine, me, 0});
+        for (int k = 0; k < n; ++k) {
+          int p = (me + k) % n;
+          int64_t b = std::max<int64_t>(0, std::min(cap, it.bytes[p] - w0));
+          if (b) recvs.push_back({nullptr, (char*)it.e->output + it.displ[p] + w0, 0, b, p, 0});
+          used[p] = b;
+        }
+        st = flush();
+        if (!st.ok()) return st;
+      }
       continue;
     }
-    const int64_t cap = (int64_t)team->buffer_bytes() / 16 * 16;
-    int64_t maxb = *std::max_element(bytes.begin(), bytes.end());
-    for (int64_t w0 = 0; w0 < maxb; w0 += cap) {
-      std::vector<kern::CopyDesc> sends, recvs;
-      int64_t mine = std::max<int64_t>(0, std::min(cap, bytes[me] - w0));
-      if (mine) sends.push_back({(const char*)e->input + w0, nullptr, 0, mine, me, 0});
-      for (int k = 0; k < n; ++k) {
-        int p = (me + k) % n;
-        int64_t b = std::max<int64_t>(0, std::min(cap, bytes[p] - w0));
-        if (b) recvs.push_back({nullptr, (char*)e->output + displ[p] + w0, 0, b, p, 0});
-      }
-      Status st = RunExchange(*team, ctx, device, s, sends, recvs, env_.params->comm_ctas);
-      if (!st.ok()) return st;
+    bool fits = true;
+    for (int p = 0; p < n; ++p) if (used[p] + Align16(it.bytes[p]) > cap) fits = false;
+    if (!fits) { Status st = flush(); if (!st.ok()) return st; }
+    if (it.bytes[me]) sends.push_back({it.e->input, nullptr, used[me], it.bytes[me], me, 0});
+    for (int k = 0; k < n; ++k) {
+      int p = (me + k) % n;  // start at my own block and rotate: at any instant the N ranks pull from N different peers
+      if (it.bytes[p]) recvs.push_back({nullptr, (char*)it.e->output + it.displ[p], used[p], it.bytes[p], p, 0});
     }
+    for (int p = 0; p < n; ++p) used[p] += Align16(it.bytes[p]);
   }
+  Status st = flush();
+  if (!st.ok()) return st;
   return FinishEvent(device, s, es.size(), done);
 }
 
+// Broadcast responses of one root are fused by the controller; a fused response is ONE launch.  With NVLS the root
+// stores through the multicast mapping (multimem.st: one source read, one egress stream, the switch replicates) and
+// every rank copies out of its OWN buffer; without it the peers pull from the root's buffer.
 Status GpuOps::Broadcast(ProcessSet& ps, Entries& es, const Response& r, int device, SharedEvent** done) {
   const int me = ps.set_rank(), n = ps.set_size();
   HVD_CUDA(cudaSetDevice(device));
@@ -715,33 +793,52 @@ Status GpuOps::Broadcast(ProcessSet& ps, Entries& es, const Response& r, int dev
   cudaStream_t s = ctx.Stream(device);
   WaitReady(es, s);
   const int root = r.root_rank;
-  for (auto& e : es) {
-    if (!e) return Status::PreconditionError("Broadcast is not supported with Join at this time.");
-    const int64_t bytes = (int64_t)e->bytes();
-    if (n == 1 || bytes == 0) {
-      if (e->output && e->output != e->input && bytes) HVD_CUDA(cudaMemcpyAsync(e->output, e->input, (size_t)bytes, cudaMemcpyDeviceToDevice, s));
-      continue;
-    }
-    std::shared_ptr<SymmTeam> team = (env_.backend == "cpu") ? nullptr : EnsureTeam(ps, device);
-    if (!team) {
+  for (auto& e : es) if (!e) return Status::PreconditionError("Broadcast is not supported with Join at this time.");
+  std::shared_ptr<SymmTeam> team = (n == 1 || env_.backend == "cpu") ? nullptr : EnsureTeam(ps, device);
+  if (!team) {
+    for (auto& e : es) {
+      const int64_t bytes = (int64_t)e->bytes();
+      if (n == 1 || bytes == 0) {
+        if (e->output && e->output != e->input && bytes) HVD_CUDA(cudaMemcpyAsync(e->output, e->input, (size_t)bytes, cudaMemcpyDeviceToDevice, s));
+        continue;
+      }
       std::vector<char> host((size_t)bytes);
       if (me == root) { HVD_CUDA(cudaMemcpyAsync(host.data(), e->input, (size_t)bytes, cudaMemcpyDeviceToHost, s)); }
       HVD_CUDA(cudaStreamSynchronize(s));
       cpu::Broadcast(ps.transport.get(), host.data(), bytes, root);
       if (me != root || e->output != e->input) HVD_CUDA(cudaMemcpyAsync(e->output, host.data(), (size_t)bytes, cudaMemcpyHostToDevice, s));
       HVD_CUDA(cudaStreamSynchronize(s));
-      continue;
     }
-    const int64_t cap = (int64_t)team->buffer_bytes() / 16 * 16;
-    for (int64_t w0 = 0; w0 < bytes; w0 += cap) {
-      int64_t b = std::min(cap, bytes - w0);
-      std::vector<kern::CopyDesc> sends, recvs;
-      if (me == root) sends.push_back({(const char*)e->input + w0, nullptr, 0, b, me, 0});
-      if (me != root || (e->output && e->output != e->input)) recvs.push_back({nullptr, (char*)e->output + w0, 0, b, root, 0});
-      Status st = RunExchange(*team, ctx, device, s, sends, recvs, env_.params->comm_ctas);
-      if (!st.ok()) return st;
+    return FinishEvent(device, s, es.size(), done);
+  }
+  static const bool mc_bcast = EnvBool("HVD_BROADCAST_MULTICAST", true);
+  const bool use_mc = mc_bcast && team->has_multicast() && n > 2;
+  const int64_t cap = (int64_t)team->buffer_bytes() / 16 * 16;
+  std::vector<kern::CopyDesc> sends, recvs;
+  int64_t used = 0;
+  auto flush = [&]() -> Status {
+    if (used == 0) return Status::OK();
+    Status st = RunExchange(*team, ctx, device, s, sends, recvs, env_.params->comm_ctas, used);
+    sends.clear(); recvs.clear(); used = 0;
+    return st;
+  };
+  auto add = [&](const char* in, char* out, int64_t b) {
+    if (me == root) sends.push_back({in, nullptr, used, b, me, use_mc ? kern::kSendMulticast : 0});
+    if (me != root || (out && out != in)) recvs.push_back({nullptr, out, used, b, use_mc ? me : root, 0});
+    used += Align16(b);
+  };
+  for (auto& e : es) {
+    const int64_t bytes = (int64_t)e->bytes();
+    if (bytes == 0) continue;
+    for (int64_t w0 = 0; w0 < bytes; ) {
+      if (cap - used < 16) { Status st = flush(); if (!st.ok()) return st; }
+      const int64_t b = std::min(cap - used, bytes - w0);
+      add((const char*)e->input + w0, e->output ? (char*)e->output + w0 : nullptr, b);
+      w0 += b;
     }
   }
+  Status st = flush();
+  if (!st.ok()) return st;
   return FinishEvent(device, s, es.size(), done);
 }
 
@@ -803,7 +900,7 @@ Status GpuOps::Alltoall(ProcessSet& ps, Entries& es, const Response& r, int devi
         int64_t b = std::max<int64_t>(0, std::min(win, rbytes[p] - w0));
         if (b) recvs.push_back({nullptr, (char*)e->output + rdisp[p] + w0, me * win, b, p, 0});
       }
-      Status st = RunExchange(*team, ctx, device, s, sends, recvs, env_.params->comm_ctas);
+      Status st = RunExchange(*team, ctx, device, s, sends, recvs, env_.params->comm_ctas, std::min<int64_t>(maxblock - w0, win) * n);
       if (!st.ok()) return st;
     }
   }

@@ -272,6 +272,53 @@ def _():
     assert outs[0].shape == (2, 3) and outs[1].shape == (1, 2)
 
 
+@check('fused_other_collectives')
+def _():
+    """Allgather / reducescatter / broadcast responses negotiated in one cycle are fused (one launch on GPUs): many small
+    async ops with ragged sizes, values checked, and fewer responses than tensors in the engine's metrics
+    (reference: controller.cc:915-918 reducescatter, :1003-1086 allgather fusion)."""
+    m0 = hvd.metrics()
+    K = 12
+    # allgather: tensor k has (rank + k) % 3 + 1 rows of k + 1 columns
+    ag_in = [torch.full([(rank + k) % 3 + 1, k + 1], float(rank * 100 + k), device=DEV) for k in range(K)]
+    hs = [hvd.allgather_async(t, name='fo.ag.%d' % k) for k, t in enumerate(ag_in)]
+    outs = [hvd.synchronize(h) for h in hs]
+    for k, g in enumerate(outs):
+        off = 0
+        for r in range(size):
+            n = (r + k) % 3 + 1
+            assert g.shape[1] == k + 1 and (g[off:off + n] == r * 100 + k).all(), (k, r, g)
+            off += n
+        assert g.shape[0] == off
+    # reducescatter: ragged first dims (not multiples of size)
+    rs_in = [rand([size * 2 + k % 3, k % 4 + 1], torch.float32, 900 + 17 * k + rank) for k in range(K)]
+    hs = [hvd.reducescatter_async(t, op=hvd.Sum, name='fo.rs.%d' % k) for k, t in enumerate(rs_in)]
+    outs = [hvd.synchronize(h) for h in hs]
+    for k, out in enumerate(outs):
+        rows = size * 2 + k % 3
+        total = torch.stack([rand([rows, k % 4 + 1], torch.float32, 900 + 17 * k + r).double() for r in range(size)]).sum(0)
+        counts = [rows // size + (1 if r < rows % size else 0) for r in range(size)]
+        off = sum(counts[:rank])
+        torch.testing.assert_close(out.double(), total[off:off + counts[rank]], rtol=1e-5, atol=1e-5)
+    # broadcast: two roots interleaved, mixed dtypes, odd byte counts
+    bc = []
+    for k in range(K):
+        dt = [torch.float32, torch.uint8, torch.int64][k % 3]
+        bc.append(torch.full([k * 3 + 1], rank + 1, dtype=dt, device=DEV))
+    hs = [hvd.broadcast_async_(t, root_rank=k % min(size, 2), name='fo.bc.%d' % k) for k, t in enumerate(bc)]
+    for h in hs:
+        hvd.synchronize(h)
+    for k, t in enumerate(bc):
+        assert (t == k % min(size, 2) + 1).all(), (k, t)
+    m1 = hvd.metrics()
+    for op in ('allgather', 'reducescatter', 'broadcast'):
+        tensors = m1[op]['tensors'] - m0.get(op, {}).get('tensors', 0)
+        responses = m1[op]['responses'] - m0.get(op, {}).get('responses', 0)
+        assert tensors == K, (op, tensors)
+        if os.environ.get('HOROVOD_FUSION_THRESHOLD', '') != '0':
+            assert responses < tensors, (op, responses, tensors)
+
+
 @check('autograd')
 def _():
     # allreduce: grad of sum-allreduce is sum-allreduce of ones
