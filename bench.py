@@ -38,6 +38,10 @@ def parse():
     p.add_argument('--bucket-wire-dtype', default=None, choices=['bf16', 'fp16'],
                    help='experimental: reduce the fp32 gradient buckets as bf16/fp16 (registered shadow buckets)')
     p.add_argument('--no-cuda-graph', action='store_true', help='eager forward/backward with gradient hooks instead of hvd.GraphedStep')
+    p.add_argument('--bucket-cap-mb', type=float, default=32, help='size of the zero-copy gradient buckets')
+    p.add_argument('--parity', action='store_true', help="the stock reference benchmark's configuration: fp32 (no TF32, no autocast), eager "
+                   'hook-driven step, unfused optimizer — what `--impl reference` would run, for a same-config comparison')
+    p.add_argument('--no-extras', action='store_true', help='skip extra.bert_large / extra.allreduce_busbw / extra.checks')
     p.add_argument('--sizes', default=None, help='allreduce sweep: comma separated byte sizes')
     p.add_argument('--dtype', default='fp32', help='allreduce sweep dtype: fp32|bf16|fp16')
     return p.parse_args()
@@ -185,34 +189,30 @@ def build_model(args, torch):
     return model, make_batch, step_fn, bs, seq, 'samples/sec'
 
 
-def train_bench(args):
-    import torch
-    import horovod_b200.torch as hvd
+def _time_train(args, model_name, steps, warmup, hvd, torch, sample_clocks):
+    """One training configuration: device-timed arm (inputs resident) and end-to-end arm (per-step pinned H2D input copy +
+    D2H loss read).  Returns a dict; frees the model before returning."""
     from horovod_b200.data import DevicePrefetcher
-
-    if args.op == 'adasum':
-        # the GPU Adasum kernels work inside the symmetric buffer: make it hold the largest single delta (GPT-2's 206 MB wte)
-        os.environ.setdefault('HVD_SYMM_BUFFER_BYTES', str(256 << 20))
-    hvd.init()
-    rank, size = hvd.rank(), hvd.size()
-    local_rank = hvd.local_rank()
-    torch.cuda.set_device(local_rank)
-    torch.backends.cudnn.benchmark = True
-    torch.backends.cuda.matmul.allow_tf32 = True
-    torch.backends.cudnn.allow_tf32 = True
-    model, make_batch, step_fn, bs, seq, unit = build_model(args, torch)
+    rank, size, local_rank = hvd.rank(), hvd.size(), hvd.local_rank()
+    margs = argparse.Namespace(**vars(args))
+    margs.model = model_name
+    if model_name != args.model:
+        margs.batch_size, margs.seq_len = None, None
+    model, make_batch, step_fn, bs, seq, unit = build_model(margs, torch)
     use_bf16 = not args.fp32
+    eager = args.no_cuda_graph or args.parity
     lr_scaler = size if args.op == 'average' else 1
-    if args.model == 'resnet50':
+    if model_name == 'resnet50':
         base_opt = torch.optim.SGD(model.parameters(), lr=0.01 * lr_scaler, momentum=0.9)
     else:
         base_opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01)
     op = hvd.Average if args.op == 'average' else hvd.Adasum
-    # graphed step: no backward/allreduce overlap to preserve, so fewer, larger buckets (fewer launches and host round trips)
+    kw = {}
+    if op == hvd.Average:
+        kw = {'bucket_cap_mb': args.bucket_cap_mb,
+              'bucket_wire_dtype': {'bf16': torch.bfloat16, 'fp16': torch.float16, None: None}[args.bucket_wire_dtype]}
     opt = hvd.DistributedOptimizer(base_opt, named_parameters=model.named_parameters(), op=op,
-                                   fused=not args.no_fused_optimizer, **({} if op != hvd.Average else
-                                                                         {'bucket_cap_mb': 32 if args.no_cuda_graph else 256,
-                                                                          'bucket_wire_dtype': {'bf16': torch.bfloat16, 'fp16': torch.float16, None: None}[args.bucket_wire_dtype]}))
+                                   fused=not (args.no_fused_optimizer or args.parity), **kw)
     hvd.broadcast_parameters(model.state_dict(), root_rank=0)
     hvd.broadcast_optimizer_state(opt, root_rank=0)
     model.train()
@@ -225,12 +225,12 @@ def train_bench(args):
         with torch.autocast('cuda', dtype=torch.bfloat16, enabled=use_bf16):
             return step_fn(batch)
 
-    # forward + backward replayed as one CUDA graph; step() then reduces the gradient buckets and applies the fused update
-    # (hvd.GraphedStep falls back to the eager hook-driven step if capture is impossible, e.g. for the Adasum optimizer)
-    graphed = hvd.GraphedStep(fwd, opt, dev_batch, enabled=not args.no_cuda_graph)
-
-    def one_step(batch):
-        return graphed(*batch)
+    # the whole step — forward, backward and (multi-GPU) the gradient buckets' allreduce kernels, overlapped with backward
+    # on a forked stream — is ONE CUDA graph; step() then applies the fused update.  Falls back to the eager hook-driven
+    # step if capture is impossible (e.g. the Adasum optimizer's per-parameter steps).
+    graphed = hvd.GraphedStep(fwd, opt, dev_batch, enabled=not eager)
+    comm_nodes = len(getattr(opt, '_buckets', [])) if graphed.comm_in_graph else 0
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
 
     def timed(nsteps, e2e):
         hvd.barrier()
@@ -241,7 +241,9 @@ def train_bench(args):
         last = None
         if e2e:
             # every step: host -> device copy of that step's inputs from pinned memory on the prefetcher's copy stream (the
-            # copy of step i+1 overlaps the compute of step i), then a device -> host read of the step's loss
+            # copy of step i+1 overlaps the compute of step i) and a device -> host copy of the step's loss into pinned
+            # memory; the host reads the loss of step i-1 while step i runs (a training loop logs, it does not stall on
+            # .item()), and the last loss before the clock stops
             class _Loader:
                 def __len__(self):
                     return nsteps
@@ -250,57 +252,236 @@ def train_bench(args):
                     for _ in range(nsteps):
                         yield host_batch
             pf = DevicePrefetcher(_Loader(), device=f'cuda:{local_rank}', depth=2)
+            copied = torch.cuda.Event()
+            pending = False
             for batch in pf:
-                last = one_step(batch).item()
+                if pending:
+                    copied.synchronize()
+                    last = float(loss_host[0])
+                loss = graphed(*batch)
+                loss_host.copy_(loss.detach().float().reshape(1), non_blocking=True)
+                copied.record()
+                pending = True
+            copied.synchronize()
+            last = float(loss_host[0])
             assert pf.h2d_bytes == h2d_bytes * nsteps
         else:
             for _ in range(nsteps):
-                last = one_step(dev_batch)
+                last = graphed(*dev_batch)
         e1.record()
         torch.cuda.synchronize()
         hvd.barrier()
         ms = e0.elapsed_time(e1)
         k1 = hvd.runtime_stats()['kernel_launches']
-        # max over ranks
         t = torch.tensor([ms], dtype=torch.float64)
-        ms = hvd.allreduce(t, op=hvd.Max, name='bench.ms').item()
-        return ms, k1 - k0, last
+        ms = hvd.allreduce(t, op=hvd.Max, name='bench.ms').item()  # max over ranks
+        return ms, (k1 - k0) + nsteps * comm_nodes, last
 
-    for _ in range(max(3, args.warmup)):
-        one_step(dev_batch)
+    for _ in range(max(3, warmup)):
+        graphed(*dev_batch)
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if (rank == 0 and sample_clocks) else None
     if sampler:
         sampler.start()
-    ms, launches, _ = timed(args.steps, e2e=False)
+    ms, launches, _ = timed(steps, e2e=False)
     clocks = sampler.stop() if sampler else None
-    # end-to-end arm: H2D of the inputs from pinned memory + D2H read of the loss inside the timed region
     for _ in range(2):
-        one_step(tuple(t.cuda(non_blocking=True) for t in host_batch)).item()
-    e2e_ms, _, last_loss = timed(args.steps, e2e=True)
+        graphed(*tuple(t.cuda(non_blocking=True) for t in host_batch))
+    e2e_ms, _, last_loss = timed(steps, e2e=True)
+
+    # every rank must hold bit-identical parameters after the run (each applied the same reduced gradients)
+    flat = torch.cat([p.detach().float().reshape(-1) for p in model.parameters()])
+    digest = torch.stack([flat.double().sum(), flat.double().abs().sum(), flat[::997].double().pow(2).sum()]).cpu()
+    dmin = hvd.allreduce(digest, op=hvd.Min, name='bench.digest.min.' + model_name)
+    dmax = hvd.allreduce(digest, op=hvd.Max, name='bench.digest.max.' + model_name)
+    params_identical = bool(torch.equal(dmin, dmax)) and bool(torch.isfinite(digest).all())
 
     global_batch = bs * size
-    value = global_batch * args.steps / (ms / 1e3)
-    e2e_value = global_batch * args.steps / (e2e_ms / 1e3)
+    out = {
+        'model': model_name, 'unit': unit, 'value': round(global_batch * steps / (ms / 1e3), 2), 'ms_per_step': round(ms / steps, 3),
+        'e2e_value': round(global_batch * steps / (e2e_ms / 1e3), 2), 'e2e_ms_per_step': round(e2e_ms / steps, 3),
+        'h2d_bytes_per_step': h2d_bytes, 'last_loss': last_loss, 'gpu_launches': int(launches), 'clocks': clocks,
+        'global_batch': global_batch, 'per_gpu_batch': bs, 'seq_len': seq, 'params_identical_across_ranks': params_identical,
+        'cuda_graph': bool(graphed.captured), 'cuda_graph_fallback': graphed.fallback_reason,
+        'allreduce_in_graph': bool(graphed.comm_in_graph), 'gradient_buckets': len(getattr(opt, '_buckets', [])),
+        'optimizer': 'SGD(momentum=0.9)' if model_name == 'resnet50' else 'AdamW',
+    }
+    del graphed, opt, base_opt, model, dev_batch, host_batch
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
+def _nccl_group(torch, hvd):
+    """torch.distributed NCCL process group next to the hvd runtime (the reference's data path IS ncclAllReduce:
+    ops/nccl_operations.cc:256): bootstrapped through the same c10d store hvd.init() used, never a second server."""
+    import torch.distributed as dist
+    if dist.is_initialized():
+        return dist
+    from horovod_b200.common.basics import _EmbeddedRendezvous
+    try:
+        if _EmbeddedRendezvous.stores:
+            store = dist.PrefixStore('bench_nccl', _EmbeddedRendezvous.stores[-1])
+            dist.init_process_group('nccl', store=store, rank=hvd.rank(), world_size=hvd.size(),
+                                    device_id=torch.device('cuda', hvd.local_rank()))
+        else:
+            return None
+    except Exception as e:  # noqa: BLE001
+        sys.stderr.write('bench: NCCL comparison arm unavailable: %s\n' % e)
+        return None
+    return dist
+
+
+def _busbw_extra(args, hvd, torch):
+    """allreduce bus bandwidth, ordinary cudaMalloc tensors, DEFAULT configuration of this library next to ncclAllReduce
+    (torch.distributed NCCL) in the same job; device-timed, max over ranks, values checked."""
+    size = hvd.size()
+    dist = _nccl_group(torch, hvd)
+    rows = []
+    for nbytes in (4 << 10, 256 << 10, 4 << 20, 64 << 20, 512 << 20):
+        n = nbytes // 4
+        x = torch.ones(n, device='cuda')
+        iters = max(4, min(50, int(2e9 // max(nbytes, 1 << 20))))
+        row = {'bytes': nbytes}
+        for arm in ('ours', 'nccl'):
+            if arm == 'nccl' and dist is None:
+                continue
+            call = (lambda: hvd.allreduce_(x, op=hvd.Sum, name='bw.%d' % nbytes)) if arm == 'ours' else (lambda: dist.all_reduce(x))
+            x.fill_(1.0)
+            call()
+            torch.cuda.synchronize()
+            ok = bool((x[:8] == size).all() and (x[-8:] == size).all())
+            for _ in range(2):
+                call()
+            hvd.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                call()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = hvd.allreduce(torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64), op=hvd.Max, name='bw.ms').item()
+            row[arm + '_us'] = round(ms * 1e3, 1)
+            row[arm + '_busbw_gbs'] = round(nbytes / (ms / 1e3) / 1e9 * 2 * (size - 1) / size, 1)
+            row[arm + '_correct'] = ok
+        rows.append(row)
+        del x
+    return {'dtype': 'fp32', 'tensors': 'plain cudaMalloc (unregistered), in place, blocking loop', 'rows': rows,
+            'roofline_gbs_per_direction': 900}
+
+
+def _checks_extra(hvd, torch):
+    """Closed-form allreduce on every kernel path of the data plane, in the bench process (multi-GPU correctness the
+    driver can see): small (one-shot), medium (two-shot / NVLS), large plain (software pipeline), registered zero-copy,
+    and a collective captured as a CUDA-graph node."""
+    size, rank = hvd.size(), hvd.rank()
+    exp_sum = float(sum(range(1, size + 1)))
+    res = {}
+
+    def run(name, tensor, fn):
+        tensor.fill_(float(rank + 1))
+        fn(tensor)
+        torch.cuda.synchronize()
+        res[name] = bool((tensor == exp_sum).all().item())
+
+    run('oneshot_4KiB', torch.empty(1024, device='cuda'), lambda t: hvd.allreduce_(t, op=hvd.Sum, name='chk.a'))
+    run('twoshot_or_nvls_8MiB', torch.empty(2 << 20, device='cuda'), lambda t: hvd.allreduce_(t, op=hvd.Sum, name='chk.b'))
+    run('pipelined_96MiB_plain', torch.empty(24 << 20, device='cuda'), lambda t: hvd.allreduce_(t, op=hvd.Sum, name='chk.c'))
+    run('bf16_16MiB', torch.empty(8 << 20, device='cuda', dtype=torch.bfloat16), lambda t: hvd.allreduce_(t, op=hvd.Sum, name='chk.d'))
+    if hvd.symm_available():
+        z = hvd.symm_empty(4 << 20, dtype=torch.float32)
+        run('zero_copy_16MiB_registered', z, lambda t: hvd.allreduce_(t, op=hvd.Sum, name='chk.e'))
+        g = torch.cuda.CUDAGraph()
+        z.fill_(0)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            hvd.captured_allreduce_(z, op=hvd.Sum)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+            hvd.captured_allreduce_(z, op=hvd.Sum)
+        run('cuda_graph_node_16MiB', z, lambda t: g.replay())
+    ag = hvd.allgather(torch.full((3,), float(rank), device='cuda'), name='chk.ag')
+    res['allgather'] = bool((ag.view(size, 3)[:, 0].cpu() == torch.arange(size, dtype=torch.float32)).all())
+    rs = hvd.reducescatter(torch.ones(size * 4, 5, device='cuda') * (rank + 1), op=hvd.Sum, name='chk.rs')
+    res['reducescatter'] = bool((rs == exp_sum).all().item()) and tuple(rs.shape) == (4, 5)
+    b = torch.full((1 << 20,), float(rank), device='cuda')
+    hvd.broadcast_(b, root_rank=size - 1, name='chk.bc')
+    res['broadcast'] = bool((b == size - 1).all().item())
+    flags = torch.tensor([1.0 if v else 0.0 for v in res.values()])
+    agree = hvd.allreduce(flags, op=hvd.Min, name='chk.all')
+    return {k: bool(agree[i] > 0) for i, k in enumerate(res)}
+
+
+def train_bench(args):
+    import torch
+    import horovod_b200.torch as hvd
+
+    t_start = time.time()
+    if args.op == 'adasum':
+        # the GPU Adasum kernels work inside the symmetric buffer: make it hold the largest single delta (GPT-2's 206 MB wte)
+        os.environ.setdefault('HVD_SYMM_BUFFER_BYTES', str(256 << 20))
+    hvd.init()
+    rank, size = hvd.rank(), hvd.size()
+    torch.cuda.set_device(hvd.local_rank())
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cuda.matmul.allow_tf32 = not args.parity
+    torch.backends.cudnn.allow_tf32 = not args.parity
+    if args.parity:
+        args.fp32 = True  # the stock reference benchmark: fp32, eager hooks, unfused optimizer, batch 64
+    main = _time_train(args, args.model, args.steps, args.warmup, hvd, torch, sample_clocks=True)
+    extra = {}
+    if not args.no_extras:
+        try:
+            if size > 1:
+                extra['checks'] = _checks_extra(hvd, torch)
+                extra['allreduce_busbw'] = _busbw_extra(args, hvd, torch)
+            if args.model == 'resnet50' and args.op == 'average' and time.time() - t_start < 240:
+                # the second model of the BASELINE metric, same timing rules, fewer steps to bound the run
+                b = _time_train(args, 'bert-large', min(args.steps, 20), 3, hvd, torch, sample_clocks=False)
+                extra['bert_large'] = {'metric': 'bert-large synthetic pretraining throughput (whole job)', 'value': b['value'], 'unit': b['unit'],
+                                       'ms_per_step': b['ms_per_step'], 'steps': min(args.steps, 20), 'warmup': 3, 'dtype': 'bf16' if not args.fp32 else 'fp32',
+                                       'e2e': {'value': b['e2e_value'], 'ms_per_step': b['e2e_ms_per_step'], 'h2d_bytes_per_step': b['h2d_bytes_per_step'],
+                                               'd2h_bytes_per_step': 4},
+                                       'config': {'global_batch': b['global_batch'], 'per_gpu_batch': b['per_gpu_batch'], 'seq_len': b['seq_len'],
+                                                  'optimizer': b['optimizer'], 'cuda_graph': b['cuda_graph'], 'allreduce_in_graph': b['allreduce_in_graph'],
+                                                  'gradient_buckets': b['gradient_buckets']},
+                                       'gpu_launches': b['gpu_launches'], 'params_identical_across_ranks': b['params_identical_across_ranks']}
+        except Exception as e:  # noqa: BLE001 - the headline number must survive a failing extra
+            extra['error'] = '%s: %s' % (type(e).__name__, str(e)[:300])
+    extra.setdefault('checks', {})['params_identical_across_ranks'] = main['params_identical_across_ranks']
     if rank == 0:
         out = {
             'metric': f'{args.model} synthetic training throughput, hvd.DistributedOptimizer op={args.op} (whole job)',
-            'value': round(value, 2), 'unit': unit, 'n_gpus': size, 'steps': args.steps, 'warmup': max(3, args.warmup),
-            'ms_per_step': round(ms / args.steps, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'bf16' if use_bf16 else 'fp32(tf32)', 'data': 'synthetic (random images/tokens, random-init weights)',
-            'impl': 'ours',
-            'config': {'model': args.model, 'global_batch': global_batch, 'per_gpu_batch': bs, 'seq_len': seq,
-                       'parallelism': f'dp{size}', 'optimizer': 'SGD(momentum=0.9)' if args.model == 'resnet50' else 'AdamW',
-                       'fused_optimizer': not args.no_fused_optimizer, 'grad_dtype': 'fp32', 'bucket_wire_dtype': args.bucket_wire_dtype or 'fp32',
-                       'cuda_graph': bool(graphed.captured), 'cuda_graph_fallback': graphed.fallback_reason,
+            'value': main['value'], 'unit': main['unit'], 'n_gpus': size, 'steps': args.steps, 'warmup': max(3, args.warmup),
+            'ms_per_step': main['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16' if not args.fp32 else ('fp32' if args.parity else 'fp32(tf32)'),
+            'data': 'synthetic (random images/tokens, random-init weights)', 'impl': 'ours',
+            'config': {'model': args.model, 'global_batch': main['global_batch'], 'per_gpu_batch': main['per_gpu_batch'],
+                       'seq_len': main['seq_len'], 'parallelism': f'dp{size}', 'optimizer': main['optimizer'],
+                       'fused_optimizer': not (args.no_fused_optimizer or args.parity), 'grad_dtype': 'fp32',
+                       'bucket_wire_dtype': args.bucket_wire_dtype or 'fp32', 'bucket_cap_mb': args.bucket_cap_mb,
+                       'parity_mode': bool(args.parity), 'cuda_graph': main['cuda_graph'], 'cuda_graph_fallback': main['cuda_graph_fallback'],
+                       'allreduce_in_graph': main['allreduce_in_graph'], 'gradient_buckets': main['gradient_buckets'],
                        'l2': 'per-step working set (activations + 100+ MB of gradients) exceeds the 126 MB L2; no explicit flush',
                        'gpu_backend': hvd.gpu_backend_info(), 'tunables': hvd.tunable_params()},
-            'clocks': clocks,
-            'e2e': {'value': round(e2e_value, 2), 'unit': unit, 'ms_per_step': round(e2e_ms / args.steps, 3),
-                    'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4, 'last_loss': last_loss},
-            'gpu_launches': int(launches),
+            'clocks': main['clocks'],
+            'e2e': {'value': main['e2e_value'], 'unit': main['unit'], 'ms_per_step': main['e2e_ms_per_step'],
+                    'h2d_bytes_per_step': main['h2d_bytes_per_step'], 'd2h_bytes_per_step': 4, 'last_loss': main['last_loss'],
+                    'loss_read': 'async D2H into pinned memory every step, read by the host one step later'},
+            'gpu_launches': main['gpu_launches'],
+            'extra': extra,
         }
         print(json.dumps(out), flush=True)
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:  # noqa: BLE001
+        pass
     hvd.shutdown()
     return 0
 

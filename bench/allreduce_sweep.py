@@ -28,8 +28,18 @@ args = p.parse_args()
 dt = {'fp32': torch.float32, 'bf16': torch.bfloat16, 'fp16': torch.float16}[args.dtype]
 sizes = [int(s) for s in args.sizes.split(',')]
 results = {}
+_extra_env = set()
 for cfg in args.configs.split(','):
-    parts = cfg.split(':')
+    # "<backend>:<variant>:<ctas>[:...]+KEY=VALUE+KEY=VALUE": extra environment knobs for this configuration only
+    for k in _extra_env:
+        os.environ.pop(k, None)
+    _extra_env = set()
+    base, *kvs = cfg.split('+')
+    for kv in kvs:
+        k, v = kv.split('=', 1)
+        os.environ[k] = v
+        _extra_env.add(k)
+    parts = base.split(':')
     os.environ['HVD_GPU_BACKEND'] = parts[0]
     os.environ['HVD_ALLREDUCE_VARIANT'] = parts[1] if len(parts) > 1 else 'auto'
     if len(parts) > 2:

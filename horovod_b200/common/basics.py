@@ -352,7 +352,8 @@ class HorovodBasics(object):
     def runtime_stats(self):
         """Counters of the background thread: cycles, idle cycles, responses executed, kernels launched."""
         return {'cycles': int(self.lib.hvd_stat(0)), 'idle_cycles': int(self.lib.hvd_stat(1)),
-                'responses': int(self.lib.hvd_stat(2)), 'kernel_launches': int(self.lib.hvd_stat(3))}
+                'responses': int(self.lib.hvd_stat(2)), 'kernel_launches': int(self.lib.hvd_stat(3)),
+                'captured_collectives': int(self.lib.hvd_stat(4))}
 
     def metrics(self):
         """Monotonic counters of this rank since init(): {'allreduce': {'responses', 'tensors', 'bytes', 'on_gpu', 'errors'}, ...}
@@ -370,6 +371,13 @@ class HorovodBasics(object):
             if any(vals.values()):
                 out[buf.value.decode().lower()] = vals
         out['runtime'] = self.runtime_stats()
+        # host-path latency probes: mean microseconds per response since init (queue = enqueue -> cycle start, negotiate,
+        # execute = descriptor staging + launch + events + callbacks, total = enqueue -> completion callback)
+        lat = {}
+        for i, name in enumerate(('queue', 'negotiate', 'execute', 'total')):
+            cnt = int(lib.hvd_stat(20 + i))
+            lat[name] = {'mean_us': round(int(lib.hvd_stat(10 + i)) / cnt / 1e3, 2) if cnt else None, 'samples': cnt}
+        out['latency'] = lat
         lib.hvd_host_path_count.restype = ctypes.c_ulonglong
         out['host_paths'] = {name: int(lib.hvd_host_path_count(i)) for i, name in enumerate(('shared_memory', 'two_level', 'base_transport'))}
         return out

@@ -178,3 +178,58 @@ def get_extension_full_path(pkg_path=None, *args):
     import os
     from horovod_b200.common.basics import lib_dir
     return os.path.join(lib_dir(), '_hvd_torch.so')
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(','):
+        if not part:
+            continue
+        if '-' in part:
+            a, b = part.split('-', 1)
+            cpus.update(range(int(a), int(b) + 1))
+        else:
+            cpus.add(int(part))
+    return cpus
+
+
+def gpu_numa_cpus(pci_domain, pci_bus, pci_device, sysfs='/sys'):
+    """CPUs local to the NUMA node of a GPU given its PCI address, or None (no NUMA information / single node)."""
+    import os
+    dev = os.path.join(sysfs, 'bus/pci/devices/%04x:%02x:%02x.0' % (pci_domain, pci_bus, pci_device))
+    try:
+        with open(os.path.join(dev, 'numa_node')) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(os.path.join(sysfs, 'devices/system/node/node%d/cpulist' % node)) as f:
+            return _parse_cpulist(f.read()) or None
+    except (OSError, ValueError):
+        return None
+
+
+def bind_to_gpu_numa(device_index, sysfs='/sys'):
+    """Restricts the calling thread (and every thread it creates afterwards, e.g. the runtime's cycle thread) to the CPUs
+    of the NUMA node the GPU hangs off — SURVEY C14 ("default: pin near GPU's NUMA node").  With 8 ranks on a two-socket
+    box, unbound rank processes bounce between sockets and the pinned-memory H2D copies of GPUs 4-7 cross the socket
+    interconnect.  No-op when the process already runs with a restricted affinity the user chose that does not overlap,
+    when sysfs has no NUMA data, or with HVD_NUMA_BIND=0.  Returns the CPU set applied, or None."""
+    import os
+    if os.environ.get('HVD_NUMA_BIND', '1') == '0' or not hasattr(os, 'sched_setaffinity'):
+        return None
+    try:
+        import torch
+        if not torch.cuda.is_available() or device_index >= torch.cuda.device_count():
+            return None
+        prop = torch.cuda.get_device_properties(device_index)
+        local = gpu_numa_cpus(getattr(prop, 'pci_domain_id', 0), prop.pci_bus_id, prop.pci_device_id, sysfs)
+        if not local:
+            return None
+        current = os.sched_getaffinity(0)
+        target = current & local
+        if not target or target == current:
+            return None
+        os.sched_setaffinity(0, target)
+        return target
+    except Exception:  # noqa: BLE001 - binding is an optimisation, never a reason to fail init
+        return None

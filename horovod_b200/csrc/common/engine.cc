@@ -62,6 +62,24 @@ void AttachNvtx(const std::shared_ptr<TensorTableEntry>& e) {
   e->nvtx_range = r;
 }
 
+struct DeviceClockBase { cudaEvent_t ev = nullptr; uint64_t host_ns = 0; uint64_t session_ns = 0; };
+// One (CUDA event, host timestamp) pair per device and timeline session: device-side offsets of later events are
+// measured against it with cudaEventElapsedTime, which places GPU spans on the host-clocked timeline.
+DeviceClockBase* DeviceBaseFor(int device, uint64_t session_ns) {
+  static std::mutex mu;
+  static std::map<int, DeviceClockBase> bases;
+  std::lock_guard<std::mutex> l(mu);
+  DeviceClockBase& b = bases[device];
+  if (b.ev && b.session_ns == session_ns) return &b;
+  if (!b.ev && cudaEventCreate(&b.ev) != cudaSuccess) { cudaGetLastError(); b.ev = nullptr; return nullptr; }
+  cudaStream_t s = GpuContext::Get().Stream(device);
+  if (cudaEventRecord(b.ev, s) != cudaSuccess || cudaEventSynchronize(b.ev) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  b.host_ns = NowNs();
+  b.session_ns = session_ns;
+  return &b;
+}
+
+
 std::string JoinInts(const std::vector<int>& v) {
   std::ostringstream os;
   for (size_t i = 0; i < v.size(); ++i) os << (i ? "," : "") << v[i];
@@ -234,6 +252,12 @@ void Engine::BackgroundThread() {
     genv.wire_dtype = wire == "bf16" ? DataType::BFLOAT16 : wire == "fp16" ? DataType::FLOAT16 : DataType::FLOAT32;
     genv.symm_buffer_bytes = (size_t)EnvInt(HVD_SYMM_BUFFER_BYTES, 128ll << 20);
     genv.want_multicast = EnvBool("HVD_ENABLE_NVLS", true);
+    genv.pipelined = EnvBool("HVD_PIPELINED_ALLREDUCE", true);
+    genv.pipe_chunk_bytes = std::max<int64_t>(1 << 20, EnvInt("HVD_PIPE_CHUNK_BYTES", 4 << 20) / 4096 * 4096);
+    genv.pipe_min_bytes = EnvInt("HVD_PIPE_MIN_BYTES", 32 << 20);
+    genv.pipe_rblock_bytes = std::max<int64_t>(4096, EnvInt("HVD_PIPE_RBLOCK_BYTES", 16384) / 4096 * 4096);
+    genv.large_msg_ctas = std::min<int64_t>(kern::kMaxCtas, std::max<int64_t>(4, EnvInt("HVD_LARGE_MSG_CTAS", 256)));
+    genv.broadcast_multicast = EnvBool("HVD_BROADCAST_MULTICAST", true);
     gpu_ops_.reset(new GpuOps(genv));
 
     // ---- GPU / NVLink topology discovery (new relative to the reference) ----
@@ -344,6 +368,7 @@ bool Engine::RunLoopOnce() {
     flush_ = false;
   }
   ++cycles_;
+  cycle_start_ns_ = NowNs();
   timeline_.MarkCycleStart();
   {  // runtime timeline start / stop requests
     std::lock_guard<std::mutex> l(tl_mu_);
@@ -362,8 +387,10 @@ bool Engine::RunLoopOnce() {
     ps->controller->set_cache_enabled(tp.cache_enabled);
     // only the GLOBAL set decides when the engine stops: the members of a sub-set may all have asked for shutdown while
     // another rank has not yet, and leaving early would cut that rank's connections in the middle of a negotiation
+    const uint64_t t_neg = NowNs();
     ResponseList rl = ps->controller->ComputeResponseList(id == 0 && shutdown_requested_.load());
     if (rl.responses.empty()) ++fast_cycles_;
+    else NoteLatency(1, NowNs() - t_neg);
     for (auto& r : rl.responses) PerformOperation(*ps, r);
     if (id == 0 && rl.shutdown) keep_going = false;
     else if (rl.shutdown) shutdown_requested_ = true;  // a sub-set's stall inspector gave up: take the job down through the global set
@@ -381,6 +408,19 @@ void Engine::PerformOperation(ProcessSet& ps, Response& r) {
   Entries es;
   ps.queue.GetTensorEntriesFromResponse(r, es);
   ++responses_;
+  const uint64_t t_exec = NowNs();
+  struct Probe {  // latency probes: one sample per response, taken when the function returns (callbacks have run)
+    Engine* eng; uint64_t t0; uint64_t first_enqueue;
+    ~Probe() {
+      const uint64_t now = NowNs();
+      eng->NoteLatency(2, now - t0);
+      if (first_enqueue) {
+        if (eng->cycle_start_ns_ > first_enqueue) eng->NoteLatency(0, eng->cycle_start_ns_ - first_enqueue);
+        eng->NoteLatency(3, now - first_enqueue);
+      }
+    }
+  } probe{this, t_exec, 0};
+  for (auto& e : es) if (e && e->enqueue_ns && (probe.first_enqueue == 0 || e->enqueue_ns < probe.first_enqueue)) probe.first_enqueue = e->enqueue_ns;
   auto finish_all = [&](const Status& st) {
     for (auto& e : es) if (e && e->callback) { Completion c; c.status = st; c.received_splits = e->received_splits; e->callback(c); }
   };
@@ -453,6 +493,18 @@ void Engine::PerformOperation(ProcessSet& ps, Response& r) {
 
   Status st;
   SharedEvent* done = nullptr;
+  // device-timed timeline row: CUDA events (timing enabled) around the kernels of this response on the hvd stream
+  cudaEvent_t tl_t0 = nullptr, tl_t1 = nullptr;
+  DeviceClockBase* tl_base = nullptr;
+  if (device != CPU_DEVICE_ID && timeline_.Initialized()) {
+    tl_base = DeviceBaseFor(device, timeline_.session_start_ns());
+    if (tl_base && cudaEventCreate(&tl_t0) == cudaSuccess && cudaEventCreate(&tl_t1) == cudaSuccess) {
+      cudaEventRecord(tl_t0, GpuContext::Get().Stream(device));
+    } else {
+      if (tl_t0) cudaEventDestroy(tl_t0);
+      tl_t0 = tl_t1 = nullptr; cudaGetLastError();
+    }
+  }
   try {
     if (device == CPU_DEVICE_ID) {
       st = ExecuteCpu(ps, es, r);
@@ -488,17 +540,28 @@ void Engine::PerformOperation(ProcessSet& ps, Response& r) {
     }
   }
 
+  if (tl_t1) cudaEventRecord(tl_t1, GpuContext::Get().Stream(device));
   if (done) {
     if (timeline_.Initialized()) {
       done->refs.fetch_add(1);
       std::vector<std::string> names;
       for (auto& e : es) if (e) names.push_back(e->name);
-      finalizers_.Execute([this, done, names] {
+      const std::string act = std::string("GPU ") + ResponseTypeName(r.type);
+      finalizers_.Execute([this, done, names, tl_t0, tl_t1, tl_base, act] {
         cudaSetDevice(done->device);
         cudaEventSynchronize(done->ev);
+        if (tl_t0 && tl_t1 && tl_base && cudaEventSynchronize(tl_t1) == cudaSuccess) {
+          float off_ms = 0, dur_ms = 0;
+          if (cudaEventElapsedTime(&off_ms, tl_base->ev, tl_t0) == cudaSuccess && cudaEventElapsedTime(&dur_ms, tl_t0, tl_t1) == cudaSuccess)
+            timeline_.DeviceSpan(names, act, timeline_.ToTimelineUs(tl_base->host_ns) + (int64_t)(off_ms * 1e3), (int64_t)(dur_ms * 1e3));
+        }
+        if (tl_t0) cudaEventDestroy(tl_t0);
+        if (tl_t1) cudaEventDestroy(tl_t1);
+        cudaGetLastError();
         for (auto& n : names) timeline_.End(n);
         GpuContext::Get().Release(done);
       });
+      tl_t0 = tl_t1 = nullptr;
     }
     for (auto& e : es) {
       if (e && e->callback) {
@@ -513,6 +576,8 @@ void Engine::PerformOperation(ProcessSet& ps, Response& r) {
     if (timeline_.Initialized()) for (auto& e : es) if (e) timeline_.End(e->name);
     finish_all(st);
   }
+  if (tl_t0) cudaEventDestroy(tl_t0);
+  if (tl_t1) cudaEventDestroy(tl_t1);
 }
 
 // ---------------------------------------------------------------------------
@@ -898,6 +963,18 @@ void* Engine::AllocSymmetric(size_t bytes, int device, int32_t psid, std::string
     if (ps->team) *keep_alive = ps->team->KeepAlive();
   }
   return c.aux_ptr;
+}
+
+Status Engine::CapturedAllreduce(void* ptr, int64_t bytes, DataType dtype, ReduceOp op, double prescale, double postscale,
+                                 int32_t psid, int max_ctas, void* stream) {
+  std::shared_ptr<ProcessSet> ps;
+  Status st = CheckSet(psid, &ps);
+  if (!st.ok()) return st;
+  if (op == ReduceOp::ADASUM) return Status::InvalidArgument("captured allreduce does not support Adasum");
+  if (op == ReduceOp::AVERAGE) { op = ReduceOp::SUM; postscale /= (double)ps->set_size(); }
+  if (ps->set_size() == 1) return Status::OK();
+  captured_launches_.fetch_add(1, std::memory_order_relaxed);
+  return gpu_ops_->CapturedAllreduce(*ps, ptr, bytes, dtype, op, prescale, postscale, max_ctas, (cudaStream_t)stream);
 }
 
 Status Engine::StartTimeline(const std::string& file, bool mark_cycles) {

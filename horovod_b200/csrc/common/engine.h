@@ -80,6 +80,11 @@ class Engine {
   // `keep_alive` (optional) receives a token that keeps the region mapped for as long as the caller holds it
   void* AllocSymmetric(size_t bytes, int device, int32_t process_set_id, std::string* err, std::shared_ptr<void>* keep_alive = nullptr);
 
+  // Zero-copy allreduce of a registered tensor launched on the caller's stream (CUDA-graph capturable, no negotiation);
+  // `stream` is a cudaStream_t.  See GpuOps::CapturedAllreduce.
+  Status CapturedAllreduce(void* ptr, int64_t bytes, DataType dtype, ReduceOp op, double prescale, double postscale,
+                           int32_t process_set_id, int max_ctas, void* stream);
+
   // ---- timeline ----
   Status StartTimeline(const std::string& file, bool mark_cycles);
   Status StopTimeline();
@@ -94,6 +99,13 @@ class Engine {
   uint64_t cycles() const { return cycles_.load(); }
   uint64_t fast_path_cycles() const { return fast_cycles_.load(); }
   uint64_t responses_executed() const { return responses_.load(); }
+  uint64_t captured_launches() const { return captured_launches_.load(); }
+  // Host-path latency probes (sums of nanoseconds + sample counts since init): where a collective's time goes before the
+  // GPU sees it.  0 queue = enqueue -> its cycle starts, 1 negotiate = ComputeResponseList, 2 execute = PerformOperation
+  // (pack descriptors, launch, record events, callbacks), 3 total = enqueue -> completion callback.
+  static constexpr int kLatKinds = 4;
+  uint64_t latency_sum_ns(int k) const { return lat_sum_[k].load(std::memory_order_relaxed); }
+  uint64_t latency_count(int k) const { return lat_cnt_[k].load(std::memory_order_relaxed); }
   // Named monotonic counters (hvd.metrics()): per collective type the number of executed (fused) responses, tensors and
   // payload bytes, split by where they ran (gpu / host), plus errors.  Index = type * kPerType + field.
   static constexpr int kMetricTypes = 12, kPerType = 5;
@@ -144,6 +156,10 @@ class Engine {
   std::string last_error_;
   std::atomic<uint64_t> cycles_{0}, fast_cycles_{0}, responses_{0};
   std::atomic<uint64_t> op_metrics_[kMetricTypes * kPerType] = {};
+  std::atomic<uint64_t> captured_launches_{0};
+  std::atomic<uint64_t> lat_sum_[kLatKinds] = {}, lat_cnt_[kLatKinds] = {};
+  uint64_t cycle_start_ns_ = 0;
+  void NoteLatency(int k, uint64_t ns) { lat_sum_[k].fetch_add(ns, std::memory_order_relaxed); lat_cnt_[k].fetch_add(1, std::memory_order_relaxed); }
   std::atomic<int> noname_counter_{0};
   std::atomic<int> symm_alloc_counter_{0};
   std::atomic<int> join_device_{-1};  // CUDA device a joined rank contributes zeros from

@@ -43,6 +43,21 @@ void NvtxOpRange::End() {
   active_ = false;
 }
 
+uint64_t NvtxRangeStart(const std::string& message) {
+  Domain& d = D();
+  if (!d.enabled) return 0;
+  nvtxEventAttributes_t a = {};
+  a.version = NVTX_VERSION;
+  a.size = NVTX_EVENT_ATTRIB_STRUCT_SIZE;
+  a.messageType = NVTX_MESSAGE_TYPE_ASCII;
+  a.message.ascii = message.c_str();
+  return (uint64_t)nvtxDomainRangeStartEx(d.dom, &a) + 1;  // +1: 0 stays "no range"
+}
+void NvtxRangeEnd(uint64_t id) {
+  if (id == 0) return;
+  nvtxDomainRangeEnd(D().dom, (nvtxRangeId_t)(id - 1));
+}
+
 void NvtxMark(const char* message) {
   Domain& d = D();
   if (!d.enabled) return;

@@ -25,6 +25,10 @@ class NvtxOpRange {
   bool active_ = false;
 };
 
+// Free-form ranges of the timeline mirror ("<tensor>: <activity>"); 0 = not started (NVTX off).
+uint64_t NvtxRangeStart(const std::string& message);
+void NvtxRangeEnd(uint64_t id);
+
 // instant marker in the hvd domain (cycle starts, autotune changes)
 void NvtxMark(const char* message);
 bool NvtxEnabled();

@@ -322,6 +322,52 @@ Status GpuOps::HierarchicalAllreduce(ProcessSet& ps, Entries& es, const Response
   return Status::OK();
 }
 
+// Arguments of the zero-copy kernel for [ptr, ptr + bytes) if that range lies in a registered region of `team` (at byte
+// offset `expect_off` when >= 0 — the offset every rank agreed on during negotiation).
+bool GpuOps::BuildInplaceArgs(SymmTeam& team, const void* ptr, int64_t bytes, DataType dtype, ReduceOp op, double prescale,
+                              double postscale, int64_t expect_off, int max_ctas, kern::InplaceArgs* out) {
+  const int n = team.nranks();
+  SymmTeam::RegionView view;
+  int64_t off = 0;
+  if (bytes <= 0 || (bytes & 15) || !team.FindRegion(ptr, (size_t)bytes, &view, &off) || (off & 15)) return false;
+  if (expect_off >= 0 && expect_off != off) return false;
+  const bool sum_like = op == ReduceOp::SUM || op == ReduceOp::AVERAGE;
+  if (!sum_like && !(prescale == 1.0 && postscale == 1.0)) return false;
+  kern::InplaceArgs ia {};
+  for (int p = 0; p < n; ++p) ia.ptr[p] = (char*)view.ptr[p] + off;
+  ia.mc = view.mc ? (char*)view.mc + off : nullptr;
+  ia.bytes = bytes;
+  ia.scale = prescale * postscale;
+  ia.op = (int)op;
+  ia.dtype = (int)dtype;
+  ia.use_multicast = (ia.mc && sum_like && env_.variant != "twoshot" && (n >= 4 || env_.variant == "nvls") && bytes >= env_.params->nvls_min_bytes &&
+                      (dtype == DataType::FLOAT32 || dtype == DataType::FLOAT16 || dtype == DataType::BFLOAT16)) ? 1 : 0;
+  ia.ctas = (int)std::max<int64_t>(1, std::min<int64_t>(max_ctas, (bytes + 4096ll * n - 1) / (4096ll * n)));
+  *out = ia;
+  return true;
+}
+
+// Collective as a CUDA-graph node: launches the zero-copy allreduce of a registered tensor on the CALLER's stream — which
+// may be capturing — on the graph channel's flags, without a negotiation round.  Every rank must issue the same sequence
+// of captured collectives (same tensors, same order), which is what capturing the same training step on every rank
+// does; the kernel's own flag barrier is the only synchronisation, so a replayed step needs no host work at all.
+// Nothing like it exists in the reference (its cycle loop negotiates every tensor every step, controller.cc:209-252).
+Status GpuOps::CapturedAllreduce(ProcessSet& ps, void* ptr, int64_t bytes, DataType dtype, ReduceOp op, double prescale,
+                                 double postscale, int max_ctas, cudaStream_t stream) {
+  std::shared_ptr<SymmTeam> team;
+  { std::lock_guard<std::mutex> l(ps.team_mu); team = ps.team; }
+  if (!team) return Status::PreconditionError("captured allreduce: the process set has no peer-mapped team (allocate the tensor with hvd.symm_empty first)");
+  if (team->abort_state() != 0) return Status::Aborted("captured allreduce: the team was aborted");
+  kern::InplaceArgs ia {};
+  if (max_ctas <= 0) max_ctas = env_.params->comm_ctas;
+  if (!BuildInplaceArgs(*team, ptr, bytes, dtype, op, prescale, postscale, -1, std::min(max_ctas, kern::kMaxCtas), &ia))
+    return Status::InvalidArgument("captured allreduce: tensor is not (entirely) inside registered symmetric memory, is not 16 B "
+                                   "aligned, or combines MIN/MAX/PRODUCT with scale factors");
+  cudaError_t ce = kern::LaunchInplaceAllreduce(team->Params(0, kern::kGraphChannel), ia, stream);
+  if (ce != cudaSuccess) return Status::UnknownError(std::string("captured allreduce launch failed: ") + cudaGetErrorString(ce));
+  return Status::OK();
+}
+
 std::string GpuOps::Describe(ProcessSet& ps) {
   if (!ps.team_tried) return "backend=" + env_.backend + " (no GPU collective issued yet)";
   if (!ps.team && ps.local_team) return "backend=hierarchical intra-host symm=" + ps.local_team->backend() + " cross-host=cpu-transport";
@@ -361,29 +407,16 @@ Status GpuOps::Allreduce(ProcessSet& ps, Entries& es, const Response& r, int dev
       // ---- zero-copy path: the tensor lives in registered symmetric memory on EVERY rank (negotiated symm_key) ----
       const int64_t zc_bytes = pieces.size() == 1 ? pieces[0].count * (int64_t)esz : 0;
       if (r.symm_key >= 0 && pieces.size() == 1 && es[0] && zc_bytes > env_.params->oneshot_max_bytes && env_.variant != "oneshot") {
-        SymmTeam::RegionView view;
-        int64_t off = 0;
-        if (team->FindRegion(pieces[0].in, (size_t)zc_bytes, &view, &off) && (((int64_t)(r.symm_key & ((1ll << 44) - 1))) == off)) {
-          kern::InplaceArgs ia {};
-          for (int p = 0; p < n; ++p) ia.ptr[p] = (char*)view.ptr[p] + off;
-          ia.mc = view.mc ? (char*)view.mc + off : nullptr;
-          ia.bytes = zc_bytes;
-          ia.scale = r.prescale * r.postscale;
-          ia.op = (int)r.reduce_op;
-          ia.dtype = (int)r.dtype;
-          const bool sum_like = r.reduce_op == ReduceOp::SUM || r.reduce_op == ReduceOp::AVERAGE;
-          ia.use_multicast = (ia.mc && sum_like && env_.variant != "twoshot" && (n >= 4 || env_.variant == "nvls") && zc_bytes >= env_.params->nvls_min_bytes &&
-                              (r.dtype == DataType::FLOAT32 || r.dtype == DataType::FLOAT16 || r.dtype == DataType::BFLOAT16)) ? 1 : 0;
-          if (sum_like || (r.prescale == 1.0 && r.postscale == 1.0)) {
-            ia.ctas = (int)std::max<int64_t>(1, std::min<int64_t>(env_.params->comm_ctas, (zc_bytes + 4096ll * n - 1) / (4096ll * n)));
-            kern::CommParams cp = team->Params(team->NextSlot());
-            if (env_.timeline && env_.timeline->Initialized())
-              env_.timeline->ActivityStartAll(es, ia.use_multicast ? HVD_ACT_P2P_ALLREDUCE_NVLS : HVD_ACT_P2P_ALLREDUCE_TWOSHOT);
-            cudaError_t ce = kern::LaunchInplaceAllreduce(cp, ia, s);
-            if (ce != cudaSuccess) return Status::UnknownError(std::string("zero-copy allreduce launch failed: ") + cudaGetErrorString(ce));
-            ctx.TempFreeAll(device, s);
-            return FinishEvent(device, s, es.size(), done);
-          }
+        kern::InplaceArgs ia {};
+        if (BuildInplaceArgs(*team, pieces[0].in, zc_bytes, r.dtype, r.reduce_op, r.prescale, r.postscale,
+                             (int64_t)(r.symm_key & ((1ll << 44) - 1)), env_.params->comm_ctas, &ia)) {
+          kern::CommParams cp = team->Params(team->NextSlot());
+          if (env_.timeline && env_.timeline->Initialized())
+            env_.timeline->ActivityStartAll(es, ia.use_multicast ? HVD_ACT_P2P_ALLREDUCE_NVLS : HVD_ACT_P2P_ALLREDUCE_TWOSHOT);
+          cudaError_t ce = kern::LaunchInplaceAllreduce(cp, ia, s);
+          if (ce != cudaSuccess) return Status::UnknownError(std::string("zero-copy allreduce launch failed: ") + cudaGetErrorString(ce));
+          ctx.TempFreeAll(device, s);
+          return FinishEvent(device, s, es.size(), done);
         }
       }
       // wire dtype: optional in-kernel compression of fp32 sums
@@ -417,24 +450,24 @@ Status GpuOps::Allreduce(ProcessSet& ps, Entries& es, const Response& r, int dev
           else if (nvls_ok && n >= 4 && seg_bytes >= tp.nvls_min_bytes) variant = kern::kNvls;  // in-switch reduction pays off from 4 GPUs (measured: slower than two-shot at N=2)
         }
         // opt-in: software-pipelined pack / NVLS / unpack for large segments of plain tensors (docs/roadmap.md B1)
-        static const bool pipelined_on = EnvBool("HVD_PIPELINED_ALLREDUCE", false);
-        static const int64_t pipe_chunk = std::max<int64_t>(1 << 20, EnvInt("HVD_PIPE_CHUNK_BYTES", 8 << 20) / 4096 * 4096);
-        static const int64_t pipe_min = EnvInt("HVD_PIPE_MIN_BYTES", 32 << 20);
-        if (pipelined_on && env_.variant == "auto" && seg_bytes >= pipe_min && (r.reduce_op == ReduceOp::SUM || r.reduce_op == ReduceOp::AVERAGE) &&
-            cap / pipe_chunk >= 2) {
+        const bool pipelined_on = env_.pipelined;
+        const int64_t pipe_chunk = env_.pipe_chunk_bytes, pipe_min = env_.pipe_min_bytes;
+        // (measured at N = 2, where the reduce stage is plain P2P: 195 GB/s pipelined vs 476 GB/s for the three-phase kernel
+        // at 1 GiB — the pipeline only pays when the reduce stage is the in-switch multimem one)
+        if (pipelined_on && env_.variant == "auto" && nvls_ok && n >= 4 && seg_bytes >= pipe_min && cap / pipe_chunk >= 2) {
           variant = kern::kPipelined;
           a.pipe_chunk_bytes = pipe_chunk;
-          a.pipe_rblock_bytes = std::max<int64_t>(4096, EnvInt("HVD_PIPE_RBLOCK_BYTES", 16384) / 4096 * 4096);
+          a.pipe_rblock_bytes = env_.pipe_rblock_bytes;
           a.pipe_slots = (int)std::min<int64_t>(kern::kPipeMaxSlots, cap / pipe_chunk);
           a.pipe_base = team->NextPipeBase((uint32_t)((seg_bytes + pipe_chunk - 1) / pipe_chunk));
-          a.pipe_use_nvls = (nvls_ok && n >= 4) ? 1 : 0;
+          a.pipe_use_nvls = 1;
         }
         a.variant = variant;
         int64_t per = variant == kern::kOneShot ? 8192 : (int64_t)4096 * n;  // >= 2 rows (one-shot) or one row per rank (two-shot) per CTA
         // small messages are latency bound (few CTAs = cheap barrier, SMs left to compute); large ones need many loads in flight
         // >= 64 MiB of plain (unregistered) tensors: the local pack / unpack phases are HBM-latency bound at one CTA per
         // SM (ncu: 12.5 % warps active, 1.3 TB/s), so go to two CTAs per SM
-        static const int64_t big_ctas = std::min<int64_t>(kern::kMaxCtas, EnvInt("HVD_LARGE_MSG_CTAS", 256));
+        const int64_t big_ctas = env_.large_msg_ctas;
         const int64_t cap_ctas = seg_bytes <= (1 << 20) ? std::min<int64_t>(tp.comm_ctas, 16)
                                : seg_bytes <= (16 << 20) ? std::min<int64_t>(tp.comm_ctas, 64)
                                : seg_bytes < (64 << 20) ? tp.comm_ctas : std::max<int64_t>(tp.comm_ctas, big_ctas);
@@ -811,8 +844,7 @@ Status GpuOps::Broadcast(ProcessSet& ps, Entries& es, const Response& r, int dev
     }
     return FinishEvent(device, s, es.size(), done);
   }
-  static const bool mc_bcast = EnvBool("HVD_BROADCAST_MULTICAST", true);
-  const bool use_mc = mc_bcast && team->has_multicast() && n > 2;
+  const bool use_mc = env_.broadcast_multicast && team->has_multicast() && n > 2;
   const int64_t cap = (int64_t)team->buffer_bytes() / 16 * 16;
   std::vector<kern::CopyDesc> sends, recvs;
   int64_t used = 0;

@@ -18,6 +18,8 @@
 #include "../common/controller.h"
 #include "../common/process_set.h"
 #include "../common/timeline.h"
+#include "../kernels/p2p_kernels.h"
+#include "../symm/symm_memory.h"
 
 namespace hvd {
 
@@ -69,6 +71,11 @@ struct GpuOpEnv {
   DataType wire_dtype = DataType::FLOAT32;  // FLOAT32 = no compression
   size_t symm_buffer_bytes = 128ull << 20;
   bool want_multicast = true;
+  // software-pipelined allreduce of large plain (unregistered) tensors: pack / reduce / unpack CTAs on a chunk ring
+  bool pipelined = true;
+  int64_t pipe_chunk_bytes = 4 << 20, pipe_min_bytes = 32 << 20, pipe_rblock_bytes = 16384;
+  int64_t large_msg_ctas = 256;   // CTAs for >= 64 MiB fused messages (two per SM)
+  bool broadcast_multicast = true;
 };
 
 class GpuOps {
@@ -85,6 +92,13 @@ class GpuOps {
   Status Reducescatter(ProcessSet& ps, Entries& es, const Response& r, int device, SharedEvent** done);
   // Description of the data path chosen for a set (for hvd.gpu_backend_info()).
   std::string Describe(ProcessSet& ps);
+
+  // Zero-copy allreduce of a registered tensor as ONE kernel on `stream` (which may be capturing into a CUDA graph), on the
+  // graph channel, with no negotiation: callable from framework threads.
+  Status CapturedAllreduce(ProcessSet& ps, void* ptr, int64_t bytes, DataType dtype, ReduceOp op, double prescale,
+                           double postscale, int max_ctas, cudaStream_t stream);
+  bool BuildInplaceArgs(SymmTeam& team, const void* ptr, int64_t bytes, DataType dtype, ReduceOp op, double prescale,
+                        double postscale, int64_t expect_off, int max_ctas, kern::InplaceArgs* out);
 
   // Lazily creates (collectively) the peer-mapped team of a process set.
   std::shared_ptr<SymmTeam> EnsureTeam(ProcessSet& ps, int device);

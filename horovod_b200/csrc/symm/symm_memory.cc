@@ -263,13 +263,15 @@ SymmTeam::~SymmTeam() = default;
 
 std::shared_ptr<void> SymmTeam::KeepAlive() const { return std::static_pointer_cast<void>(impl_); }
 
-kern::CommParams SymmTeam::Params(int which) const {
+kern::CommParams SymmTeam::Params(int which, int channel) const {
   kern::CommParams cp {};
   cp.nranks = nranks_;
   cp.rank = rank_;
-  for (int i = 0; i < nranks_; ++i) { cp.buf[i] = buf_[which][i]; cp.flags[i] = flags_[i]; }
+  // channel 0 = the cycle thread's flag words at the start of the region; channels >= 1 own kFlagWords each further up
+  const size_t foff = channel == 0 ? 0 : (kern::kChannelFlagsOffset / 4 + (size_t)(channel - 1) * kern::kFlagWords);
+  for (int i = 0; i < nranks_; ++i) { cp.buf[i] = buf_[which][i]; cp.flags[i] = flags_[i] + foff; }
   cp.mc_buf = mc_va_[which];
-  cp.epochs = epochs_;
+  cp.epochs = epochs_ + (size_t)channel * kern::kMaxCtas;
   cp.abort_flag = abort_dev_;
   cp.timeout_ns = timeout_ns_;
   return cp;
@@ -277,9 +279,10 @@ kern::CommParams SymmTeam::Params(int which) const {
 
 namespace {
 // flag words (kFlagWords * 4 = 8 KiB) followed by the two Adasum partial-dot tables (2 x kAdasumScratchStride)
-constexpr size_t kFlagRegionBytes = 128 * 1024;
+constexpr size_t kFlagRegionBytes = 256 * 1024;
 static_assert(kern::kFlagWords * 4 + 2 * kern::kAdasumScratchStride <= (long long)kern::kPipeAreaOffset, "Adasum scratch overlaps the pipeline words");
-static_assert(kern::kPipeAreaOffset + kern::kPipeAreaWords * 4 <= (long long)kFlagRegionBytes, "flag region too small");
+static_assert(kern::kPipeAreaOffset + kern::kPipeAreaWords * 4 <= (long long)kern::kChannelFlagsOffset, "pipeline words overlap the channel flags");
+static_assert(kern::kChannelFlagsOffset + (kern::kNumChannels - 1) * kern::kFlagWords * 4 <= (long long)kFlagRegionBytes, "flag region too small");
 }
 
 std::shared_ptr<SymmTeam> SymmTeam::Create(Transport* t, int device, size_t buffer_bytes, bool want_mc,
@@ -446,8 +449,8 @@ std::shared_ptr<SymmTeam> SymmTeam::Create(Transport* t, int device, size_t buff
     team->flags_[p] = (uint32_t*)(base[p] + 2 * buf_bytes);
   }
   bool good = cudaMemset(base[me] + 2 * buf_bytes, 0, kFlagRegionBytes) == cudaSuccess;
-  good = good && cudaMalloc(&impl->epochs, kern::kMaxCtas * sizeof(uint32_t)) == cudaSuccess &&
-         cudaMemset(impl->epochs, 0, kern::kMaxCtas * sizeof(uint32_t)) == cudaSuccess;
+  good = good && cudaMalloc(&impl->epochs, kern::kNumChannels * kern::kMaxCtas * sizeof(uint32_t)) == cudaSuccess &&
+         cudaMemset(impl->epochs, 0, kern::kNumChannels * kern::kMaxCtas * sizeof(uint32_t)) == cudaSuccess;
   good = good && cudaHostAlloc((void**)&impl->abort_host, sizeof(int), cudaHostAllocMapped) == cudaSuccess;
   if (good) { *impl->abort_host = 0; good = cudaHostGetDevicePointer((void**)&team->abort_dev_, impl->abort_host, 0) == cudaSuccess; }
   good = good && cudaDeviceSynchronize() == cudaSuccess;
@@ -623,8 +626,8 @@ std::vector<std::shared_ptr<SymmTeam>> SymmTeam::CreateSimulated(int n, int devi
     for (int p = 0; p < n; ++p) {
       team->buf_[0][p] = base[p]; team->buf_[1][p] = base[p] + buf_bytes; team->flags_[p] = (uint32_t*)(base[p] + 2 * buf_bytes);
     }
-    cudaMalloc(&impl->epochs, kern::kMaxCtas * sizeof(uint32_t));
-    cudaMemset(impl->epochs, 0, kern::kMaxCtas * sizeof(uint32_t));
+    cudaMalloc(&impl->epochs, kern::kNumChannels * kern::kMaxCtas * sizeof(uint32_t));
+    cudaMemset(impl->epochs, 0, kern::kNumChannels * kern::kMaxCtas * sizeof(uint32_t));
     cudaHostAlloc((void**)&impl->abort_host, sizeof(int), cudaHostAllocMapped);
     *impl->abort_host = 0;
     cudaHostGetDevicePointer((void**)&team->abort_dev_, impl->abort_host, 0);

@@ -55,8 +55,11 @@ class SymmTeam {
   int rank() const { return rank_; }
   size_t buffer_bytes() const { return buffer_bytes_; }
   bool has_multicast() const { return mc_va_[0] != nullptr; }
-  // CommParams for buffer slot `which` (0/1 ping-pong).
-  kern::CommParams Params(int which) const;
+  // CommParams for buffer slot `which` (0/1 ping-pong).  `channel` selects an independent set of barrier flags + epochs:
+  // kernels of different channels may run concurrently (channel 0 = the cycle thread's stream, kGraphChannel = collectives
+  // captured into CUDA graphs on framework streams, the rest = extra engine streams).  The data slots are shared: only
+  // zero-copy (registered-region) kernels may use a channel other than the one that owns the slots.
+  kern::CommParams Params(int which, int channel = 0) const;
   // Next ping-pong slot (ops alternate so a fast rank never overwrites data a
   // slow peer is still reading).
   int NextSlot() { int s = slot_; slot_ ^= 1; return s; }

@@ -442,6 +442,19 @@ at::Tensor SymmEmpty(int64_t nbytes, int device, int process_set_id) {
   return at::from_blob(p, {nbytes}, [keep](void*) mutable { keep.reset(); }, opts);
 }
 
+// In-place allreduce of a tensor that lives in registered symmetric memory, launched as ONE kernel on the current CUDA
+// stream of the calling thread — which may be capturing into a CUDA graph.  No handle, no negotiation, no host
+// synchronisation: ordering is the stream's.  reduce_op follows hvd.ReduceOp (0 Average, 1 Sum, 3 Min, 4 Max, 5 Product).
+void CapturedAllreduce(at::Tensor tensor, int reduce_op, double prescale, double postscale, int process_set_id, int max_ctas) {
+  TORCH_CHECK(tensor.is_cuda(), "captured_allreduce_: CUDA tensor expected");
+  TORCH_CHECK(tensor.is_non_overlapping_and_dense(), "captured_allreduce_: tensor must be dense");
+  c10::cuda::CUDAGuard guard(tensor.device());
+  cudaStream_t stream = c10::cuda::getCurrentCUDAStream(tensor.get_device());
+  const int64_t bytes = (int64_t)tensor.numel() * (int64_t)tensor.element_size();
+  ThrowIfError(Engine::Get().CapturedAllreduce(tensor.data_ptr(), bytes, MapDtype(tensor.scalar_type()), (ReduceOp)reduce_op, prescale,
+                                               postscale, process_set_id, max_ctas, (void*)stream));
+}
+
 // ---- fused optimizer kernels (B200-native extra; see kernels/optim_kernels.cu) --------------
 void FusedSgdStep(std::vector<at::Tensor> params, std::vector<at::Tensor> grads, std::vector<at::Tensor> momenta, double lr,
                   double momentum, double dampening, double weight_decay, bool nesterov, double grad_scale, bool first_step) {
@@ -514,6 +527,7 @@ PYBIND11_MODULE(_hvd_torch, m) {
   m.def("reset", &Reset);
   m.def("reset_noname_counters", &ResetNonameCounters);
   m.def("symm_empty", &SymmEmpty);
+  m.def("captured_allreduce_", &CapturedAllreduce);
   m.def("fused_sgd_step", &FusedSgdStep);
   m.def("fused_adam_step", &FusedAdamStep);
 }

@@ -422,7 +422,15 @@ std::shared_ptr<Transport> WrapWithHierarchicalControl(std::shared_ptr<Transport
   }
   // worth it only if some host has several ranks; every rank evaluates the same table, so the decision is collective
   bool any_shared = (int)leaders.size() < n;
-  if (!any_shared || (int)local.size() + 1 > kMaxRanks) return base;
+  // the size limit is checked on the LARGEST host of the global table, not on this rank's own host: with uneven hosts a
+  // per-host test would send some ranks into the collective below and let the others return
+  int max_local = 0;
+  for (int h : seen_hosts) {
+    int c = 0;
+    for (int r = 0; r < n; ++r) if (base->host_id(r) == h) ++c;
+    max_local = std::max(max_local, c);
+  }
+  if (!any_shared || max_local + 1 > kMaxRanks) return base;
   const int li = (int)(std::find(local.begin(), local.end(), me) - local.begin());
   const std::string name = "/" + segment_name + "-h" + std::to_string(base->host_id(me));
   Segment* seg = nullptr;

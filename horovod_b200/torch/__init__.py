@@ -15,7 +15,7 @@ from horovod_b200.torch.mpi_ops import (  # noqa: F401
     broadcast, broadcast_async, broadcast_, broadcast_async_,
     alltoall, alltoall_async,
     reducescatter, reducescatter_async, grouped_reducescatter, grouped_reducescatter_async,
-    join, barrier, poll, synchronize, symm_empty, symm_available,
+    join, barrier, poll, synchronize, symm_empty, symm_available, captured_allreduce_,
     Average, Sum, Adasum, Min, Max, Product)
 from horovod_b200.torch.functions import (broadcast_parameters, broadcast_optimizer_state, broadcast_object,  # noqa: F401
                                           allgather_object)

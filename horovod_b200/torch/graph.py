@@ -4,9 +4,13 @@
 Why (B200-first; nothing like it exists in the reference): a ResNet-50 / BERT step in eager PyTorch issues 1–3 thousand
 kernel launches, and on a B200 the GPU finishes them faster than one Python thread can issue them — the measured step
 time is the host's launch time, identical at 1 and 8 GPUs.  Replaying the step as ONE graph launch removes that bound.
-The gradient hooks of `DistributedOptimizer` cannot fire from inside a replay, so in graph mode `optimizer.step()`
-launches the allreduce of every (zero-copy) gradient bucket itself: ~100 MB of fp32 gradients take ≈0.3 ms on the NVLS
-path of an 8×B200 NVSwitch box, so losing the overlap with backward costs less than the hooks' host time did.
+On several GPUs the gradient allreduce is PART of the graph: while the step is being captured, the hook of the last
+gradient of every zero-copy bucket records that bucket's `hvd.captured_allreduce_` kernel (multimem / P2P in-place
+reduction on peer-mapped memory, flag barrier inside the kernel) on a forked high-priority stream, so on replay the
+reduction of bucket k overlaps the backward pass of the layers below it, and a whole data-parallel step — forward,
+backward, every collective — is ONE launch with no negotiation round and no host work.  `optimizer.step()` after the
+replay only applies the (fused) update.  If some trainable parameter is not in a registered bucket (sparse gradients,
+`zero_copy=False`, gradient accumulation) the reductions stay outside the graph and `step()` issues them as before.
 
     step = hvd.GraphedStep(lambda x, y: F.cross_entropy(model(x), y), optimizer, (x0, y0))
     for x, y in loader:
@@ -29,6 +33,7 @@ class GraphedStep:
         self.step_fn, self.optimizer = step_fn, optimizer
         self.captured, self.fallback_reason = False, None
         self.graph, self.static_loss = None, None
+        self.comm_in_graph = False  # True: the gradient allreduces are kernel nodes of the captured graph
         self.static_inputs = tuple(example_inputs)
         self.replays = 0
         if not enabled:
@@ -42,6 +47,7 @@ class GraphedStep:
                 self._capture(warmup_iters)
             except Exception as e:  # noqa: BLE001 - any capture failure must leave a working eager step behind
                 self._abandon(e)
+            self._agree_across_ranks()
 
     # ------------------------------------------------------------------------------------------------------------------
     def _fwd_bwd(self):
@@ -65,14 +71,38 @@ class GraphedStep:
         for p in missing:  # parameters unused by step_fn still need a static gradient for the optimizer
             p.grad = torch.zeros_like(p, memory_format=torch.preserve_format)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.static_loss = self._fwd_bwd()
+        try:
+            with torch.cuda.graph(self.graph):
+                # multi-GPU: the gradient buckets' allreduce kernels become nodes of this graph (forked onto a side stream
+                # as soon as a bucket's last gradient is recorded, joined before the capture ends)
+                self.comm_in_graph = bool(getattr(opt, '_begin_graph_capture', lambda: False)())
+                self.static_loss = self._fwd_bwd()
+                if self.comm_in_graph:
+                    opt._end_graph_capture()
+        finally:
+            if hasattr(opt, '_graph_capture'):
+                opt._graph_capture = None
         torch.cuda.synchronize()
         self.captured = True
 
+    def _agree_across_ranks(self):
+        """A graph with the allreduce kernels inside only works if EVERY rank replays the same graph: if capture failed (or
+        chose a different communication mode) anywhere, every rank drops to the eager step."""
+        ps = getattr(self.optimizer, 'process_set', None)
+        if ps is None or not ps.included() or (ps.size() or 1) <= 1:
+            return
+        from horovod_b200.torch import mpi_ops
+        mine = torch.tensor([1.0 if self.captured else 0.0, 1.0 if self.comm_in_graph else 0.0], dtype=torch.float32)
+        lo = mpi_ops.allreduce(mine, op=mpi_ops.Min, name='graphed_step.agree.min', process_set=ps)
+        hi = mpi_ops.allreduce(mine, op=mpi_ops.Max, name='graphed_step.agree.max', process_set=ps)
+        if self.captured and (lo[0] != hi[0] or lo[1] != hi[1]):
+            self._abandon(RuntimeError('CUDA graph capture did not succeed identically on every rank'))
+
     def _abandon(self, exc):
-        self.captured, self.graph = False, None
+        self.captured, self.graph, self.comm_in_graph = False, None, False
         self.optimizer._graph_mode = False
+        if hasattr(self.optimizer, '_graph_comm_captured'):
+            self.optimizer._graph_comm_captured = False
         self.fallback_reason = '%s: %s' % (type(exc).__name__, str(exc).splitlines()[0] if str(exc) else '')
         try:
             torch.cuda.synchronize()

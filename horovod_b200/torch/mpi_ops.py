@@ -58,6 +58,15 @@ def init(*args, **kwargs):
     """Initialises Horovod. Accepts `process_sets=[ProcessSet, ...]` (static registration) or "dynamic"."""
     global _handle_map
     _handle_map = {}
+    # before the native runtime spawns its cycle thread (threads inherit the affinity of their creator)
+    from horovod_b200.common.basics import _resolve_topology
+    from horovod_b200.common.util import bind_to_gpu_numa
+    try:
+        _lr = _resolve_topology()[2]
+        if torch.cuda.is_available():
+            bind_to_gpu_numa((_lr if _lr and _lr > 0 else 0) % max(1, torch.cuda.device_count()))
+    except Exception:  # noqa: BLE001
+        pass
     _basics.init(*args, **kwargs)
     _native()
     _setup_process_sets(_basics)
@@ -642,6 +651,25 @@ def symm_empty(shape, dtype=torch.float32, device=None, process_set=global_proce
     except RuntimeError as e:
         raise HorovodInternalError(e)
     return raw[:numel * itemsize].view(dtype).view(*shape)
+
+
+def captured_allreduce_(tensor, op=Average, prescale_factor=1.0, postscale_factor=1.0, process_set=global_process_set, max_ctas=0):
+    """In-place allreduce of a tensor allocated with `hvd.symm_empty` (or a view of one taken identically on every rank),
+    issued as ONE kernel on the CURRENT CUDA stream — no handle, no negotiation, no host synchronisation — so it can be
+    captured into a CUDA graph (`torch.cuda.graph`) together with the compute that produces and consumes the tensor.
+
+    Contract: every rank of the process set issues the same sequence of captured collectives (same tensors, same order);
+    the kernel's own cross-GPU flag barrier is the only synchronisation.  `hvd.GraphedStep` uses this to make a whole
+    data-parallel training step (forward, backward, gradient allreduce overlapped with backward) one graph launch.
+    Ops: Average / Sum / Min / Max / Product.  Returns the tensor."""
+    if op == Adasum:
+        raise NotImplementedError('captured_allreduce_ does not support op=Adasum')
+    try:
+        _native().captured_allreduce_(tensor, int(op), float(prescale_factor), float(postscale_factor),
+                                      process_set.process_set_id, int(max_ctas))
+    except (RuntimeError, ValueError) as e:
+        raise HorovodInternalError(e)
+    return tensor
 
 
 def symm_available(process_set=global_process_set):

@@ -65,6 +65,8 @@ class _DistributedOptimizer(torch.optim.Optimizer):
         self._fused = fused
         self._fused_steps = 0
         self._graph_mode = False  # set by hvd.GraphedStep: backward runs as a CUDA graph replay, hooks do not fire
+        self._graph_capture = None      # while hvd.GraphedStep captures: {'comm': side stream, 'ctas': n, 'launched': set()}
+        self._graph_comm_captured = False  # the captured graph contains the gradient allreduces (nothing left for step())
 
         self._handles = {}
         self._grad_accs = []
@@ -185,7 +187,8 @@ class _DistributedOptimizer(torch.optim.Optimizer):
                     flat = mpi_ops.symm_empty(total // itemsize, dtype=dtype, device=members[0][0].device, process_set=self.process_set)
                     flat.zero_()
                     bucket = {'flat': flat, 'params': [m[0] for m in members], 'pending': len(members),
-                              'name': 'bucket.%d' % len(self._buckets), 'handle': None, 'shadow': None, 'shadow_views': None}
+                              'name': 'bucket.%d' % len(self._buckets), 'handle': None, 'shadow': None, 'shadow_views': None,
+                              'offsets': {m[0]: m[1] for m in members}, 'views': {}}
                     if self._bucket_wire_dtype is not None and dtype == torch.float32:
                         shadow = mpi_ops.symm_empty(total // itemsize, dtype=self._bucket_wire_dtype, device=members[0][0].device,
                                                     process_set=self.process_set)
@@ -198,6 +201,7 @@ class _DistributedOptimizer(torch.optim.Optimizer):
                         if p.grad is not None:
                             view.copy_(p.grad)
                         p.grad = view
+                        bucket['views'][p] = view
                         self._p_to_bucket[p] = bucket
                     self._buckets.append(bucket)
             self._zero_copy = True
@@ -271,7 +275,11 @@ class _DistributedOptimizer(torch.optim.Optimizer):
     def _make_hook(self, p):
         def hook(*ignore):
             if self._graph_mode:
-                return  # (only runs while the graph is being captured) step() reduces every gradient after the replay
+                # hooks only run during warm-up and capture; while capturing, the last gradient of a bucket records the
+                # bucket's allreduce INTO the graph (on a forked side stream, so it overlaps the rest of backward)
+                if self._graph_capture is not None:
+                    self._graph_hook(p)
+                return
             if p in self._handles and self._handles[p][0] is not None:
                 if self._allreduce_delay[p] <= 0:
                     raise AssertionError(
@@ -283,9 +291,13 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             self._allreduce_delay[p] -= 1
             bucket = self._p_to_bucket.get(p)
             if bucket is not None:
-                if p.grad.data_ptr() != bucket['flat'].data_ptr() + self._bucket_offset(bucket, p):
-                    raise AssertionError('the gradient of a bucketed parameter was replaced (use optimizer.zero_grad(), '
-                                         'not p.grad = None, or construct DistributedOptimizer(..., zero_copy=False))')
+                if p.grad.is_sparse or p.grad.data_ptr() != bucket['flat'].data_ptr() + bucket['offsets'][p]:
+                    # model.zero_grad() (set_to_none=True is torch's default) or `p.grad = None` dropped the bucket view and
+                    # autograd allocated a fresh gradient: move it into the registered bucket and re-point p.grad, so the
+                    # reference idiom keeps working (one extra copy for that parameter; optimizer.zero_grad() avoids it)
+                    view = bucket['views'][p]
+                    view.copy_(p.grad.to_dense() if p.grad.is_sparse else p.grad)
+                    p.grad = view
                 self._handles[p] = ('bucket', None)
                 if self._allreduce_delay[p] == 0:
                     bucket['pending'] -= 1
@@ -304,11 +316,82 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             self._handles[p] = (handle, ctx)
         return hook
 
-    def _bucket_offset(self, bucket, p):
-        offs = bucket.get('offsets')
-        if offs is None:
-            offs = bucket['offsets'] = {q: q.grad.data_ptr() - bucket['flat'].data_ptr() for q in bucket['params']}
-        return offs[p]
+    # ---- gradient allreduce as CUDA-graph nodes (hvd.GraphedStep) --------------------------------------------------------
+    def _graph_capturable(self):
+        """The whole gradient reduction can live inside the captured step: every trainable parameter sits in a registered
+        zero-copy bucket, one backward per step, a reduction the in-place kernel implements.  Depends on the model and the
+        constructor arguments only, so every rank answers the same."""
+        if not (self._zero_copy and self._buckets and self.backward_passes_per_step == 1 and self.op in (Average, Sum)):
+            return False
+        if not self.process_set.included() or self.process_set.size() <= 1:
+            return False
+        if os.environ.get('HVD_GRAPH_COMM', '1') == '0':
+            return False
+        return all(p in self._p_to_bucket for p in self._requires_update)
+
+    def _begin_graph_capture(self):
+        """Called by hvd.GraphedStep right after stream capture began (on the capturing stream)."""
+        self._graph_comm_captured = False
+        if not self._graph_capturable():
+            return False
+        lo_pri, hi_pri = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, 'priority_range') else (0, -1)
+        self._graph_capture = {'comm': torch.cuda.Stream(priority=hi_pri), 'launched': set(),
+                               'ctas': int(os.environ.get('HVD_GRAPH_COMM_CTAS', '32')),
+                               'pending': {id(b): len(b['params']) for b in self._buckets}}
+        return True
+
+    def _graph_hook(self, p):
+        bucket = self._p_to_bucket.get(p)
+        if bucket is None:
+            return
+        cap = self._graph_capture
+        cap['pending'][id(bucket)] -= 1
+        if cap['pending'][id(bucket)] == 0:
+            self._graph_launch_bucket(bucket)
+
+    def _graph_launch_bucket(self, bucket):
+        cap = self._graph_capture
+        if self.op == Average:
+            prescale_factor, postscale_factor = 1.0 / self.gradient_predivide_factor, self.gradient_predivide_factor
+        else:
+            prescale_factor = postscale_factor = 1.0
+        comm = cap['comm']
+        comm.wait_stream(torch.cuda.current_stream())  # fork: everything recorded so far (this bucket's gradients) precedes it
+        with torch.cuda.stream(comm):
+            wire = bucket['flat']
+            if bucket.get('shadow') is not None:
+                wire = bucket['shadow']
+                wire.copy_(bucket['flat'])
+            mpi_ops.captured_allreduce_(wire, op=self.op, prescale_factor=prescale_factor, postscale_factor=postscale_factor,
+                                        process_set=self.process_set, max_ctas=cap['ctas'])
+        cap['launched'].add(id(bucket))
+
+    def _end_graph_capture(self):
+        """Before stream capture ends: buckets whose last hook never fired (parameters unused by the step) are reduced
+        now, then the capturing stream joins the communication stream."""
+        cap = self._graph_capture
+        if cap is None:
+            return
+        for bucket in self._buckets:
+            if id(bucket) not in cap['launched']:
+                self._graph_launch_bucket(bucket)
+        torch.cuda.current_stream().wait_stream(cap['comm'])
+        self._graph_capture = None
+        self._graph_comm_captured = True
+
+    def _adopt_missing_grads(self, bucket):
+        """A bucket is launched from synchronize() because some hook never fired: parameters whose gradient is None (dropped
+        by model.zero_grad() and not produced this step) contribute zeros and get their bucket view back."""
+        base = bucket['flat'].data_ptr()
+        for p in bucket['params']:
+            view = bucket['views'][p]
+            if p.grad is None:
+                if p not in self._handles:
+                    view.zero_()
+                p.grad = view
+            elif p.grad.is_sparse or p.grad.data_ptr() != base + bucket['offsets'][p]:
+                view.copy_(p.grad.to_dense() if p.grad.is_sparse else p.grad)
+                p.grad = view
 
     def _restore_shadows(self):
         """Reduced values of wire-dtype shadow buckets -> the fp32 gradients that p.grad points at."""
@@ -333,11 +416,21 @@ class _DistributedOptimizer(torch.optim.Optimizer):
         if self._graph_mode and self.process_set.size() == 1 and self.op in (Average, Sum):
             self._synchronized = True  # one rank: the reduction is the identity (prescale * postscale == 1)
             return
+        if self._graph_mode and self._graph_comm_captured:
+            # the replayed graph already reduced every bucket (captured_allreduce_ nodes): nothing to negotiate or launch
+            for bucket in self._buckets:
+                if bucket.get('shadow') is not None:
+                    bucket['shadow_fresh'] = True
+            if not _defer_shadow_copy:
+                self._restore_shadows()
+            self._synchronized = True
+            return
         if self._zero_copy:
             for bucket in self._buckets:
                 if bucket['handle'] is None:
                     # some gradient of this bucket was not produced on this rank (or accumulation is incomplete): reduce what
                     # is there so that all ranks stay in lock-step (missing gradients are zeros)
+                    self._adopt_missing_grads(bucket)
                     self._launch_bucket(bucket)
             for bucket in self._buckets:
                 synchronize(bucket['handle'])
@@ -448,66 +541,75 @@ def _find_duplicates(lst):
     return dups
 
 
-def _fused_step(opt):
-    """One multi-tensor kernel for the whole model when the wrapped optimizer is SGD or Adam/AdamW on CUDA."""
-    native = mpi_ops._native()
-    base = opt.__class__.__mro__[1] if len(opt.__class__.__mro__) > 1 else None
+def _fused_plan(opt):
+    """Pure eligibility pass of the fused optimizer step: returns the launch plan [(group, params, grads)] or None.
+    Nothing is mutated here, so a `None` leaves the wrapped optimizer's own step() as a clean fallback."""
     is_sgd = isinstance(opt, torch.optim.SGD)
     is_adam = isinstance(opt, (torch.optim.Adam, torch.optim.AdamW))
     if not (is_sgd or is_adam):
+        return None
+    grad_of = getattr(opt, '_grad_for_update', lambda q: q.grad)
+    plan = []
+    for group in opt.param_groups:
+        params = [p for p in group['params'] if p.grad is not None]
+        if not params:
+            continue
+        if group.get('maximize', False) or (is_adam and group.get('amsgrad', False)):
+            return None
+        if not all(p.is_cuda and not p.grad.is_sparse and mpi_ops._is_dense(p) and p.grad.stride() == p.stride() for p in params):
+            return None
+        by_dtype = {}
+        for p in params:
+            by_dtype.setdefault((p.dtype, grad_of(p).dtype), []).append(p)
+        if any(pd == torch.float32 and gd == torch.float16 for pd, gd in by_dtype):
+            return None  # no fp32-parameter / fp16-gradient kernel
+        for ps in by_dtype.values():
+            if is_sgd and group.get('momentum', 0.0) != 0.0:
+                have = [opt.state[p].get('momentum_buffer') is not None for p in ps]
+                if any(have) and not all(have):
+                    return None  # partially initialised momentum (parameters added later): let torch handle it
+            plan.append((group, ps, [grad_of(p) for p in ps]))
+    return plan
+
+
+def _fused_step(opt):
+    """One multi-tensor kernel for the whole model when the wrapped optimizer is SGD or Adam/AdamW on CUDA."""
+    native = mpi_ops._native()
+    plan = _fused_plan(opt)
+    if plan is None:
         return False
+    is_sgd = isinstance(opt, torch.optim.SGD)
     with torch.no_grad():
-        for group in opt.param_groups:
-            params = [p for p in group['params'] if p.grad is not None]
-            if not params:
-                continue
-            if not all(p.is_cuda and not p.grad.is_sparse and mpi_ops._is_dense(p) and p.grad.stride() == p.stride() for p in params):
-                return False
-            grad_of = getattr(opt, '_grad_for_update', lambda q: q.grad)
-            by_dtype = {}
-            for p in params:
-                by_dtype.setdefault((p.dtype, grad_of(p).dtype), []).append(p)
-            if any(pd == torch.float32 and gd == torch.float16 for pd, gd in by_dtype):
-                return False  # no fp32-parameter / fp16-gradient kernel
-            for (_, _), ps in by_dtype.items():
-                grads = [grad_of(p) for p in ps]
-                if is_sgd:
-                    mom = group.get('momentum', 0.0)
-                    bufs, first = [], False
-                    if mom != 0.0:
-                        for p in ps:
-                            st = opt.state[p]
-                            if st.get('momentum_buffer') is None:
-                                st['momentum_buffer'] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                                first = True
-                            bufs.append(st['momentum_buffer'])
-                        if first and any(opt.state[p].get('_hvd_init') for p in ps):
-                            return False
-                        for p in ps:
-                            opt.state[p]['_hvd_init'] = True
-                    if group.get('maximize', False):
-                        return False
-                    native.fused_sgd_step(ps, grads, bufs, float(group['lr']), float(mom), float(group.get('dampening', 0.0)),
-                                          float(group.get('weight_decay', 0.0)), bool(group.get('nesterov', False)), 1.0, first)
-                else:
-                    if group.get('amsgrad', False) or group.get('maximize', False):
-                        return False
-                    exp_avg, exp_avg_sq = [], []
-                    step = None
+        for group, ps, grads in plan:
+            if is_sgd:
+                mom = group.get('momentum', 0.0)
+                bufs, first = [], False
+                if mom != 0.0:
                     for p in ps:
                         st = opt.state[p]
-                        if len(st) == 0 or 'exp_avg' not in st:
-                            st['step'] = torch.tensor(0.0)
-                            st['exp_avg'] = torch.zeros_like(p, dtype=torch.float32, memory_format=torch.preserve_format)
-                            st['exp_avg_sq'] = torch.zeros_like(p, dtype=torch.float32, memory_format=torch.preserve_format)
-                        st['step'] = st['step'] + 1
-                        step = int(st['step'].item()) if torch.is_tensor(st['step']) else int(st['step'])
-                        exp_avg.append(st['exp_avg'])
-                        exp_avg_sq.append(st['exp_avg_sq'])
-                    b1, b2 = group['betas']
-                    adamw = isinstance(opt, torch.optim.AdamW) or bool(group.get('decoupled_weight_decay', False))
-                    native.fused_adam_step(ps, grads, exp_avg, exp_avg_sq, float(group['lr']), float(b1), float(b2),
-                                           float(group['eps']), float(group.get('weight_decay', 0.0)), step, 1.0, adamw)
+                        if st.get('momentum_buffer') is None:
+                            st['momentum_buffer'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                            first = True
+                        bufs.append(st['momentum_buffer'])
+                native.fused_sgd_step(ps, grads, bufs, float(group['lr']), float(mom), float(group.get('dampening', 0.0)),
+                                      float(group.get('weight_decay', 0.0)), bool(group.get('nesterov', False)), 1.0, first)
+            else:
+                exp_avg, exp_avg_sq = [], []
+                step = None
+                for p in ps:
+                    st = opt.state[p]
+                    if len(st) == 0 or 'exp_avg' not in st:
+                        st['step'] = torch.tensor(0.0)
+                        st['exp_avg'] = torch.zeros_like(p, dtype=torch.float32, memory_format=torch.preserve_format)
+                        st['exp_avg_sq'] = torch.zeros_like(p, dtype=torch.float32, memory_format=torch.preserve_format)
+                    st['step'] = st['step'] + 1
+                    step = int(st['step'].item()) if torch.is_tensor(st['step']) else int(st['step'])
+                    exp_avg.append(st['exp_avg'])
+                    exp_avg_sq.append(st['exp_avg_sq'])
+                b1, b2 = group['betas']
+                adamw = isinstance(opt, torch.optim.AdamW) or bool(group.get('decoupled_weight_decay', False))
+                native.fused_adam_step(ps, grads, exp_avg, exp_avg_sq, float(group['lr']), float(b1), float(b2),
+                                       float(group['eps']), float(group.get('weight_decay', 0.0)), step, 1.0, adamw)
     return True
 
 

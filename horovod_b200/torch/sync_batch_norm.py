@@ -33,14 +33,18 @@ class SyncBatchNorm(_BatchNorm):
                                     self.momentum)
 
     def forward(self, input):
-        if not input.is_cuda and size() > 1 and self.training:
-            return _SyncBatchNormCPU.apply(input, self.weight, self.bias, self.running_mean, self.running_var, self.eps,
-                                           self.momentum)
         self._check_input_dim(input)
         if self.training and self.track_running_stats:
             self.num_batches_tracked = self.num_batches_tracked + 1
         if not self.training and self.track_running_stats:
             return self._run_bn(input)
+        if not input.is_cuda and size() > 1:
+            # momentum=None means a cumulative moving average (torch.nn.BatchNorm semantics)
+            momentum = self.momentum
+            if momentum is None:
+                momentum = 1.0 / float(self.num_batches_tracked) if self.track_running_stats else 0.0
+            return _SyncBatchNormCPU.apply(input, self.weight, self.bias, self.running_mean, self.running_var, self.eps,
+                                           momentum)
         return self._maybe_run_sync_bn(input)
 
 
@@ -105,7 +109,8 @@ class _SyncBatchNormCPU(Function):
         invstd = torch.rsqrt(var + eps)
         if running_mean is not None:
             running_mean.mul_(1 - momentum).add_(momentum * mean)
-            running_var.mul_(1 - momentum).add_(momentum * var * n / (n - 1))
+            unbiased = var * n / (n - 1) if float(n) > 1 else var  # a single sample has no unbiased estimate
+            running_var.mul_(1 - momentum).add_(momentum * unbiased)
         shape = [1, c] + [1] * (input.dim() - 2)
         xhat = (input - mean.view(shape)) * invstd.view(shape)
         ctx.save_for_backward(xhat, weight, invstd, n)

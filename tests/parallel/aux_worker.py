@@ -48,7 +48,8 @@ elif mode == 'autotune':
         hs = [hvd.allreduce_async(x, op=hvd.Sum, name=f'at.{i}') for i in range(4)]
         for h in hs:
             hvd.synchronize(h)
-    print('AUTOTUNE PARAMS', json.dumps(hvd.tunable_params()), flush=True)
+    sys.stdout.write('AUTOTUNE PARAMS ' + json.dumps(hvd.tunable_params()) + '\n')  # one write: lines of two ranks must not interleave
+    sys.stdout.flush()
 elif mode == 'timeline':
     path = sys.argv[2]
     hvd.start_timeline(path, mark_cycles=True)

@@ -41,7 +41,12 @@ for n in (2, 4):
     dst = [torch.empty(1000 * n, device='cuda') for _ in range(n)]
     sp = (ctypes.c_uint64 * n)(*[t.data_ptr() for t in src])
     dp = (ctypes.c_uint64 * n)(*[t.data_ptr() for t in dst])
-    assert lib.hvd_sim_allgather(n, 0, 4000, sp, dp, 4) == 0
-    assert float(dst[0][-1]) == n - 1
+    rc = lib.hvd_sim_allgather(n, 0, 4000, sp, dp, 4)
+    assert rc == 0, rc
+    for r in range(n):
+        got = dst[r].view(n, 1000)
+        exp = torch.arange(n, device='cuda', dtype=torch.float32).view(n, 1).expand(n, 1000)
+        assert torch.equal(got, exp), ('allgather mismatch', n, r, got[:, 0].tolist(), got[:, -1].tolist(),
+                                       int((got != exp).sum()))
 torch.cuda.synchronize()
 print('SANITIZER TARGET OK')
