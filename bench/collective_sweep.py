@@ -37,10 +37,17 @@ if cuda:
 dev = torch.device('cuda', hvd.local_rank()) if cuda else torch.device('cpu')
 pg = None
 if args.nccl and cuda and size > 1:
+    # torch.distributed NCCL next to the hvd runtime, bootstrapped through the c10d store hvd.init() already uses (torchrun's
+    # agent store) — never a second TCP server
     import torch.distributed as dist
-    dist.init_process_group('nccl', rank=rank, world_size=size,
-                            init_method='tcp://%s:%d' % (os.environ.get('MASTER_ADDR', '127.0.0.1'), int(os.environ.get('MASTER_PORT', '29400')) + 7))
-    pg = dist
+    from horovod_b200.common.basics import _EmbeddedRendezvous
+    if _EmbeddedRendezvous.stores:
+        from datetime import timedelta
+        dist.init_process_group('nccl', store=dist.PrefixStore('collective_sweep', _EmbeddedRendezvous.stores[-1]), rank=rank,
+                                world_size=size, device_id=dev, timeout=timedelta(seconds=60))
+        pg = dist
+    elif rank == 0:
+        print('no c10d store (not launched by torchrun): NCCL arm skipped', flush=True)
 
 
 def timed(fn, iters):

@@ -106,6 +106,13 @@ def build_core(force=False, verbose=False):
     old = open(stamp_file).read() if os.path.exists(stamp_file) else ""
     if force or not os.path.exists(lib) or old != link_stamp:
         _run([NVCC] + ARCH + ["-shared", "-o", lib] + objs + ["-cudart", "static", "-lpthread", "-ldl", "-lrt"])
+        # libcuda is resolved lazily with dlsym (a CPU-only box must be able to load the library): a direct reference to a
+        # driver entry point would only fail at dlopen time on such a box, so fail the build instead
+        undef = [l.split()[-1] for l in _run(["nm", "-D", "--undefined-only", lib]).splitlines() if l.split()]
+        direct = sorted(u for u in undef if u.startswith("cu") and len(u) > 2 and u[2].isupper() and not u.startswith("cuda"))
+        if direct:
+            os.remove(lib)
+            raise RuntimeError("libhvd_core.so references CUDA driver symbols directly (use dlsym): " + ", ".join(direct))
         with open(stamp_file, "w") as f:
             f.write(link_stamp)
     return lib

@@ -353,7 +353,7 @@ class HorovodBasics(object):
         """Counters of the background thread: cycles, idle cycles, responses executed, kernels launched."""
         return {'cycles': int(self.lib.hvd_stat(0)), 'idle_cycles': int(self.lib.hvd_stat(1)),
                 'responses': int(self.lib.hvd_stat(2)), 'kernel_launches': int(self.lib.hvd_stat(3)),
-                'captured_collectives': int(self.lib.hvd_stat(4))}
+                'captured_collectives': int(self.lib.hvd_stat(4)), 'ipc_zero_copy_allreduces': int(self.lib.hvd_stat(5))}
 
     def metrics(self):
         """Monotonic counters of this rank since init(): {'allreduce': {'responses', 'tensors', 'bytes', 'on_gpu', 'errors'}, ...}
@@ -371,12 +371,13 @@ class HorovodBasics(object):
             if any(vals.values()):
                 out[buf.value.decode().lower()] = vals
         out['runtime'] = self.runtime_stats()
-        # host-path latency probes: mean microseconds per response since init (queue = enqueue -> cycle start, negotiate,
-        # execute = descriptor staging + launch + events + callbacks, total = enqueue -> completion callback)
+        # host-path latency probes, monotonic like every other counter (so `utils.metrics.Interval` can diff them): total
+        # nanoseconds and sample counts per stage — queue = enqueue -> its cycle starts, negotiate, execute = descriptor
+        # staging + launch + events + callbacks, total = enqueue -> completion callback; mean = ns / samples
         lat = {}
         for i, name in enumerate(('queue', 'negotiate', 'execute', 'total')):
-            cnt = int(lib.hvd_stat(20 + i))
-            lat[name] = {'mean_us': round(int(lib.hvd_stat(10 + i)) / cnt / 1e3, 2) if cnt else None, 'samples': cnt}
+            lat[name + '_ns'] = int(lib.hvd_stat(10 + i))
+            lat[name + '_samples'] = int(lib.hvd_stat(20 + i))
         out['latency'] = lat
         lib.hvd_host_path_count.restype = ctypes.c_ulonglong
         out['host_paths'] = {name: int(lib.hvd_host_path_count(i)) for i, name in enumerate(('shared_memory', 'two_level', 'base_transport'))}

@@ -137,6 +137,7 @@ unsigned long long hvd_stat(int which) {
     case 2: return e.responses_executed();
     case 3: return kern::KernelLaunchCount();
     case 4: return e.captured_launches();
+    case 5: return e.gpu_ops().ipc_launches();
     case 10: case 11: case 12: case 13: return e.latency_sum_ns(which - 10);
     case 20: case 21: case 22: case 23: return e.latency_count(which - 20);
     default: return 0;

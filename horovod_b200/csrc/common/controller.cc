@@ -135,6 +135,7 @@ ResponseList Controller::ComputeResponseList(bool shutdown_requested) {
     // rank (the OR bit is global) runs the cached response through the fusion-buffer kernel, where the joined rank
     // contributes zeros (the slow path does the same in ConstructResponse).
     if (status & kStatusJoined) resp.symm_key = -1;
+    resp.from_cache = true;
     auto it = pending_hits_.find(b);
     if (it != pending_hits_.end()) {
       resp.group_id = it->second.group_id;
@@ -396,6 +397,12 @@ Response Controller::ConstructResponse(const std::string& name, const std::vecto
   resp.root_rank = first.root_rank;
   resp.symm_key = first.symm_key;
   for (auto& q : requests) if (q.symm_key != first.symm_key) resp.symm_key = -1;  // zero-copy only if EVERY rank registered it identically
+  if (resp.symm_key < 0) {
+    // every rank offers an in-place plain allocation it can export over CUDA IPC (keys differ per rank by construction)
+    bool all_ipc = true;
+    for (auto& q : requests) if (q.symm_key > -2) all_ipc = false;
+    resp.symm_key = all_ipc ? -2 : -1;
+  }
   if ((int)requests.size() < set_size) resp.symm_key = -1;                         // joined ranks have no registered tensor
   resp.devices.assign(set_size, first.device);
   for (auto& q : requests) if (q.request_rank >= 0 && q.request_rank < set_size) resp.devices[q.request_rank] = q.device;
@@ -427,7 +434,7 @@ std::deque<Response> Controller::FuseResponses(std::deque<Response> responses, i
         bool compatible = n.type == r.type && n.dtype == r.dtype && n.devices == r.devices &&
                           n.prescale == r.prescale && n.postscale == r.postscale && n.reduce_op == r.reduce_op &&
                           n.root_rank == r.root_rank &&
-                          (!disable_group_fusion || n.group_id == r.group_id) && n.symm_key < 0 && r.symm_key < 0;
+                          (!disable_group_fusion || n.group_id == r.group_id) && n.symm_key == -1 && r.symm_key == -1;
         int64_t nb = compatible ? AlignedBytes(n) : 0;
         if (compatible && total + nb <= threshold) {
           total += nb;

@@ -13,6 +13,7 @@
 #include "../ops/cpu_ops.h"
 #include "../ops/nccl_baseline.h"
 #include "../symm/symm_memory.h"
+#include "../ops/ipc_registry.h"
 #include "env.h"
 #include "logging.h"
 #include "nvtx_op_range.h"
@@ -252,12 +253,25 @@ void Engine::BackgroundThread() {
     genv.wire_dtype = wire == "bf16" ? DataType::BFLOAT16 : wire == "fp16" ? DataType::FLOAT16 : DataType::FLOAT32;
     genv.symm_buffer_bytes = (size_t)EnvInt(HVD_SYMM_BUFFER_BYTES, 128ll << 20);
     genv.want_multicast = EnvBool("HVD_ENABLE_NVLS", true);
-    genv.pipelined = EnvBool("HVD_PIPELINED_ALLREDUCE", true);
+    genv.pipelined = EnvBool("HVD_PIPELINED_ALLREDUCE", false);
     genv.pipe_chunk_bytes = std::max<int64_t>(1 << 20, EnvInt("HVD_PIPE_CHUNK_BYTES", 4 << 20) / 4096 * 4096);
     genv.pipe_min_bytes = EnvInt("HVD_PIPE_MIN_BYTES", 32 << 20);
     genv.pipe_rblock_bytes = std::max<int64_t>(4096, EnvInt("HVD_PIPE_RBLOCK_BYTES", 16384) / 4096 * 4096);
     genv.large_msg_ctas = std::min<int64_t>(kern::kMaxCtas, std::max<int64_t>(4, EnvInt("HVD_LARGE_MSG_CTAS", 256)));
     genv.broadcast_multicast = EnvBool("HVD_BROADCAST_MULTICAST", true);
+    // on-the-fly IPC registration of plain in-place tensors (ops/ipc_registry.h); 0 disables
+    ipc_min_bytes_ = (genv.backend == "p2p" && EnvBool("HVD_IPC_REGISTRATION", true) && GpuContext::Get().Available())
+                         ? std::max<int64_t>(16, EnvInt("HVD_IPC_MIN_BYTES", 4 << 20)) : 0;
+    genv.ipc_max_ranks = (int)EnvInt("HVD_IPC_MAX_RANKS", 2);
+    genv.dual_lane = EnvBool("HVD_DUAL_LANE_ALLREDUCE", true);
+    genv.dual_lane_min_bytes = EnvInt("HVD_DUAL_LANE_MIN_BYTES", 64 << 20);
+    genv.zero_copy_nvls_min_bytes = EnvInt("HVD_ZERO_COPY_NVLS_MIN_BYTES", 1 << 20);
+    genv.calibrate = EnvBool("HVD_CALIBRATE", true) && !EnvBool(HOROVOD_AUTOTUNE, false);
+    genv.on_calibrated = [this](int64_t oneshot_max, int64_t nvls_min) {
+      // measured crossovers replace the built-in defaults unless the user pinned a value
+      if (!EnvIsSet(HVD_ONESHOT_MAX_BYTES)) params_.SetOneshotMaxBytes(oneshot_max);
+      if (!EnvIsSet(HVD_NVLS_MIN_BYTES)) params_.SetNvlsMinBytes(nvls_min);
+    };
     gpu_ops_.reset(new GpuOps(genv));
 
     // ---- GPU / NVLink topology discovery (new relative to the reference) ----
@@ -766,6 +780,9 @@ Status Engine::EnqueueAllreduces(std::vector<std::shared_ptr<TensorTableEntry>>&
       int idx = -1;
       if (team && (e->bytes() % 16) == 0 && team->FindRegion(e->input, e->bytes(), nullptr, &off, &idx) && (off % 16) == 0)
         q.symm_key = ((int64_t)idx << 44) | off;
+      else if (ipc_min_bytes_ > 0 && (int64_t)e->bytes() >= ipc_min_bytes_ && (e->bytes() % 16) == 0 && ((uintptr_t)e->input % 16) == 0 &&
+               ps->set_size() > 1)
+        q.symm_key = IpcKeyFor(e->input);  // plain allocation: candidate for on-the-fly IPC registration (<= -2, or -1)
     }
     msgs.push_back(std::move(q));
   }

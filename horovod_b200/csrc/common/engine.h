@@ -157,6 +157,7 @@ class Engine {
   std::atomic<uint64_t> cycles_{0}, fast_cycles_{0}, responses_{0};
   std::atomic<uint64_t> op_metrics_[kMetricTypes * kPerType] = {};
   std::atomic<uint64_t> captured_launches_{0};
+  int64_t ipc_min_bytes_ = 0;  // plain in-place GPU tensors of at least this size are offered for IPC registration (0 = off)
   std::atomic<uint64_t> lat_sum_[kLatKinds] = {}, lat_cnt_[kLatKinds] = {};
   uint64_t cycle_start_ns_ = 0;
   void NoteLatency(int k, uint64_t ns) { lat_sum_[k].fetch_add(ns, std::memory_order_relaxed); lat_cnt_[k].fetch_add(1, std::memory_order_relaxed); }

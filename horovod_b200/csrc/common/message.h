@@ -56,7 +56,9 @@ struct Request {
   ReduceOp reduce_op = ReduceOp::SUM;
   int32_t group_id = -1;
   int32_t group_size = 0;
-  int64_t symm_key = -1;  // (region << 44 | offset) when the tensor lives in registered symmetric memory, else -1
+  // >= 0: (region << 44 | offset), the tensor lives in registered symmetric memory; <= -2: per-rank key of a plain device
+  // allocation that can be IPC-registered on the fly (ops/ipc_registry.h); -1: neither
+  int64_t symm_key = -1;
   void Serialize(ByteWriter& w) const;
   static Request Parse(ByteReader& r);
 };
@@ -89,7 +91,9 @@ struct Response {
   int32_t last_joined_rank = -1;
   int32_t root_rank = 0;
   int32_t group_id = -1;              // not serialised beyond fusion decisions
-  int64_t symm_key = -1;              // >= 0: every rank holds this tensor at the same place of the same registered region
+  int64_t symm_key = -1;              // >= 0: every rank holds this tensor at the same place of the same registered region;
+                                      // -2: every rank holds it in an IPC-registrable plain allocation (in place)
+  bool from_cache = false;            // local, not serialised: replayed from the response cache (no rank's tensor moved)
   int64_t payload_bytes = 0;          // fusion accounting: bytes this response moves through the fusion / symmetric buffer
   void Serialize(ByteWriter& w) const;
   static Response Parse(ByteReader& r);

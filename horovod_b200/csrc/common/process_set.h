@@ -16,6 +16,7 @@
 namespace hvd {
 
 class SymmTeam;
+class IpcRegistry;
 struct NcclComm;
 
 struct ProcessSet {
@@ -30,6 +31,7 @@ struct ProcessSet {
   std::shared_ptr<SymmTeam> team;
   mutable std::mutex team_mu;  // `team` is published by the background thread, read by enqueueing threads
   bool team_tried = false;
+  std::shared_ptr<IpcRegistry> ipc;      // peer mappings of ordinary allocations (ops/ipc_registry.h), cycle thread only
   std::shared_ptr<NcclComm> nccl;
   bool nccl_tried = false;
   // multi-host sets: intra-host peer-mapped team + cross-host communicator of the hierarchical GPU allreduce

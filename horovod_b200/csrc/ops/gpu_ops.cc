@@ -1,5 +1,7 @@
 #include "gpu_ops.h"
+#include <sys/stat.h>
 #include <unistd.h>
+#include <sstream>
 #include <algorithm>
 #include <cstring>
 #include "../common/env.h"
@@ -7,6 +9,7 @@
 #include "../kernels/p2p_kernels.h"
 #include "../symm/symm_memory.h"
 #include "cpu_ops.h"
+#include "ipc_registry.h"
 #include "nccl_baseline.h"
 
 namespace hvd {
@@ -52,6 +55,20 @@ GpuContext::PerDevice& GpuContext::Dev(int device) {
 }
 
 cudaStream_t GpuContext::Stream(int device) { std::lock_guard<std::mutex> l(mu_); return Dev(device).stream; }
+cudaStream_t GpuContext::AuxStream(int device) {
+  std::lock_guard<std::mutex> l(mu_);
+  PerDevice& d = Dev(device);
+  if (!d.aux_stream) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    cudaStreamCreateWithPriority(&d.aux_stream, cudaStreamNonBlocking, hi);
+    cudaEventCreateWithFlags(&d.fork_ev, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&d.join_ev, cudaEventDisableTiming);
+  }
+  return d.aux_stream;
+}
+cudaEvent_t GpuContext::ForkEvent(int device) { AuxStream(device); std::lock_guard<std::mutex> l(mu_); return Dev(device).fork_ev; }
+cudaEvent_t GpuContext::JoinEvent(int device) { AuxStream(device); std::lock_guard<std::mutex> l(mu_); return Dev(device).join_ev; }
 
 SharedEvent* GpuContext::NewEvent(int device, int refs) {
   std::lock_guard<std::mutex> l(mu_);
@@ -124,6 +141,9 @@ void GpuContext::Reset() {
     cudaSetDevice(kv.first);
     if (kv.second.pinned) cudaFreeHost(kv.second.pinned);
     if (kv.second.stream) { cudaStreamSynchronize(kv.second.stream); cudaStreamDestroy(kv.second.stream); }
+    if (kv.second.aux_stream) { cudaStreamSynchronize(kv.second.aux_stream); cudaStreamDestroy(kv.second.aux_stream); }
+    if (kv.second.fork_ev) cudaEventDestroy(kv.second.fork_ev);
+    if (kv.second.join_ev) cudaEventDestroy(kv.second.join_ev);
     for (auto e : kv.second.pool) cudaEventDestroy(e);
     if (kv.second.host_ring) cudaFreeHost(kv.second.host_ring);
     if (kv.second.dev_ring) cudaFree(kv.second.dev_ring);
@@ -197,6 +217,8 @@ std::shared_ptr<SymmTeam> GpuOps::EnsureTeam(ProcessSet& ps, int device) {
   if (ps.team) ps.team->set_timeout_seconds(EnvDouble("HVD_KERNEL_TIMEOUT_SECONDS", 60.0));
   if (ps.team) LOG(INFO) << "process set " << ps.id << ": symmetric team of " << ps.team->nranks() << " GPUs, backend "
                  << ps.team->backend() << ", 2 x " << (ps.team->buffer_bytes() >> 20) << " MiB";
+  // (same decision on every rank: a team exists everywhere or nowhere, the flags come from the shared environment)
+  if (ps.team && ps.id == 0 && env_.calibrate && env_.variant == "auto") Calibrate(ps, *ps.team, device);
   return ps.team;
 }
 
@@ -340,7 +362,8 @@ bool GpuOps::BuildInplaceArgs(SymmTeam& team, const void* ptr, int64_t bytes, Da
   ia.scale = prescale * postscale;
   ia.op = (int)op;
   ia.dtype = (int)dtype;
-  ia.use_multicast = (ia.mc && sum_like && env_.variant != "twoshot" && (n >= 4 || env_.variant == "nvls") && bytes >= env_.params->nvls_min_bytes &&
+  // (the crossover of THIS kernel — no pack / unpack around the NVLink phase — is not the packed kernels' nvls_min_bytes)
+  ia.use_multicast = (ia.mc && sum_like && env_.variant != "twoshot" && (n >= 4 || env_.variant == "nvls") && bytes >= env_.zero_copy_nvls_min_bytes &&
                       (dtype == DataType::FLOAT32 || dtype == DataType::FLOAT16 || dtype == DataType::BFLOAT16)) ? 1 : 0;
   ia.ctas = (int)std::max<int64_t>(1, std::min<int64_t>(max_ctas, (bytes + 4096ll * n - 1) / (4096ll * n)));
   *out = ia;
@@ -366,6 +389,117 @@ Status GpuOps::CapturedAllreduce(ProcessSet& ps, void* ptr, int64_t bytes, DataT
   cudaError_t ce = kern::LaunchInplaceAllreduce(team->Params(0, kern::kGraphChannel), ia, stream);
   if (ce != cudaSuccess) return Status::UnknownError(std::string("captured allreduce launch failed: ") + cudaGetErrorString(ce));
   return Status::OK();
+}
+
+// CTAs of a fused allreduce launch.  Small messages are latency bound (few CTAs = cheap flag barrier, SMs left to compute);
+// >= 64 MiB of plain tensors are bound by the local pack / unpack phases, which need two CTAs per SM (ncu: 12.5 % warps
+// active at one).
+int GpuOps::CtasFor(int variant, int64_t seg_bytes, int n) const {
+  const TunableParams& tp = *env_.params;
+  const int64_t per = variant == kern::kOneShot ? 8192 : (int64_t)4096 * n;  // >= 2 rows (one-shot) or one row per rank (two-shot) per CTA
+  const int64_t big_ctas = env_.large_msg_ctas;
+  const int64_t cap_ctas = seg_bytes <= (1 << 20) ? std::min<int64_t>(tp.comm_ctas, 16)
+                         : seg_bytes <= (16 << 20) ? std::min<int64_t>(tp.comm_ctas, 64)
+                         : seg_bytes < (64 << 20) ? tp.comm_ctas : std::max<int64_t>(tp.comm_ctas, big_ctas);
+  return (int)std::max<int64_t>(1, std::min<int64_t>(cap_ctas, (seg_bytes + per - 1) / per));
+}
+
+// Measures, on THIS box and team, where the allreduce variants cross over ("variant picked per message size
+// from measured bus bandwidth"): every rank runs the same short sequence of real launches on scratch tensors, rank 0's
+// device-timed results decide, the decision is broadcast and cached per (GPU, team size, NVLS) so later jobs skip the
+// ~10 ms measurement.  Collective over the set's transport; runs once, on the cycle thread, right after team creation.
+void GpuOps::Calibrate(ProcessSet& ps, SymmTeam& team, int device) {
+  Transport* t = ps.transport.get();
+  const int n = team.nranks(), me = t->rank();
+  if (n < 2) return;
+  cudaDeviceProp prop {};
+  cudaGetDeviceProperties(&prop, device);
+  std::string gpu = prop.name;
+  for (auto& c : gpu) if (!isalnum((unsigned char)c)) c = '_';
+  const char* home = getenv("HOME");
+  const std::string dir = EnvStr("HVD_CACHE_DIR", std::string(home ? home : "/tmp") + "/.cache/horovod_b200");
+  const std::string path = dir + "/crossover_v2_" + gpu + "_n" + std::to_string(n) + "_mc" + (team.has_multicast() ? "1" : "0") + ".txt";
+  int64_t vals[3] = {0, 0, 0};  // found, oneshot_max_bytes, nvls_min_bytes
+  if (me == 0 && EnvBool("HVD_CALIBRATION_CACHE", true)) {
+    if (FILE* f = fopen(path.c_str(), "r")) {
+      long long a = 0, b = 0;
+      if (fscanf(f, "%lld %lld", &a, &b) == 2 && a >= 0 && b >= 0) { vals[0] = 1; vals[1] = a; vals[2] = b; }
+      fclose(f);
+    }
+  }
+  t->Bcast(vals, sizeof vals, 0);
+  if (!vals[0]) {
+    GpuContext& ctx = GpuContext::Get();
+    cudaStream_t s = ctx.Stream(device);
+    const std::vector<int64_t> sizes = {32 << 10, 128 << 10, 512 << 10, 2 << 20, 8 << 20, 32 << 20};
+    const int64_t maxb = std::min<int64_t>(sizes.back(), (int64_t)team.buffer_bytes() / 128 * 128);
+    char* buf = nullptr;
+    const bool mem_ok = cudaMalloc((void**)&buf, (size_t)maxb) == cudaSuccess;
+    uint64_t okw = mem_ok ? 1 : 0;
+    t->AllreduceBits(&okw, 1, nullptr, 0);
+    if (!okw) { if (buf) cudaFree(buf); cudaGetLastError(); return; }
+    cudaMemsetAsync(buf, 0, (size_t)maxb, s);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const bool nvls_ok = team.has_multicast() && n >= 4;
+    const int variants[3] = {kern::kOneShot, kern::kTwoShot, kern::kNvls};
+    std::vector<double> us(sizes.size() * 3, 1e30);
+    for (size_t si = 0; si < sizes.size(); ++si) {
+      const int64_t bytes = std::min(sizes[si], maxb);
+      for (int vi = 0; vi < 3; ++vi) {
+        if (variants[vi] == kern::kNvls && !nvls_ok) continue;
+        kern::AllreduceArgs a {};
+        a.ndesc = 1; a.descs = nullptr;
+        a.inline_descs[0].in = buf; a.inline_descs[0].out = buf; a.inline_descs[0].offset = 0; a.inline_descs[0].count = bytes / 4;
+        a.total_bytes = bytes; a.reduce_lo = 0; a.reduce_hi = bytes;
+        a.prescale = 1.0; a.postscale = 1.0; a.op = (int)ReduceOp::SUM; a.dtype = (int)DataType::FLOAT32; a.wire_dtype = (int)DataType::FLOAT32;
+        a.variant = variants[vi];
+        a.ctas = CtasFor(a.variant, bytes, n);
+        const int warm = 2, iters = 6;
+        bool ok = true;
+        for (int it = 0; it < warm + iters && ok; ++it) {
+          if (it == warm) cudaEventRecord(e0, s);
+          ok = kern::LaunchAllreduce(team.Params(team.NextSlot()), a, s) == cudaSuccess;
+        }
+        cudaEventRecord(e1, s);
+        if (cudaStreamSynchronize(s) != cudaSuccess || !ok) { cudaGetLastError(); continue; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        us[si * 3 + vi] = ms * 1e3 / iters;
+      }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(buf);
+    if (team.abort_state() != 0) return;  // a barrier timed out: keep the defaults (the next real op reports the failure)
+    if (me == 0) {
+      int64_t oneshot_max = 0, nvls_min = 0;
+      bool nvls_found = false;
+      std::ostringstream tab;
+      for (size_t si = 0; si < sizes.size(); ++si) {
+        const double t1 = us[si * 3], t2 = us[si * 3 + 1], t3 = us[si * 3 + 2];
+        tab << " " << (sizes[si] >> 10) << "K:" << (int)(t1 + 0.5) << "/" << (int)(t2 + 0.5) << "/" << (t3 > 1e29 ? -1 : (int)(t3 + 0.5));
+        if (oneshot_max == (si ? sizes[si - 1] : 0) && t1 <= std::min(t2, t3) * 1.03) oneshot_max = sizes[si];  // contiguous prefix
+        if (!nvls_found && t3 < 1e29 && t3 <= t2) { nvls_min = sizes[si]; nvls_found = true; }
+      }
+      if (!nvls_found) nvls_min = nvls_ok ? (64ll << 20) : (1ll << 60);  // not faster in the measured range / unavailable
+      if (oneshot_max == 0) oneshot_max = 4096;
+      vals[1] = oneshot_max; vals[2] = nvls_min;
+      LOG(INFO) << "allreduce variant calibration on " << n << " x " << prop.name << " (us one-shot/two-shot/NVLS):" << tab.str()
+                << " -> one-shot up to " << oneshot_max << " B, NVLS from " << nvls_min << " B";
+      if (EnvBool("HVD_CALIBRATION_CACHE", true)) {
+        std::string cmd_dir = dir;
+        for (size_t i = 1; i <= cmd_dir.size(); ++i)
+          if (i == cmd_dir.size() || cmd_dir[i] == '/') { std::string sub = cmd_dir.substr(0, i); mkdir(sub.c_str(), 0755); }
+        if (FILE* f = fopen((path + ".tmp").c_str(), "w")) {
+          fprintf(f, "%lld %lld\n", (long long)oneshot_max, (long long)nvls_min);
+          fclose(f);
+          rename((path + ".tmp").c_str(), path.c_str());
+        }
+      }
+    }
+    t->Bcast(vals, sizeof vals, 0);
+  }
+  if (env_.on_calibrated) env_.on_calibrated(vals[1], vals[2]);
 }
 
 std::string GpuOps::Describe(ProcessSet& ps) {
@@ -419,14 +553,73 @@ Status GpuOps::Allreduce(ProcessSet& ps, Entries& es, const Response& r, int dev
           return FinishEvent(device, s, es.size(), done);
         }
       }
+      // ---- plain tensor, in place, IPC-registrable on every rank (negotiated symm_key == -2): zero-copy P2P two-shot on
+      //      the peers' mappings of each other's ordinary allocations ----
+      if (r.symm_key == -2 && pieces.size() == 1 && es[0] && pieces[0].in == pieces[0].out && env_.variant != "oneshot") {
+        const bool sum_like = r.reduce_op == ReduceOp::SUM || r.reduce_op == ReduceOp::AVERAGE;
+        const bool nvls_better = sum_like && team->has_multicast() && n > env_.ipc_max_ranks &&
+                                 (r.dtype == DataType::FLOAT32 || r.dtype == DataType::FLOAT16 || r.dtype == DataType::BFLOAT16);
+        if (!nvls_better) {
+          if (!ps.ipc) ps.ipc = std::make_shared<IpcRegistry>();
+          const int64_t bytes = pieces[0].count * (int64_t)esz;
+          // fresh response (same on every rank): the collective moment to (re)exchange handles; cached response: no rank's
+          // tensor moved since the exchange recorded under this name (a moved tensor invalidates the cache entry)
+          const IpcRegistry::Entry* ent = r.from_cache ? ps.ipc->Find(es[0]->name)
+                                                       : &ps.ipc->Exchange(ps.transport.get(), es[0]->name, pieces[0].in, (size_t)bytes);
+          if (ent && ent->my_ptr != pieces[0].in) ent = nullptr;
+          if (ent && ent->usable && (sum_like || (r.prescale == 1.0 && r.postscale == 1.0))) {
+            kern::InplaceArgs ia {};
+            for (int p = 0; p < n; ++p) ia.ptr[p] = ent->ptr[p];
+            ia.mc = nullptr; ia.bytes = bytes; ia.scale = r.prescale * r.postscale; ia.op = (int)r.reduce_op; ia.dtype = (int)r.dtype;
+            ia.use_multicast = 0;
+            ia.ctas = (int)std::max<int64_t>(1, std::min<int64_t>(env_.params->comm_ctas, (bytes + 4096ll * n - 1) / (4096ll * n)));
+            kern::CommParams cp = team->Params(team->NextSlot());
+            if (env_.timeline && env_.timeline->Initialized()) env_.timeline->ActivityStartAll(es, HVD_ACT_P2P_ALLREDUCE_TWOSHOT);
+            cudaError_t ce = kern::LaunchInplaceAllreduce(cp, ia, s);
+            if (ce == cudaSuccess) {
+              ipc_launches_.fetch_add(1, std::memory_order_relaxed);
+              ctx.TempFreeAll(device, s);
+              return FinishEvent(device, s, es.size(), done);
+            }
+            cudaGetLastError();  // e.g. a dtype the in-place kernel does not implement: fall through to the packed path
+          }
+        }
+      }
       // wire dtype: optional in-kernel compression of fp32 sums
       DataType wire = r.dtype;
       if (r.dtype == DataType::FLOAT32 && (env_.wire_dtype == DataType::BFLOAT16 || env_.wire_dtype == DataType::FLOAT16) &&
           (r.reduce_op == ReduceOp::SUM || r.reduce_op == ReduceOp::AVERAGE))
         wire = env_.wire_dtype;
       const int64_t wsz = (int64_t)DataTypeSize(wire);
-      const int64_t cap = (int64_t)team->buffer_bytes() / 128 * 128;
+      int64_t cap = (int64_t)team->buffer_bytes() / 128 * 128;
       const TunableParams& tp = *env_.params;
+      // ---- large fused messages of plain tensors: TWO LANES.  The three-phase kernel is pack (HBM) -> NVLink phase -> unpack
+      // (HBM) back to back, so the links idle while it packs and HBM idles while it reduces (8 x B200, 1 GiB: 2.98 ms vs
+      // 2.24 ms for the pure NVLink phase of the zero-copy kernel).  The message is cut into segments that alternate
+      // between two streams — lane 0 = the hvd stream on channel 0 / buffer slot 0, lane 1 = an auxiliary stream on its
+      // own barrier channel / slot 1 — so one lane's pack and unpack run under the other lane's NVLink phase.  No
+      // fine-grained hand-offs: the overlap comes from two ordinary kernels being resident together (2 x 128 CTAs <= 296
+      // slots).  Only the two-barrier variants (two-shot / NVLS) may reuse a slot back to back: after barrier 2 nobody reads
+      // a peer's buffer any more.
+      int64_t fused_total = 0;
+      for (auto& p : pieces) fused_total += Align128(p.count * wsz);
+      const bool dual = env_.dual_lane && env_.variant != "oneshot" && fused_total >= env_.dual_lane_min_bytes && !env_.pipelined;
+      cudaStream_t lane_stream[2] = {s, s};
+      if (dual) {
+        lane_stream[1] = ctx.AuxStream(device);
+        const int64_t seg = std::max<int64_t>(16ll << 20, std::min<int64_t>(64ll << 20, (fused_total / 8 + 127) / 128 * 128));
+        cap = std::min(cap, seg);
+        // fork: the auxiliary lane starts after everything already queued on the hvd stream (earlier ops may still own slot 1)
+        HVD_CUDA(cudaEventRecord(ctx.ForkEvent(device), s));
+        HVD_CUDA(cudaStreamWaitEvent(lane_stream[1], ctx.ForkEvent(device), 0));
+        WaitReady(es, lane_stream[1]);
+      }
+      int lane = 0;
+      // lane 0 takes the slot this op would have used anyway, lane 1 the other one — which the PREVIOUS op used, possibly
+      // with a one-barrier kernel a slow peer is still reading from: lane 1 therefore starts only after lane 0's first
+      // kernel (whose barrier proves every rank has left the previous op)
+      const int first_slot = dual ? team->NextSlot() : 0;
+      bool lane1_gated = false;
       // split into segments that fit the symmetric buffer
       std::vector<kern::TensorDesc> descs;
       int64_t seg_bytes = 0;
@@ -446,7 +639,7 @@ Status GpuOps::Allreduce(ProcessSet& ps, Entries& es, const Response& r, int dev
         else if (env_.variant == "twoshot") variant = kern::kTwoShot;
         else if (env_.variant == "nvls" && nvls_ok) variant = kern::kNvls;
         else {
-          if (seg_bytes <= tp.oneshot_max_bytes) variant = kern::kOneShot;
+          if (seg_bytes <= tp.oneshot_max_bytes && !dual) variant = kern::kOneShot;
           else if (nvls_ok && n >= 4 && seg_bytes >= tp.nvls_min_bytes) variant = kern::kNvls;  // in-switch reduction pays off from 4 GPUs (measured: slower than two-shot at N=2)
         }
         // opt-in: software-pipelined pack / NVLS / unpack for large segments of plain tensors (docs/roadmap.md B1)
@@ -463,31 +656,31 @@ Status GpuOps::Allreduce(ProcessSet& ps, Entries& es, const Response& r, int dev
           a.pipe_use_nvls = 1;
         }
         a.variant = variant;
-        int64_t per = variant == kern::kOneShot ? 8192 : (int64_t)4096 * n;  // >= 2 rows (one-shot) or one row per rank (two-shot) per CTA
-        // small messages are latency bound (few CTAs = cheap barrier, SMs left to compute); large ones need many loads in flight
-        // >= 64 MiB of plain (unregistered) tensors: the local pack / unpack phases are HBM-latency bound at one CTA per
-        // SM (ncu: 12.5 % warps active, 1.3 TB/s), so go to two CTAs per SM
+        a.ctas = CtasFor(variant, seg_bytes, n);
         const int64_t big_ctas = env_.large_msg_ctas;
-        const int64_t cap_ctas = seg_bytes <= (1 << 20) ? std::min<int64_t>(tp.comm_ctas, 16)
-                               : seg_bytes <= (16 << 20) ? std::min<int64_t>(tp.comm_ctas, 64)
-                               : seg_bytes < (64 << 20) ? tp.comm_ctas : std::max<int64_t>(tp.comm_ctas, big_ctas);
-        a.ctas = (int)std::max<int64_t>(1, std::min<int64_t>(cap_ctas, (seg_bytes + per - 1) / per));
+        if (dual) a.ctas = (int)std::max<int64_t>(8, std::min<int64_t>(big_ctas / 2, kern::kMaxCtas / 2));
         if (variant == kern::kPipelined) a.ctas = (int)std::min<int64_t>(kern::kMaxCtas, std::max<int64_t>(tp.comm_ctas, big_ctas)) / 4 * 4;
         if (a.ndesc <= kern::kInlineDescs) {
           memcpy(a.inline_descs, descs.data(), descs.size() * sizeof(kern::TensorDesc));
           a.descs = nullptr;
         } else {
-          a.descs = (const kern::TensorDesc*)ctx.Stage(device, descs.data(), descs.size() * sizeof(kern::TensorDesc), s);
+          a.descs = (const kern::TensorDesc*)ctx.Stage(device, descs.data(), descs.size() * sizeof(kern::TensorDesc), lane_stream[lane]);
           if (!a.descs) return Status::UnknownError("descriptor table too large");
         }
-        kern::CommParams cp = team->Params(team->NextSlot());
+        kern::CommParams cp = dual ? team->Params(first_slot ^ lane, lane == 0 ? 0 : kern::kAuxChannel) : team->Params(team->NextSlot());
+        if (dual && lane == 1 && !lane1_gated) {
+          cudaStreamWaitEvent(lane_stream[1], ctx.ForkEvent(device), 0);  // re-recorded below, after lane 0's first kernel
+          lane1_gated = true;
+        }
         if (env_.timeline && env_.timeline->Initialized())
           env_.timeline->ActivityStartAll(es, variant == kern::kOneShot ? HVD_ACT_P2P_ALLREDUCE_ONESHOT
                                               : variant == kern::kNvls ? HVD_ACT_P2P_ALLREDUCE_NVLS : HVD_ACT_P2P_ALLREDUCE_TWOSHOT);
-        cudaError_t ce = kern::LaunchAllreduce(cp, a, s);
+        cudaError_t ce = kern::LaunchAllreduce(cp, a, lane_stream[lane]);
         if (ce != cudaSuccess) return Status::UnknownError(std::string("allreduce kernel launch failed: ") + cudaGetErrorString(ce));
         descs.clear();
         seg_bytes = 0;
+        if (dual && lane == 0 && !lane1_gated) cudaEventRecord(ctx.ForkEvent(device), s);  // "lane 0's first kernel is done"
+        if (dual) lane ^= 1;
         return Status::OK();
       };
       for (auto& p : pieces) {
@@ -506,6 +699,10 @@ Status GpuOps::Allreduce(ProcessSet& ps, Entries& es, const Response& r, int dev
       }
       st = flush();
       if (!st.ok()) return st;
+      if (dual) {  // join: the completion event (recorded on the hvd stream) covers the auxiliary lane
+        HVD_CUDA(cudaEventRecord(ctx.JoinEvent(device), lane_stream[1]));
+        HVD_CUDA(cudaStreamWaitEvent(s, ctx.JoinEvent(device), 0));
+      }
     }
   }
   ctx.TempFreeAll(device, s);

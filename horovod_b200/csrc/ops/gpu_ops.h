@@ -8,6 +8,7 @@
 // ops/nccl_operations.{h,cc} (NCCL ops).
 #pragma once
 #include <atomic>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -36,6 +37,10 @@ class GpuContext {
   bool Available();
   int DeviceCount();
   cudaStream_t Stream(int device);
+  // second private stream of the device (lane 1 of the dual-lane large-message allreduce) and its fork / join events
+  cudaStream_t AuxStream(int device);
+  cudaEvent_t ForkEvent(int device);
+  cudaEvent_t JoinEvent(int device);
   SharedEvent* NewEvent(int device, int refs);
   void Release(SharedEvent* e);
   // Copies a small host table to device memory on `s` (pinned ring -> device ring).
@@ -50,6 +55,8 @@ class GpuContext {
  private:
   struct PerDevice {
     cudaStream_t stream = nullptr;
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
     std::vector<cudaEvent_t> pool;
     char* host_ring = nullptr; char* dev_ring = nullptr; size_t ring_off = 0;
     std::vector<void*> temps;
@@ -72,10 +79,23 @@ struct GpuOpEnv {
   size_t symm_buffer_bytes = 128ull << 20;
   bool want_multicast = true;
   // software-pipelined allreduce of large plain (unregistered) tensors: pack / reduce / unpack CTAs on a chunk ring
-  bool pipelined = true;
+  bool pipelined = false;  // opt-in: measured 8 x B200: 328 GB/s (4 MiB chunks) .. 455 GB/s (16 MiB) vs 630 GB/s for the three-phase kernel
   int64_t pipe_chunk_bytes = 4 << 20, pipe_min_bytes = 32 << 20, pipe_rblock_bytes = 16384;
   int64_t large_msg_ctas = 256;   // CTAs for >= 64 MiB fused messages (two per SM)
   bool broadcast_multicast = true;
+  // large fused messages of plain tensors alternate between two streams / barrier channels / buffer slots so that one
+  // lane's pack + unpack (HBM) overlap the other lane's NVLink phase
+  bool dual_lane = true;
+  int64_t dual_lane_min_bytes = 64 << 20;
+  // teams of up to this many ranks reduce IPC-registered plain tensors in place with the P2P two-shot kernel; larger
+  // teams keep the software-pipelined NVLS kernel for sums (in-switch reduction beats P2P there) and use IPC only for
+  // MIN / MAX / PRODUCT
+  int ipc_max_ranks = 2;
+  // Kernel-variant crossovers measured on this box when the global set's team is created (cached per topology under
+  // HVD_CACHE_DIR): the engine applies them to the tunable parameters unless the environment pinned those.
+  int64_t zero_copy_nvls_min_bytes = 1 << 20;  // registered tensors: multimem from this size (two-shot P2P below)
+  bool calibrate = true;
+  std::function<void(int64_t oneshot_max_bytes, int64_t nvls_min_bytes)> on_calibrated;
 };
 
 class GpuOps {
@@ -100,6 +120,9 @@ class GpuOps {
   bool BuildInplaceArgs(SymmTeam& team, const void* ptr, int64_t bytes, DataType dtype, ReduceOp op, double prescale,
                         double postscale, int64_t expect_off, int max_ctas, kern::InplaceArgs* out);
 
+  // allreduces that ran zero-copy on IPC-registered plain tensors
+  uint64_t ipc_launches() const { return ipc_launches_.load(std::memory_order_relaxed); }
+
   // Lazily creates (collectively) the peer-mapped team of a process set.
   std::shared_ptr<SymmTeam> EnsureTeam(ProcessSet& ps, int device);
 
@@ -113,8 +136,11 @@ class GpuOps {
   // returns InProgress() when the kernel path does not apply (caller falls back to host staging)
   Status AdasumP2P(ProcessSet& ps, SymmTeam& team, Entries& es, const Response& r, const std::vector<int64_t>& counts,
                    int device, cudaStream_t s);
+  void Calibrate(ProcessSet& ps, SymmTeam& team, int device);
+  int CtasFor(int variant, int64_t seg_bytes, int n) const;
   GpuOpEnv env_;
   uint64_t team_counter_ = 0;
+  std::atomic<uint64_t> ipc_launches_{0};
 };
 
 // Row split of dim 0 for reducescatter: the first dim0 % size ranks get one extra row

@@ -147,10 +147,49 @@ def check_join_with_cached_bucket():
     print('[ok] join_with_cached_bucket', flush=True)
 
 
+def check_ipc_registration():
+    """Plain (cudaMalloc) tensors reduced in place: peers map each other's allocation over CUDA IPC and the zero-copy
+    kernel runs on them; a tensor that moves to another allocation is re-registered; MIN/MAX and out-of-place calls and
+    small tensors keep working (packed path)."""
+    import os
+    n = 3 << 20  # 12 MiB fp32
+    x = torch.empty(n, device=dev)
+    c0 = hvd.runtime_stats()['ipc_zero_copy_allreduces']
+    for it in range(4):
+        x.copy_(torch.arange(n, device=dev) % 7 + rank + it)
+        hvd.allreduce_(x, op=hvd.Sum, name='ipc.t')
+        exp = (torch.arange(n, device=dev) % 7) * size + sum(range(size)) + it * size
+        assert torch.equal(x, exp.float()), (it, x[:4], exp[:4])
+    used = hvd.runtime_stats()['ipc_zero_copy_allreduces'] - c0
+    expect_ipc = size <= int(os.environ.get('HVD_IPC_MAX_RANKS', '2')) and os.environ.get('HVD_IPC_REGISTRATION', '1') != '0'
+    assert (used == 4) == expect_ipc, (used, expect_ipc)
+    # the same name on a NEW allocation (the old one stays alive so the address differs): renegotiated, re-registered
+    keep = x
+    y = torch.empty(n + 1024, device=dev)[:n]
+    y.fill_(float(rank + 1))
+    hvd.allreduce_(y, op=hvd.Sum, name='ipc.t')
+    assert float(y[0]) == sum(range(1, size + 1)) and float(y[-1]) == sum(range(1, size + 1))
+    # averaged, bf16, and a view at an offset inside a larger allocation
+    big = torch.empty(4 * n, device=dev, dtype=torch.bfloat16)
+    v = big[n:3 * n]
+    v.fill_(float(rank + 1))
+    hvd.allreduce_(v, op=hvd.Average, name='ipc.view')
+    assert torch.allclose(v.float(), torch.full_like(v, (size + 1) / 2.0).float(), rtol=1e-2)
+    # MAX goes through the in-place kernel's P2P path on any team size
+    m = torch.full((n,), float(rank), device=dev)
+    hvd.allreduce_(m, op=hvd.Max, name='ipc.max')
+    assert float(m[0]) == size - 1 and float(m[-1]) == size - 1
+    # out-of-place and small tensors: packed path, same values
+    z = hvd.allreduce(torch.full((n,), 2.0, device=dev), op=hvd.Sum, name='ipc.oop')
+    assert float(z[0]) == 2.0 * size
+    del keep
+    print('[ok] ipc_registration (%d zero-copy launches on plain tensors)' % (hvd.runtime_stats()['ipc_zero_copy_allreduces'] - c0), flush=True)
+
+
 only = set(sys.argv[1].split(',')) if len(sys.argv) > 1 else None
 checks = [('captured', check_captured_allreduce), ('graphed', check_graphed_step_comm_in_graph),
           ('graphed_bf16', lambda: check_graphed_step_comm_in_graph(torch.bfloat16)),
-          ('zero_grad', check_model_zero_grad_idiom), ('join', check_join_with_cached_bucket)]
+          ('zero_grad', check_model_zero_grad_idiom), ('join', check_join_with_cached_bucket), ('ipc', check_ipc_registration)]
 for name, fn in checks:
     if only is None or name in only:
         fn()

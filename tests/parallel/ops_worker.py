@@ -102,7 +102,9 @@ def _():
         for i, n in enumerate([1, 1000003, 17, 262144]):
             ref = sum(rand([n], dtype, 77 + r * 13 + i).double() for r in range(size)).to(dtype)
             if dtype.is_floating_point:
-                torch.testing.assert_close(outs[i], ref, **tol(dtype))
+                # two-level sums round twice in the tensor's dtype (intra-host, then cross-host): 2 ulp of bf16 at |x| <= 16
+                t = dict(rtol=2e-2, atol=8e-2) if dtype == torch.bfloat16 else tol(dtype)
+                torch.testing.assert_close(outs[i], ref, **t)
             else:
                 assert torch.equal(outs[i], ref)
     x = torch.full((5, 3), float(rank + 1), device=DEV)
