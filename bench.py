@@ -320,16 +320,28 @@ def _nccl_group(torch, hvd):
     if dist.is_initialized():
         return dist
     from horovod_b200.common.basics import _EmbeddedRendezvous
+    # NCCL prints its version banner on stdout at communicator creation: this program's stdout carries exactly one JSON
+    # line, so library chatter goes to stderr while the group (and its first collective) come up
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     try:
         if _EmbeddedRendezvous.stores:
             store = dist.PrefixStore('bench_nccl', _EmbeddedRendezvous.stores[-1])
             dist.init_process_group('nccl', store=store, rank=hvd.rank(), world_size=hvd.size(),
                                     device_id=torch.device('cuda', hvd.local_rank()))
+            warm = torch.ones(1024, device='cuda')
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
         else:
             return None
     except Exception as e:  # noqa: BLE001
         sys.stderr.write('bench: NCCL comparison arm unavailable: %s\n' % e)
         return None
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     return dist
 
 

@@ -4,7 +4,7 @@
 set -u
 OUT=gpurun_out
 mkdir -p $OUT profiles
-NCU="ncu --set full --clock-control none --import-source on -c 1"
+NCU="ncu --set full --clock-control none --import-source on -c 2"
 declare -A K=( [allreduce]="regex:^.*allreduce_kernel" [inplace]="regex:inplace_allreduce_kernel" [exchange]="regex:exchange_kernel"
                [exchange_tma]="regex:exchange_tma_kernel" [pipelined]="regex:pipelined_allreduce_kernel" [adasum]="regex:adasum_"
                [optim_sgd]="regex:fused_sgd_kernel" [optim_adam]="regex:fused_adam_kernel" )

@@ -206,6 +206,9 @@ void Engine::BackgroundThread() {
       char hn[256] = "localhost";
       gethostname(hn, sizeof hn);
       std::string host = cfg_.hostname.empty() ? std::string(hn) : cfg_.hostname;
+      // test-only: the elastic fault-injection tests present one machine as several launcher "hosts" (localhost /
+      // 127.0.0.1); with this knob the RUNTIME still sees one host, i.e. one NVLink team over all ranks
+      if (EnvBool("HVD_TEST_ONE_HOST", false)) host = "hvd-test-one-host";
       store.Set(cfg_.scope, "host." + std::to_string(cfg_.rank), host);
       std::vector<std::string> hosts(cfg_.size);
       for (int r = 0; r < cfg_.size; ++r) hosts[r] = r == cfg_.rank ? host : store.Get(cfg_.scope, "host." + std::to_string(r), timeout);
@@ -263,6 +266,7 @@ void Engine::BackgroundThread() {
     ipc_min_bytes_ = (genv.backend == "p2p" && EnvBool("HVD_IPC_REGISTRATION", true) && GpuContext::Get().Available())
                          ? std::max<int64_t>(16, EnvInt("HVD_IPC_MIN_BYTES", 4 << 20)) : 0;
     genv.ipc_max_ranks = (int)EnvInt("HVD_IPC_MAX_RANKS", 2);
+    genv.latency_lane_bytes = std::min<int64_t>(1 << 20, std::max<int64_t>(0, EnvInt("HVD_LATENCY_LANE_BYTES", 256 << 10)));
     genv.dual_lane = EnvBool("HVD_DUAL_LANE_ALLREDUCE", true);
     genv.dual_lane_min_bytes = EnvInt("HVD_DUAL_LANE_MIN_BYTES", 64 << 20);
     genv.zero_copy_nvls_min_bytes = EnvInt("HVD_ZERO_COPY_NVLS_MIN_BYTES", 1 << 20);

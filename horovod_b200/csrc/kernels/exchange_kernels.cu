@@ -18,18 +18,20 @@ namespace kern {
 namespace {
 
 constexpr int kRow = kThreads * 16;
-constexpr int kXChunk = 16384;  // chunk -> CTA mapping granularity inside the symmetric buffer
+constexpr int kXChunk = 32768;  // chunk -> CTA mapping granularity inside the symmetric buffer (one 8-deep trip of the CTA)
 
 __device__ __forceinline__ void copy_bytes_vec(const char* src, char* dst, int64_t n) {
-  // 16 B vectors with 4 in flight per thread when both sides are 16 B aligned, bytes otherwise
+  // 16 B vectors, 8 in flight per thread (all loads of a trip are issued before the first store: an NVLink round trip is
+  // ~2 us) when both sides are 16 B aligned, bytes otherwise
   if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
     const int64_t nv = n / 16;
-    for (int64_t i0 = threadIdx.x; i0 < nv; i0 += 4 * kThreads) {
-      uint4 v[4];
+    constexpr int U = 8;
+    for (int64_t i0 = threadIdx.x; i0 < nv; i0 += (int64_t)U * kThreads) {
+      uint4 v[U];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { int64_t i = i0 + (int64_t)j * kThreads; if (i < nv) v[j] = ld_stream(src + i * 16); }
+      for (int j = 0; j < U; ++j) { int64_t i = i0 + (int64_t)j * kThreads; if (i < nv) v[j] = ld_stream(src + i * 16); }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { int64_t i = i0 + (int64_t)j * kThreads; if (i < nv) st_stream(dst + i * 16, v[j]); }
+      for (int j = 0; j < U; ++j) { int64_t i = i0 + (int64_t)j * kThreads; if (i < nv) st_stream(dst + i * 16, v[j]); }
     }
     for (int64_t i = nv * 16 + threadIdx.x; i < n; i += kThreads) dst[i] = src[i];
   } else {
@@ -75,9 +77,10 @@ __device__ __forceinline__ void mc_copy_vec(const char* src, char* mc, int64_t n
 template <typename F>
 __device__ __forceinline__ void for_my_chunks(int64_t offset, int64_t bytes, int cta, int grid, F f) {
   const int64_t end = offset + bytes;
-  int64_t c = offset / kXChunk;
-  for (; c * kXChunk < end; ++c) {
-    if ((int)(c % grid) != cta) continue;
+  const int64_t c0 = offset / kXChunk;
+  // first chunk >= c0 that belongs to this CTA, then every grid-th one
+  int64_t c = c0 + ((cta - (int)(c0 % grid) + grid) % grid);
+  for (; c * kXChunk < end; c += grid) {
     int64_t lo = c * kXChunk, hi = lo + kXChunk;
     if (lo < offset) lo = offset;
     if (hi > end) hi = end;
@@ -121,7 +124,7 @@ exchange_kernel(const __grid_constant__ CommParams cp, const __grid_constant__ E
 // global (local HBM or a peer over NVLink) -> smem stage -> global.  No registers or LSU slots are spent on the payload
 // and (kTmaStages - 1) x 16 KiB per CTA are in flight regardless of occupancy, which is what a pure copy collective
 // (allgather / broadcast / alltoall) wants on a B200.
-constexpr int kTmaStages = 4;
+constexpr int kTmaStages = 3;  // 3 x 32 KiB: two CTAs per SM still fit in 227 KB of shared memory
 constexpr int kTmaStageBytes = kXChunk;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -31,6 +31,7 @@ constexpr int kFlagWords = kMaxCtas * kMaxPeers;
 // Independent barrier channels (flag words + epochs) of one team: see SymmTeam::Params
 constexpr int kNumChannels = 8;
 constexpr int kGraphChannel = 1;              // collectives captured into CUDA graphs (framework streams)
+constexpr int kLatencyChannel = 3;            // the latency lane of small allreduce responses
 constexpr int kAuxChannel = 2;                // lane 1 of the dual-lane large-message allreduce (auxiliary hvd stream)
 constexpr int kChannelFlagsOffset = 128 * 1024;  // bytes from the start of the flag region; channel c >= 1 at + (c-1) * kFlagWords * 4
 

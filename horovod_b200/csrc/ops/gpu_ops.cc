@@ -22,6 +22,7 @@ namespace hvd {
 
 namespace {
 constexpr size_t kRingBytes = 8 << 20;
+constexpr int64_t kLatencyAreaBytes = 1 << 20;  // tail of each symmetric buffer slot reserved for the latency lane
 int64_t Align128(int64_t b) { return (b + 127) / 128 * 128; }
 }  // namespace
 
@@ -67,6 +68,16 @@ cudaStream_t GpuContext::AuxStream(int device) {
   }
   return d.aux_stream;
 }
+cudaStream_t GpuContext::LatencyStream(int device) {
+  std::lock_guard<std::mutex> l(mu_);
+  PerDevice& d = Dev(device);
+  if (!d.lat_stream) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    cudaStreamCreateWithPriority(&d.lat_stream, cudaStreamNonBlocking, hi);
+  }
+  return d.lat_stream;
+}
 cudaEvent_t GpuContext::ForkEvent(int device) { AuxStream(device); std::lock_guard<std::mutex> l(mu_); return Dev(device).fork_ev; }
 cudaEvent_t GpuContext::JoinEvent(int device) { AuxStream(device); std::lock_guard<std::mutex> l(mu_); return Dev(device).join_ev; }
 
@@ -98,7 +109,13 @@ const void* GpuContext::Stage(int device, const void* host, size_t bytes, cudaSt
   const size_t raw = bytes;
   bytes = (bytes + 255) / 256 * 256;
   if (bytes > kRingBytes) return nullptr;
-  if (d.ring_off + bytes > kRingBytes) { cudaStreamSynchronize(s); d.ring_off = 0; }  // wrap: everything older is consumed
+  if (d.ring_off + bytes > kRingBytes) {  // wrap: everything older must have been consumed, on every stream that stages here
+    cudaStreamSynchronize(s);
+    if (d.stream && d.stream != s) cudaStreamSynchronize(d.stream);
+    if (d.aux_stream && d.aux_stream != s) cudaStreamSynchronize(d.aux_stream);
+    if (d.lat_stream && d.lat_stream != s) cudaStreamSynchronize(d.lat_stream);
+    d.ring_off = 0;
+  }
   char* h = d.host_ring + d.ring_off;
   char* dv = d.dev_ring + d.ring_off;
   d.ring_off += bytes;
@@ -142,6 +159,7 @@ void GpuContext::Reset() {
     if (kv.second.pinned) cudaFreeHost(kv.second.pinned);
     if (kv.second.stream) { cudaStreamSynchronize(kv.second.stream); cudaStreamDestroy(kv.second.stream); }
     if (kv.second.aux_stream) { cudaStreamSynchronize(kv.second.aux_stream); cudaStreamDestroy(kv.second.aux_stream); }
+    if (kv.second.lat_stream) { cudaStreamSynchronize(kv.second.lat_stream); cudaStreamDestroy(kv.second.lat_stream); }
     if (kv.second.fork_ev) cudaEventDestroy(kv.second.fork_ev);
     if (kv.second.join_ev) cudaEventDestroy(kv.second.join_ev);
     for (auto e : kv.second.pool) cudaEventDestroy(e);
@@ -215,6 +233,7 @@ std::shared_ptr<SymmTeam> GpuOps::EnsureTeam(ProcessSet& ps, int device) {
   if (!ps.team) LOG(WARNING) << "peer-mapped symmetric memory unavailable for process set " << ps.id << " (" << why
                              << "); GPU collectives fall back to host staging";
   if (ps.team) ps.team->set_timeout_seconds(EnvDouble("HVD_KERNEL_TIMEOUT_SECONDS", 60.0));
+  if (ps.team && env_.latency_lane_bytes > 0 && ps.team->buffer_bytes() >= (size_t)(8 * kLatencyAreaBytes)) ps.team->set_reserved_tail((size_t)kLatencyAreaBytes);
   if (ps.team) LOG(INFO) << "process set " << ps.id << ": symmetric team of " << ps.team->nranks() << " GPUs, backend "
                  << ps.team->backend() << ", 2 x " << (ps.team->buffer_bytes() >> 20) << " MiB";
   // (same decision on every rank: a team exists everywhere or nowhere, the flags come from the shared environment)
@@ -398,7 +417,8 @@ int GpuOps::CtasFor(int variant, int64_t seg_bytes, int n) const {
   const TunableParams& tp = *env_.params;
   const int64_t per = variant == kern::kOneShot ? 8192 : (int64_t)4096 * n;  // >= 2 rows (one-shot) or one row per rank (two-shot) per CTA
   const int64_t big_ctas = env_.large_msg_ctas;
-  const int64_t cap_ctas = seg_bytes <= (1 << 20) ? std::min<int64_t>(tp.comm_ctas, 16)
+  // (2 x B200: a 1 MiB one-shot took 22 us on 16 CTAs — four dependent NVLink trips per CTA — against NCCL's 14 us)
+  const int64_t cap_ctas = seg_bytes <= (256 << 10) ? std::min<int64_t>(tp.comm_ctas, 16)
                          : seg_bytes <= (16 << 20) ? std::min<int64_t>(tp.comm_ctas, 64)
                          : seg_bytes < (64 << 20) ? tp.comm_ctas : std::max<int64_t>(tp.comm_ctas, big_ctas);
   return (int)std::max<int64_t>(1, std::min<int64_t>(cap_ctas, (seg_bytes + per - 1) / per));
@@ -517,6 +537,17 @@ Status GpuOps::Allreduce(ProcessSet& ps, Entries& es, const Response& r, int dev
   HVD_CUDA(cudaSetDevice(device));
   GpuContext& ctx = GpuContext::Get();
   cudaStream_t s = ctx.Stream(device);
+  // ---- latency lane: a small response does not queue behind a 256 MiB one.  Responses of at most latency_lane_bytes
+  // (decided from the negotiated sizes, i.e. identically on every rank) run on their own stream, barrier channel and
+  // reserved tail of the symmetric buffers (the role of the reference's HOROVOD_NUM_NCCL_STREAMS rotation,
+  // gpu_operations.cc:138-141, made deterministic across ranks) ----
+  bool lat_lane = false;
+  if (env_.latency_lane_bytes > 0 && n > 1 && env_.backend == "p2p" && r.symm_key == -1 && r.type == ResponseType::ALLREDUCE) {
+    int64_t total = 0;
+    for (auto c : r.tensor_sizes) total += Align128(c * (int64_t)DataTypeSize(r.dtype));
+    lat_lane = total > 0 && total <= env_.latency_lane_bytes;
+  }
+  if (lat_lane) s = ctx.LatencyStream(device);
   WaitReady(es, s);
   std::vector<Piece> pieces;
   Status st = BuildPieces(es, r, device, s, &pieces);
@@ -591,7 +622,11 @@ Status GpuOps::Allreduce(ProcessSet& ps, Entries& es, const Response& r, int dev
           (r.reduce_op == ReduceOp::SUM || r.reduce_op == ReduceOp::AVERAGE))
         wire = env_.wire_dtype;
       const int64_t wsz = (int64_t)DataTypeSize(wire);
+      // the tail of each buffer slot (reserved when the team was created) belongs to the latency lane
+      const int64_t lat_area = (int64_t)team->reserved_tail();
       int64_t cap = (int64_t)team->buffer_bytes() / 128 * 128;
+      if (lat_lane && lat_area < env_.latency_lane_bytes) lat_lane = false;  // tiny buffers: no reserved tail (same on every rank)
+      if (lat_lane) cap = lat_area / 128 * 128;
       const TunableParams& tp = *env_.params;
       // ---- large fused messages of plain tensors: TWO LANES.  The three-phase kernel is pack (HBM) -> NVLink phase -> unpack
       // (HBM) back to back, so the links idle while it packs and HBM idles while it reduces (8 x B200, 1 GiB: 2.98 ms vs
@@ -603,7 +638,7 @@ Status GpuOps::Allreduce(ProcessSet& ps, Entries& es, const Response& r, int dev
       // a peer's buffer any more.
       int64_t fused_total = 0;
       for (auto& p : pieces) fused_total += Align128(p.count * wsz);
-      const bool dual = env_.dual_lane && env_.variant != "oneshot" && fused_total >= env_.dual_lane_min_bytes && !env_.pipelined;
+      const bool dual = env_.dual_lane && env_.variant != "oneshot" && fused_total >= env_.dual_lane_min_bytes && !env_.pipelined && !lat_lane;
       cudaStream_t lane_stream[2] = {s, s};
       if (dual) {
         lane_stream[1] = ctx.AuxStream(device);
@@ -667,7 +702,9 @@ Status GpuOps::Allreduce(ProcessSet& ps, Entries& es, const Response& r, int dev
           a.descs = (const kern::TensorDesc*)ctx.Stage(device, descs.data(), descs.size() * sizeof(kern::TensorDesc), lane_stream[lane]);
           if (!a.descs) return Status::UnknownError("descriptor table too large");
         }
-        kern::CommParams cp = dual ? team->Params(first_slot ^ lane, lane == 0 ? 0 : kern::kAuxChannel) : team->Params(team->NextSlot());
+        kern::CommParams cp = dual ? team->Params(first_slot ^ lane, lane == 0 ? 0 : kern::kAuxChannel)
+                            : lat_lane ? team->Params(team->NextLatencySlot(), kern::kLatencyChannel, (int64_t)team->buffer_bytes())
+                                       : team->Params(team->NextSlot());
         if (dual && lane == 1 && !lane1_gated) {
           cudaStreamWaitEvent(lane_stream[1], ctx.ForkEvent(device), 0);  // re-recorded below, after lane 0's first kernel
           lane1_gated = true;

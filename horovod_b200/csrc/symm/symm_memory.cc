@@ -263,14 +263,14 @@ SymmTeam::~SymmTeam() = default;
 
 std::shared_ptr<void> SymmTeam::KeepAlive() const { return std::static_pointer_cast<void>(impl_); }
 
-kern::CommParams SymmTeam::Params(int which, int channel) const {
+kern::CommParams SymmTeam::Params(int which, int channel, int64_t byte_offset) const {
   kern::CommParams cp {};
   cp.nranks = nranks_;
   cp.rank = rank_;
   // channel 0 = the cycle thread's flag words at the start of the region; channels >= 1 own kFlagWords each further up
   const size_t foff = channel == 0 ? 0 : (kern::kChannelFlagsOffset / 4 + (size_t)(channel - 1) * kern::kFlagWords);
-  for (int i = 0; i < nranks_; ++i) { cp.buf[i] = buf_[which][i]; cp.flags[i] = flags_[i] + foff; }
-  cp.mc_buf = mc_va_[which];
+  for (int i = 0; i < nranks_; ++i) { cp.buf[i] = (char*)buf_[which][i] + byte_offset; cp.flags[i] = flags_[i] + foff; }
+  cp.mc_buf = mc_va_[which] ? (char*)mc_va_[which] + byte_offset : nullptr;
   cp.epochs = epochs_ + (size_t)channel * kern::kMaxCtas;
   cp.abort_flag = abort_dev_;
   cp.timeout_ns = timeout_ns_;

@@ -53,16 +53,22 @@ class SymmTeam {
 
   int nranks() const { return nranks_; }
   int rank() const { return rank_; }
-  size_t buffer_bytes() const { return buffer_bytes_; }
+  // bytes of one buffer slot available to ordinary ops; the reserved tail [buffer_bytes(), buffer_bytes() + reserved_tail())
+  // belongs to the latency lane
+  size_t buffer_bytes() const { return buffer_bytes_ - reserved_tail_; }
+  size_t reserved_tail() const { return reserved_tail_; }
+  void set_reserved_tail(size_t b) { reserved_tail_ = b < buffer_bytes_ ? b : 0; }
   bool has_multicast() const { return mc_va_[0] != nullptr; }
   // CommParams for buffer slot `which` (0/1 ping-pong).  `channel` selects an independent set of barrier flags + epochs:
   // kernels of different channels may run concurrently (channel 0 = the cycle thread's stream, kGraphChannel = collectives
   // captured into CUDA graphs on framework streams, the rest = extra engine streams).  The data slots are shared: only
   // zero-copy (registered-region) kernels may use a channel other than the one that owns the slots.
-  kern::CommParams Params(int which, int channel = 0) const;
+  // `byte_offset` shifts the data pointers (buffers and multicast alias) into a sub-area of the slot.
+  kern::CommParams Params(int which, int channel = 0, int64_t byte_offset = 0) const;
   // Next ping-pong slot (ops alternate so a fast rank never overwrites data a
   // slow peer is still reading).
   int NextSlot() { int s = slot_; slot_ ^= 1; return s; }
+  int NextLatencySlot() { int s = lat_slot_; lat_slot_ ^= 1; return s; }  // the latency lane alternates on its own
   // Running chunk counter of the software-pipelined allreduce: every rank launches the same sequence of pipelined
   // kernels with the same chunk counts, so the value is identical on all ranks without communication.
   uint32_t NextPipeBase(uint32_t nchunks) { uint32_t b = pipe_seq_; pipe_seq_ += nchunks; return b; }
@@ -85,14 +91,14 @@ class SymmTeam {
   SymmTeam() = default;
   struct Impl;
   int nranks_ = 0, rank_ = 0, device_ = 0;
-  size_t buffer_bytes_ = 0;
+  size_t buffer_bytes_ = 0, reserved_tail_ = 0;
   void* buf_[2][kern::kMaxPeers] = {};
   uint32_t* flags_[kern::kMaxPeers] = {};
   void* mc_va_[2] = {nullptr, nullptr};
   uint32_t* epochs_ = nullptr;
   int* abort_host_ = nullptr;   // pinned, mapped
   int* abort_dev_ = nullptr;    // device alias of abort_host_
-  int slot_ = 0;
+  int slot_ = 0, lat_slot_ = 0;
   uint32_t pipe_seq_ = 0;
   unsigned long long timeout_ns_ = 0;
   std::string backend_;

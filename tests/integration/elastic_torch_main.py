@@ -19,14 +19,21 @@ p.add_argument('--exit-schedule', default='{}')
 p.add_argument('--exit-mode', default='exception', choices=['exception', 'kill'])
 p.add_argument('--discovery-schedule-epoch-file', default=None)
 p.add_argument('--batch-sleep', type=float, default=0.0)
+p.add_argument('--device', default='cpu', choices=['cpu', 'cuda'])
 args = p.parse_args()
 schedule = {tuple(int(x) for x in k.split(',')): v for k, v in json.loads(args.exit_schedule).items()}
 
 hvd.init()
 torch.manual_seed(1234)
-model = torch.nn.Linear(4, 1)
-optimizer = hvd.DistributedOptimizer(torch.optim.SGD(model.parameters(), lr=0.01), named_parameters=model.named_parameters())
 start_rank = int(os.environ.get('HOROVOD_RANK', 0))
+DEV = torch.device('cpu')
+if args.device == 'cuda':
+    # every worker keeps the GPU of its ORIGINAL rank for its whole life (ranks are renumbered after a reset, and the two
+    # launcher "hosts" of the fault-injection tests both start their local ranks at 0)
+    DEV = torch.device('cuda', start_rank % torch.cuda.device_count())
+    torch.cuda.set_device(DEV)
+model = torch.nn.Linear(4, 1).to(DEV)
+optimizer = hvd.DistributedOptimizer(torch.optim.SGD(model.parameters(), lr=0.01), named_parameters=model.named_parameters())
 hostname = os.environ.get('HOROVOD_HOSTNAME')
 
 
@@ -60,7 +67,7 @@ def train(state):
                 import time
                 time.sleep(args.batch_sleep)
             optimizer.zero_grad()
-            loss = model(torch.ones(2, 4) * (hvd.rank() + 1)).pow(2).mean()
+            loss = model(torch.ones(2, 4, device=DEV) * (hvd.rank() + 1)).pow(2).mean()
             loss.backward()
             optimizer.step()
             state.batch += 1

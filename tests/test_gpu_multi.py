@@ -98,3 +98,23 @@ def test_fused_collectives_and_pipelined_allreduce(native_built):
                            args=["--device", "cuda", "--only", "fused_other_collectives,allgather,broadcast,reducescatter,"
                                  "allreduce_sum_avg,allreduce_async_fused,large_allreduce"])
     assert "ALL OK" in out, out[-4000:]
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+def test_elastic_rank_failure_on_gpus(native_built, tmp_path):
+    """Elastic recovery with the NVLink data plane (reference test/integration/test_elastic_torch.py:33-49): two workers
+    on two GPUs of ONE peer-mapped team; rank 1 is SIGKILLed in the middle of epoch 1.  The survivor's collective (its
+    kernel may be spinning at the flag barrier of a peer that no longer exists) must end through the abort flag, the job
+    re-forms at size 1, restores the last commit and finishes."""
+    from test_integration_elastic import _run_elastic
+    rc, out, recs = _run_elastic(tmp_path, [(None, ['localhost:1', '127.0.0.1:1'])], 2, 1, 2,
+                                 exit_schedule={'1,2': [1]}, exit_mode='kill', main_args=['--device', 'cuda'], timeout=400,
+                                 env_extra={'HVD_TEST_ONE_HOST': '1', 'HVD_KERNEL_TIMEOUT_SECONDS': '15', 'HOROVOD_LOG_LEVEL': 'info'})
+    done = recs[-1]
+    assert done.get('done') and done['size'] == 1, (done, out[-3000:])
+    sizes_by_epoch = {}
+    for r in recs:
+        if 'epoch' in r:
+            sizes_by_epoch.setdefault(r['epoch'], set()).add(r['size'])
+    assert sizes_by_epoch[0] == {2} and sizes_by_epoch[2] == {1}, sizes_by_epoch
+    assert 'symmetric team of 2 GPUs' in out, out[-3000:]

@@ -15,7 +15,7 @@ MAIN = os.path.join(REPO, 'tests', 'integration', 'elastic_torch_main.py')
 
 
 def _run_elastic(tmp_path, discovery_lines_by_epoch, np_, min_np, max_np, exit_schedule=None, exit_mode='exception', extra=(),
-                 timeout=300, expect_fail=False, batch_sleep=0.0):
+                 timeout=300, expect_fail=False, batch_sleep=0.0, main_args=(), env_extra=None):
     logfile = str(tmp_path / 'log.jsonl')
     epoch_file = str(tmp_path / 'epoch')
     with open(epoch_file, 'w') as f:
@@ -32,10 +32,11 @@ def _run_elastic(tmp_path, discovery_lines_by_epoch, np_, min_np, max_np, exit_s
     script.write_text('\n'.join(body) + '\n')
     script.chmod(script.stat().st_mode | stat.S_IEXEC)
     env = dict(os.environ, PYTHONPATH=REPO, OMP_NUM_THREADS='1', HOROVOD_LOG_LEVEL='warning')
+    env.update(env_extra or {})
     cmd = [sys.executable, '-m', 'horovod_b200.runner.launch', '-np', str(np_), '--min-np', str(min_np), '--max-np', str(max_np),
            '--host-discovery-script', str(script), *extra, sys.executable, MAIN, '--logfile', logfile,
            '--discovery-schedule-epoch-file', epoch_file, '--exit-mode', exit_mode,
-           '--exit-schedule', json.dumps(exit_schedule or {}), '--batch-sleep', str(batch_sleep)]
+           '--exit-schedule', json.dumps(exit_schedule or {}), '--batch-sleep', str(batch_sleep), *main_args]
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env, timeout=timeout, cwd=REPO)
     out = p.stdout.decode(errors='replace')
     if not expect_fail:
