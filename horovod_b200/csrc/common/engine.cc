@@ -267,6 +267,7 @@ void Engine::BackgroundThread() {
                          ? std::max<int64_t>(16, EnvInt("HVD_IPC_MIN_BYTES", 4 << 20)) : 0;
     genv.ipc_max_ranks = (int)EnvInt("HVD_IPC_MAX_RANKS", 2);
     genv.latency_lane_bytes = std::min<int64_t>(1 << 20, std::max<int64_t>(0, EnvInt("HVD_LATENCY_LANE_BYTES", 256 << 10)));
+    genv.adasum_persistent = EnvBool("HVD_ADASUM_PERSISTENT", true);
     genv.dual_lane = EnvBool("HVD_DUAL_LANE_ALLREDUCE", true);
     genv.dual_lane_min_bytes = EnvInt("HVD_DUAL_LANE_MIN_BYTES", 64 << 20);
     genv.zero_copy_nvls_min_bytes = EnvInt("HVD_ZERO_COPY_NVLS_MIN_BYTES", 1 << 20);

@@ -163,17 +163,32 @@ int hvd_sim_adasum(int nranks, int device, int ntensors, const int64_t* counts, 
     if (!dtabs[r]) return -2;
     cps[r] = sim->teams[r]->Params(sim->teams[r]->NextSlot());
   }
-  const int steps = kern::AdasumNumLaunches(nranks);
+  // HVD_ADASUM_PERSISTENT (default 1): the single-launch kernel; every simulated rank gets its own scratch + grid-sync block
+  const char* pe = getenv("HVD_ADASUM_PERSISTENT");
+  const bool persistent = !(pe && atoi(pe) == 0);
+  std::vector<void*> pscratch(nranks, nullptr), psync(nranks, nullptr);
+  if (persistent) {
+    for (int r = 0; r < nranks; ++r) {
+      cudaMalloc(&pscratch[r], kern::AdasumPersistentScratchBytes(ctas, ntensors));
+      cudaMalloc(&psync[r], 256);
+      cudaMemset(psync[r], 0, 256);
+    }
+  }
+  auto free_persist = [&]() { for (int r = 0; r < nranks; ++r) { if (pscratch[r]) cudaFree(pscratch[r]); if (psync[r]) cudaFree(psync[r]); } };
+  const int steps = persistent ? 1 : kern::AdasumNumLaunches(nranks);
   for (int k = 0; k < steps; ++k) {
     for (int r = 0; r < nranks; ++r) {
       kern::AdasumArgs a {};
       a.descs = dtabs[r]; a.ndesc = ntensors; a.total_bytes = total; a.dtype = dtype; a.ctas = ctas;
       a.scratch_stride_bytes = kern::kAdasumScratchStride;
-      cudaError_t e = kern::LaunchAdasumStep(cps[r], a, prescale, postscale, sim->streams[r], k);
-      if (e != cudaSuccess) return (int)e;
+      a.persist_scratch = pscratch[r]; a.persist_sync = psync[r];
+      cudaError_t e = kern::LaunchAdasumStep(cps[r], a, prescale, postscale, sim->streams[r], persistent ? -1 : k);
+      if (e != cudaSuccess) { free_persist(); return (int)e; }
     }
   }
-  return Finish(nranks, cudaDeviceSynchronize());
+  const cudaError_t sync = cudaDeviceSynchronize();
+  free_persist();
+  return Finish(nranks, sync);
 }
 
 // Zero-copy in-place allreduce over N simulated ranks: ptrs[r] = rank r's tensor (plain device memory here).

@@ -171,7 +171,7 @@ __device__ __forceinline__ void tma_copy_my_chunks(TmaRing& ring, int64_t offset
   const int64_t end = offset + (bytes & ~(int64_t)15);
   if (end <= offset) return;  // fewer than 16 bytes: the byte tail of the caller covers it
   // chunk walker shared by the load side (`lc`) and the store side (`sc`)
-  auto next_mine = [&](int64_t c) { while (c * kXChunk < end && (int)(c % grid) != cta) ++c; return c; };
+  auto next_mine = [&](int64_t c) { return c + ((cta - (int)(c % grid) + grid) % grid); };  // first chunk >= c of this CTA
   auto bounds = [&](int64_t c, int64_t& lo, int64_t& hi) {
     lo = c * kXChunk; hi = lo + kXChunk;
     if (lo < offset) lo = offset;

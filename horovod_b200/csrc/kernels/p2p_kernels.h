@@ -151,7 +151,13 @@ struct AdasumArgs {
   int dtype;
   int ctas;
   int64_t scratch_stride_bytes;         // distance between the two per-level partial-dot tables in the flag region
+  // Persistent single-launch variant (both non-null): local device scratch of AdasumPersistentScratchBytes(ctas, ndesc)
+  // and a 16-byte grid-synchronisation block; `ctas` CTAs must be co-resident on the device.
+  void* persist_scratch = nullptr;
+  void* persist_sync = nullptr;
 };
+size_t AdasumPersistentScratchBytes(int ctas, int ndesc);
+size_t AdasumPersistentSyncBytes();
 constexpr int64_t kAdasumScratchStride = 30000;
 constexpr int kAdasumMaxTensors = 1250;
 cudaError_t LaunchAdasum(const CommParams& cp, const AdasumArgs& args, double prescale, double postscale, cudaStream_t stream);

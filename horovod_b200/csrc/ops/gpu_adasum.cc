@@ -89,13 +89,29 @@ Status GpuOps::AdasumP2P(ProcessSet& ps, SymmTeam& team, Entries& es, const Resp
     descs[i].count = counts[i];
     total += (counts[i] * 4 + 127) / 128 * 128;
   }
-  if (total > (int64_t)team.buffer_bytes()) return Status::InProgress();  // larger than the symmetric buffer: host path
+  if (total > (int64_t)team.buffer_bytes()) {
+    // larger than the symmetric buffer: the host implementation takes over (D2H, CPU VHDD, H2D) — correct but slow, so say so
+    static bool warned = false;
+    if (!warned) {
+      warned = true;
+      LOG(WARNING) << "Adasum: a fused response of " << (total >> 20) << " MiB (fp32) does not fit the " << (team.buffer_bytes() >> 20)
+                   << " MiB symmetric buffer and is reduced on the host; raise HVD_SYMM_BUFFER_BYTES or lower HOROVOD_FUSION_THRESHOLD";
+    }
+    return Status::InProgress();
+  }
   const auto* dt = (const kern::TensorDesc*)ctx.Stage(device, descs.data(), descs.size() * sizeof(kern::TensorDesc), s);
   if (!dt) return Status::InProgress();
   kern::AdasumArgs a {};
   a.descs = dt; a.ndesc = (int)descs.size(); a.total_bytes = total; a.dtype = (int)r.dtype;
   a.ctas = (int)std::max<int64_t>(1, std::min<int64_t>(env_.params->comm_ctas, (total + 16383) / 16384));
   a.scratch_stride_bytes = kern::kAdasumScratchStride;
+  if (env_.adasum_persistent) {
+    // one resident kernel for the whole reduction (grid barriers inside): its CTAs must fit on the device together
+    a.ctas = std::min(a.ctas, 128);
+    a.persist_scratch = ctx.TempAlloc(device, kern::AdasumPersistentScratchBytes(a.ctas, a.ndesc), false, s);
+    a.persist_sync = ctx.GridSyncBlock(device);
+    if (!a.persist_scratch || !a.persist_sync) { a.persist_scratch = nullptr; a.persist_sync = nullptr; }
+  }
   kern::CommParams cp = team.Params(team.NextSlot());
   if (env_.timeline && env_.timeline->Initialized()) env_.timeline->ActivityStartAll(es, HVD_ACT_P2P_ADASUM);
   cudaError_t e = kern::LaunchAdasum(cp, a, r.prescale, r.postscale, s);

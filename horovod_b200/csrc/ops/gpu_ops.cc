@@ -78,6 +78,15 @@ cudaStream_t GpuContext::LatencyStream(int device) {
   }
   return d.lat_stream;
 }
+void* GpuContext::GridSyncBlock(int device) {
+  std::lock_guard<std::mutex> l(mu_);
+  PerDevice& d = Dev(device);
+  if (!d.grid_sync) {
+    if (cudaMalloc(&d.grid_sync, 256) != cudaSuccess) { cudaGetLastError(); d.grid_sync = nullptr; return nullptr; }
+    cudaMemset(d.grid_sync, 0, 256);
+  }
+  return d.grid_sync;
+}
 cudaEvent_t GpuContext::ForkEvent(int device) { AuxStream(device); std::lock_guard<std::mutex> l(mu_); return Dev(device).fork_ev; }
 cudaEvent_t GpuContext::JoinEvent(int device) { AuxStream(device); std::lock_guard<std::mutex> l(mu_); return Dev(device).join_ev; }
 
@@ -160,6 +169,7 @@ void GpuContext::Reset() {
     if (kv.second.stream) { cudaStreamSynchronize(kv.second.stream); cudaStreamDestroy(kv.second.stream); }
     if (kv.second.aux_stream) { cudaStreamSynchronize(kv.second.aux_stream); cudaStreamDestroy(kv.second.aux_stream); }
     if (kv.second.lat_stream) { cudaStreamSynchronize(kv.second.lat_stream); cudaStreamDestroy(kv.second.lat_stream); }
+    if (kv.second.grid_sync) cudaFree(kv.second.grid_sync);
     if (kv.second.fork_ev) cudaEventDestroy(kv.second.fork_ev);
     if (kv.second.join_ev) cudaEventDestroy(kv.second.join_ev);
     for (auto e : kv.second.pool) cudaEventDestroy(e);

@@ -39,7 +39,8 @@ class GpuContext {
   cudaStream_t Stream(int device);
   // second private stream of the device (lane 1 of the dual-lane large-message allreduce) and its fork / join events
   cudaStream_t AuxStream(int device);
-  cudaStream_t LatencyStream(int device);  // small responses (GpuOpEnv::latency_lane_bytes)
+  cudaStream_t LatencyStream(int device);
+  void* GridSyncBlock(int device);         // 256 zeroed bytes: grid-barrier state of the persistent Adasum kernel  // small responses (GpuOpEnv::latency_lane_bytes)
   cudaEvent_t ForkEvent(int device);
   cudaEvent_t JoinEvent(int device);
   SharedEvent* NewEvent(int device, int refs);
@@ -58,6 +59,7 @@ class GpuContext {
     cudaStream_t stream = nullptr;
     cudaStream_t aux_stream = nullptr;
     cudaStream_t lat_stream = nullptr;
+    void* grid_sync = nullptr;
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
     std::vector<cudaEvent_t> pool;
     char* host_ring = nullptr; char* dev_ring = nullptr; size_t ring_off = 0;
@@ -90,6 +92,7 @@ struct GpuOpEnv {
   // allreduce responses of at most this many fused bytes run on the latency lane (own stream / barrier channel / reserved
   // buffer tail) instead of queueing behind large ones on the main stream; 0 = off
   int64_t latency_lane_bytes = 256 << 10;
+  bool adasum_persistent = true;   // single-launch Adasum (grid barriers inside the kernel) instead of 2 + 2 log2(N) launches
   bool dual_lane = true;
   int64_t dual_lane_min_bytes = 64 << 20;
   // teams of up to this many ranks reduce IPC-registered plain tensors in place with the P2P two-shot kernel; larger

@@ -338,7 +338,8 @@ class _DistributedOptimizer(torch.optim.Optimizer):
         self._graph_capture = {'comm': torch.cuda.Stream(priority=hi_pri), 'launched': set(),
                                # few CTAs while backward still needs the SMs (8 x B200, BERT-large: 16 CTAs 30.64 ms/step, 32: 30.73,
                                # 64: 31.82), all of them for the tail bucket(s) that nothing overlaps any more
-                               'ctas': int(os.environ.get('HVD_GRAPH_COMM_CTAS', '16')),
+                               # (without NVLS — teams of 2 — the P2P two-shot kernel needs more CTAs to keep up with backward)
+                               'ctas': int(os.environ.get('HVD_GRAPH_COMM_CTAS', '16' if '+mc' in mpi_ops.gpu_backend_info() and self.process_set.size() >= 4 else '32')),
                                'tail_ctas': int(os.environ.get('HVD_GRAPH_COMM_TAIL_CTAS', '128')), 'tail': False,
                                'pending': {id(b): len(b['params']) for b in self._buckets}}
         return True

@@ -186,10 +186,49 @@ def check_ipc_registration():
     print('[ok] ipc_registration (%d zero-copy launches on plain tensors)' % (hvd.runtime_stats()['ipc_zero_copy_allreduces'] - c0), flush=True)
 
 
+def check_latency_lane():
+    """A small allreduce issued right after a very large one must not wait for it: small responses run on their own
+    stream / barrier channel / buffer tail (HVD_LATENCY_LANE_BYTES)."""
+    import os
+    import time
+    big = torch.ones(96 << 20, device=dev)      # 384 MiB fp32: milliseconds on the wire
+    small = torch.full((1024,), float(rank + 1), device=dev)
+    exp_small = float(sum(range(1, size + 1)))
+    for _ in range(2):  # warm-up: negotiation, caches, IPC registration of `big`
+        hvd.allreduce_(big, op=hvd.Sum, name='lane.big')
+        hvd.allreduce_(small.clone(), op=hvd.Sum, name='lane.small')
+    torch.cuda.synchronize()
+    hvd.barrier()
+    ratios = []
+    for it in range(3):
+        big.fill_(1.0)
+        s1 = small.clone()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        hb = hvd.allreduce_async_(big, op=hvd.Sum, name='lane.big')
+        hs = hvd.allreduce_async_(s1, op=hvd.Sum, name='lane.small')
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            hvd.synchronize(hs)          # the side stream waits for the small collective only
+            side.synchronize()
+            t_small = time.perf_counter() - t0
+        hvd.synchronize(hb)
+        torch.cuda.current_stream().synchronize()
+        t_big = time.perf_counter() - t0
+        assert float(s1[0]) == exp_small and float(big[0]) == float(size) and float(big[-1]) == float(size)
+        ratios.append(t_small / t_big)
+    lane_on = int(os.environ.get('HVD_LATENCY_LANE_BYTES', str(256 << 10))) > 0
+    best = min(ratios)
+    print('[info] latency lane %s: small/big completion time ratio %.2f' % ('on' if lane_on else 'off', best), flush=True)
+    if lane_on:
+        assert best < 0.6, ('the small allreduce waited for the large one', ratios)
+    print('[ok] latency_lane', flush=True)
+
+
 only = set(sys.argv[1].split(',')) if len(sys.argv) > 1 else None
 checks = [('captured', check_captured_allreduce), ('graphed', check_graphed_step_comm_in_graph),
           ('graphed_bf16', lambda: check_graphed_step_comm_in_graph(torch.bfloat16)),
-          ('zero_grad', check_model_zero_grad_idiom), ('join', check_join_with_cached_bucket), ('ipc', check_ipc_registration)]
+          ('zero_grad', check_model_zero_grad_idiom), ('join', check_join_with_cached_bucket), ('ipc', check_ipc_registration), ('lane', check_latency_lane)]
 for name, fn in checks:
     if only is None or name in only:
         fn()

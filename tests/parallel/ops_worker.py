@@ -341,6 +341,24 @@ def _():
     assert torch.allclose(y, torch.full_like(y, (size + 1) / 2.0)) and float(x[0]) == rank + 1
 
 
+@check('wire_dtype_env')
+def _():
+    """HVD_WIRE_DTYPE=bf16|fp16: fp32 tensors travel as 16-bit values (cast fused into the pack / unpack phases of the
+    allreduce kernel, fp32 accumulation).  Values within 16-bit tolerance; on GPUs with the knob set the result must differ
+    from the exact fp32 sum somewhere (i.e. the compression really happened)."""
+    ts = [rand([n], torch.float32, 400 + rank * 7 + i) for i, n in enumerate([100003, 17, 65536])]
+    hs = [hvd.allreduce_async(t, op=hvd.Sum, name='wire.%d' % i) for i, t in enumerate(ts)]
+    outs = [hvd.synchronize(h) for h in hs]
+    exact = True
+    for i, n in enumerate([100003, 17, 65536]):
+        ref = sum(rand([n], torch.float32, 400 + r * 7 + i).double() for r in range(size)).float()
+        torch.testing.assert_close(outs[i], ref, rtol=2e-2, atol=2e-2 * size)
+        exact = exact and bool(torch.allclose(outs[i], ref, rtol=1e-6, atol=1e-6))
+    if args.device == 'cuda' and size > 1 and os.environ.get('HVD_WIRE_DTYPE', 'none') in ('bf16', 'fp16') and \
+            os.environ.get('HVD_GPU_BACKEND', 'p2p') == 'p2p':
+        assert not exact, 'HVD_WIRE_DTYPE is set but the sums are exact to fp32 precision'
+
+
 @check('autograd')
 def _():
     # allreduce: grad of sum-allreduce is sum-allreduce of ones

@@ -49,10 +49,9 @@ def test_nccl_baseline_backend(native_built):
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
 def test_wire_compression_env(native_built):
-    # bf16 on the wire (fp32 gradients cast inside the pack / unpack phases of the fused kernel): the optimizer check's
-    # tolerances allow it, the exact-value allreduce checks (1e-5) do not by design
+    # bf16 on the wire (fp32 gradients cast inside the pack / unpack phases of the fused kernel)
     rc, out = run_parallel("ops_worker.py", np=2, timeout=300, env={"HVD_WIRE_DTYPE": "bf16"},
-                           args=["--device", "cuda", "--only", "optimizer"])
+                           args=["--device", "cuda", "--only", "wire_dtype_env"])
     assert "ALL OK" in out, out[-3000:]
 
 
