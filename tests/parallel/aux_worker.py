@@ -57,6 +57,14 @@ elif mode == 'timeline':
         hvd.allreduce(torch.ones(64), name='tl.ar')
         hvd.allgather(torch.ones(2, 2), name='tl.ag')
     hvd.barrier()
+    if hvd.rank() == 0:
+        # the file must be a complete JSON document WHILE the timeline is still running (closing bracket rewritten in place
+        # after every drain of the writer's ring), not only after stop_timeline()
+        time.sleep(0.3)
+        live = json.loads(open(path).read())
+        assert isinstance(live, list) and len(live) > 10, len(live)
+        print('TIMELINE LIVE JSON OK', len(live), flush=True)
+    hvd.barrier()
     hvd.stop_timeline()
     hvd.barrier()
     print('TIMELINE DONE', flush=True)

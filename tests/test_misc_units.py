@@ -151,3 +151,19 @@ def test_every_hvd_knob_is_documented():
     doc = open(os.path.join(root, 'docs', 'knobs.md')).read()
     missing = sorted(n for n in names if n not in doc and not n.startswith('HVD_TEST_'))
     assert not missing, 'undocumented knobs: %s' % missing
+
+
+def test_gpu_numa_cpu_list_from_sysfs(tmp_path):
+    """NUMA binding helper (pin near the GPU's NUMA node): PCI address -> numa_node -> cpulist, on a fake sysfs."""
+    from horovod_b200.common.util import _parse_cpulist, bind_to_gpu_numa, gpu_numa_cpus
+    d = tmp_path
+    (d / 'bus/pci/devices/0000:1b:00.0').mkdir(parents=True)
+    (d / 'devices/system/node/node1').mkdir(parents=True)
+    (d / 'bus/pci/devices/0000:1b:00.0/numa_node').write_text('1\n')
+    (d / 'devices/system/node/node1/cpulist').write_text('56-59,112\n')
+    assert gpu_numa_cpus(0, 0x1b, 0, str(d)) == {56, 57, 58, 59, 112}
+    assert gpu_numa_cpus(0, 0x1c, 0, str(d)) is None            # unknown device
+    (d / 'bus/pci/devices/0000:1b:00.0/numa_node').write_text('-1\n')
+    assert gpu_numa_cpus(0, 0x1b, 0, str(d)) is None            # no NUMA information
+    assert _parse_cpulist('0-2,8,10-11') == {0, 1, 2, 8, 10, 11}
+    assert bind_to_gpu_numa(0, str(d)) is None                   # no GPU here: never touches the affinity
