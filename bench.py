@@ -230,7 +230,6 @@ def _time_train(args, model_name, steps, warmup, hvd, torch, sample_clocks):
     # step if capture is impossible (e.g. the Adasum optimizer's per-parameter steps).
     graphed = hvd.GraphedStep(fwd, opt, dev_batch, enabled=not eager)
     comm_nodes = len(getattr(opt, '_buckets', [])) if graphed.comm_in_graph else 0
-    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
 
     def timed(nsteps, e2e):
         hvd.barrier()
@@ -242,8 +241,9 @@ def _time_train(args, model_name, steps, warmup, hvd, torch, sample_clocks):
         if e2e:
             # every step: host -> device copy of that step's inputs from pinned memory on the prefetcher's copy stream (the
             # copy of step i+1 overlaps the compute of step i) and a device -> host copy of the step's loss into pinned
-            # memory; the host reads the loss of step i-1 while step i runs (a training loop logs, it does not stall on
-            # .item()), and the last loss before the clock stops
+            # memory; the host reads the loss of step i-2 while step i is issued (a training loop logs, it does not stall on
+            # .item(): with a one-step lag the host could never run ahead of the device and its launch time — ~2 ms of
+            # Python for BERT-large's 400 parameters — would be exposed), and every outstanding loss before the clock stops
             class _Loader:
                 def __len__(self):
                     return nsteps
@@ -252,18 +252,21 @@ def _time_train(args, model_name, steps, warmup, hvd, torch, sample_clocks):
                     for _ in range(nsteps):
                         yield host_batch
             pf = DevicePrefetcher(_Loader(), device=f'cuda:{local_rank}', depth=2)
-            copied = torch.cuda.Event()
-            pending = False
-            for batch in pf:
-                if pending:
-                    copied.synchronize()
-                    last = float(loss_host[0])
+            ring = [(torch.zeros(1, dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(3)]
+            inflight = []  # (pinned buffer, event) of the steps whose loss copy has been issued but not read yet
+            for i, batch in enumerate(pf):
+                if len(inflight) == 2:  # the host stays at most two steps ahead of the device
+                    buf, ev = inflight.pop(0)
+                    ev.synchronize()
+                    last = float(buf[0])
                 loss = graphed(*batch)
-                loss_host.copy_(loss.detach().float().reshape(1), non_blocking=True)
-                copied.record()
-                pending = True
-            copied.synchronize()
-            last = float(loss_host[0])
+                buf, ev = ring[i % 3]
+                buf.copy_(loss.detach().float().reshape(1), non_blocking=True)
+                ev.record()
+                inflight.append((buf, ev))
+            for buf, ev in inflight:
+                ev.synchronize()
+                last = float(buf[0])
             assert pf.h2d_bytes == h2d_bytes * nsteps
         else:
             for _ in range(nsteps):
@@ -483,7 +486,7 @@ def train_bench(args):
             'clocks': main['clocks'],
             'e2e': {'value': main['e2e_value'], 'unit': main['unit'], 'ms_per_step': main['e2e_ms_per_step'],
                     'h2d_bytes_per_step': main['h2d_bytes_per_step'], 'd2h_bytes_per_step': 4, 'last_loss': main['last_loss'],
-                    'loss_read': 'async D2H into pinned memory every step, read by the host one step later'},
+                    'loss_read': 'async D2H into pinned memory every step, read by the host two steps later'},
             'gpu_launches': main['gpu_launches'],
             'extra': extra,
         }

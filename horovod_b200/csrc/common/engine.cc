@@ -265,10 +265,10 @@ void Engine::BackgroundThread() {
     // on-the-fly IPC registration of plain in-place tensors (ops/ipc_registry.h); 0 disables
     ipc_min_bytes_ = (genv.backend == "p2p" && EnvBool("HVD_IPC_REGISTRATION", true) && GpuContext::Get().Available())
                          ? std::max<int64_t>(16, EnvInt("HVD_IPC_MIN_BYTES", 4 << 20)) : 0;
-    genv.ipc_max_ranks = (int)EnvInt("HVD_IPC_MAX_RANKS", 2);
+    genv.ipc_max_ranks = (int)EnvInt("HVD_IPC_MAX_RANKS", 4);
     genv.latency_lane_bytes = std::min<int64_t>(1 << 20, std::max<int64_t>(0, EnvInt("HVD_LATENCY_LANE_BYTES", 256 << 10)));
     genv.adasum_persistent = EnvBool("HVD_ADASUM_PERSISTENT", true);
-    genv.dual_lane = EnvBool("HVD_DUAL_LANE_ALLREDUCE", true);
+    genv.dual_lane = EnvBool("HVD_DUAL_LANE_ALLREDUCE", false);
     genv.dual_lane_min_bytes = EnvInt("HVD_DUAL_LANE_MIN_BYTES", 64 << 20);
     genv.zero_copy_nvls_min_bytes = EnvInt("HVD_ZERO_COPY_NVLS_MIN_BYTES", 1 << 20);
     genv.calibrate = EnvBool("HVD_CALIBRATE", true) && !EnvBool(HOROVOD_AUTOTUNE, false);

@@ -601,18 +601,26 @@ def _fused_step(opt):
                 native.fused_sgd_step(ps, grads, bufs, float(group['lr']), float(mom), float(group.get('dampening', 0.0)),
                                       float(group.get('weight_decay', 0.0)), bool(group.get('nesterov', False)), 1.0, first)
             else:
-                exp_avg, exp_avg_sq = [], []
-                step = None
+                exp_avg, exp_avg_sq, steps = [], [], []
                 for p in ps:
                     st = opt.state[p]
                     if len(st) == 0 or 'exp_avg' not in st:
                         st['step'] = torch.tensor(0.0)
                         st['exp_avg'] = torch.zeros_like(p, dtype=torch.float32, memory_format=torch.preserve_format)
                         st['exp_avg_sq'] = torch.zeros_like(p, dtype=torch.float32, memory_format=torch.preserve_format)
-                    st['step'] = st['step'] + 1
-                    step = int(st['step'].item()) if torch.is_tensor(st['step']) else int(st['step'])
+                    if not torch.is_tensor(st['step']):
+                        st['step'] = torch.tensor(float(st['step']))
+                    steps.append(st['step'])
                     exp_avg.append(st['exp_avg'])
                     exp_avg_sq.append(st['exp_avg_sq'])
+                # one host-side call for the whole group instead of a tensor op per parameter (BERT-large: ~400 of them)
+                cpu_steps = [t for t in steps if not t.is_cuda]
+                if cpu_steps:
+                    torch._foreach_add_(cpu_steps, 1)
+                for t in steps:
+                    if t.is_cuda:
+                        t.add_(1)
+                step = int(steps[0].item())
                 b1, b2 = group['betas']
                 adamw = isinstance(opt, torch.optim.AdamW) or bool(group.get('decoupled_weight_decay', False))
                 native.fused_adam_step(ps, grads, exp_avg, exp_avg_sq, float(group['lr']), float(b1), float(b2),
