@@ -423,6 +423,9 @@ def _checks_extra(hvd, torch):
     res['allgather'] = bool((ag.view(size, 3)[:, 0].cpu() == torch.arange(size, dtype=torch.float32)).all())
     rs = hvd.reducescatter(torch.ones(size * 4, 5, device='cuda') * (rank + 1), op=hvd.Sum, name='chk.rs')
     res['reducescatter'] = bool((rs == exp_sum).all().item()) and tuple(rs.shape) == (4, 5)
+    a2a = hvd.alltoall(torch.arange(size * 4, device='cuda', dtype=torch.float32) + 1000 * rank, name='chk.a2a')
+    exp_a2a = torch.cat([torch.arange(rank * 4, rank * 4 + 4, dtype=torch.float32) + 1000 * r for r in range(size)]).cuda()
+    res['alltoall'] = bool(torch.equal(a2a, exp_a2a))
     b = torch.full((1 << 20,), float(rank), device='cuda')
     hvd.broadcast_(b, root_rank=size - 1, name='chk.bc')
     res['broadcast'] = bool((b == size - 1).all().item())

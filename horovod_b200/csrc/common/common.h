@@ -43,6 +43,7 @@ enum class ReduceOp : uint8_t { AVERAGE = 0, SUM = 1, ADASUM = 2, MIN = 3, MAX =
 const char* ReduceOpName(ReduceOp op);
 
 constexpr int CPU_DEVICE_ID = -1;
+constexpr int32_t kUniformSplits = -2;  // Request/Response::root_rank of an alltoall without explicit splits
 
 // Names with special meaning in the negotiation stream.
 constexpr const char* JOIN_TENSOR_NAME = "join.noname";

@@ -395,6 +395,12 @@ Response Controller::ConstructResponse(const std::string& name, const std::vecto
   resp.postscale = first.postscale;
   resp.reduce_op = first.reduce_op;
   resp.root_rank = first.root_rank;
+  if (t == RequestType::ALLTOALL) {
+    // uniform only if NO rank gave explicit splits and every rank sends the same number of rows
+    bool uniform = true;
+    for (auto& q : requests) if (q.root_rank != kUniformSplits || q.shape.empty() || q.shape[0] != first.shape[0]) uniform = false;
+    resp.root_rank = uniform ? kUniformSplits : 0;
+  }
   resp.symm_key = first.symm_key;
   for (auto& q : requests) if (q.symm_key != first.symm_key) resp.symm_key = -1;  // zero-copy only if EVERY rank registered it identically
   if (resp.symm_key < 0) {

@@ -682,7 +682,8 @@ Status Engine::ExecuteCpu(ProcessSet& ps, Entries& es, const Response& r) {
         for (int d = 1; d < e->shape.ndim(); ++d) row *= e->shape.dim(d);
         std::vector<int64_t> mine(n), all((size_t)n * n);
         for (int p = 0; p < n; ++p) mine[p] = e->splits[p];
-        t->AllgatherInts(mine.data(), n, all.data());
+        if (r.root_rank == kUniformSplits) std::fill(all.begin(), all.end(), mine[0]);  // negotiated: same shape, no explicit splits anywhere
+        else t->AllgatherInts(mine.data(), n, all.data());
         std::vector<int64_t> sb(n), rb(n);
         int64_t out_rows = 0;
         e->received_splits.assign(n, 0);
@@ -845,7 +846,8 @@ Status Engine::EnqueueAlltoall(std::shared_ptr<TensorTableEntry> e, int32_t psid
   if (!st.ok()) return st;
   const int n = ps->set_size();
   if (e->shape.ndim() < 1) return Status::InvalidArgument("alltoall requires a tensor with at least one dimension");
-  if (e->splits.empty()) {
+  const bool implicit_splits = e->splits.empty();
+  if (implicit_splits) {
     if (e->shape.dim(0) % n != 0)
       return Status::InvalidArgument("tensor must have first dimension divisible by the number of workers when no splits are specified.");
     e->splits.assign(n, (int32_t)(e->shape.dim(0) / n));
@@ -856,7 +858,12 @@ Status Engine::EnqueueAlltoall(std::shared_ptr<TensorTableEntry> e, int32_t psid
     if (sum > e->shape.dim(0)) return Status::InvalidArgument("Sum of splits entries is greater than the first dimension of tensor.");
   }
   e->process_set_id = psid; e->type = RequestType::ALLTOALL; e->enqueue_ns = NowNs(); AttachNvtx(e);
-  st = ps->queue.AddToTensorQueue(e, MakeRequest(*e, ps->set_rank(), RequestType::ALLTOALL));
+  Request q = MakeRequest(*e, ps->set_rank(), RequestType::ALLTOALL);
+  // root_rank is unused by alltoall: kUniformSplits marks "no splits given" — when every rank says so with the same shape the
+  // split matrix is known everywhere and the per-call exchange through the control plane (the reference's
+  // AlltoallGetRecvSplits, mpi_controller.cc:243) is skipped
+  q.root_rank = implicit_splits ? kUniformSplits : 0;
+  st = ps->queue.AddToTensorQueue(e, q);
   if (!st.ok()) return st;
   NotePending((int64_t)e->bytes());
   Wake();

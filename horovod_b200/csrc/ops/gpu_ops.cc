@@ -1132,7 +1132,8 @@ Status GpuOps::Alltoall(ProcessSet& ps, Entries& es, const Response& r, int devi
     // exchange the split matrix through the control plane (reference: AlltoallGetRecvSplits)
     std::vector<int64_t> mine(n), all((size_t)n * n);
     for (int p = 0; p < n; ++p) mine[p] = e->splits[p];
-    ps.transport->AllgatherInts(mine.data(), n, all.data());
+    if (r.root_rank == kUniformSplits) std::fill(all.begin(), all.end(), mine[0]);  // negotiated uniform splits: nothing to exchange
+    else ps.transport->AllgatherInts(mine.data(), n, all.data());
     std::vector<int64_t> sbytes(n), rbytes(n), sdisp(n + 1, 0), rdisp(n + 1, 0);
     e->received_splits.assign(n, 0);
     int64_t out_rows = 0;

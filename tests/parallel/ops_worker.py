@@ -242,6 +242,20 @@ def _():
         out = hvd.alltoall(t)
         exp = torch.cat([torch.arange(rank * 3, rank * 3 + 3).to(dtype) + 1000 * r for r in range(size)]).to(DEV)
         assert torch.equal(out, exp)
+        # no explicit splits but a different dim 0 on every rank (rank r sends r + 1 rows to each destination): the
+        # uniform-splits shortcut must NOT apply, the split matrix is exchanged
+        t = torch.full((size * (rank + 1), 2), float(rank), device=DEV).to(dtype)
+        out = hvd.alltoall(t, name='a2a.implicit.ragged.%s' % dtype)
+        assert out.shape[0] == sum(r + 1 for r in range(size)), out.shape
+        off = 0
+        for r in range(size):
+            assert (out[off:off + r + 1] == r).all(), (r, out)
+            off += r + 1
+        # one rank passes explicit (uniform) splits, the others none: same result as all-implicit
+        t = torch.arange(size * 2, device=DEV).to(dtype) + 100 * rank
+        out = hvd.alltoall(t, splits=[2] * size, name='a2a.mixed.%s' % dtype)[0] if rank == 0 else hvd.alltoall(t, name='a2a.mixed.%s' % dtype)
+        exp = torch.cat([torch.arange(rank * 2, rank * 2 + 2).to(dtype) + 100 * r for r in range(size)]).to(DEV)
+        assert torch.equal(out, exp), (out, exp)
         # uneven splits: rank r sends (d + 1) rows to destination d
         splits = torch.tensor([d + 1 for d in range(size)], dtype=torch.int32)
         rows = int(splits.sum())
