@@ -143,6 +143,36 @@ void TestValidation() {
   Request b0 = mk(0, {4}, DataType::FLOAT32, RequestType::BROADCAST), b1 = mk(1, {4}, DataType::FLOAT32, RequestType::BROADCAST);
   b1.root_rank = 1;
   CHECK_T(Controller::ConstructResponse("v", {b0, b1}, 2, {}).error_message.find("root") != std::string::npos);
+  // zero-copy keys: registered region only if identical everywhere; IPC (-2) only if EVERY rank offers a plain-allocation key
+  Request z0 = mk(0, {1024}), z1 = mk(1, {1024});
+  z0.device = z1.device = 0;
+  z0.symm_key = z1.symm_key = (3ll << 44) | 4096;
+  CHECK_T(Controller::ConstructResponse("v", {z0, z1}, 2, {}).symm_key == ((3ll << 44) | 4096));
+  z1.symm_key = (3ll << 44) | 8192;
+  CHECK_T(Controller::ConstructResponse("v", {z0, z1}, 2, {}).symm_key == -1);
+  z0.symm_key = -12345; z1.symm_key = -99;   // per-rank IPC keys differ by construction
+  CHECK_T(Controller::ConstructResponse("v", {z0, z1}, 2, {}).symm_key == -2);
+  z1.symm_key = -1;                          // one rank cannot export its tensor
+  CHECK_T(Controller::ConstructResponse("v", {z0, z1}, 2, {}).symm_key == -1);
+  z1.symm_key = -99;
+  CHECK_T(Controller::ConstructResponse("v", {z0}, 2, {1}).symm_key == -1);  // a joined rank has no tensor to register
+  // a response that carries a zero-copy key is never fused with its neighbours
+  {
+    std::deque<Response> zs;
+    Response a = MkResp("za", 1 << 20), b = MkResp("zb", 1 << 20), c = MkResp("zc", 1 << 20);
+    b.symm_key = -2;
+    zs.push_back(a); zs.push_back(b); zs.push_back(c);
+    auto fused = Controller::FuseResponses(zs, 1ll << 30, false);
+    CHECK_T(fused.size() == 2 && fused[0].tensor_names == std::vector<std::string>({"za", "zc"}) && fused[1].symm_key == -2);
+  }
+  // alltoall without explicit splits: "uniform" only when NO rank gave splits and every rank sends the same number of rows
+  Request a0 = mk(0, {8, 2}, DataType::FLOAT32, RequestType::ALLTOALL), a1 = mk(1, {8, 2}, DataType::FLOAT32, RequestType::ALLTOALL);
+  a0.root_rank = a1.root_rank = kUniformSplits;
+  CHECK_T(Controller::ConstructResponse("v", {a0, a1}, 2, {}).root_rank == kUniformSplits);
+  a1.root_rank = 0;  // explicit splits on one rank
+  CHECK_T(Controller::ConstructResponse("v", {a0, a1}, 2, {}).root_rank == 0);
+  a1.root_rank = kUniformSplits; a1.shape = {12, 2};  // different dim 0
+  CHECK_T(Controller::ConstructResponse("v", {a0, a1}, 2, {}).root_rank == 0);
 }
 
 void TestCache() {
