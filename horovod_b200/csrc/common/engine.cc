@@ -267,6 +267,8 @@ void Engine::BackgroundThread() {
                          ? std::max<int64_t>(16, EnvInt("HVD_IPC_MIN_BYTES", 4 << 20)) : 0;
     genv.ipc_max_ranks = (int)EnvInt("HVD_IPC_MAX_RANKS", 4);
     genv.latency_lane_bytes = std::min<int64_t>(1 << 20, std::max<int64_t>(0, EnvInt("HVD_LATENCY_LANE_BYTES", 256 << 10)));
+    // the reference's knob for concurrent responses (operations.cc:465): 1 = a single stream, i.e. no latency lane
+    if (EnvIsSet(HOROVOD_NUM_STREAMS) && EnvInt(HOROVOD_NUM_STREAMS, 1) <= 1 && !EnvIsSet("HVD_LATENCY_LANE_BYTES")) genv.latency_lane_bytes = 0;
     genv.adasum_persistent = EnvBool("HVD_ADASUM_PERSISTENT", true);
     genv.dual_lane = EnvBool("HVD_DUAL_LANE_ALLREDUCE", false);
     genv.dual_lane_min_bytes = EnvInt("HVD_DUAL_LANE_MIN_BYTES", 64 << 20);

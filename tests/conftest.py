@@ -23,7 +23,9 @@ def run_parallel(script, np=2, args=(), timeout=180, env=None, expect_fail=False
         e.update(env)
     path = script if os.path.isabs(script) else os.path.join(REPO, "tests", "parallel", script)
     cmd = [sys.executable, "-m", "horovod_b200.runner.launch", "-np", str(np), *launcher_args, sys.executable, path, *args]
-    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=e, timeout=timeout, cwd=REPO)
+    # the timeout only guards against hangs: on a loaded or freshly started box (first `import torch` can take a minute per
+    # process) a tight limit turns slowness into a failure, so never go below five minutes
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=e, timeout=max(timeout, 300), cwd=REPO)
     out = p.stdout.decode(errors="replace")
     if not expect_fail and p.returncode != 0:
         raise AssertionError(f"parallel run failed (rc={p.returncode}):\n{out[-6000:]}")

@@ -9,7 +9,7 @@ import pytest
 from conftest import REPO
 
 
-def hvdrun(*args, timeout=120, env=None):
+def hvdrun(*args, timeout=300, env=None):
     e = dict(os.environ, PYTHONPATH=REPO + os.pathsep + os.environ.get('PYTHONPATH', ''), HOROVOD_LOG_LEVEL='warning')
     e.update(env or {})
     p = subprocess.run([sys.executable, '-m', 'horovod_b200.runner.launch', *args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
@@ -47,7 +47,7 @@ def test_timestamp_prefix(native_built):
 
 def test_nonzero_exit_code_is_reported(native_built):
     code = "import os, sys, time; r = int(os.environ['HOROVOD_RANK']); time.sleep(0.5 if r else 30) if r == 0 else None; sys.exit(3 if r == 1 else 0)"
-    rc, out = hvdrun('-np', '2', sys.executable, '-c', code, timeout=60)
+    rc, out = hvdrun('-np', '2', sys.executable, '-c', code, timeout=300)
     assert rc != 0
     assert 'exited with non-zero status' in out and 'Exit code: 3' in out and 'Process name: 1' in out, out
 
