@@ -7,11 +7,15 @@ namespace {
 struct Domain {
   bool enabled = false;
   nvtxDomainHandle_t dom = nullptr;
+  // timeline mirror: same two domains as the reference (timeline.cc:332-425) so existing Nsight filters keep working
+  nvtxDomainHandle_t tl_dom = nullptr, tl_act_dom = nullptr;
   nvtxStringHandle_t names[(int)NvtxOp::COUNT] = {};
   Domain() {
     enabled = !EnvBool("HOROVOD_DISABLE_NVTX_RANGES", false);
     if (!enabled) return;
     dom = nvtxDomainCreateA("hvd");
+    tl_dom = nvtxDomainCreateA("HorovodTimeline");
+    tl_act_dom = nvtxDomainCreateA("HorovodTimelineActivities");
     static const char* kNames[] = {"HorovodAllreduce", "HorovodGroupedAllreduce", "HorovodAllgather", "HorovodGroupedAllgather",
                                    "HorovodBroadcast", "HorovodAlltoall", "HorovodReducescatter", "HorovodGroupedReducescatter",
                                    "HorovodJoin", "HorovodBarrier", "HorovodAdasum"};
@@ -43,19 +47,20 @@ void NvtxOpRange::End() {
   active_ = false;
 }
 
-uint64_t NvtxRangeStart(const std::string& message) {
+uint64_t NvtxRangeStart(const std::string& message, bool activity) {
   Domain& d = D();
   if (!d.enabled) return 0;
+  nvtxDomainHandle_t dom = activity ? d.tl_act_dom : d.tl_dom;
   nvtxEventAttributes_t a = {};
   a.version = NVTX_VERSION;
   a.size = NVTX_EVENT_ATTRIB_STRUCT_SIZE;
   a.messageType = NVTX_MESSAGE_TYPE_ASCII;
   a.message.ascii = message.c_str();
-  return (uint64_t)nvtxDomainRangeStartEx(d.dom, &a) + 1;  // +1: 0 stays "no range"
+  return (uint64_t)nvtxDomainRangeStartEx(dom, &a) + 1;  // +1: 0 stays "no range"
 }
-void NvtxRangeEnd(uint64_t id) {
+void NvtxRangeEnd(uint64_t id, bool activity) {
   if (id == 0) return;
-  nvtxDomainRangeEnd(D().dom, (nvtxRangeId_t)(id - 1));
+  nvtxDomainRangeEnd(activity ? D().tl_act_dom : D().tl_dom, (nvtxRangeId_t)(id - 1));
 }
 
 void NvtxMark(const char* message) {

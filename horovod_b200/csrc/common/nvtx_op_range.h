@@ -25,9 +25,10 @@ class NvtxOpRange {
   bool active_ = false;
 };
 
-// Free-form ranges of the timeline mirror ("<tensor>: <activity>"); 0 = not started (NVTX off).
-uint64_t NvtxRangeStart(const std::string& message);
-void NvtxRangeEnd(uint64_t id);
+// Free-form ranges of the timeline mirror ("<tensor>: <op or activity>") in the reference's domains: top-level ops in
+// "HorovodTimeline", nested activities in "HorovodTimelineActivities"; 0 = not started (NVTX off).
+uint64_t NvtxRangeStart(const std::string& message, bool activity);
+void NvtxRangeEnd(uint64_t id, bool activity);
 
 // instant marker in the hvd domain (cycle starts, autotune changes)
 void NvtxMark(const char* message);

@@ -41,8 +41,8 @@ void Timeline::Shutdown() {
   if (writer_.joinable()) writer_.join();
   if (file_) { if (!closed_) fputs("\n]\n", file_); fclose(file_); file_ = nullptr; }
   std::lock_guard<std::mutex> l(mu_);
-  for (auto& kv : nvtx_act_) NvtxRangeEnd(kv.second);
-  for (auto& kv : nvtx_top_) NvtxRangeEnd(kv.second);
+  for (auto& kv : nvtx_act_) NvtxRangeEnd(kv.second, true);
+  for (auto& kv : nvtx_top_) NvtxRangeEnd(kv.second, false);
   pids_.clear(); states_.clear(); nvtx_top_.clear(); nvtx_act_.clear();
 }
 
@@ -126,7 +126,7 @@ void Timeline::Start(const std::string& name, ResponseType type, size_t bytes) {
   std::string args = bytes ? "\"bytes\": " + std::to_string(bytes) : "";
   Push({'B', Pid(name), ResponseTypeName(type), args, NowUs()});
   states_[name] = State::TOP_LEVEL;
-  if (NvtxEnabled()) { NvtxRangeEnd(nvtx_top_[name]); nvtx_top_[name] = NvtxRangeStart(name + ": " + ResponseTypeName(type)); }
+  if (NvtxEnabled()) { NvtxRangeEnd(nvtx_top_[name], false); nvtx_top_[name] = NvtxRangeStart(name + ": " + ResponseTypeName(type), false); }
 }
 void Timeline::ActivityStart(const std::string& name, const std::string& activity) {
   if (!Initialized()) return;
@@ -135,7 +135,7 @@ void Timeline::ActivityStart(const std::string& name, const std::string& activit
   if (states_[name] == State::UNKNOWN) return;
   Push({'B', Pid(name), activity, "", NowUs()});
   states_[name] = State::ACTIVITY;
-  if (NvtxEnabled()) { NvtxRangeEnd(nvtx_act_[name]); nvtx_act_[name] = NvtxRangeStart(name + ": " + activity); }
+  if (NvtxEnabled()) { NvtxRangeEnd(nvtx_act_[name], true); nvtx_act_[name] = NvtxRangeStart(name + ": " + activity, true); }
 }
 void Timeline::ActivityEnd(const std::string& name) {
   if (!Initialized()) return;
@@ -143,7 +143,7 @@ void Timeline::ActivityEnd(const std::string& name) {
   if (states_[name] != State::ACTIVITY) return;
   Push({'E', Pid(name), "", "", NowUs()});
   states_[name] = State::TOP_LEVEL;
-  if (NvtxEnabled()) { NvtxRangeEnd(nvtx_act_[name]); nvtx_act_[name] = 0; }
+  if (NvtxEnabled()) { NvtxRangeEnd(nvtx_act_[name], true); nvtx_act_[name] = 0; }
 }
 void Timeline::ActivityStartAll(const std::vector<std::shared_ptr<TensorTableEntry>>& es, const std::string& a) {
   if (!Initialized()) return;
@@ -160,8 +160,8 @@ void Timeline::End(const std::string& name, const std::string& args) {
   if (states_[name] == State::ACTIVITY || states_[name] == State::TOP_LEVEL) Push({'E', Pid(name), "", args, NowUs()});
   states_[name] = State::UNKNOWN;
   if (NvtxEnabled()) {
-    auto a = nvtx_act_.find(name); if (a != nvtx_act_.end()) { NvtxRangeEnd(a->second); nvtx_act_.erase(a); }
-    auto t = nvtx_top_.find(name); if (t != nvtx_top_.end()) { NvtxRangeEnd(t->second); nvtx_top_.erase(t); }
+    auto a = nvtx_act_.find(name); if (a != nvtx_act_.end()) { NvtxRangeEnd(a->second, true); nvtx_act_.erase(a); }
+    auto t = nvtx_top_.find(name); if (t != nvtx_top_.end()) { NvtxRangeEnd(t->second, false); nvtx_top_.erase(t); }
   }
 }
 void Timeline::DeviceSpan(const std::vector<std::string>& names, const std::string& activity, int64_t start_us, int64_t dur_us) {
