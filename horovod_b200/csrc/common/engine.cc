@@ -568,13 +568,20 @@ void Engine::PerformOperation(ProcessSet& ps, Response& r) {
       std::vector<std::string> names;
       for (auto& e : es) if (e) names.push_back(e->name);
       const std::string act = std::string("GPU ") + ResponseTypeName(r.type);
-      finalizers_.Execute([this, done, names, tl_t0, tl_t1, tl_base, act] {
+      const uint64_t launched_ns = NowNs();
+      finalizers_.Execute([this, done, names, tl_t0, tl_t1, tl_base, act, launched_ns] {
         cudaSetDevice(done->device);
         cudaEventSynchronize(done->ev);
         if (tl_t0 && tl_t1 && tl_base && cudaEventSynchronize(tl_t1) == cudaSuccess) {
           float off_ms = 0, dur_ms = 0;
-          if (cudaEventElapsedTime(&off_ms, tl_base->ev, tl_t0) == cudaSuccess && cudaEventElapsedTime(&dur_ms, tl_t0, tl_t1) == cudaSuccess)
-            timeline_.DeviceSpan(names, act, timeline_.ToTimelineUs(tl_base->host_ns) + (int64_t)(off_ms * 1e3), (int64_t)(dur_ms * 1e3));
+          if (cudaEventElapsedTime(&off_ms, tl_base->ev, tl_t0) == cudaSuccess && cudaEventElapsedTime(&dur_ms, tl_t0, tl_t1) == cudaSuccess) {
+            const int64_t start_us = timeline_.ToTimelineUs(tl_base->host_ns) + (int64_t)(off_ms * 1e3);
+            // QUEUE (reference activity name, common.h:80-114): launched on the host, not yet running on the device — the
+            // stream was still busy or waiting for the tensors' ready events
+            const int64_t launched_us = timeline_.ToTimelineUs(launched_ns);
+            if (start_us > launched_us + 1) timeline_.DeviceSpan(names, HVD_ACT_QUEUE, launched_us, start_us - launched_us);
+            timeline_.DeviceSpan(names, act, start_us, (int64_t)(dur_ms * 1e3));
+          }
         }
         if (tl_t0) cudaEventDestroy(tl_t0);
         if (tl_t1) cudaEventDestroy(tl_t1);
