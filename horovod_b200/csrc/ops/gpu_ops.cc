@@ -500,7 +500,11 @@ void GpuOps::Calibrate(ProcessSet& ps, SymmTeam& team, int device) {
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(buf);
-    if (team.abort_state() != 0) return;  // a barrier timed out: keep the defaults (the next real op reports the failure)
+    // a barrier that timed out on ANY rank voids the measurement everywhere (collective decision: nobody may skip the
+    // broadcast below on its own); the defaults stay and the next real op reports the failure
+    uint64_t healthy = team.abort_state() == 0 ? 1 : 0;
+    t->AllreduceBits(&healthy, 1, nullptr, 0);
+    if (!healthy) return;
     if (me == 0) {
       int64_t oneshot_max = 0, nvls_min = 0;
       bool nvls_found = false;
