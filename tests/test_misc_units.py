@@ -167,3 +167,39 @@ def test_gpu_numa_cpu_list_from_sysfs(tmp_path):
     assert gpu_numa_cpus(0, 0x1b, 0, str(d)) is None            # no NUMA information
     assert _parse_cpulist('0-2,8,10-11') == {0, 1, 2, 8, 10, 11}
     assert bind_to_gpu_numa(0, str(d)) is None                   # no GPU here: never touches the affinity
+
+
+def test_fused_step_validation_is_pure_and_falls_back_cleanly(native_built):
+    """DistributedOptimizer(fused=True) on parameters the fused kernels cannot take (CPU tensors): the eligibility pass must
+    not touch any optimizer state, and the wrapped optimizer's own step() must then run exactly once (round-1 advisor
+    finding: the old code mutated momentum buffers / Adam step counts before bailing out and left '_hvd_init' in state_dict)."""
+    import copy
+
+    import torch
+
+    import horovod_b200.torch as hvd
+    from horovod_b200.torch.optimizer import _fused_plan
+    hvd.init()
+    try:
+        for make in (lambda ps: torch.optim.SGD(ps, lr=0.1, momentum=0.9), lambda ps: torch.optim.AdamW(ps, lr=0.01)):
+            torch.manual_seed(0)
+            model = torch.nn.Linear(6, 3)
+            ref = copy.deepcopy(model)
+            opt = hvd.DistributedOptimizer(make(model.parameters()), named_parameters=model.named_parameters(), fused=True)
+            ropt = make(ref.parameters())
+            for step in range(3):
+                x = torch.randn(4, 6, generator=torch.Generator().manual_seed(step))
+                for m, o in ((model, opt), (ref, ropt)):
+                    o.zero_grad()
+                    m(x).square().mean().backward()
+                assert _fused_plan(opt) is None            # CPU parameters: not eligible ...
+                before = {k: v for k, v in opt.state_dict()['state'].items()}
+                assert _fused_plan(opt) is None and opt.state_dict()['state'].keys() == before.keys()  # ... and nothing was touched
+                opt.step()
+                ropt.step()
+            for a, b in zip(model.parameters(), ref.parameters()):
+                torch.testing.assert_close(a, b)           # stepped exactly once per step()
+            for st in opt.state_dict()['state'].values():
+                assert '_hvd_init' not in st
+    finally:
+        hvd.shutdown()
