@@ -21,31 +21,30 @@ class SyncBatchNorm(_BatchNorm):
         if input.dim() < 2:
             raise ValueError('expected at least 2D input (got {}D input)'.format(input.dim()))
 
-    def _run_bn(self, input):
+    def _run_bn(self, input, factor):
         return F.batch_norm(input, self.running_mean, self.running_var, self.weight, self.bias,
-                            self.training or not self.track_running_stats, self.momentum, self.eps)
+                            self.training or not self.track_running_stats, factor, self.eps)
 
     @torch.jit.unused
-    def _maybe_run_sync_bn(self, input):
+    def _maybe_run_sync_bn(self, input, factor):
         if size() == 1:
-            return self._run_bn(input)
-        return _SyncBatchNorm.apply(input, self.weight, self.bias, self.running_mean, self.running_var, self.eps,
-                                    self.momentum)
+            return self._run_bn(input, factor)
+        return _SyncBatchNorm.apply(input, self.weight, self.bias, self.running_mean, self.running_var, self.eps, factor)
 
     def forward(self, input):
         self._check_input_dim(input)
+        # exponential averaging factor as in torch.nn.modules.batchnorm._BatchNorm.forward: momentum=None means a cumulative
+        # moving average over the batches seen so far
+        factor = 0.0 if self.momentum is None else self.momentum
         if self.training and self.track_running_stats:
             self.num_batches_tracked = self.num_batches_tracked + 1
+            if self.momentum is None:
+                factor = 1.0 / float(self.num_batches_tracked)
         if not self.training and self.track_running_stats:
-            return self._run_bn(input)
+            return self._run_bn(input, factor)
         if not input.is_cuda and size() > 1:
-            # momentum=None means a cumulative moving average (torch.nn.BatchNorm semantics)
-            momentum = self.momentum
-            if momentum is None:
-                momentum = 1.0 / float(self.num_batches_tracked) if self.track_running_stats else 0.0
-            return _SyncBatchNormCPU.apply(input, self.weight, self.bias, self.running_mean, self.running_var, self.eps,
-                                           momentum)
-        return self._maybe_run_sync_bn(input)
+            return _SyncBatchNormCPU.apply(input, self.weight, self.bias, self.running_mean, self.running_var, self.eps, factor)
+        return self._maybe_run_sync_bn(input, factor)
 
 
 class _SyncBatchNorm(Function):

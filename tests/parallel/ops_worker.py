@@ -667,6 +667,26 @@ def _():
     (yr * w).sum().backward()
     torch.testing.assert_close(x.grad, full.grad[rank * 4:(rank + 1) * 4], rtol=1e-3, atol=1e-4)
     torch.testing.assert_close(bn.running_mean, ref.running_mean, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(bn.running_var, ref.running_var, rtol=1e-4, atol=1e-5)
+    assert int(bn.num_batches_tracked) == 1
+    # momentum=None = cumulative moving average (torch.nn.BatchNorm semantics), two steps
+    bn2, ref2 = hvd.SyncBatchNorm(3, momentum=None).to(DEV), torch.nn.BatchNorm1d(3, momentum=None).to(DEV)
+    for it in range(2):
+        xs2 = [torch.randn(4, 3, generator=torch.Generator().manual_seed(10 * it + r)).to(DEV) for r in range(size)]
+        bn2(xs2[rank])
+        ref2(torch.cat(xs2))
+    torch.testing.assert_close(bn2.running_mean, ref2.running_mean, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(bn2.running_var, ref2.running_var, rtol=1e-4, atol=1e-5)
+    assert int(bn2.num_batches_tracked) == 2
+    # eval mode uses the running statistics and needs no communication; wrong input rank is rejected like in torch
+    bn.eval()
+    ref.eval()
+    torch.testing.assert_close(bn(xs[rank]), ref(xs[rank]), rtol=1e-4, atol=1e-5)
+    try:
+        hvd.SyncBatchNorm(3).to(DEV)(torch.randn(3, device=DEV))
+        raise AssertionError('1-D input accepted')
+    except ValueError:
+        pass
 
 
 @check('adasum')
