@@ -66,9 +66,28 @@ void WriteAll(int fd, const void* buf, size_t n) {
   }
 }
 
+// A peer that is alive but frozen (SIGSTOP, a hung node) never closes its socket: with HVD_TCP_TIMEOUT_SECONDS (default: the
+// value of HVD_SHM_TIMEOUT_SECONDS, else 0 = wait forever) a receive that makes no progress for that long fails instead of
+// blocking the cycle thread forever (the reference's Gloo transport gives up after HOROVOD_GLOO_TIMEOUT_SECONDS).
+double RecvTimeoutSeconds() {
+  static const double t = [] {
+    const char* e = getenv("HVD_TCP_TIMEOUT_SECONDS");
+    if (!e) e = getenv("HVD_SHM_TIMEOUT_SECONDS");
+    return e ? std::max(0.0, atof(e)) : 0.0;
+  }();
+  return t;
+}
+
 void ReadAll(int fd, void* buf, size_t n) {
   auto* p = (char*)buf;
+  const double timeout_s = RecvTimeoutSeconds();
   while (n) {
+    if (timeout_s > 0) {
+      struct pollfd pf {fd, POLLIN, 0};
+      int rc = poll(&pf, 1, (int)(timeout_s * 1000));
+      if (rc == 0) throw TransportError("a peer sent nothing for " + std::to_string((int)timeout_s) + " s (HVD_TCP_TIMEOUT_SECONDS): frozen or unreachable");
+      if (rc < 0) { if (errno == EINTR) continue; throw TransportError(std::string("poll failed: ") + strerror(errno)); }
+    }
     ssize_t k = ::recv(fd, p, n, 0);
     if (k == 0) throw TransportError("peer closed connection");
     if (k < 0) {
@@ -98,12 +117,20 @@ class TcpTransport : public Transport {
     if (rn == 0) { Send(sp, sbuf, sn); return; }
     int sfd = fd(sp), rfd = fd(rp);
     auto* s = (const char*)sbuf; auto* r = (char*)rbuf;
+    const double timeout_s = RecvTimeoutSeconds();
+    double last_progress = Now();
     while (sn || rn) {
       struct pollfd pf[2]; int np = 0, si = -1, ri = -1;
       if (sn) { pf[np] = {sfd, POLLOUT, 0}; si = np++; }
       if (rn) { pf[np] = {rfd, POLLIN, 0}; ri = np++; }
-      int rc = poll(pf, np, 5000);
+      int rc = poll(pf, np, timeout_s > 0 ? (int)std::min(5000.0, timeout_s * 1000) : 5000);
       if (rc < 0) { if (errno == EINTR) continue; throw TransportError("poll failed"); }
+      if (rc == 0) {
+        if (timeout_s > 0 && Now() - last_progress > timeout_s)
+          throw TransportError("no progress on a send/receive pair for " + std::to_string((int)timeout_s) + " s (HVD_TCP_TIMEOUT_SECONDS): peer frozen or unreachable");
+        continue;
+      }
+      last_progress = Now();
       if (ri >= 0 && (pf[ri].revents & (POLLIN | POLLHUP | POLLERR))) {
         ssize_t k = ::recv(rfd, r, rn, MSG_DONTWAIT);
         if (k == 0) throw TransportError("peer closed connection");

@@ -181,3 +181,11 @@ def test_shm_wait_timeout_on_a_stopped_peer(native_built):
     after the timeout instead of spinning forever."""
     rc, out = run_parallel("shm_timeout_worker.py", np=2, timeout=120, env={"HVD_SHM_TIMEOUT_SECONDS": "3"}, expect_fail=True)
     assert "TIMEOUT RAISED" in out and "NO ERROR" not in out, out[-3000:]
+
+
+def test_tcp_wait_timeout_on_a_stopped_peer(native_built):
+    """HVD_TCP_TIMEOUT_SECONDS: the same frozen peer with every negotiation round over sockets (HVD_CONTROL_PLANE=tcp, what a
+    multi-host job uses across hosts): a stopped process never closes its socket, the receive has to give up on its own."""
+    rc, out = run_parallel("shm_timeout_worker.py", np=2, timeout=120, expect_fail=True,
+                           env={"HVD_TCP_TIMEOUT_SECONDS": "3", "HVD_CONTROL_PLANE": "tcp"})
+    assert "TIMEOUT RAISED" in out and "NO ERROR" not in out, out[-3000:]
