@@ -26,8 +26,11 @@ def create_distributed_optimizer(keras, optimizer, name, device_dense, device_sp
             super().__init__(**kwargs)
             self._hvd_reduced = False
             self._hvd_local = set()
-            self._hvd_agg = hvd.LocalGradientAggregationHelper(backward_passes_per_step, self._hvd_allreduce,
-                                                               average_aggregated_gradients)
+            # local (unsynchronised) variables are filtered in _hvd_allreduce, the helper only keeps the window
+            self._hvd_agg = hvd.LocalGradientAggregationHelperEager(backward_passes_per_step, self._hvd_allreduce,
+                                                                    sparse_as_dense=True,
+                                                                    average_aggregated_gradients=average_aggregated_gradients,
+                                                                    process_set=process_set, scale_local_gradients=False)
 
         # -- local (non-synchronised) variables -----------------------------------------------------------------
         def register_local_var(self, var):
@@ -49,7 +52,7 @@ def create_distributed_optimizer(keras, optimizer, name, device_dense, device_sp
             pairs = list(grads_and_vars)
             grads, variables = [g for g, _ in pairs], [v for _, v in pairs]
             red = self._hvd_agg.compute_gradients(grads, variables)
-            if red is None:
+            if not self._hvd_agg.synced:      # still inside an aggregation window: nothing to apply on this pass
                 return None
             return list(zip(red, variables))
 

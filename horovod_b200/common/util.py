@@ -180,6 +180,23 @@ def get_extension_full_path(pkg_path=None, *args):
     return os.path.join(lib_dir(), '_hvd_torch.so')
 
 
+def get_ext_suffix():
+    """File suffix of Python extension modules of the running interpreter (reference common/util.py:26-35)."""
+    import sysconfig
+    return sysconfig.get_config_var('EXT_SUFFIX') or sysconfig.get_config_var('SO') or '.so'
+
+
+def check_extension(ext_name, ext_env_var=None, pkg_path=None, *args):
+    """Raises ImportError with a build hint when the native library behind `ext_name` (e.g. 'horovod.torch') is missing
+    (reference common/util.py:38-46; `ext_env_var` named the HOROVOD_WITH_* switch of the reference's per-framework builds —
+    here every front end shares one library, built by `python -m horovod_b200.build`)."""
+    import os
+    full_path = get_extension_full_path(pkg_path, *args)
+    if not os.path.exists(full_path):
+        raise ImportError('Extension %s has not been built: %s not found.\nRun `python -m horovod_b200.build` (or '
+                          '`python setup.py build_ext --inplace`) to build the native runtime.' % (ext_name, full_path))
+
+
 def _parse_cpulist(text):
     cpus = set()
     for part in text.strip().split(','):

@@ -68,6 +68,14 @@ try:
     raise AssertionError('list accepted')
 except ValueError:
     pass
+# module paths of the reference: horovod.mxnet.{mpi_ops,functions,compression}
+from horovod_b200.mxnet import compression, functions, mpi_ops
+assert mpi_ops.allreduce_ is hvd.allreduce_ and functions.broadcast_object is hvd.broadcast_object
+assert hvd.Compression.fp16 is compression.FP16Compressor and issubclass(compression.NoneCompressor, compression.Compressor)
+c, ctx = compression.FP16Compressor.compress(mx.nd.array(np.ones(3, np.float32)))
+assert 'float16' in str(c.dtype) and 'float32' in str(compression.FP16Compressor.decompress(c, ctx).dtype)
+assert hvd.broadcast_object({'k': r}, root_rank=n - 1)['k'] == n - 1 and hvd.allgather_object(r) == list(range(n))
+assert hvd.split_list([1, 2, 3], 2) == [[1, 2], [3]]
 hvd.barrier()
 if r == 0:
     print('MX FAKE OK')

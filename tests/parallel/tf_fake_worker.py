@@ -64,11 +64,37 @@ assert dense.shape == (n + 1, 3)
 
 # backward_passes_per_step aggregation helper
 calls = []
-helper = hvd.LocalGradientAggregationHelper(2, lambda g, v: calls.append(1) or [hvd.allreduce(x, op=hvd.Sum, name='agg') for x in g], True)
-assert helper.compute_gradients([tf.constant(np.ones(2) * 2.0)], [w[1]]) is None
-res = helper.compute_gradients([tf.constant(np.ones(2) * 4.0)], [w[1]])
-np.testing.assert_allclose(res[0].numpy(), np.ones(2) * 3.0 * n)
-assert len(calls) == 1
+for cls in (hvd.LocalGradientAggregationHelperEager, hvd.LocalGradientAggregationHelper):
+    calls = []
+    helper = cls(2, lambda g, v: calls.append(1) or [hvd.allreduce(x, op=hvd.Sum, name='agg') for x in g],
+                 average_aggregated_gradients=True)
+    helper.register_local_var(w[3])
+    part = helper.compute_gradients([tf.constant(np.ones(2) * 2.0), tf.constant(np.ones(2) * n)], [w[1], w[3]])
+    assert not helper.synced and not calls                  # first pass of the window: local running sums only
+    np.testing.assert_allclose(part[0].numpy(), np.ones(2) * 2.0)
+    applied = []
+    assert helper.apply_gradients(lambda: applied.append(1), object()) is None and not applied
+    res = helper.compute_gradients([tf.constant(np.ones(2) * 4.0), tf.constant(np.ones(2) * n)], [w[1], w[3]])
+    assert helper.synced and len(calls) == 1
+    np.testing.assert_allclose(res[0].numpy(), np.ones(2) * 3.0 * n)      # (2 + 4) summed over ranks / 2 passes
+    np.testing.assert_allclose(res[1].numpy(), np.ones(2))                # local: 2n / n ranks / 2 passes, never reduced
+    helper.apply_gradients(lambda: applied.append(1), object())
+    assert applied == [1]
+    # the next window starts from zero
+    part = helper.compute_gradients([tf.constant(np.ones(2) * 1.0), None], [w[1], w[3]])
+    np.testing.assert_allclose(part[0].numpy(), np.ones(2)) and part[1] is None
+    helper.compute_gradients([tf.constant(np.ones(2) * 1.0), None], [w[1], w[3]])
+try:
+    hvd.LocalGradientAggregationHelperEager(2, lambda g, v: g).compute_gradients([sl], [w[0]])
+    raise SystemExit('IndexedSlices must be rejected without sparse_as_dense')
+except ValueError:
+    pass
+from horovod_b200.tensorflow import functions, gradient_aggregation, gradient_aggregation_eager, mpi_ops, util  # module paths of the reference
+assert mpi_ops.allgather is hvd.allgather and functions.broadcast_variables is hvd.broadcast_variables
+assert hvd.handle_average_backwards_compatibility(None, True) == hvd.Average and hvd.handle_average_backwards_compatibility(None, None) == hvd.Average
+assert util.refs_to_vars(util.vars_to_refs([w[0]]))[0] is w[0] or hasattr(w[0], 'ref')
+assert gradient_aggregation.apply_op_to_not_none_tensors(lambda t, k: t * k, [None, 2], 3) == [None, 6]
+assert hvd.broadcast_object({'a': r}, root_rank=0, session=None)['a'] == 0 and hvd.allgather_object(r, session=None) == list(range(n))
 
 # callbacks
 from horovod_b200.tensorflow.keras.callbacks import MetricAverageCallback, BroadcastGlobalVariablesCallback, LearningRateWarmupCallback
