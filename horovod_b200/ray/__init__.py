@@ -1,4 +1,6 @@
-"""Ray integration (parity: horovod/ray/__init__.py: RayExecutor, ElasticRayExecutor, RayHostDiscovery)."""
+"""Ray integration (parity: horovod/ray/__init__.py: RayExecutor, BaseHorovodWorker, ElasticRayExecutor)."""
+from horovod_b200.ray.worker import BaseHorovodWorker  # noqa: F401
 from horovod_b200.ray.runner import RayExecutor, RayBackend  # noqa: F401
 from horovod_b200.ray.elastic import RayHostDiscovery, ElasticRayExecutor  # noqa: F401
-from horovod_b200.runner.cluster_job import WorkerActor as BaseHorovodWorker  # noqa: F401  (the reference's worker actor name)
+
+__all__ = ['RayExecutor', 'BaseHorovodWorker', 'ElasticRayExecutor', 'RayHostDiscovery', 'RayBackend']

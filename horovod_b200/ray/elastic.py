@@ -58,7 +58,7 @@ class ElasticRayExecutor:
                                start_timeout=start_timeout, **kwargs)
 
     def __init__(self, settings, use_gpu=False, cpus_per_slot=1, gpus_per_slot=None, env_vars=None, override_discovery=True,
-                 actor_factory=None):
+                 actor_factory=None, queue_factory=None):
         if gpus_per_slot and not use_gpu:
             raise ValueError('gpus_per_slot is set, but use_gpu is False. use_gpu must be True if gpus_per_slot is set.')
         gpus_per_slot = gpus_per_slot or 1
@@ -69,6 +69,7 @@ class ElasticRayExecutor:
         self.env_vars = dict(env_vars or {})
         self.driver, self.rendezvous = None, None
         self._actor_factory = actor_factory  # (hostname, env) -> object with .execute(fn) [tests]; default: Ray actor
+        self._queue_factory = queue_factory  # () -> picklable queue for run(callbacks=...); default: ray.util.queue.Queue
 
     def start(self):
         self.rendezvous = RendezvousServer(self.settings.verbose)
@@ -98,8 +99,35 @@ class ElasticRayExecutor:
                 ray.kill(actor)
         return _H()
 
+    def _log_queue(self):
+        if self._queue_factory is not None:
+            return self._queue_factory()
+        from ray.util.queue import Queue
+        return Queue()
+
     def run(self, worker_fn, callbacks=None):
+        """`callbacks`: every dict a worker hands to `horovod_b200.ray.ray_logger.log` is passed to each of them on the
+        driver while the job runs (reference elastic_v2.py `_process_calls`)."""
         results_q = queue.Queue()
+        stop_drain = threading.Event()
+        if callbacks:
+            import functools
+            from horovod_b200.runner.cluster_job import _with_log_queue
+            log_q = self._log_queue()
+            worker_fn = functools.partial(_with_log_queue, log_q, worker_fn, (), None)
+
+            def drain_once():
+                while not log_q.empty():
+                    item = log_q.get()
+                    for cb in callbacks:
+                        cb(item)
+
+            def drain_loop():
+                while not stop_drain.wait(0.1):
+                    drain_once()
+                drain_once()
+            drainer = threading.Thread(target=drain_loop, daemon=True)
+            drainer.start()
 
         def spawn(slot_info, events):
             env = dict(self.env_vars)
@@ -131,6 +159,9 @@ class ElasticRayExecutor:
         res = self.driver.get_results()
         self.driver.stop()
         self.rendezvous.stop()
+        if callbacks:
+            stop_drain.set()
+            drainer.join(timeout=10)
         if res.error_message:
             raise RuntimeError(res.error_message)
         out = {}

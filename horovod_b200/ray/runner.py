@@ -9,11 +9,16 @@ The scheduler-independent part (rank table, rendezvous, env hand-off, ordered re
 groups.  Pass `backend=` to run the same executor on another ActorBackend (the tests use LocalProcessBackend since Ray
 is not installed in this image).
 """
-from horovod_b200.runner.cluster_job import ActorBackend, ClusterJob, WorkerActor
+from dataclasses import dataclass
+from typing import Optional
+
+from horovod_b200.ray.adapter import Adapter, BaseParams
+from horovod_b200.ray.worker import BaseHorovodWorker
+from horovod_b200.runner.cluster_job import ActorBackend, ClusterJob
 
 
-class _Settings:
-    """What create_settings returns (reference MiniSettings)."""
+class MiniSettings:
+    """What create_settings returns (reference runner.py:25-42)."""
 
     def __init__(self, timeout_s=30, ssh_identity_file=None, ssh_str=None, placement_group_timeout_s=100, nics=None, verbose=0):
         self.timeout_s, self.ssh_identity_file, self.ssh_str = timeout_s, ssh_identity_file, ssh_str
@@ -43,7 +48,7 @@ class RayBackend(ActorBackend):
                 raise TimeoutError('Placement group creation timed out. Make sure your cluster either has enough resources or use an '
                                    'autoscaling cluster. Current resources available: %s, resources requested by the placement group: %s'
                                    % (ray.available_resources(), bundles))
-        self._remote_cls = ray.remote(WorkerActor)
+        self._remote_cls = ray.remote(BaseHorovodWorker)
 
     def create(self, index, env=None):
         from ray.util.scheduling_strategies import PlacementGroupSchedulingStrategy
@@ -65,6 +70,14 @@ class RayBackend(ActorBackend):
     def kill(self, handle):
         self.ray.kill(handle)
 
+    def make_queue(self):
+        from ray.util.queue import Queue
+        return Queue()
+
+    def ready(self, futures, timeout=0.0):
+        done, _ = self.ray.wait(list(futures), num_returns=len(futures), timeout=timeout)
+        return len(done) == len(futures)
+
     def shutdown(self):
         if self._own_pg and self.pg is not None:
             from ray.util.placement_group import remove_placement_group
@@ -72,95 +85,64 @@ class RayBackend(ActorBackend):
             self.pg = None
 
 
-class RayExecutor:
-    """Job class for hvd + Ray.
+_Settings = MiniSettings
 
-    Either `num_workers` (packed wherever resources are) or `num_hosts` x `num_workers_per_host` (one bundle group per
-    host, spread strictly).  `use_gpu` gives every worker `gpus_per_worker` GPUs; CUDA_VISIBLE_DEVICES inside an
-    actor is what Ray sets, and hvd's local_rank indexes into it.
-    """
 
-    @classmethod
-    def create_settings(cls, timeout_s=30, ssh_identity_file=None, ssh_str=None, placement_group_timeout_s=100, nics=None):
-        return _Settings(timeout_s, ssh_identity_file, ssh_str, placement_group_timeout_s, nics)
+@dataclass
+class StaticParams(BaseParams):
+    """A job of fixed size: `num_workers` packed wherever resources are, or `num_hosts` x `num_workers_per_host`."""
+    num_workers: Optional[int] = None
+    num_hosts: Optional[int] = None
+    num_workers_per_host: int = 1
+    use_current_placement_group: bool = True
 
-    def __init__(self, settings=None, num_workers=None, num_hosts=None, num_workers_per_host=1, cpus_per_worker=1, use_gpu=False,
-                 gpus_per_worker=None, use_current_placement_group=True, backend=None, env_vars=None, min_workers=None,
-                 max_workers=None, reset_limit=None, cooldown_range=None, elastic_timeout=600, override_discovery=True,
-                 elastic_actor_factory=None):
-        self.elastic = min_workers is not None or max_workers is not None
-        if self.elastic:
-            if num_workers is not None or num_hosts is not None:
-                raise ValueError('`num_workers` / `num_hosts` describe a static job; use `min_workers` / `max_workers` alone for an elastic one.')
-            if min_workers is None or min_workers < 1:
-                raise ValueError('`min_workers` must be provided (>= 1) for an elastic job.')
-            if max_workers is not None and max_workers < min_workers:
-                raise ValueError('`max_workers` (%s) must not be smaller than `min_workers` (%s).' % (max_workers, min_workers))
-            self._elastic_args = dict(min_workers=min_workers, max_workers=max_workers, reset_limit=reset_limit,
-                                      cooldown_range=cooldown_range, elastic_timeout=elastic_timeout,
-                                      override_discovery=override_discovery, actor_factory=elastic_actor_factory)
-            num_workers = min_workers
-        if num_workers is None and num_hosts is None:
+    def __post_init__(self):
+        super().__post_init__()
+        if self.num_workers is None and self.num_hosts is None:
             raise ValueError('Either `num_workers` or `num_hosts` must be set.')
-        if num_workers is not None and num_hosts is not None:
+        if self.num_workers is not None and self.num_hosts is not None:
             raise ValueError('Only one of `num_workers` and `num_hosts` may be set.')
-        if gpus_per_worker and not use_gpu:
-            raise ValueError('gpus_per_worker is set, but use_gpu is False. use_gpu must be True if gpus_per_worker is set.')
-        if use_gpu and isinstance(gpus_per_worker, int) and gpus_per_worker < 1:
-            raise ValueError(f'gpus_per_worker must be >= 1: Got {gpus_per_worker}.')
-        self.settings = settings or _Settings()
-        self.colocated = num_hosts is not None
-        self.num_workers = num_workers if num_workers is not None else num_hosts * num_workers_per_host
-        self.num_hosts, self.num_workers_per_host = num_hosts, num_workers_per_host
-        self.cpus_per_worker, self.use_gpu = cpus_per_worker, use_gpu
-        self.gpus_per_worker = (gpus_per_worker or 1) if use_gpu else 0
-        self.use_current_placement_group = use_current_placement_group
-        self.env_vars = dict(env_vars or {})
-        self._backend, self.job = backend, None
 
-    def _placement(self):
+    @property
+    def elastic(self):
+        return False
+
+    @property
+    def adapter(self):
+        return StaticAdapter
+
+    @property
+    def total_workers(self):
+        return self.num_workers if self.num_workers is not None else self.num_hosts * self.num_workers_per_host
+
+    def placement(self):
         """(bundles, strategy, worker -> bundle index, per-worker resources)"""
         from horovod_b200.ray import strategy
-        if self.colocated:
+        if self.num_hosts is not None:
             plan = strategy.ColocatedStrategy(self.num_hosts, self.num_workers_per_host, self.cpus_per_worker, self.gpus_per_worker)
         else:
             plan = strategy.PackStrategy(self.num_workers, self.cpus_per_worker, self.gpus_per_worker)
         return plan.describe()
 
-    def _start_elastic(self, extra_env_vars):
-        from horovod_b200.ray.elastic import ElasticRayExecutor
-        a = self._elastic_args
-        settings = ElasticRayExecutor.create_settings(min_num_proc=a['min_workers'], max_num_proc=a['max_workers'],
-                                                      reset_limit=a['reset_limit'], elastic_timeout=a['elastic_timeout'],
-                                                      timeout_s=self.settings.timeout_s, nics=self.settings.nics,
-                                                      **({'cooldown_range': a['cooldown_range']} if a['cooldown_range'] else {}))
-        if not a['override_discovery']:
-            settings.discovery = getattr(self.settings, 'discovery', None)
-        env = dict(self.env_vars)
-        env.update(extra_env_vars or {})
-        self._elastic_executor = ElasticRayExecutor(settings, use_gpu=self.use_gpu, cpus_per_slot=self.cpus_per_worker,
-                                                    gpus_per_slot=self.gpus_per_worker or None, env_vars=env,
-                                                    override_discovery=a['override_discovery'], actor_factory=a['actor_factory'])
-        self._elastic_executor.start()
+
+class StaticAdapter(Adapter):
+    """Fixed set of workers inside one placement group (reference runner.py:424-660).  The scheduler-independent part is
+    `ClusterJob`; `backend=` swaps Ray for another ActorBackend."""
+
+    def __init__(self, settings, params, env_vars=None, backend=None):
+        self.settings, self.params = settings, params
+        self.env_vars = dict(env_vars or {})
+        self.backend, self.job = backend, None
 
     def start(self, executable_cls=None, executable_args=None, executable_kwargs=None, extra_env_vars=None):
-        """Creates the workers, assigns ranks and (optionally) instantiates `executable_cls` on each of them.  An elastic
-        executor (`min_workers` / `max_workers`) starts discovery + rendezvous instead; its workers are created by `run`."""
-        if self.elastic:
-            if executable_cls is not None:
-                raise ValueError('executable_cls is not supported by the elastic executor: workers come and go between resets.')
-            return self._start_elastic(extra_env_vars)
-        backend = self._backend
-        if backend is None:
-            bundles, strat, worker_bundle, worker_res = self._placement()
-            backend = RayBackend(bundles, strat, self.settings.placement_group_timeout_s, self.use_current_placement_group,
-                                 worker_bundle, worker_res)
-            self._backend = backend
+        if self.backend is None:
+            bundles, strat, worker_bundle, worker_res = self.params.placement()
+            self.backend = RayBackend(bundles, strat, self.settings.placement_group_timeout_s,
+                                      self.params.use_current_placement_group, worker_bundle, worker_res)
         env = dict(self.env_vars)
         env.update(extra_env_vars or {})
-        self.job = ClusterJob(backend, self.num_workers, env=env, nics=self.settings.nics, verbose=getattr(self.settings, 'verbose', 0),
-                              start_timeout=max(self.settings.timeout_s, 30)).start()
-        self._has_executable = executable_cls is not None
+        self.job = ClusterJob(self.backend, self.params.total_workers, env=env, nics=self.settings.nics,
+                              verbose=getattr(self.settings, 'verbose', 0), start_timeout=max(self.settings.timeout_s, 30)).start()
         if executable_cls is not None:
             a, k = tuple(executable_args or ()), dict(executable_kwargs or {})
 
@@ -170,32 +152,103 @@ class RayExecutor:
                 return True
             self.job.run(make)
 
-    def execute(self, fn):
-        """fn(executable) on every worker (the object created by start(executable_cls=...)); results in rank order."""
+    @staticmethod
+    def _on_executable(fn):
         def call():
             import builtins
             return fn(getattr(builtins, '_hvd_ray_executable', None))
-        return self.job.run(call)
+        return call
+
+    def execute(self, fn, callbacks=None):
+        return self.job.run(self._on_executable(fn), callbacks=callbacks)
 
     def run(self, fn, args=None, kwargs=None, callbacks=None):
-        if self.elastic:
-            import functools
-            return self._elastic_executor.run(functools.partial(fn, *tuple(args or ()), **dict(kwargs or {})), callbacks=callbacks)
-        return self.job.run(fn, tuple(args or ()), dict(kwargs or {}))
+        return self.job.run(fn, tuple(args or ()), dict(kwargs or {}), callbacks=callbacks)
 
-    def run_remote(self, fn, args=None, kwargs=None):
-        """Non-blocking: returns the backend's futures (Ray ObjectRefs) in rank order."""
+    def run_remote(self, fn, args=None, kwargs=None, callbacks=None):
         return self.job.run_remote(fn, tuple(args or ()), dict(kwargs or {}))
 
     def execute_single(self, fn):
-        def call():
-            import builtins
-            return fn(getattr(builtins, '_hvd_ray_executable', None))
-        return self.job.run_single(call, 0)
+        return self.job.run_single(self._on_executable(fn), 0)
 
     def shutdown(self):
         if self.job:
             self.job.shutdown()
             self.job = None
-        if hasattr(self._backend, 'shutdown'):
-            self._backend.shutdown()
+        if hasattr(self.backend, 'shutdown'):
+            self.backend.shutdown()
+
+
+class RayExecutor:
+    """Job class for hvd + Ray.
+
+    Either `num_workers` (packed wherever resources are) or `num_hosts` x `num_workers_per_host` (one bundle group per
+    host, spread strictly), or — elastic — `min_workers` / `max_workers`.  `use_gpu` gives every worker `gpus_per_worker`
+    GPUs; CUDA_VISIBLE_DEVICES inside an actor is what Ray sets, and hvd's local_rank indexes into it.  The keyword
+    arguments become a params object (`StaticParams` / `elastic_v2.ElasticParams`) whose adapter does the work.
+    """
+
+    @classmethod
+    def create_settings(cls, timeout_s=30, ssh_identity_file=None, ssh_str=None, placement_group_timeout_s=100, nics=None):
+        return MiniSettings(timeout_s, ssh_identity_file, ssh_str, placement_group_timeout_s, nics)
+
+    def __init__(self, settings=None, num_workers=None, num_hosts=None, num_workers_per_host=1, cpus_per_worker=1, use_gpu=False,
+                 gpus_per_worker=None, use_current_placement_group=True, backend=None, env_vars=None, min_workers=None,
+                 max_workers=None, reset_limit=None, cooldown_range=None, elastic_timeout=600, override_discovery=True,
+                 elastic_actor_factory=None, elastic_queue_factory=None):
+        self.settings = settings or MiniSettings()
+        self.env_vars = dict(env_vars or {})
+        if min_workers is not None or max_workers is not None:
+            if num_workers is not None or num_hosts is not None:
+                raise ValueError('`num_workers` / `num_hosts` describe a static job; use `min_workers` / `max_workers` alone for an elastic one.')
+            from horovod_b200.ray.elastic_v2 import ElasticParams
+            self.params = ElasticParams(cpus_per_worker=cpus_per_worker, use_gpu=use_gpu, gpus_per_worker=gpus_per_worker,
+                                        min_workers=min_workers, max_workers=max_workers, reset_limit=reset_limit,
+                                        cooldown_range=cooldown_range, elastic_timeout=elastic_timeout,
+                                        override_discovery=override_discovery)
+            self.adapter = self.params.adapter(self.settings, self.params, env_vars=self.env_vars, actor_factory=elastic_actor_factory,
+                                               queue_factory=elastic_queue_factory)
+        else:
+            self.params = StaticParams(cpus_per_worker=cpus_per_worker, use_gpu=use_gpu, gpus_per_worker=gpus_per_worker,
+                                       num_workers=num_workers, num_hosts=num_hosts, num_workers_per_host=num_workers_per_host,
+                                       use_current_placement_group=use_current_placement_group)
+            self.adapter = self.params.adapter(self.settings, self.params, env_vars=self.env_vars, backend=backend)
+
+    # -- what callers and tests read ------------------------------------------------------------------------------------------
+    @property
+    def elastic(self):
+        return self.params.elastic
+
+    @property
+    def num_workers(self):
+        return self.params.min_workers if self.elastic else self.params.total_workers
+
+    @property
+    def job(self):
+        return getattr(self.adapter, 'job', None)
+
+    def _placement(self):
+        return self.params.placement()
+
+    # -- delegations ----------------------------------------------------------------------------------------------------------
+    def start(self, executable_cls=None, executable_args=None, executable_kwargs=None, extra_env_vars=None):
+        """Creates the workers, assigns ranks and (optionally) instantiates `executable_cls` on each of them.  An elastic
+        executor (`min_workers` / `max_workers`) starts discovery + rendezvous instead; its workers are created by `run`."""
+        return self.adapter.start(executable_cls, executable_args, executable_kwargs, extra_env_vars)
+
+    def execute(self, fn, callbacks=None):
+        """fn(executable) on every worker (the object created by start(executable_cls=...)); results in rank order."""
+        return self.adapter.execute(fn, callbacks=callbacks)
+
+    def run(self, fn, args=None, kwargs=None, callbacks=None):
+        return self.adapter.run(fn, args=args, kwargs=kwargs, callbacks=callbacks)
+
+    def run_remote(self, fn, args=None, kwargs=None, callbacks=None):
+        """Non-blocking: returns the backend's futures (Ray ObjectRefs) in rank order."""
+        return self.adapter.run_remote(fn, args=args, kwargs=kwargs, callbacks=callbacks)
+
+    def execute_single(self, fn):
+        return self.adapter.execute_single(fn)
+
+    def shutdown(self):
+        return self.adapter.shutdown()

@@ -61,6 +61,25 @@ class ActorBackend:
     def kill(self, handle):
         raise NotImplementedError
 
+    # -- optional: needed only for run(..., callbacks=[...]) ------------------------------------------------------------
+    def make_queue(self):
+        """A queue object that can be pickled into the workers (worker -> driver messages)."""
+        raise NotImplementedError('%s has no worker -> driver queue: run() cannot take callbacks' % type(self).__name__)
+
+    def ready(self, futures, timeout=0.0):
+        """True when every future is resolved; waits at most `timeout` seconds."""
+        raise NotImplementedError
+
+
+def _with_log_queue(queue, fn, args, kwargs):
+    """Runs inside a worker: whatever `horovod_b200.ray.ray_logger.log(...)` receives travels to the driver's callbacks."""
+    from horovod_b200.ray import ray_logger
+    ray_logger.configure(queue)
+    try:
+        return fn(*args, **(kwargs or {}))
+    finally:
+        ray_logger.configure(None)
+
 
 # ---- local subprocess backend ----------------------------------------------------------------------------------------
 def _proc_main(index, conn, env):
@@ -92,6 +111,29 @@ class LocalProcessBackend(ActorBackend):
     def __init__(self, node_ids=None, start_method='spawn'):
         self.ctx = mp.get_context(start_method)
         self.node_ids = node_ids or {}
+        self._manager = None
+
+    def make_queue(self):
+        if self._manager is None:
+            self._manager = self.ctx.Manager()
+        return self._manager.Queue()
+
+    def ready(self, futures, timeout=0.0):
+        import time
+        from multiprocessing.connection import wait
+        deadline = time.monotonic() + (timeout or 0.0)
+        pending = [f.conn for f in futures]
+        while True:
+            pending = [c for c in pending if not c.poll(0)]
+            left = deadline - time.monotonic()
+            if not pending or left <= 0:
+                return not pending
+            wait(pending, left)
+
+    def shutdown(self):
+        if self._manager is not None:
+            self._manager.shutdown()
+            self._manager = None
 
     def create(self, index, env=None):
         parent, child = self.ctx.Pipe()
@@ -185,10 +227,29 @@ class ClusterJob:
         order = sorted(range(self.num_workers), key=lambda i: self.slots[i].rank)
         return [self.handles[i] for i in order]
 
-    def run(self, fn, args=(), kwargs=None, timeout=None):
-        """fn(*args, **kwargs) on every worker; results in rank order."""
-        futures = [self.backend.call(h, 'execute', fn, args, kwargs) for h in self.by_rank()]
-        return self.backend.get(futures, timeout)
+    def run(self, fn, args=(), kwargs=None, timeout=None, callbacks=None):
+        """fn(*args, **kwargs) on every worker; results in rank order.  With `callbacks`, every dict a worker passes to
+        `horovod_b200.ray.ray_logger.log` is handed to each callback on the driver while the workers run."""
+        if not callbacks:
+            futures = [self.backend.call(h, 'execute', fn, args, kwargs) for h in self.by_rank()]
+            return self.backend.get(futures, timeout)
+        q = self.backend.make_queue()
+        futures = [self.backend.call(h, 'execute', _with_log_queue, (q, fn, tuple(args), kwargs)) for h in self.by_rank()]
+
+        def drain():
+            while not q.empty():
+                item = q.get()
+                for cb in callbacks:
+                    cb(item)
+        import time
+        t0 = time.monotonic()
+        while not self.backend.ready(futures, 0.1):
+            drain()
+            if timeout is not None and time.monotonic() - t0 > timeout:
+                raise TimeoutError('workers did not finish within %s s' % timeout)
+        out = self.backend.get(futures, timeout)
+        drain()
+        return out
 
     def run_remote(self, fn, args=(), kwargs=None):
         return [self.backend.call(h, 'execute', fn, args, kwargs) for h in self.by_rank()]

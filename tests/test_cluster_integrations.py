@@ -214,3 +214,74 @@ def test_spark_run_elastic_retries_with_fewer_tasks(native_built, tmp_path):
     with pytest.raises(RuntimeError, match='too wide'):                                          # may not shrink below min_num_proc
         hvd_spark.run_elastic(_fails_until_two, args=(str(tmp_path),), num_proc=3, min_num_proc=3, reset_limit=1, _launch=_mp_launch,
                               start_timeout=120, verbose=0)
+
+
+def _logging_worker(scale):
+    from horovod_b200.ray import ray_logger
+    rank = int(os.environ['HOROVOD_RANK'])
+    for step in range(3):
+        assert ray_logger.log({'rank': rank, 'step': step, 'loss': scale * step})
+    return rank
+
+
+def test_ray_executor_callbacks_receive_worker_logs(native_built):
+    """run(fn, callbacks=[...]): dicts passed to ray_logger.log inside the workers reach the driver's callbacks (reference
+    test_ray.py::test_horovod_train with callbacks); without callbacks `log` is a no-op that returns False."""
+    from horovod_b200.ray import RayExecutor, ray_logger
+    assert ray_logger.log({'x': 1}) is False
+    ex = RayExecutor(RayExecutor.create_settings(timeout_s=30), num_workers=2, backend=LocalProcessBackend(), env_vars={'OMP_NUM_THREADS': '1'})
+    ex.start()
+    seen = []
+    try:
+        assert ex.run(_logging_worker, args=[0.5], callbacks=[seen.append]) == [0, 1]
+        assert ex.run(lambda: __import__('horovod_b200.ray.ray_logger', fromlist=['x']).log({'late': 1})) == [False, False]
+    finally:
+        ex.shutdown()
+    assert sorted((d['rank'], d['step']) for d in seen) == [(r, s) for r in (0, 1) for s in range(3)]
+    assert all(d['loss'] == 0.5 * d['step'] for d in seen)
+
+
+def test_unified_elastic_executor_callbacks_and_unsupported_calls(native_built):
+    """Elastic flavour of the unified executor: callbacks travel through the queue factory; the fixed-worker-set calls
+    (execute / run_remote) say why they do not exist."""
+    import multiprocessing as mp
+    from horovod_b200.ray import RayExecutor
+    from horovod_b200.ray.elastic_v2 import ElasticAdapter, ElasticParams
+    from horovod_b200.runner.elastic.discovery import FixedHosts
+
+    backend = LocalProcessBackend()
+    manager = mp.get_context('spawn').Manager()
+    created = []
+
+    def actor_factory(hostname, env):
+        h = backend.create(len(created), dict(env, OMP_NUM_THREADS='1', HOROVOD_LOG_LEVEL='warning'))
+        created.append(h)
+
+        class Actor:
+            def execute(self, fn):
+                return backend.get([backend.call(h, 'execute', fn)], 120)[0]
+
+            def kill(self):
+                backend.kill(h)
+        return Actor()
+
+    settings = RayExecutor.create_settings(timeout_s=30)
+    settings.discovery = FixedHosts({'localhost': 2})
+    ex = RayExecutor(settings, min_workers=2, max_workers=2, override_discovery=False, elastic_actor_factory=actor_factory,
+                     elastic_queue_factory=manager.Queue, env_vars={'HVD_TEST_FLAG': 'y'})
+    assert isinstance(ex.params, ElasticParams) and isinstance(ex.adapter, ElasticAdapter) and ex.elastic
+    ex.start()
+    seen = []
+    try:
+        with pytest.raises(NotImplementedError):
+            ex.execute(lambda t: t)
+        with pytest.raises(NotImplementedError):
+            ex.run_remote(lambda: 1)
+        res = ex.run(_logging_worker, args=[2.0], callbacks=[seen.append])
+    finally:
+        for h in created:
+            backend.kill(h)
+        ex.shutdown()
+        manager.shutdown()
+    assert sorted(res) == [0, 1]
+    assert sorted((d['rank'], d['step']) for d in seen) == [(r, s) for r in (0, 1) for s in range(3)]

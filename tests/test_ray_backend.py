@@ -111,3 +111,71 @@ def test_ray_backend_against_stand_in(tmp_path):
     script.write_text(SCRIPT)
     r = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and 'RAY BACKEND OK' in r.stdout, (r.stdout[-2000:], r.stderr[-4000:])
+
+
+def test_params_and_adapter_interfaces():
+    from horovod_b200.ray.adapter import Adapter, BaseParams
+    from horovod_b200.ray.elastic_v2 import ElasticAdapter, ElasticParams
+    from horovod_b200.ray.runner import StaticAdapter, StaticParams
+    p = StaticParams(num_hosts=2, num_workers_per_host=3, use_gpu=True)
+    assert not p.elastic and p.adapter is StaticAdapter and p.total_workers == 6 and p.gpus_per_worker == 1
+    assert StaticParams(num_workers=4).gpus_per_worker == 0
+    with pytest.raises(ValueError):
+        StaticParams()
+    with pytest.raises(ValueError):
+        BaseParams(gpus_per_worker=2)
+    e = ElasticParams(min_workers=2, max_workers=4, cooldown_range=[1, 2])
+    assert e.elastic and e.adapter is ElasticAdapter
+    with pytest.raises(ValueError):
+        ElasticParams(min_workers=0)
+    assert issubclass(StaticAdapter, Adapter) and issubclass(ElasticAdapter, Adapter)
+    with pytest.raises(TypeError):
+        Adapter()                                                        # abstract
+
+
+def test_base_worker_and_utils(monkeypatch):
+    from horovod_b200.ray import BaseHorovodWorker, utils
+    w = BaseHorovodWorker(world_rank=3, world_size=8)
+    assert w.update_env_vars({'HVD_FAKE_VAR': 7}) and w.env_vars()['HVD_FAKE_VAR'] == '7'
+    monkeypatch.setenv('CUDA_VISIBLE_DEVICES', '2,5')
+    assert w.get_gpu_ids() == ['2', '5']
+    assert w.execute(lambda a, b=1: a + b, (1,), {'b': 2}) == 3
+
+    class Exe:
+        def __init__(self, k, scale=1):
+            self.v = k * scale
+    w.start_executable(Exe, [3], {'scale': 2})
+    assert w.execute(lambda exe: exe.v) == 6
+    assert utils.nics_to_env_var({'eth1', 'eth0'}) == {'HOROVOD_GLOO_IFACE': 'eth0', 'NCCL_SOCKET_IFNAME': 'eth0,eth1'}
+
+    class S:
+        nics = None
+    s = S()
+    s.nics = ['ib0']
+    assert utils.detect_nics(s, ['a', 'b']) == {'ib0'}
+    s.nics = None
+    assert utils.detect_nics(s, ['a']) and isinstance(utils.detect_nics(s, ['a']), set)      # one host: whatever is local
+    tables = {'w1': {'lo': ['127.0.0.1'], 'eth0': ['10.0.0.1'], 'ib0': ['10.1.0.1']}, 'w2': {'lo': ['127.0.0.1'], 'eth0': ['10.0.0.2']}}
+    assert utils.detect_nics(s, ['a', 'b'], ['w1', 'w2'], call=lambda w, fn: tables[w]) == {'eth0'}
+    tables['w2'] = {'lo': ['127.0.0.1'], 'enp1': ['10.0.0.2']}
+    with pytest.raises(RuntimeError, match='common'):
+        utils.detect_nics(s, ['a', 'b'], ['w1', 'w2'], call=lambda w, fn: tables[w])
+
+
+def test_test_discovery_adds_and_removes_hosts(monkeypatch):
+    from horovod_b200.ray.elastic_v2 import TestDiscovery
+    nodes = [{'alive': True, 'NodeManagerAddress': '10.0.0.%d' % i, 'Resources': {'CPU': 4.0}} for i in range(1, 5)]
+    clock = [1000.0]
+    monkeypatch.setattr('horovod_b200.ray.elastic_v2.time.time', lambda: clock[0])
+    d = TestDiscovery(min_hosts=2, max_hosts=3, change_frequency_s=10, nodes_fn=lambda: nodes, verbose=False, seed=1)
+    assert len(d.find_available_hosts_and_slots()) == 4            # nothing changes before the first period is over
+    sizes = []
+    for _ in range(40):
+        clock[0] += 11
+        hosts = d.find_available_hosts_and_slots()
+        assert all(s == 4 for s in hosts.values())
+        sizes.append(len(hosts))
+    assert sizes[0] == 3 and min(sizes) >= 2 and max(sizes[1:]) <= 3 and len(set(sizes)) > 1, sizes
+    nodes.pop()                                                    # a removed host that really disappeared is forgotten
+    clock[0] += 11
+    assert set(d.find_available_hosts_and_slots()) <= {'10.0.0.1', '10.0.0.2', '10.0.0.3'}
