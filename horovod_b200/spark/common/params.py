@@ -13,15 +13,19 @@ import copy
 
 class P:
     """One parameter: `P('batch_size', 32, check=positive_int, doc='...')`."""
-    __slots__ = ('name', 'default', 'check', 'doc')
+    __slots__ = ('name', 'default', 'check', 'doc', 'camels')
 
-    def __init__(self, name, default=None, check=None, doc=''):
+    def __init__(self, name, default=None, check=None, doc='', camel=()):
+        """`camel`: accessor stems other than the mechanical CamelCase of `name` (the reference's `setInMemoryCacheAll`
+        for `inmemory_cache_all`); every stem gets a set/get pair."""
         self.name, self.default, self.check, self.doc = name, default, check, doc
+        head, *rest = name.split('_')
+        own = ''.join([head.capitalize()] + [r.capitalize() for r in rest])
+        self.camels = (own,) + tuple(c for c in ((camel,) if isinstance(camel, str) else camel) if c != own)
 
     @property
     def camel(self):
-        head, *rest = self.name.split('_')
-        return ''.join([head.capitalize()] + [r.capitalize() for r in rest])
+        return self.camels[0]
 
 
 def _positive_int(name, v):
@@ -48,6 +52,16 @@ def _validation(name, v):
         raise ValueError('%s must be a column name or a fraction in [0, 1), got %r' % (name, v))
 
 
+def _reader_pool(name, v):
+    if v not in (None, 'thread', 'process', 'dummy'):
+        raise ValueError("%s must be 'thread', 'process' or 'dummy', got %r" % (name, v))
+
+
+def _mp_start(name, v):
+    if v not in (None, 'spawn', 'fork', 'forkserver'):
+        raise ValueError("%s must be 'spawn', 'fork' or 'forkserver', got %r" % (name, v))
+
+
 def _callable_or_none(name, v):
     if v is not None and not callable(v):
         raise ValueError('%s must be callable, got %r' % (name, v))
@@ -66,10 +80,11 @@ class ParamsBase:
                 table[p.name] = p
         cls._table = table
         for p in table.values():
-            if 'set' + p.camel not in cls.__dict__:
-                setattr(cls, 'set' + p.camel, _make_setter(p))
-            if 'get' + p.camel not in cls.__dict__:
-                setattr(cls, 'get' + p.camel, _make_getter(p))
+            for camel in p.camels:
+                if 'set' + camel not in cls.__dict__:
+                    setattr(cls, 'set' + camel, _make_setter(p, camel))
+                if 'get' + camel not in cls.__dict__:
+                    setattr(cls, 'get' + camel, _make_getter(p, camel))
 
     def __init__(self, **kwargs):
         self._values = {name: copy.copy(p.default) for name, p in self._table.items()}
@@ -114,19 +129,19 @@ class ParamsBase:
         raise AttributeError(name)
 
 
-def _make_setter(p):
+def _make_setter(p, camel=None):
     def setter(self, value):
         self._set(p.name, value)
         return self
-    setter.__name__ = 'set' + p.camel
+    setter.__name__ = 'set' + (camel or p.camel)
     setter.__doc__ = p.doc
     return setter
 
 
-def _make_getter(p):
+def _make_getter(p, camel=None):
     def getter(self):
         return self._get(p.name)
-    getter.__name__ = 'get' + p.camel
+    getter.__name__ = 'get' + (camel or p.camel)
     getter.__doc__ = p.doc
     return getter
 
@@ -152,7 +167,8 @@ class EstimatorParams(ParamsBase):
         P('verbose', 1, _non_negative_int, 'verbosity'),
         P('random_seed', 0, None, 'seed for the split and for shuffling'),
         P('shuffle', True, None, 'shuffle the training rows of a rank every epoch'),
-        P('shuffle_buffer_size', None, _non_negative_int, 'accepted for compatibility: shards are shuffled in memory'),
+        P('shuffle_buffer_size', None, _non_negative_int, 'accepted for compatibility: shards are shuffled in memory',
+          camel='ShufflingBufferSize'),
         P('partitions_per_process', 1, _positive_int, 'Parquet files written per training process'),
         P('run_id', None, None, 'name of the run directory in the store; an existing checkpoint there is resumed'),
         P('train_steps_per_epoch', None, _positive_int, 'steps per epoch (default: rows of the smallest shard // batch_size)'),
@@ -160,11 +176,22 @@ class EstimatorParams(ParamsBase):
         P('transformation_fn', None, _callable_or_none, 'fn(dict of column -> tensor/array) -> dict applied to every batch'),
         P('input_shapes', None, None, 'one shape per feature column ([-1, ...]); rows are reshaped before the model sees them'),
         P('label_shapes', None, None, 'one shape per label column'),
-        P('inmemory_cache_all', False, None, 'keep the decoded shard in memory across epochs'),
+        P('inmemory_cache_all', False, None, 'keep the decoded shard in memory across epochs', camel='InMemoryCacheAll'),
         P('use_gpu', True, None, 'train on cuda:<local_rank> when a GPU is visible'),
         P('gradient_compression', None, None, 'hvd.Compression.* for the gradient allreduce'),
         P('backward_passes_per_step', 1, _positive_int, 'local gradient accumulation steps'),
         P('compress_sparse_cols', False, None, 'accepted for compatibility'),
+        P('categorical_cols', None, _str_list, 'categorical feature columns, handed to the data module (tabular readers)'),
+        P('continuous_cols', None, _str_list, 'continuous feature columns, handed to the data module (tabular readers)'),
+        P('data_module', None, None, 'DataModule class that feeds the training loop (default: the framework\'s Parquet module)'),
+        P('train_reader_num_workers', None, _non_negative_int,
+          'reader threads for training data: >= 1 decodes batches on a background thread (async loader)', camel='TrainReaderNumWorker'),
+        P('val_reader_num_workers', None, _non_negative_int, 'same for validation data', camel='ValReaderNumWorker'),
+        P('reader_pool_type', 'thread', _reader_pool, "'thread' (the async loaders' pool), 'process' and 'dummy' are accepted; readers here are threads"),
+        P('mp_start_method', None, _mp_start, "accepted for compatibility: training processes are fresh interpreters started by the launcher ('spawn' semantics) whatever is set"),
+        P('tensorflow_dataset_prefetch_buffer_size', None, _non_negative_int, 'accepted for compatibility (tf.data prefetch depth of the reference\'s Keras reader)'),
+        P('transformation_edit_fields', None, None, 'fields transformation_fn adds or retypes: [(name, numpy dtype, shape, nullable)]'),
+        P('transformation_removed_fields', None, _str_list, 'columns transformation_fn drops; they are removed from every batch after it ran'),
     )
 
 
@@ -173,7 +200,7 @@ class ModelParams(ParamsBase):
         P('model', None, None, 'the trained model'),
         P('history', None, None, 'per-epoch metrics of the run that produced the model'),
         P('feature_columns', None, _str_list, 'feature column names'),
-        P('label_columns', None, _str_list, 'label column names'),
+        P('label_columns', None, _str_list, 'label column names', camel='LabelColoumns'),
         P('output_cols', None, _str_list, 'names of the prediction columns appended by transform()'),
         P('run_id', None, None, 'run that produced the model'),
         P('metadata', None, None, 'column metadata of the training data'),

@@ -7,8 +7,26 @@ filesystem).  Layout under `prefix_path`:
     runs/<run_id>/checkpoint.pt      rank-0 checkpoints
     runs/<run_id>/logs/
 """
+import contextlib
 import os
 import shutil
+import tempfile
+
+
+def split_protocol(path):
+    """'s3://bucket/x' -> ('s3', 'bucket/x'); 'C:/x' and '/x' -> (None, path) (reference store.py `split_protocol`)."""
+    if '://' in path:
+        scheme, rest = path.split('://', 1)
+        if len(scheme) > 1:
+            return scheme, rest
+    return None, path
+
+
+class _RemoteStore:
+    """Plain, picklable snapshot of the paths and helpers a training process needs (what `Store.to_remote` returns)."""
+
+    def __init__(self, attrs):
+        self.__dict__.update(attrs)
 
 
 class Store:
@@ -43,6 +61,56 @@ class Store:
 
     def write_text(self, path, text):
         self.write(path, text.encode('utf-8'))
+
+    def is_parquet_dataset(self, path):
+        raise NotImplementedError
+
+    def get_parquet_dataset(self, path):
+        raise NotImplementedError
+
+    def saving_runs(self):
+        raise NotImplementedError
+
+    def get_runs_path(self):
+        raise NotImplementedError
+
+    def get_checkpoints(self, run_id, suffix='.ckpt'):
+        raise NotImplementedError
+
+    def get_checkpoint_filename(self):
+        raise NotImplementedError
+
+    def get_logs_subdir(self):
+        raise NotImplementedError
+
+    def get_local_output_dir_fn(self, run_id):
+        raise NotImplementedError
+
+    def sync_fn(self, run_id):
+        """fn(local_run_path): uploads what a training process wrote locally into the run's directory of the store."""
+        raise NotImplementedError
+
+    def to_remote(self, run_id, dataset_idx):
+        """Snapshot for the training processes: attributes instead of methods, nothing that needs Spark or a live
+        filesystem handle to unpickle (reference store.py:130-156)."""
+        return _RemoteStore(self._remote_attrs(run_id, dataset_idx))
+
+    def _remote_attrs(self, run_id, dataset_idx):
+        saving = self.saving_runs()
+        return {
+            'train_data_path': self.get_train_data_path(dataset_idx),
+            'val_data_path': self.get_val_data_path(dataset_idx),
+            'test_data_path': self.get_test_data_path(dataset_idx),
+            'saving_runs': saving,
+            'runs_path': self.get_runs_path(),
+            'run_path': self.get_run_path(run_id),
+            'checkpoint_path': self.get_checkpoint_path(run_id),
+            'logs_path': self.get_logs_path(run_id),
+            'checkpoint_filename': self.get_checkpoint_filename(),
+            'logs_subdir': self.get_logs_subdir(),
+            'get_local_output_dir': self.get_local_output_dir_fn(run_id),
+            'sync': self.sync_fn(run_id),
+        }
 
     @staticmethod
     def create(prefix_path, *args, **kwargs):
@@ -132,6 +200,84 @@ class FilesystemStore(Store):
         info = self.fs.get_file_info(pafs.FileSelector(self._local(path), allow_not_found=True))
         return any(i.path.endswith('.parquet') for i in info)
 
+    def get_parquet_dataset(self, path):
+        import pyarrow.parquet as pq
+        return pq.ParquetDataset(self._local(path), filesystem=self.fs)
+
+    def get_data_metadata_path(self, path):
+        """Where the estimator keeps the row count / schema summary of a materialised DataFrame."""
+        return self.get_localized_path(path).rstrip('/') + '/_metadata.json'
+
+    def get_checkpoints(self, run_id, suffix='.ckpt'):
+        """Files below the run directory that end in `suffix` (what the Lightning-style trainers write per epoch)."""
+        import pyarrow.fs as pafs
+        root = self._local(self.get_run_path(run_id))
+        info = self.fs.get_file_info(pafs.FileSelector(root, recursive=True, allow_not_found=True))
+        return sorted(i.path for i in info if i.type == pafs.FileType.File and i.path.endswith(suffix))
+
+    def get_localized_path(self, path):
+        """`path` as this store's filesystem object addresses it (scheme and authority removed)."""
+        return self._local(path)
+
+    def get_full_path(self, path):
+        """`path` as a URI another process can open without this object."""
+        if split_protocol(path)[0] is not None:
+            return path
+        scheme = split_protocol(self.prefix_path)[0]
+        return path if scheme is None else f'{scheme}://{path.lstrip("/") if scheme not in ("file", "hdfs", "viewfs") else path}'
+
+    def get_full_path_fn(self):
+        prefix = split_protocol(self.prefix_path)[0]
+
+        def full(path):
+            return path if prefix is None or '://' in path else f'{prefix}://{path}'
+        return full
+
+    def get_filesystem(self):
+        return self.fs
+
+    @classmethod
+    def matches(cls, path):
+        """Any URI with a scheme (the most general store; `Store.create` tries the specific ones first)."""
+        return split_protocol(path)[0] is not None
+
+    def get_local_output_dir_fn(self, run_id):
+        """Training processes write checkpoints / logs into a scratch directory first; `sync_fn` uploads it."""
+        @contextlib.contextmanager
+        def local_run_path():
+            d = tempfile.mkdtemp(prefix='hvd_run_')
+            try:
+                yield d
+            finally:
+                shutil.rmtree(d, ignore_errors=True)
+        return local_run_path
+
+    def copy(self, lpath, rpath, recursive=False):
+        """Local file or directory -> this store."""
+        import pyarrow.fs as pafs
+        dst = self._local(rpath)
+        if os.path.isdir(lpath):
+            if not recursive:
+                raise IsADirectoryError(lpath)
+            pafs.copy_files(lpath, dst, source_filesystem=pafs.LocalFileSystem(), destination_filesystem=self.fs)
+        else:
+            self.fs.create_dir(os.path.dirname(dst), recursive=True)
+            with open(lpath, 'rb') as f, self.fs.open_output_stream(dst) as out:
+                shutil.copyfileobj(f, out)
+
+    def sync_fn(self, run_id):
+        run_path, copy = self.get_run_path(run_id), self.copy
+
+        def fn(local_run_path):
+            copy(local_run_path, run_path, recursive=True)
+        return fn
+
+    def read_serialized_keras_model(self, ckpt_path, model, custom_objects):
+        """The checkpoint written by the Keras estimator, re-encoded the way `KerasModel` keeps models (bytes of an
+        in-memory h5 / weights blob).  `model` supplies the architecture when the checkpoint holds weights only."""
+        from horovod_b200.spark.keras import util as kutil
+        return kutil.checkpoint_to_serialized_model(self.read(ckpt_path), model, custom_objects)
+
     def delete(self, path):
         if self.exists(path):
             self.fs.delete_dir(self._local(path))
@@ -154,6 +300,16 @@ class LocalStore(FilesystemStore):
 
     def delete(self, path):
         shutil.rmtree(path, ignore_errors=True)
+
+    @classmethod
+    def matches(cls, path):
+        return split_protocol(path)[0] in (None, 'file')
+
+    def get_full_path(self, path):
+        return path if '://' in path else 'file://' + os.path.abspath(path)
+
+    def get_full_path_fn(self):
+        return lambda path: path if '://' in path else 'file://' + os.path.abspath(path)
 
 
 class HDFSStore(FilesystemStore):
@@ -187,6 +343,21 @@ class HDFSStore(FilesystemStore):
     def _local(self, path):
         return self.parse_url(path)[2] if '://' in path else path
 
+    @classmethod
+    def matches(cls, path):
+        return split_protocol(path)[0] in ('hdfs', 'viewfs')
+
+    def get_full_path(self, path):
+        if '://' in path:
+            return path
+        scheme, rest = split_protocol(self.prefix_path)
+        return f'{scheme}://{rest.partition("/")[0]}{path}'
+
+    def get_full_path_fn(self):
+        scheme, rest = split_protocol(self.prefix_path)
+        authority = rest.partition('/')[0]
+        return lambda path: path if '://' in path else f'{scheme}://{authority}{path}'
+
 
 def is_databricks():
     return 'DATABRICKS_RUNTIME_VERSION' in os.environ
@@ -202,6 +373,14 @@ class DBFSLocalStore(LocalStore):
     @staticmethod
     def matches(path):
         return path.startswith('dbfs:/') or path == '/dbfs' or path.startswith('/dbfs/')
+
+    matches_dbfs = matches
+
+    def get_localized_path(self, path):
+        return self.normalize_path(path)
+
+    def get_full_path(self, path):
+        return 'file://' + self.normalize_path(path)
 
     @staticmethod
     def normalize_path(path):

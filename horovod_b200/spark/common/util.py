@@ -167,59 +167,7 @@ class PreparedDataset:
         return 'PreparedDataset(idx=%s, train_rows=%d, val_rows=%d)' % (self.idx, self.train_rows, self.val_rows)
 
 
-class _DatasetCache:
-    """Remembers which DataFrame objects are already materialised in which store so that fitting several models (a
-    hyper-parameter search) on the same DataFrame writes the Parquet once.  Entries die with their DataFrame."""
-
-    def __init__(self):
-        self._lock = threading.Lock()
-        self._entries = {}       # key -> (weakref to df or None, PreparedDataset, users)
-
-    @staticmethod
-    def _key(df, store, validation, columns, num_files):
-        return (id(df), getattr(store, 'prefix_path', id(store)), repr(validation), tuple(columns), num_files)
-
-    def lookup(self, df, store, validation, columns, num_files):
-        key = self._key(df, store, validation, columns, num_files)
-        with self._lock:
-            hit = self._entries.get(key)
-            if hit is None:
-                return key, None
-            ref, dataset, users = hit
-            if ref is not None and ref() is not df:          # the id was recycled by another object
-                del self._entries[key]
-                return key, None
-            if not store.exists(dataset.train_path):
-                del self._entries[key]
-                return key, None
-            self._entries[key] = (ref, dataset, users + 1)
-            return key, dataset
-
-    def insert(self, key, df, dataset):
-        try:
-            ref = weakref.ref(df)
-        except TypeError:
-            ref = None
-        with self._lock:
-            self._entries[key] = (ref, dataset, 1)
-
-    def release(self, key):
-        with self._lock:
-            hit = self._entries.get(key)
-            if hit:
-                self._entries[key] = (hit[0], hit[1], max(0, hit[2] - 1))
-
-    def clear(self, store=None):
-        """Forgets (and deletes from `store`) every materialised dataset nobody is training on."""
-        with self._lock:
-            for key, (ref, dataset, users) in list(self._entries.items()):
-                if users == 0:
-                    if store is not None:
-                        store.delete(dataset.train_path)
-                        if dataset.val_path:
-                            store.delete(dataset.val_path)
-                    del self._entries[key]
-
+from horovod_b200.spark.common.cache import TrainingDataCache as _DatasetCache  # noqa: E402
 
 _dataset_cache = _DatasetCache()
 
@@ -270,6 +218,19 @@ def prepare_data(num_processes, store, df, label_columns, feature_columns, valid
             store.delete(dataset.train_path)
             if dataset.val_path:
                 store.delete(dataset.val_path)
+
+
+def make_transform(transformation_fn, removed_fields=None):
+    """The per-batch transform of an estimator: `transformation_fn` (if any), then the columns listed in
+    `transformation_removed_fields` are dropped from the batch."""
+    removed = set(removed_fields or ())
+    if not removed:
+        return transformation_fn
+
+    def transform(batch):
+        out = transformation_fn(batch) if transformation_fn else batch
+        return {k: v for k, v in out.items() if k not in removed}
+    return transform
 
 
 def existing_dataset(store, dataset_idx=None):

@@ -54,6 +54,17 @@ def deserialize_model(data, custom_objects=None):
         return keras.models.load_model(path, custom_objects=custom_objects, compile=False)
 
 
+def checkpoint_to_serialized_model(ckpt_bytes, model, custom_objects=None):
+    """Bytes of a run's checkpoint (what `_StoreCheckpoint` writes: weights + epoch) -> bytes in `serialize_model` format,
+    with `model` supplying the architecture.  A checkpoint that already is a serialized model passes through."""
+    import cloudpickle
+    rec = cloudpickle.loads(ckpt_bytes)
+    if isinstance(rec, dict) and 'format' in rec:
+        return ckpt_bytes
+    model.set_weights(weights_from_bytes(rec['weights']))
+    return serialize_model(model)
+
+
 def serialize_optimizer(optimizer):
     import cloudpickle
     return cloudpickle.dumps((type(optimizer), optimizer.get_config()))

@@ -12,8 +12,6 @@ intermediate format is the same (Parquet in the Store) but the reader is pyarrow
 DataFrame (written by Spark itself) or a pandas DataFrame (written by pyarrow) — so the estimator also works on a single
 multi-GPU box without Spark (`LocalBackend`).
 """
-import io
-
 import numpy as np
 import torch
 
@@ -21,154 +19,8 @@ from horovod_b200.spark.common.estimator import HorovodEstimator, HorovodModel
 from horovod_b200.spark.common.params import P
 
 
-def _serialize(obj):
-    """torch.save through cloudpickle: a model class defined in a script / notebook / test module that the workers cannot
-    import travels by value."""
-    import cloudpickle
-    if isinstance(obj, torch.nn.Module) and getattr(__import__('sys').modules.get(type(obj).__module__), '__file__', None):
-        from horovod_b200.runner import _pickle_by_value_if_not_importable
-        _pickle_by_value_if_not_importable(type(obj))
-    buf = io.BytesIO()
-    torch.save(obj, buf, pickle_module=cloudpickle)
-    return buf.getvalue()
-
-
-def _deserialize(data):
-    return torch.load(io.BytesIO(data), weights_only=False)
-
-
-def _as_list(x, n):
-    if x is None:
-        return [None] * n
-    if isinstance(x, (list, tuple)):
-        if len(x) != n:
-            raise ValueError('expected %d entries, got %d' % (n, len(x)))
-        return list(x)
-    return [x] * n
-
-
-class _BatchLoss:
-    """sum_i weight_i * loss_i(output_i, label_i), with optional per-row sample weights; also evaluates the metrics."""
-
-    def __init__(self, model, loss, loss_weights, metrics, feature_cols, label_cols, sample_weight_col):
-        n = len(label_cols)
-        self.model, self.feature_cols, self.label_cols, self.sample_weight_col = model, feature_cols, label_cols, sample_weight_col
-        self.losses = _as_list(loss, n)
-        self.weights = [1.0 if w is None else float(w) for w in _as_list(loss_weights, n)]
-        self.metrics = list(metrics or [])
-
-    def _pairs(self, batch):
-        out = self.model(*[batch[c].float() if batch[c].dtype.is_floating_point else batch[c] for c in self.feature_cols])
-        outs = list(out) if isinstance(out, (tuple, list)) else [out]
-        for o, col in zip(outs, self.label_cols):
-            y = batch[col]
-            if o.dtype.is_floating_point and y.dtype.is_floating_point:
-                y = y.to(o.dtype)
-            if o.dim() == y.dim() + 1 and o.shape[-1] == 1:
-                o = o.squeeze(-1)
-            yield o, y
-
-    def __call__(self, batch, with_metrics=False):
-        total, extra = 0.0, {}
-        for i, (o, y) in enumerate(self._pairs(batch)):
-            l = self.losses[i](o, y)
-            if l.dim() > 0:
-                if self.sample_weight_col:
-                    w = batch[self.sample_weight_col].to(l.dtype)
-                    l = l * w.reshape([-1] + [1] * (l.dim() - 1))
-                l = l.mean()
-            total = total + self.weights[i] * l
-            if with_metrics:
-                for m in self.metrics:
-                    name = getattr(m, '__name__', type(m).__name__) + ('' if len(self.label_cols) == 1 else '_%d' % i)
-                    extra[name] = torch.as_tensor(m(o.detach(), y), dtype=torch.float32, device=o.device).mean()
-        return (total, extra) if with_metrics else total
-
-
-def _train_fn(spec):
-    """Runs on every rank; `spec` is the plain dict built by TorchEstimator._fit_on_prepared_data."""
-    import horovod_b200.torch as hvd
-    from horovod_b200.data import DevicePrefetcher
-    from horovod_b200.spark.data_loaders import ParquetShard, PytorchDataLoader, PytorchInmemDataLoader
-    hvd.init()
-    dev = torch.device('cuda', hvd.local_rank()) if spec['use_gpu'] and torch.cuda.is_available() else torch.device('cpu')
-    if dev.type == 'cuda':
-        torch.cuda.set_device(dev)
-    store = spec['store']
-    model = _deserialize(spec['model']).to(dev)
-    opt = spec['optimizer_cls'](model.parameters(), **spec['optimizer_defaults'])
-    first_epoch = 0
-    resume = spec['resume']
-    if resume is not None and hvd.rank() == 0:            # rank 0 loads, everybody receives by broadcast
-        ck = _deserialize(resume)
-        model.load_state_dict(ck['model'])
-        opt.load_state_dict(ck['optimizer'])
-        first_epoch = ck['epoch'] + 1
-    first_epoch = hvd.broadcast_object(first_epoch, root_rank=0, name='est.first_epoch')
-    opt = hvd.DistributedOptimizer(opt, named_parameters=model.named_parameters(),
-                                   compression=spec['compression'] or hvd.Compression.none,
-                                   backward_passes_per_step=spec['backward_passes_per_step'])
-    hvd.broadcast_parameters(model.state_dict(), root_rank=0)
-    hvd.broadcast_optimizer_state(opt, root_rank=0)
-
-    cols = list(spec['feature_cols']) + list(spec['label_cols']) + ([spec['sample_weight_col']] if spec['sample_weight_col'] else [])
-    loader_cls = PytorchInmemDataLoader if spec['inmemory_cache_all'] else PytorchDataLoader
-
-    def loader(path, batch_size, shuffle, steps):
-        shard = ParquetShard(store, path, cols, hvd.rank(), hvd.size(), spec['row_shapes'])
-        return loader_cls(shard, batch_size=batch_size, shuffle=shuffle, seed=spec['seed'], steps=steps,
-                          transformation_fn=spec['transformation_fn'], pin_memory=dev.type == 'cuda')
-    train = loader(spec['train_path'], spec['batch_size'], spec['shuffle'], spec['train_steps'])
-    val = loader(spec['val_path'], spec['val_batch_size'], False, spec['val_steps']) if spec['val_path'] else None
-    batch_loss = _BatchLoss(model, spec['loss'], spec['loss_weights'], spec['metrics'], spec['feature_cols'], spec['label_cols'],
-                            spec['sample_weight_col'])
-    accumulate = spec['backward_passes_per_step']
-
-    def averaged(sums, count, prefix):
-        names = sorted(sums)
-        if not names:
-            return {}
-        vec = torch.stack([sums[n] for n in names]) / max(count, 1)
-        vec = hvd.allreduce(vec, name='est.%smetrics' % prefix)
-        return {prefix + n: v for n, v in zip(names, vec.tolist())}
-
-    history = []
-    for epoch in range(first_epoch, spec['epochs']):
-        model.train()
-        sums, count = {'loss': torch.zeros((), device=dev)}, 0
-        opt.zero_grad()
-        for step, batch in enumerate(DevicePrefetcher(train, device=dev)):
-            loss = batch_loss(batch)
-            (loss / accumulate).backward()
-            if (step + 1) % accumulate == 0:
-                opt.step()
-                opt.zero_grad()
-            sums['loss'] += loss.detach()
-            count += 1
-        record = {'epoch': epoch}
-        record.update(averaged(sums, count, ''))
-        if val is not None:
-            model.eval()
-            vsums, vcount = {'loss': torch.zeros((), device=dev)}, 0
-            with torch.no_grad():
-                for batch in DevicePrefetcher(val, device=dev):
-                    loss, extra = batch_loss(batch, with_metrics=True)
-                    vsums['loss'] += loss
-                    for k, v in extra.items():
-                        vsums[k] = vsums.get(k, torch.zeros((), device=dev)) + v
-                    vcount += 1
-            record.update(averaged(vsums, vcount, 'val_'))
-        history.append(record)
-        for cb in spec['callbacks']:
-            cb(epoch, record) if callable(cb) else cb.on_epoch_end(epoch, record)
-        if spec['verbose'] and hvd.rank() == 0:
-            print('epoch %d: %s' % (epoch, record), flush=True)
-        if spec['ckpt_path'] and hvd.rank() == 0:
-            store.write(spec['ckpt_path'], _serialize({'model': model.state_dict(), 'optimizer': opt.state_dict(), 'epoch': epoch}))
-    state = {k: v.cpu() for k, v in model.state_dict().items()} if hvd.rank() == 0 else None
-    hvd.barrier()  # shutdown is job-wide: nobody leaves while a peer still talks to the runtime
-    hvd.shutdown()
-    return {'history': history, 'state_dict': state}
+from horovod_b200.spark.torch.remote import RemoteTrainer, _BatchLoss, _as_list, _train_fn  # noqa: F401
+from horovod_b200.spark.torch.util import _deserialize, _serialize  # noqa: F401
 
 
 class TorchEstimator(HorovodEstimator):
@@ -179,9 +31,10 @@ class TorchEstimator(HorovodEstimator):
     plus every knob of `EstimatorParams` (also reachable as setX/getX and through `fit(df, params={...})`).
     """
     PARAMS = (
-        P('train_minibatch_fn', None, None, 'accepted for compatibility; the loop lives in spark/torch/estimator.py:_train_fn'),
+        P('train_minibatch_fn', None, None, 'accepted for compatibility; the loop lives in spark/torch/remote.py:_train_fn'),
+        P('loss_constructors', None, None, 'callables that build the loss function(s) on the training processes (instead of `loss`)'),
     )
-    REQUIRED = ('model', 'optimizer', 'loss', 'feature_cols', 'label_cols', 'store')
+    REQUIRED = ('model', 'optimizer', 'feature_cols', 'label_cols', 'store')
 
     def __init__(self, **kwargs):
         super().__init__(**kwargs)
@@ -191,6 +44,11 @@ class TorchEstimator(HorovodEstimator):
         if not isinstance(self._get('optimizer'), torch.optim.Optimizer):
             raise ValueError('optimizer must be a torch.optim.Optimizer instance')
         n = len(self._get('label_cols'))
+        if not self._get('loss') and not self._get('loss_constructors'):
+            raise ValueError('TorchEstimator: required parameter(s) missing: loss (or loss_constructors)')
+        if self._get('loss_constructors'):
+            if not all(callable(c) for c in _as_list(self._get('loss_constructors'), n)):
+                raise ValueError('loss_constructors must be callables that return a loss function')
         _as_list(self._get('loss'), n)
         _as_list(self._get('loss_weights'), n)
 
@@ -210,19 +68,26 @@ class TorchEstimator(HorovodEstimator):
             train_steps=g('train_steps_per_epoch'), val_steps=g('validation_steps_per_epoch'), use_gpu=g('use_gpu'),
             verbose=g('verbose'), transformation_fn=g('transformation_fn'), row_shapes=self._row_shapes(),
             inmemory_cache_all=g('inmemory_cache_all'), compression=g('gradient_compression'),
-            backward_passes_per_step=g('backward_passes_per_step'))
+            backward_passes_per_step=g('backward_passes_per_step'), data_module=g('data_module'),
+            loss_constructors=g('loss_constructors'), train_reader_num_workers=g('train_reader_num_workers'),
+            val_reader_num_workers=g('val_reader_num_workers'), transformation_removed_fields=g('transformation_removed_fields'),
+            categorical_cols=g('categorical_cols'), continuous_cols=g('continuous_cols'))
         results = backend.run(_train_fn, args=(spec,))
         rank0 = results[0]
         model = g('model')
         model.load_state_dict(rank0['state_dict'])
         return TorchModel(model=model, feature_columns=spec['feature_cols'], label_columns=spec['label_cols'], history=rank0['history'],
-                          run_id=run_id, metadata=dataset.metadata, input_shapes=g('input_shapes'))
+                          run_id=run_id, metadata=dataset.metadata, input_shapes=g('input_shapes'), optimizer=optimizer,
+                          loss=g('loss'), loss_constructors=g('loss_constructors'))
 
 
 class TorchModel(HorovodModel):
     """Transformer returned by fit(): appends `<label>__output` prediction columns."""
     PARAMS = (
         P('input_shapes', None, None, 'one shape per feature column'),
+        P('optimizer', None, None, 'the optimizer the model was trained with'),
+        P('loss', None, None, 'the loss function(s) the model was trained with'),
+        P('loss_constructors', None, None, 'callables that build the loss function(s)'),
     )
 
     def __init__(self, model=None, feature_cols=None, label_cols=None, **kwargs):
