@@ -13,73 +13,8 @@ import numpy as np
 from horovod_b200.spark.common.estimator import HorovodEstimator, HorovodModel
 from horovod_b200.spark.common.params import P
 from horovod_b200.spark.keras import util as kutil
-
-
-class _NumpyShardBatches:
-    """One pass = `steps` dict-of-numpy batches from this rank's shard."""
-
-    def __init__(self, shard, batch_size, shuffle, seed, steps, transformation_fn):
-        self.shard, self.batch_size, self.shuffle, self.seed = shard, batch_size, shuffle, seed
-        self.steps = steps or shard.steps(batch_size)
-        self.transformation_fn = transformation_fn
-        self.passes = 0
-
-    def __call__(self):
-        data, n = self.shard.load(), self.shard.rows
-        rng = np.random.RandomState((self.seed * 1000003 + self.passes) % (2 ** 31))
-        order = rng.permutation(n) if self.shuffle else np.arange(n)
-        self.passes += 1
-        for s in range(self.steps):
-            idx = order[(np.arange(self.batch_size) + s * self.batch_size) % n]
-            batch = {c: v[idx] for c, v in data.items()}
-            yield self.transformation_fn(batch) if self.transformation_fn else batch
-
-
-def _train_fn(spec):
-    import horovod_b200.tensorflow.keras as hvd
-    from horovod_b200.spark.data_loaders import ParquetShard
-    hvd.init()
-    keras = kutil.keras_module()
-    store = spec['store']
-    model = kutil.deserialize_model(spec['model'], spec['custom_objects'])
-    first_epoch = 0
-    if spec['resume'] is not None:
-        ck = __import__('cloudpickle').loads(spec['resume'])
-        model.set_weights(kutil.weights_from_bytes(ck['weights']))
-        first_epoch = ck['epoch'] + 1
-    optimizer = hvd.DistributedOptimizer(kutil.deserialize_optimizer(spec['optimizer']),
-                                         compression=spec['compression'] or hvd.Compression.none,
-                                         backward_passes_per_step=spec['backward_passes_per_step'])
-    model.compile(optimizer=optimizer, loss=spec['loss'], loss_weights=spec['loss_weights'], metrics=spec['metrics'])
-
-    cols = spec['columns']
-
-    def batches(path, batch_size, shuffle, steps):
-        shard = ParquetShard(store, path, cols, hvd.rank(), hvd.size(), spec['row_shapes'])
-        return _NumpyShardBatches(shard, batch_size, shuffle, spec['seed'], steps, spec['transformation_fn'])
-    train = batches(spec['train_path'], spec['batch_size'], spec['shuffle'], spec['train_steps'])
-    val = batches(spec['val_path'], spec['val_batch_size'], False, spec['val_steps']) if spec['val_path'] else None
-
-    class _StoreCheckpoint(keras.callbacks.Callback):
-        def on_epoch_end(self, epoch, logs=None):
-            import cloudpickle
-            store.write(spec['ckpt_path'], cloudpickle.dumps({'weights': kutil.weights_to_bytes(self.model.get_weights()), 'epoch': epoch}))
-
-    callbacks = [hvd.callbacks.BroadcastGlobalVariablesCallback(0), hvd.callbacks.MetricAverageCallback()]
-    callbacks += list(spec['callbacks'])
-    if hvd.rank() == 0 and spec['ckpt_path']:
-        callbacks.append(_StoreCheckpoint())
-    fit_kwargs = dict(steps_per_epoch=train.steps, epochs=spec['epochs'], initial_epoch=first_epoch, callbacks=callbacks,
-                      verbose=spec['verbose'] if hvd.rank() == 0 else 0)
-    if val is not None:
-        fit_kwargs.update(validation_data=kutil.batch_generator(val, spec['feature_cols'], spec['label_cols'], spec['sample_weight_col']),
-                          validation_steps=val.steps)
-    history = model.fit(kutil.batch_generator(train, spec['feature_cols'], spec['label_cols'], spec['sample_weight_col']), **fit_kwargs)
-    hist = {k: [float(x) for x in v] for k, v in getattr(history, 'history', {}).items()}
-    weights = kutil.weights_to_bytes(model.get_weights()) if hvd.rank() == 0 else None
-    hvd.barrier()
-    hvd.shutdown()
-    return {'history': hist, 'weights': weights}
+from horovod_b200.spark.keras.datamodule import _NumpyShardBatches  # noqa: F401
+from horovod_b200.spark.keras.remote import RemoteTrainer, _train_fn  # noqa: F401
 
 
 class KerasEstimator(HorovodEstimator):
@@ -88,6 +23,7 @@ class KerasEstimator(HorovodEstimator):
     PARAMS = (
         P('custom_objects', None, None, 'custom layers / losses needed to rebuild the model on the workers'),
         P('checkpoint_callback', None, None, 'accepted for compatibility: rank 0 checkpoints into the store after every epoch'),
+        P('backend_env', None, None, 'environment variables set on every training process before Keras / TensorFlow initialise'),
     )
     REQUIRED = ('model', 'optimizer', 'loss', 'feature_cols', 'label_cols', 'store')
 
@@ -116,7 +52,8 @@ class KerasEstimator(HorovodEstimator):
                     epochs=g('epochs'), shuffle=g('shuffle'), seed=g('random_seed') or 0, train_steps=g('train_steps_per_epoch'),
                     val_steps=g('validation_steps_per_epoch'), verbose=g('verbose'), transformation_fn=g('transformation_fn'),
                     row_shapes=self._row_shapes(), compression=g('gradient_compression'),
-                    backward_passes_per_step=g('backward_passes_per_step'))
+                    backward_passes_per_step=g('backward_passes_per_step'), backend_env=g('backend_env'),
+                    data_module=g('data_module'), transformation_removed_fields=g('transformation_removed_fields'))
         rank0 = backend.run(_train_fn, args=(spec,))[0]
         model = g('model')
         model.set_weights(kutil.weights_from_bytes(rank0['weights']))

@@ -10,53 +10,12 @@ import torch
 
 from horovod_b200.spark.common.estimator import HorovodEstimator, HorovodModel
 from horovod_b200.spark.common.params import P
-from horovod_b200.spark.torch.estimator import _deserialize, _serialize
+from horovod_b200.spark.lightning.remote import RemoteTrainer, _train_fn, translate_trainer_args  # noqa: F401
+from horovod_b200.spark.lightning.util import _deserialize, _serialize  # noqa: F401
 
 
 def _is_protocol_module(m):
     return callable(getattr(m, 'training_step', None)) and callable(getattr(m, 'configure_optimizers', None))
-
-
-def _train_fn(spec):
-    import horovod_b200.torch as hvd
-    from horovod_b200.data import DevicePrefetcher
-    from horovod_b200.spark.data_loaders import ParquetShard, PytorchDataLoader, PytorchInmemDataLoader
-    from horovod_b200.spark.lightning.trainer import ModuleProtocolTrainer
-    hvd.init()
-    dev = torch.device('cuda', hvd.local_rank()) if spec['use_gpu'] and torch.cuda.is_available() else torch.device('cpu')
-    if dev.type == 'cuda':
-        torch.cuda.set_device(dev)
-    store = spec['store']
-    module = _deserialize(spec['module'])
-    first_epoch, opt_state = 0, None
-    if spec['resume'] is not None and hvd.rank() == 0:
-        ck = _deserialize(spec['resume'])
-        module.load_state_dict(ck['model'])
-        first_epoch, opt_state = ck['epoch'] + 1, ck['optimizer']
-    first_epoch = hvd.broadcast_object(first_epoch, root_rank=0, name='pl.first_epoch')
-    cols = spec['columns']
-    loader_cls = PytorchInmemDataLoader if spec['inmemory_cache_all'] else PytorchDataLoader
-
-    def loader(path, batch_size, shuffle, steps):
-        shard = ParquetShard(store, path, cols, hvd.rank(), hvd.size(), spec['row_shapes'])
-        return loader_cls(shard, batch_size=batch_size, shuffle=shuffle, seed=spec['seed'], steps=steps,
-                          transformation_fn=spec['transformation_fn'], pin_memory=dev.type == 'cuda')
-
-    def checkpoint(mod, opt, epoch):
-        if spec['ckpt_path']:
-            store.write(spec['ckpt_path'], _serialize({'model': mod.state_dict(), 'optimizer': opt.state_dict(), 'epoch': epoch}))
-    trainer = ModuleProtocolTrainer(hvd, dev, epochs=spec['epochs'], first_epoch=first_epoch, compression=spec['compression'],
-                                    backward_passes_per_step=spec['backward_passes_per_step'], gradient_clip_val=spec['gradient_clip_val'],
-                                    callbacks=spec['callbacks'], checkpoint=checkpoint, verbose=spec['verbose'],
-                                    prefetcher=lambda l: DevicePrefetcher(l, device=dev))
-    trainer.setup(module, optimizer_state=opt_state)
-    train = loader(spec['train_path'], spec['batch_size'], spec['shuffle'], spec['train_steps'])
-    val = loader(spec['val_path'], spec['val_batch_size'], False, spec['val_steps']) if spec['val_path'] else None
-    history = trainer.fit(module, train, val)
-    state = {k: v.cpu() for k, v in module.state_dict().items()} if hvd.rank() == 0 else None
-    hvd.barrier()
-    hvd.shutdown()
-    return {'history': history, 'state_dict': state}
 
 
 class LightningEstimator(HorovodEstimator):
@@ -64,14 +23,19 @@ class LightningEstimator(HorovodEstimator):
     column name -> tensor); or pass a plain nn.Module together with `optimizer` and `loss`."""
     PARAMS = (
         P('gradient_clip_val', None, None, 'clip the global gradient norm after the allreduce'),
-        P('num_gpus', None, None, 'accepted for compatibility: one GPU per process'),
+        P('num_gpus', None, None, 'accepted for compatibility: one GPU per process', camel='NumGPUs'),
         P('logger', None, None, 'accepted for compatibility: the history is returned with the model'),
         P('log_every_n_steps', 50, None, 'accepted for compatibility'),
-        P('data_module', None, None, 'accepted for compatibility: shards are read by horovod_b200.spark.data_loaders'),
         P('loader_num_epochs', None, None, 'accepted for compatibility'),
         P('terminate_on_nan', False, None, 'accepted for compatibility'),
         P('profiler', None, None, 'accepted for compatibility'),
         P('checkpoint_callback', None, None, 'accepted for compatibility: rank 0 checkpoints into the store after every epoch'),
+        P('trainer_args', None, None, 'pytorch_lightning.Trainer keyword arguments; max_epochs / gradient_clip_val / accumulate_grad_batches are honoured'),
+        P('loss_constructors', None, None, 'callables that build the loss function(s) for a plain nn.Module (instead of `loss`)'),
+        P('train_minibatch_fn', None, None, 'accepted for compatibility: the step is the module\'s training_step'),
+        P('train_async_data_loader_queue_size', 64, None, 'batches the training reader thread may run ahead (with train_reader_num_workers >= 1)'),
+        P('val_async_data_loader_queue_size', 64, None, 'same for the validation reader'),
+        P('debug_data_loader', False, None, 'print per-batch timing of the async readers'),
     )
 
     def __init__(self, **kwargs):
@@ -83,15 +47,16 @@ class LightningEstimator(HorovodEstimator):
         if not _is_protocol_module(model):
             if not isinstance(model, torch.nn.Module):
                 raise ValueError('model must follow the LightningModule protocol or be a torch.nn.Module')
-            if self._get('optimizer') is None or self._get('loss') is None:
+            if self._get('optimizer') is None or (self._get('loss') is None and not self._get('loss_constructors')):
                 raise ValueError('a plain torch.nn.Module needs `optimizer` and `loss` (or implement training_step / configure_optimizers)')
 
     def _module(self):
         model = self._get('model')
         if _is_protocol_module(model):
             return model
-        from horovod_b200.spark.lightning.trainer import to_lightning_module
-        return to_lightning_module(model, self._get('optimizer'), self._get('loss'), self._get('loss_weights'),
+        from horovod_b200.spark.lightning.legacy import to_lightning_module
+        loss = [make() for make in self._get('loss_constructors')] if self._get('loss_constructors') else self._get('loss')
+        return to_lightning_module(model, self._get('optimizer'), loss, self._get('loss_weights'),
                                    self._get('feature_cols'), self._get('label_cols'), self._get('sample_weight_col'))
 
     def _fit_on_prepared_data(self, backend, dataset):
@@ -106,16 +71,25 @@ class LightningEstimator(HorovodEstimator):
                     use_gpu=g('use_gpu'), verbose=g('verbose'), transformation_fn=g('transformation_fn'), row_shapes=self._row_shapes(),
                     inmemory_cache_all=g('inmemory_cache_all'), compression=g('gradient_compression'),
                     backward_passes_per_step=g('backward_passes_per_step'), gradient_clip_val=g('gradient_clip_val'),
-                    callbacks=list(g('callbacks') or []))
+                    callbacks=list(g('callbacks') or []), trainer_args=g('trainer_args'), data_module=g('data_module'),
+                    train_reader_num_workers=g('train_reader_num_workers'), val_reader_num_workers=g('val_reader_num_workers'),
+                    train_async_data_loader_queue_size=g('train_async_data_loader_queue_size'),
+                    val_async_data_loader_queue_size=g('val_async_data_loader_queue_size'), debug_data_loader=g('debug_data_loader'),
+                    transformation_removed_fields=g('transformation_removed_fields'))
+        translate_trainer_args(g('trainer_args'))          # fail on the driver, not inside the job
         rank0 = backend.run(_train_fn, args=(spec,))[0]
         module.load_state_dict(rank0['state_dict'])
         return LightningModel(model=module, feature_columns=list(g('feature_cols')), label_columns=list(g('label_cols')),
-                              history=rank0['history'], run_id=run_id, metadata=dataset.metadata, input_shapes=g('input_shapes'))
+                              history=rank0['history'], run_id=run_id, metadata=dataset.metadata, input_shapes=g('input_shapes'),
+                              optimizer=g('optimizer'), loss=g('loss'), loss_constructors=g('loss_constructors'))
 
 
 class LightningModel(HorovodModel):
     PARAMS = (
         P('input_shapes', None, None, 'one shape per feature column'),
+        P('optimizer', None, None, 'the optimizer the model was trained with'),
+        P('loss', None, None, 'the loss function(s) the model was trained with'),
+        P('loss_constructors', None, None, 'callables that build the loss function(s)'),
     )
 
     def _predict(self, columns):

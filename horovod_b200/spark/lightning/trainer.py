@@ -177,28 +177,4 @@ class ModuleProtocolTrainer:
         return history
 
 
-class LegacyModule(torch.nn.Module):
-    """A plain nn.Module + optimizer + loss(es) presented through the protocol (reference: spark/lightning/legacy.py:20-115)."""
-
-    def __init__(self, model, optimizer, loss_fns, loss_weights, feature_cols, label_cols, sample_weight_col=None):
-        super().__init__()
-        from horovod_b200.spark.torch.estimator import _BatchLoss
-        self.model = model
-        self._optimizer = optimizer
-        self._loss = _BatchLoss(model, loss_fns, loss_weights, None, list(feature_cols), list(label_cols), sample_weight_col)
-
-    def forward(self, *args, **kwargs):
-        return self.model(*args, **kwargs)
-
-    def configure_optimizers(self):
-        return self._optimizer
-
-    def training_step(self, batch, batch_idx):
-        return {'loss': self._loss(batch)}
-
-    def validation_step(self, batch, batch_idx):
-        return {'val_loss': self._loss(batch)}
-
-
-def to_lightning_module(model, optimizer, loss_fns, loss_weights, feature_cols, label_cols, sample_weight_col=None):
-    return LegacyModule(model, optimizer, loss_fns, loss_weights, feature_cols, label_cols, sample_weight_col)
+from horovod_b200.spark.lightning.legacy import LegacyModule, to_lightning_module  # noqa: E402,F401

@@ -52,6 +52,42 @@ np.testing.assert_allclose(np.array(out['label__output'].tolist()), df['label'].
 assert est.store.exists(est.store.get_checkpoint_path('k1'))
 more = est.fit(df, params={'epochs': 7})              # resumes after epoch 4
 assert len(more.getHistory()['loss']) == 2, more.getHistory()
+
+# the run's checkpoint -> a serialized model (Store.read_serialized_keras_model), optimizer transport, backend_env, data module
+blob = est.store.read_serialized_keras_model(est.store.get_checkpoint_path('k1'), LinearModel(3, 1), None)
+np.testing.assert_allclose(kutil.deserialize_model(blob).get_weights()[0].ravel(), w, atol=0.1)
+from horovod_b200.spark.keras import optimizer as kopt, datamodule as kdm, remote as kremote
+o3 = kopt.deserialize_tf_keras_optimizer(kopt.serialize_tf_keras_optimizer(SGD(0.5)), model=m)
+assert isinstance(o3, SGD) and abs(o3.get_config()['learning_rate'] - 0.5) < 1e-7 and kopt.is_string(kopt.serialize_bare_keras_optimizer(SGD()))
+assert kdm.PetastormDataModule is kdm.ParquetDataModule and callable(kremote.RemoteTrainer({}))
+import os
+marker = os.path.join(store, 'env_seen')
+
+
+class EnvCheck:                                    # a callback that records what the training process sees
+    def __init__(self, path):
+        self.path = path
+
+    def set_model(self, model):
+        pass
+
+    def on_epoch_end(self, epoch, logs=None):
+        import horovod_b200.tensorflow.keras as hvd
+        if hvd.rank() == 1:
+            open(self.path, 'w').write(os.environ.get('HVD_TEST_KERAS_BACKEND', 'missing'))
+
+    def __getattr__(self, name):
+        if name.startswith('on_'):
+            return lambda *a, **k: None
+        raise AttributeError(name)
+
+
+est2 = KerasEstimator(model=LinearModel(3, 1), optimizer=SGD(0.1), loss='mse', feature_cols=['features'], label_cols=['label'],
+                      batch_size=32, epochs=1, store=store, backend=LocalBackend(2, env=env), verbose=0,
+                      backend_env={'HVD_TEST_KERAS_BACKEND': 'numpy'}, callbacks=[EnvCheck(marker)], data_module=kdm.ParquetDataModule)
+assert est2.getBackendEnv() == {'HVD_TEST_KERAS_BACKEND': 'numpy'} and est2.getDataModule() is kdm.ParquetDataModule
+est2.fit(df)
+assert open(marker).read() == 'numpy'
 print('KERAS ESTIMATOR OK')
 '''
 

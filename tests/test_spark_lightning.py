@@ -139,3 +139,33 @@ def test_protocol_trainer_single_process_hooks(native_built):
         assert {'loss', 'val_loss', 'train_mae', 'epoch'} <= set(hist[0])
     finally:
         hvd.shutdown()
+
+
+def test_trainer_args_loss_constructors_async_readers_and_module_paths(native_built, tmp_path):
+    """The reference's Lightning-estimator knobs: trainer_args (translated for the protocol trainer), loss_constructors for a
+    plain nn.Module, async reader threads with their queue sizes; plus the reference's module paths."""
+    from horovod_b200.spark.lightning import datamodule, legacy, remote, util as lutil
+    assert remote.translate_trainer_args({'max_epochs': 3, 'gpus': 1, 'accumulate_grad_batches': 2}) == {'epochs': 3, 'backward_passes_per_step': 2}
+    with pytest.raises(ValueError, match='limit_train_batches'):
+        remote.translate_trainer_args({'limit_train_batches': 0.5})
+    assert datamodule.PetastormDataModule is datamodule.ParquetDataModule and callable(remote.RemoteTrainer({}))
+    m = torch.nn.Linear(2, 1)
+    back = lutil.deserialize_fn()(lutil.serialize_fn()(m))
+    assert torch.equal(back.weight, m.weight) and lutil.is_module_available('torch') and not lutil.is_module_available('pytorch_lightning_x')
+    assert lutil.save_into_bio({'a': 1}, torch.save).read(2) == b'PK'
+
+    df, w = _frame(256, seed=2)
+    torch.manual_seed(2)
+    net = torch.nn.Linear(3, 1)
+    est = LightningEstimator(model=net, optimizer=torch.optim.SGD(net.parameters(), lr=0.1), loss_constructors=[lambda: torch.nn.MSELoss()],
+                             feature_cols=['features'], label_cols=['label'], batch_size=16, epochs=1, validation=0.25,
+                             store=str(tmp_path / 's'), backend=LocalBackend(2), use_gpu=False, verbose=0,
+                             trainer_args={'max_epochs': 4, 'enable_progress_bar': False})
+    est.setTrainReaderNumWorker(1).setTrainAsyncDataLoaderQueueSize(4).setValAsyncDataLoaderQueueSize(2).setNumGPUs(1)
+    assert est.getTrainAsyncDataLoaderQueueSize() == 4 and est.getTrainerArgs()['max_epochs'] == 4 and est.getDebugDataLoader() is False
+    model = est.fit(df)
+    hist = model.getHistory()
+    assert [h['epoch'] for h in hist] == [0, 1, 2, 3] and hist[-1]['loss'] < 0.1 * hist[0]['loss']      # max_epochs won over epochs=1
+    assert isinstance(model.getModel(), legacy.LegacyModule) and model.getLossConstructors() and model.getLoss() is None
+    with pytest.raises(ValueError, match='trainer_args'):
+        est.copy({'trainer_args': {'precision': 16}}).fit(df)
