@@ -117,6 +117,25 @@ class ParamsBase:
             other.setParams(**extra)
         return other
 
+    # -- persistence (Spark ML's MLWritable / MLReadable surface) -----------------------------------------------------------
+    def write(self):
+        from horovod_b200.spark.common.serialization import HorovodParamsWriter
+        return HorovodParamsWriter(self)
+
+    def save(self, path):
+        """Shortcut for `write().save(path)`."""
+        self.write().save(path)
+
+    @classmethod
+    def read(cls):
+        from horovod_b200.spark.common.serialization import HorovodParamsReader
+        return HorovodParamsReader(cls)
+
+    @classmethod
+    def load(cls, path):
+        """Shortcut for `read().load(path)`."""
+        return cls.read().load(path)
+
     def explainParams(self):
         return '\n'.join('%s: %s (default: %r, current: %r)' % (n, p.doc, p.default, self._values[n])
                          for n, p in sorted(self._table.items()))

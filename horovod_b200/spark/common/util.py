@@ -207,6 +207,7 @@ def prepare_data(num_processes, store, df, label_columns, feature_columns, valid
         if verbose:
             print('prepared %s: %d train rows, %d validation rows, %.0f bytes/row' %
                   (dataset.idx, train_rows, val_rows, dataset.metadata['avg_row_size']), flush=True)
+        set_dataset_properties(dataset.idx, (dataset.train_rows, dataset.val_rows, dataset.metadata, dataset.metadata['avg_row_size']))
         if keep:
             _dataset_cache.insert(key, df, dataset)
     try:
@@ -243,3 +244,116 @@ def existing_dataset(store, dataset_idx=None):
     meta = parquet_metadata(store, train_path)
     val_rows = parquet_metadata(store, val_path)['rows'] if has_val else 0
     return PreparedDataset(dataset_idx, train_path, val_path if has_val else None, meta['rows'], val_rows, meta)
+
+
+# ---- small helpers of the reference's util module that user code and the estimators' callers rely on --------------------------
+def to_list(var, length):
+    """None -> None; a scalar or a one-element list -> that element `length` times; a list of `length` entries -> itself."""
+    if var is None:
+        return None
+    var = list(var) if isinstance(var, (list, tuple)) else [var]
+    if len(var) == 1:
+        return var * length
+    if len(var) != length:
+        raise ValueError('List must have %d entries (or one), found %d' % (length, len(var)))
+    return var
+
+
+def numpy_type_to_str(dtype):
+    """np.float32 / dtype('float32') / 'float32' -> 'float32' (what the metadata dictionaries store)."""
+    return np.dtype(dtype).name
+
+
+_SPARK_TO_NUMPY = {'BooleanType': np.bool_, 'ByteType': np.int8, 'ShortType': np.int16, 'IntegerType': np.int32, 'LongType': np.int64,
+                   'FloatType': np.float32, 'DoubleType': np.float64, 'StringType': np.str_, 'BinaryType': np.bytes_}
+
+
+def data_type_to_str(dtype):
+    """Spark SQL type (instance or class) -> its name without the 'Type' suffix: IntegerType() -> 'Integer'; vector and
+    array columns report 'Vector' / 'Array' (reference util.py `data_type_to_str`)."""
+    name = dtype if isinstance(dtype, str) else getattr(dtype, '__name__', None) or type(dtype).__name__
+    if name in ('VectorUDT', 'DenseVector', 'SparseVector'):
+        return 'Vector'
+    return name[:-4] if name.endswith('Type') else name
+
+
+def data_type_to_numpy(dtype):
+    """Spark SQL scalar type -> numpy scalar type; vectors and arrays of floats -> float64 / float32 element type."""
+    name = dtype if isinstance(dtype, str) else getattr(dtype, '__name__', None) or type(dtype).__name__
+    if name in ('VectorUDT', 'DenseVector', 'SparseVector', 'Vector'):
+        return np.float64
+    if name == 'ArrayType':
+        return data_type_to_numpy(getattr(dtype, 'elementType', 'DoubleType'))
+    key = name if name.endswith('Type') else name + 'Type'
+    if key not in _SPARK_TO_NUMPY:
+        raise ValueError('Unrecognized data type: %s' % name)
+    return _SPARK_TO_NUMPY[key]
+
+
+def spark_scalar_to_python_type(dtype):
+    """Spark SQL scalar type -> the Python type of a collected value."""
+    np_type = data_type_to_numpy(dtype)
+    if np_type is np.bool_:
+        return bool
+    if np_type is np.str_:
+        return str
+    if np_type is np.bytes_:
+        return bytes
+    return float if np.issubdtype(np_type, np.floating) else int
+
+
+def pyarrow_to_spark_data_type(dtype):
+    """pyarrow DataType -> the NAME of the Spark SQL type that holds it ('IntegerType', 'ArrayType(FloatType)', ...); returns
+    the pyspark class instance instead when pyspark is importable."""
+    import pyarrow.types as pat
+    table = ((pat.is_boolean, 'BooleanType'), (pat.is_int8, 'ByteType'), (pat.is_int16, 'ShortType'), (pat.is_int32, 'IntegerType'),
+             (pat.is_int64, 'LongType'), (pat.is_float32, 'FloatType'), (pat.is_float64, 'DoubleType'), (pat.is_string, 'StringType'),
+             (pat.is_large_string, 'StringType'), (pat.is_binary, 'BinaryType'), (pat.is_large_binary, 'BinaryType'))
+    if pat.is_list(dtype) or pat.is_large_list(dtype) or pat.is_fixed_size_list(dtype):
+        inner = pyarrow_to_spark_data_type(dtype.value_type)
+        try:
+            from pyspark.sql.types import ArrayType
+            return ArrayType(inner)
+        except ImportError:
+            return 'ArrayType(%s)' % inner
+    for pred, name in table:
+        if pred(dtype):
+            try:
+                import pyspark.sql.types as st
+                return getattr(st, name)()
+            except ImportError:
+                return name
+    raise ValueError('Unrecognized pyarrow data type: %s' % dtype)
+
+
+def get_simple_meta_from_parquet(store, label_columns, feature_columns, sample_weight_col=None, dataset_idx=None):
+    """(train_rows, val_rows, metadata, avg_row_size) of the Parquet the store already holds for `dataset_idx`; raises when a
+    needed column is missing or the training set is empty (reference util.py :444-500)."""
+    train_path = store.get_train_data_path(dataset_idx)
+    if not store.exists(train_path) or not store.is_parquet_dataset(train_path):
+        raise ValueError('{} is not a parquet dataset'.format(train_path))
+    meta = parquet_metadata(store, train_path)
+    if meta['rows'] == 0:
+        raise ValueError('Training data is empty: {}'.format(train_path))
+    needed = list(label_columns) + list(feature_columns) + ([sample_weight_col] if sample_weight_col else [])
+    missing = [c for c in needed if c not in meta['columns']]
+    if missing:
+        raise ValueError('Column(s) %s not found in %s (columns: %s)' % (missing, train_path, sorted(meta['columns'])))
+    val_path = store.get_val_data_path(dataset_idx)
+    val_rows = parquet_metadata(store, val_path)['rows'] if store.exists(val_path) and store.is_parquet_dataset(val_path) else 0
+    metadata = {c: {'spark_data_type': None, 'is_sparse_vector_only': False, 'shape': info['shape'], 'intermediate_format':
+                    'array' if info['shape'] else 'nochange', 'max_size': int(np.prod(info['shape'])) if info['shape'] else 1,
+                    'dtype': info['dtype']} for c, info in meta['columns'].items()}
+    return meta['rows'], val_rows, metadata, meta['avg_row_size']
+
+
+_dataset_properties = {}
+
+
+def get_dataset_properties(dataset_idx):
+    """(train_rows, val_rows, metadata, avg_row_size) remembered for a dataset prepared in this process."""
+    return _dataset_properties[dataset_idx]
+
+
+def set_dataset_properties(dataset_idx, props):
+    _dataset_properties[dataset_idx] = props

@@ -285,3 +285,15 @@ def test_unified_elastic_executor_callbacks_and_unsupported_calls(native_built):
         manager.shutdown()
     assert sorted(res) == [0, 1]
     assert sorted((d['rank'], d['step']) for d in seen) == [(r, s) for r in (0, 1) for s in range(3)]
+
+
+def test_spark_conf_for_elastic_jobs():
+    from horovod_b200.spark import conf
+    c = conf.elastic_conf()
+    assert c['spark.task.maxFailures'] == conf.SPARK_CONF_MAX_INT and c['spark.blacklist.enabled'] == 'false'
+    strict = conf.elastic_conf(reuse_failed_executors=False)
+    assert strict['spark.blacklist.enabled'] == 'true' and strict['spark.blacklist.stage.maxFailedTasksPerExecutor'] == '1'
+    assert set(k for k, _ in (conf.SPARK_CONF_REUSE_FAILING_NODE, conf.SPARK_CONF_REUSE_NODE_ONCE_FOR_SAME_TASK)) <= set(conf.SPARK_CONF_DEFAULT_VALUES)
+    warned = []
+    assert conf.check_elastic_conf(lambda k, d: d, warn=warned.append) == {'spark.task.maxFailures': '4'} and 'maxFailures' in warned[0]
+    assert conf.check_elastic_conf(lambda k, d: c.get(k, d)) == {}

@@ -100,3 +100,31 @@ def test_torch_loaders(tmp_path):
         assert [x['id'].tolist() for x in asy] == [x['id'].tolist() for x in PytorchDataLoader(shard, batch_size=8, shuffle=False)]
     finally:
         asy.close_async_loader()
+
+
+def test_reference_util_helpers(tmp_path):
+    import pyarrow as pa
+    assert util.to_list(None, 3) is None and util.to_list(1, 3) == [1, 1, 1] and util.to_list([1, 2], 2) == [1, 2]
+    with pytest.raises(ValueError):
+        util.to_list([1, 2], 3)
+    assert util.numpy_type_to_str(np.float32) == 'float32' and util.numpy_type_to_str('int64') == 'int64'
+    assert util.data_type_to_str('IntegerType') == 'Integer' and util.data_type_to_str('VectorUDT') == 'Vector'
+    assert util.data_type_to_numpy('FloatType') is np.float32 and util.data_type_to_numpy('Long') is np.int64
+    assert util.spark_scalar_to_python_type('DoubleType') is float and util.spark_scalar_to_python_type('ShortType') is int
+    assert util.spark_scalar_to_python_type('BooleanType') is bool and util.spark_scalar_to_python_type('StringType') is str
+    with pytest.raises(ValueError):
+        util.data_type_to_numpy('MapType')
+    assert util.pyarrow_to_spark_data_type(pa.int32()) == 'IntegerType'
+    assert util.pyarrow_to_spark_data_type(pa.list_(pa.float32())) == 'ArrayType(FloatType)'
+    store = LocalStore(str(tmp_path))
+    with pytest.raises(ValueError, match='not a parquet dataset'):
+        util.get_simple_meta_from_parquet(store, ['label'], ['vec'])
+    df = _frame(40)
+    with util.prepare_data(2, store, df, ['label'], ['vec'], validation=0.25, keep=True) as ds:
+        tr, va, meta, avg = util.get_simple_meta_from_parquet(store, ['label'], ['vec'], dataset_idx=ds.idx)
+        assert tr == ds.train_rows and va == ds.val_rows and tr + va == 40 and avg > 0
+        assert meta['vec']['intermediate_format'] == 'array' and meta['label']['intermediate_format'] == 'nochange'
+        assert meta['vec']['max_size'] == int(np.prod(meta['vec']['shape']))
+        assert util.get_dataset_properties(ds.idx)[0] == tr
+        with pytest.raises(ValueError, match='nope'):
+            util.get_simple_meta_from_parquet(store, ['nope'], ['vec'], dataset_idx=ds.idx)

@@ -172,3 +172,47 @@ def test_make_transform_drops_removed_fields():
     f = make_transform(lambda b: dict(b, extra=1), ['a'])
     assert f({'a': 1, 'b': 2}) == {'b': 2, 'extra': 1}
     assert make_transform(None, ['a'])({'a': 1, 'b': 2}) == {'b': 2}
+
+
+def test_estimator_and_model_save_load_round_trip(native_built, tmp_path):
+    """write().save(path) / load(path) (Spark ML's MLWritable / MLReadable surface; reference test_spark_torch.py
+    ::test_torch_direct_parquet_train + serialization tests): a trained TorchModel comes back with the same weights and
+    predictions, an estimator with its knobs, losses and store."""
+    import json
+    from horovod_b200.spark.common.serialization import HorovodParamsReader
+    from horovod_b200.spark.torch import TorchModel
+    rng = np.random.RandomState(3)
+    x = rng.randn(128, 2).astype(np.float32)
+    df = pd.DataFrame({'features': list(x), 'label': x @ np.array([1.0, -1.0], dtype=np.float32)})
+    torch.manual_seed(3)
+    model = torch.nn.Linear(2, 1)
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    est = TorchEstimator(model=model, optimizer=opt, loss=torch.nn.functional.mse_loss, feature_cols=['features'], label_cols=['label'],
+                         batch_size=16, epochs=3, store=str(tmp_path / 'store'), backend=LocalBackend(1), use_gpu=False, verbose=0)
+    est_path = str(tmp_path / 'saved_estimator')
+    est.save(est_path)
+    with pytest.raises(IOError, match='overwrite'):
+        est.write().save(est_path)
+    est.setEpochs(2).write().overwrite().save(est_path)
+    meta = json.load(open(est_path + '/metadata/part-00000'))
+    assert meta['class'].endswith('TorchEstimator') and meta['paramMap']['epochs'] == 2 and '__torch__' in meta['paramMap']['model']
+    est2 = TorchEstimator.load(est_path)
+    assert est2.getEpochs() == 2 and est2.getFeatureCols() == ['features'] and isinstance(est2.getStore(), LocalStore)
+    assert isinstance(est2.getOptimizer(), torch.optim.SGD) and est2.getLoss() is torch.nn.functional.mse_loss
+    assert torch.equal(est2.getModel().weight, model.weight)
+    tm = est2.fit(df)                                                # the loaded estimator trains
+    assert len(tm.getHistory()) == 2
+    model_path = str(tmp_path / 'saved_model')
+    tm.write().save(model_path)
+    tm2 = TorchModel.load(model_path)
+    assert tm2.getHistory() == tm.getHistory() and tm2.getRunId() == tm.getRunId() and tm2.getOutputCols() == ['label__output']
+    np.testing.assert_allclose(np.array(tm2.transform(df.head(6))['label__output'].tolist()),
+                               np.array(tm.transform(df.head(6))['label__output'].tolist()))
+    assert isinstance(HorovodParamsReader().load(model_path), TorchModel)          # class resolved from the metadata
+    with pytest.raises(TypeError):
+        TorchEstimator.load(model_path)
+    # through a Store's filesystem
+    st = est.getStore()
+    tm.write().option('store', st).save(st.get_run_path(tm.getRunId()) + '/model')
+    assert st.exists(st.get_run_path(tm.getRunId()) + '/model/metadata/part-00000')
+    assert TorchModel.read().option('store', st).load(st.get_run_path(tm.getRunId()) + '/model').getRunId() == tm.getRunId()
