@@ -156,61 +156,29 @@ class LearningRateWarmupCallback(LearningRateScheduleCallback):
             print('\nEpoch %d: finished gradual learning rate warmup to %g.' % (epoch + 1, _get_lr(self.model.optimizer)))
 
 
-# ---- elastic -------------------------------------------------------------------------------------------------------------
-class CommitStateCallback(tf.keras.callbacks.Callback):
+# ---- elastic (logic in _keras/elastic.py, mixed with this Keras' Callback class) ---------------------------------------------
+from horovod_b200._keras import elastic as _elastic_impl  # noqa: E402
+
+
+class CommitStateCallback(_elastic_impl.CommitStateCallbackImpl, tf.keras.callbacks.Callback):
     """state.commit() every `batches_per_commit` batches and at every epoch end."""
 
     def __init__(self, state, batches_per_commit=1):
-        super().__init__()
-        self.state, self.batches_per_commit = state, batches_per_commit
-        self.batches_remaining = batches_per_commit
-
-    def on_train_begin(self, logs=None):
-        self.batches_remaining = self.batches_per_commit
-
-    def on_batch_end(self, batch, logs=None):
-        self.batches_remaining -= 1
-        if self.batches_remaining == 0:
-            self.state.commit()
-            self.batches_remaining = self.batches_per_commit
-
-    def on_epoch_end(self, epoch, logs=None):
-        self.state.commit()
-        self.batches_remaining = self.batches_per_commit
+        super().__init__(tf.keras.backend if hasattr(tf.keras, 'backend') else None, state, batches_per_commit)
 
 
-class UpdateBatchStateCallback(tf.keras.callbacks.Callback):
+class UpdateBatchStateCallback(_elastic_impl.UpdateBatchStateCallbackImpl, tf.keras.callbacks.Callback):
     """Tracks state.batch so that a restarted epoch skips the batches already consumed."""
 
     def __init__(self, state):
-        super().__init__()
-        self.state = state
-        self.steps_per_epoch = None
-
-    def on_train_begin(self, logs=None):
-        self.steps_per_epoch = (self.params or {}).get('steps')
-
-    def on_epoch_begin(self, epoch, logs=None):
-        if self.steps_per_epoch and 'steps' in (self.params or {}):
-            self.params['steps'] = self.steps_per_epoch - self.state.batch
-
-    def on_batch_end(self, batch, logs=None):
-        self.state.batch = batch
-
-    def on_epoch_end(self, epoch, logs=None):
-        self.state.batch = 0
+        super().__init__(tf.keras.backend if hasattr(tf.keras, 'backend') else None, state)
 
 
-class UpdateEpochStateCallback(tf.keras.callbacks.Callback):
+class UpdateEpochStateCallback(_elastic_impl.UpdateEpochStateCallbackImpl, tf.keras.callbacks.Callback):
+    """Tracks state.epoch across resets."""
+
     def __init__(self, state):
-        super().__init__()
-        self.state = state
-
-    def on_train_begin(self, logs=None):
-        self._initial = self.state.epoch
-
-    def on_epoch_end(self, epoch, logs=None):
-        self.state.epoch = self._initial + epoch + 1 if epoch < self._initial else epoch + 1
+        super().__init__(tf.keras.backend if hasattr(tf.keras, 'backend') else None, state)
 
 
 class BestModelCheckpoint(tf.keras.callbacks.Callback):
@@ -253,3 +221,11 @@ class BestModelCheckpoint(tf.keras.callbacks.Callback):
             self.model.save(path)
         if self.verbose:
             print('Epoch %d: %s improved to %.5f, saving model to %s' % (epoch + 1, self.monitor, value, path))
+
+
+# the reference splits every callback into a backend-independent `...Impl` and the Keras subclass; here the classes above are
+# written against the Callback protocol directly, so the Impl names are the classes themselves
+BroadcastGlobalVariablesCallbackImpl = BroadcastGlobalVariablesCallback
+MetricAverageCallbackImpl = MetricAverageCallback
+LearningRateScheduleCallbackImpl = LearningRateScheduleCallback
+LearningRateWarmupCallbackImpl = LearningRateWarmupCallback

@@ -116,8 +116,42 @@ def test_training_side_dispatcher_and_restrictions():
         svc.shutdown()
 
 
+def test_spark_compute_worker_driver(tmp):
+    """spark/tensorflow/compute_worker.main with an injected `run`: the driver hosts the ComputeService, writes the config and
+    starts one worker per task; the plan rejects task counts that do not divide by the dispatchers."""
+    from horovod_b200.spark.tensorflow import compute_worker as scw
+    assert scw.plan(4, 2) == 2
+    with pytest.raises(ValueError, match='multiple'):
+        scw.plan(3, 2)
+    cfg_file = str(tmp / 'compute.json')
+    seen = {}
+
+    def fake_run(fn, args=(), num_proc=None, verbose=None, **kw):
+        cfg = args[0]
+        assert fn is compute_worker_fn and num_proc == 2 and cfg.dispatchers == 1 and cfg.workers_per_dispatcher == 2
+        on_disk = TfDataServiceConfig.read(cfg_file)
+        assert on_disk.addresses == cfg.addresses and on_disk.key == cfg.key and on_disk.dispatcher_side == 'compute'
+        threads = [threading.Thread(target=fn, args=(cfg,), kwargs=dict(rank=r, servers=FakeServers), daemon=True) for r in range(num_proc)]
+        for t in threads:
+            t.start()
+        addr = cfg.compute_client().wait_for_dispatcher_registration(0, 10)
+        cfg.compute_client().wait_for_dispatcher_worker_registration(0, 10)
+        seen['addr'] = addr
+        cfg.compute_client().shutdown()
+        for t in threads:
+            t.join(20)
+            assert not t.is_alive()
+        return [None] * num_proc
+    assert scw.main(cfg_file, dispatchers=1, timeout=10, run=fake_run, workers=2) == [None, None]
+    assert seen['addr'].startswith('grpc://')
+    a = scw.parse_args(['cfg.json', '--dispatchers', '2', '--dispatcher-side', 'training'])
+    assert (a.configfile, a.dispatchers, a.dispatcher_side, a.timeout) == ('cfg.json', 2, 'training', 60)
+
+
 if __name__ == '__main__':
     import pathlib, tempfile
+    with tempfile.TemporaryDirectory() as d:
+        test_spark_compute_worker_driver(pathlib.Path(d))
     with tempfile.TemporaryDirectory() as d:
         test_config_round_trip(pathlib.Path(d))
     test_compute_side_dispatchers_end_to_end()

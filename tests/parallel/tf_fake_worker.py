@@ -201,6 +201,50 @@ for epoch, value in enumerate([1.0, 0.5, 0.7, 0.4]):
     best.on_epoch_end(epoch, {'val_loss': value})
 assert saved == ['/tmp/ckpt-1', '/tmp/ckpt-2', '/tmp/ckpt-4'] and best.best == 0.4 and best.best_epoch == 3
 assert hvdk.callbacks.BestModelCheckpoint(monitor='val_acc').mode == 'max'
+
+# elastic callbacks (logic in _keras/elastic.py, reference _keras/elastic.py): commit cadence, batch / epoch bookkeeping
+import horovod_b200.keras.elastic as hke
+import horovod_b200.tensorflow.keras.elastic as hvdke
+from horovod_b200._keras import elastic as keras_elastic_impl
+
+
+class _State:
+    def __init__(self):
+        self.commits, self.batch, self.epoch = 0, 0, 0
+
+    def commit(self):
+        self.commits += 1
+
+
+st = _State()
+cb = hvdke.CommitStateCallback(st, batches_per_commit=3)
+assert isinstance(cb, keras_elastic_impl.CommitStateCallbackImpl) and hke.CommitStateCallback is hvdke.CommitStateCallback
+cb.on_train_begin()
+for b in range(7):
+    cb.on_batch_end(b)
+assert st.commits == 2 and cb.batches_remaining == 2
+cb.on_epoch_end(0)
+assert st.commits == 3 and cb.batches_remaining == 3
+ub = hvdke.UpdateBatchStateCallback(st)
+ub.params = {'steps': 10}
+ub.on_train_begin()
+st.batch = 4                                          # restored from the last commit: 4 batches of this epoch are done
+ub.on_epoch_begin(0)
+assert ub.params['steps'] == 6
+ub.on_batch_end(5)
+assert st.batch == 5
+ub.on_epoch_end(0)
+assert st.batch == 0
+ue = hvdke.UpdateEpochStateCallback(st)
+st.epoch = 3                                          # resumed job: Keras counts from 0 again, the state keeps counting
+ue.on_train_begin()
+ue.on_epoch_end(0)
+assert st.epoch == 4
+ue.on_epoch_end(1)
+assert st.epoch == 5
+assert hvdke.TensorFlowKerasState is hke.TensorFlowKerasState
+from horovod_b200._keras import callbacks as kcb
+assert kcb.MetricAverageCallbackImpl is kcb.MetricAverageCallback and kcb.LearningRateWarmupCallbackImpl is kcb.LearningRateWarmupCallback
 # TF extras
 assert hvd.broadcast_object_fn(root_rank=n - 1, name='bofn')({'from': r}) == {'from': n - 1}
 assert hvd.check_num_rank_power_of_2(4) and not hvd.check_num_rank_power_of_2(6) and hvd.gpu_available() in (True, False)
