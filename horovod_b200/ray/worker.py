@@ -13,9 +13,10 @@ class BaseHorovodWorker(WorkerActor):
 
     def __init__(self, world_rank=0, world_size=1):
         super().__init__(world_rank)
-        os.environ.setdefault('HOROVOD_HOSTNAME', self.node_id())
-        os.environ.setdefault('HOROVOD_RANK', str(world_rank))
-        os.environ.setdefault('HOROVOD_SIZE', str(world_size))
+        # an actor is its own process: its environment describes this worker until the executor hands out the rank table
+        os.environ['HOROVOD_HOSTNAME'] = self.node_id()
+        os.environ['HOROVOD_RANK'] = str(world_rank)
+        os.environ['HOROVOD_SIZE'] = str(world_size)
 
     def get_gpu_ids(self):
         """GPU ids Ray assigned to this actor (falls back to CUDA_VISIBLE_DEVICES outside Ray)."""

@@ -135,7 +135,10 @@ def test_params_and_adapter_interfaces():
 
 def test_base_worker_and_utils(monkeypatch):
     from horovod_b200.ray import BaseHorovodWorker, utils
+    for k in ('HOROVOD_HOSTNAME', 'HOROVOD_RANK', 'HOROVOD_SIZE', 'HVD_FAKE_VAR'):
+        monkeypatch.setenv(k, 'restored-at-teardown')       # the worker writes these into os.environ (it owns its process)
     w = BaseHorovodWorker(world_rank=3, world_size=8)
+    assert os.environ['HOROVOD_RANK'] == '3' and os.environ['HOROVOD_SIZE'] == '8'
     assert w.update_env_vars({'HVD_FAKE_VAR': 7}) and w.env_vars()['HVD_FAKE_VAR'] == '7'
     monkeypatch.setenv('CUDA_VISIBLE_DEVICES', '2,5')
     assert w.get_gpu_ids() == ['2', '5']
