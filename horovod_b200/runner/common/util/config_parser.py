@@ -14,6 +14,10 @@ def _flag(v):
     return 1 if v else 0
 
 
+def _only_when_set(v):
+    return 1 if v else None
+
+
 def _mb_to_bytes(v):
     return int(v * 1024 * 1024)
 
@@ -50,6 +54,7 @@ OPTIONS = [
     _opt('stall_check_warning_time_seconds', 'stall_check', 'warning_time_seconds', 'HOROVOD_STALL_CHECK_TIME_SECONDS', nonneg=True),
     _opt('stall_check_shutdown_time_seconds', 'stall_check', 'shutdown_time_seconds', 'HOROVOD_STALL_SHUTDOWN_TIME_SECONDS', nonneg=True),
     _opt('mpi_threads_disable', 'library_options', 'mpi_threads_disable', 'HOROVOD_MPI_THREADS_DISABLE', _flag),
+    _opt('tcp_flag', 'library_options', 'tcp', 'NCCL_IB_DISABLE', _only_when_set),      # --tcp: no InfiniBand for NCCL either
     _opt('gloo_timeout_seconds', 'library_options', 'gloo_timeout_seconds', 'HOROVOD_GLOO_TIMEOUT_SECONDS', nonneg=True),
     _opt('gpu_backend', 'library_options', 'gpu_backend', 'HVD_GPU_BACKEND'),
     _opt('allreduce_variant', 'library_options', 'allreduce_variant', 'HVD_ALLREDUCE_VARIANT'),
@@ -102,5 +107,7 @@ def set_env_from_args(env, args):
         value = getattr(args, o.attr, None)
         if value is None or (o.needs and not getattr(args, o.needs, None)):
             continue
-        env[o.env] = str(o.conv(value) if o.conv else value)
+        value = o.conv(value) if o.conv else value
+        if value is not None:
+            env[o.env] = str(value)
     return env

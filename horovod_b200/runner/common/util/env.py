@@ -25,3 +25,13 @@ def get_env_rank_and_size(environ=None):
         if rank_var in environ and size_var in environ:
             return int(environ[rank_var]), int(environ[size_var])
     return 0, 1
+
+
+# Kubeflow's MPI operator gives launcher pods no sshd: remote commands go through this script (`kubectl exec` underneath), and
+# the operator announces it as Open MPI's rsh agent
+KUBEFLOW_MPI_EXEC = '/etc/mpi/kubexec.sh'
+
+
+def is_kubeflow_mpi(environ=None):
+    environ = os.environ if environ is None else environ
+    return environ.get('OMPI_MCA_plm_rsh_agent') == KUBEFLOW_MPI_EXEC

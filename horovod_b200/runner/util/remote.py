@@ -2,7 +2,10 @@
 `get_ssh_command` / `get_remote_command`)."""
 import shlex
 
+from horovod_b200.runner.common.util import env as env_util
 from horovod_b200.runner.util.network import is_local_host
+
+SSH_COMMAND_PREFIX = 'ssh -o PasswordAuthentication=no -o StrictHostKeyChecking=no'
 
 SSH_BASE_OPTIONS = ('-o', 'PasswordAuthentication=no', '-o', 'StrictHostKeyChecking=no')
 
@@ -21,7 +24,10 @@ def ssh_argv(host, port=None, identity_file=None, timeout_s=None, extra_options=
 
 
 def get_ssh_command(local_command, host, port=None, identity_file=None, timeout_s=None):
-    """Shell string that runs `local_command` on `host` through ssh (no password prompts, no host-key questions)."""
+    """Shell string that runs `local_command` on `host` through ssh (no password prompts, no host-key questions); inside a
+    Kubeflow MPI-operator launcher pod (no sshd in the worker pods) through the operator's `kubexec.sh` instead."""
+    if env_util.is_kubeflow_mpi():
+        return '%s %s %s' % (env_util.KUBEFLOW_MPI_EXEC, host, shlex.quote(local_command))
     return ' '.join(ssh_argv(host, port, identity_file, timeout_s)) + ' ' + shlex.quote(local_command)
 
 

@@ -76,6 +76,10 @@ def test_config_file_and_override(tmp_path):
     assert args.timeline_filename == 'tl.json' and args.no_stall_check and args.log_level == 'DEBUG'
     with pytest.raises(ValueError):
         _parse(['-np', '2', '--cycle-time-ms', '-1', 'python', 'x.py'])
+    # --tcp also keeps NCCL off InfiniBand; without the flag the variable is not touched
+    from horovod_b200.runner.common.util import config_parser
+    assert config_parser.set_env_from_args({}, _parse(['-np', '2', '--tcp', 'python', 'x.py']))['NCCL_IB_DISABLE'] == '1'
+    assert 'NCCL_IB_DISABLE' not in config_parser.set_env_from_args({}, _parse(['-np', '2', 'python', 'x.py']))
 
 
 def test_mpi_command_construction():
@@ -348,6 +352,13 @@ def test_remote_command_and_pipe():
     assert cmd.endswith("""'echo '"'"'a b'"'"''""")
     assert remote.get_remote_command('ls', 'localhost') == 'ls' and remote.get_remote_command('ls', '10.255.255.1').startswith('ssh ')
     assert remote.ssh_argv('h')[-1] == 'h' and '-p' not in remote.ssh_argv('h')
+    # Kubeflow MPI operator: worker pods have no sshd, the operator's kubexec.sh is the remote shell
+    from horovod_b200.runner.common.util import env as env_util
+    assert not env_util.is_kubeflow_mpi({}) and remote.SSH_COMMAND_PREFIX.startswith('ssh ')
+    with mock.patch.dict(os.environ, {'OMPI_MCA_plm_rsh_agent': env_util.KUBEFLOW_MPI_EXEC}):
+        assert env_util.is_kubeflow_mpi()
+        assert remote.get_remote_command("echo 'a b'", 'worker-1') == """/etc/mpi/kubexec.sh worker-1 'echo '"'"'a b'"'"''"""
+        assert remote.get_remote_command('ls', 'localhost') == 'ls'
 
     pipe = streams.Pipe(max_chunks=2)
     got = []
