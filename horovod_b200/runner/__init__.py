@@ -1,4 +1,4 @@
-"""Programmatic launcher API: `horovod_b200.run(fn, args=(...), np=4)` runs a Python function on every rank and returns
+"""Programmatic launcher API: `horovod_b200.run(fn, args=(...), num_proc=4)` runs a Python function on every rank and returns
 the list of results (reference horovod/runner/__init__.py:95-247)."""
 
 
@@ -95,12 +95,34 @@ def _pickle_by_value_if_not_importable(func):
             pass
 
 
-def run(func, args=(), kwargs=None, np=1, min_np=None, max_np=None, slots=None, reset_limit=None, cooldown_range=None,
-        hosts=None, hostfile=None, start_timeout=None, ssh_port=None, ssh_identity_file=None, disable_cache=None,
-        output_filename=None, verbose=None, use_gloo=None, use_mpi=None, mpi_args=None, network_interfaces=None,
-        executable=None):
-    """Launches `func(*args, **kwargs)` on `np` processes and returns the per-rank results, rank-ordered."""
+def run(func, args=(), kwargs=None, num_proc=None, min_num_proc=None, max_num_proc=None, slots=None, reset_limit=None,
+        cooldown_range=None, hosts=None, hostfile=None, host_discovery_script=None, start_timeout=None, ssh_port=None,
+        ssh_identity_file=None, disable_cache=None, output_filename=None, verbose=None, use_gloo=None, use_mpi=None, mpi_args=None,
+        network_interface=None, network_interfaces=None, executable=None, np=None, min_np=None, max_np=None):
+    """Launches `func(*args, **kwargs)` on `num_proc` processes and returns the per-rank results, rank-ordered (reference
+    horovod/runner/__init__.py `run` :95-260).  `host_discovery_script` (or `min_num_proc`) makes the job elastic.  `np`,
+    `min_np`, `max_np` and `network_interface` are the deprecated spellings of `num_proc`, `min_num_proc`, `max_num_proc` and
+    `network_interfaces`."""
+    import warnings
     from horovod_b200.runner.launch import _run
+
+    def pick(new, old, new_name, old_name, default=None):
+        if old is not None:
+            if new is not None and new != old:
+                raise ValueError('%s and %s were both given with different values; %s is deprecated, use %s' % (new_name, old_name, old_name, new_name))
+            warnings.warn('%s is deprecated, use %s instead' % (old_name, new_name), DeprecationWarning, stacklevel=3)
+            return old
+        return default if new is None else new
+    np = pick(num_proc, np, 'num_proc', 'np', default=1)
+    min_np = pick(min_num_proc, min_np, 'min_num_proc', 'min_np')
+    max_np = pick(max_num_proc, max_np, 'max_num_proc', 'max_np')
+    if network_interface is not None:
+        if network_interfaces is not None:
+            raise ValueError('network_interface and network_interfaces were both given; network_interface is deprecated')
+        warnings.warn('network_interface is deprecated, use network_interfaces instead', DeprecationWarning, stacklevel=2)
+        network_interfaces = network_interface
+    if isinstance(network_interfaces, (list, tuple, set)):
+        network_interfaces = ','.join(sorted(network_interfaces))
     if kwargs is None:
         kwargs = {}
 
@@ -118,6 +140,7 @@ def run(func, args=(), kwargs=None, np=1, min_np=None, max_np=None, slots=None, 
     hargs.cooldown_range = cooldown_range
     hargs.hosts = hosts
     hargs.hostfile = hostfile
+    hargs.host_discovery_script = host_discovery_script
     hargs.start_timeout = start_timeout
     hargs.ssh_port = ssh_port
     hargs.ssh_identity_file = ssh_identity_file

@@ -19,7 +19,7 @@ def launch_gloo(command, exec_command, settings, nics, env, server_ip):
 def gloo_run_elastic(settings, env, command_or_func, executable=None):
     """Elastic launch; the discovery / size limits come from the elastic settings object."""
     if callable(command_or_func):
-        raise ValueError('pass functions through horovod_b200.run(func, ..., min_np=..., max_np=...): it ships the function to the '
+        raise ValueError('pass functions through horovod_b200.run(func, ..., min_num_proc=..., max_num_proc=...): it ships the function to the '
                          'workers and then calls the elastic launcher with the task command')
     return elastic_run(settings, env, command_or_func, settings.discovery, settings.min_num_proc, settings.max_num_proc,
                        settings.elastic_timeout, settings.reset_limit, getattr(settings, 'cooldown_range', None))

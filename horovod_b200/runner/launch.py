@@ -399,8 +399,31 @@ def _run_elastic(args):
     env = os.environ.copy()
     config_parser.set_env_from_args(env, args)
     os.environ.update({k: v for k, v in env.items() if k.startswith(('HOROVOD_', 'HVD_'))})
-    return elastic_run(settings, env, args.command, disc, settings.min_num_proc, settings.max_num_proc,
-                       settings.elastic_timeout, settings.reset_limit, settings.cooldown_range)
+    if not args.run_func:
+        return elastic_run(settings, env, args.command, disc, settings.min_num_proc, settings.max_num_proc,
+                           settings.elastic_timeout, settings.reset_limit, settings.cooldown_range)
+    # run-func mode: the pickled function travels through a KV store; every worker of the FINAL round uploads its return
+    # value under the rank it held then (hvd.init rewrites HOROVOD_RANK on every elastic reset)
+    from horovod_b200.runner.http.http_server import KVStoreServer
+    import cloudpickle
+    kvstore = KVStoreServer(verbose=settings.verbose)
+    port = kvstore.start_server()
+    try:
+        kvstore.put('runfunc', 'func', cloudpickle.dumps(args.run_func))
+        command = [args.executable or sys.executable, '-m', 'horovod_b200.runner.run_task', str(network.get_driver_ip(settings.nics)), str(port)]
+        elastic_run(settings, env, command, disc, settings.min_num_proc, settings.max_num_proc,
+                    settings.elastic_timeout, settings.reset_limit, settings.cooldown_range)
+        results = []
+        while True:
+            raw = kvstore.get('runfunc_result', str(len(results)))
+            if raw is None:
+                break
+            results.append(cloudpickle.loads(raw))
+        if len(results) < settings.min_num_proc:
+            raise RuntimeError('hvdrun: only %d of at least %d workers returned a result' % (len(results), settings.min_num_proc))
+        return results
+    finally:
+        kvstore.shutdown_server()
 
 
 def is_gloo_used(use_gloo=None, use_mpi=None, use_jsrun=None):

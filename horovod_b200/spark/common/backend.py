@@ -55,7 +55,7 @@ class LocalBackend(Backend):
         saved = {k: os.environ.get(k) for k in extra}
         os.environ.update({k: str(v) for k, v in extra.items()})  # the launcher forwards the driver's environment
         try:
-            return horovod_b200.run(fn, args=args, kwargs=kwargs, np=self._num_proc, **self._kw)
+            return horovod_b200.run(fn, args=args, kwargs=kwargs, num_proc=self._num_proc, **self._kw)
         finally:
             for k, v in saved.items():
                 if v is None:

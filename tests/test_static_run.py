@@ -74,12 +74,38 @@ def _fn(a, b=0):
     return (r, a + b)
 
 
+def _elastic_fn():
+    import torch
+    import horovod_b200.torch as hvd
+    hvd.init()
+    out = hvd.allreduce(torch.ones(1), op=hvd.Sum, name='e').item()
+    res = (hvd.rank(), hvd.size(), out)
+    hvd.shutdown()
+    return res
+
+
 def test_run_func_api_returns_rank_ordered_results(native_built):
     import horovod_b200
-    res = horovod_b200.run(_fn, args=(10,), kwargs={'b': 5}, np=2)
+    res = horovod_b200.run(_fn, args=(10,), kwargs={'b': 5}, num_proc=2)
     assert res == [(0, 15), (1, 15)]
+    with pytest.warns(DeprecationWarning, match='np is deprecated'):          # the old spelling still works
+        assert horovod_b200.run(_fn, args=(1,), np=2, network_interfaces=['lo']) == [(0, 1), (1, 1)]
+    with pytest.raises(ValueError, match='deprecated'):
+        horovod_b200.run(_fn, args=(1,), num_proc=2, np=3)
+    with pytest.raises(ValueError, match='network_interface'):
+        horovod_b200.run(_fn, args=(1,), num_proc=1, network_interface='lo', network_interfaces='lo')
     with pytest.raises(Exception):
-        horovod_b200.run(lambda: 1 / 0, np=2)
+        horovod_b200.run(lambda: 1 / 0, num_proc=2)
+
+
+def test_run_func_api_elastic_with_discovery_script(native_built, tmp_path):
+    """run(..., host_discovery_script=...) is the programmatic form of `hvdrun --host-discovery-script`."""
+    import horovod_b200
+    script = tmp_path / 'discover.sh'
+    script.write_text('#!/bin/sh\necho localhost:2\n')
+    script.chmod(0o755)
+    res = horovod_b200.run(_elastic_fn, num_proc=2, min_num_proc=2, max_num_proc=2, host_discovery_script=str(script))
+    assert sorted(res) == [(0, 2, 2.0), (1, 2, 2.0)]
 
 
 def test_hard_crash_of_one_worker_terminates_the_job(native_built):
