@@ -357,3 +357,27 @@ def get_dataset_properties(dataset_idx):
 
 def set_dataset_properties(dataset_idx, props):
     _dataset_properties[dataset_idx] = props
+
+
+def get_available_devices():
+    """GPU addresses Spark assigned to THIS task (`spark.task.resource.gpu.amount`, Spark >= 3); [] outside a Spark task or when
+    the job requested no GPU resources (reference util.py `get_available_devices`)."""
+    try:
+        from pyspark import TaskContext
+    except ImportError:
+        return []
+    ctx = TaskContext.get()
+    if ctx is None or not hasattr(ctx, 'resources'):
+        return []
+    gpu = ctx.resources().get('gpu')
+    return list(gpu.addresses) if gpu is not None else []
+
+
+def gpu_index_for(local_rank, devices=None, environ=None):
+    """CUDA device index of a training process: the GPU Spark assigned to the task when there is one, else `local_rank`.
+    HOROVOD_SPARK_USE_LOCAL_RANK_GPU_INDEX=1 forces `local_rank` (clusters whose GPU addresses are not CUDA ordinals)."""
+    environ = os.environ if environ is None else environ
+    devices = get_available_devices() if devices is None else devices
+    if devices and environ.get('HOROVOD_SPARK_USE_LOCAL_RANK_GPU_INDEX', '0') == '0':
+        return int(devices[0])
+    return local_rank

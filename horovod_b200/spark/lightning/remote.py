@@ -30,7 +30,8 @@ def _train_fn(spec):
     from horovod_b200.spark.lightning.datamodule import ParquetDataModule
     from horovod_b200.spark.lightning.trainer import ModuleProtocolTrainer
     hvd.init()
-    dev = torch.device('cuda', hvd.local_rank()) if spec['use_gpu'] and torch.cuda.is_available() else torch.device('cpu')
+    from horovod_b200.spark.common.util import gpu_index_for
+    dev = torch.device('cuda', gpu_index_for(hvd.local_rank())) if spec['use_gpu'] and torch.cuda.is_available() else torch.device('cpu')
     if dev.type == 'cuda':
         torch.cuda.set_device(dev)
     store = spec['store']

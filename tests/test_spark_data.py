@@ -128,3 +128,10 @@ def test_reference_util_helpers(tmp_path):
         assert util.get_dataset_properties(ds.idx)[0] == tr
         with pytest.raises(ValueError, match='nope'):
             util.get_simple_meta_from_parquet(store, ['nope'], ['vec'], dataset_idx=ds.idx)
+
+
+def test_gpu_index_for_spark_task_resources():
+    assert util.get_available_devices() == []                       # no pyspark / no task context here
+    assert util.gpu_index_for(3, devices=[], environ={}) == 3
+    assert util.gpu_index_for(3, devices=['5', '6'], environ={}) == 5
+    assert util.gpu_index_for(3, devices=['5'], environ={'HOROVOD_SPARK_USE_LOCAL_RANK_GPU_INDEX': '1'}) == 3
