@@ -352,6 +352,57 @@ def _():
     hvd.barrier()
 
 
+@check('dynamic_requires_grad')
+def _():
+    """GAN-style alternation (reference test_torch.py::test_dynamic_requires_grad): two DistributedOptimizers, parameters
+    switched on and off between steps; only the trained half gets (reduced, identical) gradients, the other half none."""
+    torch.manual_seed(1234)
+    gen, disc = torch.nn.Conv2d(1, 4, 1).to(DEV), torch.nn.Conv2d(4, 1, 1).to(DEV)
+    hvd.broadcast_parameters(gen.state_dict(), root_rank=0)
+    hvd.broadcast_parameters(disc.state_dict(), root_rank=0)
+    inp = torch.rand([1, 1, 8, 8], generator=torch.Generator().manual_seed(100 + rank)).to(DEV)   # rank-specific data
+    gen_opt = hvd.DistributedOptimizer(torch.optim.SGD(gen.parameters(), lr=0.1), named_parameters=[('gen.' + n, q) for n, q in gen.named_parameters()])
+    disc_opt = hvd.DistributedOptimizer(torch.optim.SGD(disc.parameters(), lr=0.1), named_parameters=[('disc.' + n, q) for n, q in disc.named_parameters()])
+
+    def has_grad(q):
+        return q.grad is not None and bool(q.grad.abs().max() > 0)
+
+    def train_step(train_generator=False, train_discriminator=False):
+        for q in gen.parameters():
+            q.requires_grad_(train_generator)
+        for q in disc.parameters():
+            q.requires_grad_(train_discriminator)
+        gen_opt.zero_grad()
+        disc_opt.zero_grad()
+        disc(gen(inp)).sum().backward()
+        if train_generator:
+            gen_opt.step()
+        if train_discriminator:
+            disc_opt.step()
+        for q in gen.parameters():
+            assert train_generator == has_grad(q), ('generator', train_generator, q.grad)
+        for q in disc.parameters():
+            assert train_discriminator == has_grad(q), ('discriminator', train_discriminator, q.grad)
+
+    for _ in range(4):
+        train_step(train_generator=True)
+        train_step(train_discriminator=True)
+    train_step(train_generator=True, train_discriminator=True)
+    # different data on every rank, averaged gradients: the replicas must still be identical
+    for name, q in list(gen.named_parameters()) + list(disc.named_parameters()):
+        got = hvd.allgather(q.detach().reshape(1, -1), name='dyn.' + name + str(q.numel()))
+        assert torch.allclose(got, got[0:1].expand_as(got), atol=1e-6), name
+
+
+@check('missing_named_parameters')
+def _():
+    """named_parameters that covers only part of the optimizer's parameters is an error (reference
+    test_missing_named_parameters); so are duplicate names (test_duplicate_names is in duplicate_names_per_op)."""
+    net = torch.nn.Sequential(torch.nn.Conv2d(1, 4, 1), torch.nn.Conv2d(4, 1, 1)).to(DEV)
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    raises(ValueError, lambda: hvd.DistributedOptimizer(opt, named_parameters=list(net.named_parameters())[0:1]))
+
+
 @check('barriers_mixed')
 def _():
     ps = even_set()
