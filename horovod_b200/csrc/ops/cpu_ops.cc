@@ -1,6 +1,9 @@
 #include "cpu_ops.h"
 #include <algorithm>
 #include <atomic>
+#include <mutex>
+#include <deque>
+#include <condition_variable>
 #include <cfloat>
 #include <chrono>
 #include <cmath>
@@ -206,6 +209,61 @@ inline void BulkReduce(void* dst, const void* src, int64_t count, DataType dtype
   BulkTeam::Get().For(count, (int64_t)((256 << 10) / es), [&](int64_t lo, int64_t hi) {
     ReduceInto((char*)dst + lo * es, (const char*)src + lo * es, hi - lo, dtype, op);
   });
+}
+
+// One thread per process that executes ReduceInto jobs in submission order: the cross-host ring hands it the chunk it just
+// received and goes back to the sockets (RingAllreduce).  Created on first use; HVD_RING_CHUNK_BYTES (default 1 MiB, 0 = no
+// pipelining) is the chunk size.
+class RingReducer {
+ public:
+  static RingReducer& Get() { static RingReducer r; return r; }
+  uint64_t Submit(void* dst, const void* src, int64_t count, DataType dtype, ReduceOp op) {
+    std::lock_guard<std::mutex> g(mu_);
+    if (!started_) { started_ = true; thread_ = std::thread([this] { Run(); }); }
+    jobs_.push_back({dst, src, count, dtype, op});
+    cv_.notify_one();
+    return ++submitted_;
+  }
+  void Wait(uint64_t ticket) {
+    if (ticket == 0) return;
+    for (int spin = 0; done_.load(std::memory_order_acquire) < ticket; ++spin)
+      if (spin < 2000) __builtin_ia32_pause(); else std::this_thread::yield();
+  }
+  ~RingReducer() {
+    { std::lock_guard<std::mutex> g(mu_); stop_ = true; cv_.notify_one(); }
+    if (thread_.joinable()) thread_.join();
+  }
+
+ private:
+  struct Job { void* dst; const void* src; int64_t count; DataType dtype; ReduceOp op; };
+  void Run() {
+    std::unique_lock<std::mutex> lk(mu_);
+    while (true) {
+      cv_.wait(lk, [this] { return stop_ || !jobs_.empty(); });
+      if (jobs_.empty()) return;
+      Job j = jobs_.front();
+      jobs_.pop_front();
+      lk.unlock();
+      ReduceInto(j.dst, j.src, j.count, j.dtype, j.op);
+      done_.fetch_add(1, std::memory_order_release);
+      lk.lock();
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<Job> jobs_;
+  std::thread thread_;
+  bool started_ = false, stop_ = false;
+  uint64_t submitted_ = 0;
+  std::atomic<uint64_t> done_{0};
+};
+
+static int64_t RingChunkElems(size_t es) {
+  static const int64_t bytes = [] {
+    const char* e = getenv("HVD_RING_CHUNK_BYTES");
+    return e ? std::max<int64_t>(0, atoll(e)) : (int64_t)1 << 20;
+  }();
+  return bytes / (int64_t)es;
 }
 
 static std::atomic<unsigned long long> g_path_count[3];
@@ -486,12 +544,36 @@ void RingAllreduce(Transport* t, char* b, int64_t count, DataType dtype, ReduceO
   for (int i = 0; i <= n; ++i) off[i] = count * i / n;
   int64_t maxseg = 0;
   for (int i = 0; i < n; ++i) maxseg = std::max(maxseg, off[i + 1] - off[i]);
-  std::vector<char> tmp((size_t)maxseg * es);
   const int next = (r + 1) % n, prev = (r - 1 + n) % n;
-  for (int s = 0; s < n - 1; ++s) {
-    int si = (r - s + n) % n, ri = (r - s - 1 + n) % n;
-    t->SendRecv(next, b + off[si] * es, (size_t)(off[si + 1] - off[si]) * es, prev, tmp.data(), (size_t)(off[ri + 1] - off[ri]) * es);
-    ReduceInto(b + off[ri] * es, tmp.data(), off[ri + 1] - off[ri], dtype, op);
+  const int64_t chunk = RingChunkElems(es);
+  if (chunk > 0 && maxseg >= 2 * chunk) {
+    // big segments: every step moves its segment in chunks; the reducer thread folds chunk k into the buffer while this
+    // thread already exchanges chunk k+1 (two staging buffers), so the wire and the adds overlap
+    RingReducer& red = RingReducer::Get();
+    std::vector<char> stage[2] = {std::vector<char>((size_t)chunk * es), std::vector<char>((size_t)chunk * es)};
+    for (int s = 0; s < n - 1; ++s) {
+      const int si = (r - s + n) % n, ri = (r - s - 1 + n) % n;
+      const int64_t slen = off[si + 1] - off[si], rlen = off[ri + 1] - off[ri];
+      const int64_t pieces = (std::max(slen, rlen) + chunk - 1) / chunk;
+      uint64_t ticket[2] = {0, 0};
+      for (int64_t k = 0; k < pieces; ++k) {
+        const int64_t so = std::min(slen, k * chunk), sc = std::min(chunk, slen - so);
+        const int64_t ro = std::min(rlen, k * chunk), rc = std::min(chunk, rlen - ro);
+        char* st = stage[k & 1].data();
+        red.Wait(ticket[k & 1]);                       // the reduce that read this staging buffer two pieces ago
+        t->SendRecv(next, b + (off[si] + so) * es, (size_t)sc * es, prev, st, (size_t)rc * es);
+        ticket[k & 1] = rc > 0 ? red.Submit(b + (off[ri] + ro) * es, st, rc, dtype, op) : 0;
+      }
+      red.Wait(ticket[0]);                             // the next step sends the segment this step reduced
+      red.Wait(ticket[1]);
+    }
+  } else {
+    std::vector<char> tmp((size_t)maxseg * es);
+    for (int s = 0; s < n - 1; ++s) {
+      int si = (r - s + n) % n, ri = (r - s - 1 + n) % n;
+      t->SendRecv(next, b + off[si] * es, (size_t)(off[si + 1] - off[si]) * es, prev, tmp.data(), (size_t)(off[ri + 1] - off[ri]) * es);
+      ReduceInto(b + off[ri] * es, tmp.data(), off[ri + 1] - off[ri], dtype, op);
+    }
   }
   for (int s = 0; s < n - 1; ++s) {
     int si = (r + 1 - s + n) % n, ri = (r - s + n) % n;

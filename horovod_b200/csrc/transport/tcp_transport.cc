@@ -78,9 +78,32 @@ double RecvTimeoutSeconds() {
   return t;
 }
 
+// Negotiation messages and small payloads are answered within tens of microseconds; a blocking recv() pays a sleep / wake-up
+// round trip through the scheduler that is longer than that.  So every receive first polls the socket without blocking for
+// HVD_TCP_SPIN_US microseconds (default 50; 0 = block immediately), then falls back to the blocking path.
+double SpinSeconds() {
+  static const double t = [] {
+    const char* e = getenv("HVD_TCP_SPIN_US");
+    return (e ? std::max(0.0, atof(e)) : 50.0) * 1e-6;
+  }();
+  return t;
+}
+
 void ReadAll(int fd, void* buf, size_t n) {
   auto* p = (char*)buf;
   const double timeout_s = RecvTimeoutSeconds();
+  const double spin_s = SpinSeconds();
+  if (spin_s > 0) {
+    const double until = Now() + spin_s;
+    while (n) {
+      ssize_t k = ::recv(fd, p, n, MSG_DONTWAIT);
+      if (k > 0) { p += k; n -= (size_t)k; continue; }
+      if (k == 0) throw TransportError("peer closed connection");
+      if (errno != EAGAIN && errno != EWOULDBLOCK && errno != EINTR) throw TransportError(std::string("recv failed: ") + strerror(errno));
+      if (Now() > until) break;
+      __builtin_ia32_pause();
+    }
+  }
   while (n) {
     if (timeout_s > 0) {
       struct pollfd pf {fd, POLLIN, 0};
@@ -119,11 +142,15 @@ class TcpTransport : public Transport {
     auto* s = (const char*)sbuf; auto* r = (char*)rbuf;
     const double timeout_s = RecvTimeoutSeconds();
     double last_progress = Now();
+    double spin_until = SpinSeconds() > 0 ? last_progress + SpinSeconds() : 0;
     while (sn || rn) {
       struct pollfd pf[2]; int np = 0, si = -1, ri = -1;
       if (sn) { pf[np] = {sfd, POLLOUT, 0}; si = np++; }
       if (rn) { pf[np] = {rfd, POLLIN, 0}; ri = np++; }
-      int rc = poll(pf, np, timeout_s > 0 ? (int)std::min(5000.0, timeout_s * 1000) : 5000);
+      // same reasoning as in ReadAll: the first look at the sockets does not sleep
+      int rc = poll(pf, np, 0);
+      if (rc == 0 && spin_until > 0 && Now() < spin_until) { __builtin_ia32_pause(); continue; }
+      if (rc == 0) rc = poll(pf, np, timeout_s > 0 ? (int)std::min(5000.0, timeout_s * 1000) : 5000);
       if (rc < 0) { if (errno == EINTR) continue; throw TransportError("poll failed"); }
       if (rc == 0) {
         if (timeout_s > 0 && Now() - last_progress > timeout_s)
@@ -131,6 +158,7 @@ class TcpTransport : public Transport {
         continue;
       }
       last_progress = Now();
+      if (spin_until > 0) spin_until = last_progress + SpinSeconds();
       if (ri >= 0 && (pf[ri].revents & (POLLIN | POLLHUP | POLLERR))) {
         ssize_t k = ::recv(rfd, r, rn, MSG_DONTWAIT);
         if (k == 0) throw TransportError("peer closed connection");

@@ -61,6 +61,17 @@ def test_fake_two_hosts_np4(native_built):
     assert "ALL OK" in out, out[-3000:]
 
 
+@pytest.mark.parametrize("np_,hosts", [(3, "3"), (4, "2")])
+def test_pipelined_tcp_ring_allreduce(native_built, np_, hosts):
+    """Cross-host ring with a tiny HVD_RING_CHUNK_BYTES: every ring step is cut into many chunks and the reducer thread folds
+    chunk k while chunk k+1 is on the wire (cpu_ops.cc:RingAllreduce).  3 ranks on 3 "hosts" = the plain ring with uneven
+    segments; 4 ranks on 2 "hosts" = the cross-host rings of the two-level allreduce.  Exact integer-valued sums."""
+    rc, out = run_parallel("ops_worker.py", np=np_, timeout=400, env={"HVD_TEST_FAKE_HOSTS": hosts, "HVD_RING_CHUNK_BYTES": "8192"},
+                           args=["--only", "rank_size,allreduce_sum_avg,allreduce_min_max_product,allreduce_mixed_dtype_fusion,"
+                                 "large_allreduce,reducescatter"])
+    assert "ALL OK" in out, out[-3000:]
+
+
 def test_numpy_frontend_np2(native_built):
     rc, out = run_parallel("numpy_worker.py", np=2, timeout=200)
     assert "NUMPY OK" in out, out[-3000:]
