@@ -242,6 +242,41 @@ void TestCpuOps(int n) {
   CHECK_T(bad.load() == 0);
 }
 
+// AND / OR reduction of bit vectors among a subset of ranks: star for small groups, recursive doubling (with the fold-in of the
+// members beyond the largest power of two) otherwise.  HVD_BITS_TREE_MIN_RANKS is read once per process, so the selftest driver
+// (tests/test_native_unit.py) runs this binary a second time with the knob at 2.
+void TestBitsAmong(int n) {
+  auto hub = CreateLoopbackHub(n);
+  std::vector<std::thread> th;
+  std::atomic<int> bad{0};
+  for (int r = 0; r < n; ++r) {
+    th.emplace_back([&, r] {
+      auto t = LoopbackEndpoint(hub, r);
+      // all ranks
+      uint64_t a[2] = {~0ull & ~(1ull << r), 0xF0F0ull}, o[1] = {1ull << (r + 8)};
+      t->AllreduceBits(a, 2, o, 1);
+      uint64_t want_a = ~0ull, want_o = 0;
+      for (int p = 0; p < n; ++p) { want_a &= ~(1ull << p); want_o |= 1ull << (p + 8); }
+      if (a[0] != want_a || a[1] != 0xF0F0ull || o[0] != want_o) bad++;
+      // the odd ranks only, listed in reverse order (positions, not ranks, drive the exchange pattern)
+      std::vector<int> odd;
+      for (int p = n - 1; p >= 0; --p) if (p & 1) odd.push_back(p);
+      if ((r & 1) && odd.size() > 1) {
+        int me = 0;
+        while (odd[me] != r) ++me;
+        uint64_t w[2] = {~(1ull << r), (uint64_t)r};
+        t->AllreduceBitsAmong(odd, me, w, 1, 2);
+        uint64_t wa = ~0ull, wo = 0;
+        for (int p : odd) { wa &= ~(1ull << p); wo |= (uint64_t)p; }
+        if (w[0] != wa || w[1] != wo) bad++;
+      }
+      t->Barrier();
+    });
+  }
+  for (auto& t : th) t.join();
+  CHECK_T(bad.load() == 0);
+}
+
 void TestAdasum(int n) {
   if (n & (n - 1)) return;
   auto hub = CreateLoopbackHub(n);
@@ -419,6 +454,7 @@ extern "C" int hvd_selftest(int nranks, char* log, int log_len) {
   TestBayes();
   TestAutotune();
   for (int n : {1, 2, 3, nranks}) { if (n < 1) continue; TestCpuOps(n); TestAdasum(n); }
+  for (int n : {2, 3, 5, 6, 7, 8, 11}) TestBitsAmong(n);
   TestEngines(nranks);
   TestEngines(1);
   std::string s = g_log.str();

@@ -363,21 +363,12 @@ class HierShmControlTransport : public Transport {
       for (int i = 0; i < n_or; ++i) or_words[i] |= s.data[buf][n_and + i];
     }
     if (leaders_.size() > 1) {
-      std::vector<uint64_t> mine((size_t)std::max(n, 1)), tmp((size_t)std::max(n, 1));
+      std::vector<uint64_t> mine((size_t)std::max(n, 1));
       if (n_and) memcpy(mine.data(), and_words, (size_t)n_and * 8);
       if (n_or) memcpy(mine.data() + n_and, or_words, (size_t)n_or * 8);
-      const size_t wire = (size_t)std::max(n, 1) * 8;      // an empty vector (barrier) still travels as one word
-      if (rank() == leaders_[0]) {
-        for (size_t h = 1; h < leaders_.size(); ++h) {
-          base_->Recv(leaders_[h], tmp.data(), wire);
-          for (int i = 0; i < n_and; ++i) mine[i] &= tmp[i];
-          for (int i = n_and; i < n; ++i) mine[i] |= tmp[i];
-        }
-        for (size_t h = 1; h < leaders_.size(); ++h) base_->Send(leaders_[h], mine.data(), wire);
-      } else {
-        base_->Send(leaders_[0], mine.data(), wire);
-        base_->Recv(leaders_[0], mine.data(), wire);
-      }
+      int me = 0;
+      while (leaders_[me] != rank()) ++me;
+      base_->AllreduceBitsAmong(leaders_, me, mine.data(), n_and, n);
       if (n_and) memcpy(and_words, mine.data(), (size_t)n_and * 8);
       if (n_or) memcpy(or_words, mine.data() + n_and, (size_t)n_or * 8);
     }

@@ -1,6 +1,7 @@
 #include "transport.h"
 #include <algorithm>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <mutex>
@@ -56,22 +57,61 @@ void Transport::Bcast(void* buf, size_t n, int root) {
 void Transport::AllreduceBits(uint64_t* and_words, int n_and, uint64_t* or_words, int n_or) {
   if (size() == 1) return;
   const int n = n_and + n_or;
-  std::vector<uint64_t> mine(n), tmp(n);
+  std::vector<uint64_t> mine((size_t)std::max(n, 1));
   if (n_and) memcpy(mine.data(), and_words, n_and * 8);
   if (n_or) memcpy(mine.data() + n_and, or_words, n_or * 8);
-  if (rank() == 0) {
-    for (int r = 1; r < size(); ++r) {
-      Recv(r, tmp.data(), n * 8);
-      for (int i = 0; i < n_and; ++i) mine[i] &= tmp[i];
-      for (int i = n_and; i < n; ++i) mine[i] |= tmp[i];
-    }
-    for (int r = 1; r < size(); ++r) Send(r, mine.data(), n * 8);
-  } else {
-    Send(0, mine.data(), n * 8);
-    Recv(0, mine.data(), n * 8);
-  }
+  std::vector<int> all(size());
+  for (int i = 0; i < size(); ++i) all[i] = i;
+  AllreduceBitsAmong(all, rank(), mine.data(), n_and, n);
   if (n_and) memcpy(and_words, mine.data(), n_and * 8);
   if (n_or) memcpy(or_words, mine.data() + n_and, n_or * 8);
+}
+
+static int BitsTreeMinRanks() {
+  static const int v = [] {
+    const char* e = getenv("HVD_BITS_TREE_MIN_RANKS");
+    return e ? std::max(2, atoi(e)) : 9;
+  }();
+  return v;
+}
+
+void Transport::AllreduceBitsAmong(const std::vector<int>& peers, int me, uint64_t* words, int n_and, int n) {
+  const int m = (int)peers.size();
+  if (m <= 1) return;
+  const size_t wire = (size_t)std::max(n, 1) * 8;          // an empty vector (barrier) still travels as one word
+  std::vector<uint64_t> tmp((size_t)std::max(n, 1));
+  auto fold = [&] {
+    for (int i = 0; i < n_and; ++i) words[i] &= tmp[i];
+    for (int i = n_and; i < n; ++i) words[i] |= tmp[i];
+  };
+  if (m < BitsTreeMinRanks()) {
+    // star: the replies of m - 1 members arrive concurrently, the root pays one receive each
+    if (me == 0) {
+      for (int i = 1; i < m; ++i) { Recv(peers[i], tmp.data(), wire); fold(); }
+      for (int i = 1; i < m; ++i) Send(peers[i], words, wire);
+    } else {
+      Send(peers[0], words, wire);
+      Recv(peers[0], words, wire);
+    }
+    return;
+  }
+  // recursive doubling over the largest power of two p <= m; the m - p extra members hand their words to a partner first
+  // and get the result back at the end: ceil(log2 m) + 2 message times instead of 2 (m - 1) at the root
+  int p = 1;
+  while (p * 2 <= m) p *= 2;
+  const int extra = m - p;
+  if (me >= p) {
+    Send(peers[me - p], words, wire);
+    Recv(peers[me - p], words, wire);
+    return;
+  }
+  if (me < extra) { Recv(peers[me + p], tmp.data(), wire); fold(); }
+  for (int mask = 1; mask < p; mask <<= 1) {
+    const int partner = peers[me ^ mask];
+    SendRecv(partner, words, wire, partner, tmp.data(), wire);
+    fold();
+  }
+  if (me < extra) Send(peers[me + p], words, wire);
 }
 
 void Transport::Barrier() {

@@ -64,6 +64,10 @@ class Transport {
   virtual void BcastBytes(std::vector<uint8_t>* buf, int root = 0);
   // In-place: and_words <- AND over ranks, or_words <- OR over ranks.
   virtual void AllreduceBits(uint64_t* and_words, int n_and, uint64_t* or_words, int n_or);
+  // The same reduction among a subset: `peers` are ranks of THIS communicator (identical list on every member), `me` is the
+  // caller's position in it, `words` holds n_and AND-words followed by n - n_and OR-words.  Star through peers[0] for small
+  // groups, recursive doubling (log2 rounds of pairwise exchanges) from HVD_BITS_TREE_MIN_RANKS members on.
+  void AllreduceBitsAmong(const std::vector<int>& peers, int me, uint64_t* words, int n_and, int n);
   virtual void Barrier();
   virtual void AllgatherInts(const int64_t* mine, int n, int64_t* out);
   virtual void Bcast(void* buf, size_t n, int root);

@@ -72,6 +72,16 @@ def test_pipelined_tcp_ring_allreduce(native_built, np_, hosts):
     assert "ALL OK" in out, out[-3000:]
 
 
+@pytest.mark.parametrize("np_,env", [(3, {"HVD_CONTROL_PLANE": "tcp"}), (4, {"HVD_CONTROL_PLANE": "tcp"}), (3, {"HVD_TEST_FAKE_HOSTS": "3"})])
+def test_recursive_doubling_bit_reduction(native_built, np_, env):
+    """HVD_BITS_TREE_MIN_RANKS=2 forces the log-depth exchange of the negotiation bit vectors (default: from 9 members on) for
+    3 members (one extra rank folded into a power-of-two core) and 4 members, over the plain TCP plane and among host leaders."""
+    rc, out = run_parallel("ops_worker.py", np=np_, timeout=400, env=dict(env, HVD_BITS_TREE_MIN_RANKS="2"),
+                           args=["--only", "rank_size,allreduce_sum_avg,allreduce_async_fused,grouped_allreduce,allgather,broadcast,"
+                                 "process_sets,errors,cache_invalidation,barrier_join"])
+    assert "ALL OK" in out, out[-3000:]
+
+
 def test_numpy_frontend_np2(native_built):
     rc, out = run_parallel("numpy_worker.py", np=2, timeout=200)
     assert "NUMPY OK" in out, out[-3000:]
