@@ -60,8 +60,22 @@ elif mode == 'timeline':
     if hvd.rank() == 0:
         # the file must be a complete JSON document WHILE the timeline is still running (closing bracket rewritten in place
         # after every drain of the writer's ring), not only after stop_timeline()
-        time.sleep(0.3)
-        live = json.loads(open(path).read())
+        # (the writer keeps appending cycle markers, and a read that straddles one of its updates sees a torn file — old
+        # tail plus new tail — so the check is what a person reloading the trace viewer does: read again)
+        live, last_error = None, None
+        for _ in range(40):
+            time.sleep(0.05)
+            fd = os.open(path, os.O_RDONLY)
+            try:
+                data = os.read(fd, os.fstat(fd).st_size)         # one read call of the size the file has right now
+            finally:
+                os.close(fd)
+            try:
+                live = json.loads(data)
+                break
+            except ValueError as e:
+                last_error = e
+        assert live is not None, last_error
         assert isinstance(live, list) and len(live) > 10, len(live)
         print('TIMELINE LIVE JSON OK', len(live), flush=True)
     hvd.barrier()
