@@ -54,6 +54,7 @@ if __name__ == '__main__':
     p.add_argument('--spark', action='store_true')
     p.add_argument('--lightning', action='store_true')
     p.add_argument('--store', default=None, help='Store prefix (a directory, hdfs://..., s3://..., dbfs:/...)')
+    p.add_argument('--save-model', default=None, help='directory to save the fitted model to (Spark ML layout) and load it back from')
     a = p.parse_args()
     df = make_frame()
     if a.spark:
@@ -79,4 +80,10 @@ if __name__ == '__main__':
         acc = float((pred == out['label'].values).mean())
         print('history:', fitted.getHistory()[-1])
         print('held-out accuracy: %.3f' % acc)
+        if a.save_model:
+            fitted.write().overwrite().save(a.save_model)            # <dir>/metadata/part-00000, like any Spark ML stage
+            again = type(fitted).load(a.save_model)
+            pred2 = np.array(again.transform(sample)['label__output'].tolist()).argmax(1)
+            assert (pred2 == pred).all() and again.getRunId() == fitted.getRunId()
+            print('saved to and reloaded from', a.save_model)
         print('ESTIMATOR EXAMPLE OK' if acc > 0.8 else 'accuracy too low')

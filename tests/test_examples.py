@@ -45,8 +45,9 @@ def _python(*cmd, timeout=600):
 
 
 def test_estimator_examples(native_built, tmp_path):
-    rc, out = _python('examples/spark_torch_estimator.py', '--num-proc', '2', '--epochs', '2', '--store', str(tmp_path / 's1'))
-    assert rc == 0 and 'ESTIMATOR EXAMPLE OK' in out, out[-3000:]
+    rc, out = _python('examples/spark_torch_estimator.py', '--num-proc', '2', '--epochs', '2', '--store', str(tmp_path / 's1'),
+                      '--save-model', str(tmp_path / 'saved'))
+    assert rc == 0 and 'ESTIMATOR EXAMPLE OK' in out and 'saved to and reloaded from' in out, out[-3000:]
     rc, out = _python('examples/spark_torch_estimator.py', '--num-proc', '2', '--epochs', '2', '--lightning', '--store', str(tmp_path / 's2'))
     assert rc == 0 and 'ESTIMATOR EXAMPLE OK' in out, out[-3000:]
 
