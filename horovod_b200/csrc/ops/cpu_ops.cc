@@ -379,32 +379,52 @@ bool ShmAlltoallv(Transport* t, const char* in, const std::vector<int64_t>& sd, 
   ShmData d;
   if (!t->ShmDataPlane(&d)) return false;
   const int n = t->size(), r = t->rank();
-  const int64_t hdr = (int64_t)(n + 1) * 8;
+  const int64_t hdr = (int64_t)(n + 2) * 8;
   const int64_t S = (int64_t)d.slot_bytes - hdr;
   if (S < 4096) return false;
   const int64_t my_total = sd[n];
-  int64_t pieces = 1;
-  for (int64_t p = 0; p < pieces; ++p) {
-    const int half = (int)(t->ShmNextPiece() & 1);
+  int64_t my_longest_block = 0;
+  for (int i = 0; i < n; ++i) if (i != r) my_longest_block = std::max(my_longest_block, sd[i + 1] - sd[i]);
+  // ---- round 0: header (send displacements, total, longest block) + the whole send buffer when it fits into one slot ----
+  int half = (int)(t->ShmNextPiece() & 1);
+  {
     char* mine = d.slot(r, half);
     int64_t* h = (int64_t*)mine;
     for (int i = 0; i < n; ++i) h[i] = sd[i];
     h[n] = my_total;
-    const int64_t len = std::min(S, my_total - p * S);
-    if (len > 0) memcpy(mine + hdr, in + p * S, (size_t)len);
-    t->Barrier();
-    if (p == 0) {
-      int64_t longest = 0;
-      for (int q = 0; q < n; ++q) longest = std::max(longest, ((const int64_t*)d.slot(q, half))[n]);
-      pieces = std::max<int64_t>(1, (longest + S - 1) / S);
-    }
-    const int64_t piece_lo = p * S, piece_hi = piece_lo + S;
+    h[n + 1] = my_longest_block;
+    if (my_total > 0 && my_total <= S) memcpy(mine + hdr, in, (size_t)my_total);
+  }
+  t->Barrier();
+  int64_t longest_total = 0, longest_block = 0;
+  for (int q = 0; q < n; ++q) {
+    const int64_t* h = (const int64_t*)d.slot(q, half);
+    longest_total = std::max(longest_total, h[n]);
+    longest_block = std::max(longest_block, h[n + 1]);
+  }
+  if (longest_total <= S) {
+    // small exchange: everything is already published, every rank pulls its blocks (one barrier in total)
     for (int q = 0; q < n; ++q) {
       if (q == r || rb[q] == 0) continue;
       const char* theirs = d.slot(q, half);
-      const int64_t want_lo = ((const int64_t*)theirs)[r], want_hi = want_lo + rb[q];
-      const int64_t lo = std::max(want_lo, piece_lo), hi = std::min(want_hi, piece_hi);
-      if (hi > lo) memcpy(out + rd[q] + (lo - want_lo), theirs + hdr + (lo - piece_lo), (size_t)(hi - lo));
+      memcpy(out + rd[q], theirs + hdr + ((const int64_t*)theirs)[r], (size_t)rb[q]);
+    }
+    return true;
+  }
+  // ---- large exchange: n - 1 rounds; in round k every rank publishes (a piece of) its block for rank r + k and pulls from
+  // rank r - k, so each slot has exactly one reader and every rank copies the same amount per piece (publishing the send
+  // buffer front to back instead makes all ranks target rank 0 first, then rank 1, ...: one busy receiver, n - 1 idle) ----
+  const int64_t pieces = (longest_block + S - 1) / S;
+  for (int k = 1; k < n; ++k) {
+    const int to = (r + k) % n, from = (r - k + n) % n;
+    const int64_t slen = sd[to + 1] - sd[to], rlen = rb[from];
+    for (int64_t p = 0; p < pieces; ++p) {
+      half = (int)(t->ShmNextPiece() & 1);
+      const int64_t so = std::min(slen, p * S), sc = std::min(S, slen - so);
+      if (sc > 0) memcpy(d.slot(r, half) + hdr, in + sd[to] + so, (size_t)sc);
+      t->Barrier();
+      const int64_t ro = std::min(rlen, p * S), rc = std::min(S, rlen - ro);
+      if (rc > 0) memcpy(out + rd[from] + ro, d.slot(from, half) + hdr, (size_t)rc);
     }
   }
   return true;
