@@ -659,11 +659,7 @@ void Alltoallv(Transport* t, const void* in, const std::vector<int64_t>& sb, voi
   const char* i8 = (const char*)in; char* o8 = (char*)out;
   if (sb[r]) memcpy(o8 + rd[r], i8 + sd[r], (size_t)sb[r]);
   if (n > 1 && Took(0, ShmAlltoallv(t, i8, sd, o8, rd, rb))) return;
-  if (n > 1) Took(2, true);
-  for (int s = 1; s < n; ++s) {
-    int to = (r + s) % n, from = (r - s + n) % n;
-    t->SendRecv(to, i8 + sd[to], (size_t)sb[to], from, o8 + rd[from], (size_t)rb[from]);
-  }
+  if (n > 1) { Took(2, true); t->AlltoallvBytes(i8, sd.data(), o8, rd.data()); }
 }
 
 void Reducescatter(Transport* t, void* buf, const std::vector<int64_t>& counts, void* out, DataType dtype, ReduceOp op) {

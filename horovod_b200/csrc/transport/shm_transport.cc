@@ -238,6 +238,7 @@ class ShmControlTransport : public Transport {
   void SendRecv(int sp, const void* sb, size_t sn, int rp, void* rb, size_t rn) override {
     base_->SendRecv(sp, sb, sn, rp, rb, rn);
   }
+  void AlltoallvBytes(const char* in, const int64_t* sd, char* out, const int64_t* rd) override { base_->AlltoallvBytes(in, sd, out, rd); }
 
   void AllreduceBits(uint64_t* and_words, int n_and, uint64_t* or_words, int n_or) override {
     const int n = n_and + n_or;
@@ -337,6 +338,7 @@ class HierShmControlTransport : public Transport {
   void SendRecv(int sp, const void* sb, size_t sn, int rp, void* rb, size_t rn) override {
     base_->SendRecv(sp, sb, sn, rp, rb, rn);
   }
+  void AlltoallvBytes(const char* in, const int64_t* sd, char* out, const int64_t* rd) override { base_->AlltoallvBytes(in, sd, out, rd); }
 
   void AllreduceBits(uint64_t* and_words, int n_and, uint64_t* or_words, int n_or) override {
     const int n = n_and + n_or;

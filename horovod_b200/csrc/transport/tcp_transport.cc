@@ -172,6 +172,55 @@ class TcpTransport : public Transport {
       }
     }
   }
+  // All peers at once: every socket with bytes left to send or receive sits in ONE poll set, so a small exchange costs one
+  // message time instead of n - 1 and large blocks stream over all connections concurrently.
+  void AlltoallvBytes(const char* in, const int64_t* sd, char* out, const int64_t* rd) override {
+    static const bool concurrent = [] { const char* e = getenv("HVD_TCP_ALLTOALL_CONCURRENT"); return !e || atoi(e) != 0; }();
+    if (!concurrent) { Transport::AlltoallvBytes(in, sd, out, rd); return; }
+    struct Leg { int fd; const char* s; size_t sn; char* r; size_t rn; };
+    std::vector<Leg> legs;
+    for (int k = 1; k < size_; ++k) {              // rotation order: the first sockets polled differ from rank to rank
+      const int p = (rank_ + k) % size_;
+      Leg l{fd(p), in + sd[p], (size_t)(sd[p + 1] - sd[p]), out + rd[p], (size_t)(rd[p + 1] - rd[p])};
+      if (l.sn || l.rn) legs.push_back(l);
+    }
+    const double timeout_s = RecvTimeoutSeconds();
+    double last_progress = Now();
+    double spin_until = SpinSeconds() > 0 ? last_progress + SpinSeconds() : 0;
+    std::vector<struct pollfd> pf;
+    while (true) {
+      pf.clear();
+      for (auto& l : legs) if (l.sn || l.rn) pf.push_back({l.fd, (short)((l.sn ? POLLOUT : 0) | (l.rn ? POLLIN : 0)), 0});
+      if (pf.empty()) return;
+      int rc = poll(pf.data(), (nfds_t)pf.size(), 0);
+      if (rc == 0 && spin_until > 0 && Now() < spin_until) { __builtin_ia32_pause(); continue; }
+      if (rc == 0) rc = poll(pf.data(), (nfds_t)pf.size(), timeout_s > 0 ? (int)std::min(5000.0, timeout_s * 1000) : 5000);
+      if (rc < 0) { if (errno == EINTR) continue; throw TransportError("poll failed"); }
+      if (rc == 0) {
+        if (timeout_s > 0 && Now() - last_progress > timeout_s)
+          throw TransportError("no progress on an all-to-all exchange for " + std::to_string((int)timeout_s) + " s (HVD_TCP_TIMEOUT_SECONDS): peer frozen or unreachable");
+        continue;
+      }
+      size_t i = 0;
+      for (auto& l : legs) {
+        if (!(l.sn || l.rn)) continue;
+        const short ev = pf[i++].revents;
+        if (l.rn && (ev & (POLLIN | POLLHUP | POLLERR))) {
+          ssize_t k = ::recv(l.fd, l.r, l.rn, MSG_DONTWAIT);
+          if (k == 0) throw TransportError("peer closed connection");
+          if (k < 0) { if (errno != EAGAIN && errno != EWOULDBLOCK && errno != EINTR) throw TransportError(std::string("recv failed: ") + strerror(errno)); }
+          else { l.r += k; l.rn -= (size_t)k; }
+        }
+        if (l.sn && (ev & (POLLOUT | POLLHUP | POLLERR))) {
+          ssize_t k = ::send(l.fd, l.s, l.sn, MSG_DONTWAIT | MSG_NOSIGNAL);
+          if (k < 0) { if (errno != EAGAIN && errno != EWOULDBLOCK && errno != EINTR) throw TransportError(std::string("send failed: ") + strerror(errno)); }
+          else { l.s += k; l.sn -= (size_t)k; }
+        }
+      }
+      last_progress = Now();
+      if (spin_until > 0) spin_until = last_progress + SpinSeconds();
+    }
+  }
   std::vector<int> fds_;
   bool single_host_ = true;
   std::vector<int> host_ids_;

@@ -54,6 +54,14 @@ void Transport::Bcast(void* buf, size_t n, int root) {
   }
 }
 
+void Transport::AlltoallvBytes(const char* in, const int64_t* sd, char* out, const int64_t* rd) {
+  const int n = size(), r = rank();
+  for (int k = 1; k < n; ++k) {
+    const int to = (r + k) % n, from = (r - k + n) % n;
+    SendRecv(to, in + sd[to], (size_t)(sd[to + 1] - sd[to]), from, out + rd[from], (size_t)(rd[from + 1] - rd[from]));
+  }
+}
+
 void Transport::AllreduceBits(uint64_t* and_words, int n_and, uint64_t* or_words, int n_or) {
   if (size() == 1) return;
   const int n = n_and + n_or;

@@ -59,6 +59,11 @@ class Transport {
   // Full-duplex exchange that cannot deadlock when both sides send first.
   virtual void SendRecv(int send_peer, const void* sbuf, size_t sn, int recv_peer, void* rbuf, size_t rn) = 0;
 
+  // Personalised exchange with every other rank: byte range [sd[p], sd[p+1]) of `in` goes to rank p, [rd[p], rd[p+1]) of `out`
+  // comes from rank p (the caller copies its own block).  Default: n - 1 rounds of SendRecv (to r + k, from r - k); the TCP
+  // mesh progresses all peers at once.
+  virtual void AlltoallvBytes(const char* in, const int64_t* sd, char* out, const int64_t* rd);
+
   // ---- collectives (default: star through `root`) ----
   virtual void GatherBytes(const std::vector<uint8_t>& mine, std::vector<std::vector<uint8_t>>* all, int root = 0);
   virtual void BcastBytes(std::vector<uint8_t>* buf, int root = 0);
