@@ -266,6 +266,37 @@ static int64_t RingChunkElems(size_t es) {
   return bytes / (int64_t)es;
 }
 
+// One reduce-scatter step of a ring: send `slen` elements from `send`, receive `rlen` elements from `prev` and fold them into
+// `acc`.  Big steps move in chunks through two staging buffers: the reducer thread folds chunk k while this thread already
+// exchanges chunk k + 1, so the wire and the adds overlap.  `tmp` is scratch owned by the caller (sized on demand).
+// `longest` is the longest segment of the WHOLE ring (known to every rank): it alone decides whether and into how many pieces
+// the steps are cut, so both ends of every connection agree on the message boundaries (message-based transports need that).
+static void RingReduceStep(Transport* t, int next, int prev, const char* send, int64_t slen, char* acc, int64_t rlen, int64_t longest,
+                           DataType dtype, ReduceOp op, std::vector<char>* tmp) {
+  const size_t es = DataTypeSize(dtype);
+  const int64_t chunk = RingChunkElems(es);
+  if (chunk <= 0 || longest < 2 * chunk) {
+    if (tmp->size() < (size_t)rlen * es) tmp->resize((size_t)rlen * es);
+    t->SendRecv(next, send, (size_t)slen * es, prev, tmp->data(), (size_t)rlen * es);
+    ReduceInto(acc, tmp->data(), rlen, dtype, op);
+    return;
+  }
+  if (tmp->size() < (size_t)(2 * chunk) * es) tmp->resize((size_t)(2 * chunk) * es);
+  RingReducer& red = RingReducer::Get();
+  const int64_t pieces = (longest + chunk - 1) / chunk;
+  uint64_t ticket[2] = {0, 0};
+  for (int64_t k = 0; k < pieces; ++k) {
+    const int64_t so = std::min(slen, k * chunk), sc = std::min(chunk, slen - so);
+    const int64_t ro = std::min(rlen, k * chunk), rc = std::min(chunk, rlen - ro);
+    char* st = tmp->data() + (size_t)(k & 1) * (size_t)chunk * es;
+    red.Wait(ticket[k & 1]);                       // the reduce that read this staging half two pieces ago
+    t->SendRecv(next, send + so * es, (size_t)sc * es, prev, st, (size_t)rc * es);
+    ticket[k & 1] = rc > 0 ? red.Submit(acc + ro * es, st, rc, dtype, op) : 0;
+  }
+  red.Wait(ticket[0]);                             // the next ring step sends what this one reduced
+  red.Wait(ticket[1]);
+}
+
 static std::atomic<unsigned long long> g_path_count[3];
 unsigned long long HostPathCount(int which) { return which >= 0 && which < 3 ? g_path_count[which].load(std::memory_order_relaxed) : 0; }
 static inline bool Took(int path, bool taken) { if (taken) g_path_count[path].fetch_add(1, std::memory_order_relaxed); return taken; }
@@ -565,35 +596,10 @@ void RingAllreduce(Transport* t, char* b, int64_t count, DataType dtype, ReduceO
   int64_t maxseg = 0;
   for (int i = 0; i < n; ++i) maxseg = std::max(maxseg, off[i + 1] - off[i]);
   const int next = (r + 1) % n, prev = (r - 1 + n) % n;
-  const int64_t chunk = RingChunkElems(es);
-  if (chunk > 0 && maxseg >= 2 * chunk) {
-    // big segments: every step moves its segment in chunks; the reducer thread folds chunk k into the buffer while this
-    // thread already exchanges chunk k+1 (two staging buffers), so the wire and the adds overlap
-    RingReducer& red = RingReducer::Get();
-    std::vector<char> stage[2] = {std::vector<char>((size_t)chunk * es), std::vector<char>((size_t)chunk * es)};
-    for (int s = 0; s < n - 1; ++s) {
-      const int si = (r - s + n) % n, ri = (r - s - 1 + n) % n;
-      const int64_t slen = off[si + 1] - off[si], rlen = off[ri + 1] - off[ri];
-      const int64_t pieces = (std::max(slen, rlen) + chunk - 1) / chunk;
-      uint64_t ticket[2] = {0, 0};
-      for (int64_t k = 0; k < pieces; ++k) {
-        const int64_t so = std::min(slen, k * chunk), sc = std::min(chunk, slen - so);
-        const int64_t ro = std::min(rlen, k * chunk), rc = std::min(chunk, rlen - ro);
-        char* st = stage[k & 1].data();
-        red.Wait(ticket[k & 1]);                       // the reduce that read this staging buffer two pieces ago
-        t->SendRecv(next, b + (off[si] + so) * es, (size_t)sc * es, prev, st, (size_t)rc * es);
-        ticket[k & 1] = rc > 0 ? red.Submit(b + (off[ri] + ro) * es, st, rc, dtype, op) : 0;
-      }
-      red.Wait(ticket[0]);                             // the next step sends the segment this step reduced
-      red.Wait(ticket[1]);
-    }
-  } else {
-    std::vector<char> tmp((size_t)maxseg * es);
-    for (int s = 0; s < n - 1; ++s) {
-      int si = (r - s + n) % n, ri = (r - s - 1 + n) % n;
-      t->SendRecv(next, b + off[si] * es, (size_t)(off[si + 1] - off[si]) * es, prev, tmp.data(), (size_t)(off[ri + 1] - off[ri]) * es);
-      ReduceInto(b + off[ri] * es, tmp.data(), off[ri + 1] - off[ri], dtype, op);
-    }
+  std::vector<char> tmp;
+  for (int s = 0; s < n - 1; ++s) {
+    const int si = (r - s + n) % n, ri = (r - s - 1 + n) % n;
+    RingReduceStep(t, next, prev, b + off[si] * es, off[si + 1] - off[si], b + off[ri] * es, off[ri + 1] - off[ri], maxseg, dtype, op, &tmp);
   }
   for (int s = 0; s < n - 1; ++s) {
     int si = (r + 1 - s + n) % n, ri = (r - s + n) % n;
@@ -671,13 +677,12 @@ void Reducescatter(Transport* t, void* buf, const std::vector<int64_t>& counts, 
   if (n > 1 && Took(0, ShmReducescatter(t, b, off, (char*)out, dtype, op))) return;
   if (n > 1) Took(2, true);
   if (n > 1) {
-    int64_t maxseg = *std::max_element(counts.begin(), counts.end());
-    std::vector<char> tmp((size_t)maxseg * es);
+    std::vector<char> tmp;
+    const int64_t maxseg = *std::max_element(counts.begin(), counts.end());
     const int next = (r + 1) % n, prev = (r - 1 + n) % n;
     for (int s = 0; s < n - 1; ++s) {
       int si = (r - s - 1 + 2 * n) % n, ri = (r - s - 2 + 2 * n) % n;
-      t->SendRecv(next, b + off[si] * es, (size_t)counts[si] * es, prev, tmp.data(), (size_t)counts[ri] * es);
-      ReduceInto(b + off[ri] * es, tmp.data(), counts[ri], dtype, op);
+      RingReduceStep(t, next, prev, b + off[si] * es, counts[si], b + off[ri] * es, counts[ri], maxseg, dtype, op, &tmp);
     }
   }
   if (counts[r]) memcpy(out, b + off[r] * es, (size_t)counts[r] * es);
