@@ -75,7 +75,7 @@ class ElasticRayExecutor:
         self.rendezvous = RendezvousServer(self.settings.verbose)
         self.driver = ElasticDriver(self.rendezvous, self.settings.discovery, self.settings.min_num_proc, self.settings.max_num_proc,
                                     timeout=self.settings.elastic_timeout, reset_limit=self.settings.reset_limit,
-                                    verbose=self.settings.verbose)
+                                    cooldown_range=getattr(self.settings, 'cooldown_range', None), verbose=self.settings.verbose)
         port = self.rendezvous.start_server()
         create_rendezvous_handler(self.driver).install(self.rendezvous)
         self.driver.wait_for_available_slots(self.settings.min_num_proc)
@@ -109,6 +109,7 @@ class ElasticRayExecutor:
         """`callbacks`: every dict a worker hands to `horovod_b200.ray.ray_logger.log` is passed to each of them on the
         driver while the job runs (reference elastic_v2.py `_process_calls`)."""
         results_q = queue.Queue()
+        errors = []                              # (hostname, rank, exception) of every worker that failed, in order
         stop_drain = threading.Event()
         if callbacks:
             import functools
@@ -144,6 +145,7 @@ class ElasticRayExecutor:
                     box['code'] = 0
                 except Exception as e:  # a dead actor is a failed worker: the driver blacklists / re-plans
                     box['code'], box['error'] = 1, e
+                    errors.append((slot_info.hostname, slot_info.rank, e))
                 done.set()
             threading.Thread(target=body, daemon=True).start()
             while not done.wait(0.1):
@@ -162,12 +164,19 @@ class ElasticRayExecutor:
         if callbacks:
             stop_drain.set()
             drainer.join(timeout=10)
+        def first_error():
+            if not errors:
+                return ''
+            host, rank, e = errors[0]
+            return '\nfirst worker failure (rank %s on %s): %s' % (rank, host, e)
         if res.error_message:
-            raise RuntimeError(res.error_message)
+            raise RuntimeError(res.error_message + first_error())
         out = {}
         while not results_q.empty():
             r, v = results_q.get()
             out[r] = v
+        if not out:
+            raise RuntimeError('the elastic job ended without a single successful worker' + first_error())
         return [out[r] for r in sorted(out)]
 
 

@@ -357,3 +357,160 @@ class ConnectBackBackend(ActorBackend):
             self.listener.close()
         except Exception:
             pass
+
+
+# ---- elastic flavour: tasks come and go -----------------------------------------------------------------------------------------
+class ConnectBackPool:
+    """Tasks launched by someone else's scheduler (Spark) dial back whenever they start — the first attempt of a task, or the
+    attempt Spark schedules after a failure — and are handed to the elastic driver as slots: discovery reports how many live
+    tasks sit on which node, "spawning a worker" means taking an idle task of the requested node.
+
+    `launch(n, task_main)` starts n tasks like ConnectBackBackend's launcher; unlike there, connections are accepted for the
+    whole life of the pool."""
+
+    class Task:
+        def __init__(self, index, conn, node):
+            self.index, self.conn, self.node = index, conn, node
+            self.busy, self.alive = False, True
+
+    def __init__(self, launch, num_tasks, host=None, timeout=120):
+        import functools
+        import secrets
+        import threading
+        from multiprocessing.connection import Listener
+        self.authkey = secrets.token_bytes(16)
+        self.listener = Listener((host or _routable_ip(), 0), authkey=self.authkey)
+        self.address = self.listener.address
+        self.timeout = timeout
+        self._lock = threading.Condition()
+        self._tasks = []
+        self._closed = False
+        task_main = functools.partial(_task_entry, address=tuple(self.address), authkey=self.authkey)
+        self._acceptor = threading.Thread(target=self._accept_loop, name='hvd-pool-accept', daemon=True)
+        self._acceptor.start()
+        self._launch_handle = launch(num_tasks, task_main)
+
+    # -- connections ----------------------------------------------------------------------------------------------------------
+    def _accept_loop(self):
+        import cloudpickle
+        while not self._closed:
+            try:
+                conn = self.listener.accept()
+                tag, idx = conn.recv()
+                assert tag == 'hello'
+                conn.send(cloudpickle.dumps(('node_id', (), {})))
+                if not conn.poll(self.timeout):
+                    conn.close()
+                    continue
+                status, node = conn.recv()
+                if status != 'ok':
+                    conn.close()
+                    continue
+            except Exception:  # noqa: BLE001 - listener closed, or a task that died while saying hello
+                if self._closed:
+                    return
+                continue
+            with self._lock:
+                self._tasks.append(ConnectBackPool.Task(idx, conn, node))
+                self._lock.notify_all()
+
+    def _sweep(self):
+        """Marks idle tasks whose connection is gone (callers hold the lock)."""
+        for t in self._tasks:
+            if t.alive and not t.busy:
+                try:
+                    if t.conn.poll(0):          # an idle task never sends: readable means EOF (or garbage)
+                        t.conn.recv()
+                        t.alive = False
+                except (EOFError, OSError):
+                    t.alive = False
+
+    def wait_for(self, count, timeout):
+        import time
+        deadline = time.monotonic() + timeout
+        with self._lock:
+            while True:
+                self._sweep()
+                alive = sum(1 for t in self._tasks if t.alive)
+                if alive >= count:
+                    return alive
+                left = deadline - time.monotonic()
+                if left <= 0:
+                    raise TimeoutError('only %d of %d tasks connected back within %s s' % (alive, count, timeout))
+                self._lock.wait(min(left, 0.2))
+
+    def hosts_and_slots(self):
+        with self._lock:
+            self._sweep()
+            out = OrderedDict()
+            for t in self._tasks:
+                if t.alive:
+                    out[t.node] = out.get(t.node, 0) + 1
+            return out
+
+    # -- workers ----------------------------------------------------------------------------------------------------------------
+    def actor_factory(self, hostname, env):
+        """(hostname, env) -> object with execute(fn) / kill(): an idle task of that node, with `env` applied."""
+        import time
+        deadline = time.monotonic() + self.timeout
+        with self._lock:
+            while True:
+                self._sweep()
+                task = next((t for t in self._tasks if t.alive and not t.busy and t.node == hostname), None)
+                if task is not None:
+                    task.busy = True
+                    break
+                left = deadline - time.monotonic()
+                if left <= 0:
+                    raise RuntimeError('no idle task on %s' % hostname)
+                self._lock.wait(min(left, 0.2))
+        pool = self
+
+        class Worker:
+            def _call(self, method, *args):
+                import cloudpickle
+                try:
+                    task.conn.send(cloudpickle.dumps((method, args, {})))
+                    while not task.conn.poll(0.5):
+                        if not task.alive:
+                            raise RuntimeError('task %s on %s was stopped' % (task.index, task.node))
+                    status, value = task.conn.recv()
+                except (EOFError, OSError) as e:
+                    task.alive = False
+                    raise RuntimeError('task %s on %s died: %s' % (task.index, task.node, e or type(e).__name__))
+                if status != 'ok':
+                    raise RuntimeError('worker raised:\n' + str(value))
+                return value
+
+            def execute(self, fn):
+                try:
+                    self._call('update_env', env)
+                    return self._call('execute', fn)
+                finally:
+                    with pool._lock:
+                        task.busy = False
+                        pool._lock.notify_all()
+
+            def kill(self):
+                task.alive = False
+                try:
+                    task.conn.close()            # the task's serve loop ends on EOF: the scheduler sees the task finish
+                except Exception:  # noqa: BLE001
+                    pass
+        return Worker()
+
+    def shutdown(self):
+        self._closed = True
+        try:
+            self.listener.close()
+        except Exception:  # noqa: BLE001
+            pass
+        with self._lock:
+            for t in self._tasks:
+                try:
+                    if t.alive:
+                        t.conn.send(None)
+                    t.conn.close()
+                except Exception:  # noqa: BLE001
+                    pass
+                t.alive = False

@@ -13,7 +13,7 @@ import threading
 from horovod_b200.runner.cluster_job import ClusterJob, ConnectBackBackend
 
 
-def _spark_launch(spark_context, start_timeout):
+def _spark_launch(spark_context, start_timeout, barrier=True):
     def launch(n, task_main):
         def mapper(index, _it):
             yield task_main(index)
@@ -23,7 +23,7 @@ def _spark_launch(spark_context, start_timeout):
         def job():
             try:
                 rdd = spark_context.parallelize(range(n), n)
-                rdd = rdd.barrier() if hasattr(rdd, 'barrier') else rdd  # all-or-nothing scheduling of the n tasks
+                rdd = rdd.barrier() if barrier and hasattr(rdd, 'barrier') else rdd  # all-or-nothing scheduling of the n tasks
                 result['out'] = rdd.mapPartitionsWithIndex(mapper).collect()
             except Exception as e:
                 result['err'] = e
@@ -72,24 +72,61 @@ def run(fn, args=(), kwargs=None, num_proc=None, start_timeout=None, use_mpi=Non
 
 
 def run_elastic(fn, args=(), kwargs=None, num_proc=None, min_num_proc=None, max_num_proc=None, start_timeout=None,
-                elastic_timeout=None, reset_limit=None, env=None, stdout=None, stderr=None, verbose=1, nics=None,
+                elastic_timeout=None, reset_limit=None, cooldown_range=None, env=None, stdout=None, stderr=None, verbose=1, nics=None,
                 prefix_output_with_timestamp=False, spark_context=None, _launch=None):
-    """Elastic variant: the job starts with `num_proc` tasks; `fn` is expected to be wrapped with `hvd.elastic.run`.
-    Spark re-schedules failed barrier tasks itself, so membership changes surface as a new barrier stage attempt: the
-    driver re-runs the job with the workers that reconnected (between min_num_proc and max_num_proc)."""
-    if spark_context is not None and hasattr(spark_context, 'getConf'):
-        import warnings
-        from horovod_b200.spark.conf import check_elastic_conf
-        check_elastic_conf(spark_context.getConf().get, warn=warnings.warn)
+    """Elastic variant (reference spark/runner.py `run_elastic` :312-420): `fn` is an `@hvd.elastic.run` training function.
+
+    `max_num_proc` (default: num_proc) Spark tasks dial back to the driver and become the SLOTS of an elastic job
+    (`cluster_job.ConnectBackPool`): discovery counts the live tasks per executor host, the elastic driver
+    (`runner.elastic.driver.ElasticDriver`) plans ranks over them, and "spawning a worker" hands the function to an idle task
+    of the requested host.  A task that dies takes its slot with it — the survivors roll back to their last commit and carry on
+    as long as `min_num_proc` remain; the attempt Spark schedules for the failed task (`spark.task.maxFailures`, see
+    `spark/conf.py`) dials back as a fresh slot and is picked up at the next reset.  Returns the results of the final round in
+    rank order."""
+    import functools
+    import warnings
+    from horovod_b200.ray.elastic import ElasticRayExecutor as _ElasticExecutor     # scheduler-independent despite the name
+    from horovod_b200.runner.cluster_job import ConnectBackPool
+    from horovod_b200.runner.elastic.discovery import HostDiscovery
+    kwargs = kwargs or {}
+    start_timeout = start_timeout or int(os.environ.get('HOROVOD_SPARK_START_TIMEOUT', '600'))
+    if _launch is None:
+        if spark_context is None:
+            try:
+                import pyspark
+            except ImportError as e:
+                raise ImportError('horovod_b200.spark.run_elastic needs PySpark (not installed in this environment)') from e
+            spark_context = pyspark.SparkContext._active_spark_context
+            if spark_context is None:
+                raise Exception('Could not find an active SparkContext, are you running in a PySpark session?')
+        if hasattr(spark_context, 'getConf'):
+            from horovod_b200.spark.conf import check_elastic_conf
+            check_elastic_conf(spark_context.getConf().get, warn=warnings.warn)
+        if num_proc is None:
+            num_proc = _default_num_proc(spark_context)
+        _launch = _spark_launch(spark_context, start_timeout, barrier=False)   # all-or-nothing scheduling is what elastic avoids
+    elif num_proc is None:
+        raise ValueError('num_proc is required with a custom launcher')
     min_np = min_num_proc or num_proc
-    attempts = (reset_limit or 3) + 1
-    last = None
-    for _ in range(attempts):
-        try:
-            return run(fn, args, kwargs, num_proc=num_proc, start_timeout=start_timeout, env=dict(env or {}, HOROVOD_ELASTIC='0'),
-                       verbose=verbose, nics=nics, spark_context=spark_context, _launch=_launch)
-        except (RuntimeError, TimeoutError) as e:  # a task died: retry with the same width while >= min_np is available
-            last = e
-            if num_proc is not None and min_np is not None and num_proc > min_np:
-                num_proc -= 1
-    raise last
+    max_np = max_num_proc or num_proc
+    if not min_np <= num_proc <= max_np:
+        raise ValueError('need min_num_proc <= num_proc <= max_num_proc, got %s <= %s <= %s' % (min_np, num_proc, max_np))
+    pool = ConnectBackPool(_launch, max_np, timeout=start_timeout)
+
+    class _PoolDiscovery(HostDiscovery):
+        def find_available_hosts_and_slots(self):
+            return pool.hosts_and_slots()
+
+    try:
+        pool.wait_for(min_np, start_timeout)
+        extra = {'cooldown_range': cooldown_range} if cooldown_range else {}
+        settings = _ElasticExecutor.create_settings(min_num_proc=min_np, max_num_proc=max_np, reset_limit=reset_limit,
+                                                    elastic_timeout=elastic_timeout or 600, timeout_s=start_timeout, nics=nics, **extra)
+        settings.discovery = _PoolDiscovery()
+        settings.num_proc = num_proc
+        settings.verbose = 2 if verbose and verbose > 1 else 0
+        executor = _ElasticExecutor(settings, env_vars=dict(env or {}), override_discovery=False, actor_factory=pool.actor_factory)
+        executor.start()
+        return executor.run(functools.partial(fn, *tuple(args), **dict(kwargs)))
+    finally:
+        pool.shutdown()

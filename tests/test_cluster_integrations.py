@@ -2,6 +2,7 @@
 nor PySpark is installed here).  Reference coverage model: test/single/test_ray.py (RayExecutor: rank table, env,
 run/execute/execute_single/run_remote, train end-to-end) and test/integration/test_spark.py (`horovod.spark.run`)."""
 import os
+import time
 
 import pytest
 
@@ -188,32 +189,101 @@ def test_unified_ray_executor_elastic_mode(native_built):
     assert sorted(r[0] for r in res) == [0, 1] and all(r[1] == 2 and r[2] == [3.0, 3.0] for r in res), res
 
 
-def _fails_until_two(marker_dir):
-    """Raises on every rank while the job is wider than 2 ranks (a stand-in for 'one executor keeps dying')."""
-    import os
+def _mp_launch_on_nodes(nodes, respawn_marker=None):
+    """Launcher that stands in for a non-barrier Spark stage: task i runs on fake node nodes[i]; with `respawn_marker`, a task
+    that exits before the marker file exists is started again once (Spark's task retry)."""
+    def launch(n, task_main):
+        import multiprocessing as mp
+        import threading
+        ctx = mp.get_context('spawn')
+
+        def start(i):
+            env = {'OMP_NUM_THREADS': '1', 'HOROVOD_LOG_LEVEL': 'warning', 'HVD_NODE_ID_OVERRIDE': nodes[i]}
+            p = ctx.Process(target=task_main, args=(i, env), daemon=True)
+            p.start()
+            return p
+        procs = [start(i) for i in range(n)]
+        if respawn_marker is not None:
+            def watch():
+                retried = set()
+                while not os.path.exists(respawn_marker):
+                    for i, p in enumerate(procs):
+                        if not p.is_alive() and p.exitcode not in (0, None) and i not in retried:
+                            retried.add(i)
+                            procs.append(start(i))
+                    time.sleep(0.2)
+            threading.Thread(target=watch, daemon=True).start()
+        return procs
+    return launch
+
+
+def _elastic_train(marker_dir, batches=12, die_on_node=None, die_at=4, step_sleep=0.0):
+    """An ordinary elastic training function: commits every 2 batches; the task on `die_on_node` kills its process at batch
+    `die_at` of its first life."""
     import torch
     import horovod_b200.torch as hvd
     hvd.init()
-    try:
-        if hvd.size() > 2:
-            open(os.path.join(marker_dir, 'attempt.%d.%d' % (hvd.size(), hvd.rank())), 'w').close()
-            raise RuntimeError('too wide: %d' % hvd.size())
-        out = hvd.allreduce(torch.ones(2), op=hvd.Sum, name='narrow').tolist()
-        return hvd.rank(), hvd.size(), out
-    finally:
-        hvd.shutdown()
+    w = torch.zeros(1)
+    state = hvd.elastic.TorchState(batch=0, total=0.0, sizes=[])
+    node = os.environ.get('HVD_NODE_ID_OVERRIDE')
+
+    @hvd.elastic.run
+    def train(state):
+        while state.batch < batches:
+            if node == die_on_node and state.batch == die_at and not os.path.exists(os.path.join(marker_dir, 'died')):
+                open(os.path.join(marker_dir, 'died'), 'w').close()
+                os._exit(17)
+            s = hvd.allreduce(torch.ones(1), op=hvd.Sum, name='elastic.sum').item()
+            time.sleep(step_sleep)
+            state.total += s
+            state.sizes.append(int(s))
+            state.batch += 1
+            if state.batch % 2 == 0:
+                state.commit()
+        return state.batch, state.total, list(state.sizes)
+    out = train(state)
+    res = (hvd.rank(), hvd.size(), node) + tuple(out)
+    hvd.shutdown()
+    return res
 
 
-def test_spark_run_elastic_retries_with_fewer_tasks(native_built, tmp_path):
-    """run_elastic: a failed attempt is retried one task narrower until it fits (num_proc 3 -> 2 here), never below min_num_proc."""
+def test_spark_run_elastic_survives_a_dying_task(native_built, tmp_path):
+    """run_elastic over a pool of connect-back tasks (what Spark tasks are): 3 tasks on 3 'hosts', the one on host c kills its
+    process mid-training; its host is dropped, the two survivors roll back to their last commit and finish as a 2-rank job."""
     import horovod_b200.spark as hvd_spark
-    res = hvd_spark.run_elastic(_fails_until_two, args=(str(tmp_path),), num_proc=3, min_num_proc=2, reset_limit=2, _launch=_mp_launch,
-                                start_timeout=120, verbose=0)
-    assert sorted(r[0] for r in res) == [0, 1] and all(r[1] == 2 and r[2] == [2.0, 2.0] for r in res), res
-    assert sorted(os.listdir(tmp_path)) == ['attempt.3.0', 'attempt.3.1', 'attempt.3.2']       # exactly one wide attempt
-    with pytest.raises(RuntimeError, match='too wide'):                                          # may not shrink below min_num_proc
-        hvd_spark.run_elastic(_fails_until_two, args=(str(tmp_path),), num_proc=3, min_num_proc=3, reset_limit=1, _launch=_mp_launch,
-                              start_timeout=120, verbose=0)
+    res = hvd_spark.run_elastic(_elastic_train, args=(str(tmp_path),), kwargs={'die_on_node': 'c'}, num_proc=3, min_num_proc=2,
+                                _launch=_mp_launch_on_nodes(['a', 'b', 'c']), start_timeout=120, elastic_timeout=60, verbose=0)
+    assert len(res) == 2 and sorted(r[0] for r in res) == [0, 1] and all(r[1] == 2 for r in res), res
+    assert sorted(r[2] for r in res) == ['a', 'b'] and os.path.exists(tmp_path / 'died')
+    for _, _, _, batch, total, sizes in res:
+        assert batch == 12 and sizes[:4] == [3, 3, 3, 3] and sizes[-1] == 2 and set(sizes) == {2, 3}, sizes
+        assert total == float(sum(sizes))
+    assert res[0][3:] == res[1][3:]                                      # both survivors replayed the same history
+
+
+def test_spark_run_elastic_picks_up_the_retried_task(native_built, tmp_path):
+    """The attempt the scheduler starts for the failed task dials back as a fresh slot on another host and joins at the next
+    reset: the job ends with 3 ranks again."""
+    import horovod_b200.spark as hvd_spark
+    marker = str(tmp_path / 'done')
+    try:
+        res = hvd_spark.run_elastic(_elastic_train, args=(str(tmp_path),), kwargs={'die_on_node': 'c', 'batches': 400, 'die_at': 4, 'step_sleep': 0.03},
+                                    num_proc=3, min_num_proc=2, max_num_proc=3, cooldown_range=[1, 2],
+                                    _launch=_mp_launch_on_nodes(['a', 'b', 'c'], respawn_marker=marker), start_timeout=120,
+                                    elastic_timeout=60, verbose=0)
+    finally:
+        open(marker, 'w').close()
+    assert len(res) == 3 and sorted(r[0] for r in res) == [0, 1, 2] and all(r[1] == 3 for r in res), res
+    sizes = res[0][5]
+    assert sizes[:4] == [3, 3, 3, 3] and 2 in sizes and sizes[-1] == 3, (sizes[:10], sizes[-5:])
+
+
+def test_spark_run_elastic_argument_checks():
+    import horovod_b200.spark as hvd_spark
+    with pytest.raises(ValueError, match='num_proc is required'):
+        hvd_spark.run_elastic(lambda: 0, _launch=lambda n, f: [])
+    with pytest.raises(ValueError, match='min_num_proc <= num_proc <= max_num_proc'):
+        hvd_spark.run_elastic(lambda: 0, num_proc=2, min_num_proc=3, _launch=lambda n, f: [])
 
 
 def _logging_worker(scale):
