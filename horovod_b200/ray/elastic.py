@@ -154,7 +154,9 @@ class ElasticRayExecutor:
                         actor.kill()
                     return 1, 0
             if box['code'] == 0:
-                results_q.put((slot_info.rank, box['value']))
+                # the rank of a worker changes with every reset: key the result by the slot (host, local rank) it ran in and
+                # order by the driver's FINAL rank table below
+                results_q.put(((slot_info.hostname, slot_info.local_rank), slot_info.rank, box['value']))
             return box['code'], 0
 
         self.driver.start(self.settings.num_proc or self.settings.min_num_proc, spawn)
@@ -173,11 +175,15 @@ class ElasticRayExecutor:
             raise RuntimeError(res.error_message + first_error())
         out = {}
         while not results_q.empty():
-            r, v = results_q.get()
-            out[r] = v
+            (host, local_rank), spawn_rank, v = results_q.get()
+            try:
+                final = self.driver.get_slot_info(host, local_rank).rank if self.driver.has_rank_assignment(host, local_rank) else None
+            except Exception:  # noqa: BLE001 - a slot that left the final layout
+                final = None
+            out[(0, final) if final is not None else (1, spawn_rank, host, local_rank)] = v
         if not out:
             raise RuntimeError('the elastic job ended without a single successful worker' + first_error())
-        return [out[r] for r in sorted(out)]
+        return [out[k] for k in sorted(out)]
 
 
 def _driver_ip():
