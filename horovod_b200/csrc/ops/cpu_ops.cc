@@ -564,9 +564,8 @@ bool HierBroadcast(Transport* t, char* buf, int64_t bytes, int root) {
 // ---------------------------------------------------------------------------
 
 void Allreduce(Transport* t, void* buf, int64_t count, DataType dtype, ReduceOp op) {
-  const int n = t->size(), r = t->rank();
+  const int n = t->size();
   if (n == 1 || count == 0) return;
-  const size_t es = DataTypeSize(dtype);
   char* b = (char*)buf;
   if (Took(0, ShmAllreduce(t, b, count, dtype, op))) return;
   if (Took(1, HierAllreduce(t, b, count, dtype, op))) return;
@@ -631,7 +630,7 @@ void RingAllgatherv(Transport* t, char* o, const std::vector<int64_t>& bytes, co
 }
 
 void Broadcast(Transport* t, void* buf, int64_t bytes, int root) {
-  const int n = t->size(), r = t->rank();
+  const int n = t->size();
   if (n == 1 || bytes == 0) return;
   if (Took(0, ShmBroadcast(t, (char*)buf, bytes, root))) return;
   if (Took(1, HierBroadcast(t, (char*)buf, bytes, root))) return;

@@ -377,7 +377,9 @@ def gpu_index_for(local_rank, devices=None, environ=None):
     """CUDA device index of a training process: the GPU Spark assigned to the task when there is one, else `local_rank`.
     HOROVOD_SPARK_USE_LOCAL_RANK_GPU_INDEX=1 forces `local_rank` (clusters whose GPU addresses are not CUDA ordinals)."""
     environ = os.environ if environ is None else environ
-    devices = get_available_devices() if devices is None else devices
+    if devices is None:
+        from horovod_b200.spark.task import get_available_devices as task_devices      # explicitly recorded resources win
+        devices = task_devices()
     if devices and environ.get('HOROVOD_SPARK_USE_LOCAL_RANK_GPU_INDEX', '0') == '0':
         return int(devices[0])
     return local_rank

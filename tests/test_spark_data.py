@@ -135,3 +135,19 @@ def test_gpu_index_for_spark_task_resources():
     assert util.gpu_index_for(3, devices=[], environ={}) == 3
     assert util.gpu_index_for(3, devices=['5', '6'], environ={}) == 5
     assert util.gpu_index_for(3, devices=['5'], environ={'HOROVOD_SPARK_USE_LOCAL_RANK_GPU_INDEX': '1'}) == 3
+
+
+def test_task_info_resources():
+    from horovod_b200.spark import task
+    assert task.get_available_devices() == []
+
+    class Res:
+        addresses = ['3', '4']
+    try:
+        task.set_resources({'gpu': Res()})
+        assert task.get_available_devices() == ['3', '4'] and util.gpu_index_for(0, environ={}) == 3
+        task.set_resources({'gpu': ['7']})
+        assert task.get_available_devices() == ['7'] and util.gpu_index_for(1, environ={'HOROVOD_SPARK_USE_LOCAL_RANK_GPU_INDEX': '1'}) == 1
+    finally:
+        task.set_resources({})
+    assert util.gpu_index_for(2, environ={}) == 2
