@@ -1,5 +1,6 @@
 """`import horovod_b200.torch as hvd` — PyTorch front end (API parity: horovod/torch/__init__.py)."""
 from horovod_b200.common.exceptions import HorovodInternalError, HostsUpdatedInterrupt  # noqa: F401
+from horovod_b200.common.util import check_extension  # noqa: F401  (the native library is loaded, and reported missing, on first use)
 from horovod_b200.common.process_sets import (ProcessSet, global_process_set, add_process_set,  # noqa: F401
                                               remove_process_set)
 from horovod_b200.torch.compression import Compression  # noqa: F401
