@@ -171,6 +171,17 @@ def _allreduce_async(tensor, output, name, op, prescale_factor, postscale_factor
     return handle
 
 
+def _differentiate(*tensors):
+    """False when no input can receive a gradient: the synchronous collectives then skip the autograd.Function wrapper (its
+    `apply` costs more host time than the whole engine path of a small blocking collective)."""
+    if not torch.is_grad_enabled():
+        return False
+    for t in tensors:
+        if t.requires_grad:
+            return True
+    return False
+
+
 def allreduce_async(tensor, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0,
                     process_set=global_process_set):
     """Asynchronous averaging/summing allreduce; returns a handle for poll()/synchronize(). The input is not modified."""
@@ -204,7 +215,10 @@ def allreduce(tensor, average=None, name=None, compression=None, op=None, presca
     from horovod_b200.torch.compression import Compression
     compression = compression or Compression.none
     tensor_compressed, ctx = compression.compress(tensor)
-    summed = HorovodAllreduce.apply(tensor_compressed, average, name, op, prescale_factor, postscale_factor, process_set)
+    if _differentiate(tensor_compressed):
+        summed = HorovodAllreduce.apply(tensor_compressed, average, name, op, prescale_factor, postscale_factor, process_set)
+    else:
+        summed = synchronize(allreduce_async(tensor_compressed, average, name, op, prescale_factor, postscale_factor, process_set))
     return compression.decompress(summed, ctx)
 
 
@@ -274,7 +288,10 @@ def grouped_allreduce(tensors, average=None, name=None, compression=None, op=Non
     from horovod_b200.torch.compression import Compression
     compression = compression or Compression.none
     compressed, ctxs = zip(*[compression.compress(t) for t in tensors])
-    summed = HorovodGroupedAllreduce.apply(average, name, op, prescale_factor, postscale_factor, process_set, *compressed)
+    if _differentiate(*compressed):
+        summed = HorovodGroupedAllreduce.apply(average, name, op, prescale_factor, postscale_factor, process_set, *compressed)
+    else:
+        summed = synchronize(grouped_allreduce_async(list(compressed), average, name, op, prescale_factor, postscale_factor, process_set))
     return [compression.decompress(t, c) for t, c in zip(summed, ctxs)]
 
 
@@ -344,6 +361,8 @@ class HorovodAllgather(torch.autograd.Function):
 
 def allgather(tensor, name=None, process_set=global_process_set):
     """Synchronous, differentiable allgather along dim 0 (dim 0 may differ between ranks)."""
+    if not _differentiate(tensor):
+        return synchronize(allgather_async(tensor, name, process_set))
     return HorovodAllgather.apply(tensor, name, process_set)
 
 
@@ -381,6 +400,8 @@ class HorovodGroupedAllgather(torch.autograd.Function):
 
 def grouped_allgather(tensors, name=None, process_set=global_process_set):
     """Synchronous, differentiable allgather of a list of tensors negotiated as one group."""
+    if not _differentiate(*tensors):
+        return list(synchronize(grouped_allgather_async(list(tensors), name, process_set)))
     return list(HorovodGroupedAllgather.apply(name, process_set, *tensors))
 
 
@@ -418,6 +439,8 @@ class HorovodBroadcast(torch.autograd.Function):
 
 def broadcast(tensor, root_rank, name=None, process_set=global_process_set):
     """Synchronous, differentiable broadcast of root_rank's tensor; the input is not modified."""
+    if not _differentiate(tensor):
+        return synchronize(broadcast_async(tensor, root_rank, name, process_set))
     return HorovodBroadcast.apply(tensor, root_rank, name, process_set)
 
 
@@ -477,6 +500,8 @@ class HorovodAlltoall(torch.autograd.Function):
 
 def alltoall(tensor, splits=None, name=None, process_set=global_process_set):
     """Synchronous, differentiable alltoall; with `splits` returns (output, received_splits)."""
+    if not _differentiate(tensor):
+        return synchronize(alltoall_async(tensor, splits, name, process_set))
     return HorovodAlltoall.apply(tensor, splits, name, process_set)
 
 
@@ -523,7 +548,10 @@ def reducescatter(tensor, name=None, compression=None, op=Average, process_set=g
     from horovod_b200.torch.compression import Compression
     compression = compression or Compression.none
     tensor_compressed, ctx = compression.compress(tensor)
-    reduced = HorovodReducescatter.apply(tensor_compressed, name, op, process_set, prescale_factor, postscale_factor)
+    if _differentiate(tensor_compressed):
+        reduced = HorovodReducescatter.apply(tensor_compressed, name, op, process_set, prescale_factor, postscale_factor)
+    else:
+        reduced = synchronize(reducescatter_async(tensor_compressed, name, op, process_set, prescale_factor, postscale_factor))
     return compression.decompress(reduced, ctx)
 
 
@@ -563,7 +591,10 @@ def grouped_reducescatter(tensors, name=None, compression=None, op=Average, proc
     from horovod_b200.torch.compression import Compression
     compression = compression or Compression.none
     compressed, ctxs = zip(*[compression.compress(t) for t in tensors])
-    reduced = HorovodGroupedReducescatter.apply(name, op, process_set, prescale_factor, postscale_factor, *compressed)
+    if _differentiate(*compressed):
+        reduced = HorovodGroupedReducescatter.apply(name, op, process_set, prescale_factor, postscale_factor, *compressed)
+    else:
+        reduced = synchronize(grouped_reducescatter_async(list(compressed), name, op, process_set, prescale_factor, postscale_factor))
     return [compression.decompress(t, c) for t, c in zip(reduced, ctxs)]
 
 
