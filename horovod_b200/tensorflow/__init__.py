@@ -269,11 +269,120 @@ def PartialDistributedGradientTape(gradtape, device_dense='', device_sparse='', 
     return tape
 
 
+# ---- legacy (tf.compat.v1.train.Optimizer) wrappers ------------------------------------------------------------------------------
+_LegacyOptimizer = getattr(getattr(getattr(tf, 'compat', None), 'v1', None), 'train', None)
+_LegacyOptimizer = getattr(_LegacyOptimizer, 'Optimizer', None)
+
+if _LegacyOptimizer is not None:
+    class _DistributedOptimizer(_LegacyOptimizer):
+        """`compute_gradients` of the wrapped optimizer followed by the allreduce (reference tensorflow/__init__.py:632-735);
+        everything else is delegated, so slots and variables are the wrapped optimizer's."""
+
+        def __init__(self, optimizer, name=None, use_locking=False, device_dense='', device_sparse='', compression=Compression.none,
+                     sparse_as_dense=False, op=_ops.Average, gradient_predivide_factor=1.0, backward_passes_per_step=1,
+                     average_aggregated_gradients=False, groups=None, process_set=_ops.global_process_set,
+                     scale_local_gradients=True):
+            super().__init__(name=name or 'Distributed%s' % type(optimizer).__name__, use_locking=use_locking)
+            self._optimizer = optimizer
+            self._process_set, self._scale_local = process_set, scale_local_gradients
+            self._allreduce_grads = _make_allreduce_grads_fn(self._name if hasattr(self, '_name') else (name or 'DistributedOptimizer'),
+                                                             device_dense, device_sparse, compression, sparse_as_dense, op,
+                                                             gradient_predivide_factor, groups, process_set)
+            self._local_vars = set()
+            self._agg_helper = None
+            if backward_passes_per_step > 1:
+                self._agg_helper = LocalGradientAggregationHelper(
+                    backward_passes_per_step, self._allreduce_grads, sparse_as_dense=sparse_as_dense,
+                    average_aggregated_gradients=average_aggregated_gradients, rank=_ops.rank() if _ops.is_initialized() else 0,
+                    optimizer_type=LocalGradientAggregationHelper._OPTIMIZER_TYPE_LEGACY, process_set=process_set,
+                    scale_local_gradients=scale_local_gradients)
+
+        def register_local_var(self, var):
+            """Gradients of `var` stay local (divided by the set size when scale_local_gradients)."""
+            if self._agg_helper is not None:
+                self._agg_helper.register_local_var(var)
+            self._local_vars.add(var.ref() if hasattr(var, 'ref') else id(var))
+
+        def compute_gradients(self, *args, **kwargs):
+            pairs = list(self._optimizer.compute_gradients(*args, **kwargs))
+            grads, variables = [g for g, _ in pairs], [v for _, v in pairs]
+            if self._agg_helper is not None:
+                reduced = self._agg_helper.compute_gradients(grads, variables)
+            else:
+                key = (lambda v: v.ref()) if variables and hasattr(variables[0], 'ref') else id
+                shared = [i for i, v in enumerate(variables) if key(v) not in self._local_vars]
+                reduced = list(grads)
+                for i, r in zip(shared, self._allreduce_grads([grads[i] for i in shared], [variables[i] for i in shared])):
+                    reduced[i] = r
+                if self._scale_local and len(shared) != len(reduced):
+                    n, keep = float(self._process_set.size()), set(shared)
+                    reduced = [g if (i in keep or g is None) else g / n for i, g in enumerate(reduced)]
+            return list(zip(reduced, variables))
+
+        def apply_gradients(self, *args, **kwargs):
+            if self._agg_helper is not None:
+                return self._agg_helper.apply_gradients(lambda: self._optimizer.apply_gradients(*args, **kwargs), self._optimizer,
+                                                        *args, **kwargs)
+            return self._optimizer.apply_gradients(*args, **kwargs)
+
+        def get_slot(self, *args, **kwargs):
+            return self._optimizer.get_slot(*args, **kwargs)
+
+        def get_slot_names(self, *args, **kwargs):
+            return self._optimizer.get_slot_names(*args, **kwargs)
+
+        def variables(self, *args, **kwargs):
+            return self._optimizer.variables(*args, **kwargs)
+
+    class _DistributedAdasumOptimizer(_LegacyOptimizer):
+        """Adasum needs the UPDATE each rank would make, not its gradient (reference :738-893): every rank applies its own
+        gradients locally, the per-variable delta against the last synchronised value is combined with op=Adasum, and the
+        variables are set to that value plus the combined delta.  With backward_passes_per_step > 1 the local optimizer runs
+        that many steps between two combinations."""
+
+        def __init__(self, optimizer, name=None, use_locking=False, device_dense='', device_sparse='', compression=Compression.none,
+                     backward_passes_per_step=1):
+            super().__init__(name=name or 'DistributedDelta%s' % type(optimizer).__name__, use_locking=use_locking)
+            self._optimizer, self._compression = optimizer, compression
+            self._passes, self._step = int(backward_passes_per_step), 0
+            self._start = {}
+
+        def compute_gradients(self, *args, **kwargs):
+            return self._optimizer.compute_gradients(*args, **kwargs)
+
+        def apply_gradients(self, grads_and_vars, *args, **kwargs):
+            pairs = [(g, v) for g, v in grads_and_vars if g is not None]
+            key = (lambda v: v.ref()) if pairs and hasattr(pairs[0][1], 'ref') else id
+            for _, v in pairs:
+                if key(v) not in self._start:
+                    self._start[key(v)] = tf.Variable(v.value() if hasattr(v, 'value') else v, trainable=False)
+            out = self._optimizer.apply_gradients(pairs, *args, **kwargs)
+            self._step += 1
+            if self._step % self._passes:
+                return out
+            for i, (_, v) in enumerate(pairs):
+                start = self._start[key(v)]
+                delta = allreduce(v - start, op=_ops.Adasum, compression=self._compression, name='adasum_delta_%d' % i)
+                start.assign(start + delta)
+                v.assign(start)
+            return out
+
+        def get_slot(self, *args, **kwargs):
+            return self._optimizer.get_slot(*args, **kwargs)
+
+        def get_slot_names(self, *args, **kwargs):
+            return self._optimizer.get_slot_names(*args, **kwargs)
+
+        def variables(self, *args, **kwargs):
+            return self._optimizer.variables(*args, **kwargs)
+
+
 def DistributedOptimizer(optimizer, name=None, use_locking=False, device_dense='', device_sparse='', compression=Compression.none,
                          sparse_as_dense=False, backward_passes_per_step=1, op=_ops.Average, gradient_predivide_factor=1.0,
                          average_aggregated_gradients=False, num_groups=0, groups=None, process_set=_ops.global_process_set,
                          scale_local_gradients=True):
-    """Wraps a Keras (TF2) optimizer so gradients are reduced across ranks before they are applied."""
+    """Wraps an optimizer so gradients are reduced across ranks before they are applied: a `tf.compat.v1.train.Optimizer` gets
+    the `compute_gradients` wrapper (or the delta wrapper for op=Adasum), a Keras optimizer the Keras subclass wrapper."""
     if gradient_predivide_factor != 1.0 and op != _ops.Average:
         raise ValueError('gradient_predivide_factor not supported with op != Average')
     if op == _ops.Adasum and average_aggregated_gradients:
@@ -281,6 +390,18 @@ def DistributedOptimizer(optimizer, name=None, use_locking=False, device_dense='
     if num_groups != 0:
         warnings.warn('Parameter `num_groups` has been replaced by `groups`', DeprecationWarning)
         groups = groups if groups is not None else num_groups
+    if groups is not None and not (isinstance(groups, list) or groups > 0):
+        raise ValueError('groups should be a non-negative integer or a list of list of tf.Variable.')
+    if _LegacyOptimizer is not None and isinstance(optimizer, _LegacyOptimizer):
+        if op == _ops.Adasum:
+            if process_set.process_set_id != 0:
+                raise NotImplementedError('Adasum does not support process sets yet')
+            return _DistributedAdasumOptimizer(optimizer, name, use_locking, device_dense, device_sparse, compression, backward_passes_per_step)
+        return _DistributedOptimizer(optimizer, name, use_locking, device_dense, device_sparse, compression, sparse_as_dense, op,
+                                     gradient_predivide_factor, backward_passes_per_step, average_aggregated_gradients, groups,
+                                     process_set, scale_local_gradients)
+    if op == _ops.Adasum:
+        raise ValueError('op == Adasum is not supported yet with Keras')
     from horovod_b200._keras import create_distributed_optimizer
     return create_distributed_optimizer(tf.keras, optimizer, name, device_dense, device_sparse, compression, sparse_as_dense,
                                         gradient_predivide_factor, op, backward_passes_per_step, average_aggregated_gradients,

@@ -210,4 +210,41 @@ keras = types.SimpleNamespace(callbacks=types.SimpleNamespace(Callback=_Callback
                               layers=types.SimpleNamespace(BatchNormalization=_BN), backend=_Backend,
                               optimizers=types.SimpleNamespace(Optimizer=object), models=types.SimpleNamespace())
 experimental = types.SimpleNamespace(dlpack=None)
-compat = types.SimpleNamespace(v1=types.SimpleNamespace(global_variables=lambda: []))
+
+
+class _LegacyOptimizer:
+    """tf.compat.v1.train.Optimizer stand-in: `canned` gradients instead of differentiation, plain SGD in apply_gradients."""
+
+    def __init__(self, use_locking=False, name='Optimizer'):
+        self._use_locking, self._name = use_locking, name
+        self.canned = None
+        self.applied = 0
+
+    def compute_gradients(self, loss, var_list=None, **kwargs):
+        return list(zip(self.canned, var_list))
+
+    def apply_gradients(self, grads_and_vars, global_step=None, name=None):
+        for g, v in grads_and_vars:
+            if g is not None:
+                v.assign(v - Tensor(_np.asarray(g.numpy()) * self._lr))
+        self.applied += 1
+        return self.applied
+
+    def get_slot(self, var, name):
+        return None
+
+    def get_slot_names(self):
+        return ['momentum']
+
+    def variables(self):
+        return []
+
+
+class _GradientDescentOptimizer(_LegacyOptimizer):
+    def __init__(self, learning_rate, use_locking=False, name='GradientDescent'):
+        super().__init__(use_locking, name)
+        self._lr = learning_rate
+
+
+compat = types.SimpleNamespace(v1=types.SimpleNamespace(global_variables=lambda: [], train=types.SimpleNamespace(
+    Optimizer=_LegacyOptimizer, GradientDescentOptimizer=_GradientDescentOptimizer)))

@@ -202,6 +202,40 @@ for epoch, value in enumerate([1.0, 0.5, 0.7, 0.4]):
 assert saved == ['/tmp/ckpt-1', '/tmp/ckpt-2', '/tmp/ckpt-4'] and best.best == 0.4 and best.best_epoch == 3
 assert hvdk.callbacks.BestModelCheckpoint(monitor='val_acc').mode == 'max'
 
+# legacy tf.compat.v1.train.Optimizer: compute_gradients wrapper, local vars, aggregation window, Adasum delta optimizer
+legacy = tf.compat.v1.train.GradientDescentOptimizer(0.5)
+dopt = hvd.DistributedOptimizer(legacy, op=hvd.Sum)
+assert isinstance(dopt, tf.compat.v1.train.Optimizer) and dopt.get_slot_names() == ['momentum']
+lv = [tf.Variable(np.zeros(2), name='lv0:0'), tf.Variable(np.zeros(2), name='lv1:0')]
+dopt.register_local_var(lv[1])
+legacy.canned = [tf.constant(np.ones(2) * (r + 1)), tf.constant(np.ones(2) * n)]
+gv = dopt.compute_gradients(None, var_list=lv)
+np.testing.assert_allclose(gv[0][0].numpy(), np.ones(2) * n * (n + 1) / 2)       # summed over ranks
+np.testing.assert_allclose(gv[1][0].numpy(), np.ones(2))                         # local: n / n, not reduced
+dopt.apply_gradients(gv)
+np.testing.assert_allclose(lv[0].numpy(), -0.5 * np.ones(2) * n * (n + 1) / 2)
+legacy2 = tf.compat.v1.train.GradientDescentOptimizer(1.0)
+dopt2 = hvd.DistributedOptimizer(legacy2, op=hvd.Average, backward_passes_per_step=2, average_aggregated_gradients=True)
+v2 = [tf.Variable(np.zeros(3), name='agg:0')]
+for step, g in enumerate((2.0, 4.0)):
+    legacy2.canned = [tf.constant(np.ones(3) * g * (r + 1))]
+    dopt2.apply_gradients(dopt2.compute_gradients(None, var_list=v2))
+    assert legacy2.applied == (0 if step == 0 else 1)                           # the first pass of the window applies nothing
+np.testing.assert_allclose(v2[0].numpy(), -np.ones(3) * 3.0 * (n + 1) / 2)       # mean over ranks of (2+4)/2 * (r+1)
+try:
+    hvd.DistributedOptimizer(_Opt() if '_Opt' in dir() else object(), op=hvd.Adasum)
+    raise SystemExit('Adasum with a Keras optimizer must be rejected')
+except ValueError:
+    pass
+ada = hvd.DistributedOptimizer(tf.compat.v1.train.GradientDescentOptimizer(1.0), op=hvd.Adasum)
+av = [tf.Variable(np.zeros(4), name='ada:0')]
+ada._optimizer.canned = [tf.constant(np.eye(4)[r % 4] * -1.0)]                    # orthogonal updates: Adasum adds them up
+ada.apply_gradients(ada.compute_gradients(None, var_list=av))
+expect = np.zeros(4)
+for q in range(n):
+    expect[q % 4] += 1.0
+np.testing.assert_allclose(av[0].numpy(), expect, atol=1e-6)
+
 # elastic callbacks (logic in _keras/elastic.py, reference _keras/elastic.py): commit cadence, batch / epoch bookkeeping
 import horovod_b200.keras.elastic as hke
 import horovod_b200.tensorflow.keras.elastic as hvdke
