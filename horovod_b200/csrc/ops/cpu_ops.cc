@@ -642,8 +642,30 @@ namespace {
 void TreeBroadcast(Transport* t, void* buf, int64_t bytes, int root) {
   const int n = t->size(), r = t->rank();
   if (n == 1 || bytes == 0) return;
-  // binomial tree rooted at `root`
   int vr = (r - root + n) % n;
+  const int64_t chunk = RingChunkElems(1);
+  if (n >= 3 && chunk > 0 && bytes >= 4 * chunk) {
+    // big message, three or more ranks: a chain in rank order, chunk by chunk — every link carries the message once and the
+    // links run concurrently ((chunks + n - 2) chunk times), where the binomial tree makes the root send the WHOLE message
+    // log2(n) times in a row
+    char* b = (char*)buf;
+    const int64_t pieces = (bytes + chunk - 1) / chunk;
+    auto len = [&](int64_t k) { return (size_t)std::min(chunk, bytes - k * chunk); };
+    const int prev = ((vr - 1 + n) % n + root) % n, next = ((vr + 1) % n + root) % n;
+    if (vr == 0) {
+      for (int64_t k = 0; k < pieces; ++k) t->Send(next, b + k * chunk, len(k));
+    } else if (vr == n - 1) {
+      for (int64_t k = 0; k < pieces; ++k) t->Recv(prev, b + k * chunk, len(k));
+    } else {
+      t->Recv(prev, b, len(0));
+      for (int64_t k = 0; k < pieces; ++k) {
+        if (k + 1 < pieces) t->SendRecv(next, b + k * chunk, len(k), prev, b + (k + 1) * chunk, len(k + 1));
+        else t->Send(next, b + k * chunk, len(k));
+      }
+    }
+    return;
+  }
+  // binomial tree rooted at `root`
   int mask = 1;
   while (mask < n) {
     if (vr & mask) { t->Recv(((vr - mask) + root) % n, buf, (size_t)bytes); break; }

@@ -65,10 +65,11 @@ def test_fake_two_hosts_np4(native_built):
 def test_pipelined_tcp_ring_allreduce(native_built, np_, hosts):
     """Cross-host ring with a tiny HVD_RING_CHUNK_BYTES: every ring step is cut into many chunks and the reducer thread folds
     chunk k while chunk k+1 is on the wire (cpu_ops.cc:RingAllreduce).  3 ranks on 3 "hosts" = the plain ring with uneven
-    segments; 4 ranks on 2 "hosts" = the cross-host rings of the two-level allreduce.  Exact integer-valued sums."""
+    segments; 4 ranks on 2 "hosts" = the cross-host rings of the two-level allreduce.  Exact integer-valued sums.  With three
+    ranks the broadcasts of >= 4 chunks take the chunked chain instead of the binomial tree (cpu_ops.cc:TreeBroadcast)."""
     rc, out = run_parallel("ops_worker.py", np=np_, timeout=400, env={"HVD_TEST_FAKE_HOSTS": hosts, "HVD_RING_CHUNK_BYTES": "8192"},
                            args=["--only", "rank_size,allreduce_sum_avg,allreduce_min_max_product,allreduce_mixed_dtype_fusion,"
-                                 "large_allreduce,reducescatter"])
+                                 "large_allreduce,reducescatter,broadcast,objects_and_state"])
     assert "ALL OK" in out, out[-3000:]
 
 
