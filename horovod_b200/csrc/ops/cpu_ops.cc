@@ -405,59 +405,96 @@ bool ShmBroadcast(Transport* t, char* buf, int64_t bytes, int root) {
 // Every rank publishes, in front of each piece of its send buffer, where the block for each destination starts (a
 // receiver knows how much it gets from a peer, not where that block sits in the peer's buffer) and how long the buffer is
 // (so that all ranks agree on the number of pieces after the first barrier).
-bool ShmAlltoallv(Transport* t, const char* in, const std::vector<int64_t>& sd, char* out, const std::vector<int64_t>& rd,
-                  const std::vector<int64_t>& rb) {
-  ShmData d;
-  if (!t->ShmDataPlane(&d)) return false;
-  const int n = t->size(), r = t->rank();
-  const int64_t hdr = (int64_t)(n + 2) * 8;
+// Personalised exchange among the ranks that share one set of shm slots.  `group[i]` is the communicator rank that owns slot
+// i (the whole communicator on one host; the ranks of this host in a multi-host job), `me` the caller's slot index; `barrier`
+// synchronises exactly that group.  Blocks for / from ranks outside the group are not touched.
+template <typename BarrierFn>
+bool SlotAlltoallv(Transport* t, const ShmData& d, const std::vector<int>& group, int me, BarrierFn barrier, const char* in,
+                   const std::vector<int64_t>& sd, char* out, const std::vector<int64_t>& rd) {
+  const int g = (int)group.size();
+  const int64_t hdr = (int64_t)(g + 2) * 8;
   const int64_t S = (int64_t)d.slot_bytes - hdr;
   if (S < 4096) return false;
-  const int64_t my_total = sd[n];
+  // what I send inside the group, packed in group order
+  std::vector<int64_t> gd((size_t)g + 1, 0);
   int64_t my_longest_block = 0;
-  for (int i = 0; i < n; ++i) if (i != r) my_longest_block = std::max(my_longest_block, sd[i + 1] - sd[i]);
-  // ---- round 0: header (send displacements, total, longest block) + the whole send buffer when it fits into one slot ----
+  for (int i = 0; i < g; ++i) {
+    const int64_t len = i == me ? 0 : sd[(size_t)group[(size_t)i] + 1] - sd[(size_t)group[(size_t)i]];
+    gd[(size_t)i + 1] = gd[(size_t)i] + len;
+    my_longest_block = std::max(my_longest_block, len);
+  }
+  const int64_t my_total = gd[(size_t)g];
+  // ---- round 0: header (packed displacements, total, longest block) + all my blocks when they fit into one slot ----
   int half = (int)(t->ShmNextPiece() & 1);
   {
-    char* mine = d.slot(r, half);
+    char* mine = d.slot(me, half);
     int64_t* h = (int64_t*)mine;
-    for (int i = 0; i < n; ++i) h[i] = sd[i];
-    h[n] = my_total;
-    h[n + 1] = my_longest_block;
-    if (my_total > 0 && my_total <= S) memcpy(mine + hdr, in, (size_t)my_total);
+    for (int i = 0; i < g; ++i) h[i] = gd[(size_t)i];
+    h[g] = my_total;
+    h[g + 1] = my_longest_block;
+    if (my_total > 0 && my_total <= S)
+      for (int i = 0; i < g; ++i)
+        if (gd[(size_t)i + 1] > gd[(size_t)i]) memcpy(mine + hdr + gd[(size_t)i], in + sd[(size_t)group[(size_t)i]], (size_t)(gd[(size_t)i + 1] - gd[(size_t)i]));
   }
-  t->Barrier();
+  barrier();
   int64_t longest_total = 0, longest_block = 0;
-  for (int q = 0; q < n; ++q) {
+  for (int q = 0; q < g; ++q) {
     const int64_t* h = (const int64_t*)d.slot(q, half);
-    longest_total = std::max(longest_total, h[n]);
-    longest_block = std::max(longest_block, h[n + 1]);
+    longest_total = std::max(longest_total, h[g]);
+    longest_block = std::max(longest_block, h[g + 1]);
   }
+  auto rlen_of = [&](int q) { return rd[(size_t)group[(size_t)q] + 1] - rd[(size_t)group[(size_t)q]]; };
   if (longest_total <= S) {
     // small exchange: everything is already published, every rank pulls its blocks (one barrier in total)
-    for (int q = 0; q < n; ++q) {
-      if (q == r || rb[q] == 0) continue;
+    for (int q = 0; q < g; ++q) {
+      if (q == me || rlen_of(q) == 0) continue;
       const char* theirs = d.slot(q, half);
-      memcpy(out + rd[q], theirs + hdr + ((const int64_t*)theirs)[r], (size_t)rb[q]);
+      memcpy(out + rd[(size_t)group[(size_t)q]], theirs + hdr + ((const int64_t*)theirs)[me], (size_t)rlen_of(q));
     }
     return true;
   }
-  // ---- large exchange: n - 1 rounds; in round k every rank publishes (a piece of) its block for rank r + k and pulls from
-  // rank r - k, so each slot has exactly one reader and every rank copies the same amount per piece (publishing the send
-  // buffer front to back instead makes all ranks target rank 0 first, then rank 1, ...: one busy receiver, n - 1 idle) ----
+  // ---- large exchange: g - 1 rounds; in round k every rank publishes (a piece of) its block for slot me + k and pulls from
+  // slot me - k, so each slot has exactly one reader and every rank copies the same amount per piece (publishing the send
+  // buffer front to back instead makes all ranks target rank 0 first, then rank 1, ...: one busy receiver, g - 1 idle) ----
   const int64_t pieces = (longest_block + S - 1) / S;
-  for (int k = 1; k < n; ++k) {
-    const int to = (r + k) % n, from = (r - k + n) % n;
-    const int64_t slen = sd[to + 1] - sd[to], rlen = rb[from];
+  for (int k = 1; k < g; ++k) {
+    const int to = (me + k) % g, from = (me - k + g) % g;
+    const int64_t slen = sd[(size_t)group[(size_t)to] + 1] - sd[(size_t)group[(size_t)to]], rlen = rlen_of(from);
     for (int64_t p = 0; p < pieces; ++p) {
       half = (int)(t->ShmNextPiece() & 1);
       const int64_t so = std::min(slen, p * S), sc = std::min(S, slen - so);
-      if (sc > 0) memcpy(d.slot(r, half) + hdr, in + sd[to] + so, (size_t)sc);
-      t->Barrier();
+      if (sc > 0) memcpy(d.slot(me, half) + hdr, in + sd[(size_t)group[(size_t)to]] + so, (size_t)sc);
+      barrier();
       const int64_t ro = std::min(rlen, p * S), rc = std::min(S, rlen - ro);
-      if (rc > 0) memcpy(out + rd[from] + ro, d.slot(from, half) + hdr, (size_t)rc);
+      if (rc > 0) memcpy(out + rd[(size_t)group[(size_t)from]] + ro, d.slot(from, half) + hdr, (size_t)rc);
     }
   }
+  return true;
+}
+
+bool ShmAlltoallv(Transport* t, const char* in, const std::vector<int64_t>& sd, char* out, const std::vector<int64_t>& rd) {
+  ShmData d;
+  if (!t->ShmDataPlane(&d)) return false;
+  std::vector<int> all((size_t)t->size());
+  for (int i = 0; i < t->size(); ++i) all[(size_t)i] = i;
+  return SlotAlltoallv(t, d, all, t->rank(), [t] { t->Barrier(); }, in, sd, out, rd);
+}
+
+// Multi-host, same number of ranks on every host: the blocks for the ranks of my host travel through the host's shm slots, the
+// blocks for every other rank over the TCP mesh (all of them in one poll set).
+bool HierAlltoallv(Transport* t, const char* in, const std::vector<int64_t>& sd, char* out, const std::vector<int64_t>& rd) {
+  HierData h;
+  if (!t->HierDataPlane(&h)) return false;
+  const auto& column = *h.column;
+  const int L = h.local_size, l = h.local_rank, n = t->size();
+  int x = -1;
+  for (size_t i = 0; i < column[(size_t)l].size(); ++i) if (column[(size_t)l][i] == t->rank()) x = (int)i;
+  if (x < 0) return false;
+  std::vector<int> host((size_t)L);
+  std::vector<uint8_t> local((size_t)n, 0);
+  for (int c = 0; c < L; ++c) { host[(size_t)c] = column[(size_t)c][(size_t)x]; local[(size_t)host[(size_t)c]] = 1; }
+  if (L > 1 && !SlotAlltoallv(t, h.local, host, l, [t] { t->LocalBarrier(); }, in, sd, out, rd)) return false;
+  t->AlltoallvBytes(in, sd.data(), out, rd.data(), local.data());
   return true;
 }
 
@@ -685,7 +722,8 @@ void Alltoallv(Transport* t, const void* in, const std::vector<int64_t>& sb, voi
   for (int i = 0; i < n; ++i) { sd[i + 1] = sd[i] + sb[i]; rd[i + 1] = rd[i] + rb[i]; }
   const char* i8 = (const char*)in; char* o8 = (char*)out;
   if (sb[r]) memcpy(o8 + rd[r], i8 + sd[r], (size_t)sb[r]);
-  if (n > 1 && Took(0, ShmAlltoallv(t, i8, sd, o8, rd, rb))) return;
+  if (n > 1 && Took(0, ShmAlltoallv(t, i8, sd, o8, rd))) return;
+  if (n > 1 && Took(1, HierAlltoallv(t, i8, sd, o8, rd))) return;
   if (n > 1) { Took(2, true); t->AlltoallvBytes(i8, sd.data(), o8, rd.data()); }
 }
 

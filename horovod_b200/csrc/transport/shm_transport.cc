@@ -238,7 +238,9 @@ class ShmControlTransport : public Transport {
   void SendRecv(int sp, const void* sb, size_t sn, int rp, void* rb, size_t rn) override {
     base_->SendRecv(sp, sb, sn, rp, rb, rn);
   }
-  void AlltoallvBytes(const char* in, const int64_t* sd, char* out, const int64_t* rd) override { base_->AlltoallvBytes(in, sd, out, rd); }
+  void AlltoallvBytes(const char* in, const int64_t* sd, char* out, const int64_t* rd, const uint8_t* skip) override {
+    base_->AlltoallvBytes(in, sd, out, rd, skip);
+  }
 
   void AllreduceBits(uint64_t* and_words, int n_and, uint64_t* or_words, int n_or) override {
     const int n = n_and + n_or;
@@ -338,7 +340,9 @@ class HierShmControlTransport : public Transport {
   void SendRecv(int sp, const void* sb, size_t sn, int rp, void* rb, size_t rn) override {
     base_->SendRecv(sp, sb, sn, rp, rb, rn);
   }
-  void AlltoallvBytes(const char* in, const int64_t* sd, char* out, const int64_t* rd) override { base_->AlltoallvBytes(in, sd, out, rd); }
+  void AlltoallvBytes(const char* in, const int64_t* sd, char* out, const int64_t* rd, const uint8_t* skip) override {
+    base_->AlltoallvBytes(in, sd, out, rd, skip);
+  }
 
   void AllreduceBits(uint64_t* and_words, int n_and, uint64_t* or_words, int n_or) override {
     const int n = n_and + n_or;

@@ -174,13 +174,14 @@ class TcpTransport : public Transport {
   }
   // All peers at once: every socket with bytes left to send or receive sits in ONE poll set, so a small exchange costs one
   // message time instead of n - 1 and large blocks stream over all connections concurrently.
-  void AlltoallvBytes(const char* in, const int64_t* sd, char* out, const int64_t* rd) override {
+  void AlltoallvBytes(const char* in, const int64_t* sd, char* out, const int64_t* rd, const uint8_t* skip) override {
     static const bool concurrent = [] { const char* e = getenv("HVD_TCP_ALLTOALL_CONCURRENT"); return !e || atoi(e) != 0; }();
-    if (!concurrent) { Transport::AlltoallvBytes(in, sd, out, rd); return; }
+    if (!concurrent) { Transport::AlltoallvBytes(in, sd, out, rd, skip); return; }
     struct Leg { int fd; const char* s; size_t sn; char* r; size_t rn; };
     std::vector<Leg> legs;
     for (int k = 1; k < size_; ++k) {              // rotation order: the first sockets polled differ from rank to rank
       const int p = (rank_ + k) % size_;
+      if (skip && skip[p]) continue;
       Leg l{fd(p), in + sd[p], (size_t)(sd[p + 1] - sd[p]), out + rd[p], (size_t)(rd[p + 1] - rd[p])};
       if (l.sn || l.rn) legs.push_back(l);
     }

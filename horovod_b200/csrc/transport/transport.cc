@@ -54,11 +54,14 @@ void Transport::Bcast(void* buf, size_t n, int root) {
   }
 }
 
-void Transport::AlltoallvBytes(const char* in, const int64_t* sd, char* out, const int64_t* rd) {
+void Transport::AlltoallvBytes(const char* in, const int64_t* sd, char* out, const int64_t* rd, const uint8_t* skip) {
   const int n = size(), r = rank();
   for (int k = 1; k < n; ++k) {
     const int to = (r + k) % n, from = (r - k + n) % n;
-    SendRecv(to, in + sd[to], (size_t)(sd[to + 1] - sd[to]), from, out + rd[from], (size_t)(rd[from + 1] - rd[from]));
+    const size_t sn = skip && skip[to] ? 0 : (size_t)(sd[to + 1] - sd[to]), rn = skip && skip[from] ? 0 : (size_t)(rd[from + 1] - rd[from]);
+    if (sn && rn) SendRecv(to, in + sd[to], sn, from, out + rd[from], rn);
+    else if (sn) Send(to, in + sd[to], sn);
+    else if (rn) Recv(from, out + rd[from], rn);
   }
 }
 

@@ -62,7 +62,8 @@ class Transport {
   // Personalised exchange with every other rank: byte range [sd[p], sd[p+1]) of `in` goes to rank p, [rd[p], rd[p+1]) of `out`
   // comes from rank p (the caller copies its own block).  Default: n - 1 rounds of SendRecv (to r + k, from r - k); the TCP
   // mesh progresses all peers at once.
-  virtual void AlltoallvBytes(const char* in, const int64_t* sd, char* out, const int64_t* rd);
+  // `skip[p] != 0` leaves rank p out (its blocks travel some other way).
+  virtual void AlltoallvBytes(const char* in, const int64_t* sd, char* out, const int64_t* rd, const uint8_t* skip = nullptr);
 
   // ---- collectives (default: star through `root`) ----
   virtual void GatherBytes(const std::vector<uint8_t>& mine, std::vector<std::vector<uint8_t>>* all, int root = 0);
