@@ -24,10 +24,10 @@ class LightningEstimator(HorovodEstimator):
     PARAMS = (
         P('gradient_clip_val', None, None, 'clip the global gradient norm after the allreduce'),
         P('num_gpus', None, None, 'accepted for compatibility: one GPU per process', camel='NumGPUs'),
-        P('logger', None, None, 'accepted for compatibility: the history is returned with the model'),
-        P('log_every_n_steps', 50, None, 'accepted for compatibility'),
+        P('logger', None, None, 'object with log_metrics(dict, step=): gets the step loss every log_every_n_steps steps and every epoch record (rank 0)'),
+        P('log_every_n_steps', 50, None, 'training steps between two logger calls'),
         P('loader_num_epochs', None, None, 'accepted for compatibility'),
-        P('terminate_on_nan', False, None, 'accepted for compatibility'),
+        P('terminate_on_nan', False, None, 'raise as soon as a training loss is NaN or infinite (one device -> host read per step)'),
         P('profiler', None, None, 'accepted for compatibility'),
         P('checkpoint_callback', None, None, 'accepted for compatibility: rank 0 checkpoints into the store after every epoch'),
         P('trainer_args', None, None, 'pytorch_lightning.Trainer keyword arguments; max_epochs / gradient_clip_val / accumulate_grad_batches are honoured'),
@@ -75,7 +75,8 @@ class LightningEstimator(HorovodEstimator):
                     train_reader_num_workers=g('train_reader_num_workers'), val_reader_num_workers=g('val_reader_num_workers'),
                     train_async_data_loader_queue_size=g('train_async_data_loader_queue_size'),
                     val_async_data_loader_queue_size=g('val_async_data_loader_queue_size'), debug_data_loader=g('debug_data_loader'),
-                    transformation_removed_fields=g('transformation_removed_fields'))
+                    transformation_removed_fields=g('transformation_removed_fields'), logger=g('logger'),
+                    log_every_n_steps=g('log_every_n_steps'), terminate_on_nan=g('terminate_on_nan'))
         translate_trainer_args(g('trainer_args'))          # fail on the driver, not inside the job
         rank0 = backend.run(_train_fn, args=(spec,))[0]
         module.load_state_dict(rank0['state_dict'])

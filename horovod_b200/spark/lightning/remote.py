@@ -64,7 +64,8 @@ def _train_fn(spec):
     trainer_kwargs = dict(epochs=spec['epochs'], first_epoch=first_epoch, compression=spec['compression'],
                           backward_passes_per_step=spec['backward_passes_per_step'], gradient_clip_val=spec['gradient_clip_val'],
                           callbacks=spec['callbacks'], checkpoint=checkpoint, verbose=spec['verbose'],
-                          prefetcher=lambda l: DevicePrefetcher(l, device=dev))
+                          prefetcher=lambda l: DevicePrefetcher(l, device=dev), logger=spec.get('logger'),
+                          log_every_n_steps=spec.get('log_every_n_steps') or 50, terminate_on_nan=bool(spec.get('terminate_on_nan')))
     trainer_kwargs.update(translate_trainer_args(spec.get('trainer_args')))
     trainer = ModuleProtocolTrainer(hvd, dev, **trainer_kwargs)
     trainer.setup(module, optimizer_state=opt_state)

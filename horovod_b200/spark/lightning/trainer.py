@@ -83,7 +83,12 @@ class ModuleProtocolTrainer:
     """fit(module, train_loader, val_loader=None) -> history (list of per-epoch dicts, identical on every rank)."""
 
     def __init__(self, hvd, device, epochs=1, first_epoch=0, compression=None, backward_passes_per_step=1, gradient_clip_val=None,
-                 callbacks=(), checkpoint=None, verbose=0, prefetcher=None):
+                 callbacks=(), checkpoint=None, verbose=0, prefetcher=None, logger=None, log_every_n_steps=50, terminate_on_nan=False):
+        """`logger`: object with `log_metrics(dict, step=)` (any pytorch_lightning logger qualifies), called on rank 0 every
+        `log_every_n_steps` training steps with the step's loss and once per epoch with the averaged record.
+        `terminate_on_nan`: a non-finite training loss raises ValueError on the rank that sees it (costs one device -> host read
+        per step)."""
+        self.logger, self.log_every_n_steps, self.terminate_on_nan = logger, max(1, int(log_every_n_steps or 50)), terminate_on_nan
         self.hvd, self.device, self.epochs, self.first_epoch = hvd, device, epochs, first_epoch
         self.compression, self.accumulate = compression, backward_passes_per_step
         self.clip, self.callbacks, self.checkpoint, self.verbose = gradient_clip_val, list(callbacks), checkpoint, verbose
@@ -117,6 +122,7 @@ class ModuleProtocolTrainer:
         module.log, module.log_dict = sink.log, sink.log_dict
         opt, hvd = self.optimizer, self.hvd
         history = []
+        global_step = 0
         _hook(module, 'on_fit_start')
         _hook(module, 'on_train_start')
         for epoch in range(self.first_epoch, self.epochs):
@@ -128,6 +134,11 @@ class ModuleProtocolTrainer:
             for i, batch in enumerate(self.prefetcher(train_loader)):
                 out = module.training_step(batch, i)
                 loss = out['loss'] if isinstance(out, dict) else out
+                if self.terminate_on_nan and not bool(torch.isfinite(loss.detach()).all()):
+                    raise ValueError('The loss returned in `training_step` is %s at epoch %d, step %d.' % (loss.detach().tolist(), epoch, i))
+                global_step += 1
+                if self.logger is not None and hvd.rank() == 0 and global_step % self.log_every_n_steps == 0:
+                    self.logger.log_metrics({'loss': float(loss.detach())}, step=global_step)
                 (loss / self.accumulate).backward()
                 if (i + 1) % self.accumulate == 0:
                     if self.clip:
@@ -166,6 +177,8 @@ class ModuleProtocolTrainer:
                 vals.update(sink.drain(self.device))
                 record.update(self._average(vals, 'val'))
             history.append(record)
+            if self.logger is not None and hvd.rank() == 0:
+                self.logger.log_metrics({k: v for k, v in record.items() if k != 'epoch'}, step=global_step)
             for cb in self.callbacks:
                 cb(epoch, record) if callable(cb) else _hook(cb, 'on_epoch_end', epoch, record)
             if self.verbose and hvd.rank() == 0:

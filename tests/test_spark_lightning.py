@@ -137,6 +137,23 @@ def test_protocol_trainer_single_process_hooks(native_built):
         assert seen == [0, 1, 2] and m.epoch_starts == 3 and hist[2]['loss'] < hist[0]['loss']
         assert abs(tr.optimizer.param_groups[0]['lr'] - 0.1 * 0.9 ** 12) < 1e-9
         assert {'loss', 'val_loss', 'train_mae', 'epoch'} <= set(hist[0])
+
+        class Logger:
+            def __init__(self):
+                self.calls = []
+
+            def log_metrics(self, metrics, step=None):
+                self.calls.append((step, dict(metrics)))
+        lg = Logger()
+        ModuleProtocolTrainer(hvd, torch.device('cpu'), epochs=2, logger=lg, log_every_n_steps=3).fit(M(), batches, batches)
+        steps = [s for s, _ in lg.calls]
+        assert steps == [3, 4, 6, 8] and set(lg.calls[0][1]) == {'loss'} and {'loss', 'val_loss'} <= set(lg.calls[1][1]), lg.calls
+
+        class Diverges(M):
+            def training_step(self, batch, batch_idx):
+                return super().training_step(batch, batch_idx) * float('nan') if batch_idx == 2 else super().training_step(batch, batch_idx)
+        with pytest.raises(ValueError, match='step 2'):
+            ModuleProtocolTrainer(hvd, torch.device('cpu'), epochs=1, terminate_on_nan=True).fit(Diverges(), batches)
     finally:
         hvd.shutdown()
 
