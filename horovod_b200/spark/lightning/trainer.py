@@ -149,6 +149,9 @@ class ModuleProtocolTrainer:
                     else:
                         opt.step()
                     opt.zero_grad()
+                    if self.scheduler is not None:
+                        # the scheduler watches the optimizer it was built on; the step ran through the distributed wrapper
+                        setattr(self.scheduler.optimizer, '_opt_called', True)
                     if self.scheduler is not None and self.interval == 'step':
                         self.scheduler.step()
                 total += loss.detach()
