@@ -346,23 +346,33 @@ bool ShmAllreduce(Transport* t, char* b, int64_t count, DataType dtype, ReduceOp
   return true;
 }
 
+// Every step each rank publishes, for EVERY destination q, the next `sub` elements of q's segment (destination-major layout
+// inside its slot); after the barrier rank q folds sub-chunk q of all n slots straight into its output.  All ranks copy and
+// reduce the same amount per step (walking the buffer front to back instead keeps one owner busy reducing n slots while the
+// others wait: 64 MiB of input took 46 ms at np=4, an ALLREDUCE of the same buffer 25 ms).
 bool ShmReducescatter(Transport* t, const char* b, const std::vector<int64_t>& off, char* out, DataType dtype, ReduceOp op) {
   ShmData d;
   if (!t->ShmDataPlane(&d)) return false;
   const int n = t->size(), r = t->rank();
   const size_t es = DataTypeSize(dtype);
-  const int64_t count = off[n], per_piece = (int64_t)(d.slot_bytes / es);
-  for (int64_t done = 0; done < count; done += per_piece) {
-    const int64_t m = std::min(per_piece, count - done);
+  const int64_t sub = (int64_t)(d.slot_bytes / es) / n;
+  if (sub < 16) return false;
+  int64_t longest = 0;
+  for (int q = 0; q < n; ++q) longest = std::max(longest, off[q + 1] - off[q]);
+  const int64_t mine_len = off[r + 1] - off[r];
+  for (int64_t done = 0; done < longest; done += sub) {
     const int half = (int)(t->ShmNextPiece() & 1);
-    memcpy(d.slot(r, half), b + done * es, (size_t)m * es);
+    char* slot = d.slot(r, half);
+    for (int q = 0; q < n; ++q) {
+      const int64_t c = std::min(sub, off[q + 1] - off[q] - done);
+      if (c > 0) memcpy(slot + (size_t)q * (size_t)sub * es, b + (off[q] + done) * es, (size_t)c * es);
+    }
     t->Barrier();
-    // the part of my output segment that lies inside this piece
-    const int64_t lo = std::max(off[r], done), hi = std::min(off[r + 1], done + m);
-    if (hi > lo) {
-      char* dst = out + (lo - off[r]) * es;
-      memcpy(dst, d.slot(r, half) + (lo - done) * es, (size_t)(hi - lo) * es);
-      for (int p = 1; p < n; ++p) ReduceInto(dst, d.slot((r + p) % n, half) + (lo - done) * es, hi - lo, dtype, op);
+    const int64_t c = std::min(sub, mine_len - done);
+    if (c > 0) {
+      char* dst = out + done * es;
+      memcpy(dst, slot + (size_t)r * (size_t)sub * es, (size_t)c * es);
+      for (int p = 1; p < n; ++p) ReduceInto(dst, d.slot((r + p) % n, half) + (size_t)r * (size_t)sub * es, c, dtype, op);
     }
   }
   return true;
