@@ -581,6 +581,73 @@ bool HierAllgatherv(Transport* t, char* o, const std::vector<int64_t>& bytes, co
   return true;
 }
 
+// Ring reduce-scatter in place: afterwards segment r of `b` (counts / off in elements) holds the reduction over all ranks.
+void RingReducescatter(Transport* t, char* b, const std::vector<int64_t>& counts, const std::vector<int64_t>& off, DataType dtype, ReduceOp op) {
+  const int n = t->size(), r = t->rank();
+  if (n == 1) return;
+  const size_t es = DataTypeSize(dtype);
+  std::vector<char> tmp;
+  const int64_t maxseg = *std::max_element(counts.begin(), counts.end());
+  const int next = (r + 1) % n, prev = (r - 1 + n) % n;
+  for (int s = 0; s < n - 1; ++s) {
+    int si = (r - s - 1 + 2 * n) % n, ri = (r - s - 2 + 2 * n) % n;
+    RingReduceStep(t, next, prev, b + off[si] * es, counts[si], b + off[ri] * es, counts[ri], maxseg, dtype, op, &tmp);
+  }
+}
+
+// Multi-host, same number of ranks on every host.  (1) Inside a host, destination-major steps through the shm slots: local rank
+// c ends up with the host's partial sums of every segment that belongs to a rank with local index c (on any host).  (2) The H
+// ranks with my local index reduce-scatter those partial sums over their cross-host ring: 1/L of the bytes per TCP stream, and
+// nothing that stays inside a host ever touches a socket.
+bool HierReducescatter(Transport* t, const char* b, const std::vector<int64_t>& off, char* out, DataType dtype, ReduceOp op) {
+  HierData h;
+  if (!t->HierDataPlane(&h)) return false;
+  const auto& column = *h.column;
+  const int L = h.local_size, l = h.local_rank;
+  const int H = (int)column[0].size();
+  const size_t es = DataTypeSize(dtype);
+  const int64_t sub = (int64_t)(h.local.slot_bytes / es) / L;
+  if (sub < 16) return false;
+  int x_me = -1;
+  for (int x = 0; x < H; ++x) if (column[(size_t)l][(size_t)x] == t->rank()) x_me = x;
+  if (x_me < 0 || h.cross->rank() != x_me) return false;
+  auto seg_len = [&](int rank) { return off[(size_t)rank + 1] - off[(size_t)rank]; };
+  std::vector<int64_t> col_len((size_t)L, 0);
+  int64_t longest = 0;
+  for (int c = 0; c < L; ++c) { for (int rk : column[(size_t)c]) col_len[(size_t)c] += seg_len(rk); longest = std::max(longest, col_len[(size_t)c]); }
+  // copies elements [lo, lo + cnt) of the virtual vector "segments of column c, host by host" out of the user buffer
+  auto gather = [&](int c, int64_t lo, int64_t cnt, char* dst) {
+    int64_t pos = 0;
+    for (int rk : column[(size_t)c]) {
+      const int64_t blo = pos, bhi = pos + seg_len(rk);
+      const int64_t a = std::max(blo, lo), z = std::min(bhi, lo + cnt);
+      if (z > a) memcpy(dst + (a - lo) * es, b + (off[(size_t)rk] + (a - blo)) * es, (size_t)(z - a) * es);
+      pos = bhi;
+    }
+  };
+  std::vector<char> partial((size_t)std::max<int64_t>(col_len[(size_t)l], 1) * es);
+  for (int64_t done = 0; done < longest; done += sub) {
+    const int half = (int)(t->ShmNextPiece() & 1);
+    char* slot = h.local.slot(l, half);
+    for (int c = 0; c < L; ++c) {
+      const int64_t cnt = std::min(sub, col_len[(size_t)c] - done);
+      if (cnt > 0) gather(c, done, cnt, slot + (size_t)c * (size_t)sub * es);
+    }
+    t->LocalBarrier();
+    const int64_t cnt = std::min(sub, col_len[(size_t)l] - done);
+    if (cnt > 0) {
+      char* dst = partial.data() + done * es;
+      memcpy(dst, slot + (size_t)l * (size_t)sub * es, (size_t)cnt * es);
+      for (int p = 1; p < L; ++p) ReduceInto(dst, h.local.slot((l + p) % L, half) + (size_t)l * (size_t)sub * es, cnt, dtype, op);
+    }
+  }
+  std::vector<int64_t> cc((size_t)H), coff((size_t)H + 1, 0);
+  for (int x = 0; x < H; ++x) { cc[(size_t)x] = seg_len(column[(size_t)l][(size_t)x]); coff[(size_t)x + 1] = coff[(size_t)x] + cc[(size_t)x]; }
+  RingReducescatter(h.cross, partial.data(), cc, coff, dtype, op);
+  if (cc[(size_t)x_me]) memcpy(out, partial.data() + coff[(size_t)x_me] * es, (size_t)cc[(size_t)x_me] * es);
+  return true;
+}
+
 void TreeBroadcast(Transport* t, void* buf, int64_t bytes, int root);
 
 // Two-level broadcast: across hosts only the ranks with the root's local index talk (binomial tree over H ranks instead of
@@ -744,16 +811,8 @@ void Reducescatter(Transport* t, void* buf, const std::vector<int64_t>& counts, 
   for (int i = 0; i < n; ++i) off[i + 1] = off[i] + counts[i];
   char* b = (char*)buf;
   if (n > 1 && Took(0, ShmReducescatter(t, b, off, (char*)out, dtype, op))) return;
-  if (n > 1) Took(2, true);
-  if (n > 1) {
-    std::vector<char> tmp;
-    const int64_t maxseg = *std::max_element(counts.begin(), counts.end());
-    const int next = (r + 1) % n, prev = (r - 1 + n) % n;
-    for (int s = 0; s < n - 1; ++s) {
-      int si = (r - s - 1 + 2 * n) % n, ri = (r - s - 2 + 2 * n) % n;
-      RingReduceStep(t, next, prev, b + off[si] * es, counts[si], b + off[ri] * es, counts[ri], maxseg, dtype, op, &tmp);
-    }
-  }
+  if (n > 1 && Took(1, HierReducescatter(t, b, off, (char*)out, dtype, op))) return;
+  if (n > 1) { Took(2, true); RingReducescatter(t, b, counts, off, dtype, op); }
   if (counts[r]) memcpy(out, b + off[r] * es, (size_t)counts[r] * es);
 }
 
