@@ -158,13 +158,14 @@ def clean():
     shutil.rmtree(OUT, ignore_errors=True)
 
 
-def build_tsan_selftest(force=False):
+def build_tsan_selftest(force=False, sanitizer="thread"):
     """ThreadSanitizer build of the C++ runtime + its native self-test (N engines in one process over the loopback
     transport: controller, response cache, fusion, CPU ops, process sets, join, error paths) as a stand-alone executable.
     The sm_100a kernel objects are linked as they are (device code is not instrumented).  The reference has no sanitizer
-    build at all."""
+    build at all.  `sanitizer="address,undefined"` builds the AddressSanitizer + UBSan flavour of the same binary."""
     build_core()
-    odir = os.path.join(os.path.dirname(OBJ), "obj_tsan")
+    tag = "tsan" if sanitizer == "thread" else "san_" + "".join(c if c.isalnum() else "_" for c in sanitizer)
+    odir = os.path.join(os.path.dirname(OBJ), "obj_" + tag)
     os.makedirs(odir, exist_ok=True)
     hstamp = _header_digest()
     cc, _ = _sources()
@@ -177,9 +178,9 @@ def build_tsan_selftest(force=False):
     def one(src):
         rel = os.path.relpath(src, CSRC).replace("/", "__") if src.startswith(CSRC) else os.path.basename(src)
         obj = os.path.join(odir, rel + ".o")
-        stamp = _src_stamp(src, hstamp + "tsan")
+        stamp = _src_stamp(src, hstamp + tag)
         if force or _needs(src, obj, stamp):
-            _run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-fPIC", "-pthread"] + inc + ["-c", src, "-o", obj])
+            _run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=" + sanitizer, "-fno-omit-frame-pointer", "-fPIC", "-pthread"] + inc + ["-c", src, "-o", obj])
             for f in os.listdir(odir):
                 if f.startswith(rel + ".o.") and f != rel + ".o." + stamp:
                     os.remove(os.path.join(odir, f))
@@ -188,8 +189,8 @@ def build_tsan_selftest(force=False):
     with ThreadPoolExecutor(max_workers=max(2, os.cpu_count() or 4)) as ex:
         objs = list(ex.map(one, cc + [main]))
     kernels = [os.path.join(OBJ, f) for f in sorted(os.listdir(OBJ)) if f.startswith("kernels__") and f.endswith(".o")]
-    exe = os.path.join(os.path.dirname(OBJ), "selftest_tsan")
-    _run(["g++", "-fsanitize=thread", "-pthread"] + objs + kernels + ["-o", exe, "-L" + os.path.join(CUDA_HOME, "lib64"),
+    exe = os.path.join(os.path.dirname(OBJ), "selftest_" + tag)
+    _run(["g++", "-fsanitize=" + sanitizer, "-pthread"] + objs + kernels + ["-o", exe, "-L" + os.path.join(CUDA_HOME, "lib64"),
                                                                       "-lcudart_static", "-ldl", "-lrt", "-lpthread"])
     return exe
 

@@ -40,7 +40,7 @@ class ByteReader {
   bool done() const { return p_ >= end_; }
  private:
   void need(size_t n);
-  void rd(void* o, size_t n) { need(n); memcpy(o, p_, n); p_ += n; }
+  void rd(void* o, size_t n) { need(n); if (n) memcpy(o, p_, n); p_ += n; }
   const uint8_t* p_; const uint8_t* end_;
 };
 

@@ -30,6 +30,23 @@ def test_native_selftest_under_thread_sanitizer():
         assert p.returncode == 0, (extra, p.returncode, p.stdout.decode()[-2000:], err[-2000:])
 
 
+def test_native_selftest_under_address_and_ub_sanitizers():
+    """The same self-test built with -fsanitize=address,undefined (found a memcpy(nullptr, p, 0) in the wire codec): no report
+    of either sanitizer, in the default configuration and with tiny ring chunks + log-depth bit reduction."""
+    if shutil.which('g++') is None:
+        pytest.skip('no g++')
+    from horovod_b200 import build
+    exe = build.build_tsan_selftest(sanitizer='address,undefined')
+    env = dict(os.environ, ASAN_OPTIONS='detect_leaks=0 exitcode=67', UBSAN_OPTIONS='print_stacktrace=1', HOROVOD_LOG_LEVEL='error')
+    for extra in ({}, {'HVD_RING_CHUNK_BYTES': '4096', 'HVD_BITS_TREE_MIN_RANKS': '2'}):
+        p = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=dict(env, **extra), timeout=900)
+        err = p.stderr.decode(errors='replace')
+        if 'AddressSanitizer' in err and ('Shadow memory range interleaves' in err or 'failed to allocate' in err):
+            pytest.skip('AddressSanitizer cannot run in this container (address space layout)')
+        assert 'runtime error:' not in err and 'ERROR: AddressSanitizer' not in err, (extra, err[-6000:])
+        assert p.returncode == 0, (extra, p.returncode, p.stdout.decode()[-2000:], err[-2000:])
+
+
 @pytest.mark.gpu
 @pytest.mark.skipif(os.environ.get('HVD_RUN_COMPUTE_SANITIZER', '0') != '1',
                     reason='opt-in (HVD_RUN_COMPUTE_SANITIZER=1): memcheck instruments every kernel of the process, minutes per run')
