@@ -9,7 +9,10 @@
 #include <future>
 #include <sstream>
 #include <thread>
+#include <cstdlib>
+#include <unistd.h>
 #include "../ops/cpu_ops.h"
+#include "../transport/transport.h"
 #include "controller.h"
 #include "engine.h"
 #include "half.h"
@@ -277,6 +280,116 @@ void TestBitsAmong(int n) {
   CHECK_T(bad.load() == 0);
 }
 
+// The shared-memory control + data plane with the "ranks" being threads of this process (each maps the segments itself, like a
+// process would): multi-piece allreduce, destination-major reducescatter, both regimes of the slot alltoall (everything in one
+// slot / rotation rounds with ragged blocks), allgatherv and broadcast through slots of 8 KiB.  This is what puts
+// shm_transport.cc and the Shm* collectives of cpu_ops.cc under the thread / address sanitizer builds.
+void PlaneCollectives(Transport* tp, int n, int r, std::atomic<int>& bad) {
+  Transport* t = tp;
+  // bit vectors + barrier through the segment
+  uint64_t a = ~(1ull << r), o = 1ull << r;
+  t->AllreduceBits(&a, 1, &o, 1);
+  uint64_t wa = ~0ull, wo = 0;
+  for (int p = 0; p < n; ++p) { wa &= ~(1ull << p); wo |= 1ull << p; }
+  if (a != wa || o != wo) bad++;
+  // allreduce over several pieces
+  const int64_t cnt = 10007;
+  std::vector<float> v(cnt);
+  for (int64_t i = 0; i < cnt; ++i) v[i] = (float)(r + 1) * (float)(i % 5);
+  cpu::Allreduce(t, v.data(), cnt, DataType::FLOAT32, ReduceOp::SUM);
+  for (int64_t i = 0; i < cnt; ++i) if (std::fabs(v[i] - (float)(n * (n + 1) / 2) * (float)(i % 5)) > 1e-3f) { bad++; break; }
+  // reducescatter, uneven segments, several steps
+  std::vector<int64_t> counts(n);
+  int64_t tc = 0;
+  for (int p = 0; p < n; ++p) { counts[p] = 1500 + 700 * p; tc += counts[p]; }
+  std::vector<double> buf(tc), out(counts[r]);
+  for (int64_t i = 0; i < tc; ++i) buf[i] = (double)(r + 1) + (double)i;
+  cpu::Reducescatter(t, buf.data(), counts, out.data(), DataType::FLOAT64, ReduceOp::SUM);
+  int64_t off = 0;
+  for (int p = 0; p < r; ++p) off += counts[p];
+  for (int64_t i = 0; i < counts[r]; ++i) if (std::fabs(out[i] - ((double)n * (n + 1) / 2 + (double)n * (double)(off + i))) > 1e-6) { bad++; break; }
+  // alltoall: k = 1 fits into one slot, k = 40 needs the rotation rounds; rank r sends (r + d) % 3 * k + (d ? 1 : 0) ints to d
+  for (int k : {1, 40}) {
+    std::vector<int64_t> sb(n), rb(n);
+    std::vector<int32_t> send;
+    for (int dst = 0; dst < n; ++dst) {
+      const int64_t len = (int64_t)((r + dst) % 3) * 50 * k + (dst ? 1 : 0);
+      sb[dst] = len * 4;
+      for (int64_t i = 0; i < len; ++i) send.push_back(r * 1000 + dst * 10 + (int32_t)(i % 7));
+    }
+    int64_t rt = 0;
+    for (int src = 0; src < n; ++src) { rb[src] = ((int64_t)((src + r) % 3) * 50 * k + (r ? 1 : 0)) * 4; rt += rb[src]; }
+    std::vector<int32_t> recv((size_t)(rt / 4) + 1, -1);
+    cpu::Alltoallv(t, send.data(), sb, recv.data(), rb);
+    int64_t pos = 0;
+    for (int src = 0; src < n; ++src)
+      for (int64_t i = 0; i < rb[src] / 4; ++i, ++pos) if (recv[(size_t)pos] != src * 1000 + r * 10 + (int32_t)(i % 7)) { bad++; break; }
+  }
+  // allgatherv + broadcast from every root
+  std::vector<int64_t> bytes(n);
+  int64_t total = 0;
+  for (int p = 0; p < n; ++p) { bytes[p] = 3000 * (p + 1) + 1; total += bytes[p]; }
+  std::vector<char> mine(bytes[r], (char)('a' + r)), all(total);
+  cpu::Allgatherv(t, mine.data(), all.data(), bytes);
+  int64_t o2 = 0;
+  for (int p = 0; p < n; ++p) { for (int64_t i = 0; i < bytes[p]; ++i) if (all[o2 + i] != (char)('a' + p)) { bad++; break; } o2 += bytes[p]; }
+  for (int root = 0; root < n; ++root) {
+    std::vector<int32_t> x(5000, r == root ? 77 + root : -1);
+    cpu::Broadcast(t, x.data(), (int64_t)x.size() * 4, root);
+    if (x.front() != 77 + root || x.back() != 77 + root) bad++;
+  }
+}
+
+void TestShmPlane(int n) {
+  if (n < 2) return;
+  setenv("HVD_SHM_SLOT_BYTES", "8192", 1);
+  static std::atomic<int> serial{0};
+  const std::string seg = "hvd-selftest-" + std::to_string((long)getpid()) + "-" + std::to_string(serial.fetch_add(1));
+  auto hub = CreateLoopbackHub(n);
+  std::vector<std::thread> th;
+  std::atomic<int> bad{0}, no_plane{0};
+  for (int r = 0; r < n; ++r) {
+    th.emplace_back([&, r] {
+      std::shared_ptr<Transport> t = WrapWithShmControl(LoopbackEndpoint(hub, r), seg);
+      ShmData d;
+      if (!t->ShmDataPlane(&d)) { no_plane++; return; }               // no /dev/shm here: nothing to test
+      PlaneCollectives(t.get(), n, r, bad);
+      t->Barrier();
+    });
+  }
+  for (auto& t : th) t.join();
+  unsetenv("HVD_SHM_SLOT_BYTES");
+  CHECK_T(bad.load() == 0);
+  CHECK_T(no_plane.load() == 0 || no_plane.load() == n);
+}
+
+// The two-level planes (shm inside a "host", loopback queues standing in for the sockets between hosts): hosts x per_host ranks.
+void TestHierPlane(int hosts, int per_host) {
+  const int n = hosts * per_host;
+  setenv("HVD_SHM_SLOT_BYTES", "8192", 1);
+  static std::atomic<int> serial{0};
+  const std::string seg = "hvd-selftest-h-" + std::to_string((long)getpid()) + "-" + std::to_string(serial.fetch_add(1));
+  std::vector<int> table((size_t)n);
+  for (int r = 0; r < n; ++r) table[(size_t)r] = r / per_host;
+  auto hub = CreateLoopbackHub(n);
+  std::vector<std::thread> th;
+  std::atomic<int> bad{0}, no_plane{0};
+  for (int r = 0; r < n; ++r) {
+    th.emplace_back([&, r] {
+      std::shared_ptr<Transport> t = WrapWithHierarchicalControl(LoopbackEndpoint(hub, r, table), seg);
+      HierData h;
+      if (!t->HierDataPlane(&h)) { no_plane++; return; }
+      if (h.local_size != per_host || (int)(*h.column)[0].size() != hosts) bad++;
+      PlaneCollectives(t.get(), n, r, bad);
+      t->Barrier();
+    });
+  }
+  for (auto& t : th) t.join();
+  unsetenv("HVD_SHM_SLOT_BYTES");
+  CHECK_T(bad.load() == 0);
+  CHECK_T(no_plane.load() == 0 || no_plane.load() == n);
+}
+
 void TestAdasum(int n) {
   if (n & (n - 1)) return;
   auto hub = CreateLoopbackHub(n);
@@ -455,6 +568,10 @@ extern "C" int hvd_selftest(int nranks, char* log, int log_len) {
   TestAutotune();
   for (int n : {1, 2, 3, nranks}) { if (n < 1) continue; TestCpuOps(n); TestAdasum(n); }
   for (int n : {2, 3, 5, 6, 7, 8, 11}) TestBitsAmong(n);
+  for (int n : {2, 3, 4}) TestShmPlane(n);
+  TestHierPlane(2, 2);
+  TestHierPlane(3, 2);
+  TestHierPlane(2, 3);
   TestEngines(nranks);
   TestEngines(1);
   std::string s = g_log.str();

@@ -186,9 +186,16 @@ class LoopbackHub {
 namespace {
 class LoopbackTransport : public Transport {
  public:
-  LoopbackTransport(std::shared_ptr<LoopbackHub> hub, int rank) : hub_(std::move(hub)), rank_(rank) {}
+  LoopbackTransport(std::shared_ptr<LoopbackHub> hub, int rank, std::vector<int> hosts = {})
+      : hub_(std::move(hub)), rank_(rank), hosts_(std::move(hosts)) {}
   int rank() const override { return rank_; }
   int size() const override { return hub_->size(); }
+  // optional host table: lets unit tests present the ranks of one process as several hosts (two-level planes)
+  bool single_host() const override {
+    for (int h : hosts_) if (h != hosts_[0]) return false;
+    return true;
+  }
+  int host_id(int i) const override { return i >= 0 && i < (int)hosts_.size() ? hosts_[(size_t)i] : 0; }
   void Send(int peer, const void* b, size_t n) override { hub_->Push(rank_, peer, b, n); }
   void Recv(int peer, void* b, size_t n) override { hub_->Pop(peer, rank_, b, n); }
   void SendRecv(int sp, const void* sb, size_t sn, int rp, void* rb, size_t rn) override {
@@ -199,12 +206,13 @@ class LoopbackTransport : public Transport {
  private:
   std::shared_ptr<LoopbackHub> hub_;
   int rank_;
+  std::vector<int> hosts_;
 };
 }  // namespace
 
 std::shared_ptr<LoopbackHub> CreateLoopbackHub(int size) { return std::make_shared<LoopbackHub>(size); }
-std::shared_ptr<Transport> LoopbackEndpoint(std::shared_ptr<LoopbackHub> hub, int rank) {
-  return std::make_shared<LoopbackTransport>(std::move(hub), rank);
+std::shared_ptr<Transport> LoopbackEndpoint(std::shared_ptr<LoopbackHub> hub, int rank, std::vector<int> hosts) {
+  return std::make_shared<LoopbackTransport>(std::move(hub), rank, std::move(hosts));
 }
 
 }  // namespace hvd

@@ -164,7 +164,8 @@ std::shared_ptr<Transport> CreateTcpTransport(int rank, int size, KVStore* store
 // no equivalent of — its multi-rank tests always need real MPI/Gloo processes).
 class LoopbackHub;
 std::shared_ptr<LoopbackHub> CreateLoopbackHub(int size);
-std::shared_ptr<Transport> LoopbackEndpoint(std::shared_ptr<LoopbackHub> hub, int rank);
+// `hosts`: optional host id per rank (unit tests of the two-level planes present one process as several hosts)
+std::shared_ptr<Transport> LoopbackEndpoint(std::shared_ptr<LoopbackHub> hub, int rank, std::vector<int> hosts = {});
 
 // Shared-memory control plane overlay: wraps a base transport whose ranks are
 // all on one host and replaces AllreduceBits/Barrier with atomics on a POSIX
