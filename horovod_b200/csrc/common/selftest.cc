@@ -4,6 +4,10 @@
 // collectives are exercised without any launcher — the reference has no
 // equivalent (all its multi-rank tests need real MPI/Gloo processes).
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <map>
 #include <cmath>
 #include <cstdio>
 #include <future>
@@ -363,6 +367,62 @@ void TestShmPlane(int n) {
   CHECK_T(no_plane.load() == 0 || no_plane.load() == n);
 }
 
+// A REAL socket mesh between the threads of this process (rendezvous through an in-memory KV store): the spinning receives, the
+// all-peers-at-once alltoall, the chunk-pipelined ring with its reducer thread, the chunked chain broadcast and the log-depth
+// bit reduction of tcp_transport.cc / transport.cc / cpu_ops.cc, so that they run under the sanitizer builds too.
+class MemKVStore : public KVStore {
+ public:
+  void Set(const std::string& scope, const std::string& key, const std::string& value) override {
+    std::lock_guard<std::mutex> l(m_);
+    kv_[scope + "/" + key] = value;
+    cv_.notify_all();
+  }
+  std::string Get(const std::string& scope, const std::string& key, double timeout_s) override {
+    std::unique_lock<std::mutex> l(m_);
+    const std::string k = scope + "/" + key;
+    if (!cv_.wait_for(l, std::chrono::duration<double>(timeout_s), [&] { return kv_.count(k) > 0; }))
+      throw TransportError("MemKVStore: timed out waiting for " + k);
+    return kv_[k];
+  }
+
+ private:
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::map<std::string, std::string> kv_;
+};
+
+void TestTcpMesh(int n) {
+  MemKVStore store;
+  static std::atomic<int> serial{0};
+  const std::string scope = "selftest.tcp." + std::to_string(serial.fetch_add(1));
+  std::vector<std::thread> th;
+  std::atomic<int> bad{0}, failed{0};
+  for (int r = 0; r < n; ++r) {
+    th.emplace_back([&, r] {
+      std::shared_ptr<Transport> t;
+      try {
+        t = CreateTcpTransport(r, n, &store, scope, "127.0.0.1", 30.0);
+      } catch (const std::exception& e) { failed++; return; }     // no loopback networking in this sandbox
+      try {
+        PlaneCollectives(t.get(), n, r, bad);
+        // a long allreduce and a long broadcast: pipelined ring steps (when HVD_RING_CHUNK_BYTES is small) / chunked chain
+        const int64_t cnt = 300007;
+        std::vector<float> v(cnt);
+        for (int64_t i = 0; i < cnt; ++i) v[i] = (float)(r + 1) * (float)(i % 3);
+        cpu::Allreduce(t.get(), v.data(), cnt, DataType::FLOAT32, ReduceOp::SUM);
+        for (int64_t i = 0; i < cnt; ++i) if (std::fabs(v[i] - (float)(n * (n + 1) / 2) * (float)(i % 3)) > 1e-3f) { bad++; break; }
+        std::vector<int32_t> x(200003, r == n - 1 ? 4242 : -1);
+        cpu::Broadcast(t.get(), x.data(), (int64_t)x.size() * 4, n - 1);
+        if (x.front() != 4242 || x[100001] != 4242 || x.back() != 4242) bad++;
+        t->Barrier();
+      } catch (const std::exception& e) { bad++; }
+    });
+  }
+  for (auto& t : th) t.join();
+  CHECK_T(bad.load() == 0);
+  CHECK_T(failed.load() == 0 || failed.load() == n);
+}
+
 // The two-level planes (shm inside a "host", loopback queues standing in for the sockets between hosts): hosts x per_host ranks.
 void TestHierPlane(int hosts, int per_host) {
   const int n = hosts * per_host;
@@ -569,6 +629,7 @@ extern "C" int hvd_selftest(int nranks, char* log, int log_len) {
   for (int n : {1, 2, 3, nranks}) { if (n < 1) continue; TestCpuOps(n); TestAdasum(n); }
   for (int n : {2, 3, 5, 6, 7, 8, 11}) TestBitsAmong(n);
   for (int n : {2, 3, 4}) TestShmPlane(n);
+  for (int n : {2, 3, 5}) TestTcpMesh(n);
   TestHierPlane(2, 2);
   TestHierPlane(3, 2);
   TestHierPlane(2, 3);
