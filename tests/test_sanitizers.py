@@ -21,7 +21,7 @@ def test_native_selftest_under_thread_sanitizer():
     env = dict(os.environ, TSAN_OPTIONS='halt_on_error=0 report_signal_unsafe=0 exitcode=66', HOROVOD_LOG_LEVEL='error')
     # second pass: tiny ring chunks (the reducer thread of the pipelined ring runs for every ring step of the self-test's
     # 400 KB allreduce) and the log-depth bit reduction instead of the star
-    for extra in ({}, {'HVD_RING_CHUNK_BYTES': '4096', 'HVD_BITS_TREE_MIN_RANKS': '2'}):
+    for extra in ({}, {'HVD_RING_CHUNK_BYTES': '4096', 'HVD_BITS_TREE_MIN_RANKS': '2'}, {'HVD_TCP_ALLTOALL_CONCURRENT': '0', 'HVD_TCP_SPIN_US': '0'}):
         p = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=dict(env, **extra), timeout=600)
         err = p.stderr.decode(errors='replace')
         if 'FATAL: ThreadSanitizer' in err and 'unexpected memory mapping' in err:
@@ -38,7 +38,7 @@ def test_native_selftest_under_address_and_ub_sanitizers():
     from horovod_b200 import build
     exe = build.build_tsan_selftest(sanitizer='address,undefined')
     env = dict(os.environ, ASAN_OPTIONS='detect_leaks=0 exitcode=67', UBSAN_OPTIONS='print_stacktrace=1', HOROVOD_LOG_LEVEL='error')
-    for extra in ({}, {'HVD_RING_CHUNK_BYTES': '4096', 'HVD_BITS_TREE_MIN_RANKS': '2'}):
+    for extra in ({}, {'HVD_RING_CHUNK_BYTES': '4096', 'HVD_BITS_TREE_MIN_RANKS': '2'}, {'HVD_TCP_ALLTOALL_CONCURRENT': '0', 'HVD_TCP_SPIN_US': '0'}):
         p = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=dict(env, **extra), timeout=900)
         err = p.stderr.decode(errors='replace')
         if 'AddressSanitizer' in err and ('Shadow memory range interleaves' in err or 'failed to allocate' in err):
