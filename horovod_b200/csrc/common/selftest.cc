@@ -296,6 +296,13 @@ void PlaneCollectives(Transport* tp, int n, int r, std::atomic<int>& bad) {
   uint64_t wa = ~0ull, wo = 0;
   for (int p = 0; p < n; ++p) { wa &= ~(1ull << p); wo |= 1ull << p; }
   if (a != wa || o != wo) bad++;
+  // integer tables (small: through the slots where there are some; larger than a slot's words: the star of the base transport)
+  for (int per : {3, 700}) {
+    std::vector<int64_t> mine_i((size_t)per), all_i((size_t)per * (size_t)n, -1);
+    for (int i = 0; i < per; ++i) mine_i[(size_t)i] = (int64_t)r * 100000 + i;
+    t->AllgatherInts(mine_i.data(), per, all_i.data());
+    for (int p = 0; p < n; ++p) for (int i = 0; i < per; ++i) if (all_i[(size_t)p * (size_t)per + (size_t)i] != (int64_t)p * 100000 + i) { bad++; break; }
+  }
   // allreduce over several pieces
   const int64_t cnt = 10007;
   std::vector<float> v(cnt);

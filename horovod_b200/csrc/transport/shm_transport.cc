@@ -261,6 +261,23 @@ class ShmControlTransport : public Transport {
     }
   }
   void Barrier() override { AllreduceBits(nullptr, 0, nullptr, 0); }
+  // Small integer tables (alltoall split matrices, IPC handle records, topology at init) through the same slots and round
+  // counter as the bit vectors: one publication + n - 1 reads instead of a star over sockets.
+  void AllgatherInts(const int64_t* mine, int n, int64_t* out) override {
+    if (size() == 1 || n > kMaxWords || n <= 0) { Transport::AllgatherInts(mine, n, out); return; }
+    const uint64_t k = ++round_;
+    const int buf = (int)(k & 1);
+    Slot& me = seg_->slots[rank()];
+    memcpy(me.data[buf], mine, (size_t)n * 8);
+    me.seq.store(k, std::memory_order_release);
+    memcpy(out + (size_t)rank() * (size_t)n, mine, (size_t)n * 8);
+    for (int r = 0; r < size(); ++r) {
+      if (r == rank()) continue;
+      Slot& s = seg_->slots[r];
+      WaitSeq(s, k, r);
+      memcpy(out + (size_t)r * (size_t)n, s.data[buf], (size_t)n * 8);
+    }
+  }
 
  private:
   static void WaitSeq(Slot& s, uint64_t k, int r) { WaitSlot(s, k, r); }
