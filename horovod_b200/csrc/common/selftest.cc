@@ -296,6 +296,26 @@ void PlaneCollectives(Transport* tp, int n, int r, std::atomic<int>& bad) {
   uint64_t wa = ~0ull, wo = 0;
   for (int p = 0; p < n; ++p) { wa &= ~(1ull << p); wo |= 1ull << p; }
   if (a != wa || o != wo) bad++;
+  // coordinator round: variable-length blobs to a root and one blob back; `big` makes one payload larger than an 8 KiB slot, which
+  // sends every rank down the socket path together
+  for (int big : {0, 1}) {
+    for (int root : {0, n - 1}) {
+      std::vector<uint8_t> mine((size_t)(10 + 37 * r + (big && r == n - 1 ? 20000 : 0)), (uint8_t)(r + 1));
+      std::vector<std::vector<uint8_t>> all;
+      t->GatherBytes(mine, &all, root);
+      if (r == root) {
+        if ((int)all.size() != n) bad++;
+        else for (int p = 0; p < n; ++p) {
+          const size_t want = (size_t)(10 + 37 * p + (big && p == n - 1 ? 20000 : 0));
+          if (all[(size_t)p].size() != want || (want && (all[(size_t)p].front() != (uint8_t)(p + 1) || all[(size_t)p].back() != (uint8_t)(p + 1)))) bad++;
+        }
+      }
+      std::vector<uint8_t> resp;
+      if (r == root) resp.assign((size_t)(big ? 30000 : 123), (uint8_t)(200 + root % 50));
+      t->BcastBytes(&resp, root);
+      if (resp.size() != (size_t)(big ? 30000 : 123) || resp.front() != (uint8_t)(200 + root % 50) || resp.back() != (uint8_t)(200 + root % 50)) bad++;
+    }
+  }
   // integer tables (small: through the slots where there are some; larger than a slot's words: the star of the base transport)
   for (int per : {3, 700}) {
     std::vector<int64_t> mine_i((size_t)per), all_i((size_t)per * (size_t)n, -1);

@@ -261,6 +261,50 @@ class ShmControlTransport : public Transport {
     }
   }
   void Barrier() override { AllreduceBits(nullptr, 0, nullptr, 0); }
+  // The coordinator round of uncached requests (names, shapes -> responses) through the data slots: every rank writes
+  // [length][payload] into its slot, one barrier, the root reads; a payload that does not fit a slot is announced in the header
+  // and EVERY rank (all of them read all headers) falls back to the socket path together.
+  void GatherBytes(const std::vector<uint8_t>& mine, std::vector<std::vector<uint8_t>>* all, int root) override {
+    if (!data_ || size() == 1) { Transport::GatherBytes(mine, all, root); return; }
+    const int half = (int)(ShmNextPiece() & 1);
+    const size_t cap = slot_bytes_ - 8;
+    char* slot = data_ + ((size_t)rank() * 2 + (size_t)half) * slot_bytes_;
+    const int64_t len = (int64_t)mine.size();
+    memcpy(slot, &len, 8);
+    if (len > 0 && (size_t)len <= cap) memcpy(slot + 8, mine.data(), (size_t)len);
+    Barrier();
+    bool fits = true;
+    for (int r = 0; r < size(); ++r) {
+      int64_t l = 0;
+      memcpy(&l, data_ + ((size_t)r * 2 + (size_t)half) * slot_bytes_, 8);
+      if ((size_t)l > cap) fits = false;
+    }
+    if (!fits) { Transport::GatherBytes(mine, all, root); return; }
+    if (rank() != root) return;
+    all->assign((size_t)size(), {});
+    for (int r = 0; r < size(); ++r) {
+      const char* s = data_ + ((size_t)r * 2 + (size_t)half) * slot_bytes_;
+      int64_t l = 0;
+      memcpy(&l, s, 8);
+      (*all)[(size_t)r].assign((const uint8_t*)s + 8, (const uint8_t*)s + 8 + l);
+    }
+  }
+  void BcastBytes(std::vector<uint8_t>* buf, int root) override {
+    if (!data_ || size() == 1) { Transport::BcastBytes(buf, root); return; }
+    const int half = (int)(ShmNextPiece() & 1);
+    const size_t cap = slot_bytes_ - 8;
+    char* slot = data_ + ((size_t)root * 2 + (size_t)half) * slot_bytes_;
+    if (rank() == root) {
+      const int64_t len = (int64_t)buf->size();
+      memcpy(slot, &len, 8);
+      if (len > 0 && (size_t)len <= cap) memcpy(slot + 8, buf->data(), (size_t)len);
+    }
+    Barrier();
+    int64_t len = 0;
+    memcpy(&len, slot, 8);
+    if ((size_t)len > cap) { Transport::BcastBytes(buf, root); return; }
+    if (rank() != root) buf->assign((const uint8_t*)slot + 8, (const uint8_t*)slot + 8 + len);
+  }
   // Small integer tables (alltoall split matrices, IPC handle records, topology at init) through the same slots and round
   // counter as the bit vectors: one publication + n - 1 reads instead of a star over sockets.
   void AllgatherInts(const int64_t* mine, int n, int64_t* out) override {
