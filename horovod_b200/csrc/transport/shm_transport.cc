@@ -131,6 +131,51 @@ void WaitSeqReaches(std::atomic<uint64_t>& seq, const int32_t& owner_pid, uint64
 char* MapNamed(const std::string& name, size_t bytes, bool create);
 size_t DataSlotBytes();
 
+// Variable-length blobs to a root / from a root through per-rank data slots (rank i of `t` owns slot i): every rank writes
+// [length][payload] into its slot, one barrier, the root reads.  A payload that does not fit a slot is announced in the header
+// and EVERY rank (all of them read all headers) returns false together — the caller then takes the socket path.
+bool SlotGatherBytes(Transport* t, char* data, size_t slot_bytes, const std::vector<uint8_t>& mine, std::vector<std::vector<uint8_t>>* all,
+                     int root) {
+  const int n = t->size(), me = t->rank();
+  const int half = (int)(t->ShmNextPiece() & 1);
+  const size_t cap = slot_bytes - 8;
+  auto slot_of = [&](int r) { return data + ((size_t)r * 2 + (size_t)half) * slot_bytes; };
+  const int64_t len = (int64_t)mine.size();
+  memcpy(slot_of(me), &len, 8);
+  if (len > 0 && (size_t)len <= cap) memcpy(slot_of(me) + 8, mine.data(), (size_t)len);
+  t->Barrier();
+  for (int r = 0; r < n; ++r) {
+    int64_t l = 0;
+    memcpy(&l, slot_of(r), 8);
+    if ((size_t)l > cap) return false;
+  }
+  if (me != root) return true;
+  all->assign((size_t)n, {});
+  for (int r = 0; r < n; ++r) {
+    int64_t l = 0;
+    memcpy(&l, slot_of(r), 8);
+    (*all)[(size_t)r].assign((const uint8_t*)slot_of(r) + 8, (const uint8_t*)slot_of(r) + 8 + l);
+  }
+  return true;
+}
+
+bool SlotBcastBytes(Transport* t, char* data, size_t slot_bytes, std::vector<uint8_t>* buf, int root) {
+  const int half = (int)(t->ShmNextPiece() & 1);
+  const size_t cap = slot_bytes - 8;
+  char* slot = data + ((size_t)root * 2 + (size_t)half) * slot_bytes;
+  if (t->rank() == root) {
+    const int64_t len = (int64_t)buf->size();
+    memcpy(slot, &len, 8);
+    if (len > 0 && (size_t)len <= cap) memcpy(slot + 8, buf->data(), (size_t)len);
+  }
+  t->Barrier();
+  int64_t len = 0;
+  memcpy(&len, slot, 8);
+  if ((size_t)len > cap) return false;
+  if (t->rank() != root) buf->assign((const uint8_t*)slot + 8, (const uint8_t*)slot + 8 + len);
+  return true;
+}
+
 // A process set of a single-host job: point-to-point traffic goes through the parent, the per-cycle bit exchange and the
 // barrier run on the set's own channel of the parent's segment.
 class ShmSubTransport : public SubTransport {
@@ -157,6 +202,12 @@ class ShmSubTransport : public SubTransport {
     }
   }
   void Barrier() override { AllreduceBits(nullptr, 0, nullptr, 0); }
+  void GatherBytes(const std::vector<uint8_t>& mine, std::vector<std::vector<uint8_t>>* all, int root) override {
+    if (!data_ || size() == 1 || !SlotGatherBytes(this, data_, slot_bytes_, mine, all, root)) Transport::GatherBytes(mine, all, root);
+  }
+  void BcastBytes(std::vector<uint8_t>* buf, int root) override {
+    if (!data_ || size() == 1 || !SlotBcastBytes(this, data_, slot_bytes_, buf, root)) Transport::BcastBytes(buf, root);
+  }
   std::string Describe() const override {
     return "control: shared memory channel " + std::to_string(channel_) + " (" + std::to_string(size()) + " of the host's ranks); host data: " +
            (data_ ? "shared-memory slots of " + std::to_string(slot_bytes_) + " bytes" : std::string("ring over the base transport"));
@@ -261,49 +312,12 @@ class ShmControlTransport : public Transport {
     }
   }
   void Barrier() override { AllreduceBits(nullptr, 0, nullptr, 0); }
-  // The coordinator round of uncached requests (names, shapes -> responses) through the data slots: every rank writes
-  // [length][payload] into its slot, one barrier, the root reads; a payload that does not fit a slot is announced in the header
-  // and EVERY rank (all of them read all headers) falls back to the socket path together.
+  // The coordinator round of uncached requests (names, shapes -> responses) through the data slots (SlotGatherBytes).
   void GatherBytes(const std::vector<uint8_t>& mine, std::vector<std::vector<uint8_t>>* all, int root) override {
-    if (!data_ || size() == 1) { Transport::GatherBytes(mine, all, root); return; }
-    const int half = (int)(ShmNextPiece() & 1);
-    const size_t cap = slot_bytes_ - 8;
-    char* slot = data_ + ((size_t)rank() * 2 + (size_t)half) * slot_bytes_;
-    const int64_t len = (int64_t)mine.size();
-    memcpy(slot, &len, 8);
-    if (len > 0 && (size_t)len <= cap) memcpy(slot + 8, mine.data(), (size_t)len);
-    Barrier();
-    bool fits = true;
-    for (int r = 0; r < size(); ++r) {
-      int64_t l = 0;
-      memcpy(&l, data_ + ((size_t)r * 2 + (size_t)half) * slot_bytes_, 8);
-      if ((size_t)l > cap) fits = false;
-    }
-    if (!fits) { Transport::GatherBytes(mine, all, root); return; }
-    if (rank() != root) return;
-    all->assign((size_t)size(), {});
-    for (int r = 0; r < size(); ++r) {
-      const char* s = data_ + ((size_t)r * 2 + (size_t)half) * slot_bytes_;
-      int64_t l = 0;
-      memcpy(&l, s, 8);
-      (*all)[(size_t)r].assign((const uint8_t*)s + 8, (const uint8_t*)s + 8 + l);
-    }
+    if (!data_ || size() == 1 || !SlotGatherBytes(this, data_, slot_bytes_, mine, all, root)) Transport::GatherBytes(mine, all, root);
   }
   void BcastBytes(std::vector<uint8_t>* buf, int root) override {
-    if (!data_ || size() == 1) { Transport::BcastBytes(buf, root); return; }
-    const int half = (int)(ShmNextPiece() & 1);
-    const size_t cap = slot_bytes_ - 8;
-    char* slot = data_ + ((size_t)root * 2 + (size_t)half) * slot_bytes_;
-    if (rank() == root) {
-      const int64_t len = (int64_t)buf->size();
-      memcpy(slot, &len, 8);
-      if (len > 0 && (size_t)len <= cap) memcpy(slot + 8, buf->data(), (size_t)len);
-    }
-    Barrier();
-    int64_t len = 0;
-    memcpy(&len, slot, 8);
-    if ((size_t)len > cap) { Transport::BcastBytes(buf, root); return; }
-    if (rank() != root) buf->assign((const uint8_t*)slot + 8, (const uint8_t*)slot + 8 + len);
+    if (!data_ || size() == 1 || !SlotBcastBytes(this, data_, slot_bytes_, buf, root)) Transport::BcastBytes(buf, root);
   }
   // Small integer tables (alltoall split matrices, IPC handle records, topology at init) through the same slots and round
   // counter as the bit vectors: one publication + n - 1 reads instead of a star over sockets.
