@@ -131,27 +131,27 @@ void WaitSeqReaches(std::atomic<uint64_t>& seq, const int32_t& owner_pid, uint64
 char* MapNamed(const std::string& name, size_t bytes, bool create);
 size_t DataSlotBytes();
 
-// Variable-length blobs to a root / from a root through per-rank data slots (rank i of `t` owns slot i): every rank writes
-// [length][payload] into its slot, one barrier, the root reads.  A payload that does not fit a slot is announced in the header
-// and EVERY rank (all of them read all headers) returns false together — the caller then takes the socket path.
-bool SlotGatherBytes(Transport* t, char* data, size_t slot_bytes, const std::vector<uint8_t>& mine, std::vector<std::vector<uint8_t>>* all,
-                     int root) {
-  const int n = t->size(), me = t->rank();
-  const int half = (int)(t->ShmNextPiece() & 1);
+// Variable-length blobs to a root slot / from a root slot through per-member data slots: every member writes [length][payload]
+// into its slot, one barrier, the root reads.  A payload that does not fit a slot is announced in the header and EVERY member
+// (all of them read all headers) returns false together — the caller then takes the socket path.  `me` / `root` are slot
+// indices, `barrier` synchronises exactly the `nslots` members, `half` comes from the communicator's piece counter.
+template <typename BarrierFn>
+bool SlotGather(int me, int nslots, int root, int half, BarrierFn barrier, char* data, size_t slot_bytes, const std::vector<uint8_t>& mine,
+                std::vector<std::vector<uint8_t>>* all) {
   const size_t cap = slot_bytes - 8;
   auto slot_of = [&](int r) { return data + ((size_t)r * 2 + (size_t)half) * slot_bytes; };
   const int64_t len = (int64_t)mine.size();
   memcpy(slot_of(me), &len, 8);
   if (len > 0 && (size_t)len <= cap) memcpy(slot_of(me) + 8, mine.data(), (size_t)len);
-  t->Barrier();
-  for (int r = 0; r < n; ++r) {
+  barrier();
+  for (int r = 0; r < nslots; ++r) {
     int64_t l = 0;
     memcpy(&l, slot_of(r), 8);
     if ((size_t)l > cap) return false;
   }
   if (me != root) return true;
-  all->assign((size_t)n, {});
-  for (int r = 0; r < n; ++r) {
+  all->assign((size_t)nslots, {});
+  for (int r = 0; r < nslots; ++r) {
     int64_t l = 0;
     memcpy(&l, slot_of(r), 8);
     (*all)[(size_t)r].assign((const uint8_t*)slot_of(r) + 8, (const uint8_t*)slot_of(r) + 8 + l);
@@ -159,21 +159,32 @@ bool SlotGatherBytes(Transport* t, char* data, size_t slot_bytes, const std::vec
   return true;
 }
 
-bool SlotBcastBytes(Transport* t, char* data, size_t slot_bytes, std::vector<uint8_t>* buf, int root) {
-  const int half = (int)(t->ShmNextPiece() & 1);
+template <typename BarrierFn>
+bool SlotBcast(int me, int root, int half, BarrierFn barrier, char* data, size_t slot_bytes, std::vector<uint8_t>* buf) {
   const size_t cap = slot_bytes - 8;
   char* slot = data + ((size_t)root * 2 + (size_t)half) * slot_bytes;
-  if (t->rank() == root) {
+  if (me == root) {
     const int64_t len = (int64_t)buf->size();
     memcpy(slot, &len, 8);
     if (len > 0 && (size_t)len <= cap) memcpy(slot + 8, buf->data(), (size_t)len);
   }
-  t->Barrier();
+  barrier();
   int64_t len = 0;
   memcpy(&len, slot, 8);
   if ((size_t)len > cap) return false;
-  if (t->rank() != root) buf->assign((const uint8_t*)slot + 8, (const uint8_t*)slot + 8 + len);
+  if (me != root) buf->assign((const uint8_t*)slot + 8, (const uint8_t*)slot + 8 + len);
   return true;
+}
+
+// the whole communicator shares the slots (rank i owns slot i)
+bool SlotGatherBytes(Transport* t, char* data, size_t slot_bytes, const std::vector<uint8_t>& mine, std::vector<std::vector<uint8_t>>* all,
+                     int root) {
+  const int half = (int)(t->ShmNextPiece() & 1);
+  return SlotGather(t->rank(), t->size(), root, half, [t] { t->Barrier(); }, data, slot_bytes, mine, all);
+}
+bool SlotBcastBytes(Transport* t, char* data, size_t slot_bytes, std::vector<uint8_t>* buf, int root) {
+  const int half = (int)(t->ShmNextPiece() & 1);
+  return SlotBcast(t->rank(), root, half, [t] { t->Barrier(); }, data, slot_bytes, buf);
 }
 
 // A process set of a single-host job: point-to-point traffic goes through the parent, the per-cycle bit exchange and the
@@ -458,6 +469,97 @@ class HierShmControlTransport : public Transport {
     result.seq.store(k, std::memory_order_release);
   }
   void Barrier() override { AllreduceBits(nullptr, 0, nullptr, 0); }
+
+  // Coordinator round, two-level: the ranks of a host hand their blobs to the host leader through the host's data slots, the
+  // leaders send ONE message each to the root (H - 1 messages at the root instead of N - 1); responses travel the other way.
+  // Needs the root to be a host leader (the coordinator, rank 0, is) and the host data plane; otherwise the plain star.
+  void GatherBytes(const std::vector<uint8_t>& mine, std::vector<std::vector<uint8_t>>* all, int root) override {
+    if (!data_ || std::find(leaders_.begin(), leaders_.end(), root) == leaders_.end()) { Transport::GatherBytes(mine, all, root); return; }
+    const int L = (int)local_.size();
+    std::vector<std::vector<uint8_t>> loc;
+    const int half = (int)(ShmNextPiece() & 1);
+    if (!SlotGather(li_, L, 0, half, [this] { LocalBarrier(); }, data_, slot_bytes_, mine, &loc)) {
+      // a blob of this host does not fit a slot: the host's ranks (they all saw the same headers) use their sockets
+      if (li_ == 0) {
+        loc.assign((size_t)L, {});
+        loc[0] = mine;
+        for (int j = 1; j < L; ++j) {
+          int64_t n = 0;
+          base_->Recv(local_[(size_t)j], &n, sizeof n);
+          loc[(size_t)j].resize((size_t)n);
+          if (n) base_->Recv(local_[(size_t)j], loc[(size_t)j].data(), (size_t)n);
+        }
+      } else {
+        int64_t n = (int64_t)mine.size();
+        base_->Send(local_[0], &n, sizeof n);
+        if (n) base_->Send(local_[0], mine.data(), mine.size());
+      }
+    }
+    if (li_ != 0) return;
+    if (rank() == root) {
+      all->assign((size_t)size(), {});
+      for (int j = 0; j < L; ++j) (*all)[(size_t)local_[(size_t)j]] = std::move(loc[(size_t)j]);
+      for (int leader : leaders_) {
+        if (leader == root) continue;
+        int64_t n = 0;
+        base_->Recv(leader, &n, sizeof n);
+        std::vector<uint8_t> pack((size_t)n);
+        if (n) base_->Recv(leader, pack.data(), (size_t)n);
+        size_t pos = 0;                                  // [rank:int32][len:int64][payload] ...
+        while (pos + 12 <= pack.size()) {
+          int32_t rk = 0; int64_t len = 0;
+          memcpy(&rk, pack.data() + pos, 4); memcpy(&len, pack.data() + pos + 4, 8);
+          pos += 12;
+          if (rk < 0 || rk >= size() || pos + (size_t)len > pack.size()) throw TransportError("malformed gather pack from host leader " + std::to_string(leader));
+          (*all)[(size_t)rk].assign(pack.begin() + (long)pos, pack.begin() + (long)(pos + (size_t)len));
+          pos += (size_t)len;
+        }
+      }
+    } else {
+      std::vector<uint8_t> pack;
+      for (int j = 0; j < L; ++j) {
+        const int32_t rk = (int32_t)local_[(size_t)j];
+        const int64_t len = (int64_t)loc[(size_t)j].size();
+        const size_t at = pack.size();
+        pack.resize(at + 12 + (size_t)len);
+        memcpy(pack.data() + at, &rk, 4); memcpy(pack.data() + at + 4, &len, 8);
+        if (len) memcpy(pack.data() + at + 12, loc[(size_t)j].data(), (size_t)len);
+      }
+      int64_t n = (int64_t)pack.size();
+      base_->Send(root, &n, sizeof n);
+      if (n) base_->Send(root, pack.data(), pack.size());
+    }
+  }
+  void BcastBytes(std::vector<uint8_t>* buf, int root) override {
+    if (!data_ || std::find(leaders_.begin(), leaders_.end(), root) == leaders_.end()) { Transport::BcastBytes(buf, root); return; }
+    if (li_ == 0) {
+      if (rank() == root) {
+        int64_t n = (int64_t)buf->size();
+        for (int leader : leaders_) {
+          if (leader == root) continue;
+          base_->Send(leader, &n, sizeof n);
+          if (n) base_->Send(leader, buf->data(), buf->size());
+        }
+      } else {
+        int64_t n = 0;
+        base_->Recv(root, &n, sizeof n);
+        buf->resize((size_t)n);
+        if (n) base_->Recv(root, buf->data(), (size_t)n);
+      }
+    }
+    const int L = (int)local_.size();
+    const int half = (int)(ShmNextPiece() & 1);
+    if (SlotBcast(li_, 0, half, [this] { LocalBarrier(); }, data_, slot_bytes_, buf)) return;
+    if (li_ == 0) {
+      int64_t n = (int64_t)buf->size();
+      for (int j = 1; j < L; ++j) { base_->Send(local_[(size_t)j], &n, sizeof n); if (n) base_->Send(local_[(size_t)j], buf->data(), buf->size()); }
+    } else {
+      int64_t n = 0;
+      base_->Recv(local_[0], &n, sizeof n);
+      buf->resize((size_t)n);
+      if (n) base_->Recv(local_[0], buf->data(), (size_t)n);
+    }
+  }
   std::string Describe() const override {
     return "control: two-level (shared memory among the " + std::to_string(local_.size()) + " ranks of this host, " +
            std::to_string(leaders_.size()) + " host leaders over the base transport); host data: " +
