@@ -73,6 +73,7 @@ double RecvTimeoutSeconds() {
   static const double t = [] {
     const char* e = getenv("HVD_TCP_TIMEOUT_SECONDS");
     if (!e) e = getenv("HVD_SHM_TIMEOUT_SECONDS");
+    if (!e) e = getenv("HOROVOD_GLOO_TIMEOUT_SECONDS");    // hvdrun --gloo-timeout-seconds: what the reference's Gloo ops honour
     return e ? std::max(0.0, atof(e)) : 0.0;
   }();
   return t;
