@@ -240,7 +240,8 @@ def parse_args():
     gl.add_argument('--mpi-threads-disable', action=make_override_true_action(override_args))
     gl.add_argument('--no-mpi-threads-disable', dest='mpi_threads_disable', action=make_override_false_action(override_args))
     group_lib.add_argument('--gloo-timeout-seconds', action=make_override_action(override_args), type=int,
-                           help='Seconds a rank waits for its peers during bootstrap / rendezvous before giving up (default 60).')
+                           help='Seconds a rank waits for its peers during bootstrap / rendezvous before giving up (default 60); when given, '
+                                'a socket receive of a running job that makes no progress for this long fails as well.')
     group_lib.add_argument('--mpi-args', action='store', dest='mpi_args', help='Extra MPI arguments to pass to mpirun.')
     group_lib.add_argument('--tcp', action='store_true', dest='tcp_flag', help='If this flag is set, only TCP is used for communication.')
     group_lib.add_argument('--binding-args', action='store', dest='binding_args', help='Process binding arguments.')
