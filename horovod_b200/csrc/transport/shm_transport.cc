@@ -560,6 +560,44 @@ class HierShmControlTransport : public Transport {
       if (n) base_->Recv(local_[0], buf->data(), (size_t)n);
     }
   }
+  // Integer tables, two-level: host slots -> leader, leaders exchange whole host rows through the first leader, full table back
+  // through the host slots (needs the homogeneous layout the data plane is built for; otherwise the star of the base class).
+  void AllgatherInts(const int64_t* mine, int n, int64_t* out) override {
+    const int L = (int)local_.size(), H = (int)leaders_.size(), N = size();
+    if (!data_ || column_.empty() || n <= 0 || (size_t)N * (size_t)n * 8 > slot_bytes_) { Transport::AllgatherInts(mine, n, out); return; }
+    auto slot_of = [&](int j, int half) { return (int64_t*)(data_ + ((size_t)j * 2 + (size_t)half) * slot_bytes_); };
+    int x = 0;                                           // my host's position in the column tables
+    while (column_[(size_t)li_][(size_t)x] != rank()) ++x;
+    int half = (int)(ShmNextPiece() & 1);
+    memcpy(slot_of(li_, half), mine, (size_t)n * 8);
+    LocalBarrier();
+    std::vector<int64_t> table((size_t)N * (size_t)n);
+    if (li_ == 0) {
+      std::vector<int64_t> row((size_t)L * (size_t)n);
+      for (int j = 0; j < L; ++j) memcpy(row.data() + (size_t)j * (size_t)n, slot_of(j, half), (size_t)n * 8);
+      auto place = [&](int host, const int64_t* r) {
+        for (int j = 0; j < L; ++j) memcpy(table.data() + (size_t)column_[(size_t)j][(size_t)host] * (size_t)n, r + (size_t)j * (size_t)n, (size_t)n * 8);
+      };
+      if (rank() == leaders_[0]) {
+        place(x, row.data());
+        std::vector<int64_t> other((size_t)L * (size_t)n);
+        for (int h = 1; h < H; ++h) {
+          base_->Recv(leaders_[(size_t)h], other.data(), other.size() * 8);
+          int hx = 0;                                    // which column position that leader's host has
+          while (column_[0][(size_t)hx] != leaders_[(size_t)h]) ++hx;
+          place(hx, other.data());
+        }
+        for (int h = 1; h < H; ++h) base_->Send(leaders_[(size_t)h], table.data(), table.size() * 8);
+      } else {
+        base_->Send(leaders_[0], row.data(), row.size() * 8);
+        base_->Recv(leaders_[0], table.data(), table.size() * 8);
+      }
+    }
+    half = (int)(ShmNextPiece() & 1);
+    if (li_ == 0) memcpy(slot_of(0, half), table.data(), table.size() * 8);
+    LocalBarrier();
+    memcpy(out, slot_of(0, half), (size_t)N * (size_t)n * 8);
+  }
   std::string Describe() const override {
     return "control: two-level (shared memory among the " + std::to_string(local_.size()) + " ranks of this host, " +
            std::to_string(leaders_.size()) + " host leaders over the base transport); host data: " +
