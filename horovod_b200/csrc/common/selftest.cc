@@ -501,8 +501,10 @@ void TestAdasum(int n) {
 }
 
 // N engines on the loopback hub: negotiation, cache fast path, fusion, errors, join.
-void TestEngines(int n) {
+void TestEngines(int n, bool shm_planes = false) {
   auto hub = CreateLoopbackHub(n);
+  static std::atomic<int> serial{0};
+  const std::string seg = "hvd-selftest-e-" + std::to_string((long)getpid()) + "-" + std::to_string(serial.fetch_add(1));
   std::vector<std::unique_ptr<Engine>> engines;
   for (int r = 0; r < n; ++r) engines.emplace_back(new Engine());
   std::vector<std::thread> th;
@@ -510,7 +512,10 @@ void TestEngines(int n) {
   for (int r = 0; r < n; ++r) {
     th.emplace_back([&, r] {
       InitConfig cfg;
-      cfg.rank = r; cfg.size = n; cfg.local_rank = r; cfg.local_size = n; cfg.transport = LoopbackEndpoint(hub, r);
+      cfg.rank = r; cfg.size = n; cfg.local_rank = r; cfg.local_size = n;
+      // with shm_planes the engines negotiate and move host tensors the way the ranks of one host do (bit vectors, coordinator
+      // round and data through the shared-memory segments)
+      cfg.transport = shm_planes ? WrapWithShmControl(LoopbackEndpoint(hub, r), seg) : LoopbackEndpoint(hub, r);
       Engine& e = *engines[r];
       if (!e.Init(cfg).ok()) { bad++; return; }
       auto run_allreduce = [&](const std::string& name, std::vector<float>& v, ReduceOp op) -> Status {
@@ -661,6 +666,7 @@ extern "C" int hvd_selftest(int nranks, char* log, int log_len) {
   TestHierPlane(3, 2);
   TestHierPlane(2, 3);
   TestEngines(nranks);
+  TestEngines(nranks, true);
   TestEngines(1);
   std::string s = g_log.str();
   if (log && log_len > 0) { snprintf(log, log_len, "%s", s.c_str()); }
