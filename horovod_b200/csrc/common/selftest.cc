@@ -501,7 +501,7 @@ void TestAdasum(int n) {
 }
 
 // N engines on the loopback hub: negotiation, cache fast path, fusion, errors, join.
-void TestEngines(int n, bool shm_planes = false) {
+void TestEngines(int n, int planes = 0) {   // 0: loopback only, 1: one host's shm planes, 2: two-level planes (n / 2 "hosts" of 2 ranks)
   auto hub = CreateLoopbackHub(n);
   static std::atomic<int> serial{0};
   const std::string seg = "hvd-selftest-e-" + std::to_string((long)getpid()) + "-" + std::to_string(serial.fetch_add(1));
@@ -515,7 +515,13 @@ void TestEngines(int n, bool shm_planes = false) {
       cfg.rank = r; cfg.size = n; cfg.local_rank = r; cfg.local_size = n;
       // with shm_planes the engines negotiate and move host tensors the way the ranks of one host do (bit vectors, coordinator
       // round and data through the shared-memory segments)
-      cfg.transport = shm_planes ? WrapWithShmControl(LoopbackEndpoint(hub, r), seg) : LoopbackEndpoint(hub, r);
+      if (planes == 2) {
+        std::vector<int> table((size_t)n);
+        for (int q = 0; q < n; ++q) table[(size_t)q] = q / 2;
+        cfg.transport = WrapWithHierarchicalControl(LoopbackEndpoint(hub, r, table), seg);
+      } else {
+        cfg.transport = planes == 1 ? WrapWithShmControl(LoopbackEndpoint(hub, r), seg) : LoopbackEndpoint(hub, r);
+      }
       Engine& e = *engines[r];
       if (!e.Init(cfg).ok()) { bad++; return; }
       auto run_allreduce = [&](const std::string& name, std::vector<float>& v, ReduceOp op) -> Status {
@@ -666,7 +672,8 @@ extern "C" int hvd_selftest(int nranks, char* log, int log_len) {
   TestHierPlane(3, 2);
   TestHierPlane(2, 3);
   TestEngines(nranks);
-  TestEngines(nranks, true);
+  TestEngines(nranks, 1);
+  if (nranks >= 4 && nranks % 2 == 0) TestEngines(nranks, 2);
   TestEngines(1);
   std::string s = g_log.str();
   if (log && log_len > 0) { snprintf(log, log_len, "%s", s.c_str()); }
