@@ -119,6 +119,10 @@ def run_elastic(fn, args=(), kwargs=None, num_proc=None, min_num_proc=None, max_
 
     try:
         pool.wait_for(min_np, start_timeout)
+        try:                                      # the job may start with min_np tasks; give the rest a moment to dial in first
+            pool.wait_for(num_proc, min(10.0, float(start_timeout)))
+        except TimeoutError:
+            pass
         extra = {'cooldown_range': cooldown_range} if cooldown_range else {}
         settings = _ElasticExecutor.create_settings(min_num_proc=min_np, max_num_proc=max_np, reset_limit=reset_limit,
                                                     elastic_timeout=elastic_timeout or 600, timeout_s=start_timeout, nics=nics, **extra)
