@@ -191,8 +191,12 @@ bool SlotBcastBytes(Transport* t, char* data, size_t slot_bytes, std::vector<uin
 // barrier run on the set's own channel of the parent's segment.
 class ShmSubTransport : public SubTransport {
  public:
-  ShmSubTransport(Transport* parent, std::vector<int> ranks, int my_index, Segment* seg, int channel)
-      : SubTransport(parent, std::move(ranks), my_index), seg_(seg), channel_(channel) {}
+  // `slots[i]`: index of member i in the segment's slot arrays (default: its rank in the parent — single-host jobs; the
+  // two-level plane passes the members' LOCAL indices, its segment being per host)
+  ShmSubTransport(Transport* parent, std::vector<int> ranks, int my_index, Segment* seg, int channel, std::vector<int> slots = {})
+      : SubTransport(parent, std::move(ranks), my_index), seg_(seg), channel_(channel), slots_(std::move(slots)) {
+    if (slots_.empty()) slots_ = ranks_;
+  }
   void AllreduceBits(uint64_t* and_words, int n_and, uint64_t* or_words, int n_or) override {
     const int n = n_and + n_or;
     if (size() == 1) return;
@@ -200,14 +204,14 @@ class ShmSubTransport : public SubTransport {
     const uint64_t k = ++round_;
     const int buf = (int)(k & 1);
     SubSlot* row = seg_->sub[channel_];
-    SubSlot& me = row[ranks_[my_]];
+    SubSlot& me = row[slots_[(size_t)my_]];
     if (n_and) memcpy(me.data[buf], and_words, (size_t)n_and * 8);
     if (n_or) memcpy(me.data[buf] + n_and, or_words, (size_t)n_or * 8);
     me.seq.store(k, std::memory_order_release);
     for (int i = 0; i < size(); ++i) {
       if (i == my_) continue;
-      SubSlot& s = row[ranks_[i]];
-      WaitSeqReaches(s.seq, seg_->slots[ranks_[i]].pid, k, ranks_[i]);
+      SubSlot& s = row[slots_[(size_t)i]];
+      WaitSeqReaches(s.seq, seg_->slots[slots_[(size_t)i]].pid, k, ranks_[i]);
       for (int w = 0; w < n_and; ++w) and_words[w] &= s.data[buf][w];
       for (int w = 0; w < n_or; ++w) or_words[w] |= s.data[buf][n_and + w];
     }
@@ -253,6 +257,7 @@ class ShmSubTransport : public SubTransport {
  private:
   Segment* seg_;
   int channel_;
+  std::vector<int> slots_;
   uint64_t round_ = 0;
   char* data_ = nullptr;
   size_t data_bytes_ = 0, slot_bytes_ = 0;
@@ -409,6 +414,25 @@ class HierShmControlTransport : public Transport {
     return true;
   }
   uint64_t ShmNextPiece() override { return piece_++; }
+  // A process set whose members all live on ONE host negotiates and moves host tensors through that host's segment (own
+  // channel, own data slots), like a process set of a single-host job; sets that span hosts stay on the sockets.
+  std::shared_ptr<Transport> Split(const std::vector<int>& ranks) override {
+    const int channel = next_channel_++;                         // advances on every rank for every set
+    auto it = std::find(ranks.begin(), ranks.end(), rank());
+    if (it == ranks.end()) return nullptr;
+    const int idx = (int)(it - ranks.begin());
+    std::vector<int> slots;
+    for (int r : ranks) {
+      auto at = std::find(local_.begin(), local_.end(), r);
+      if (at == local_.end()) break;
+      slots.push_back((int)(at - local_.begin()));
+    }
+    if (slots.size() != ranks.size() || channel >= kSubChannels || ranks.size() < 2) return std::make_shared<SubTransport>(this, ranks, idx);
+    auto sub = std::make_shared<ShmSubTransport>(this, ranks, idx, seg_, channel, slots);
+    if (data_) sub->CreateDataPlane(name_ + "-c" + std::to_string(channel) + "-d");
+    return sub;
+  }
+  void set_name(const std::string& n) { name_ = n; }
   void LocalBarrier() override {
     const uint64_t k = ++local_round_;
     SubSlot* row = seg_->sub[0];
@@ -618,6 +642,8 @@ class HierShmControlTransport : public Transport {
   uint64_t piece_ = 0, local_round_ = 0;
   std::vector<std::vector<int>> column_;
   std::shared_ptr<Transport> cross_;
+  int next_channel_ = 1;       // row 0 of the segment's sub-slots carries LocalBarrier()
+  std::string name_;
 };
 
 }  // namespace
@@ -677,6 +703,7 @@ std::shared_ptr<Transport> WrapWithHierarchicalControl(std::shared_ptr<Transport
   }
   auto raw = base;
   auto hier = std::make_shared<HierShmControlTransport>(std::move(base), seg, std::move(local), li, std::move(leaders));
+  hier->set_name(name);
   hier->Barrier();                       // every rank of this host has published its pid
   VerifyPeerPids(seg, nlocal, li);
 

@@ -90,6 +90,28 @@ def _():
     info = hvd.control_plane_info()
     if os.environ.get('HVD_CONTROL_PLANE') != 'tcp' and L > 1:
         assert 'two-level' in info and '%d ranks of this host' % L in info and '%d host leaders' % FAKE_HOSTS in info, info
+    # a process set made of the ranks of ONE host negotiates and moves host tensors through that host's shared memory (own
+    # channel + data slots); a set that spans hosts stays on the sockets
+    if os.environ.get('HVD_CONTROL_PLANE') != 'tcp' and L > 1 and args.device == 'cpu':
+        host_sets = [hvd.add_process_set(list(range(h * L, (h + 1) * L))) for h in range(FAKE_HOSTS)]
+        spanning = hvd.add_process_set(list(range(0, size, L)))                # the first rank of every host
+        mine = host_sets[rank // L]
+        assert 'shared memory channel' in hvd.control_plane_info(mine), hvd.control_plane_info(mine)
+        for step in range(3):                                                   # uncached, then cached
+            out = hvd.allreduce(torch.full([1000], float(rank + 1)), op=hvd.Sum, name='hostset.ar', process_set=mine)
+            assert float(out[0]) == float(sum(r + 1 for r in range((rank // L) * L, (rank // L + 1) * L))), out[:3]
+        big = hvd.allreduce(torch.arange(300000, dtype=torch.float32) % 7 + rank, op=hvd.Sum, name='hostset.big', process_set=mine)
+        members = list(range((rank // L) * L, (rank // L + 1) * L))
+        assert torch.equal(big, (torch.arange(300000, dtype=torch.float32) % 7) * L + float(sum(members)))
+        g = hvd.allgather(torch.full([rank % L + 1, 2], float(rank)), name='hostset.ag', process_set=mine)
+        assert g.shape[0] == sum(range(1, L + 1)) and float(g[0, 0]) == float(members[0])
+        if spanning.included():
+            assert 'shared memory channel' not in hvd.control_plane_info(spanning)
+            s2 = hvd.allreduce(torch.ones(5), op=hvd.Sum, name='spanning.ar', process_set=spanning)
+            assert float(s2[0]) == float(FAKE_HOSTS)
+        hvd.barrier()
+        for ps in host_sets + [spanning]:
+            hvd.remove_process_set(ps)
 
 
 @check('hierarchical_allreduce')
