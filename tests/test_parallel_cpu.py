@@ -83,6 +83,15 @@ def test_recursive_doubling_bit_reduction(native_built, np_, env):
     assert "ALL OK" in out, out[-3000:]
 
 
+def test_fake_three_hosts_np6(native_built):
+    """6 ranks presented as 3 hosts x 2: two-level planes with an odd number of hosts (leader star of three, cross-host rings
+    of three, chain broadcast over three column ranks), host-local process sets on every host, every host collective."""
+    rc, out = run_parallel("ops_worker.py", np=6, timeout=400, env={"HVD_TEST_FAKE_HOSTS": "3"},
+                           args=["--only", "rank_size,fake_hosts_topology,allreduce_sum_avg,allreduce_async_fused,allgather,broadcast,"
+                                 "alltoall,reducescatter,process_sets,barrier_join,large_allreduce"])
+    assert "ALL OK" in out, out[-3000:]
+
+
 def test_numpy_frontend_np2(native_built):
     rc, out = run_parallel("numpy_worker.py", np=2, timeout=200)
     assert "NUMPY OK" in out, out[-3000:]
