@@ -3,6 +3,7 @@
 #include <unistd.h>
 #include <sstream>
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include "../common/env.h"
 #include "../common/logging.h"
@@ -224,6 +225,16 @@ std::shared_ptr<SymmTeam> GpuOps::EnsureTeam(ProcessSet& ps, int device) {
   if (ps.team_tried) {
     if (ps.team && ps.team->abort_state() == 2)
       throw TransportError("a peer GPU did not reach the collective's flag barrier within HVD_KERNEL_TIMEOUT_SECONDS");
+    // one symmetric team per process set, on the device of the set's first GPU collective.  A tensor that lives on ANOTHER
+    // device of this process (a model split over two GPUs, reference test_model_parallelism) cannot use it: that response is
+    // staged through the host instead (every rank of a symmetric program takes the same branch).
+    if (ps.team && ps.team->device() != device) {
+      static std::atomic<bool> warned{false};
+      if (!warned.exchange(true))
+        LOG(WARNING) << "a GPU tensor on device " << device << " meets the process set's peer-mapped team on device " << ps.team->device()
+                     << ": its collectives are staged through host memory (one process per GPU is the fast path)";
+      return nullptr;
+    }
     return ps.team;
   }
   ps.team_tried = true;

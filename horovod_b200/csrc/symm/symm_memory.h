@@ -52,6 +52,7 @@ class SymmTeam {
   ~SymmTeam();
 
   int nranks() const { return nranks_; }
+  int device() const { return device_; }            // the CUDA device this rank's buffers live on
   int rank() const { return rank_; }
   // bytes of one buffer slot available to ordinary ops; the reserved tail [buffer_bytes(), buffer_bytes() + reserved_tail())
   // belongs to the latency lane
